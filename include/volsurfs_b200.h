@@ -1,0 +1,125 @@
+/* volsurfs_b200 — C ABI of the B200-native per-ray rendering hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every pointer is a DEVICE pointer on the
+ * current CUDA device unless stated otherwise; `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream).  Calls only enqueue work: they never synchronise the device, never allocate device memory (callers pass
+ * outputs and scratch) and never abort the process.
+ *
+ * Return value: 0 = ok, >0 = cudaError_t of the launch, <0 = argument error
+ *   VS_ERR_INVALID_ARG (-1), VS_ERR_UNSUPPORTED (-2), VS_ERR_ALLOC (-3).
+ * (The reference instead CHECK()-aborts on bad arguments and prints-and-ignores CUDA errors,
+ *  src/VolumeRendering.cu:35,66-71.)
+ *
+ * Tensor conventions (identical to the reference's pybind surface, src/PyBridge.cxx:70-129):
+ *   ray_start_end_idx  int32 [n_rays,2]  (start,end) into the packed sample arrays; empty rays are (-1,-1)
+ *   per-sample arrays  float32 [n_samples,d] row-major contiguous
+ *   per-ray arrays     float32 [n_rays,d]
+ */
+#ifndef VOLSURFS_B200_H
+#define VOLSURFS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_OK 0
+#define VS_ERR_INVALID_ARG (-1)
+#define VS_ERR_UNSUPPORTED (-2)
+#define VS_ERR_ALLOC (-3)
+
+/* ---- library info ------------------------------------------------------------------------------------------------ */
+int vs_abi_version(void);
+/* static string for a return code of this ABI (host pointer, never NULL) */
+const char* vs_error_string(int code);
+/* number of CUDA kernels this library has enqueued since it was loaded (process-wide, monotonic) */
+long long vs_launch_count(void);
+
+/* ---- packed VolumeRendering operators (op-by-op, reference semantics incl. quirks) -------------------------------- */
+
+/* replaces VolumeRendering::cumprod_one_minus_alpha_to_transmittance, src/VolumeRendering.cu:30-78
+ * (kernel kernels/volsurfs/VolumeRenderingGPU.cuh:28-78).  T_i = prod_{j<i} x_j ; bgT = T_{s-1} (last x not applied);
+ * bgT = 1 for empty rays.  T must be zero-filled by the caller if the layout has unowned slots. */
+int vs_cumprod_fwd(const int32_t* ray_start_end_idx, const float* x, float* T, float* bgT, int64_t n_rays, int64_t n_samples,
+                   void* stream);
+
+/* replaces VolumeRendering::cumprod_one_minus_alpha_to_transmittance_backward, src/VolumeRendering.cu:671-718
+ * (kernel VolumeRenderingGPU.cuh:896-943): dx_i = cumsumLV_{i+1}/max(x_i,1e-6) + g_bgT*bgT/max(x_i,1e-6), dx_{s-1}=0 */
+int vs_cumprod_bwd(const int32_t* ray_start_end_idx, const float* grad_bgT, const float* x, const float* bgT, const float* cumsumLV,
+                   float* dx, int64_t n_rays, int64_t n_samples, void* stream);
+
+/* the python half (volume_rendering_funcs.py:105-179: LV = gT*T, reverse cumsum) fused with the kernel above */
+int vs_cumprod_bwd_fused(const int32_t* ray_start_end_idx, const float* grad_T, const float* grad_bgT, const float* x, const float* T,
+                         const float* bgT, float* dx, int64_t n_rays, int64_t n_samples, void* stream);
+
+/* replaces VolumeRendering::cumsum_over_rays, src/VolumeRendering.cu:326-370 (kernel :305-361) */
+int vs_cumsum(const int32_t* ray_start_end_idx, const float* values, float* out, int inverse, int64_t n_rays, int64_t n_samples,
+              void* stream);
+
+/* replaces VolumeRendering::integrate_with_weights_{1d,3d}, src/VolumeRendering.cu:80-176 (kernels :80-177); dim in {1,3} */
+int vs_integrate_fwd(const int32_t* ray_start_end_idx, const float* values, const float* weights, float* out, int dim, int64_t n_rays,
+                     int64_t n_samples, void* stream);
+
+/* replaces VolumeRendering::integrate_with_weights_{1d,3d}_backward, src/VolumeRendering.cu:720-818 (kernels :945-1033).
+ * ref_bug != 0 reproduces the reference's 3-D kernel reading values[.][1] for the z channel (:1021). */
+int vs_integrate_bwd(const int32_t* ray_start_end_idx, const float* grad_out, const float* values, const float* weights,
+                     float* d_values, float* d_weights, int dim, int64_t n_rays, int64_t n_samples, int ref_bug, void* stream);
+
+/* replaces VolumeRendering::sum_over_rays, src/VolumeRendering.cu:231-324 (kernel :245-303); dim in {1,2,3,32};
+ * sum_sample may be NULL */
+int vs_sum_fwd(const int32_t* ray_start_end_idx, const float* values, float* sum_ray, float* sum_sample, int dim, int64_t n_rays,
+               int64_t n_samples, void* stream);
+
+/* replaces VolumeRendering::sum_over_rays_backward, src/VolumeRendering.cu:820-899 (kernel :1035-1079); dim in {1,2,3} */
+int vs_sum_bwd(const int32_t* ray_start_end_idx, const float* grad_sum_ray, const float* grad_sum_sample, float* d_values, int dim,
+               int64_t n_rays, int64_t n_samples, void* stream);
+
+/* replaces RaySamplesPacked::update_dt, src/RaySamplesPacked.cu:396-461 (kernel RaySamplesPackedGPU.cuh:14-88) */
+int vs_update_dt(const int32_t* ray_start_end_idx, const float* samples_z, const float* ray_exit, const float* ray_max_dt,
+                 float* samples_dt, int is_background, int64_t n_rays, int64_t n_samples, void* stream);
+
+/* ---- fused compositing (one launch per direction) ------------------------------------------------------------------
+ * Replaces the chain cumprod -> alpha*T -> sum_over_rays -> integrate_3d -> integrate_1d of nerf.py:308-334 and equals
+ * the dense K-layer torch path volsurfs_py/methods/volsurfs.py:601-640,708.  bgT is the FULL product of (1-alpha).
+ * out_w / out_T (per-sample weights and transmittance) may be NULL.  d_z may be NULL.
+ * mode: 0 auto, 1 force tile kernels, 2 force scan kernels, 3 scan kernels with 8-lane groups (for A/B measurements). */
+int vs_composite_fwd(const int32_t* ray_start_end_idx, const float* alpha, const float* rgb, const float* z, float* out_rgb,
+                     float* out_depth, float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples,
+                     int mode, void* stream);
+int vs_composite_bwd(const int32_t* ray_start_end_idx, const float* alpha, const float* rgb, const float* z, const float* g_rgb,
+                     const float* g_depth, const float* g_acc, const float* g_bgT, float* d_alpha, float* d_rgb, float* d_z,
+                     int64_t n_rays, int64_t n_samples, int mode, void* stream);
+
+/* ---- packing ------------------------------------------------------------------------------------------------------- */
+/* bytes of device scratch needed by the packing entry points for n_rays rays */
+int64_t vs_pack_scratch_bytes(int64_t n_rays);
+
+/* sum of (end-start) over all rays into *total_dev (device int64); replaces RaySamplesPacked::get_total_nr_samples,
+ * src/RaySamplesPacked.cu:170-175 (which syncs through .item()) */
+int vs_count_total(const int32_t* ray_start_end_idx, int64_t n_rays, int64_t* total_dev, void* stream);
+
+/* replaces RaySamplesPacked::compact_to_valid_samples, src/RaySamplesPacked.cu:188-273
+ * (kernel kernels/volsurfs/RaySamplesPackedGPU.cuh:172-257), in two phases so the caller can size the outputs:
+ *   1. vs_compact_offsets: exclusive scan of the per-ray counts into `scratch`, total into *total_dev
+ *   2. vs_compact_gather: copies every ray's segment to its offset; empty rays get (-1,-1) */
+int vs_compact_offsets(const int32_t* se_in, int64_t n_rays, int64_t* total_dev, void* scratch, void* stream);
+int vs_compact_gather(const int32_t* se_in, const void* scratch, const int32_t* samples_idx_in, const float* samples_3d_in,
+                      const float* samples_dirs_in, const float* samples_z_in, const float* samples_dt_in, const float* values_in,
+                      int values_dim, int32_t* se_out, int32_t* samples_idx_out, float* samples_3d_out, float* samples_dirs_out,
+                      float* samples_z_out, float* samples_dt_out, float* values_out, int64_t n_rays, int64_t n_samples_out,
+                      void* stream);
+
+/* K-layer hit bookkeeping of volsurfs_py/methods/volsurfs.py:476-518,601-603 written straight into packed form.
+ * depth/tri/bary are layer-major [K,n_rays] (mesh 0 = innermost); a layer is hit iff depth <= t_far
+ * (raytracelib/raytracer.py:100).  Packed order per ray: descending mesh index (outer -> inner). */
+int vs_pack_hits_offsets(const float* depth, int K, float t_far, int64_t n_rays, int64_t* total_dev, void* scratch, void* stream);
+int vs_pack_hits_scatter(const float* rays_o, const float* rays_d, const float* depth, const int32_t* tri, const float* bary_u,
+                         const float* bary_v, const void* scratch, int K, float t_far, int32_t* se_out, int32_t* samples_idx_out,
+                         float* samples_3d_out, float* samples_dirs_out, float* samples_z_out, int32_t* layer_out, int32_t* tri_out,
+                         float* uv_out, int64_t n_rays, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLSURFS_B200_H */

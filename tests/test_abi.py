@@ -1,0 +1,89 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol that
+include/volsurfs_b200.h declares; the ctypes prototypes cover the same set; the python shim exposes the reference's
+pybind surface (src/PyBridge.cxx:70-129)."""
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+# method names bound by the reference for the two hot-path classes (src/PyBridge.cxx:70-129)
+RSP_METHODS = """compact_to_valid_samples get_nr_rays get_ray_max_dt get_samples_values get_ray_samples_idx get_ray_samples_3d
+get_ray_samples_dirs get_ray_samples_z get_ray_samples_dt get_ray_samples_values get_ray_start_end_idx get_ray_o get_ray_d
+get_ray_enter get_ray_exit is_empty copy get_values_dim get_max_nr_samples get_nr_samples_per_ray get_total_nr_samples
+set_samples_values remove_samples_values are_samples_values_set update_dt""".split()
+RSP_ATTRS = "samples_idx samples_3d samples_dirs samples_z samples_dt samples_values ray_o ray_d ray_enter ray_exit ray_start_end_idx".split()
+VR_HOT = """cumprod_one_minus_alpha_to_transmittance integrate_with_weights_1d integrate_with_weights_3d sum_over_rays
+cumsum_over_rays cumprod_one_minus_alpha_to_transmittance_backward integrate_with_weights_1d_backward
+integrate_with_weights_3d_backward sum_over_rays_backward""".split()
+
+
+def header_symbols():
+    text = (ROOT / "include" / "volsurfs_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/volsurfs_b200.h but not exported"
+
+
+def test_ctypes_prototypes_cover_header():
+    from volsurfs_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+
+
+def test_abi_version_and_error_strings(lib):
+    assert lib.vs_abi_version() == 1
+    assert b"invalid argument" in lib.vs_error_string(-1)
+    assert lib.vs_error_string(0) == b"ok"
+    assert lib.vs_pack_scratch_bytes(0) > 0
+
+
+def test_shim_exposes_pybridge_surface():
+    from volsurfs_b200.volsurfs import RaySamplesPacked, VolumeRendering
+
+    for m in RSP_METHODS:
+        assert callable(getattr(RaySamplesPacked, m)), m
+    for m in VR_HOT:
+        assert callable(getattr(VolumeRendering, m)), m
+
+
+def test_pybridge_list_matches_reference_if_mounted():
+    src = Path("/root/reference/src/PyBridge.cxx")
+    if not src.exists():
+        pytest.skip("reference not mounted")
+    text = src.read_text()
+    block = text[text.index('py::class_<RaySamplesPacked>'):text.index('py::class_<VolumeRendering>')]
+    block = "\n".join(ln for ln in block.splitlines() if not ln.strip().startswith("//"))
+    assert sorted(set(re.findall(r'\.def\("(\w+)"', block))) == sorted(set(RSP_METHODS))
+    assert sorted(set(re.findall(r'\.def_readwrite\("(\w+)"', block))) == sorted(RSP_ATTRS)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from volsurfs_b200 import _lib
+    from volsurfs_b200.volsurfs import RaySamplesPacked
+
+    with pytest.raises(_lib.VolsurfsB200Error):
+        RaySamplesPacked(4, 16, 0, 1)
+
+
+def test_install_as_volsurfs():
+    import sys
+
+    import volsurfs_b200
+
+    volsurfs_b200.install_as_volsurfs()
+    import volsurfs  # noqa: F401
+
+    assert sys.modules["volsurfs"].VolumeRendering is volsurfs_b200.volsurfs.VolumeRendering
+    del sys.modules["volsurfs"]

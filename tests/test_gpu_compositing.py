@@ -1,0 +1,195 @@
+"""GPU parity of the fused compositor (C ABI vs_composite_fwd/bwd through the python shim) against the oracle.
+Tolerance: 1e-5 relative (BASELINE.json north_star), rel = |a-b| / max(|b|, floor)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import compositing as oc
+from volsurfs_b200.synthetic import all_hit_packed, composite_bytes, dense_layers, nerf_packets, pack_dense
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _rsp(se):
+    from volsurfs_b200.volsurfs import RaySamplesPacked
+
+    rsp = RaySamplesPacked(0, 0, 0, 1)
+    rsp.ray_start_end_idx = se.cuda()
+    return rsp
+
+
+def _run(se, alpha, rgb, z, grads, mode, need_dz=True):
+    from volsurfs_b200.volsurfs import VolumeRendering as VR
+
+    rsp = _rsp(se)
+    a, c, zz = alpha.cuda(), rgb.cuda(), z.cuda()
+    fwd = VR.composite(rsp, a, c, zz, return_weights=True, mode=mode)
+    bwd = VR.composite_backward(rsp, a, c, zz, grads["g_rgb"].cuda(), grads["g_depth"].cuda(), grads["g_acc"].cuda(),
+                                grads["g_bgT"].cuda(), need_dz=need_dz, mode=mode)
+    torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in fwd], [None if t is None else t.cpu().numpy() for t in bwd]
+
+
+def _check(se, alpha, rgb, z, grads, mode):
+    fwd, bwd = _run(se, alpha, rgb, z, grads, mode)
+    sen = se.numpy()
+    o = oc.fused_composite_forward(sen, alpha.numpy(), rgb.numpy(), z.numpy(), dtype=np.float64)
+    for got, key in zip(fwd, ("rgb", "depth", "acc", "bgT", "weights", "transmittance")):
+        assert rel_err(got, o[key], floor=1e-6) < TOL, key
+    ob = oc.fused_composite_backward(sen, alpha.numpy(), rgb.numpy(), z.numpy(), grads["g_rgb"].numpy(), grads["g_depth"].numpy(),
+                                     grads["g_acc"].numpy(), grads["g_bgT"].numpy())
+    # gradients are sums of terms of mixed sign: compare against the magnitude scale of the terms (floor 1e-3*|g|max)
+    for got, key in zip(bwd, ("d_alpha", "d_rgb", "d_z")):
+        assert rel_err(got, ob[key], floor=1e-2) < TOL, key
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_c1_shells_vs_oracle(mode):
+    """BASELINE config 1: 4096 rays x 5 layers, Bernoulli(0.8) hits, exact 0/1 alphas, empty rays."""
+    d = dense_layers(4096, 5, seed_offset=1)
+    se, a, c, z = pack_dense(d["hit"], d["alpha"], d["rgb"], d["z"])
+    assert (se[:, 0] == -1).any(), "config must contain empty rays"
+    _check(se, a, c, z, d, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_golden_reference_lines(mode):
+    """CUDA result vs the vectors produced by the reference's own dense torch lines (fp32 variant)."""
+    from volsurfs_b200.volsurfs import VolumeRendering as VR
+
+    for name in ("dense_composite_k5", "dense_composite_k1", "dense_composite_k9"):
+        g = np.load(GOLDEN / f"{name}.npz")
+        hit = torch.from_numpy(g["hit"])
+        se, a, c, z = pack_dense(hit, torch.from_numpy(g["alpha"]), torch.from_numpy(g["rgb"]), torch.from_numpy(g["z"]))
+        N = hit.shape[0]
+        grads = {"g_rgb": torch.from_numpy(g["g_rgb"]), "g_depth": torch.zeros(N, 1), "g_acc": torch.zeros(N, 1),
+                 "g_bgT": torch.from_numpy(g["g_bgT"])}
+        fwd, bwd = _run(se, a, c, z, grads, mode, need_dz=False)
+        assert rel_err(fwd[0], g["fp32_rgb_fg"]) < TOL
+        assert rel_err(fwd[3], g["fp32_bg_transmittance"]) < TOL
+        ray, j = np.nonzero(g["hit"][:, ::-1])
+        lay = hit.shape[1] - 1 - j
+        assert rel_err(fwd[4][:, 0], g["fp32_weights"][ray, lay, 0]) < TOL
+        assert rel_err(bwd[0][:, 0], g["fp32_d_alpha"][ray, lay, 0], floor=1e-2) < TOL
+        assert rel_err(bwd[1], g["fp32_d_rgb"][ray, lay], floor=1e-2) < TOL
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_c3_nerf_packets_vs_oracle(mode):
+    """Variable-length packets up to 1024 samples/ray with 35 % empty rays (config 3 shape, 6k-ray subset)."""
+    p = nerf_packets(6000, seed_offset=3)
+    assert int(p["counts"].max()) == 1024 and int((p["counts"] == 0).sum()) > 1000
+    _check(p["se"], p["alpha"], p["rgb"], p["z"], p, mode)
+
+
+def test_long_rays_spill_path():
+    """rays longer than W*W = 1024 samples exercise the scratch path of the backward scan kernel"""
+    p = nerf_packets(40, seed_offset=4, max_per_ray=3000, mean=1500.0, sigma=0.4, p_empty=0.1)
+    assert int(p["counts"].max()) > 1024
+    _check(p["se"], p["alpha"], p["rgb"], p["z"], p, 2)
+
+
+@pytest.mark.parametrize("n_rays,K", [(1, 5), (255, 5), (257, 9), (1000, 1)])
+def test_edge_sizes(n_rays, K):
+    d = all_hit_packed(n_rays, K)
+    for mode in (1, 2):
+        _check(d["se"], d["alpha"], d["rgb"], d["z"], d, mode)
+
+
+def test_all_empty_and_zero_rays():
+    from volsurfs_b200.volsurfs import VolumeRendering as VR
+
+    se = torch.full((300, 2), -1, dtype=torch.int32)
+    e1, e3 = torch.zeros(0, 1), torch.zeros(0, 3)
+    for mode in (0, 1, 2):
+        rgb, depth, acc, bgT = VR.composite(_rsp(se), e1.cuda(), e3.cuda(), e1.cuda(), mode=mode)
+        assert torch.all(rgb == 0) and torch.all(depth == 0) and torch.all(acc == 0) and torch.all(bgT == 1)
+    rgb, depth, acc, bgT = VR.composite(_rsp(torch.zeros((0, 2), dtype=torch.int32)), e1.cuda(), e3.cuda(), e1.cuda())
+    assert rgb.shape == (0, 3) and bgT.shape == (0, 1)
+
+
+def test_tile_fallback_on_skewed_and_gapped_layouts():
+    """tile kernels must fall back per tile when a tile's sample range exceeds the shared-memory capacity
+    (skewed counts) or is not contiguous (uncompacted slot layout with gaps)."""
+    g = torch.Generator().manual_seed(5)
+    n = 2048
+    cnt = torch.ones(n, dtype=torch.int64)
+    cnt[100:140] = 300  # one heavy tile, mean stays < 8
+    start = torch.cumsum(cnt, 0) - cnt
+    se = torch.stack([start, start + cnt], 1).to(torch.int32)
+    S = int(cnt.sum())
+    d = {"alpha": torch.rand(S, 1, generator=g), "rgb": torch.rand(S, 3, generator=g), "z": torch.rand(S, 1, generator=g),
+         "g_rgb": torch.randn(n, 3, generator=g), "g_depth": torch.randn(n, 1, generator=g), "g_acc": torch.randn(n, 1, generator=g),
+         "g_bgT": torch.randn(n, 1, generator=g)}
+    _check(se, d["alpha"], d["rgb"], d["z"], d, 1)
+    # gapped: ray r owns slots [r*6, r*6+cnt_r), cnt_r in 0..6
+    cnt = torch.randint(0, 7, (n,), generator=g)
+    start = torch.arange(n) * 6
+    se = torch.stack([start, start + cnt], 1).to(torch.int32)
+    se[cnt == 0] = -1
+    S = n * 6
+    d.update(alpha=torch.rand(S, 1, generator=g), rgb=torch.rand(S, 3, generator=g), z=torch.rand(S, 1, generator=g))
+    fwd, bwd = _run(se, d["alpha"], d["rgb"], d["z"], d, 1, need_dz=False)
+    o = oc.fused_composite_forward(se.numpy(), d["alpha"].numpy(), d["rgb"].numpy(), d["z"].numpy(), dtype=np.float64)
+    assert rel_err(fwd[0], o["rgb"]) < TOL and rel_err(fwd[3], o["bgT"]) < TOL
+    ob = oc.fused_composite_backward(se.numpy(), d["alpha"].numpy(), d["rgb"].numpy(), d["z"].numpy(), d["g_rgb"].numpy(),
+                                     d["g_depth"].numpy(), d["g_acc"].numpy(), d["g_bgT"].numpy())
+    own = np.zeros(S, bool)
+    for s, e in se.numpy():
+        if e > s:
+            own[s:e] = True
+    assert rel_err(bwd[0][own], ob["d_alpha"][own], floor=1e-2) < TOL
+
+
+def test_autograd_function_matches_dense_torch():
+    """CompositeFunc (fused kernels under autograd) vs the dense torch path differentiated by autograd on the CPU."""
+    from volsurfs_b200.volume_rendering import composite
+
+    d = dense_layers(3000, 5, seed_offset=21)
+    se, a, c, z = pack_dense(d["hit"], d["alpha"], d["rgb"], d["z"])
+    a_g = a.cuda().requires_grad_(True)
+    c_g = c.cuda().requires_grad_(True)
+    rgb, depth, acc, bgT = composite(_rsp(se), a_g, c_g, z.cuda())
+    loss = (rgb * d["g_rgb"].cuda()).sum() + (bgT * d["g_bgT"].cuda()).sum() + (depth * d["g_depth"].cuda()).sum()
+    loss.backward()
+    ad = d["alpha"].clone().requires_grad_(True)
+    cd = d["rgb"].clone().requires_grad_(True)
+    out = oc.dense_composite_torch(ad, cd, surfs_z=d["z"])
+    lo = (out["rgb_fg"] * d["g_rgb"]).sum() + (out["bg_transmittance"] * d["g_bgT"]).sum() + (out["depth"] * d["g_depth"]).sum()
+    lo.backward()
+    hit = d["hit"].numpy()
+    ray, j = np.nonzero(hit[:, ::-1])
+    lay = hit.shape[1] - 1 - j
+    assert rel_err(rgb.detach().cpu().numpy(), out["rgb_fg"].detach().numpy()) < TOL
+    assert rel_err(bgT.detach().cpu().numpy(), out["bg_transmittance"].detach().numpy()) < TOL
+    assert rel_err(a_g.grad.cpu().numpy()[:, 0], ad.grad.numpy()[ray, lay, 0], floor=1e-2) < TOL
+    assert rel_err(c_g.grad.cpu().numpy(), cd.grad.numpy()[ray, lay], floor=1e-2) < TOL
+
+
+def test_full_size_properties():
+    """BASELINE-size run (2^22 rays x 5, all hit): size-independent properties instead of an oracle pass —
+    acc + bgT == 1, 0 <= bgT <= 1, d_rgb == g_rgb * w, and linearity of the forward in rgb."""
+    from volsurfs_b200.volsurfs import VolumeRendering as VR
+
+    n, K = 1 << 22, 5
+    d = all_hit_packed(n, K, seed_offset=31)
+    rsp = _rsp(d["se"])
+    a, c, z = d["alpha"].cuda(), d["rgb"].cuda(), d["z"].cuda()
+    rgb, depth, acc, bgT, w, T = VR.composite(rsp, a, c, z, return_weights=True)
+    assert torch.allclose(acc + bgT, torch.ones_like(acc), atol=3e-6)
+    assert bool((bgT >= 0).all()) and bool((bgT <= 1).all())
+    rgb2, *_ = VR.composite(rsp, a, 2 * c, z)
+    assert torch.allclose(rgb2, 2 * rgb, rtol=1e-6, atol=1e-7)
+    g = {k: d[k].cuda() for k in ("g_rgb", "g_depth", "g_acc", "g_bgT")}
+    d_alpha, d_rgb, _ = VR.composite_backward(rsp, a, c, z, g["g_rgb"], g["g_depth"], g["g_acc"], g["g_bgT"])
+    ray_of = torch.arange(n, device="cuda").repeat_interleave(K)
+    assert torch.allclose(d_rgb, g["g_rgb"][ray_of] * w, rtol=1e-6, atol=1e-7)
+    # spot-check 4096 rays against the oracle
+    sub = slice(0, 4096 * K)
+    o = oc.fused_composite_backward(d["se"][:4096].numpy(), d["alpha"][sub].numpy(), d["rgb"][sub].numpy(), d["z"][sub].numpy(),
+                                    d["g_rgb"][:4096].numpy(), d["g_depth"][:4096].numpy(), d["g_acc"][:4096].numpy(),
+                                    d["g_bgT"][:4096].numpy())
+    assert rel_err(d_alpha[sub].cpu().numpy(), o["d_alpha"], floor=1e-2) < TOL
+    assert composite_bytes(n, n * K) == n * 344

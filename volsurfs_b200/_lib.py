@@ -1,0 +1,81 @@
+"""ctypes binding of ``libvolsurfs_b200.so`` (C ABI declared in ``include/volsurfs_b200.h``).
+
+There is no CPU fallback: if the shared object is missing or a symbol cannot be resolved the import of the
+operators fails loudly.  ``lib()`` only *loads* the library (possible without a GPU); calling a kernel
+entry point needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libvolsurfs_b200.so"
+
+_P = c_void_p  # every device pointer
+_I64 = c_int64
+
+# name -> (restype, argtypes).  Kept in the order of include/volsurfs_b200.h.
+SIGNATURES = {
+    "vs_abi_version": (c_int, []),
+    "vs_error_string": (c_char_p, [c_int]),
+    "vs_launch_count": (ctypes.c_longlong, []),
+    "vs_cumprod_fwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
+    "vs_cumprod_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "vs_cumprod_bwd_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "vs_cumsum": (c_int, [_P, _P, _P, c_int, _I64, _I64, _P]),
+    "vs_integrate_fwd": (c_int, [_P, _P, _P, _P, c_int, _I64, _I64, _P]),
+    "vs_integrate_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int, _P]),
+    "vs_sum_fwd": (c_int, [_P, _P, _P, _P, c_int, _I64, _I64, _P]),
+    "vs_sum_bwd": (c_int, [_P, _P, _P, _P, c_int, _I64, _I64, _P]),
+    "vs_update_dt": (c_int, [_P, _P, _P, _P, _P, c_int, _I64, _I64, _P]),
+    "vs_composite_fwd": (c_int, [_P] * 10 + [_I64, _I64, c_int, _P]),
+    "vs_composite_bwd": (c_int, [_P] * 11 + [_I64, _I64, c_int, _P]),
+    "vs_pack_scratch_bytes": (_I64, [_I64]),
+    "vs_count_total": (c_int, [_P, _I64, _P, _P]),
+    "vs_compact_offsets": (c_int, [_P, _I64, _P, _P, _P]),
+    "vs_compact_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "vs_pack_hits_offsets": (c_int, [_P, c_int, c_float, _I64, _P, _P, _P]),
+    "vs_pack_hits_scatter": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_float] + [_P] * 8 + [_I64, _P]),
+}
+
+_lib = None
+
+
+class VolsurfsB200Error(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared object once and attach the prototypes. Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VolsurfsB200Error(
+            f"{LIB_PATH} not found: build it with `python -m volsurfs_b200.build` "
+            "(there is no CPU or PyTorch fallback for the volsurfs_b200 operators)"
+        )
+    handle = ctypes.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as exc:  # pragma: no cover - build/ABI mismatch
+            raise VolsurfsB200Error(f"{LIB_PATH} does not export {name}; rebuild the extension") from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    """Raise on a non-zero return code of the C ABI."""
+    if code != 0:
+        msg = lib().vs_error_string(int(code))
+        raise VolsurfsB200Error(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

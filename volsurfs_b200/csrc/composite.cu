@@ -1,0 +1,514 @@
+// volsurfs_b200 — fused alpha compositing over packed samples, forward and backward.
+//
+// One launch per direction replaces the reference's chain
+//   cumprod -> (alpha*T) -> sum_over_rays -> integrate_3d -> integrate_1d      (fwd, nerf.py:308-334)
+//   + the 5 backward kernels + torch glue                                       (bwd, volume_rendering_funcs.py:105-272)
+// and equals the dense K-layer torch path of the volsurfs method (volsurfs.py:601-640,708) when each ray's
+// samples are its layer hits in outer->inner order.
+//
+//   T_i = prod_{j<i}(1-a_j)   w_i = T_i a_i
+//   rgb = sum w c   depth = sum w z   acc = sum w   bgT = prod_all(1-a_j)       (full product, dense-path semantics)
+//
+// backward (nothing saved by the forward; T is recomputed, division free):
+//   g_i = g_rgb.c_i + g_depth z_i + g_acc
+//   R_{s-1} = g_bgT ,  R_{i-1} = a_i g_i + (1-a_i) R_i          (reverse scan of affine maps)
+//   d_alpha_i = T_i (g_i - R_i) ,  d_rgb_i = g_rgb w_i
+//
+// Algorithmic HBM bytes per ray with s samples: fwd 8+20s read, 24 written; bwd 8+24+20s read, 16s written:
+// B(s) = 64 + 56 s   (SURVEY.md section 8d).
+//
+// Two kernel families, chosen on the host from the mean segment length S/N:
+//   * "tile" (mean <= 8, the K-layer shells case): a CTA owns 256 consecutive rays, stages their contiguous sample
+//     range into shared memory with 16-byte coalesced loads, each thread then walks its own ray out of shared
+//     memory (segments of ~5 samples are too short for lanes to share), per-sample gradients go back through shared
+//     memory as coalesced 16-byte stores.
+//   * "scan" (longer rays, NeRF-style packets): a group of W lanes per ray (W = 16/32), W-wide chunks read straight
+//     from global memory (contiguous per chunk), shuffle-based exclusive cumprod forward, shuffle-based reverse affine
+//     scan backward, running values carried between chunks.
+#include "vs_common.cuh"
+
+namespace vs {
+
+constexpr int kScanThreads = 256;
+constexpr int kTileRays = 256;  // rays per CTA == threads per CTA in the tile kernels
+
+// =============================================================================================
+// scan family
+// =============================================================================================
+template <int W>
+__global__ void __launch_bounds__(kScanThreads) composite_fwd_scan_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
+    float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays) {
+    const int gl = threadIdx.x & (W - 1);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / W;
+    int start = 0, n = 0;
+    if (ray < n_rays) n = load_segment(se, ray, start);
+    const int n_max = warp_max_i32(n);
+
+    float carry = 1.f;
+    float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+    for (int base = 0; base < n_max; base += W) {
+        const int i = base + gl;
+        const bool valid = i < n;
+        const int64_t s = (int64_t)start + i;
+        float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, zz = 0.f;
+        if (valid) {
+            a = ld_stream(alpha + s);
+            cr = ld_stream(rgb + 3 * s);
+            cg = ld_stream(rgb + 3 * s + 1);
+            cb = ld_stream(rgb + 3 * s + 2);
+            zz = ld_stream(z + s);
+        }
+        float incl = group_scan_mul<W>(1.f - a, gl);
+        float Ti = carry * group_shift_up<W>(incl, gl, 1.f);
+        float w = Ti * a;
+        ar = fmaf(w, cr, ar);
+        ag = fmaf(w, cg, ag);
+        ab = fmaf(w, cb, ab);
+        ad = fmaf(w, zz, ad);
+        aa += w;
+        if (valid) {
+            if (out_w) st_stream(out_w + s, w);
+            if (out_T) st_stream(out_T + s, Ti);
+        }
+        carry *= group_bcast<W>(incl, W - 1);
+    }
+    ar = group_reduce_add<W>(ar);
+    ag = group_reduce_add<W>(ag);
+    ab = group_reduce_add<W>(ab);
+    ad = group_reduce_add<W>(ad);
+    aa = group_reduce_add<W>(aa);
+    if (ray < n_rays && gl == 0) {
+        out_rgb[3 * ray] = ar;
+        out_rgb[3 * ray + 1] = ag;
+        out_rgb[3 * ray + 2] = ab;
+        out_depth[ray] = ad;
+        out_acc[ray] = aa;
+        out_bgT[ray] = carry;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kScanThreads) composite_bwd_scan_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
+    float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays) {
+    const int gl = threadIdx.x & (W - 1);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / W;
+    int start = 0, n = 0;
+    if (ray < n_rays) n = load_segment(se, ray, start);
+    const int n_max = warp_max_i32(n);
+    if (n_max == 0) return;
+
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, gT = 0.f;
+    if (n > 0) {
+        gr = __ldg(g_rgb + 3 * ray);
+        gg = __ldg(g_rgb + 3 * ray + 1);
+        gb = __ldg(g_rgb + 3 * ray + 2);
+        gd = __ldg(g_depth + ray);
+        ga = __ldg(g_acc + ray);
+        gT = __ldg(g_bgT + ray);
+    }
+
+    // pass 1 (left to right): transmittance at the start of every chunk.  Lane c keeps chunk c's value, which covers
+    // W*W samples; beyond that the per-sample T is parked in d_alpha (scratch, overwritten in pass 2).
+    const int n_chunks_max = (n_max + W - 1) / W;
+    const bool spill = n_chunks_max > W;
+    float my_chunk_T = 1.f;
+    {
+        float carry = 1.f;
+        for (int c = 0; c < n_chunks_max; ++c) {
+            const int i = c * W + gl;
+            const bool valid = i < n;
+            float a = valid ? __ldg(alpha + start + i) : 0.f;
+            float incl = group_scan_mul<W>(1.f - a, gl);
+            if (spill) {
+                float Ti = carry * group_shift_up<W>(incl, gl, 1.f);
+                if (valid) d_alpha[(int64_t)start + i] = Ti;
+            } else if (gl == c) {
+                my_chunk_T = carry;
+            }
+            carry *= group_bcast<W>(incl, W - 1);
+        }
+    }
+
+    // pass 2 (right to left): reverse affine scan
+    float Rcarry = gT;
+    for (int c = n_chunks_max - 1; c >= 0; --c) {
+        const int i = c * W + gl;
+        const bool valid = i < n;
+        const int64_t s = (int64_t)start + i;
+        float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, zz = 0.f;
+        if (valid) {
+            a = ld_stream(alpha + s);
+            cr = ld_stream(rgb + 3 * s);
+            cg = ld_stream(rgb + 3 * s + 1);
+            cb = ld_stream(rgb + 3 * s + 2);
+            zz = ld_stream(z + s);
+        }
+        float Ti;
+        if (spill) {
+            Ti = valid ? d_alpha[s] : 0.f;
+        } else {
+            float incl = group_scan_mul<W>(1.f - a, gl);
+            float chunkT = group_bcast<W>(my_chunk_T, c & (W - 1));
+            Ti = chunkT * group_shift_up<W>(incl, gl, 1.f);
+        }
+        const float gi = fmaf(gr, cr, fmaf(gg, cg, fmaf(gb, cb, fmaf(gd, zz, ga))));
+        // F_i(x) = (1-a) x + a g_i ; identity for lanes past the end
+        float A = valid ? (1.f - a) : 1.f;
+        float B = valid ? a * gi : 0.f;
+        group_rscan_affine<W>(A, B, gl);
+        // R_{i-1} = A*Rcarry + B ; R_i is the next lane's value (Rcarry for the last lane)
+        float Rprev = fmaf(A, Rcarry, B);
+        float Ri = __shfl_down_sync(VS_FULL_MASK, Rprev, 1, W);
+        if (gl == W - 1) Ri = Rcarry;
+        if (valid) {
+            const float w = Ti * a;
+            st_stream(d_alpha + s, Ti * (gi - Ri));
+            st_stream(d_rgb + 3 * s, gr * w);
+            st_stream(d_rgb + 3 * s + 1, gg * w);
+            st_stream(d_rgb + 3 * s + 2, gb * w);
+            if (d_z) st_stream(d_z + s, gd * w);
+        }
+        Rcarry = group_bcast<W>(Rprev, 0);
+    }
+}
+
+// =============================================================================================
+// tile family (short segments)
+// =============================================================================================
+// copy src[first, first+count) -> dst[(first - align4(first)) ...] with 16-byte loads for the aligned body.
+// dst must be 16-byte aligned; src base 16-byte aligned.
+__device__ __forceinline__ void stage_in(float* __restrict__ dst, const float* __restrict__ src, int64_t first, int count, int tid,
+                                         int nthreads) {
+    const int64_t last = first + count;
+    const int64_t first_al = first & ~(int64_t)3;
+    const int64_t body0 = (first + 3) & ~(int64_t)3;
+    const int64_t body1 = last & ~(int64_t)3;
+    if (body1 > body0) {
+        const int nvec = (int)((body1 - body0) >> 2);
+        const float4* s4 = reinterpret_cast<const float4*>(src + body0);
+        float4* d4 = reinterpret_cast<float4*>(dst + (body0 - first_al));
+        for (int v = tid; v < nvec; v += nthreads) d4[v] = ld_stream4(s4 + v);
+        // head [first, body0) and tail [body1, last): at most 3 elements each
+        if (tid < 3) {
+            int64_t e = first + tid;
+            if (e < body0) dst[e - first_al] = ld_stream(src + e);
+        } else if (tid < 6) {
+            int64_t e = body1 + (tid - 3);
+            if (e < last) dst[e - first_al] = ld_stream(src + e);
+        }
+    } else {
+        for (int64_t e = first + tid; e < last; e += nthreads) dst[e - first_al] = ld_stream(src + e);
+    }
+}
+
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* __restrict__ src_smem, int64_t first, int count, int tid,
+                                          int nthreads) {
+    const int64_t last = first + count;
+    const int64_t first_al = first & ~(int64_t)3;
+    const int64_t body0 = (first + 3) & ~(int64_t)3;
+    const int64_t body1 = last & ~(int64_t)3;
+    if (body1 > body0) {
+        const int nvec = (int)((body1 - body0) >> 2);
+        float4* d4 = reinterpret_cast<float4*>(dst + body0);
+        const float4* s4 = reinterpret_cast<const float4*>(src_smem + (body0 - first_al));
+        for (int v = tid; v < nvec; v += nthreads) st_stream4(d4 + v, s4[v]);
+        if (tid < 3) {
+            int64_t e = first + tid;
+            if (e < body0) st_stream(dst + e, src_smem[e - first_al]);
+        } else if (tid < 6) {
+            int64_t e = body1 + (tid - 3);
+            if (e < last) st_stream(dst + e, src_smem[e - first_al]);
+        }
+    } else {
+        for (int64_t e = first + tid; e < last; e += nthreads) st_stream(dst + e, src_smem[e - first_al]);
+    }
+}
+
+// block-wide: lowest start / highest end / sum of counts over the tile's non-empty rays
+struct TileRange {
+    int lo, hi, total;
+};
+
+__device__ __forceinline__ TileRange tile_range(int start, int n, int* red /* 3*8 ints */) {
+    int lo = n > 0 ? start : 0x7fffffff;
+    int hi = n > 0 ? start + n : -1;
+    int tot = n;
+    lo = __reduce_min_sync(VS_FULL_MASK, lo);
+    hi = __reduce_max_sync(VS_FULL_MASK, hi);
+    tot = __reduce_add_sync(VS_FULL_MASK, tot);
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red[wid] = lo;
+        red[8 + wid] = hi;
+        red[16 + wid] = tot;
+    }
+    __syncthreads();
+    TileRange r;
+    r.lo = red[0];
+    r.hi = red[8];
+    r.total = red[16];
+#pragma unroll
+    for (int k = 1; k < kTileRays / 32; ++k) {
+        r.lo = min(r.lo, red[k]);
+        r.hi = max(r.hi, red[8 + k]);
+        r.total += red[16 + k];
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(kTileRays) composite_fwd_tile_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
+    float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays, int cap) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int red[24];
+    float* s_alpha = smem;                 // cap+4
+    float* s_z = s_alpha + (cap + 4);      // cap+4
+    float* s_rgb = s_z + (cap + 4);        // 3*cap+4
+    float* s_out = s_rgb + (3 * cap + 4);  // 6*kTileRays: per-ray outputs, written back coalesced
+
+    const int tid = threadIdx.x;
+    const int64_t ray0 = (int64_t)blockIdx.x * kTileRays;
+    const int64_t ray = ray0 + tid;
+    int start = 0, n = 0;
+    if (ray < n_rays) n = load_segment(se, ray, start);
+    const TileRange tr = tile_range(start, n, red);
+    const int count = tr.hi - tr.lo;
+    const bool staged = tr.total > 0 && count <= cap && count == tr.total;  // contiguous and fits
+
+    // base pointers + element offsets of this ray's first sample (shared-memory tile or global memory)
+    const float* pa = alpha;
+    const float* pz = z;
+    const float* pc = rgb;
+    int64_t ia = start, ic = 3 * (int64_t)start;
+    if (staged) {
+        stage_in(s_alpha, alpha, tr.lo, count, tid, kTileRays);
+        stage_in(s_z, z, tr.lo, count, tid, kTileRays);
+        stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
+        __syncthreads();
+        pa = s_alpha;
+        pz = s_z;
+        pc = s_rgb;
+        ia = start - (tr.lo & ~3);
+        ic = 3 * (int64_t)start - ((3 * (int64_t)tr.lo) & ~(int64_t)3);
+    }
+
+    float T = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const float a = pa[ia + i];
+        const float w = T * a;
+        ar = fmaf(w, pc[ic + 3 * i], ar);
+        ag = fmaf(w, pc[ic + 3 * i + 1], ag);
+        ab = fmaf(w, pc[ic + 3 * i + 2], ab);
+        ad = fmaf(w, pz[ia + i], ad);
+        aa += w;
+        if (out_w) out_w[(int64_t)start + i] = w;
+        if (out_T) out_T[(int64_t)start + i] = T;
+        T *= (1.f - a);
+    }
+    // per-ray outputs through shared memory so that the [N,3] colour rows leave as full 128-byte lines
+    s_out[3 * tid] = ar;
+    s_out[3 * tid + 1] = ag;
+    s_out[3 * tid + 2] = ab;
+    __syncthreads();
+    const int64_t rays_here = min((int64_t)kTileRays, n_rays - ray0);
+    for (int e = tid; e < 3 * rays_here; e += kTileRays) out_rgb[3 * ray0 + e] = s_out[e];
+    if (ray < n_rays) {
+        out_depth[ray] = ad;
+        out_acc[ray] = aa;
+        out_bgT[ray] = T;
+    }
+}
+
+__global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
+    float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays, int cap) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int red[24];
+    float* s_alpha = smem;                 // cap+4  (becomes d_alpha)
+    float* s_z = s_alpha + (cap + 4);      // cap+4  (becomes d_z when requested)
+    float* s_rgb = s_z + (cap + 4);        // 3*cap+4 (becomes d_rgb)
+    float* s_T = s_rgb + (3 * cap + 4);    // cap+4
+    float* s_g = s_T + (cap + 4);          // 3*kTileRays staged g_rgb
+
+    const int tid = threadIdx.x;
+    const int64_t ray0 = (int64_t)blockIdx.x * kTileRays;
+    const int64_t ray = ray0 + tid;
+    int start = 0, n = 0;
+    if (ray < n_rays) n = load_segment(se, ray, start);
+    const TileRange tr = tile_range(start, n, red);
+    if (tr.total == 0) return;
+    const int count = tr.hi - tr.lo;
+    const bool staged = count <= cap && count == tr.total;
+
+    const int64_t rays_here = min((int64_t)kTileRays, n_rays - ray0);
+    for (int e = tid; e < 3 * rays_here; e += kTileRays) s_g[e] = __ldg(g_rgb + 3 * ray0 + e);
+    float gd = 0.f, ga = 0.f, R = 0.f;
+    if (ray < n_rays) {
+        gd = __ldg(g_depth + ray);
+        ga = __ldg(g_acc + ray);
+        R = __ldg(g_bgT + ray);
+    }
+
+    if (staged) {
+        stage_in(s_alpha, alpha, tr.lo, count, tid, kTileRays);
+        stage_in(s_z, z, tr.lo, count, tid, kTileRays);
+        stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
+        __syncthreads();
+        const int ia = start - (tr.lo & ~3);
+        const int ic = (int)(3 * (int64_t)start - ((3 * (int64_t)tr.lo) & ~(int64_t)3));
+        const float gr = s_g[3 * tid], gg = s_g[3 * tid + 1], gb = s_g[3 * tid + 2];
+        float T = 1.f;
+        for (int i = 0; i < n; ++i) {
+            s_T[ia + i] = T;
+            T *= (1.f - s_alpha[ia + i]);
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            const float a = s_alpha[ia + i];
+            const float Ti = s_T[ia + i];
+            const float cr = s_rgb[ic + 3 * i], cg = s_rgb[ic + 3 * i + 1], cb = s_rgb[ic + 3 * i + 2];
+            const float zz = s_z[ia + i];
+            const float gi = fmaf(gr, cr, fmaf(gg, cg, fmaf(gb, cb, fmaf(gd, zz, ga))));
+            const float w = Ti * a;
+            s_alpha[ia + i] = Ti * (gi - R);
+            s_rgb[ic + 3 * i] = gr * w;
+            s_rgb[ic + 3 * i + 1] = gg * w;
+            s_rgb[ic + 3 * i + 2] = gb * w;
+            s_z[ia + i] = gd * w;
+            R = fmaf(1.f - a, R, a * gi);
+        }
+        __syncthreads();
+        stage_out(d_alpha, s_alpha, tr.lo, count, tid, kTileRays);
+        stage_out(d_rgb, s_rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
+        if (d_z) stage_out(d_z, s_z, tr.lo, count, tid, kTileRays);
+    } else {
+        __syncthreads();
+        const float gr = s_g[3 * tid], gg = s_g[3 * tid + 1], gb = s_g[3 * tid + 2];
+        // direct: T parked in d_alpha, then overwritten right to left
+        float T = 1.f;
+        for (int i = 0; i < n; ++i) {
+            d_alpha[(int64_t)start + i] = T;
+            T *= (1.f - alpha[(int64_t)start + i]);
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            const int64_t s = (int64_t)start + i;
+            const float a = alpha[s];
+            const float Ti = d_alpha[s];
+            const float gi = fmaf(gr, rgb[3 * s], fmaf(gg, rgb[3 * s + 1], fmaf(gb, rgb[3 * s + 2], fmaf(gd, z[s], ga))));
+            const float w = Ti * a;
+            d_alpha[s] = Ti * (gi - R);
+            d_rgb[3 * s] = gr * w;
+            d_rgb[3 * s + 1] = gg * w;
+            d_rgb[3 * s + 2] = gb * w;
+            if (d_z) d_z[s] = gd * w;
+            R = fmaf(1.f - a, R, a * gi);
+        }
+    }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// shared-memory capacity (in samples) of a tile: 1.5x the mean load of 256 rays, at least 256
+static inline int tile_cap(int64_t n_rays, int64_t n_samples) {
+    double mean = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
+    int cap = (int)(mean * kTileRays * 1.5) + 64;
+    cap = (cap + 3) & ~3;
+    if (cap < 256) cap = 256;
+    return cap;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+// mode: 0 = auto, 1 = force tile family, 2 = force scan family (W from mean), 3 = scan with W=8 (A/B measurements)
+int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, float* out_rgb, float* out_depth,
+                     float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples, int mode,
+                     void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 3);
+    if (n_rays == 0) return VS_OK;
+    VS_CHECK_ARG(se && out_rgb && out_depth && out_acc && out_bgT);
+    VS_CHECK_ARG(n_samples == 0 || (alpha && rgb && z));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double mean = (double)n_samples / (double)n_rays;
+    bool tile = (mode == 1) || (mode == 0 && mean <= 8.0);
+    if (tile && !(aligned16(alpha) && aligned16(rgb) && aligned16(z))) tile = false;
+    if (tile) {
+        const int cap = tile_cap(n_rays, n_samples);
+        const size_t smem = sizeof(float) * ((size_t)5 * cap + 12 + 3 * kTileRays);
+        if (smem > 200 * 1024) {
+            tile = false;
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(composite_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            composite_fwd_tile_kernel<<<(unsigned)div_up(n_rays, kTileRays), kTileRays, smem, st>>>(
+                se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays, cap);
+            return launched(1);
+        }
+    }
+    int Wsel = mode == 3 ? 8 : pick_group_width(n_rays, n_samples);
+    if (Wsel < 8) Wsel = 8;
+    const unsigned grid = (unsigned)div_up(n_rays * Wsel, kScanThreads);
+    switch (Wsel) {
+        case 8:
+            composite_fwd_scan_kernel<8><<<grid, kScanThreads, 0, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays);
+            break;
+        case 16:
+            composite_fwd_scan_kernel<16><<<grid, kScanThreads, 0, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays);
+            break;
+        default:
+            composite_fwd_scan_kernel<32><<<grid, kScanThreads, 0, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays);
+            break;
+    }
+    return launched(1);
+}
+
+int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, const float* g_rgb, const float* g_depth,
+                     const float* g_acc, const float* g_bgT, float* d_alpha, float* d_rgb, float* d_z, int64_t n_rays, int64_t n_samples,
+                     int mode, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 3);
+    if (n_rays == 0 || n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(se && alpha && rgb && z && g_rgb && g_depth && g_acc && g_bgT && d_alpha && d_rgb);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double mean = (double)n_samples / (double)n_rays;
+    bool tile = (mode == 1) || (mode == 0 && mean <= 8.0);
+    if (tile && !(aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z))))
+        tile = false;
+    if (tile) {
+        const int cap = tile_cap(n_rays, n_samples);
+        const size_t smem = sizeof(float) * ((size_t)6 * cap + 16 + 3 * kTileRays);
+        if (smem > 200 * 1024) {
+            tile = false;
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(composite_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            composite_bwd_tile_kernel<<<(unsigned)div_up(n_rays, kTileRays), kTileRays, smem, st>>>(
+                se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays, cap);
+            return launched(1);
+        }
+    }
+    int Wsel = mode == 3 ? 8 : pick_group_width(n_rays, n_samples);
+    if (Wsel < 8) Wsel = 8;
+    const unsigned grid = (unsigned)div_up(n_rays * Wsel, kScanThreads);
+    switch (Wsel) {
+        case 8:
+            composite_bwd_scan_kernel<8><<<grid, kScanThreads, 0, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays);
+            break;
+        case 16:
+            composite_bwd_scan_kernel<16><<<grid, kScanThreads, 0, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays);
+            break;
+        default:
+            composite_bwd_scan_kernel<32><<<grid, kScanThreads, 0, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays);
+            break;
+    }
+    return launched(1);
+}
+
+}  // extern "C"

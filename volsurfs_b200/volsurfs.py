@@ -1,0 +1,474 @@
+"""Python twin of the reference's pybind11 module ``volsurfs`` (src/PyBridge.cxx:19) for the hot path.
+
+Same class names, method names, argument order and tensor shapes as ``PyBridge.cxx:70-129`` so that
+``volsurfs_py/volume_rendering/*`` and the renderers can ``from volsurfs import VolumeRendering,
+RaySamplesPacked`` unchanged (see :func:`volsurfs_b200.install_as_volsurfs`).  Every operator goes through the
+C ABI of ``libvolsurfs_b200.so`` on the caller's current CUDA stream; there is no CPU or PyTorch fallback.
+
+Deliberate differences from the reference:
+  * tensors live on the *current* CUDA device instead of a hard-coded ``cuda:0``
+    (src/VolumeRendering.cu:45, src/RaySamplesPacked.cu:16-42);
+  * kernels are enqueued on torch's current stream and nothing calls ``cudaDeviceSynchronize``
+    (src/VolumeRendering.cu:54,65);
+  * argument errors raise ``RuntimeError``/``ValueError`` instead of aborting the process through ``CHECK``;
+  * ``integrate_with_weights_3d_backward`` computes the mathematically correct ``dw`` unless
+    ``VolumeRendering.reference_bugs = True`` (the reference reads channel [1] twice,
+    kernels/volsurfs/VolumeRenderingGPU.cuh:1021).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.VolsurfsB200Error("volsurfs_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, name: str, cols=None) -> torch.Tensor:
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 2:
+        raise RuntimeError(f"{name} must be 2-dimensional, got shape {tuple(t.shape)}")
+    if cols is not None and t.shape[1] != cols:
+        raise RuntimeError(f"{name} must have {cols} columns, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+class RaySamplesPacked:
+    """Struct-of-arrays packet of per-ray sample segments (include/volsurfs/RaySamplesPacked.cuh:7-81)."""
+
+    def __init__(self, nr_rays: int, max_nr_samples: int, first_sample_idx: int = 0, values_dim: int = 1):
+        dev = _device()
+        f = dict(dtype=torch.float32, device=dev)
+        # per sample (src/RaySamplesPacked.cu:15-24)
+        self.samples_idx = torch.arange(
+            first_sample_idx, max_nr_samples + first_sample_idx, dtype=torch.int32, device=dev
+        ).unsqueeze(1)
+        self.samples_3d = torch.full((max_nr_samples, 3), -1.0, **f)
+        self.samples_dirs = torch.full((max_nr_samples, 3), -1.0, **f)
+        self.samples_z = torch.full((max_nr_samples, 1), -1.0, **f)
+        self.samples_dt = torch.full((max_nr_samples, 1), -1.0, **f)
+        self.samples_values = torch.full((max_nr_samples, values_dim), -1.0, **f)
+        # per ray (:26-38)
+        self.ray_start_end_idx = torch.full((nr_rays, 2), -1, dtype=torch.int32, device=dev)
+        self.ray_o = torch.full((nr_rays, 3), -1.0, **f)
+        self.ray_d = torch.full((nr_rays, 3), -1.0, **f)
+        self.ray_enter = torch.full((nr_rays, 1), -1.0, **f)
+        self.ray_exit = torch.full((nr_rays, 1), -1.0, **f)
+        self.ray_max_dt = torch.full((nr_rays, 1), -1.0, **f)
+        # flags (:45-47); C++-only in the reference, plain attributes here
+        self.has_samples_values = False
+        self.has_dt = False
+        self.is_compacted = True
+        # extension: per-sample layer / triangle / barycentric (u,v) of K-layer hits (None for other producers)
+        self.samples_layer = None
+        self.samples_triangle = None
+        self.samples_uv = None
+
+    @classmethod
+    def _from_tensors(cls, **tensors) -> "RaySamplesPacked":
+        self = cls.__new__(cls)
+        self.has_samples_values = False
+        self.has_dt = False
+        self.is_compacted = True
+        self.samples_layer = self.samples_triangle = self.samples_uv = None
+        for k, v in tensors.items():
+            setattr(self, k, v)
+        return self
+
+    # -- sizes ---------------------------------------------------------------------------------------------------
+    def get_nr_rays(self) -> int:
+        return int(self.ray_start_end_idx.shape[0])
+
+    def get_max_nr_samples(self) -> int:
+        return int(self.samples_idx.shape[0])
+
+    def get_values_dim(self) -> int:
+        return int(self.samples_values.shape[1])
+
+    def get_nr_samples_per_ray(self) -> torch.Tensor:
+        se = self.ray_start_end_idx
+        return se[:, 1] - se[:, 0]
+
+    def get_total_nr_samples(self) -> int:
+        """Sum of the per-ray counts (src/RaySamplesPacked.cu:170-175). One device->host read."""
+        n = self.get_nr_rays()
+        if n == 0:
+            return 0
+        total = torch.empty(1, dtype=torch.int64, device=self.ray_start_end_idx.device)
+        check(_lib.lib().vs_count_total(ptr(self.ray_start_end_idx), n, ptr(total), _stream()), "vs_count_total")
+        return int(total.item())
+
+    def is_empty(self) -> bool:
+        return self.get_nr_rays() == 0 or self.get_total_nr_samples() == 0
+
+    # -- per-ray accessors (src/RaySamplesPacked.cu:55-150) ---------------------------------------------------------
+    def _check_ray(self, ray_idx: int):
+        if ray_idx < 0 or ray_idx >= self.get_nr_rays():
+            raise ValueError("ray_idx must be in the range [0, nr_rays)")
+
+    def get_ray_max_dt(self, ray_idx: int) -> float:
+        self._check_ray(ray_idx)
+        return float(self.ray_max_dt[ray_idx, 0].item())
+
+    def _ray_slice(self, t: torch.Tensor, ray_idx: int) -> torch.Tensor:
+        s, e = self.ray_start_end_idx[ray_idx].tolist()
+        return t[s:e]
+
+    def get_ray_samples_idx(self, ray_idx: int):
+        return self._ray_slice(self.samples_idx, ray_idx)
+
+    def get_ray_samples_3d(self, ray_idx: int):
+        return self._ray_slice(self.samples_3d, ray_idx)
+
+    def get_ray_samples_dirs(self, ray_idx: int):
+        return self._ray_slice(self.samples_dirs, ray_idx)
+
+    def get_ray_samples_z(self, ray_idx: int):
+        return self._ray_slice(self.samples_z, ray_idx)
+
+    def get_ray_samples_dt(self, ray_idx: int):
+        return self._ray_slice(self.samples_dt, ray_idx)
+
+    def get_samples_values(self):
+        return self.samples_values
+
+    def get_ray_samples_values(self, ray_idx: int):
+        if not self.has_samples_values:
+            raise RuntimeError("RaySamplesPacked does not have samples values")
+        return self._ray_slice(self.samples_values, ray_idx)
+
+    def get_ray_start_end_idx(self, ray_idx: int):
+        return self.ray_start_end_idx[ray_idx, :]
+
+    def get_ray_o(self, ray_idx: int):
+        return self.ray_o[ray_idx, :]
+
+    def get_ray_d(self, ray_idx: int):
+        return self.ray_d[ray_idx, :]
+
+    def get_ray_enter(self, ray_idx: int):
+        return self.ray_enter[ray_idx, :]
+
+    def get_ray_exit(self, ray_idx: int):
+        return self.ray_exit[ray_idx, :]
+
+    # -- values ----------------------------------------------------------------------------------------------------
+    def are_samples_values_set(self) -> bool:
+        return self.has_samples_values
+
+    def set_samples_values(self, samples_values: torch.Tensor) -> None:
+        # src/RaySamplesPacked.cu:328-340
+        if not self.is_compacted:
+            raise RuntimeError("RaySamplesPacked must be compacted before calling set_samples_values")
+        if self.has_samples_values:
+            raise RuntimeError("Trying to set samples_values when it is already set, remove them first")
+        if samples_values.dim() != 2:
+            raise RuntimeError("samples_values must be 2-dimensional")
+        if self.samples_3d.shape[0] != samples_values.shape[0]:
+            raise RuntimeError("samples_3d and samples_values do not have matching 0 dimension")
+        self.samples_values = samples_values.clone()
+        self.has_samples_values = True
+
+    def remove_samples_values(self) -> None:
+        if not self.has_samples_values:
+            raise RuntimeError("trying to remove samples_values when it is not set")
+        self.samples_values.fill_(-1.0)
+        self.has_samples_values = False
+
+    def copy(self) -> "RaySamplesPacked":
+        # src/RaySamplesPacked.cu:300-326
+        out = RaySamplesPacked._from_tensors(
+            samples_idx=self.samples_idx.clone(),
+            samples_3d=self.samples_3d.clone(),
+            samples_dirs=self.samples_dirs.clone(),
+            samples_z=self.samples_z.clone(),
+            samples_dt=self.samples_dt.clone(),
+            samples_values=self.samples_values.clone() if self.has_samples_values else torch.full_like(self.samples_values, -1.0),
+            ray_start_end_idx=self.ray_start_end_idx.clone(),
+            ray_o=self.ray_o.clone(),
+            ray_d=self.ray_d.clone(),
+            ray_enter=self.ray_enter.clone(),
+            ray_exit=self.ray_exit.clone(),
+            ray_max_dt=self.ray_max_dt.clone(),
+        )
+        out.has_samples_values = self.has_samples_values
+        out.has_dt = self.has_dt
+        out.is_compacted = self.is_compacted
+        for k in ("samples_layer", "samples_triangle", "samples_uv"):
+            v = getattr(self, k)
+            setattr(out, k, None if v is None else v.clone())
+        return out
+
+    # -- packing ---------------------------------------------------------------------------------------------------
+    def compact_to_valid_samples(self) -> "RaySamplesPacked":
+        """Gather every ray's segment to dense prefix-sum offsets (src/RaySamplesPacked.cu:188-273).
+
+        One device->host read (the total, needed to size the outputs exactly like the reference); the reference
+        takes three (``get_total_nr_samples`` twice + ``is_empty``)."""
+        if self.is_compacted:
+            raise RuntimeError("RaySamplesPacked must not be compacted before calling compact_to_valid_samples")
+        L = _lib.lib()
+        n_rays = self.get_nr_rays()
+        dev = self.ray_start_end_idx.device
+        st = _stream()
+        se_in = self.ray_start_end_idx.contiguous()
+        scratch = torch.empty(max(int(L.vs_pack_scratch_bytes(n_rays)), 8), dtype=torch.uint8, device=dev)
+        total_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(L.vs_compact_offsets(ptr(se_in), n_rays, ptr(total_dev), ptr(scratch), st), "vs_compact_offsets")
+        total = int(total_dev.item())
+        if total > 2**31 - 1:
+            raise RuntimeError("more than 2^31-1 samples cannot be indexed by int32 ray_start_end_idx")
+        vd = self.get_values_dim()
+        f = dict(dtype=torch.float32, device=dev)
+        out = RaySamplesPacked._from_tensors(
+            samples_idx=torch.empty((total, 1), dtype=torch.int32, device=dev),
+            samples_3d=torch.empty((total, 3), **f),
+            samples_dirs=torch.empty((total, 3), **f),
+            samples_z=torch.empty((total, 1), **f),
+            samples_dt=torch.empty((total, 1), **f),
+            samples_values=torch.empty((total, vd), **f),
+            ray_start_end_idx=torch.empty((n_rays, 2), dtype=torch.int32, device=dev),
+            ray_o=self.ray_o.clone(),
+            ray_d=self.ray_d.clone(),
+            ray_enter=self.ray_enter.clone(),
+            ray_exit=self.ray_exit.clone(),
+            ray_max_dt=self.ray_max_dt.clone(),
+        )
+        out.has_samples_values = self.has_samples_values
+        out.has_dt = self.has_dt
+        out.is_compacted = True
+        if n_rays == 0:
+            return out
+        check(
+            L.vs_compact_gather(
+                ptr(se_in), ptr(scratch),
+                ptr(self.samples_idx.contiguous()), ptr(self.samples_3d.contiguous()), ptr(self.samples_dirs.contiguous()),
+                ptr(self.samples_z.contiguous()), ptr(self.samples_dt.contiguous()), ptr(self.samples_values.contiguous()), vd,
+                ptr(out.ray_start_end_idx), ptr(out.samples_idx), ptr(out.samples_3d), ptr(out.samples_dirs),
+                ptr(out.samples_z), ptr(out.samples_dt), ptr(out.samples_values), n_rays, total, st,
+            ),
+            "vs_compact_gather",
+        )
+        return out
+
+    def update_dt(self, is_background: bool) -> None:
+        """dt_i = clamp(z_{i+1}-z_i, 0, max_dt); last = clamp(t_exit-z, 0, max_dt) or 1e10 for the background
+        (kernels/volsurfs/RaySamplesPackedGPU.cuh:14-88)."""
+        if not self.is_compacted:
+            raise RuntimeError("RaySamplesPacked must be compacted before calling update_dt")
+        n_rays = self.get_nr_rays()
+        n_samples = self.get_max_nr_samples()
+        if n_rays == 0 or n_samples == 0:
+            raise RuntimeError("RaySamplesPacked must not be empty before calling update_dt")
+        self.samples_dt = self.samples_dt.contiguous()
+        check(
+            _lib.lib().vs_update_dt(
+                ptr(self.ray_start_end_idx), ptr(self.samples_z.contiguous()), ptr(self.ray_exit.contiguous()),
+                ptr(self.ray_max_dt.contiguous()), ptr(self.samples_dt), int(bool(is_background)), n_rays, n_samples, _stream(),
+            ),
+            "vs_update_dt",
+        )
+        self.has_dt = True
+
+
+class VolumeRendering:
+    """Static packed-sample operators (include/volsurfs/VolumeRendering.cuh:19-97, bound at PyBridge.cxx:113-129)."""
+
+    #: reproduce the reference's integrate_with_weights_3d_backward z-channel bug (VolumeRenderingGPU.cuh:1021)
+    reference_bugs = False
+
+    @staticmethod
+    def _prep(rsp: RaySamplesPacked, what: str):
+        if not rsp.is_compacted:
+            raise RuntimeError(f"RaySamplesPacked must be compacted before calling {what}")
+        se = rsp.ray_start_end_idx
+        if se.dtype != torch.int32 or se.dim() != 2 or se.shape[1] != 2 or not se.is_cuda:
+            raise RuntimeError("ray_start_end_idx must be an int32 CUDA tensor of shape [nr_rays, 2]")
+        return se.contiguous(), int(se.shape[0])
+
+    # ---- forward ops ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def cumprod_one_minus_alpha_to_transmittance(ray_samples_packed, alpha_samples):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "cumprod")
+        x = _f32c(alpha_samples, "alpha_samples", 1)
+        S = x.shape[0]
+        T = torch.zeros((S, 1), dtype=torch.float32, device=x.device)
+        bg = torch.empty((n_rays, 1), dtype=torch.float32, device=x.device)
+        check(_lib.lib().vs_cumprod_fwd(ptr(se), ptr(x), ptr(T), ptr(bg), n_rays, S, _stream()), "vs_cumprod_fwd")
+        return T, bg
+
+    @staticmethod
+    def _integrate(ray_samples_packed, values, weights, dim):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, f"integrate_with_weights_{dim}d")
+        v = _f32c(values, "values", dim)
+        w = _f32c(weights, "weights", 1)
+        if v.shape[0] != w.shape[0]:
+            raise RuntimeError("values and weights must have the same number of samples")
+        out = torch.empty((n_rays, dim), dtype=torch.float32, device=v.device)
+        check(_lib.lib().vs_integrate_fwd(ptr(se), ptr(v), ptr(w), ptr(out), dim, n_rays, v.shape[0], _stream()), "vs_integrate_fwd")
+        return out
+
+    @staticmethod
+    def integrate_with_weights_1d(ray_samples_packed, values, weights):
+        return VolumeRendering._integrate(ray_samples_packed, values, weights, 1)
+
+    @staticmethod
+    def integrate_with_weights_3d(ray_samples_packed, values, weights):
+        return VolumeRendering._integrate(ray_samples_packed, values, weights, 3)
+
+    @staticmethod
+    def sum_over_rays(ray_samples_packed, samples_values):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "sum_over_rays")
+        v = _f32c(samples_values, "samples_values")
+        d = v.shape[1]
+        if not (d <= 3 or d == 32) or d == 0:
+            raise RuntimeError(f"samples_values should have 1, 2, 3 or 32 values per sample, got {tuple(v.shape)}")
+        per_ray = torch.empty((n_rays, d), dtype=torch.float32, device=v.device)
+        per_sample = torch.zeros_like(v)
+        check(_lib.lib().vs_sum_fwd(ptr(se), ptr(v), ptr(per_ray), ptr(per_sample), d, n_rays, v.shape[0], _stream()), "vs_sum_fwd")
+        return per_ray, per_sample
+
+    @staticmethod
+    def cumsum_over_rays(ray_samples_packed, samples_values, inverse):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "cumsum_over_rays")
+        v = _f32c(samples_values, "samples_values", 1)
+        out = torch.zeros_like(v)
+        check(_lib.lib().vs_cumsum(ptr(se), ptr(v), ptr(out), int(bool(inverse)), n_rays, v.shape[0], _stream()), "vs_cumsum")
+        return out
+
+    # ---- backward ops --------------------------------------------------------------------------------------------
+    @staticmethod
+    def cumprod_one_minus_alpha_to_transmittance_backward(
+        grad_transmittance, grad_bg_transmittance, ray_samples_packed, alpha, transmittance, bg_transmittance, cumsumLV
+    ):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "cumprod backward")
+        x = _f32c(alpha, "alpha", 1)
+        gbg = _f32c(grad_bg_transmittance, "grad_bg_transmittance", 1)
+        bg = _f32c(bg_transmittance, "bg_transmittance", 1)
+        cs = _f32c(cumsumLV, "cumsumLV", 1)
+        dx = torch.zeros_like(x)
+        check(
+            _lib.lib().vs_cumprod_bwd(ptr(se), ptr(gbg), ptr(x), ptr(bg), ptr(cs), ptr(dx), n_rays, x.shape[0], _stream()),
+            "vs_cumprod_bwd",
+        )
+        return dx
+
+    @staticmethod
+    def cumprod_backward_fused(grad_transmittance, grad_bg_transmittance, ray_samples_packed, alpha, transmittance, bg_transmittance):
+        """LV product + reverse cumsum + division in one launch (extension; same result as the two-step path)."""
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "cumprod backward")
+        x = _f32c(alpha, "alpha", 1)
+        gT = _f32c(grad_transmittance, "grad_transmittance", 1)
+        gbg = _f32c(grad_bg_transmittance, "grad_bg_transmittance", 1)
+        T = _f32c(transmittance, "transmittance", 1)
+        bg = _f32c(bg_transmittance, "bg_transmittance", 1)
+        dx = torch.zeros_like(x)
+        check(
+            _lib.lib().vs_cumprod_bwd_fused(ptr(se), ptr(gT), ptr(gbg), ptr(x), ptr(T), ptr(bg), ptr(dx), n_rays, x.shape[0], _stream()),
+            "vs_cumprod_bwd_fused",
+        )
+        return dx
+
+    @staticmethod
+    def _integrate_backward(grad_result, ray_samples_packed, values, weights, dim):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, f"integrate_with_weights_{dim}d_backward")
+        g = _f32c(grad_result, "grad_result", dim)
+        v = _f32c(values, "values", dim)
+        w = _f32c(weights, "weights", 1)
+        dv = torch.zeros_like(v)
+        dw = torch.zeros_like(w)
+        check(
+            _lib.lib().vs_integrate_bwd(
+                ptr(se), ptr(g), ptr(v), ptr(w), ptr(dv), ptr(dw), dim, n_rays, v.shape[0], int(VolumeRendering.reference_bugs), _stream()
+            ),
+            "vs_integrate_bwd",
+        )
+        return dv, dw
+
+    @staticmethod
+    def integrate_with_weights_1d_backward(grad_result, ray_samples_packed, values, weights, result):
+        return VolumeRendering._integrate_backward(grad_result, ray_samples_packed, values, weights, 1)
+
+    @staticmethod
+    def integrate_with_weights_3d_backward(grad_result, ray_samples_packed, values, weights, result):
+        return VolumeRendering._integrate_backward(grad_result, ray_samples_packed, values, weights, 3)
+
+    @staticmethod
+    def sum_over_rays_backward(grad_values_sum_per_ray, grad_values_sum_per_sample, ray_samples_packed, sample_values):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "sum_over_rays_backward")
+        v = _f32c(sample_values, "sample_values")
+        d = v.shape[1]
+        if d not in (1, 2, 3):
+            raise RuntimeError("sum_over_rays_backward supports 1, 2 or 3 values per sample")
+        gr = _f32c(grad_values_sum_per_ray, "grad_values_sum_per_ray", d)
+        gs = _f32c(grad_values_sum_per_sample, "grad_values_sum_per_sample", d)
+        dv = torch.zeros_like(v)
+        check(_lib.lib().vs_sum_bwd(ptr(se), ptr(gr), ptr(gs), ptr(dv), d, n_rays, v.shape[0], _stream()), "vs_sum_bwd")
+        return dv
+
+    # ---- fused compositing (extension; the product's fast path) -------------------------------------------------
+    @staticmethod
+    def composite(ray_samples_packed, alpha, rgb, z=None, return_weights=False, mode=0):
+        """rgb [N,3], depth [N,1], acc [N,1], bgT [N,1] (+ weights, transmittance [S,1]) in one launch."""
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "composite")
+        a = _f32c(alpha, "alpha", 1)
+        c = _f32c(rgb, "rgb", 3)
+        zz = _f32c(ray_samples_packed.samples_z if z is None else z, "z", 1)
+        S = a.shape[0]
+        if c.shape[0] != S or zz.shape[0] != S:
+            raise RuntimeError("alpha, rgb and z must have the same number of samples")
+        f = dict(dtype=torch.float32, device=a.device)
+        out_rgb = torch.empty((n_rays, 3), **f)
+        out_depth = torch.empty((n_rays, 1), **f)
+        out_acc = torch.empty((n_rays, 1), **f)
+        out_bgT = torch.empty((n_rays, 1), **f)
+        w = torch.zeros((S, 1), **f) if return_weights else None
+        T = torch.zeros((S, 1), **f) if return_weights else None
+        check(
+            _lib.lib().vs_composite_fwd(
+                ptr(se), ptr(a), ptr(c), ptr(zz), ptr(out_rgb), ptr(out_depth), ptr(out_acc), ptr(out_bgT), ptr(w), ptr(T),
+                n_rays, S, int(mode), _stream(),
+            ),
+            "vs_composite_fwd",
+        )
+        if return_weights:
+            return out_rgb, out_depth, out_acc, out_bgT, w, T
+        return out_rgb, out_depth, out_acc, out_bgT
+
+    @staticmethod
+    def composite_backward(ray_samples_packed, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, need_dz=False, mode=0):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "composite_backward")
+        a = _f32c(alpha, "alpha", 1)
+        c = _f32c(rgb, "rgb", 3)
+        zz = _f32c(z, "z", 1)
+        S = a.shape[0]
+        gC = _f32c(g_rgb, "g_rgb", 3)
+        gD = _f32c(g_depth, "g_depth", 1)
+        gA = _f32c(g_acc, "g_acc", 1)
+        gB = _f32c(g_bgT, "g_bgT", 1)
+        for name, t in (("g_rgb", gC), ("g_depth", gD), ("g_acc", gA), ("g_bgT", gB)):
+            if t.shape[0] != n_rays:
+                raise RuntimeError(f"{name} must have one row per ray")
+        d_alpha = torch.empty_like(a)
+        d_rgb = torch.empty_like(c)
+        d_z = torch.empty_like(zz) if need_dz else None
+        check(
+            _lib.lib().vs_composite_bwd(
+                ptr(se), ptr(a), ptr(c), ptr(zz), ptr(gC), ptr(gD), ptr(gA), ptr(gB), ptr(d_alpha), ptr(d_rgb), ptr(d_z),
+                n_rays, S, int(mode), _stream(),
+            ),
+            "vs_composite_bwd",
+        )
+        return d_alpha, d_rgb, d_z
