@@ -49,3 +49,18 @@ def rel_err(a, b, floor=1e-6):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def grad_err(a, b):
+    """Error metric for gradients (sums of mixed-sign terms, so individual entries can cancel to ~0):
+    max |a-b| / max(|b|, rms(b)) — relative to the entry itself unless it is smaller than the tensor's typical
+    magnitude, in which case relative to that magnitude.  The fp32 torch-autograd reference itself differs from the
+    fp64 truth by ~1e-6 under this metric (tests/test_gpu_compositing.py::test_reference_fp32_error_scale)."""
+    import numpy as np
+
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    rms = float(np.sqrt(np.mean(b * b))) or 1.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), rms)))

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, rel_err
+from conftest import GOLDEN, grad_err, rel_err
 from oracle import compositing as oc
 from volsurfs_b200.synthetic import all_hit_packed, composite_bytes, dense_layers, nerf_packets, pack_dense
 
@@ -40,12 +40,11 @@ def _check(se, alpha, rgb, z, grads, mode):
         assert rel_err(got, o[key], floor=1e-6) < TOL, key
     ob = oc.fused_composite_backward(sen, alpha.numpy(), rgb.numpy(), z.numpy(), grads["g_rgb"].numpy(), grads["g_depth"].numpy(),
                                      grads["g_acc"].numpy(), grads["g_bgT"].numpy())
-    # gradients are sums of terms of mixed sign: compare against the magnitude scale of the terms (floor 1e-3*|g|max)
     for got, key in zip(bwd, ("d_alpha", "d_rgb", "d_z")):
-        assert rel_err(got, ob[key], floor=1e-2) < TOL, key
+        assert grad_err(got, ob[key]) < TOL, key
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_c1_shells_vs_oracle(mode):
     """BASELINE config 1: 4096 rays x 5 layers, Bernoulli(0.8) hits, exact 0/1 alphas, empty rays."""
     d = dense_layers(4096, 5, seed_offset=1)
@@ -72,8 +71,8 @@ def test_golden_reference_lines(mode):
         ray, j = np.nonzero(g["hit"][:, ::-1])
         lay = hit.shape[1] - 1 - j
         assert rel_err(fwd[4][:, 0], g["fp32_weights"][ray, lay, 0]) < TOL
-        assert rel_err(bwd[0][:, 0], g["fp32_d_alpha"][ray, lay, 0], floor=1e-2) < TOL
-        assert rel_err(bwd[1], g["fp32_d_rgb"][ray, lay], floor=1e-2) < TOL
+        assert grad_err(bwd[0][:, 0], g["fp32_d_alpha"][ray, lay, 0]) < TOL
+        assert grad_err(bwd[1], g["fp32_d_rgb"][ray, lay]) < TOL
 
 
 @pytest.mark.parametrize("mode", [0, 2])
@@ -94,7 +93,7 @@ def test_long_rays_spill_path():
 @pytest.mark.parametrize("n_rays,K", [(1, 5), (255, 5), (257, 9), (1000, 1)])
 def test_edge_sizes(n_rays, K):
     d = all_hit_packed(n_rays, K)
-    for mode in (1, 2):
+    for mode in (1, 2, 4):
         _check(d["se"], d["alpha"], d["rgb"], d["z"], d, mode)
 
 
@@ -103,7 +102,7 @@ def test_all_empty_and_zero_rays():
 
     se = torch.full((300, 2), -1, dtype=torch.int32)
     e1, e3 = torch.zeros(0, 1), torch.zeros(0, 3)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 4):
         rgb, depth, acc, bgT = VR.composite(_rsp(se), e1.cuda(), e3.cuda(), e1.cuda(), mode=mode)
         assert torch.all(rgb == 0) and torch.all(depth == 0) and torch.all(acc == 0) and torch.all(bgT == 1)
     rgb, depth, acc, bgT = VR.composite(_rsp(torch.zeros((0, 2), dtype=torch.int32)), e1.cuda(), e3.cuda(), e1.cuda())
@@ -124,6 +123,7 @@ def test_tile_fallback_on_skewed_and_gapped_layouts():
          "g_rgb": torch.randn(n, 3, generator=g), "g_depth": torch.randn(n, 1, generator=g), "g_acc": torch.randn(n, 1, generator=g),
          "g_bgT": torch.randn(n, 1, generator=g)}
     _check(se, d["alpha"], d["rgb"], d["z"], d, 1)
+    _check(se, d["alpha"], d["rgb"], d["z"], d, 4)
     # gapped: ray r owns slots [r*6, r*6+cnt_r), cnt_r in 0..6
     cnt = torch.randint(0, 7, (n,), generator=g)
     start = torch.arange(n) * 6
@@ -140,7 +140,7 @@ def test_tile_fallback_on_skewed_and_gapped_layouts():
     for s, e in se.numpy():
         if e > s:
             own[s:e] = True
-    assert rel_err(bwd[0][own], ob["d_alpha"][own], floor=1e-2) < TOL
+    assert grad_err(bwd[0][own], ob["d_alpha"][own]) < TOL
 
 
 def test_autograd_function_matches_dense_torch():
@@ -164,8 +164,8 @@ def test_autograd_function_matches_dense_torch():
     lay = hit.shape[1] - 1 - j
     assert rel_err(rgb.detach().cpu().numpy(), out["rgb_fg"].detach().numpy()) < TOL
     assert rel_err(bgT.detach().cpu().numpy(), out["bg_transmittance"].detach().numpy()) < TOL
-    assert rel_err(a_g.grad.cpu().numpy()[:, 0], ad.grad.numpy()[ray, lay, 0], floor=1e-2) < TOL
-    assert rel_err(c_g.grad.cpu().numpy(), cd.grad.numpy()[ray, lay], floor=1e-2) < TOL
+    assert grad_err(a_g.grad.cpu().numpy()[:, 0], ad.grad.numpy()[ray, lay, 0]) < TOL
+    assert grad_err(c_g.grad.cpu().numpy(), cd.grad.numpy()[ray, lay]) < TOL
 
 
 def test_full_size_properties():
@@ -191,5 +191,34 @@ def test_full_size_properties():
     o = oc.fused_composite_backward(d["se"][:4096].numpy(), d["alpha"][sub].numpy(), d["rgb"][sub].numpy(), d["z"][sub].numpy(),
                                     d["g_rgb"][:4096].numpy(), d["g_depth"][:4096].numpy(), d["g_acc"][:4096].numpy(),
                                     d["g_bgT"][:4096].numpy())
-    assert rel_err(d_alpha[sub].cpu().numpy(), o["d_alpha"], floor=1e-2) < TOL
+    assert grad_err(d_alpha[sub].cpu().numpy(), o["d_alpha"]) < TOL
     assert composite_bytes(n, n * K) == n * 344
+
+
+def test_reference_fp32_error_scale():
+    """Calibrates the gradient metric: the reference's own fp32 torch-autograd gradients vs the fp64 truth, and ours vs
+    the same truth, under grad_err.  Ours must be within the 1e-5 budget and not worse than 4x the reference's error."""
+    from volsurfs_b200.volsurfs import VolumeRendering as VR
+
+    d = dense_layers(4096, 5, seed_offset=1)
+    hit = d["hit"].numpy()
+    ray, j = np.nonzero(hit[:, ::-1])
+    lay = hit.shape[1] - 1 - j
+
+    def dense_grads(dtype):
+        a = d["alpha"].to(dtype).requires_grad_(True)
+        c = d["rgb"].to(dtype).requires_grad_(True)
+        out = oc.dense_composite_torch(a, c)
+        ((out["rgb_fg"] * d["g_rgb"].to(dtype)).sum() + (out["bg_transmittance"] * d["g_bgT"].to(dtype)).sum()).backward()
+        return a.grad.numpy()[ray, lay, 0], c.grad.numpy()[ray, lay]
+
+    da64, dc64 = dense_grads(torch.float64)
+    da32, dc32 = dense_grads(torch.float32)
+    se, a, c, z = pack_dense(d["hit"], d["alpha"], d["rgb"], d["z"])
+    N = se.shape[0]
+    g = {"g_rgb": d["g_rgb"], "g_depth": torch.zeros(N, 1), "g_acc": torch.zeros(N, 1), "g_bgT": d["g_bgT"]}
+    _, bwd = _run(se, a, c, z, g, 0, need_dz=False)
+    ref_err = max(grad_err(da32, da64), grad_err(dc32, dc64))
+    our_err = max(grad_err(bwd[0][:, 0], da64), grad_err(bwd[1], dc64))
+    print(f"fp32 torch autograd vs fp64: {ref_err:.2e}; CUDA vs fp64: {our_err:.2e}")
+    assert our_err < TOL and our_err < 4 * ref_err + 1e-7

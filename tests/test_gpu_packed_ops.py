@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_err
+from conftest import grad_err, rel_err
 from oracle import compositing as oc
 from oracle.packing import RaySamplesPackedNP
 from volsurfs_b200.synthetic import dense_layers, nerf_packets, pack_dense
@@ -50,19 +50,19 @@ def test_forward_ops(case):
 
     o1 = VR.integrate_with_weights_1d(rsp, v1.cuda(), w.cuda())
     o3 = VR.integrate_with_weights_3d(rsp, v3.cuda(), w.cuda())
-    assert rel_err(o1.cpu().numpy(), oc.packed_integrate_with_weights(sen, v1.numpy(), w.numpy(), np.float64), floor=1e-2) < TOL
-    assert rel_err(o3.cpu().numpy(), oc.packed_integrate_with_weights(sen, v3.numpy(), w.numpy(), np.float64), floor=1e-2) < TOL
+    assert grad_err(o1.cpu().numpy(), oc.packed_integrate_with_weights(sen, v1.numpy(), w.numpy(), np.float64)) < TOL
+    assert grad_err(o3.cpu().numpy(), oc.packed_integrate_with_weights(sen, v3.numpy(), w.numpy(), np.float64)) < TOL
 
     for d in (1, 2, 3, 32):
         v = torch.randn(S, d, generator=g)
         sr, ss = VR.sum_over_rays(rsp, v.cuda())
         sro, sso = oc.packed_sum_over_rays(sen, v.numpy(), np.float64)
-        assert rel_err(sr.cpu().numpy(), sro, floor=1e-2) < TOL, d
-        assert rel_err(ss.cpu().numpy(), sso, floor=1e-2) < TOL, d
+        assert grad_err(sr.cpu().numpy(), sro) < TOL, d
+        assert grad_err(ss.cpu().numpy(), sso) < TOL, d
 
     for inverse in (False, True):
         cs = VR.cumsum_over_rays(rsp, v1.cuda(), inverse)
-        assert rel_err(cs.cpu().numpy(), oc.packed_cumsum_over_rays(sen, v1.numpy(), inverse, np.float64), floor=1e-2) < TOL
+        assert grad_err(cs.cpu().numpy(), oc.packed_cumsum_over_rays(sen, v1.numpy(), inverse, np.float64)) < TOL
 
 
 @pytest.mark.parametrize("case", list(_cases()), ids=lambda c: c[0])
@@ -135,7 +135,7 @@ def test_reference_autograd_chain_vs_fused():
     loss2 = (rgb_f * p["g_rgb"].cuda()).sum() + (bgT_f * p["g_bgT"].cuda()).sum()
     loss2.backward()
     assert rel_err(pred.detach().cpu().numpy(), rgb_f.detach().cpu().numpy()) < TOL
-    assert rel_err(c2.grad.cpu().numpy(), rgb.grad.cpu().numpy(), floor=1e-2) < TOL
+    assert grad_err(c2.grad.cpu().numpy(), rgb.grad.cpu().numpy()) < TOL
     # alpha-gradients agree except where 1-alpha underflows the reference's clamp_min divisor
     ok = (1 - p["alpha"][:, 0]) > 1e-3
     assert rel_err(a2.grad.cpu().numpy()[ok], alpha.grad.cpu().numpy()[ok], floor=1e-1) < 1e-3

@@ -228,6 +228,41 @@ __device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* 
     }
 }
 
+// TMA flavour of stage_in: the 16-byte aligned span [first & ~3, (first+count) & ~3) travels as ONE bulk copy issued by the
+// calling thread (completion on `bar`); tma_span_bytes() is what the caller adds to the barrier's expected byte count.
+// The <= 3 elements behind the span are plain loads (stage_in_tail, any 3 threads).
+__device__ __forceinline__ uint32_t tma_span_bytes(int64_t first, int count) {
+    return (uint32_t)((((first + count) & ~(int64_t)3) - (first & ~(int64_t)3)) * 4);
+}
+__device__ __forceinline__ void tma_stage_in(float* dst, const float* src, int64_t first, int count, uint64_t* bar) {
+    const uint32_t bytes = tma_span_bytes(first, count);
+    if (bytes) bulk_g2s(dst, src + (first & ~(int64_t)3), bytes, bar);
+}
+__device__ __forceinline__ void stage_in_tail(float* dst, const float* src, int64_t first, int count, int k /*0..2*/) {
+    const int64_t last = first + count;
+    const int64_t e = (last & ~(int64_t)3) + k;
+    if (e < last && e >= first) dst[e - (first & ~(int64_t)3)] = ld_stream(src + e);
+}
+// TMA flavour of stage_out: aligned body [roundup4(first), rounddown4(last)) as one bulk store by the calling thread
+__device__ __forceinline__ void tma_stage_out(float* dst, const float* src_smem, int64_t first, int count) {
+    const int64_t last = first + count;
+    const int64_t body0 = (first + 3) & ~(int64_t)3, body1 = last & ~(int64_t)3;
+    if (body1 > body0) bulk_s2g(dst + body0, src_smem + (body0 - (first & ~(int64_t)3)), (uint32_t)((body1 - body0) * 4));
+}
+// head [first, roundup4(first)) and tail [rounddown4(last), last) of an output range: k = 0..5 (any 6 threads)
+__device__ __forceinline__ void stage_out_edges(float* dst, const float* src_smem, int64_t first, int count, int k) {
+    const int64_t last = first + count;
+    const int64_t first_al = first & ~(int64_t)3;
+    const int64_t body0 = (first + 3) & ~(int64_t)3, body1 = last & ~(int64_t)3;
+    if (body1 > body0) {
+        const int64_t e = k < 3 ? first + k : body1 + (k - 3);
+        const bool ok = k < 3 ? e < body0 : e < last;
+        if (ok) st_stream(dst + e, src_smem[e - first_al]);
+    } else {  // no aligned body: fewer than 8 elements in total
+        for (int64_t e = first + k; e < last; e += 6) st_stream(dst + e, src_smem[e - first_al]);
+    }
+}
+
 // block-wide: lowest start / highest end / sum of counts over the tile's non-empty rays
 struct TileRange {
     int lo, hi, total;
@@ -260,18 +295,21 @@ __device__ __forceinline__ TileRange tile_range(int start, int n, int* red /* 3*
     return r;
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(kTileRays) composite_fwd_tile_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
     float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays, int cap) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int red[24];
+    __shared__ __align__(8) uint64_t bar;
     float* s_alpha = smem;                 // cap+4
     float* s_z = s_alpha + (cap + 4);      // cap+4
     float* s_rgb = s_z + (cap + 4);        // 3*cap+4
-    float* s_out = s_rgb + (3 * cap + 4);  // 6*kTileRays: per-ray outputs, written back coalesced
+    float* s_out = s_rgb + (3 * cap + 4);  // 3*kTileRays: per-ray colours, written back coalesced
 
     const int tid = threadIdx.x;
+    if (TMA && tid == 0) mbar_init(&bar, 1);
     const int64_t ray0 = (int64_t)blockIdx.x * kTileRays;
     const int64_t ray = ray0 + tid;
     int start = 0, n = 0;
@@ -286,10 +324,27 @@ __global__ void __launch_bounds__(kTileRays) composite_fwd_tile_kernel(
     const float* pc = rgb;
     int64_t ia = start, ic = 3 * (int64_t)start;
     if (staged) {
-        stage_in(s_alpha, alpha, tr.lo, count, tid, kTileRays);
-        stage_in(s_z, z, tr.lo, count, tid, kTileRays);
-        stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
-        __syncthreads();
+        if (TMA) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar, 2 * tma_span_bytes(tr.lo, count) + tma_span_bytes(3 * (int64_t)tr.lo, 3 * count));
+                tma_stage_in(s_alpha, alpha, tr.lo, count, &bar);
+                tma_stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, &bar);
+                tma_stage_in(s_z, z, tr.lo, count, &bar);
+            } else if (tid >= 32 && tid < 35) {
+                stage_in_tail(s_alpha, alpha, tr.lo, count, tid - 32);
+            } else if (tid >= 64 && tid < 67) {
+                stage_in_tail(s_z, z, tr.lo, count, tid - 64);
+            } else if (tid >= 96 && tid < 99) {
+                stage_in_tail(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid - 96);
+            }
+            __syncthreads();
+            mbar_wait(&bar, 0);
+        } else {
+            stage_in(s_alpha, alpha, tr.lo, count, tid, kTileRays);
+            stage_in(s_z, z, tr.lo, count, tid, kTileRays);
+            stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
+            __syncthreads();
+        }
         pa = s_alpha;
         pz = s_z;
         pc = s_rgb;
@@ -324,6 +379,7 @@ __global__ void __launch_bounds__(kTileRays) composite_fwd_tile_kernel(
     }
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
@@ -335,8 +391,10 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
     float* s_rgb = s_z + (cap + 4);        // 3*cap+4 (becomes d_rgb)
     float* s_T = s_rgb + (3 * cap + 4);    // cap+4
     float* s_g = s_T + (cap + 4);          // 3*kTileRays staged g_rgb
+    __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
+    if (TMA && tid == 0) mbar_init(&bar, 1);
     const int64_t ray0 = (int64_t)blockIdx.x * kTileRays;
     const int64_t ray = ray0 + tid;
     int start = 0, n = 0;
@@ -356,10 +414,27 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
     }
 
     if (staged) {
-        stage_in(s_alpha, alpha, tr.lo, count, tid, kTileRays);
-        stage_in(s_z, z, tr.lo, count, tid, kTileRays);
-        stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
-        __syncthreads();
+        if (TMA) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar, 2 * tma_span_bytes(tr.lo, count) + tma_span_bytes(3 * (int64_t)tr.lo, 3 * count));
+                tma_stage_in(s_alpha, alpha, tr.lo, count, &bar);
+                tma_stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, &bar);
+                tma_stage_in(s_z, z, tr.lo, count, &bar);
+            } else if (tid >= 32 && tid < 35) {
+                stage_in_tail(s_alpha, alpha, tr.lo, count, tid - 32);
+            } else if (tid >= 64 && tid < 67) {
+                stage_in_tail(s_z, z, tr.lo, count, tid - 64);
+            } else if (tid >= 96 && tid < 99) {
+                stage_in_tail(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid - 96);
+            }
+            __syncthreads();
+            mbar_wait(&bar, 0);
+        } else {
+            stage_in(s_alpha, alpha, tr.lo, count, tid, kTileRays);
+            stage_in(s_z, z, tr.lo, count, tid, kTileRays);
+            stage_in(s_rgb, rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
+            __syncthreads();
+        }
         const int ia = start - (tr.lo & ~3);
         const int ic = (int)(3 * (int64_t)start - ((3 * (int64_t)tr.lo) & ~(int64_t)3));
         const float gr = s_g[3 * tid], gg = s_g[3 * tid + 1], gb = s_g[3 * tid + 2];
@@ -382,10 +457,28 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
             s_z[ia + i] = gd * w;
             R = fmaf(1.f - a, R, a * gi);
         }
-        __syncthreads();
-        stage_out(d_alpha, s_alpha, tr.lo, count, tid, kTileRays);
-        stage_out(d_rgb, s_rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
-        if (d_z) stage_out(d_z, s_z, tr.lo, count, tid, kTileRays);
+        if (TMA) {
+            fence_proxy_async();  // make this thread's shared-memory writes visible to the bulk-copy engine
+            __syncthreads();
+            if (tid == 0) {
+                tma_stage_out(d_alpha, s_alpha, tr.lo, count);
+                tma_stage_out(d_rgb, s_rgb, 3 * (int64_t)tr.lo, 3 * count);
+                if (d_z) tma_stage_out(d_z, s_z, tr.lo, count);
+                bulk_commit();
+                bulk_wait_read_all();  // shared memory must stay alive until the engine has read it
+            } else if (tid >= 32 && tid < 38) {
+                stage_out_edges(d_alpha, s_alpha, tr.lo, count, tid - 32);
+            } else if (tid >= 64 && tid < 70) {
+                stage_out_edges(d_rgb, s_rgb, 3 * (int64_t)tr.lo, 3 * count, tid - 64);
+            } else if (tid >= 96 && tid < 102) {
+                if (d_z) stage_out_edges(d_z, s_z, tr.lo, count, tid - 96);
+            }
+        } else {
+            __syncthreads();
+            stage_out(d_alpha, s_alpha, tr.lo, count, tid, kTileRays);
+            stage_out(d_rgb, s_rgb, 3 * (int64_t)tr.lo, 3 * count, tid, kTileRays);
+            if (d_z) stage_out(d_z, s_z, tr.lo, count, tid, kTileRays);
+        }
     } else {
         __syncthreads();
         const float gr = s_g[3 * tid], gg = s_g[3 * tid + 1], gb = s_g[3 * tid + 2];
@@ -413,10 +506,10 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// shared-memory capacity (in samples) of a tile: 1.5x the mean load of 256 rays, at least 256
+// shared-memory capacity (in samples) of a tile: 1.25x the mean load of 256 rays, at least 256
 static inline int tile_cap(int64_t n_rays, int64_t n_samples) {
     double mean = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
-    int cap = (int)(mean * kTileRays * 1.5) + 64;
+    int cap = (int)(mean * kTileRays * 1.25) + 64;
     cap = (cap + 3) & ~3;
     if (cap < 256) cap = 256;
     return cap;
@@ -428,17 +521,18 @@ using namespace vs;
 
 extern "C" {
 
-// mode: 0 = auto, 1 = force tile family, 2 = force scan family (W from mean), 3 = scan with W=8 (A/B measurements)
+// mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = scan family (W from mean), 3 = scan with W=8, 4 = tile family with
+// LDG/STS staging (3 and 4 exist for A/B measurements)
 int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, float* out_rgb, float* out_depth,
                      float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples, int mode,
                      void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 3);
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 4);
     if (n_rays == 0) return VS_OK;
     VS_CHECK_ARG(se && out_rgb && out_depth && out_acc && out_bgT);
     VS_CHECK_ARG(n_samples == 0 || (alpha && rgb && z));
     cudaStream_t st = (cudaStream_t)stream;
     const double mean = (double)n_samples / (double)n_rays;
-    bool tile = (mode == 1) || (mode == 0 && mean <= 8.0);
+    bool tile = (mode == 1) || (mode == 4) || (mode == 0 && mean <= 8.0);
     if (tile && !(aligned16(alpha) && aligned16(rgb) && aligned16(z))) tile = false;
     if (tile) {
         const int cap = tile_cap(n_rays, n_samples);
@@ -446,10 +540,11 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
         if (smem > 200 * 1024) {
             tile = false;
         } else {
-            cudaError_t e = cudaFuncSetAttribute(composite_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern = mode == 4 ? composite_fwd_tile_kernel<false> : composite_fwd_tile_kernel<true>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            composite_fwd_tile_kernel<<<(unsigned)div_up(n_rays, kTileRays), kTileRays, smem, st>>>(
-                se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays, cap);
+            kern<<<(unsigned)div_up(n_rays, kTileRays), kTileRays, smem, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w,
+                                                                              out_T, n_rays, cap);
             return launched(1);
         }
     }
@@ -473,12 +568,12 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
 int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, const float* g_rgb, const float* g_depth,
                      const float* g_acc, const float* g_bgT, float* d_alpha, float* d_rgb, float* d_z, int64_t n_rays, int64_t n_samples,
                      int mode, void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 3);
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 4);
     if (n_rays == 0 || n_samples == 0) return VS_OK;
     VS_CHECK_ARG(se && alpha && rgb && z && g_rgb && g_depth && g_acc && g_bgT && d_alpha && d_rgb);
     cudaStream_t st = (cudaStream_t)stream;
     const double mean = (double)n_samples / (double)n_rays;
-    bool tile = (mode == 1) || (mode == 0 && mean <= 8.0);
+    bool tile = (mode == 1) || (mode == 4) || (mode == 0 && mean <= 8.0);
     if (tile && !(aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z))))
         tile = false;
     if (tile) {
@@ -487,10 +582,11 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
         if (smem > 200 * 1024) {
             tile = false;
         } else {
-            cudaError_t e = cudaFuncSetAttribute(composite_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern = mode == 4 ? composite_bwd_tile_kernel<false> : composite_bwd_tile_kernel<true>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            composite_bwd_tile_kernel<<<(unsigned)div_up(n_rays, kTileRays), kTileRays, smem, st>>>(
-                se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays, cap);
+            kern<<<(unsigned)div_up(n_rays, kTileRays), kTileRays, smem, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb,
+                                                                              d_z, n_rays, cap);
             return launched(1);
         }
     }

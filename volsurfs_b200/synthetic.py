@@ -107,3 +107,64 @@ def nerf_packets(n_rays: int, seed_offset: int = 3, max_per_ray: int = 1024, p_e
 def composite_bytes(n_rays: int, n_samples: int) -> int:
     """Algorithmic HBM bytes of fused compositing fwd+bwd: sum_r (64 + 56 s_r)."""
     return 64 * n_rays + 56 * n_samples
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# geometry: nested "kitten-like" shells and pinhole camera rays (config C2 / C5)
+# ---------------------------------------------------------------------------------------------------------------------
+def shell_meshes(K: int = 5, n_lat: int = 224, n_lon: int = 224, r_base: float = 0.30, offset: float = 0.01, seed_offset: int = 40):
+    """K nested star-shaped shells: UV-sphere topology (2*n_lon*(n_lat-1) triangles, ~100k at 224x224), radius field
+    r0(theta,phi) = r_base*(1 + 0.25*sum_m a_m f_m(theta,phi)) with fixed-seed low-frequency lobes, shell k at
+    r0 + k*offset (k = 0 innermost ... K-1 outermost), as produced by offset-SDF level sets
+    (reference utils/mesh_extraction.py:375-405).  Returns a list of (vertices [V,3] f32, faces [F,3] i32)."""
+    rng = np.random.default_rng(BASE_SEED + seed_offset)
+    amps = rng.uniform(-1, 1, 4)
+    phases = rng.uniform(0, 2 * np.pi, 4)
+    theta = np.linspace(0.0, np.pi, n_lat + 1)[1:-1]                 # interior latitudes
+    phi = np.linspace(0.0, 2 * np.pi, n_lon, endpoint=False)
+    T, P = np.meshgrid(theta, phi, indexing="ij")
+
+    def lobes(t, p):
+        return (amps[0] * np.sin(t) * np.cos(p + phases[0]) + amps[1] * np.sin(2 * t) * np.sin(2 * p + phases[1])
+                + amps[2] * np.sin(t) ** 2 * np.cos(3 * p + phases[2]) + amps[3] * np.cos(2 * t + phases[3]))
+
+    r_grid = r_base * (1 + 0.25 * 0.5 * lobes(T, P))
+    r_north = r_base * (1 + 0.25 * 0.5 * lobes(0.0, 0.0))
+    r_south = r_base * (1 + 0.25 * 0.5 * lobes(np.pi, 0.0))
+    dirs = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3)
+    rows, cols = n_lat - 1, n_lon
+    idx = np.arange(rows * cols).reshape(rows, cols)
+    nxt = np.roll(idx, -1, axis=1)
+    quads_a = np.stack([idx[:-1], idx[1:], nxt[1:]], -1).reshape(-1, 3)
+    quads_b = np.stack([idx[:-1], nxt[1:], nxt[:-1]], -1).reshape(-1, 3)
+    north, south = rows * cols, rows * cols + 1
+    cap_n = np.stack([np.full(cols, north), idx[0], nxt[0]], -1)
+    cap_s = np.stack([np.full(cols, south), nxt[-1], idx[-1]], -1)
+    faces = np.concatenate([quads_a, quads_b, cap_n, cap_s]).astype(np.int32)
+    meshes = []
+    for k in range(K):
+        rk = (r_grid + k * offset).reshape(-1, 1)
+        v = np.concatenate([dirs * rk, [[0, 0, r_north + k * offset]], [[0, 0, -(r_south + k * offset)]]]).astype(np.float32)
+        meshes.append((np.ascontiguousarray(v), faces.copy()))
+    return meshes
+
+
+def camera_rays(height: int = 800, width: int = 800, fov_deg: float = 40.0, radius: float = 1.5, azimuth_deg: float = 30.0,
+                elevation_deg: float = 20.0, shuffle_seed=None):
+    """Pinhole camera on an orbit looking at the origin; rays in scanline order, directions normalised
+    (mvdatasets/utils/raycasting.py:167-247 conventions).  Returns (rays_o [H*W,3], rays_d [H*W,3]) float32 tensors."""
+    az, el = np.deg2rad(azimuth_deg), np.deg2rad(elevation_deg)
+    eye = radius * np.array([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)])
+    fwd = -eye / np.linalg.norm(eye)
+    right = np.cross(fwd, [0, 0, 1.0])
+    right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    f = 0.5 * width / np.tan(0.5 * np.deg2rad(fov_deg))
+    j, i = np.meshgrid(np.arange(height) + 0.5, np.arange(width) + 0.5, indexing="ij")
+    d = ((i - 0.5 * width)[..., None] * right + (0.5 * height - j)[..., None] * up + f * fwd).reshape(-1, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = np.broadcast_to(eye, d.shape)
+    if shuffle_seed is not None:
+        perm = np.random.default_rng(shuffle_seed).permutation(d.shape[0])
+        d = d[perm]
+    return torch.from_numpy(np.ascontiguousarray(o, dtype=np.float32)), torch.from_numpy(np.ascontiguousarray(d, dtype=np.float32))
