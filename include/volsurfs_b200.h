@@ -119,6 +119,37 @@ int vs_pack_hits_scatter(const float* rays_o, const float* rays_d, const float* 
                          float* samples_3d_out, float* samples_dirs_out, float* samples_z_out, int32_t* layer_out, int32_t* tri_out,
                          float* uv_out, int64_t n_rays, void* stream);
 
+/* ---- K-layer shell intersection ------------------------------------------------------------------------------------
+ * Replaces, for this path, raytracelib's create_raytracer + RayTracer.trace called once per mesh
+ * (submodules/raytracelib/src/raytracer.cu:23-69, src/bvh.cu:186-263,420-469, raytracelib/raytracer.py:7-113;
+ * call site volsurfs_py/methods/volsurfs.py:476-485). */
+
+/* Build the per-layer BVHs on the host from HOST arrays (verts[k]: float32 [n_verts[k],3], faces[k]: int32 [n_faces[k],3];
+ * mesh 0 = innermost) and upload them to the current device.  The handle owns device memory.  Synchronous. */
+int vs_shells_build(int K, const float* const* verts, const int64_t* n_verts, const int32_t* const* faces, const int64_t* n_faces,
+                    void** handle_out);
+int vs_shells_free(void* handle);
+int vs_shells_num_layers(const void* handle);
+int vs_shells_info(const void* handle, int layer, int64_t* n_nodes, int64_t* n_tris);
+/* 1 if a traversal stack ever overflowed since the build (results unreliable); synchronises the device */
+int vs_shells_overflowed(const void* handle);
+
+/* Nearest hit (t > 0, first along the ray) with layers [layer_first, layer_first+layer_count) in one launch.
+ * Outputs layer-major [layer_count, n_rays]: depth (1e6 on a miss, include/raytracing/common.h:21), original face index
+ * (-1 on a miss), barycentric u and v of triangle.cuh:53-55 (0 on a miss). */
+int vs_shells_trace(const void* handle, const float* rays_o, const float* rays_d, int64_t n_rays, int layer_first, int layer_count,
+                    float* depth_out, int32_t* tri_out, float* u_out, float* v_out, void* stream);
+
+/* The reference's per-mesh result buffers (bvh.cu:440-468) from one layer's compact record: positions = o + depth*d,
+ * unit face normals, triangles_mesh_id / triangles_id (int64), barycentric (1-u-v, u, v). */
+int vs_shells_expand(const void* handle, int layer, const float* rays_o, const float* rays_d, const float* depth, const int32_t* tri,
+                     const float* u, const float* v, int64_t n_rays, float* positions, float* normals, int64_t* tri_mesh_id,
+                     int64_t* tri_id, float* barycentric, void* stream);
+
+/* Unit face normals of packed hits (volsurfs.py:503: surfs_normals[hits, i] = normals[hits]).  n_valid_dev may be NULL. */
+int vs_shells_sample_normals(const void* handle, const int32_t* layer_of, const int32_t* tri, int64_t n_samples,
+                             const int64_t* n_valid_dev, float* normals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

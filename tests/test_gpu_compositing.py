@@ -206,15 +206,15 @@ def test_reference_fp32_error_scale():
     lay = hit.shape[1] - 1 - j
 
     def dense_grads(dtype):
-        a = d["alpha"].to(dtype).requires_grad_(True)
-        c = d["rgb"].to(dtype).requires_grad_(True)
+        a = d["alpha"].to(dtype).clone().requires_grad_(True)
+        c = d["rgb"].to(dtype).clone().requires_grad_(True)
         out = oc.dense_composite_torch(a, c)
         ((out["rgb_fg"] * d["g_rgb"].to(dtype)).sum() + (out["bg_transmittance"] * d["g_bgT"].to(dtype)).sum()).backward()
-        return a.grad.numpy()[ray, lay, 0], c.grad.numpy()[ray, lay]
+        return a.grad.detach().numpy()[ray, lay, 0], c.grad.detach().numpy()[ray, lay]
 
     da64, dc64 = dense_grads(torch.float64)
     da32, dc32 = dense_grads(torch.float32)
-    se, a, c, z = pack_dense(d["hit"], d["alpha"], d["rgb"], d["z"])
+    se, a, c, z = pack_dense(d["hit"], d["alpha"].detach(), d["rgb"].detach(), d["z"])
     N = se.shape[0]
     g = {"g_rgb": d["g_rgb"], "g_depth": torch.zeros(N, 1), "g_acc": torch.zeros(N, 1), "g_bgT": d["g_bgT"]}
     _, bwd = _run(se, a, c, z, g, 0, need_dz=False)

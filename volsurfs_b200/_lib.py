@@ -38,6 +38,14 @@ SIGNATURES = {
     "vs_compact_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "vs_pack_hits_offsets": (c_int, [_P, c_int, c_float, _I64, _P, _P, _P]),
     "vs_pack_hits_scatter": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_float] + [_P] * 8 + [_I64, _P]),
+    "vs_shells_build": (c_int, [c_int, _P, _P, _P, _P, _P]),
+    "vs_shells_free": (c_int, [_P]),
+    "vs_shells_num_layers": (c_int, [_P]),
+    "vs_shells_info": (c_int, [_P, c_int, _P, _P]),
+    "vs_shells_overflowed": (c_int, [_P]),
+    "vs_shells_trace": (c_int, [_P, _P, _P, _I64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "vs_shells_expand": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "vs_shells_sample_normals": (c_int, [_P, _P, _P, _I64, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,643 @@
+// volsurfs_b200 — K-layer shell intersector: nearest hit of every ray against each of K nested meshes in ONE launch.
+//
+// Replaces, for the per-ray rendering path, the K python-loop calls of raytracelib's RayTracer.trace
+// (volsurfs_py/methods/volsurfs.py:476-485 -> raytracelib/raytracer.py:35-113 -> src/bvh.cu:186-263,420-469): there, one thread
+// per ray walks a 4-ary median-split BVH with 32-byte AoS nodes and 56-byte AoS triangles out of global memory, one mesh per
+// launch, with a device synchronisation and a host-visible any_hit flag after every mesh.
+//
+// Here:
+//   * the BVH of each layer is built on the host with a binned surface-area heuristic, collapsed to 4-wide nodes whose four
+//     child boxes sit in one 128-byte line (SoA: 6 x float4 + 4 child refs), emitted in breadth-first order;
+//   * one launch covers all (layer, ray) pairs: blockIdx.y is the layer, a CTA walks `kRaysPerBlock` consecutive rays;
+//   * the top of the layer's tree (first kTopNodes nodes = 4 levels) is staged into shared memory by one TMA bulk copy
+//     (cp.async.bulk + mbarrier) when the CTA starts, so the always-visited upper levels never leave the SM;
+//   * triangles are 3 x float4 (vertex + original face index), read with 16-byte loads.
+//
+// Parity contract (bit-exact hits): the ray/triangle arithmetic is the reference's (include/raytracing/triangle.cuh:42-70) in
+// IEEE fp32 with no contraction and Eigen's evaluation order, identical to oracle/raytrace_oracle.c:
+//   n = (b-a)x(c-a), q = (o-a)xd, D = 1/(d.n), u = D*-(q.(c-a)), v = D*(q.(b-a)), t = D*-(n.(o-a)),
+//   dot(x,y) = x0*y0 + (x1*y1 + x2*y2);  miss if u<0 || u>1 || v<0 || u+v>1 || t<0;  accept if t > 0 && t < best.
+// The nearest hit does not depend on the BVH as long as no box containing the winning triangle is culled, so child boxes are
+// padded by a relative epsilon and children are visited whenever t_near <= best (ties in t resolve to the lowest original
+// face index, which is what a brute-force pass in index order returns).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "vs_common.cuh"
+
+namespace vs {
+
+constexpr float kMaxDist = 1e6f;  // include/raytracing/common.h:21
+constexpr int kTraceThreads = 128;
+constexpr int kRaysPerThread = 4;
+constexpr int kRaysPerBlock = kTraceThreads * kRaysPerThread;
+constexpr int kTopNodes = 85;  // 1 + 4 + 16 + 64 nodes = first four levels of a full 4-ary tree (10.6 KB)
+constexpr int kStack = 48;
+constexpr int kLeafMax = 4;
+
+struct __align__(16) Node4 {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t child[4];  // > 0 inner node index, 0 empty slot, < 0 leaf: ~child = first_tri * 8 + (count - 1)
+    int32_t pad[4];
+};
+static_assert(sizeof(Node4) == 128, "Node4 must be one 128-byte line");
+
+struct Layer {
+    Node4* nodes = nullptr;      // device
+    float4* tris = nullptr;      // device, 3 float4 per triangle in BVH order; .w of the first = original face index
+    int32_t* orig_to_bvh = nullptr;  // device
+    int32_t n_nodes = 0;
+    int64_t n_tris = 0;
+};
+
+struct Shells {
+    int K = 0;
+    std::vector<Layer> layers;
+    Layer* layers_dev = nullptr;  // device copy of the table
+    int* overflow_dev = nullptr;  // set to 1 if a traversal stack ever overflowed
+};
+
+// =====================================================================================================================
+// host: binned-SAH BVH2 -> BVH4 collapse -> BFS layout
+// =====================================================================================================================
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        for (int k = 0; k < 3; ++k) lo[k] = FLT_MAX, hi[k] = -FLT_MAX;
+    }
+    void grow(const float* p) {
+        for (int k = 0; k < 3; ++k) lo[k] = std::min(lo[k], p[k]), hi[k] = std::max(hi[k], p[k]);
+    }
+    void grow(const Box& b) {
+        for (int k = 0; k < 3; ++k) lo[k] = std::min(lo[k], b.lo[k]), hi[k] = std::max(hi[k], b.hi[k]);
+    }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct B2Node {
+    Box box;
+    int left = -1, right = -1;  // children (inner) ...
+    int first = 0, count = 0;   // ... or primitive range (leaf, count > 0)
+};
+
+struct Builder {
+    const float* verts;
+    const int32_t* faces;
+    int64_t n_faces;
+    std::vector<Box> pbox;
+    std::vector<float> pcen;  // 3 per prim
+    std::vector<int32_t> order;
+    std::vector<B2Node> nodes;
+
+    void prim_setup() {
+        pbox.resize(n_faces);
+        pcen.resize(3 * n_faces);
+        order.resize(n_faces);
+        for (int64_t i = 0; i < n_faces; ++i) {
+            Box b;
+            b.reset();
+            for (int c = 0; c < 3; ++c) b.grow(verts + 3 * (int64_t)faces[3 * i + c]);
+            pbox[i] = b;
+            for (int k = 0; k < 3; ++k) pcen[3 * i + k] = 0.5f * (b.lo[k] + b.hi[k]);
+            order[i] = (int32_t)i;
+        }
+    }
+
+    void build() {
+        prim_setup();
+        nodes.reserve(2 * n_faces / 2 + 16);
+        nodes.emplace_back();
+        struct Item {
+            int node;
+            int64_t lo, hi;
+        };
+        std::vector<Item> stack;
+        stack.push_back({0, 0, n_faces});
+        constexpr int NB = 16;
+        while (!stack.empty()) {
+            Item it = stack.back();
+            stack.pop_back();
+            Box nb, cb;
+            nb.reset();
+            cb.reset();
+            for (int64_t i = it.lo; i < it.hi; ++i) {
+                nb.grow(pbox[order[i]]);
+                cb.grow(&pcen[3 * (int64_t)order[i]]);
+            }
+            nodes[it.node].box = nb;
+            const int64_t cnt = it.hi - it.lo;
+            if (cnt <= kLeafMax) {
+                nodes[it.node].first = (int)it.lo;
+                nodes[it.node].count = (int)cnt;
+                continue;
+            }
+            int axis = 0;
+            float ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
+            if (ext[1] > ext[axis]) axis = 1;
+            if (ext[2] > ext[axis]) axis = 2;
+            int64_t mid = -1;
+            if (ext[axis] > 0.f) {
+                Box bb[NB];
+                int bc[NB];
+                for (int b = 0; b < NB; ++b) bb[b].reset(), bc[b] = 0;
+                const float scale = NB / ext[axis];
+                auto bin_of = [&](int32_t p) {
+                    int b = (int)((pcen[3 * (int64_t)p + axis] - cb.lo[axis]) * scale);
+                    return std::min(std::max(b, 0), NB - 1);
+                };
+                for (int64_t i = it.lo; i < it.hi; ++i) {
+                    int b = bin_of(order[i]);
+                    bb[b].grow(pbox[order[i]]);
+                    bc[b]++;
+                }
+                float right_area[NB];
+                int right_cnt[NB];
+                Box acc;
+                acc.reset();
+                int c = 0;
+                for (int b = NB - 1; b > 0; --b) {
+                    acc.grow(bb[b]);
+                    c += bc[b];
+                    right_area[b] = acc.area();
+                    right_cnt[b] = c;
+                }
+                acc.reset();
+                c = 0;
+                float best = FLT_MAX;
+                int best_split = -1;
+                for (int b = 0; b < NB - 1; ++b) {
+                    acc.grow(bb[b]);
+                    c += bc[b];
+                    if (c == 0 || right_cnt[b + 1] == 0) continue;
+                    float cost = acc.area() * c + right_area[b + 1] * right_cnt[b + 1];
+                    if (cost < best) best = cost, best_split = b;
+                }
+                if (best_split >= 0) {
+                    auto first_right = std::partition(order.begin() + it.lo, order.begin() + it.hi,
+                                                      [&](int32_t p) { return bin_of(p) <= best_split; });
+                    mid = first_right - order.begin();
+                }
+            }
+            if (mid <= it.lo || mid >= it.hi) {  // degenerate: median split in index order along the axis
+                mid = it.lo + cnt / 2;
+                std::nth_element(order.begin() + it.lo, order.begin() + mid, order.begin() + it.hi, [&](int32_t a, int32_t b) {
+                    return pcen[3 * (int64_t)a + axis] < pcen[3 * (int64_t)b + axis];
+                });
+            }
+            int l = (int)nodes.size();
+            nodes.emplace_back();
+            nodes.emplace_back();
+            nodes[it.node].left = l;
+            nodes[it.node].right = l + 1;
+            stack.push_back({l, it.lo, mid});
+            stack.push_back({l + 1, mid, it.hi});
+        }
+    }
+};
+
+// collapse + BFS numbering. Returns wide nodes and the triangle order.
+static void collapse_bfs(const Builder& B, std::vector<Node4>& out) {
+    struct Wide {
+        int kids[4];
+        int n;
+    };
+    // BFS over "wide" nodes: each is identified by the BVH2 node it was grown from
+    std::vector<int> queue;   // BVH2 root of each wide node, in BFS order
+    std::vector<Wide> wides;
+    queue.push_back(0);
+    size_t head = 0;
+    std::vector<int> wide_index_of(B.nodes.size(), -1);
+    while (head < queue.size()) {
+        int root = queue[head];
+        wide_index_of[root] = (int)head;
+        ++head;
+        Wide w;
+        w.n = 0;
+        const B2Node& r = B.nodes[root];
+        if (r.count > 0) {  // a single-leaf tree: the root itself becomes the only child
+            w.kids[w.n++] = root;
+        } else {
+            w.kids[w.n++] = r.left;
+            w.kids[w.n++] = r.right;
+            while (w.n < 4) {
+                int pick = -1;
+                float best = -1.f;
+                for (int i = 0; i < w.n; ++i) {
+                    const B2Node& c = B.nodes[w.kids[i]];
+                    if (c.count == 0 && c.box.area() > best) best = c.box.area(), pick = i;
+                }
+                if (pick < 0) break;
+                const B2Node& c = B.nodes[w.kids[pick]];
+                w.kids[pick] = c.left;
+                w.kids[w.n++] = c.right;
+            }
+        }
+        for (int i = 0; i < w.n; ++i)
+            if (B.nodes[w.kids[i]].count == 0) queue.push_back(w.kids[i]);
+        wides.push_back(w);
+    }
+    out.resize(wides.size());
+    for (size_t wi = 0; wi < wides.size(); ++wi) {
+        Node4 nd;
+        std::memset(&nd, 0, sizeof(nd));
+        for (int i = 0; i < 4; ++i) {
+            if (i < wides[wi].n) {
+                const B2Node& c = B.nodes[wides[wi].kids[i]];
+                float pad[3];
+                for (int k = 0; k < 3; ++k) {
+                    float m = std::max(std::fabs(c.box.lo[k]), std::fabs(c.box.hi[k]));
+                    pad[k] = 4e-6f * m + 1e-7f * (c.box.hi[k] - c.box.lo[k]) + 1e-30f;
+                }
+                nd.lox[i] = c.box.lo[0] - pad[0];
+                nd.loy[i] = c.box.lo[1] - pad[1];
+                nd.loz[i] = c.box.lo[2] - pad[2];
+                nd.hix[i] = c.box.hi[0] + pad[0];
+                nd.hiy[i] = c.box.hi[1] + pad[1];
+                nd.hiz[i] = c.box.hi[2] + pad[2];
+                if (c.count > 0) nd.child[i] = ~(c.first * 8 + (c.count - 1));
+                else nd.child[i] = wide_index_of[wides[wi].kids[i]];
+            } else {
+                nd.lox[i] = nd.loy[i] = nd.loz[i] = FLT_MAX;
+                nd.hix[i] = nd.hiy[i] = nd.hiz[i] = -FLT_MAX;
+                nd.child[i] = 0;
+            }
+        }
+        out[wi] = nd;
+    }
+}
+
+// =====================================================================================================================
+// device
+// =====================================================================================================================
+__device__ __forceinline__ float dot_rn(float x0, float x1, float x2, float y0, float y1, float y2) {
+    return __fadd_rn(__fmul_rn(x0, y0), __fadd_rn(__fmul_rn(x1, y1), __fmul_rn(x2, y2)));
+}
+
+// triangle.cuh:42-70 in oracle arithmetic; returns is_hit, leaves t/u/v as computed (t untouched on a miss)
+__device__ __forceinline__ bool tri_test(const float4 A, const float4 Bv, const float4 C, float ox, float oy, float oz, float dx, float dy,
+                                         float dz, float& t, float& u, float& v) {
+    const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
+    const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
+    const float rx = __fsub_rn(ox, A.x), ry = __fsub_rn(oy, A.y), rz = __fsub_rn(oz, A.z);
+    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    const float qx = __fsub_rn(__fmul_rn(ry, dz), __fmul_rn(rz, dy));
+    const float qy = __fsub_rn(__fmul_rn(rz, dx), __fmul_rn(rx, dz));
+    const float qz = __fsub_rn(__fmul_rn(rx, dy), __fmul_rn(ry, dx));
+    const float D = __fdiv_rn(1.0f, dot_rn(dx, dy, dz, nx, ny, nz));
+    u = __fmul_rn(D, -dot_rn(qx, qy, qz, e2x, e2y, e2z));
+    v = __fmul_rn(D, dot_rn(qx, qy, qz, e1x, e1y, e1z));
+    t = __fmul_rn(D, -dot_rn(nx, ny, nz, rx, ry, rz));
+    return !(u < 0.0f || u > 1.0f || v < 0.0f || __fadd_rn(u, v) > 1.0f || t < 0.0f);
+}
+
+__device__ __forceinline__ void cswap_desc(float& ka, int& va, float& kb, int& vb) {  // larger key first
+    if (ka < kb) {
+        float tk = ka;
+        ka = kb;
+        kb = tk;
+        int tv = va;
+        va = vb;
+        vb = tv;
+    }
+}
+
+__global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer* __restrict__ layers, int layer_first,
+                                                                     const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                     int64_t n_rays, float* __restrict__ depth_out,
+                                                                     int32_t* __restrict__ tri_out, float* __restrict__ u_out,
+                                                                     float* __restrict__ v_out, int* __restrict__ overflow) {
+    __shared__ __align__(128) Node4 s_top[kTopNodes];
+    __shared__ __align__(8) uint64_t bar;
+    const int layer = layer_first + blockIdx.y;
+    const Layer L = layers[layer];
+    const int n_top = min(L.n_nodes, kTopNodes);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_arrive_expect_tx(&bar, (uint32_t)(n_top * sizeof(Node4)));
+        bulk_g2s(s_top, L.nodes, (uint32_t)(n_top * sizeof(Node4)), &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const Node4* __restrict__ gnodes = L.nodes;
+    const float4* __restrict__ tris = L.tris;
+    const int64_t out_base = (int64_t)blockIdx.y * n_rays;  // outputs are [n_layers_traced, n_rays]
+
+    for (int it = 0; it < kRaysPerThread; ++it) {
+        const int64_t r = (int64_t)blockIdx.x * kRaysPerBlock + it * kTraceThreads + threadIdx.x;
+        if (r >= n_rays) break;
+        const float ox = __ldg(rays_o + 3 * r), oy = __ldg(rays_o + 3 * r + 1), oz = __ldg(rays_o + 3 * r + 2);
+        const float dx = __ldg(rays_d + 3 * r), dy = __ldg(rays_d + 3 * r + 1), dz = __ldg(rays_d + 3 * r + 2);
+        const float idx_ = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
+
+        float best_t = kMaxDist, best_u = 0.f, best_v = 0.f;
+        int best_tri = -1;
+
+        int stack_ref[kStack];
+        float stack_t[kStack];
+        int sp = 0;
+        stack_ref[sp] = 0;  // the root is wide node 0
+        stack_t[sp] = -FLT_MAX;
+        ++sp;
+        while (sp > 0) {
+            --sp;
+            const int ref = stack_ref[sp];
+            if (stack_t[sp] > best_t) continue;
+            if (ref < 0) {
+                const int enc = ~ref;
+                const int first = enc >> 3, cnt = (enc & 7) + 1;
+                for (int k = 0; k < cnt; ++k) {
+                    const float4 A = __ldg(tris + 3 * (int64_t)(first + k));
+                    const float4 Bv = __ldg(tris + 3 * (int64_t)(first + k) + 1);
+                    const float4 C = __ldg(tris + 3 * (int64_t)(first + k) + 2);
+                    float t, u, v;
+                    if (tri_test(A, Bv, C, ox, oy, oz, dx, dy, dz, t, u, v)) {
+                        const int oi = __float_as_int(A.w);
+                        if (t > 0.0f && (t < best_t || (t == best_t && best_tri >= 0 && oi < best_tri))) {
+                            best_t = t;
+                            best_u = u;
+                            best_v = v;
+                            best_tri = oi;
+                        }
+                    }
+                }
+                continue;
+            }
+            const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
+            const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
+            const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
+            const float4 hiy = *reinterpret_cast<const float4*>(nd->hiy), hiz = *reinterpret_cast<const float4*>(nd->hiz);
+            const int4 ch = *reinterpret_cast<const int4*>(nd->child);
+            float tn[4];
+            int cr[4] = {ch.x, ch.y, ch.z, ch.w};
+            const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
+            const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float t0x = (lx[i] - ox) * idx_, t1x = (hx[i] - ox) * idx_;
+                const float t0y = (ly[i] - oy) * idy, t1y = (hy[i] - oy) * idy;
+                const float t0z = (lz[i] - oz) * idz, t1z = (hz[i] - oz) * idz;
+                const float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+                const float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+                // padded boxes + slack on the far plane keep the test conservative w.r.t. the triangle arithmetic
+                const bool hit = cr[i] != 0 && tnear <= tfar * 1.0000004f + 1e-30f && tfar >= 0.0f && tnear <= best_t;
+                tn[i] = hit ? tnear : FLT_MAX;
+            }
+            // far -> near so that the nearest child is popped first
+            cswap_desc(tn[0], cr[0], tn[2], cr[2]);
+            cswap_desc(tn[1], cr[1], tn[3], cr[3]);
+            cswap_desc(tn[0], cr[0], tn[1], cr[1]);
+            cswap_desc(tn[2], cr[2], tn[3], cr[3]);
+            cswap_desc(tn[1], cr[1], tn[2], cr[2]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (tn[i] != FLT_MAX) {
+                    if (sp < kStack) {
+                        stack_ref[sp] = cr[i];
+                        stack_t[sp] = tn[i];
+                        ++sp;
+                    } else {
+                        atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
+                    }
+                }
+            }
+        }
+        depth_out[out_base + r] = best_t;
+        tri_out[out_base + r] = best_tri;
+        u_out[out_base + r] = best_u;
+        v_out[out_base + r] = best_v;
+    }
+}
+
+// reference-format outputs of RayTracer.trace(mesh_id) (bvh.cu:440-468, raytracer.py:103-113) from the compact hit record
+__global__ void __launch_bounds__(256) shells_expand_kernel(const Layer* __restrict__ layers, int layer, const float* __restrict__ rays_o,
+                                                            const float* __restrict__ rays_d, const float* __restrict__ depth,
+                                                            const int32_t* __restrict__ tri, const float* __restrict__ u,
+                                                            const float* __restrict__ v, int64_t n_rays, float* __restrict__ positions,
+                                                            float* __restrict__ normals, int64_t* __restrict__ tri_mesh_id,
+                                                            int64_t* __restrict__ tri_id, float* __restrict__ bary) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const Layer L = layers[layer];
+    const float t = depth[r];
+    positions[3 * r] = __fadd_rn(rays_o[3 * r], __fmul_rn(t, rays_d[3 * r]));
+    positions[3 * r + 1] = __fadd_rn(rays_o[3 * r + 1], __fmul_rn(t, rays_d[3 * r + 1]));
+    positions[3 * r + 2] = __fadd_rn(rays_o[3 * r + 2], __fmul_rn(t, rays_d[3 * r + 2]));
+    const int ti = tri[r];
+    if (ti >= 0) {
+        const int64_t p = L.orig_to_bvh[ti];
+        const float4 A = L.tris[3 * p], Bv = L.tris[3 * p + 1], C = L.tris[3 * p + 2];
+        const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
+        const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
+        float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+        float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+        float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+        const float zz = dot_rn(nx, ny, nz, nx, ny, nz);
+        if (zz > 0.0f) {  // Eigen normalized(): v / sqrt(v.v), unchanged for the zero vector
+            const float s = __fsqrt_rn(zz);
+            nx = __fdiv_rn(nx, s);
+            ny = __fdiv_rn(ny, s);
+            nz = __fdiv_rn(nz, s);
+        }
+        normals[3 * r] = nx;
+        normals[3 * r + 1] = ny;
+        normals[3 * r + 2] = nz;
+        tri_mesh_id[r] = 0;
+        tri_id[r] = ti;
+        const float uu = u[r], vv = v[r];
+        bary[3 * r] = __fsub_rn(1.0f, __fadd_rn(uu, vv));
+        bary[3 * r + 1] = uu;
+        bary[3 * r + 2] = vv;
+    } else {
+        normals[3 * r] = normals[3 * r + 1] = normals[3 * r + 2] = 0.f;
+        bary[3 * r] = bary[3 * r + 1] = bary[3 * r + 2] = 0.f;
+        tri_mesh_id[r] = -1;
+        tri_id[r] = -1;
+    }
+}
+
+// per-sample unit face normals for packed hits (appearance stage): normal of triangle `tri[s]` of layer `layer[s]`
+__global__ void __launch_bounds__(256) shells_normals_kernel(const Layer* __restrict__ layers, const int32_t* __restrict__ layer_of,
+                                                             const int32_t* __restrict__ tri, int64_t n_samples,
+                                                             const int64_t* __restrict__ n_valid_dev, float* __restrict__ normals) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_samples) return;
+    if (n_valid_dev != nullptr && s >= *n_valid_dev) return;
+    const Layer L = layers[layer_of[s]];
+    const int64_t p = L.orig_to_bvh[tri[s]];
+    const float4 A = L.tris[3 * p], Bv = L.tris[3 * p + 1], C = L.tris[3 * p + 2];
+    const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
+    const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
+    float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+    float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+    float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    const float zz = dot_rn(nx, ny, nz, nx, ny, nz);
+    if (zz > 0.0f) {
+        const float sq = __fsqrt_rn(zz);
+        nx = __fdiv_rn(nx, sq);
+        ny = __fdiv_rn(ny, sq);
+        nz = __fdiv_rn(nz, sq);
+    }
+    normals[3 * s] = nx;
+    normals[3 * s + 1] = ny;
+    normals[3 * s + 2] = nz;
+}
+
+static void free_layer(Layer& L) {
+    if (L.nodes) cudaFree(L.nodes);
+    if (L.tris) cudaFree(L.tris);
+    if (L.orig_to_bvh) cudaFree(L.orig_to_bvh);
+    L = Layer();
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+// Builds the K per-layer BVHs on the HOST from HOST arrays (like raytracelib's create_raytracer, src/raytracer.cu:23-45, which
+// takes numpy arrays) and uploads them to the current device.  verts[k]: float32 [n_verts[k],3]; faces[k]: int32 [n_faces[k],3].
+// The handle owns device memory; free it with vs_shells_free.  Synchronous (cudaMemcpy).
+int vs_shells_build(int K, const float* const* verts, const int64_t* n_verts, const int32_t* const* faces, const int64_t* n_faces,
+                    void** handle_out) {
+    VS_CHECK_ARG(K > 0 && verts && n_verts && faces && n_faces && handle_out);
+    for (int k = 0; k < K; ++k) {
+        VS_CHECK_ARG(verts[k] && faces[k] && n_verts[k] > 0 && n_faces[k] > 0);
+        if (n_faces[k] >= (1 << 27)) return VS_ERR_UNSUPPORTED;
+        for (int64_t i = 0; i < 3 * n_faces[k]; ++i) VS_CHECK_ARG(faces[k][i] >= 0 && faces[k][i] < n_verts[k]);
+    }
+    Shells* S = new Shells();
+    S->K = K;
+    S->layers.resize(K);
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < K && err == cudaSuccess; ++k) {
+        Builder B;
+        B.verts = verts[k];
+        B.faces = faces[k];
+        B.n_faces = n_faces[k];
+        B.build();
+        std::vector<Node4> wide;
+        collapse_bfs(B, wide);
+        const int64_t T = n_faces[k];
+        std::vector<float4> tris(3 * T);
+        std::vector<int32_t> o2b(T);
+        for (int64_t p = 0; p < T; ++p) {
+            const int32_t oi = B.order[p];
+            o2b[oi] = (int32_t)p;
+            const float* a = verts[k] + 3 * (int64_t)faces[k][3 * oi];
+            const float* b = verts[k] + 3 * (int64_t)faces[k][3 * oi + 1];
+            const float* c = verts[k] + 3 * (int64_t)faces[k][3 * oi + 2];
+            float w;
+            std::memcpy(&w, &oi, 4);
+            tris[3 * p] = make_float4(a[0], a[1], a[2], w);
+            tris[3 * p + 1] = make_float4(b[0], b[1], b[2], 0.f);
+            tris[3 * p + 2] = make_float4(c[0], c[1], c[2], 0.f);
+        }
+        Layer& L = S->layers[k];
+        L.n_nodes = (int32_t)wide.size();
+        L.n_tris = T;
+        if ((err = cudaMalloc(&L.nodes, sizeof(Node4) * std::max<size_t>(wide.size(), kTopNodes))) != cudaSuccess) break;
+        if ((err = cudaMalloc(&L.tris, sizeof(float4) * 3 * T)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&L.orig_to_bvh, sizeof(int32_t) * T)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(L.nodes, wide.data(), sizeof(Node4) * wide.size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(L.tris, tris.data(), sizeof(float4) * 3 * T, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(L.orig_to_bvh, o2b.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    }
+    if (err == cudaSuccess) err = cudaMalloc(&S->overflow_dev, sizeof(int));
+    if (err == cudaSuccess) err = cudaMemset(S->overflow_dev, 0, sizeof(int));
+    if (err == cudaSuccess) err = cudaMalloc(&S->layers_dev, sizeof(Layer) * K);
+    if (err == cudaSuccess) err = cudaMemcpy(S->layers_dev, S->layers.data(), sizeof(Layer) * K, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        for (auto& L : S->layers) free_layer(L);
+        if (S->layers_dev) cudaFree(S->layers_dev);
+        if (S->overflow_dev) cudaFree(S->overflow_dev);
+        delete S;
+        return (int)err;
+    }
+    *handle_out = S;
+    return VS_OK;
+}
+
+int vs_shells_free(void* handle) {
+    if (!handle) return VS_OK;
+    Shells* S = reinterpret_cast<Shells*>(handle);
+    for (auto& L : S->layers) free_layer(L);
+    if (S->layers_dev) cudaFree(S->layers_dev);
+    if (S->overflow_dev) cudaFree(S->overflow_dev);
+    delete S;
+    return VS_OK;
+}
+
+// 1 if any traversal since the build dropped a stack entry (results would be unreliable), else 0.  Synchronises the device.
+int vs_shells_overflowed(const void* handle) {
+    if (!handle) return 0;
+    int v = 0;
+    cudaMemcpy(&v, reinterpret_cast<const Shells*>(handle)->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
+}
+
+int vs_shells_info(const void* handle, int layer, int64_t* n_nodes, int64_t* n_tris) {
+    VS_CHECK_ARG(handle);
+    const Shells* S = reinterpret_cast<const Shells*>(handle);
+    VS_CHECK_ARG(layer >= 0 && layer < S->K);
+    if (n_nodes) *n_nodes = S->layers[layer].n_nodes;
+    if (n_tris) *n_tris = S->layers[layer].n_tris;
+    return VS_OK;
+}
+
+int vs_shells_num_layers(const void* handle) { return handle ? reinterpret_cast<const Shells*>(handle)->K : 0; }
+
+// Nearest hit of every ray with layers [layer_first, layer_first+layer_count).  Outputs are layer-major
+// [layer_count, n_rays]: depth (1e6 = miss), original face index (-1 = miss), barycentric u, v (0 on a miss).
+int vs_shells_trace(const void* handle, const float* rays_o, const float* rays_d, int64_t n_rays, int layer_first, int layer_count,
+                    float* depth_out, int32_t* tri_out, float* u_out, float* v_out, void* stream) {
+    VS_CHECK_ARG(handle && n_rays >= 0);
+    const Shells* S = reinterpret_cast<const Shells*>(handle);
+    VS_CHECK_ARG(layer_first >= 0 && layer_count > 0 && layer_first + layer_count <= S->K);
+    if (n_rays == 0) return VS_OK;
+    VS_CHECK_ARG(rays_o && rays_d && depth_out && tri_out && u_out && v_out);
+    dim3 grid((unsigned)div_up(n_rays, kRaysPerBlock), (unsigned)layer_count);
+    shells_trace_kernel<<<grid, kTraceThreads, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_first, rays_o, rays_d, n_rays, depth_out,
+                                                                         tri_out, u_out, v_out, S->overflow_dev);
+    return launched(1);
+}
+
+// Reference-format result of RayTracer.trace(mesh_id=layer): positions [N,3], unit face normals [N,3], triangles_mesh_id /
+// triangles_id int64 [N], barycentric (1-u-v,u,v) [N,3], from one layer's compact hit record.
+int vs_shells_expand(const void* handle, int layer, const float* rays_o, const float* rays_d, const float* depth, const int32_t* tri,
+                     const float* u, const float* v, int64_t n_rays, float* positions, float* normals, int64_t* tri_mesh_id,
+                     int64_t* tri_id, float* barycentric, void* stream) {
+    VS_CHECK_ARG(handle && n_rays >= 0);
+    const Shells* S = reinterpret_cast<const Shells*>(handle);
+    VS_CHECK_ARG(layer >= 0 && layer < S->K);
+    if (n_rays == 0) return VS_OK;
+    VS_CHECK_ARG(rays_o && rays_d && depth && tri && u && v && positions && normals && tri_mesh_id && tri_id && barycentric);
+    shells_expand_kernel<<<(unsigned)div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        S->layers_dev, layer, rays_o, rays_d, depth, tri, u, v, n_rays, positions, normals, tri_mesh_id, tri_id, barycentric);
+    return launched(1);
+}
+
+// Unit face normals of packed hits: normals[s] = normal of face tri[s] of layer layer_of[s].  n_valid_dev (optional, device
+// int64) limits the work to the first *n_valid_dev samples of capacity-sized arrays.
+int vs_shells_sample_normals(const void* handle, const int32_t* layer_of, const int32_t* tri, int64_t n_samples,
+                             const int64_t* n_valid_dev, float* normals, void* stream) {
+    VS_CHECK_ARG(handle && n_samples >= 0);
+    if (n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(layer_of && tri && normals);
+    const Shells* S = reinterpret_cast<const Shells*>(handle);
+    shells_normals_kernel<<<(unsigned)div_up(n_samples, 256), 256, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_of, tri, n_samples,
+                                                                                              n_valid_dev, normals);
+    return launched(1);
+}
+
+}  // extern "C"

@@ -64,3 +64,137 @@ def pack_layer_hits(rays_o, rays_d, depth, tri=None, bary_u=None, bary_v=None, t
             "vs_pack_hits_scatter",
         )
     return out
+
+
+class ShellTracer:
+    """K nested meshes on the GPU: the B200 counterpart of ``raytracelib.RayTracer``
+    (submodules/raytracelib/raytracelib/raytracer.py:7-223).
+
+    ``meshes``: list of objects with ``.vertices`` / ``.faces`` (as raytracelib expects) or ``(vertices, faces)`` tuples,
+    mesh 0 = innermost (mesh file order, volsurfs_py/utils/mesh_loaders.py:22-31).  The BVHs are built once on the host.
+
+    * :meth:`trace_layers` — all K layers in ONE launch, layer-major compact records (depth, face, u, v);
+    * :meth:`render_samples` — trace + pack into a compacted :class:`RaySamplesPacked` (outer -> inner per ray);
+    * :meth:`trace` — reference-compatible per-mesh result dict (same keys, dtypes and shapes as raytracer.py:103-113),
+      without the reference's ``torch.cuda.synchronize()``.
+    """
+
+    def __init__(self, meshes, t_near: float = 1e-3, t_far: float = 100.0):
+        import ctypes
+
+        import numpy as np
+
+        L = _lib.lib()
+        self.t_near, self.t_far = t_near, t_far
+        self.nr_meshes = len(meshes)
+        vs, fs = [], []
+        for m in meshes:
+            v, f = (m.vertices, m.faces) if hasattr(m, "vertices") else m
+            if torch.is_tensor(v):
+                v = v.detach().cpu().numpy()
+            if torch.is_tensor(f):
+                f = f.detach().cpu().numpy()
+            v = np.ascontiguousarray(v, dtype=np.float32)
+            f = np.ascontiguousarray(f, dtype=np.int32)
+            assert f.shape[0] > 8, "BVH needs at least 8 triangles."  # raytracer.py:17
+            vs.append(v)
+            fs.append(f)
+        K = self.nr_meshes
+        vptr = (ctypes.c_void_p * K)(*[v.ctypes.data for v in vs])
+        fptr = (ctypes.c_void_p * K)(*[f.ctypes.data for f in fs])
+        nv = (ctypes.c_int64 * K)(*[v.shape[0] for v in vs])
+        nf = (ctypes.c_int64 * K)(*[f.shape[0] for f in fs])
+        handle = ctypes.c_void_p()
+        if not torch.cuda.is_available():
+            raise _lib.VolsurfsB200Error("ShellTracer needs a CUDA device (no CPU fallback)")
+        check(L.vs_shells_build(K, vptr, nv, fptr, nf, ctypes.byref(handle)), "vs_shells_build")
+        self._handle = handle
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_faces = [int(f.shape[0]) for f in fs]
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                _lib.lib().vs_shells_free(h)
+            except Exception:  # noqa: BLE001
+                pass
+            self._handle = None
+
+    def num_nodes(self, layer: int = 0) -> int:
+        import ctypes
+
+        n = ctypes.c_int64()
+        check(_lib.lib().vs_shells_info(self._handle, layer, ctypes.byref(n), None), "vs_shells_info")
+        return int(n.value)
+
+    def overflowed(self) -> bool:
+        return bool(_lib.lib().vs_shells_overflowed(self._handle))
+
+    @staticmethod
+    def _rays(rays_o, rays_d):
+        assert torch.is_tensor(rays_o) and rays_o.is_cuda, "rays_o must be a torch.Tensor on cuda"
+        assert torch.is_tensor(rays_d) and rays_d.is_cuda, "rays_d must be a torch.Tensor on cuda"
+        return rays_o.float().contiguous().view(-1, 3), rays_d.float().contiguous().view(-1, 3)
+
+    @torch.no_grad()
+    def trace_layers(self, rays_o, rays_d, layer_first: int = 0, layer_count=None):
+        """-> dict(depth [k,N] f32 (1e6 = miss), tri [k,N] i32 (-1 = miss), u, v [k,N] f32) for layers
+        [layer_first, layer_first + layer_count)"""
+        rays_o, rays_d = self._rays(rays_o, rays_d)
+        k = self.nr_meshes - layer_first if layer_count is None else layer_count
+        n = rays_o.shape[0]
+        dev = rays_o.device
+        depth = torch.empty((k, n), dtype=torch.float32, device=dev)
+        tri = torch.empty((k, n), dtype=torch.int32, device=dev)
+        u = torch.empty((k, n), dtype=torch.float32, device=dev)
+        v = torch.empty((k, n), dtype=torch.float32, device=dev)
+        check(
+            _lib.lib().vs_shells_trace(self._handle, ptr(rays_o), ptr(rays_d), n, layer_first, k, ptr(depth), ptr(tri), ptr(u), ptr(v), _stream()),
+            "vs_shells_trace",
+        )
+        return {"depth": depth, "tri": tri, "u": u, "v": v, "rays_o": rays_o, "rays_d": rays_d}
+
+    @torch.no_grad()
+    def render_samples(self, rays_o, rays_d, exact_size: bool = True, with_normals: bool = True):
+        """trace all layers and pack the hits: compacted RaySamplesPacked (+ ``samples_normals`` [S,3])"""
+        rec = self.trace_layers(rays_o, rays_d)
+        rsp = pack_layer_hits(rec["rays_o"], rec["rays_d"], rec["depth"], rec["tri"], rec["u"], rec["v"], t_far=self.t_far,
+                              exact_size=exact_size)
+        if with_normals:
+            S = rsp.get_max_nr_samples()
+            rsp.samples_normals = torch.zeros((S, 3), dtype=torch.float32, device=rec["depth"].device)
+            check(
+                _lib.lib().vs_shells_sample_normals(self._handle, ptr(rsp.samples_layer), ptr(rsp.samples_triangle), S,
+                                                    None if exact_size else ptr(rsp.total_dev), ptr(rsp.samples_normals), _stream()),
+                "vs_shells_sample_normals",
+            )
+        return rsp
+
+    @torch.no_grad()
+    def trace(self, rays_o, rays_d, mesh_id: int = 0, **_unused):
+        """Reference-compatible single-mesh trace (raytracer.py:35-113): same dict keys / dtypes / shapes."""
+        assert mesh_id < self.nr_meshes, "mesh_id must be smaller than the number of meshes in the scene"
+        rec = self.trace_layers(rays_o, rays_d, layer_first=mesh_id, layer_count=1)
+        rays_o, rays_d = rec["rays_o"], rec["rays_d"]
+        n = rays_o.shape[0]
+        dev = rays_o.device
+        positions = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        normals = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        bary = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        tmid = torch.empty((n,), dtype=torch.int64, device=dev)
+        tid = torch.empty((n,), dtype=torch.int64, device=dev)
+        depth = rec["depth"][0]
+        check(
+            _lib.lib().vs_shells_expand(self._handle, mesh_id, ptr(rays_o), ptr(rays_d), ptr(depth), ptr(rec["tri"][0]), ptr(rec["u"][0]),
+                                        ptr(rec["v"][0]), n, ptr(positions), ptr(normals), ptr(tmid), ptr(tid), ptr(bary), _stream()),
+            "vs_shells_expand",
+        )
+        is_hit = depth <= self.t_far          # raytracer.py:100
+        return {
+            "any_hit": is_hit.any(dim=-1), "is_hit": is_hit, "positions": positions, "triangles_mesh_id": tmid, "triangles_id": tid,
+            "depth": depth, "normals": normals, "barycentric": bary, "view_dirs": rays_d,
+        }
+
+    def trace_all(self, rays_o, rays_d, **kw):
+        return [self.trace(rays_o, rays_d, mesh_id=i) for i in range(self.nr_meshes)]
