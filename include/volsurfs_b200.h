@@ -150,6 +150,21 @@ int vs_shells_expand(const void* handle, int layer, const float* rays_o, const f
 int vs_shells_sample_normals(const void* handle, const int32_t* layer_of, const int32_t* tri, int64_t n_samples,
                              const int64_t* n_valid_dev, float* normals, void* stream);
 
+/* ---- fused appearance head (tensor cores) ----------------------------------------------------------------------------
+ * Replaces RGB.forward (volsurfs_py/models/rgb.py:104-149: [pos features | SH(dirs) | normals?] -> MLP -> sigmoid), MLP.forward
+ * (models/mlp.py:8-52), SHEncoder.__call__ (encodings/sphericalharmonics.py:84-153) and the alpha decay of
+ * volsurfs_py/methods/volsurfs.py:583-594 at their call sites volsurfs.py:544-549,575-594.
+ * dims = [in, h1, ..., out] (n_layers + 1 entries): in <= 128, hidden widths multiples of 16 and <= 128, out <= 8. */
+int64_t vs_mlp_blob_bytes(int n_layers, const int* dims);
+/* weights[l]: DEVICE fp32 [dims[l+1], dims[l]] (torch.nn.Linear layout), biases[l]: DEVICE fp32 [dims[l+1]] or NULL; the pointer
+ * arrays themselves are HOST arrays.  Writes the fp16 tensor-core layout + fp32 biases into `blob` (device, 16-byte aligned). */
+int vs_mlp_pack(int n_layers, const int* dims, const float* const* weights, const float* const* biases, void* blob, void* stream);
+/* out[s,:out] = sigmoid(MLP([pos[s] | SH_deg(dirs[s]) | normals[s] if normal_dep])) * (alpha_decay ? 2*sigmoid(10*clamp(-d.n,0,1))-1 : 1)
+ * activation: 0 ReLU, 1 GELU(erf).  n_valid_dev: optional device int64 capping n_samples.  variant: 0 (debug knob). */
+int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
+                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, int64_t n_samples,
+                   const int64_t* n_valid_dev, int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
