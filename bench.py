@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray rendering hot path (BASELINE.json metric: Mrays/s fwd+bwd, 5-layer shells; % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic rays on every rank (rays are sharded, weak scaling):
+  K-layer shell intersection (one launch) -> hit packing -> face normals -> rgb head + alpha head (tcgen05 MLPs) ->
+  fused compositing forward -> L1 loss gradient -> fused compositing backward (d_alpha, d_rgb per hit).
+Workload at every N: BASELINE config[1] per GPU — 800x800 camera rays against 5 nested ~100k-triangle shells, legacy
+[128,128,64] GELU heads on 51 positional features (synthetic stand-in for the permutohedral encoder) + SH deg 3.
+
+Prints ONE JSON line (rank 0).  `value` is the device-resident whole-job throughput, `e2e` the same step driven from pinned
+host ray buffers with the image copied back, `roofline` describes the dominant kernel of the step, `stages` every stage,
+`compositing_roofline` the headline compositing kernels at 2^24 rays (the size SURVEY.md section 8d prescribes),
+`cpu_baseline` the reference algorithm (oracle port: C BVH tracer + torch CPU heads + the reference's dense torch
+compositing differentiated by autograd) on a bounded sample on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Mrays/s fwd+bwd, 5-layer shells"
+UNIT = "Mrays/s"
+K_LAYERS = 5
+IMG = 800
+HIDDEN = (128, 128, 64)
+POS_DIM = 51
+CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples SM clock + throttle reasons of one GPU while the timed region runs (pynvml; nvidia-smi fallback)"""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for name, bit in {**self.BAD, **self.NOTE}.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(0.02)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._sample()
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {"sm_mhz": int(statistics.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's algorithm on the host cores (oracle port)
+# ----------------------------------------------------------------------------------------------------------------------
+class CpuReferencePath:
+    """The reference's CPU-runnable path, restated by oracle/: per-mesh BVH trace (C, OpenMP, raytracelib algorithm), per-mesh
+    shading of the hit points with the legacy torch heads, the dense [N,K] torch compositing of volsurfs.py:601-640,708 and its
+    autograd backward down to the per-surface colour/alpha (the same depth our step differentiates to)."""
+
+    def __init__(self, n_rays: int):
+        import numpy as np
+        import torch
+
+        from oracle import appearance as oa
+        from oracle.raytrace import OracleRayTracer
+        from volsurfs_b200.synthetic import camera_rays, shell_meshes
+
+        self.torch, self.np, self.oa = torch, np, oa
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.meshes = shell_meshes(K=K_LAYERS)
+        self.tracer = OracleRayTracer(self.meshes)
+        o, d = camera_rays(IMG, IMG)
+        # a contiguous block of rows through the middle of the image (same hit density as the whole frame's centre)
+        first = (IMG // 2) * IMG - n_rays // 2
+        self.o, self.d = o[first:first + n_rays].contiguous(), d[first:first + n_rays].contiguous()
+        self.n_rays = n_rays
+        self.rgb_w = oa.init_linear_stack(POS_DIM + 16, HIDDEN, 3, seed=11)
+        self.alpha_w = oa.init_linear_stack(POS_DIM + 16, HIDDEN, 1, seed=12)
+        g = torch.Generator().manual_seed(13)
+        self.feats = torch.rand(n_rays, K_LAYERS, POS_DIM, generator=g) * 2 - 1
+        self.gt = torch.rand(n_rays, 3, generator=g)
+        self.cores = os.cpu_count() or 1
+
+    def step(self):
+        torch, np, oa = self.torch, self.np, self.oa
+        from oracle.compositing import dense_composite_torch
+
+        N, K = self.n_rays, K_LAYERS
+        o, d = self.o.numpy(), self.d.numpy()
+        surfs_rgb = torch.zeros(N, K, 3)
+        surfs_alpha = torch.zeros(N, K, 1)
+        for i in range(K):                                        # volsurfs.py:476-485
+            res = self.tracer.trace(o, d, i, mode="bvh")
+            if not res["any_hit"]:
+                continue
+            hits = torch.from_numpy(res["is_hit"])
+            normals = torch.from_numpy(res["normals"])[hits]
+            dirs = self.d[hits]
+            with torch.no_grad():                                 # heads are evaluated, not differentiated, in this step
+                rgb = oa.head_forward(self.feats[hits, i], dirs, normals, *self.rgb_w)
+                alpha = oa.alpha_decay(oa.head_forward(self.feats[hits, i], dirs, normals, *self.alpha_w), dirs, normals)
+            surfs_rgb[hits, i] = rgb
+            surfs_alpha[hits, i] = alpha
+        surfs_rgb.requires_grad_(True)
+        surfs_alpha.requires_grad_(True)
+        out = dense_composite_torch(surfs_alpha, surfs_rgb, rgb_bg=torch.ones(N, 3))   # volsurfs.py:601-640,708 (fp32 variant)
+        loss = (out["rgb"] - self.gt).abs().mean()                                       # utils/losses.py:14-19
+        loss.backward()
+        return float(loss.detach())
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    path = CpuReferencePath(CPU_SAMPLE_RAYS)
+    for _ in range(max(args.warmup, 1)):
+        path.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        path.step()
+    dt = time.perf_counter() - t0
+    value = path.n_rays * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world) | {"sample": f"{path.n_rays} rays per step (reference render chunk) of the 800x800 frame"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": path.cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {path.n_rays} rays (rows through the image centre), all {path.cores} host threads"},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"BASELINE config[1]: 5-mesh volsurf render of kitten-shaped synthetic shells (~100k tris/layer), {IMG}x{IMG} rays per GPU",
+        "rays_per_gpu": IMG * IMG, "layers": K_LAYERS, "triangles_per_layer": 99904, "heads": f"rgb+alpha legacy MLP {list(HIDDEN)} GELU, "
+        f"{POS_DIM} positional features (synthetic encoder output) + SH deg 3",
+        "step": "trace(K layers, 1 launch) + pack + normals + 2 MLP heads fwd + composite fwd + L1 grad + composite bwd",
+        "parallelism": f"rays sharded over {world} GPU(s), no data-path collective", "l2": "inputs_larger_than_l2 (653 MB features + 200 MB packed arrays per step)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from volsurfs_b200 import _lib
+    from volsurfs_b200.pipeline import make_synthetic_renderer
+    from volsurfs_b200.synthetic import all_hit_packed, camera_rays, composite_bytes
+    from volsurfs_b200.volsurfs import RaySamplesPacked, VolumeRendering as VR
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device for the default arm (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.lib()
+    pk = peaks()
+
+    renderer, _ = make_synthetic_renderer(K=K_LAYERS, hidden=HIDDEN, pos_dim=POS_DIM)
+    o_h, d_h = camera_rays(IMG, IMG, azimuth_deg=30.0 + 40.0 * rank)   # every rank renders its own view
+    N = o_h.shape[0]
+    o_pin, d_pin = o_h.pin_memory(), d_h.pin_memory()
+    rays_o, rays_d = o_h.to(dev), d_h.to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    feats = (torch.rand(N * K_LAYERS, POS_DIM, generator=g) * 2 - 1).to(dev)
+    gt = torch.rand(N, 3, generator=g).to(dev)
+    img_pin = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+    loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
+
+    stage_names = ["trace", "pack+normals", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad", "composite_bwd"]
+    ev = None
+
+    def step(record=None):
+        def mark(i):
+            if record is not None:
+                record[i].record()
+
+        mark(0)
+        rec = renderer.tracer.trace_layers(rays_o, rays_d)
+        mark(1)
+        from volsurfs_b200.raytracer import pack_layer_hits
+
+        rsp = pack_layer_hits(rec["rays_o"], rec["rays_d"], rec["depth"], rec["tri"], rec["u"], rec["v"], t_far=renderer.tracer.t_far,
+                              exact_size=False)
+        S = rsp.get_max_nr_samples()
+        rsp.samples_normals = torch.empty((S, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.vs_shells_sample_normals(renderer.tracer._handle, rsp.samples_layer.data_ptr(), rsp.samples_triangle.data_ptr(), S,
+                                                rsp.total_dev.data_ptr(), rsp.samples_normals.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "normals")
+        mark(2)
+        rgb = renderer.rgb_head(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
+        mark(3)
+        alpha = renderer.alpha_head(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
+        mark(4)
+        out = renderer.composite(rsp, alpha, rgb)
+        mark(5)
+        diff = out["rgb"] - gt
+        loss = diff.abs().mean()
+        g_pred = torch.sign(diff) / diff.numel()
+        mark(6)
+        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
+        mark(7)
+        return out, loss, rsp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        out, loss, rsp = step()
+    torch.cuda.synchronize()
+    n_hits = int(rsp.total_dev.item())
+    assert not renderer.tracer.overflowed()
+
+    # ---- timed region: device-resident inputs
+    records = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = lib.vs_launch_count()
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        step(records[s])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.vs_launch_count() - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    stage_ms = [statistics.mean(records[s][i].elapsed_time(records[s][i + 1]) for s in range(args.steps)) for i in range(7)]
+
+    # ---- e2e: pinned host rays in, image + loss out, every step
+    def e2e_step():
+        rays_o.copy_(o_pin, non_blocking=True)
+        rays_d.copy_(d_pin, non_blocking=True)
+        out, loss, _ = step()
+        img_pin.copy_(out["rgb"], non_blocking=True)
+        loss_pin.copy_(loss, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+        hits_t = torch.tensor([n_hits], device=dev, dtype=torch.int64)
+        dist.all_reduce(hits_t)
+        n_hits_all = int(hits_t[0])
+    else:
+        n_hits_all = n_hits
+    if rank != 0:
+        return
+
+    total_rays = N * world
+    value = total_rays * args.steps / (ms_total * 1e-3) / 1e6
+    e2e_value = total_rays * args.steps / (ms_e2e * 1e-3) / 1e6
+
+    # ---- per-stage rooflines (rank 0's numbers)
+    S_cap = N * K_LAYERS
+    flops_head = lambda out_dim: 2.0 * n_hits * (67 * 128 + 128 * 128 + 128 * 64 + 64 * out_dim)  # noqa: E731
+    stage_alg = {
+        "trace": ("hbm", N * K_LAYERS * (24 + 16)),                                   # rays in, (t, face, u, v) out per (ray, layer)
+        "pack+normals": ("hbm", N * (16 * K_LAYERS + 8 + 24) + n_hits * (4 + 4 + 12 + 12 + 4 + 4 + 8 + 12)),
+        "mlp_rgb": ("tensor", flops_head(3)),
+        "mlp_alpha": ("tensor", flops_head(1)),
+        "composite_fwd": ("hbm", 32 * N + 20 * n_hits),
+        "loss_grad": ("hbm", N * 12 * 6),
+        "composite_bwd": ("hbm", 32 * N + 36 * n_hits),
+    }
+    stages = {}
+    for name, ms in zip(stage_names, stage_ms):
+        bound, alg = stage_alg[name]
+        if bound == "hbm":
+            ach, peak, unit = alg / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = alg / (ms * 1e-3) / 1e12, pk["tflops_sustained"], "TFLOP/s"
+        stages[name] = {"ms": round(ms, 4), "share": round(ms / sum(stage_ms), 3), "bound": bound, "achieved": round(ach, 2), "peak": peak,
+                        "unit": unit, "frac": round(ach / peak, 4)}
+    dominant = max(stages, key=lambda k: stages[k]["ms"])
+    roofline = {k: stages[dominant][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+    roofline.update(kernel=dominant, traffic=None, peak_source=pk["source"],
+                    note="algorithmic bytes/flops per launch over the kernel's mean CUDA-event duration inside the timed region")
+
+    # ---- the headline compositing kernels at the size SURVEY 8d prescribes (2^24 rays x 5, traffic >> L2)
+    comp = None
+    if not args.skip_composite_roofline:
+        del feats
+        torch.cuda.empty_cache()
+        n_big = 1 << 24
+        d = all_hit_packed(n_big, K_LAYERS)
+        rsp_b = RaySamplesPacked(0, 0, 0, 1)
+        rsp_b.ray_start_end_idx = d["se"].to(dev)
+        a, c, z = d["alpha"].to(dev), d["rgb"].to(dev), d["z"].to(dev)
+        gs = [d[k].to(dev) for k in ("g_rgb", "g_depth", "g_acc", "g_bgT")]
+        for _ in range(3):
+            VR.composite(rsp_b, a, c, z)
+            VR.composite_backward(rsp_b, a, c, z, *gs)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        c0.record()
+        for _ in range(reps):
+            VR.composite(rsp_b, a, c, z)
+            VR.composite_backward(rsp_b, a, c, z, *gs)
+        c1.record()
+        torch.cuda.synchronize()
+        ms_c = c0.elapsed_time(c1) / reps
+        nbytes = composite_bytes(n_big, n_big * K_LAYERS)
+        comp = {"workload": "fused compositing fwd+bwd, 2^24 rays x 5 samples (5.8 GB algorithmic traffic per pair of launches)",
+                "mrays_s": round(n_big / (ms_c * 1e-3) / 1e6, 1), "bound": "hbm", "achieved": round(nbytes / (ms_c * 1e-3) / 1e9, 1),
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(nbytes / (ms_c * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "ms_per_fwd_bwd": round(ms_c, 4)}
+
+    # ---- cpu baseline (bounded sample, rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        path = CpuReferencePath(CPU_SAMPLE_RAYS)
+        path.step()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            path.step()
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(path.n_rays * reps / dt / 1e6, 4), "unit": UNIT, "cores": path.cores, "kind": "port",
+               "sample": f"{reps} steps x {path.n_rays} rays (rows through the image centre) of the same workload; oracle port of the "
+                         "reference algorithm (C BVH tracer with OpenMP, torch CPU heads, dense torch compositing + autograd)"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (ray/triangle, packing, compositing); f16 operands x f32 accumulate (MLP heads)", "data": "synthetic",
+        "config": workload_config(args, world) | {"hits_per_step_all_ranks": n_hits_all},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(N * 24), "d2h_bytes_per_step": int(N * 12 + 4),
+                "ms_per_step": round(ms_e2e / args.steps, 4),
+                "note": "pinned host rays -> device every step, composited image + loss -> pinned host every step; the positional "
+                        "features are produced on the device by the encoder stage and stay device-resident"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stages": stages,
+        "compositing_roofline": comp,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-composite-roofline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,6 @@
 """GPU parity of the fused tcgen05 appearance head against the fp32 oracle and the vectors produced by the reference's own MLP /
 SHEncoder classes.  The kernel multiplies fp16 operands with fp32 accumulation (like tiny-cuda-nn's FullyFusedMLP on the
-reference's default path), so the tolerance of this stage is absolute 4e-3 on the sigmoid outputs (fp16 has an 11-bit
+reference's default path), so the tolerance of this stage is absolute 2e-4 on the sigmoid outputs (observed ~1e-5; fp16 has an 11-bit
 significand; three to four layers of width <= 128) — the 1e-5 target of BASELINE.json applies to compositing, not to the MLP."""
 import numpy as np
 import pytest
@@ -10,7 +10,7 @@ from conftest import GOLDEN
 from oracle import appearance as oa
 
 pytestmark = pytest.mark.gpu
-ATOL = 4e-3
+ATOL = 2e-4  # observed ~1e-5 on B200
 
 
 def _head_from_golden(g, alpha_decay=False):
