@@ -27,7 +27,7 @@
 
 namespace vs {
 
-constexpr int kMlpThreads = 128;
+constexpr int kMlpThreads = 512;   // 16 warps: 4 column groups x 4 lane quarters work on one 128-sample tile
 constexpr int kTileM = 128;
 constexpr int kMaxLayers = 6;
 constexpr int kMaxWidth = 128;     // widest layer (TMEM columns allocated, A1 buffer)
@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int row = tid & (kTileM - 1);  // sample of the tile this thread works on (== its TMEM lane)
+    const int cg = tid >> 7;             // column group 0..3: which quarter of the columns / K-chunks this thread handles
     const int F = cfg.pos_dim;
     const int k0 = cfg.k_pad[0];
 
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // a warp may only touch lanes 32*(warp%4)..+31
 
     if ((int64_t)blockIdx.x < n_tiles && tid == 0) {  // weights + biases: resident for the whole kernel
         mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
@@ -240,8 +242,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
         const int64_t row0 = tile * kTileM;
         const int rows = (int)min((int64_t)kTileM, n - row0);
         const bool full = rows == kTileM;
-        const int64_t r = row0 + tid;
-        const bool live = tid < rows;
+        const int64_t r = row0 + row;
+        const bool live = row < rows;
 
         // ---- 1. features -> shared memory
         if (full) {
@@ -271,28 +273,30 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
 #pragma unroll
             for (int i = 0; i < 16; ++i) sh[i] = 0.f;
             sh_eval(dx, dy, dz, cfg.n_sh, sh);
-            float* ex = s_extra + tid * kExtraStride;
+            if (cg == 0) {
+                float* ex = s_extra + row * kExtraStride;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) ex[i] = sh[i];
-            // with n_sh < 16 the normal follows the SH block directly
-            if (cfg.normal_dep) {
-                ex[cfg.n_sh] = nx;
-                ex[cfg.n_sh + 1] = ny;
-                ex[cfg.n_sh + 2] = nz;
+                for (int i = 0; i < 16; ++i) ex[i] = sh[i];
+                // with n_sh < 16 the normal follows the SH block directly
+                if (cfg.normal_dep) {
+                    ex[cfg.n_sh] = nx;
+                    ex[cfg.n_sh + 1] = ny;
+                    ex[cfg.n_sh + 2] = nz;
+                }
             }
         }
+        __syncthreads();
         if (full) {
             mbar_wait(&bar_in, par_in);
             par_in ^= 1;
-        } else {
-            __syncthreads();
         }
-        // ---- 3. row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes
+        // ---- 3. row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes; the four column
+        //         groups split the K-chunks of a row
         {
-            const float* srow = s_stage + tid * F;
-            const float* ex = s_extra + tid * kExtraStride;
+            const float* srow = s_stage + row * F;
+            const float* ex = s_extra + row * kExtraStride;
             const int in_dim = cfg.in_dim;
-            for (int kc = 0; kc < k0 / 8; ++kc) {
+            for (int kc = cg; kc < k0 / 8; kc += 4) {
                 __half2 h[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
                     }
                     h[j] = __floats2half2_rn(v2[0], v2[1]);
                 }
-                *reinterpret_cast<uint4*>(s_a0 + ((size_t)kc * kTileM + tid) * 8) = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(s_a0 + ((size_t)kc * kTileM + row) * 8) = *reinterpret_cast<const uint4*>(h);
             }
         }
         if (!weights_ready) {
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
             const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l]);
             if (l + 1 < cfg.n_layers) {
                 // hidden layer epilogue: bias + activation -> fp16 -> next A operand (row = tid)
-                for (int c0 = 0; c0 < N; c0 += 16) {
+                for (int c0 = cg * 16; c0 < N; c0 += 64) {
                     float v[16];
                     tmem_ld16(tmem_lane + (uint32_t)c0, v);
                     __half2 h[8];
@@ -359,11 +363,11 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
                         }
                         h[j] = __floats2half2_rn(a, b);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(s_a1 + ((size_t)(c0 / 8) * kTileM + tid) * 8);
+                    uint4* dst = reinterpret_cast<uint4*>(s_a1 + ((size_t)(c0 / 8) * kTileM + row) * 8);
                     dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
                     dst[kTileM] = *reinterpret_cast<const uint4*>(&h[4]);  // next 8-column chunk: +128 rows * 16 bytes
                 }
-            } else {
+            } else if (cg == 0) {
                 float v[16];
                 tmem_ld16(tmem_lane, v);
                 if (live) {
