@@ -46,6 +46,7 @@ struct MlpConfig {
     int variant;             // debug: bit0 swaps LBO/SBO in the shared-memory descriptors
     int a1_width;            // widest hidden layer (size of the activation buffer), tmem_cols: power of two >= widest layer
     int tmem_cols;
+    int prefetch;            // 1: the feature tile of the CTA's next tile is fetched while the current one is processed
 };
 
 static inline int pad16(int x) { return (x + 15) / 16 * 16; }
@@ -153,14 +154,20 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
-    // 0.5 x (1 + erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), far below the fp16 rounding of the result
+    // 0.5 x (1 + erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.28: 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7 — far below
+    // the fp16 rounding of the result; one MUFU (reciprocal) per activation, everything else on the FMA pipe
     const float z = fabsf(x) * 0.70710678118f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = 1.f - p * t * __expf(-z * z);
+    float p = fmaf(z, 0.0000430638f, 0.0002765672f);
+    p = fmaf(p, z, 0.0001520143f);
+    p = fmaf(p, z, 0.0092705272f);
+    p = fmaf(p, z, 0.0422820123f);
+    p = fmaf(p, z, 0.0705230784f);
+    p = fmaf(p, z, 1.0f);
+    p = p * p;
+    p = p * p;
+    p = p * p;
+    p = p * p;
+    const float e = 1.f - __fdividef(1.f, p);
     return 0.5f * x * (1.f + copysignf(e, x));
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
                                                               const float* __restrict__ normals, float* __restrict__ out,
                                                               int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_in, bar_mma;
+    __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_mma;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -211,8 +218,9 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
     uint8_t* s_blob = smem;                                                         // blob_bytes (multiple of 16)
     __half* s_a0 = reinterpret_cast<__half*>(s_blob + cfg.blob_bytes);              // 128 x k0 fp16 (layer-0 operand)
     __half* s_a1 = s_a0 + kTileM * k0;                                              // 128 x a1_width fp16 (hidden activations)
-    float* s_stage = reinterpret_cast<float*>(s_a1 + kTileM * cfg.a1_width);        // 128 x F fp32 (TMA landing zone)
-    float* s_extra = s_stage + ((kTileM * F + 3) & ~3);                             // 128 x kExtraStride
+    const int stage_floats = (kTileM * F + 3) & ~3;
+    float* s_stage0 = reinterpret_cast<float*>(s_a1 + kTileM * cfg.a1_width);       // 128 x F fp32 (TMA landing zone) x 1 or 2
+    float* s_extra = s_stage0 + (cfg.prefetch ? 2 : 1) * stage_floats;              // 128 x kExtraStride
 
     int64_t n = n_samples;
     if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
@@ -220,7 +228,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
-        mbar_init(&bar_in, 1);
+        mbar_init(&bar_in[0], 1);
+        mbar_init(&bar_in[1], 1);
         mbar_init(&bar_mma, 1);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)cfg.tmem_cols);
@@ -235,7 +244,9 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
         bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
     }
     bool weights_ready = false;
-    uint32_t par_in = 0, par_mma = 0;
+    uint32_t par_in_bits = 0, par_mma = 0;  // bit b of par_in_bits: phase parity of bar_in[b]
+    int buf = 0;
+    bool have_prefetched = false;  // the current tile's features were requested during the previous iteration
     const uint32_t lbo_sel = (cfg.variant & 1);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -246,13 +257,26 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
         const bool live = row < rows;
 
         // ---- 1. features -> shared memory
+        float* s_stage = s_stage0 + buf * stage_floats;
         if (full) {
-            if (tid == 0) {
-                mbar_arrive_expect_tx(&bar_in, (uint32_t)(kTileM * F * 4));
-                bulk_g2s(s_stage, pos + row0 * F, (uint32_t)(kTileM * F * 4), &bar_in);
+            if (tid == 0 && !have_prefetched) {
+                mbar_arrive_expect_tx(&bar_in[buf], (uint32_t)(kTileM * F * 4));
+                bulk_g2s(s_stage, pos + row0 * F, (uint32_t)(kTileM * F * 4), &bar_in[buf]);
             }
         } else {
             for (int e = tid; e < rows * F; e += kMlpThreads) s_stage[e] = __ldg(pos + row0 * F + e);
+        }
+        // prefetch the next tile of this CTA into the other buffer (its previous contents were consumed an iteration ago)
+        bool next_prefetched = false;
+        if (cfg.prefetch) {
+            const int64_t nt = tile + gridDim.x;
+            if (nt < n_tiles && (nt + 1) * kTileM <= n) {
+                next_prefetched = true;
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&bar_in[buf ^ 1], (uint32_t)(kTileM * F * 4));
+                    bulk_g2s(s_stage0 + (buf ^ 1) * stage_floats, pos + nt * kTileM * F, (uint32_t)(kTileM * F * 4), &bar_in[buf ^ 1]);
+                }
+            }
         }
         // ---- 2. per-row extras: SH(dir), normal
         float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
@@ -287,8 +311,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
         }
         __syncthreads();
         if (full) {
-            mbar_wait(&bar_in, par_in);
-            par_in ^= 1;
+            mbar_wait(&bar_in[buf], (par_in_bits >> buf) & 1u);
+            par_in_bits ^= (1u << buf);
         }
         // ---- 3. row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes; the four column
         //         groups split the K-chunks of a row
@@ -385,6 +409,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
         // the next tile overwrites s_stage / s_extra / s_a0 and TMEM: everyone must be done reading them
         tc_fence_before();
         __syncthreads();
+        have_prefetched = next_prefetched;
+        if (cfg.prefetch) buf ^= 1;
     }
 
     tc_fence_before();
@@ -396,7 +422,7 @@ static size_t mlp_smem_bytes(const MlpConfig& c) {
     size_t b = (size_t)c.blob_bytes;
     b += (size_t)kTileM * c.k_pad[0] * 2;
     b += (size_t)kTileM * c.a1_width * 2;
-    b += (size_t)((kTileM * c.pos_dim + 3) & ~3) * 4;
+    b += (size_t)((kTileM * c.pos_dim + 3) & ~3) * 4 * (c.prefetch ? 2 : 1);
     b += (size_t)kTileM * kExtraStride * 4;
     return b + 128;
 }
@@ -455,8 +481,13 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
     c.activation = activation;
     c.alpha_decay = alpha_decay ? 1 : 0;
     c.variant = variant;
-    const size_t smem = mlp_smem_bytes(c);
+    size_t smem = mlp_smem_bytes(c);
     if (smem > 227 * 1024) return VS_ERR_UNSUPPORTED;
+    if (smem > 113 * 1024) {  // one CTA per SM anyway: spend the spare shared memory on a second feature buffer
+        c.prefetch = 1;
+        if (mlp_smem_bytes(c) > 227 * 1024) c.prefetch = 0;
+        smem = mlp_smem_bytes(c);
+    }
     cudaError_t ce = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return (int)ce;
     int dev = 0, sms = 148;
