@@ -35,12 +35,63 @@ constexpr int kTileRays = 256;  // rays per CTA == threads per CTA in the tile k
 // =============================================================================================
 // scan family
 // =============================================================================================
+// One chunk of a ray as the scan kernels hold it in registers: alpha, z of sample base+gl and three CONTIGUOUS floats of the
+// chunk's colour window (element gl + W*k of the 3W floats), so that colour loads/stores are unit-stride across the group.
+struct ScanChunk {
+    float a, z, c0, c1, c2;
+};
+
+template <int W>
+__device__ __forceinline__ ScanChunk scan_load_chunk(const float* __restrict__ alpha, const float* __restrict__ rgb,
+                                                     const float* __restrict__ z, int64_t start, int base, int n, int gl) {
+    ScanChunk ch;
+    const int i = base + gl;
+    const int64_t s = start + i;
+    const bool valid = i < n;
+    ch.a = valid ? ld_stream(alpha + s) : 0.f;
+    ch.z = valid ? ld_stream(z + s) : 0.f;
+    const int64_t w0 = 3 * (start + base);  // first float of the chunk's colour window
+    const int lim = 3 * (n - base);         // floats of the window that belong to the ray
+    ch.c0 = gl < lim ? ld_stream(rgb + w0 + gl) : 0.f;
+    ch.c1 = gl + W < lim ? ld_stream(rgb + w0 + gl + W) : 0.f;
+    ch.c2 = gl + 2 * W < lim ? ld_stream(rgb + w0 + gl + 2 * W) : 0.f;
+    return ch;
+}
+
+// window layout (element gl + W*k in register k) -> per-sample layout (sample gl owns elements 3gl..3gl+2), through the warp's
+// shared-memory scratch; `my` points at this group's 3W floats
+template <int W>
+__device__ __forceinline__ void window_to_samples(float* my, int gl, float w0, float w1, float w2, float& r, float& g, float& b) {
+    my[gl] = w0;
+    my[gl + W] = w1;
+    my[gl + 2 * W] = w2;
+    __syncwarp();
+    r = my[3 * gl];
+    g = my[3 * gl + 1];
+    b = my[3 * gl + 2];
+    __syncwarp();
+}
+template <int W>
+__device__ __forceinline__ void samples_to_window(float* my, int gl, float r, float g, float b, float& w0, float& w1, float& w2) {
+    my[3 * gl] = r;
+    my[3 * gl + 1] = g;
+    my[3 * gl + 2] = b;
+    __syncwarp();
+    w0 = my[gl];
+    w1 = my[gl + W];
+    w2 = my[gl + 2 * W];
+    __syncwarp();
+}
+
 template <int W>
 __global__ void __launch_bounds__(kScanThreads) composite_fwd_scan_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
     float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays) {
-    const int gl = threadIdx.x & (W - 1);
+    __shared__ float s_win[kScanThreads / 32][96];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (W - 1);
+    float* my = s_win[threadIdx.x >> 5] + (lane / W) * 3 * W;
     const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / W;
     int start = 0, n = 0;
     if (ray < n_rays) n = load_segment(se, ray, start);
@@ -48,31 +99,30 @@ __global__ void __launch_bounds__(kScanThreads) composite_fwd_scan_kernel(
 
     float carry = 1.f;
     float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+    ScanChunk cur = scan_load_chunk<W>(alpha, rgb, z, start, 0, n, gl);
     for (int base = 0; base < n_max; base += W) {
+        ScanChunk nxt;
+        if (base + W < n_max) nxt = scan_load_chunk<W>(alpha, rgb, z, start, base + W, n, gl);  // in flight during the scan below
         const int i = base + gl;
         const bool valid = i < n;
         const int64_t s = (int64_t)start + i;
-        float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, zz = 0.f;
-        if (valid) {
-            a = ld_stream(alpha + s);
-            cr = ld_stream(rgb + 3 * s);
-            cg = ld_stream(rgb + 3 * s + 1);
-            cb = ld_stream(rgb + 3 * s + 2);
-            zz = ld_stream(z + s);
-        }
+        float cr, cg, cb;
+        window_to_samples<W>(my, gl, cur.c0, cur.c1, cur.c2, cr, cg, cb);
+        const float a = cur.a;
         float incl = group_scan_mul<W>(1.f - a, gl);
         float Ti = carry * group_shift_up<W>(incl, gl, 1.f);
         float w = Ti * a;
         ar = fmaf(w, cr, ar);
         ag = fmaf(w, cg, ag);
         ab = fmaf(w, cb, ab);
-        ad = fmaf(w, zz, ad);
+        ad = fmaf(w, cur.z, ad);
         aa += w;
         if (valid) {
             if (out_w) st_stream(out_w + s, w);
             if (out_T) st_stream(out_T + s, Ti);
         }
         carry *= group_bcast<W>(incl, W - 1);
+        cur = nxt;
     }
     ar = group_reduce_add<W>(ar);
     ag = group_reduce_add<W>(ag);
@@ -94,7 +144,10 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
     float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays) {
-    const int gl = threadIdx.x & (W - 1);
+    __shared__ float s_win[kScanThreads / 32][96];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (W - 1);
+    float* my = s_win[threadIdx.x >> 5] + (lane / W) * 3 * W;
     const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / W;
     int start = 0, n = 0;
     if (ray < n_rays) n = load_segment(se, ray, start);
@@ -118,11 +171,13 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan_kernel(
     float my_chunk_T = 1.f;
     {
         float carry = 1.f;
+        float a_cur = gl < n ? __ldg(alpha + start + gl) : 0.f;
         for (int c = 0; c < n_chunks_max; ++c) {
             const int i = c * W + gl;
             const bool valid = i < n;
-            float a = valid ? __ldg(alpha + start + i) : 0.f;
-            float incl = group_scan_mul<W>(1.f - a, gl);
+            float a_nxt = 0.f;
+            if (c + 1 < n_chunks_max && i + W < n) a_nxt = __ldg(alpha + start + i + W);
+            float incl = group_scan_mul<W>(1.f - a_cur, gl);
             if (spill) {
                 float Ti = carry * group_shift_up<W>(incl, gl, 1.f);
                 if (valid) d_alpha[(int64_t)start + i] = Ti;
@@ -130,23 +185,22 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan_kernel(
                 my_chunk_T = carry;
             }
             carry *= group_bcast<W>(incl, W - 1);
+            a_cur = a_nxt;
         }
     }
 
     // pass 2 (right to left): reverse affine scan
     float Rcarry = gT;
+    ScanChunk cur = scan_load_chunk<W>(alpha, rgb, z, start, (n_chunks_max - 1) * W, n, gl);
     for (int c = n_chunks_max - 1; c >= 0; --c) {
+        ScanChunk nxt;
+        if (c > 0) nxt = scan_load_chunk<W>(alpha, rgb, z, start, (c - 1) * W, n, gl);
         const int i = c * W + gl;
         const bool valid = i < n;
         const int64_t s = (int64_t)start + i;
-        float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, zz = 0.f;
-        if (valid) {
-            a = ld_stream(alpha + s);
-            cr = ld_stream(rgb + 3 * s);
-            cg = ld_stream(rgb + 3 * s + 1);
-            cb = ld_stream(rgb + 3 * s + 2);
-            zz = ld_stream(z + s);
-        }
+        float cr, cg, cb;
+        window_to_samples<W>(my, gl, cur.c0, cur.c1, cur.c2, cr, cg, cb);
+        const float a = cur.a, zz = cur.z;
         float Ti;
         if (spill) {
             Ti = valid ? d_alpha[s] : 0.f;
@@ -164,15 +218,22 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan_kernel(
         float Rprev = fmaf(A, Rcarry, B);
         float Ri = __shfl_down_sync(VS_FULL_MASK, Rprev, 1, W);
         if (gl == W - 1) Ri = Rcarry;
+        const float w = Ti * a;
+        float o0, o1, o2;
+        samples_to_window<W>(my, gl, gr * w, gg * w, gb * w, o0, o1, o2);
+        {
+            const int64_t w0 = 3 * ((int64_t)start + c * W);
+            const int lim = 3 * (n - c * W);
+            if (gl < lim) st_stream(d_rgb + w0 + gl, o0);
+            if (gl + W < lim) st_stream(d_rgb + w0 + gl + W, o1);
+            if (gl + 2 * W < lim) st_stream(d_rgb + w0 + gl + 2 * W, o2);
+        }
         if (valid) {
-            const float w = Ti * a;
             st_stream(d_alpha + s, Ti * (gi - Ri));
-            st_stream(d_rgb + 3 * s, gr * w);
-            st_stream(d_rgb + 3 * s + 1, gg * w);
-            st_stream(d_rgb + 3 * s + 2, gb * w);
             if (d_z) st_stream(d_z + s, gd * w);
         }
         Rcarry = group_bcast<W>(Rprev, 0);
+        cur = nxt;
     }
 }
 
