@@ -199,6 +199,7 @@ __device__ __forceinline__ void sh_eval(float x, float y, float z, int n_sh, flo
     }
 }
 
+template <int ACT>  // 0 ReLU, 1 GELU: compile-time so the epilogue loop carries no branch
 __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cfg, const uint8_t* __restrict__ blob,
                                                               const float* __restrict__ pos, const float* __restrict__ dirs,
                                                               const float* __restrict__ normals, float* __restrict__ out,
@@ -373,19 +374,25 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
                 for (int c0 = cg * 16; c0 < N; c0 += 64) {
                     float v[16];
                     tmem_ld16(tmem_lane + (uint32_t)c0, v);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
                     __half2 h[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float a = v[2 * j] + bias[c0 + 2 * j];
-                        float b = v[2 * j + 1] + bias[c0 + 2 * j + 1];
-                        if (cfg.activation == 1) {
-                            a = gelu_erf(a);
-                            b = gelu_erf(b);
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = b4[q];
+                        float a0 = v[4 * q] + bb.x, a1 = v[4 * q + 1] + bb.y, a2 = v[4 * q + 2] + bb.z, a3 = v[4 * q + 3] + bb.w;
+                        if (ACT == 1) {
+                            a0 = gelu_erf(a0);
+                            a1 = gelu_erf(a1);
+                            a2 = gelu_erf(a2);
+                            a3 = gelu_erf(a3);
                         } else {
-                            a = fmaxf(a, 0.f);
-                            b = fmaxf(b, 0.f);
+                            a0 = fmaxf(a0, 0.f);
+                            a1 = fmaxf(a1, 0.f);
+                            a2 = fmaxf(a2, 0.f);
+                            a3 = fmaxf(a3, 0.f);
                         }
-                        h[j] = __floats2half2_rn(a, b);
+                        h[2 * q] = __floats2half2_rn(a0, a1);
+                        h[2 * q + 1] = __floats2half2_rn(a2, a3);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(s_a1 + ((size_t)(c0 / 8) * kTileM + row) * 8);
                     dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
@@ -488,7 +495,8 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
         if (mlp_smem_bytes(c) > 227 * 1024) c.prefetch = 0;
         smem = mlp_smem_bytes(c);
     }
-    cudaError_t ce = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = activation == 1 ? mlp_fwd_kernel<1> : mlp_fwd_kernel<0>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return (int)ce;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -496,7 +504,7 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
     const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     const int64_t tiles = div_up(n_samples, kTileM);
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * ctas_per_sm);
-    mlp_fwd_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(c, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
+    kern<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(c, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
                                                                      n_samples, n_valid_dev);
     return launched(1);
 }

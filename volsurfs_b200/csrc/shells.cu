@@ -48,6 +48,7 @@ static_assert(sizeof(Node4) == 128, "Node4 must be one 128-byte line");
 struct Layer {
     Node4* nodes = nullptr;      // device
     float4* tris = nullptr;      // device, 3 float4 per triangle in BVH order; .w of the first = original face index
+    float4* pre = nullptr;       // device, 4 float4 per triangle: (a, idx) (e1 = b-a) (e2 = c-a) (n = e1 x e2), oracle arithmetic
     int32_t* orig_to_bvh = nullptr;  // device
     int32_t n_nodes = 0;
     int64_t n_tris = 0;
@@ -280,23 +281,34 @@ __device__ __forceinline__ float dot_rn(float x0, float x1, float x2, float y0, 
     return __fadd_rn(__fmul_rn(x0, y0), __fadd_rn(__fmul_rn(x1, y1), __fmul_rn(x2, y2)));
 }
 
-// triangle.cuh:42-70 in oracle arithmetic; returns is_hit, leaves t/u/v as computed (t untouched on a miss)
-__device__ __forceinline__ bool tri_test(const float4 A, const float4 Bv, const float4 C, float ox, float oy, float oz, float dx, float dy,
-                                         float dz, float& t, float& u, float& v) {
-    const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
-    const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
+// triangle.cuh:42-70 in oracle arithmetic; returns is_hit, leaves t/u/v as computed.  e1 = b-a, e2 = c-a and n = e1 x e2 do not
+// depend on the ray: they are computed once per triangle by precompute_tri_kernel with the very same rounded operations.
+__device__ __forceinline__ bool tri_test(const float4 A, const float4 E1, const float4 E2, const float4 Nn, float ox, float oy, float oz,
+                                         float dx, float dy, float dz, float& t, float& u, float& v) {
     const float rx = __fsub_rn(ox, A.x), ry = __fsub_rn(oy, A.y), rz = __fsub_rn(oz, A.z);
-    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
-    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
-    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
     const float qx = __fsub_rn(__fmul_rn(ry, dz), __fmul_rn(rz, dy));
     const float qy = __fsub_rn(__fmul_rn(rz, dx), __fmul_rn(rx, dz));
     const float qz = __fsub_rn(__fmul_rn(rx, dy), __fmul_rn(ry, dx));
-    const float D = __fdiv_rn(1.0f, dot_rn(dx, dy, dz, nx, ny, nz));
-    u = __fmul_rn(D, -dot_rn(qx, qy, qz, e2x, e2y, e2z));
-    v = __fmul_rn(D, dot_rn(qx, qy, qz, e1x, e1y, e1z));
-    t = __fmul_rn(D, -dot_rn(nx, ny, nz, rx, ry, rz));
+    const float D = __fdiv_rn(1.0f, dot_rn(dx, dy, dz, Nn.x, Nn.y, Nn.z));
+    u = __fmul_rn(D, -dot_rn(qx, qy, qz, E2.x, E2.y, E2.z));
+    v = __fmul_rn(D, dot_rn(qx, qy, qz, E1.x, E1.y, E1.z));
+    t = __fmul_rn(D, -dot_rn(Nn.x, Nn.y, Nn.z, rx, ry, rz));
     return !(u < 0.0f || u > 1.0f || v < 0.0f || __fadd_rn(u, v) > 1.0f || t < 0.0f);
+}
+
+__global__ void __launch_bounds__(256) precompute_tri_kernel(const float4* __restrict__ tris, float4* __restrict__ pre, int64_t n_tris) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_tris) return;
+    const float4 A = tris[3 * p], Bv = tris[3 * p + 1], C = tris[3 * p + 2];
+    const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
+    const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
+    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    pre[4 * p] = A;
+    pre[4 * p + 1] = make_float4(e1x, e1y, e1z, 0.f);
+    pre[4 * p + 2] = make_float4(e2x, e2y, e2z, 0.f);
+    pre[4 * p + 3] = make_float4(nx, ny, nz, 0.f);
 }
 
 __device__ __forceinline__ void cswap_desc(float& ka, int& va, float& kb, int& vb) {  // larger key first
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
     mbar_wait(&bar, 0);
 
     const Node4* __restrict__ gnodes = L.nodes;
-    const float4* __restrict__ tris = L.tris;
+    const float4* __restrict__ pre = L.pre;
     const int64_t out_base = (int64_t)blockIdx.y * n_rays;  // outputs are [n_layers_traced, n_rays]
 
     for (int it = 0; it < kRaysPerThread; ++it) {
@@ -345,22 +357,78 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
         int stack_ref[kStack];
         float stack_t[kStack];
         int sp = 0;
-        stack_ref[sp] = 0;  // the root is wide node 0
-        stack_t[sp] = -FLT_MAX;
-        ++sp;
-        while (sp > 0) {
-            --sp;
-            const int ref = stack_ref[sp];
-            if (stack_t[sp] > best_t) continue;
-            if (ref < 0) {
+        // "while-while" traversal: every lane first descends through inner nodes until its current entry is a leaf, then the
+        // lanes of the warp test their leaves together (the triangle test is the expensive, otherwise badly diverged part)
+        int ref = 0;            // current entry: >= 0 wide node index (0 = root), < 0 leaf
+        float ref_t = -FLT_MAX;  // its entry distance
+        bool alive = true;
+        auto pop = [&]() {
+            while (sp > 0) {
+                --sp;
+                if (stack_t[sp] <= best_t) {
+                    ref = stack_ref[sp];
+                    ref_t = stack_t[sp];
+                    return true;
+                }
+            }
+            return false;
+        };
+        while (alive) {
+            while (alive && ref >= 0) {
+                const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
+                const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
+                const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
+                const float4 hiy = *reinterpret_cast<const float4*>(nd->hiy), hiz = *reinterpret_cast<const float4*>(nd->hiz);
+                const int4 ch = *reinterpret_cast<const int4*>(nd->child);
+                float tn[4];
+                int cr[4] = {ch.x, ch.y, ch.z, ch.w};
+                const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
+                const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float t0x = (lx[i] - ox) * idx_, t1x = (hx[i] - ox) * idx_;
+                    const float t0y = (ly[i] - oy) * idy, t1y = (hy[i] - oy) * idy;
+                    const float t0z = (lz[i] - oz) * idz, t1z = (hz[i] - oz) * idz;
+                    const float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+                    const float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+                    // padded boxes + slack on the far plane keep the test conservative w.r.t. the triangle arithmetic
+                    const bool hit = cr[i] != 0 && tnear <= tfar * 1.0000004f + 1e-30f && tfar >= 0.0f && tnear <= best_t;
+                    tn[i] = hit ? tnear : FLT_MAX;
+                }
+                // descending by entry distance: invalid (FLT_MAX) first, the nearest child last
+                cswap_desc(tn[0], cr[0], tn[2], cr[2]);
+                cswap_desc(tn[1], cr[1], tn[3], cr[3]);
+                cswap_desc(tn[0], cr[0], tn[1], cr[1]);
+                cswap_desc(tn[2], cr[2], tn[3], cr[3]);
+                cswap_desc(tn[1], cr[1], tn[2], cr[2]);
+                if (tn[3] == FLT_MAX) {
+                    alive = pop();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if (tn[i] != FLT_MAX) {
+                            if (sp < kStack) {
+                                stack_ref[sp] = cr[i];
+                                stack_t[sp] = tn[i];
+                                ++sp;
+                            } else {
+                                atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
+                            }
+                        }
+                    }
+                    ref = cr[3];  // continue with the nearest child without a round trip through the stack
+                    ref_t = tn[3];
+                }
+            }
+            if (!alive) break;
+            if (ref_t <= best_t) {
                 const int enc = ~ref;
                 const int first = enc >> 3, cnt = (enc & 7) + 1;
                 for (int k = 0; k < cnt; ++k) {
-                    const float4 A = __ldg(tris + 3 * (int64_t)(first + k));
-                    const float4 Bv = __ldg(tris + 3 * (int64_t)(first + k) + 1);
-                    const float4 C = __ldg(tris + 3 * (int64_t)(first + k) + 2);
+                    const float4* tp = pre + 4 * (int64_t)(first + k);
+                    const float4 A = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2), Nn = __ldg(tp + 3);
                     float t, u, v;
-                    if (tri_test(A, Bv, C, ox, oy, oz, dx, dy, dz, t, u, v)) {
+                    if (tri_test(A, E1, E2, Nn, ox, oy, oz, dx, dy, dz, t, u, v)) {
                         const int oi = __float_as_int(A.w);
                         if (t > 0.0f && (t < best_t || (t == best_t && best_tri >= 0 && oi < best_tri))) {
                             best_t = t;
@@ -370,46 +438,8 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                         }
                     }
                 }
-                continue;
             }
-            const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
-            const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
-            const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
-            const float4 hiy = *reinterpret_cast<const float4*>(nd->hiy), hiz = *reinterpret_cast<const float4*>(nd->hiz);
-            const int4 ch = *reinterpret_cast<const int4*>(nd->child);
-            float tn[4];
-            int cr[4] = {ch.x, ch.y, ch.z, ch.w};
-            const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
-            const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float t0x = (lx[i] - ox) * idx_, t1x = (hx[i] - ox) * idx_;
-                const float t0y = (ly[i] - oy) * idy, t1y = (hy[i] - oy) * idy;
-                const float t0z = (lz[i] - oz) * idz, t1z = (hz[i] - oz) * idz;
-                const float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-                const float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-                // padded boxes + slack on the far plane keep the test conservative w.r.t. the triangle arithmetic
-                const bool hit = cr[i] != 0 && tnear <= tfar * 1.0000004f + 1e-30f && tfar >= 0.0f && tnear <= best_t;
-                tn[i] = hit ? tnear : FLT_MAX;
-            }
-            // far -> near so that the nearest child is popped first
-            cswap_desc(tn[0], cr[0], tn[2], cr[2]);
-            cswap_desc(tn[1], cr[1], tn[3], cr[3]);
-            cswap_desc(tn[0], cr[0], tn[1], cr[1]);
-            cswap_desc(tn[2], cr[2], tn[3], cr[3]);
-            cswap_desc(tn[1], cr[1], tn[2], cr[2]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (tn[i] != FLT_MAX) {
-                    if (sp < kStack) {
-                        stack_ref[sp] = cr[i];
-                        stack_t[sp] = tn[i];
-                        ++sp;
-                    } else {
-                        atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
-                    }
-                }
-            }
+            alive = pop();
         }
         depth_out[out_base + r] = best_t;
         tri_out[out_base + r] = best_tri;
@@ -495,6 +525,7 @@ __global__ void __launch_bounds__(256) shells_normals_kernel(const Layer* __rest
 static void free_layer(Layer& L) {
     if (L.nodes) cudaFree(L.nodes);
     if (L.tris) cudaFree(L.tris);
+    if (L.pre) cudaFree(L.pre);
     if (L.orig_to_bvh) cudaFree(L.orig_to_bvh);
     L = Layer();
 }
@@ -551,6 +582,9 @@ int vs_shells_build(int K, const float* const* verts, const int64_t* n_verts, co
         if ((err = cudaMalloc(&L.orig_to_bvh, sizeof(int32_t) * T)) != cudaSuccess) break;
         if ((err = cudaMemcpy(L.nodes, wide.data(), sizeof(Node4) * wide.size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(L.tris, tris.data(), sizeof(float4) * 3 * T, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&L.pre, sizeof(float4) * 4 * T)) != cudaSuccess) break;
+        precompute_tri_kernel<<<(unsigned)div_up(T, 256), 256>>>(L.tris, L.pre, T);
+        if ((err = cudaDeviceSynchronize()) != cudaSuccess) break;
         if ((err = cudaMemcpy(L.orig_to_bvh, o2b.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice)) != cudaSuccess) break;
     }
     if (err == cudaSuccess) err = cudaMalloc(&S->overflow_dev, sizeof(int));
