@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -296,6 +297,25 @@ __device__ __forceinline__ bool tri_test(const float4 A, const float4 E1, const 
     return !(u < 0.0f || u > 1.0f || v < 0.0f || __fadd_rn(u, v) > 1.0f || t < 0.0f);
 }
 
+// triangle.cuh:42-70 in oracle arithmetic; returns is_hit, leaves t/u/v as computed (t untouched on a miss)
+__device__ __forceinline__ bool tri_test_raw(const float4 A, const float4 Bv, const float4 C, float ox, float oy, float oz, float dx, float dy,
+                                         float dz, float& t, float& u, float& v) {
+    const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
+    const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
+    const float rx = __fsub_rn(ox, A.x), ry = __fsub_rn(oy, A.y), rz = __fsub_rn(oz, A.z);
+    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    const float qx = __fsub_rn(__fmul_rn(ry, dz), __fmul_rn(rz, dy));
+    const float qy = __fsub_rn(__fmul_rn(rz, dx), __fmul_rn(rx, dz));
+    const float qz = __fsub_rn(__fmul_rn(rx, dy), __fmul_rn(ry, dx));
+    const float D = __fdiv_rn(1.0f, dot_rn(dx, dy, dz, nx, ny, nz));
+    u = __fmul_rn(D, -dot_rn(qx, qy, qz, e2x, e2y, e2z));
+    v = __fmul_rn(D, dot_rn(qx, qy, qz, e1x, e1y, e1z));
+    t = __fmul_rn(D, -dot_rn(nx, ny, nz, rx, ry, rz));
+    return !(u < 0.0f || u > 1.0f || v < 0.0f || __fadd_rn(u, v) > 1.0f || t < 0.0f);
+}
+
 __global__ void __launch_bounds__(256) precompute_tri_kernel(const float4* __restrict__ tris, float4* __restrict__ pre, int64_t n_tris) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_tris) return;
@@ -322,6 +342,7 @@ __device__ __forceinline__ void cswap_desc(float& ka, int& va, float& kb, int& v
     }
 }
 
+template <bool WW, bool PRE>
 __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer* __restrict__ layers, int layer_first,
                                                                      const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                      int64_t n_rays, float* __restrict__ depth_out,
@@ -342,6 +363,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
 
     const Node4* __restrict__ gnodes = L.nodes;
     const float4* __restrict__ pre = L.pre;
+    const float4* __restrict__ tris = L.tris;
     const int64_t out_base = (int64_t)blockIdx.y * n_rays;  // outputs are [n_layers_traced, n_rays]
 
     for (int it = 0; it < kRaysPerThread; ++it) {
@@ -354,27 +376,143 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
         float best_t = kMaxDist, best_u = 0.f, best_v = 0.f;
         int best_tri = -1;
 
+        if (WW) {
         int stack_ref[kStack];
-        float stack_t[kStack];
-        int sp = 0;
-        // "while-while" traversal: every lane first descends through inner nodes until its current entry is a leaf, then the
-        // lanes of the warp test their leaves together (the triangle test is the expensive, otherwise badly diverged part)
-        int ref = 0;            // current entry: >= 0 wide node index (0 = root), < 0 leaf
-        float ref_t = -FLT_MAX;  // its entry distance
-        bool alive = true;
-        auto pop = [&]() {
+            float stack_t[kStack];
+            int sp = 0;
+            // "while-while" traversal: every lane first descends through inner nodes until its current entry is a leaf, then the
+            // lanes of the warp test their leaves together (the triangle test is the expensive, otherwise badly diverged part)
+            int ref = 0;            // current entry: >= 0 wide node index (0 = root), < 0 leaf
+            float ref_t = -FLT_MAX;  // its entry distance
+            bool alive = true;
+            auto pop = [&]() {
+                while (sp > 0) {
+                    --sp;
+                    if (stack_t[sp] <= best_t) {
+                        ref = stack_ref[sp];
+                        ref_t = stack_t[sp];
+                        return true;
+                    }
+                }
+                return false;
+            };
+            while (alive) {
+                while (alive && ref >= 0) {
+                    const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
+                    const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
+                    const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
+                    const float4 hiy = *reinterpret_cast<const float4*>(nd->hiy), hiz = *reinterpret_cast<const float4*>(nd->hiz);
+                    const int4 ch = *reinterpret_cast<const int4*>(nd->child);
+                    float tn[4];
+                    int cr[4] = {ch.x, ch.y, ch.z, ch.w};
+                    const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
+                    const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float t0x = (lx[i] - ox) * idx_, t1x = (hx[i] - ox) * idx_;
+                        const float t0y = (ly[i] - oy) * idy, t1y = (hy[i] - oy) * idy;
+                        const float t0z = (lz[i] - oz) * idz, t1z = (hz[i] - oz) * idz;
+                        const float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+                        const float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+                        // padded boxes + slack on the far plane keep the test conservative w.r.t. the triangle arithmetic
+                        const bool hit = cr[i] != 0 && tnear <= tfar * 1.0000004f + 1e-30f && tfar >= 0.0f && tnear <= best_t;
+                        tn[i] = hit ? tnear : FLT_MAX;
+                    }
+                    // descending by entry distance: invalid (FLT_MAX) first, the nearest child last
+                    cswap_desc(tn[0], cr[0], tn[2], cr[2]);
+                    cswap_desc(tn[1], cr[1], tn[3], cr[3]);
+                    cswap_desc(tn[0], cr[0], tn[1], cr[1]);
+                    cswap_desc(tn[2], cr[2], tn[3], cr[3]);
+                    cswap_desc(tn[1], cr[1], tn[2], cr[2]);
+                    if (tn[3] == FLT_MAX) {
+                        alive = pop();
+                    } else {
+    #pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            if (tn[i] != FLT_MAX) {
+                                if (sp < kStack) {
+                                    stack_ref[sp] = cr[i];
+                                    stack_t[sp] = tn[i];
+                                    ++sp;
+                                } else {
+                                    atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
+                                }
+                            }
+                        }
+                        ref = cr[3];  // continue with the nearest child without a round trip through the stack
+                        ref_t = tn[3];
+                    }
+                }
+                if (!alive) break;
+                if (ref_t <= best_t) {
+                    const int enc = ~ref;
+                    const int first = enc >> 3, cnt = (enc & 7) + 1;
+                    for (int k = 0; k < cnt; ++k) {
+                        float4 A;
+                        float t, u, v;
+                        bool ok;
+                        if (PRE) {
+                            const float4* tp = pre + 4 * (int64_t)(first + k);
+                            A = __ldg(tp);
+                            ok = tri_test(A, __ldg(tp + 1), __ldg(tp + 2), __ldg(tp + 3), ox, oy, oz, dx, dy, dz, t, u, v);
+                        } else {
+                            const float4* tp = tris + 3 * (int64_t)(first + k);
+                            A = __ldg(tp);
+                            ok = tri_test_raw(A, __ldg(tp + 1), __ldg(tp + 2), ox, oy, oz, dx, dy, dz, t, u, v);
+                        }
+                        if (ok) {
+                            const int oi = __float_as_int(A.w);
+                            if (t > 0.0f && (t < best_t || (t == best_t && best_tri >= 0 && oi < best_tri))) {
+                                best_t = t;
+                                best_u = u;
+                                best_v = v;
+                                best_tri = oi;
+                            }
+                        }
+                    }
+                }
+                alive = pop();
+            }
+    
+        } else {
+        int stack_ref[kStack];
+            float stack_t[kStack];
+            int sp = 0;
+            stack_ref[sp] = 0;  // the root is wide node 0
+            stack_t[sp] = -FLT_MAX;
+            ++sp;
             while (sp > 0) {
                 --sp;
-                if (stack_t[sp] <= best_t) {
-                    ref = stack_ref[sp];
-                    ref_t = stack_t[sp];
-                    return true;
+                const int ref = stack_ref[sp];
+                if (stack_t[sp] > best_t) continue;
+                if (ref < 0) {
+                    const int enc = ~ref;
+                    const int first = enc >> 3, cnt = (enc & 7) + 1;
+                    for (int k = 0; k < cnt; ++k) {
+                        float4 A;
+                        float t, u, v;
+                        bool ok;
+                        if (PRE) {
+                            const float4* tp = pre + 4 * (int64_t)(first + k);
+                            A = __ldg(tp);
+                            ok = tri_test(A, __ldg(tp + 1), __ldg(tp + 2), __ldg(tp + 3), ox, oy, oz, dx, dy, dz, t, u, v);
+                        } else {
+                            const float4* tp = tris + 3 * (int64_t)(first + k);
+                            A = __ldg(tp);
+                            ok = tri_test_raw(A, __ldg(tp + 1), __ldg(tp + 2), ox, oy, oz, dx, dy, dz, t, u, v);
+                        }
+                        if (ok) {
+                            const int oi = __float_as_int(A.w);
+                            if (t > 0.0f && (t < best_t || (t == best_t && best_tri >= 0 && oi < best_tri))) {
+                                best_t = t;
+                                best_u = u;
+                                best_v = v;
+                                best_tri = oi;
+                            }
+                        }
+                    }
+                    continue;
                 }
-            }
-            return false;
-        };
-        while (alive) {
-            while (alive && ref >= 0) {
                 const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
                 const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
                 const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
@@ -384,7 +522,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                 int cr[4] = {ch.x, ch.y, ch.z, ch.w};
                 const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
                 const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
-#pragma unroll
+    #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float t0x = (lx[i] - ox) * idx_, t1x = (hx[i] - ox) * idx_;
                     const float t0y = (ly[i] - oy) * idy, t1y = (hy[i] - oy) * idy;
@@ -395,51 +533,26 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                     const bool hit = cr[i] != 0 && tnear <= tfar * 1.0000004f + 1e-30f && tfar >= 0.0f && tnear <= best_t;
                     tn[i] = hit ? tnear : FLT_MAX;
                 }
-                // descending by entry distance: invalid (FLT_MAX) first, the nearest child last
+                // far -> near so that the nearest child is popped first
                 cswap_desc(tn[0], cr[0], tn[2], cr[2]);
                 cswap_desc(tn[1], cr[1], tn[3], cr[3]);
                 cswap_desc(tn[0], cr[0], tn[1], cr[1]);
                 cswap_desc(tn[2], cr[2], tn[3], cr[3]);
                 cswap_desc(tn[1], cr[1], tn[2], cr[2]);
-                if (tn[3] == FLT_MAX) {
-                    alive = pop();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (tn[i] != FLT_MAX) {
-                            if (sp < kStack) {
-                                stack_ref[sp] = cr[i];
-                                stack_t[sp] = tn[i];
-                                ++sp;
-                            } else {
-                                atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
-                            }
-                        }
-                    }
-                    ref = cr[3];  // continue with the nearest child without a round trip through the stack
-                    ref_t = tn[3];
-                }
-            }
-            if (!alive) break;
-            if (ref_t <= best_t) {
-                const int enc = ~ref;
-                const int first = enc >> 3, cnt = (enc & 7) + 1;
-                for (int k = 0; k < cnt; ++k) {
-                    const float4* tp = pre + 4 * (int64_t)(first + k);
-                    const float4 A = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2), Nn = __ldg(tp + 3);
-                    float t, u, v;
-                    if (tri_test(A, E1, E2, Nn, ox, oy, oz, dx, dy, dz, t, u, v)) {
-                        const int oi = __float_as_int(A.w);
-                        if (t > 0.0f && (t < best_t || (t == best_t && best_tri >= 0 && oi < best_tri))) {
-                            best_t = t;
-                            best_u = u;
-                            best_v = v;
-                            best_tri = oi;
+    #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (tn[i] != FLT_MAX) {
+                        if (sp < kStack) {
+                            stack_ref[sp] = cr[i];
+                            stack_t[sp] = tn[i];
+                            ++sp;
+                        } else {
+                            atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
                         }
                     }
                 }
             }
-            alive = pop();
+    
         }
         depth_out[out_base + r] = best_t;
         tri_out[out_base + r] = best_tri;
@@ -641,8 +754,17 @@ int vs_shells_trace(const void* handle, const float* rays_o, const float* rays_d
     if (n_rays == 0) return VS_OK;
     VS_CHECK_ARG(rays_o && rays_d && depth_out && tri_out && u_out && v_out);
     dim3 grid((unsigned)div_up(n_rays, kRaysPerBlock), (unsigned)layer_count);
-    shells_trace_kernel<<<grid, kTraceThreads, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_first, rays_o, rays_d, n_rays, depth_out,
-                                                                         tri_out, u_out, v_out, S->overflow_dev);
+    static const int variant = getenv("VS_TRACE_VARIANT") ? atoi(getenv("VS_TRACE_VARIANT")) : 0;  // A/B knob for measurements
+#define VS_TRACE(WW, PRE)                                                                                                               \
+    shells_trace_kernel<WW, PRE><<<grid, kTraceThreads, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_first, rays_o, rays_d, n_rays, \
+                                                                                    depth_out, tri_out, u_out, v_out, S->overflow_dev)
+    switch (variant) {
+        case 1: VS_TRACE(false, true); break;
+        case 2: VS_TRACE(true, false); break;
+        case 3: VS_TRACE(true, true); break;
+        default: VS_TRACE(false, false); break;
+    }
+#undef VS_TRACE
     return launched(1);
 }
 
