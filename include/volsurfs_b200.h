@@ -79,6 +79,18 @@ int vs_sum_bwd(const int32_t* ray_start_end_idx, const float* grad_sum_ray, cons
 int vs_update_dt(const int32_t* ray_start_end_idx, const float* samples_z, const float* ray_exit, const float* ray_max_dt,
                  float* samples_dt, int is_background, int64_t n_rays, int64_t n_samples, void* stream);
 
+/* "next" operators of the same container.  Outputs must be zero-filled by the caller (the reference
+ * returns torch::zeros and skips rays/samples it does not own). */
+/* replaces VolumeRendering::sdf2alpha, src/VolumeRendering.cu:178-229 (kernel VolumeRenderingGPU.cuh:185-243) */
+int vs_sdf2alpha(const int32_t* ray_start_end_idx, const float* samples_dt, const float* samples_sdf, const float* logistic_beta,
+                 float* alpha, int64_t n_rays, int64_t n_samples, void* stream);
+/* replaces VolumeRendering::median_depth_over_rays, src/VolumeRendering.cu:372-416 (kernel :364-409); ref_bug != 0 keeps the
+ * reference's fallback index samples_z[nr_samples-1] (:407) */
+int vs_median_depth(const int32_t* ray_start_end_idx, const float* samples_z, const float* weights, float threshold, float* out,
+                    int64_t n_rays, int64_t n_samples, int ref_bug, void* stream);
+/* replaces VolumeRendering::compute_cdf, src/VolumeRendering.cu:418-465 (kernel :412-471) */
+int vs_compute_cdf(const int32_t* ray_start_end_idx, const float* weights, float* cdf, int64_t n_rays, int64_t n_samples, void* stream);
+
 /* ---- fused compositing (one launch per direction) ------------------------------------------------------------------
  * Replaces the chain cumprod -> alpha*T -> sum_over_rays -> integrate_3d -> integrate_1d of nerf.py:308-334 and equals
  * the dense K-layer torch path volsurfs_py/methods/volsurfs.py:601-640,708.  bgT is the FULL product of (1-alpha).

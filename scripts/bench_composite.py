@@ -71,10 +71,11 @@ if __name__ == "__main__":
     torch.cuda.set_device(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     run(f"shells_allhit_K{args.K}", all_hit_packed(args.rays, args.K), [1, 4, 3], None)  # 5.8 GB of traffic >> L2
-    run("shells_allhit_K9", all_hit_packed(args.rays // 2, 9), [1, 4, 2], None)
+    run("shells_allhit_K9", all_hit_packed(args.rays // 2, 9), [1, 2, 3], None)
     d = dense_layers(1 << 22, 5, seed_offset=1)
     se, a, c, z = pack_dense(d["hit"], d["alpha"], d["rgb"], d["z"])
     d.update(se=se, alpha=a, rgb=c, z=z)
     run("shells_bernoulli0.8_K5", d, [1, 4, 3], flush)
     run("c2_800x800_K5", all_hit_packed(640000, 5), [1, 4], flush)
-    run("c3_nerf_packets", nerf_packets(args.nerf_rays, seed_offset=3), [2], flush)
+    run("c3_nerf_packets", nerf_packets(args.nerf_rays, seed_offset=3), [2, 5, 6, 7, 3], flush)
+    run("nerf_mean24", nerf_packets(args.nerf_rays, seed_offset=5, max_per_ray=128, mean=24.0), [2, 5, 6, 3], flush)

@@ -15,7 +15,7 @@ get_ray_enter get_ray_exit is_empty copy get_values_dim get_max_nr_samples get_n
 set_samples_values remove_samples_values are_samples_values_set update_dt""".split()
 RSP_ATTRS = "samples_idx samples_3d samples_dirs samples_z samples_dt samples_values ray_o ray_d ray_enter ray_exit ray_start_end_idx".split()
 VR_HOT = """cumprod_one_minus_alpha_to_transmittance integrate_with_weights_1d integrate_with_weights_3d sum_over_rays
-cumsum_over_rays cumprod_one_minus_alpha_to_transmittance_backward integrate_with_weights_1d_backward
+cumsum_over_rays sdf2alpha median_depth_over_rays compute_cdf cumprod_one_minus_alpha_to_transmittance_backward integrate_with_weights_1d_backward
 integrate_with_weights_3d_backward sum_over_rays_backward""".split()
 
 

@@ -44,7 +44,7 @@ def _check(se, alpha, rgb, z, grads, mode):
         assert grad_err(got, ob[key]) < TOL, key
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_c1_shells_vs_oracle(mode):
     """BASELINE config 1: 4096 rays x 5 layers, Bernoulli(0.8) hits, exact 0/1 alphas, empty rays."""
     d = dense_layers(4096, 5, seed_offset=1)
@@ -75,7 +75,7 @@ def test_golden_reference_lines(mode):
         assert grad_err(bwd[1], g["fp32_d_rgb"][ray, lay]) < TOL
 
 
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 2, 3, 5, 6, 7])
 def test_c3_nerf_packets_vs_oracle(mode):
     """Variable-length packets up to 1024 samples/ray with 35 % empty rays (config 3 shape, 6k-ray subset)."""
     p = nerf_packets(6000, seed_offset=3)
@@ -87,13 +87,14 @@ def test_long_rays_spill_path():
     """rays longer than W*W = 1024 samples exercise the scratch path of the backward scan kernel"""
     p = nerf_packets(40, seed_offset=4, max_per_ray=3000, mean=1500.0, sigma=0.4, p_empty=0.1)
     assert int(p["counts"].max()) > 1024
-    _check(p["se"], p["alpha"], p["rgb"], p["z"], p, 2)
+    for mode in (2, 3, 5):  # 3: one sample per lane (spills beyond 32*32), 5: quad per lane with 8 lanes (spills beyond 4*8*8)
+        _check(p["se"], p["alpha"], p["rgb"], p["z"], p, mode)
 
 
 @pytest.mark.parametrize("n_rays,K", [(1, 5), (255, 5), (257, 9), (1000, 1)])
 def test_edge_sizes(n_rays, K):
     d = all_hit_packed(n_rays, K)
-    for mode in (1, 2, 4):
+    for mode in (1, 2, 3, 4, 5, 7):
         _check(d["se"], d["alpha"], d["rgb"], d["z"], d, mode)
 
 
@@ -102,7 +103,7 @@ def test_all_empty_and_zero_rays():
 
     se = torch.full((300, 2), -1, dtype=torch.int32)
     e1, e3 = torch.zeros(0, 1), torch.zeros(0, 3)
-    for mode in (0, 1, 2, 4):
+    for mode in (0, 1, 2, 3, 4, 6):
         rgb, depth, acc, bgT = VR.composite(_rsp(se), e1.cuda(), e3.cuda(), e1.cuda(), mode=mode)
         assert torch.all(rgb == 0) and torch.all(depth == 0) and torch.all(acc == 0) and torch.all(bgT == 1)
     rgb, depth, acc, bgT = VR.composite(_rsp(torch.zeros((0, 2), dtype=torch.int32)), e1.cuda(), e3.cuda(), e1.cuda())
@@ -222,3 +223,32 @@ def test_reference_fp32_error_scale():
     our_err = max(grad_err(bwd[0][:, 0], da64), grad_err(bwd[1], dc64))
     print(f"fp32 torch autograd vs fp64: {ref_err:.2e}; CUDA vs fp64: {our_err:.2e}")
     assert our_err < TOL and our_err < 4 * ref_err + 1e-7
+
+
+def test_scan_kernels_on_unaligned_and_gapped_segments():
+    """coarsened scan kernels: ray starts that are not multiples of four, quads shared by neighbouring rays, gaps between rays"""
+    g = torch.Generator().manual_seed(17)
+    n = 3000
+    cnt = torch.randint(0, 40, (n,), generator=g)
+    gap = torch.randint(0, 3, (n,), generator=g)
+    start = torch.cumsum(cnt + gap, 0) - cnt
+    se = torch.stack([start, start + cnt], 1).to(torch.int32)
+    se[cnt == 0] = -1
+    S = int((start + cnt).max()) + 1   # deliberately not a multiple of four
+    d = {"alpha": torch.rand(S, 1, generator=g), "rgb": torch.rand(S, 3, generator=g), "z": torch.rand(S, 1, generator=g),
+         "g_rgb": torch.randn(n, 3, generator=g), "g_depth": torch.randn(n, 1, generator=g), "g_acc": torch.randn(n, 1, generator=g),
+         "g_bgT": torch.randn(n, 1, generator=g)}
+    own = np.zeros(S, bool)
+    for s0, e0 in se.numpy():
+        if e0 > s0:
+            own[s0:e0] = True
+    for mode in (2, 5, 6, 7):
+        fwd, bwd = _run(se, d["alpha"], d["rgb"], d["z"], d, mode)
+        o = oc.fused_composite_forward(se.numpy(), d["alpha"].numpy(), d["rgb"].numpy(), d["z"].numpy(), dtype=np.float64)
+        for got, key in zip(fwd[:4], ("rgb", "depth", "acc", "bgT")):
+            assert rel_err(got, o[key], floor=1e-6) < TOL, (mode, key)
+        assert rel_err(fwd[4][own], o["weights"][own], floor=1e-6) < TOL
+        ob = oc.fused_composite_backward(se.numpy(), d["alpha"].numpy(), d["rgb"].numpy(), d["z"].numpy(), d["g_rgb"].numpy(),
+                                         d["g_depth"].numpy(), d["g_acc"].numpy(), d["g_bgT"].numpy())
+        for got, key in zip(bwd, ("d_alpha", "d_rgb", "d_z")):
+            assert grad_err(got[own], ob[key][own]) < TOL, (mode, key)

@@ -171,3 +171,40 @@ def test_update_dt_and_error_paths():
         VR.cumsum_over_rays(rsp, torch.zeros(S, 1).cuda(), False)  # CHECK(is_compacted), VolumeRendering.cu:331
     with pytest.raises(ValueError):
         rsp.get_ray_max_dt(500)                                    # std::invalid_argument, RaySamplesPacked.cu:58-61
+
+
+def test_next_ops_sdf2alpha_median_cdf():
+    """the remaining simple VolumeRendering operators against the numpy oracle"""
+    from volsurfs_b200.volsurfs import RaySamplesPacked, VolumeRendering as VR
+
+    p = nerf_packets(4000, seed_offset=14, max_per_ray=96, mean=20.0)
+    S = p["alpha"].shape[0]
+    N = p["se"].shape[0]
+    sen = p["se"].numpy()
+    g = torch.Generator().manual_seed(9)
+    rsp = RaySamplesPacked(N, S, 0, 1)
+    rsp.ray_start_end_idx = p["se"].cuda()
+    rsp.samples_z = p["z"].cuda()
+    rsp.samples_dt = p["dt"].cuda()
+    rsp.has_dt = True
+    sdf = (torch.rand(S, 1, generator=g) - 0.5) * 0.2
+    beta = torch.full((S, 1), 64.0) + torch.rand(S, 1, generator=g) * 200
+    alpha = VR.sdf2alpha(rsp, sdf.cuda(), beta.cuda())
+    want = oc.packed_sdf2alpha(sen, p["dt"].numpy(), sdf.numpy(), beta.numpy())
+    assert rel_err(alpha.cpu().numpy(), want, floor=1e-4) < 1e-4  # expf (2 ulp) vs the oracle's double exp near saturated sigmoids
+    n = sen[:, 1] - sen[:, 0]
+    last = sen[n > 0, 1] - 1
+    assert np.all(alpha.cpu().numpy()[last] == 0)  # a ray's last sample keeps alpha 0
+    # weights that sum to 1 per ray -> cdf snapping, and median depth
+    w = torch.rand(S, 1, generator=g)
+    ray_of = torch.repeat_interleave(torch.arange(N), torch.from_numpy(np.maximum(n, 0)))
+    sums = torch.zeros(N).index_add_(0, ray_of, w[:, 0])
+    w = w / sums[ray_of].unsqueeze(1)
+    cdf = VR.compute_cdf(rsp, w.cuda())
+    assert np.array_equal(cdf.cpu().numpy(), oc.packed_compute_cdf(sen, w.numpy()))
+    for thr in (0.5, 0.9, 2.0):  # 2.0 is never reached: exercises the reference's fallback index
+        md = VR.median_depth_over_rays(rsp, w.cuda(), thr)
+        assert np.array_equal(md.cpu().numpy(), oc.packed_median_depth(sen, p["z"].numpy(), w.numpy(), thr, ref_bug=True)), thr
+    rsp.has_dt = False
+    with pytest.raises(RuntimeError):
+        VR.sdf2alpha(rsp, sdf.cuda(), beta.cuda())

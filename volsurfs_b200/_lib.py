@@ -30,6 +30,9 @@ SIGNATURES = {
     "vs_sum_fwd": (c_int, [_P, _P, _P, _P, c_int, _I64, _I64, _P]),
     "vs_sum_bwd": (c_int, [_P, _P, _P, _P, c_int, _I64, _I64, _P]),
     "vs_update_dt": (c_int, [_P, _P, _P, _P, _P, c_int, _I64, _I64, _P]),
+    "vs_sdf2alpha": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "vs_median_depth": (c_int, [_P, _P, _P, c_float, _P, _I64, _I64, c_int, _P]),
+    "vs_compute_cdf": (c_int, [_P, _P, _P, _I64, _I64, _P]),
     "vs_composite_fwd": (c_int, [_P] * 10 + [_I64, _I64, c_int, _P]),
     "vs_composite_bwd": (c_int, [_P] * 11 + [_I64, _I64, c_int, _P]),
     "vs_pack_scratch_bytes": (_I64, [_I64]),

@@ -237,6 +237,263 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// scan family, coarsened: every lane owns an ALIGNED QUAD of samples per chunk (absolute sample indices 4q..4q+3), so alpha / z
+// travel as one 16-byte load and the quad's colours as three; the exclusive cumprod is a 4-element serial product per lane plus ONE
+// shuffle scan over the lanes' totals per 4W samples, the backward recurrence a serial composition of the lane's four affine maps
+// plus ONE reverse shuffle scan.  Chunks are anchored at the ray's start rounded down to a multiple of four; samples outside
+// [start, end) are masked to the identity (alpha = 0).
+// ---------------------------------------------------------------------------------------------------------------------------
+struct Quad {
+    float a[4], z[4], c[12];
+};
+
+__device__ __forceinline__ void load_quad(Quad& q, const float* __restrict__ alpha, const float* __restrict__ rgb,
+                                          const float* __restrict__ z, int64_t q0, int64_t start, int64_t end, int64_t n_samples,
+                                          bool active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q.a[j] = 0.f, q.z[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) q.c[j] = 0.f;
+    if (!active) return;
+    if (q0 + 4 <= n_samples) {  // the whole quad lies inside the arrays: 16-byte loads (bases are 16-byte aligned, q0 % 4 == 0)
+        const float4 a4 = ld_stream4(reinterpret_cast<const float4*>(alpha + q0));
+        const float4 z4 = ld_stream4(reinterpret_cast<const float4*>(z + q0));
+        const float4 c0 = ld_stream4(reinterpret_cast<const float4*>(rgb + 3 * q0));
+        const float4 c1 = ld_stream4(reinterpret_cast<const float4*>(rgb + 3 * q0 + 4));
+        const float4 c2 = ld_stream4(reinterpret_cast<const float4*>(rgb + 3 * q0 + 8));
+        q.a[0] = a4.x, q.a[1] = a4.y, q.a[2] = a4.z, q.a[3] = a4.w;
+        q.z[0] = z4.x, q.z[1] = z4.y, q.z[2] = z4.z, q.z[3] = z4.w;
+        q.c[0] = c0.x, q.c[1] = c0.y, q.c[2] = c0.z, q.c[3] = c0.w, q.c[4] = c1.x, q.c[5] = c1.y;
+        q.c[6] = c1.z, q.c[7] = c1.w, q.c[8] = c2.x, q.c[9] = c2.y, q.c[10] = c2.z, q.c[11] = c2.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (q0 + j < n_samples) {
+                q.a[j] = alpha[q0 + j];
+                q.z[j] = z[q0 + j];
+                q.c[3 * j] = rgb[3 * (q0 + j)];
+                q.c[3 * j + 1] = rgb[3 * (q0 + j) + 1];
+                q.c[3 * j + 2] = rgb[3 * (q0 + j) + 2];
+            }
+        }
+    }
+    // samples of the quad that belong to other rays (before start / at or after end) become identities
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (q0 + j < start || q0 + j >= end) q.a[j] = 0.f;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kScanThreads) composite_fwd_scan4_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
+    float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays, int64_t n_samples) {
+    const int gl = threadIdx.x & (W - 1);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / W;
+    int start = 0, n = 0;
+    if (ray < n_rays) n = load_segment(se, ray, start);
+    const int64_t end = (int64_t)start + n;
+    const int64_t A = (int64_t)start & ~(int64_t)3;
+    const int n_chunks = n > 0 ? (int)((end - A + 4 * W - 1) / (4 * W)) : 0;
+    const int n_chunks_max = warp_max_i32(n_chunks);
+
+    float carry = 1.f;
+    float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+    Quad cur;
+    load_quad(cur, alpha, rgb, z, A + 4 * gl, start, end, n_samples, n > 0 && A + 4 * gl < end);
+    for (int c = 0; c < n_chunks_max; ++c) {
+        const int64_t q0 = A + (int64_t)c * 4 * W + 4 * gl;
+        Quad nxt;
+        if (c + 1 < n_chunks_max) load_quad(nxt, alpha, rgb, z, q0 + 4 * W, start, end, n_samples, n > 0 && q0 + 4 * W < end);
+        float tl[4];
+        float p = 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tl[j] = p;
+            p *= (1.f - cur.a[j]);
+        }
+        const float incl = group_scan_mul<W>(p, gl);
+        const float baseT = carry * group_shift_up<W>(incl, gl, 1.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float Tj = baseT * tl[j];
+            const float w = Tj * cur.a[j];
+            ar = fmaf(w, cur.c[3 * j], ar);
+            ag = fmaf(w, cur.c[3 * j + 1], ag);
+            ab = fmaf(w, cur.c[3 * j + 2], ab);
+            ad = fmaf(w, cur.z[j], ad);
+            aa += w;
+            if ((out_w || out_T) && q0 + j >= start && q0 + j < end) {
+                if (out_w) out_w[q0 + j] = w;
+                if (out_T) out_T[q0 + j] = Tj;
+            }
+        }
+        carry *= group_bcast<W>(incl, W - 1);
+        cur = nxt;
+    }
+    ar = group_reduce_add<W>(ar);
+    ag = group_reduce_add<W>(ag);
+    ab = group_reduce_add<W>(ab);
+    ad = group_reduce_add<W>(ad);
+    aa = group_reduce_add<W>(aa);
+    if (ray < n_rays && gl == 0) {
+        out_rgb[3 * ray] = ar;
+        out_rgb[3 * ray + 1] = ag;
+        out_rgb[3 * ray + 2] = ab;
+        out_depth[ray] = ad;
+        out_acc[ray] = aa;
+        out_bgT[ray] = carry;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kScanThreads) composite_bwd_scan4_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
+    float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays, int64_t n_samples) {
+    const int gl = threadIdx.x & (W - 1);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / W;
+    int start = 0, n = 0;
+    if (ray < n_rays) n = load_segment(se, ray, start);
+    const int64_t end = (int64_t)start + n;
+    const int64_t A = (int64_t)start & ~(int64_t)3;
+    const int n_chunks = n > 0 ? (int)((end - A + 4 * W - 1) / (4 * W)) : 0;
+    const int n_chunks_max = warp_max_i32(n_chunks);
+    if (n_chunks_max == 0) return;
+
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, gT = 0.f;
+    if (n > 0) {
+        gr = __ldg(g_rgb + 3 * ray);
+        gg = __ldg(g_rgb + 3 * ray + 1);
+        gb = __ldg(g_rgb + 3 * ray + 2);
+        gd = __ldg(g_depth + ray);
+        ga = __ldg(g_acc + ray);
+        gT = __ldg(g_bgT + ray);
+    }
+
+    // pass 1 (left to right): transmittance at the start of every chunk; lane c keeps chunk c's value (covers 4*W*W samples),
+    // beyond that the per-sample T is parked in d_alpha and overwritten in pass 2
+    const bool spill = n_chunks_max > W;
+    float my_chunk_T = 1.f;
+    {
+        float carry = 1.f;
+        for (int c = 0; c < n_chunks_max; ++c) {
+            const int64_t q0 = A + (int64_t)c * 4 * W + 4 * gl;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            if (n > 0 && q0 < end) {
+                if (q0 + 4 <= n_samples) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + q0));
+                    a[0] = a4.x, a[1] = a4.y, a[2] = a4.z, a[3] = a4.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (q0 + j < n_samples) a[j] = alpha[q0 + j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (q0 + j < start || q0 + j >= end) a[j] = 0.f;
+            }
+            float tl[4];
+            float p = 1.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                tl[j] = p;
+                p *= (1.f - a[j]);
+            }
+            const float incl = group_scan_mul<W>(p, gl);
+            if (spill) {
+                const float baseT = carry * group_shift_up<W>(incl, gl, 1.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (q0 + j >= start && q0 + j < end) d_alpha[q0 + j] = baseT * tl[j];
+            } else if (gl == c) {
+                my_chunk_T = carry;
+            }
+            carry *= group_bcast<W>(incl, W - 1);
+        }
+    }
+
+    // pass 2 (right to left)
+    float Rcarry = gT;
+    Quad cur;
+    {
+        const int64_t q0 = A + (int64_t)(n_chunks_max - 1) * 4 * W + 4 * gl;
+        load_quad(cur, alpha, rgb, z, q0, start, end, n_samples, n > 0 && q0 < end);
+    }
+    for (int c = n_chunks_max - 1; c >= 0; --c) {
+        const int64_t q0 = A + (int64_t)c * 4 * W + 4 * gl;
+        Quad nxt;
+        if (c > 0) load_quad(nxt, alpha, rgb, z, q0 - 4 * W, start, end, n_samples, n > 0 && q0 - 4 * W < end);
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) valid[j] = q0 + j >= start && q0 + j < end;
+        float T[4];
+        if (spill) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) T[j] = valid[j] ? d_alpha[q0 + j] : 0.f;
+        } else {
+            float p = 1.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                T[j] = p;
+                p *= (1.f - cur.a[j]);
+            }
+            const float incl = group_scan_mul<W>(p, gl);
+            const float baseT = group_bcast<W>(my_chunk_T, c & (W - 1)) * group_shift_up<W>(incl, gl, 1.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) T[j] *= baseT;
+        }
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            g[j] = fmaf(gr, cur.c[3 * j], fmaf(gg, cur.c[3 * j + 1], fmaf(gb, cur.c[3 * j + 2], fmaf(gd, cur.z[j], ga))));
+        // the lane's map M = F_0 o F_1 o F_2 o F_3 with F_j(x) = (1-a_j) x + a_j g_j (identity where alpha was masked to 0)
+        float MA = 1.f, MB = 0.f;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            const float Aj = 1.f - cur.a[j], Bj = cur.a[j] * g[j];
+            MB = fmaf(Aj, MB, Bj);
+            MA = Aj * MA;
+        }
+        group_rscan_affine<W>(MA, MB, gl);
+        const float V = fmaf(MA, Rcarry, MB);  // R just left of this lane's quad
+        float R = __shfl_down_sync(VS_FULL_MASK, V, 1, W);
+        if (gl == W - 1) R = Rcarry;           // R just right of this lane's quad
+        float da[4], dc[12], dz[4];
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            const float w = T[j] * cur.a[j];
+            da[j] = T[j] * (g[j] - R);
+            dc[3 * j] = gr * w;
+            dc[3 * j + 1] = gg * w;
+            dc[3 * j + 2] = gb * w;
+            dz[j] = gd * w;
+            R = fmaf(1.f - cur.a[j], R, cur.a[j] * g[j]);
+        }
+        if (valid[0] && valid[3] && q0 + 4 <= n_samples) {  // whole quad owned by this ray: 16-byte stores
+            st_stream4(reinterpret_cast<float4*>(d_alpha + q0), make_float4(da[0], da[1], da[2], da[3]));
+            st_stream4(reinterpret_cast<float4*>(d_rgb + 3 * q0), make_float4(dc[0], dc[1], dc[2], dc[3]));
+            st_stream4(reinterpret_cast<float4*>(d_rgb + 3 * q0 + 4), make_float4(dc[4], dc[5], dc[6], dc[7]));
+            st_stream4(reinterpret_cast<float4*>(d_rgb + 3 * q0 + 8), make_float4(dc[8], dc[9], dc[10], dc[11]));
+            if (d_z) st_stream4(reinterpret_cast<float4*>(d_z + q0), make_float4(dz[0], dz[1], dz[2], dz[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (valid[j]) {
+                    d_alpha[q0 + j] = da[j];
+                    d_rgb[3 * (q0 + j)] = dc[3 * j];
+                    d_rgb[3 * (q0 + j) + 1] = dc[3 * j + 1];
+                    d_rgb[3 * (q0 + j) + 2] = dc[3 * j + 2];
+                    if (d_z) d_z[q0 + j] = dz[j];
+                }
+            }
+        }
+        Rcarry = group_bcast<W>(V, 0);
+        cur = nxt;
+    }
+}
+
 // =============================================================================================
 // tile family (short segments)
 // =============================================================================================
@@ -567,6 +824,12 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// lanes per ray of the coarsened scan kernels (4 samples per lane): a chunk of 4W samples should be of the order of the mean ray
+static inline int pick_scan4_width(int64_t n_rays, int64_t n_samples) {
+    const double mean = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
+    return mean <= 24.0 ? 8 : (mean <= 96.0 ? 16 : 32);
+}
+
 // shared-memory capacity (in samples) of a tile: 1.25x the mean load of 256 rays, at least 256
 static inline int tile_cap(int64_t n_rays, int64_t n_samples) {
     double mean = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
@@ -582,12 +845,13 @@ using namespace vs;
 
 extern "C" {
 
-// mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = scan family (W from mean), 3 = scan with W=8, 4 = tile family with
-// LDG/STS staging (3 and 4 exist for A/B measurements)
+// mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = coarsened scan family (quad per lane, W from the mean ray length),
+// 3 = one-sample-per-lane scan family, 4 = tile family with LDG/STS staging, 5/6/7 = coarsened scan with W = 8/16/32
+// (3..7 exist for A/B measurements)
 int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, float* out_rgb, float* out_depth,
                      float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples, int mode,
                      void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 4);
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 7);
     if (n_rays == 0) return VS_OK;
     VS_CHECK_ARG(se && out_rgb && out_depth && out_acc && out_bgT);
     VS_CHECK_ARG(n_samples == 0 || (alpha && rgb && z));
@@ -609,7 +873,24 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
             return launched(1);
         }
     }
-    int Wsel = mode == 3 ? 8 : pick_group_width(n_rays, n_samples);
+    const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z);
+    if (mode != 3 && a16) {  // coarsened scan kernels (quad per lane)
+        const int W4 = mode == 5 ? 8 : mode == 6 ? 16 : mode == 7 ? 32 : pick_scan4_width(n_rays, n_samples);
+        const unsigned grid4 = (unsigned)div_up(n_rays * W4, kScanThreads);
+        switch (W4) {
+            case 8:
+                composite_fwd_scan4_kernel<8><<<grid4, kScanThreads, 0, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays, n_samples);
+                break;
+            case 16:
+                composite_fwd_scan4_kernel<16><<<grid4, kScanThreads, 0, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays, n_samples);
+                break;
+            default:
+                composite_fwd_scan4_kernel<32><<<grid4, kScanThreads, 0, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays, n_samples);
+                break;
+        }
+        return launched(1);
+    }
+    int Wsel = pick_group_width(n_rays, n_samples);
     if (Wsel < 8) Wsel = 8;
     const unsigned grid = (unsigned)div_up(n_rays * Wsel, kScanThreads);
     switch (Wsel) {
@@ -629,7 +910,7 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
 int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, const float* g_rgb, const float* g_depth,
                      const float* g_acc, const float* g_bgT, float* d_alpha, float* d_rgb, float* d_z, int64_t n_rays, int64_t n_samples,
                      int mode, void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 4);
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 7);
     if (n_rays == 0 || n_samples == 0) return VS_OK;
     VS_CHECK_ARG(se && alpha && rgb && z && g_rgb && g_depth && g_acc && g_bgT && d_alpha && d_rgb);
     cudaStream_t st = (cudaStream_t)stream;
@@ -651,7 +932,24 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
             return launched(1);
         }
     }
-    int Wsel = mode == 3 ? 8 : pick_group_width(n_rays, n_samples);
+    const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z));
+    if (mode != 3 && a16) {
+        const int W4 = mode == 5 ? 8 : mode == 6 ? 16 : mode == 7 ? 32 : pick_scan4_width(n_rays, n_samples);
+        const unsigned grid4 = (unsigned)div_up(n_rays * W4, kScanThreads);
+        switch (W4) {
+            case 8:
+                composite_bwd_scan4_kernel<8><<<grid4, kScanThreads, 0, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays, n_samples);
+                break;
+            case 16:
+                composite_bwd_scan4_kernel<16><<<grid4, kScanThreads, 0, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays, n_samples);
+                break;
+            default:
+                composite_bwd_scan4_kernel<32><<<grid4, kScanThreads, 0, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays, n_samples);
+                break;
+        }
+        return launched(1);
+    }
+    int Wsel = pick_group_width(n_rays, n_samples);
     if (Wsel < 8) Wsel = 8;
     const unsigned grid = (unsigned)div_up(n_rays * Wsel, kScanThreads);
     switch (Wsel) {

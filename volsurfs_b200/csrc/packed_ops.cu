@@ -289,6 +289,72 @@ __global__ void __launch_bounds__(kThreads) update_dt_kernel(const int32_t* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "next" operators of the same container: NeuS alpha, median depth, cdf.  Their outputs depend on
+// discrete, order-sensitive decisions (first sample whose running sum crosses a threshold, snapping of the last cdf entry), so
+// they keep the reference's one-thread-per-ray left-to-right order instead of a re-associated scan.
+// ---------------------------------------------------------------------------------------------
+// VolumeRenderingGPU.cuh:185-243.  The reference mixes float variables with double literals; C's promotion rules are kept.
+__global__ void __launch_bounds__(kThreads) sdf2alpha_kernel(const int32_t* __restrict__ se, const float* __restrict__ dt,
+                                                             const float* __restrict__ sdf, const float* __restrict__ beta,
+                                                             float* __restrict__ alpha, int64_t n_rays) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    int start;
+    const int n = load_segment(se, ray, start);
+    for (int i = 0; i + 1 < n; ++i) {
+        const int64_t s = (int64_t)start + i;
+        const float d = dt[s], prev = sdf[s], next = sdf[s + 1];
+        const float mid = (float)((double)(prev + next) * 0.5);
+        float c = (float)((double)(next - prev) / ((double)d + 1e-6));
+        c = fminf(fmaxf(c, -1e3f), 0.0f);
+        const double half_step = (double)(c * d) * 0.5;
+        const float prev_e = (float)((double)mid - half_step), next_e = (float)((double)mid + half_step);
+        const float b = beta[s];
+        const float pc = (float)(1.0 / (1.0 + (double)expf(-(prev_e * b))));
+        const float nc = (float)(1.0 / (1.0 + (double)expf(-(next_e * b))));
+        alpha[s] = (float)(((double)(pc - nc) + 1e-6) / ((double)pc + 1e-6));
+    }
+}
+
+// VolumeRenderingGPU.cuh:364-409; ref_bug keeps the fallback index samples_z[nr_samples-1] (no idx_start, :407)
+__global__ void __launch_bounds__(kThreads) median_depth_kernel(const int32_t* __restrict__ se, const float* __restrict__ z,
+                                                                const float* __restrict__ w, float threshold, float* __restrict__ out,
+                                                                int64_t n_rays, int ref_bug) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    int start;
+    const int n = load_segment(se, ray, start);
+    if (n == 0) return;  // output keeps its zero initialisation
+    float run = 0.f;
+    for (int i = 0; i < n; ++i) {
+        run = __fadd_rn(run, w[(int64_t)start + i]);
+        if (run >= threshold) {
+            out[ray] = z[(int64_t)start + i];
+            return;
+        }
+    }
+    out[ray] = ref_bug ? z[n - 1] : z[(int64_t)start + n - 1];
+}
+
+// VolumeRenderingGPU.cuh:412-471: exclusive running sum; rays with < 2 samples are skipped; last entry snapped to 1 when the
+// weights sum to ~1 but the last cdf value is not ~1
+__global__ void __launch_bounds__(kThreads) compute_cdf_kernel(const int32_t* __restrict__ se, const float* __restrict__ w,
+                                                               float* __restrict__ cdf, int64_t n_rays) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    int start;
+    const int n = load_segment(se, ray, start);
+    if (n < 2) return;
+    float run = 0.f, last = 0.f;
+    for (int i = 0; i < n; ++i) {
+        last = run;
+        cdf[(int64_t)start + i] = run;
+        run = __fadd_rn(run, w[(int64_t)start + i]);
+    }
+    if (fabs((double)run - 1.0) < 1e-3 && fabs((double)last - 1.0) > 1e-3) cdf[(int64_t)start + n - 1] = 1.0f;
+}
+
 static inline dim3 grid_for(int64_t n_rays, int W) { return dim3((unsigned)div_up(n_rays * W, kThreads)); }
 
 }  // namespace vs
@@ -429,6 +495,37 @@ int vs_update_dt(const int32_t* se, const float* samples_z, const float* ray_exi
     int Wsel = pick_group_width(n_rays, n_samples);
     VS_DISPATCH_W(Wsel, update_dt_kernel<W><<<grid_for(n_rays, W), kThreads, 0, st>>>(se, samples_z, ray_exit, ray_max_dt, samples_dt,
                                                                                      n_rays, is_background));
+    return launched(1);
+}
+
+// replaces VolumeRendering::sdf2alpha (src/VolumeRendering.cu:178-229); alpha must be zero-filled (last sample of a ray keeps 0)
+int vs_sdf2alpha(const int32_t* se, const float* samples_dt, const float* samples_sdf, const float* logistic_beta, float* alpha,
+                 int64_t n_rays, int64_t n_samples, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0);
+    if (n_rays == 0 || n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(se && samples_dt && samples_sdf && logistic_beta && alpha);
+    sdf2alpha_kernel<<<(unsigned)div_up(n_rays, kThreads), kThreads, 0, (cudaStream_t)stream>>>(se, samples_dt, samples_sdf, logistic_beta,
+                                                                                              alpha, n_rays);
+    return launched(1);
+}
+
+// replaces VolumeRendering::median_depth_over_rays (src/VolumeRendering.cu:372-416); out must be zero-filled
+int vs_median_depth(const int32_t* se, const float* samples_z, const float* weights, float threshold, float* out, int64_t n_rays,
+                    int64_t n_samples, int ref_bug, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0);
+    if (n_rays == 0 || n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(se && samples_z && weights && out);
+    median_depth_kernel<<<(unsigned)div_up(n_rays, kThreads), kThreads, 0, (cudaStream_t)stream>>>(se, samples_z, weights, threshold, out,
+                                                                                                 n_rays, ref_bug);
+    return launched(1);
+}
+
+// replaces VolumeRendering::compute_cdf (src/VolumeRendering.cu:418-465); cdf must be zero-filled
+int vs_compute_cdf(const int32_t* se, const float* weights, float* cdf, int64_t n_rays, int64_t n_samples, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0);
+    if (n_rays == 0 || n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(se && weights && cdf);
+    compute_cdf_kernel<<<(unsigned)div_up(n_rays, kThreads), kThreads, 0, (cudaStream_t)stream>>>(se, weights, cdf, n_rays);
     return launched(1);
 }
 

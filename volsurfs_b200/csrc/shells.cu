@@ -754,15 +754,17 @@ int vs_shells_trace(const void* handle, const float* rays_o, const float* rays_d
     if (n_rays == 0) return VS_OK;
     VS_CHECK_ARG(rays_o && rays_d && depth_out && tri_out && u_out && v_out);
     dim3 grid((unsigned)div_up(n_rays, kRaysPerBlock), (unsigned)layer_count);
-    static const int variant = getenv("VS_TRACE_VARIANT") ? atoi(getenv("VS_TRACE_VARIANT")) : 0;  // A/B knob for measurements
+    // traversal variants kept for A/B measurements (profiles/): 1 = default (per-entry pop, precomputed triangle edges/normal);
+    // 0 = raw vertices; 2/3 = "while-while" traversal (measured slower on B200: 0.86 vs 0.72 ms on the C2 scene)
+    static const int variant = getenv("VS_TRACE_VARIANT") ? atoi(getenv("VS_TRACE_VARIANT")) : 1;
 #define VS_TRACE(WW, PRE)                                                                                                               \
     shells_trace_kernel<WW, PRE><<<grid, kTraceThreads, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_first, rays_o, rays_d, n_rays, \
                                                                                     depth_out, tri_out, u_out, v_out, S->overflow_dev)
     switch (variant) {
-        case 1: VS_TRACE(false, true); break;
+        case 0: VS_TRACE(false, false); break;
         case 2: VS_TRACE(true, false); break;
         case 3: VS_TRACE(true, true); break;
-        default: VS_TRACE(false, false); break;
+        default: VS_TRACE(false, true); break;
     }
 #undef VS_TRACE
     return launched(1);

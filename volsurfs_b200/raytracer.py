@@ -34,19 +34,21 @@ def pack_layer_hits(rays_o, rays_d, depth, tri=None, bary_u=None, bary_v=None, t
     cap = int(total_dev.item()) if exact_size else n_rays * K
     f = dict(dtype=torch.float32, device=dev)
     i32 = dict(dtype=torch.int32, device=dev)
+    # the reference fills unused fields with -1 (RaySamplesPacked.cu:13-48); the capacity-mode fast path leaves them uninitialised
+    filled = (lambda shape: torch.full(shape, -1.0, **f)) if exact_size else (lambda shape: torch.empty(shape, **f))
     out = RaySamplesPacked._from_tensors(
         samples_idx=torch.empty((cap, 1), **i32),
         samples_3d=torch.empty((cap, 3), **f),
         samples_dirs=torch.empty((cap, 3), **f),
         samples_z=torch.empty((cap, 1), **f),
-        samples_dt=torch.full((cap, 1), -1.0, **f),
-        samples_values=torch.full((cap, 1), -1.0, **f),
+        samples_dt=filled((cap, 1)),
+        samples_values=filled((cap, 1)),
         ray_start_end_idx=torch.empty((n_rays, 2), **i32),
         ray_o=rays_o,
         ray_d=rays_d,
-        ray_enter=torch.full((n_rays, 1), -1.0, **f),
-        ray_exit=torch.full((n_rays, 1), -1.0, **f),
-        ray_max_dt=torch.full((n_rays, 1), -1.0, **f),
+        ray_enter=filled((n_rays, 1)),
+        ray_exit=filled((n_rays, 1)),
+        ray_max_dt=filled((n_rays, 1)),
     )
     out.samples_layer = torch.empty((cap,), **i32)
     out.samples_triangle = torch.empty((cap,), **i32) if tri is not None else None
@@ -163,7 +165,8 @@ class ShellTracer:
                               exact_size=exact_size)
         if with_normals:
             S = rsp.get_max_nr_samples()
-            rsp.samples_normals = torch.zeros((S, 3), dtype=torch.float32, device=rec["depth"].device)
+            alloc = torch.zeros if exact_size else torch.empty
+            rsp.samples_normals = alloc((S, 3), dtype=torch.float32, device=rec["depth"].device)
             check(
                 _lib.lib().vs_shells_sample_normals(self._handle, ptr(rsp.samples_layer), ptr(rsp.samples_triangle), S,
                                                     None if exact_size else ptr(rsp.total_dev), ptr(rsp.samples_normals), _stream()),

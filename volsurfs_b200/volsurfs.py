@@ -348,6 +348,39 @@ class VolumeRendering:
         check(_lib.lib().vs_cumsum(ptr(se), ptr(v), ptr(out), int(bool(inverse)), n_rays, v.shape[0], _stream()), "vs_cumsum")
         return out
 
+    # ---- "next" ops of the container: NeuS alpha, median depth, cdf -------------------------------------------
+    @staticmethod
+    def sdf2alpha(ray_samples_packed, samples_sdf, logistic_beta):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "sdf2alpha")
+        if not ray_samples_packed.has_dt:
+            raise RuntimeError("ray_samples_packed should have dt")  # CHECK at VolumeRendering.cu:188
+        sdf = _f32c(samples_sdf, "samples_sdf", 1)
+        beta = _f32c(logistic_beta, "logistic_beta", 1)
+        dt = _f32c(ray_samples_packed.samples_dt, "samples_dt", 1)
+        alpha = torch.zeros_like(sdf)
+        check(_lib.lib().vs_sdf2alpha(ptr(se), ptr(dt), ptr(sdf), ptr(beta), ptr(alpha), n_rays, sdf.shape[0], _stream()), "vs_sdf2alpha")
+        return alpha
+
+    @staticmethod
+    def median_depth_over_rays(ray_samples_packed, samples_weights, threshold):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "median_depth")
+        w = _f32c(samples_weights, "samples_weights", 1)
+        z = _f32c(ray_samples_packed.samples_z, "samples_z", 1)
+        out = torch.zeros((n_rays, 1), dtype=torch.float32, device=w.device)
+        check(
+            _lib.lib().vs_median_depth(ptr(se), ptr(z), ptr(w), float(threshold), ptr(out), n_rays, w.shape[0], 1, _stream()),
+            "vs_median_depth",
+        )
+        return out
+
+    @staticmethod
+    def compute_cdf(ray_samples_packed, samples_weights):
+        se, n_rays = VolumeRendering._prep(ray_samples_packed, "compute_cdf")
+        w = _f32c(samples_weights, "samples_weights", 1)
+        cdf = torch.zeros_like(w)
+        check(_lib.lib().vs_compute_cdf(ptr(se), ptr(w), ptr(cdf), n_rays, w.shape[0], _stream()), "vs_compute_cdf")
+        return cdf
+
     # ---- backward ops --------------------------------------------------------------------------------------------
     @staticmethod
     def cumprod_one_minus_alpha_to_transmittance_backward(
