@@ -87,7 +87,7 @@ def test_long_rays_spill_path():
     """rays longer than W*W = 1024 samples exercise the scratch path of the backward scan kernel"""
     p = nerf_packets(40, seed_offset=4, max_per_ray=3000, mean=1500.0, sigma=0.4, p_empty=0.1)
     assert int(p["counts"].max()) > 1024
-    for mode in (2, 3, 5):  # 3: one sample per lane (spills beyond 32*32), 5: quad per lane with 8 lanes (spills beyond 4*8*8)
+    for mode in (2, 3, 5):  # 2: one sample per lane (spills beyond 32*32), 5: quad per lane with 8 lanes (spills beyond 4*8*8)
         _check(p["se"], p["alpha"], p["rgb"], p["z"], p, mode)
 
 
@@ -242,7 +242,7 @@ def test_scan_kernels_on_unaligned_and_gapped_segments():
     for s0, e0 in se.numpy():
         if e0 > s0:
             own[s0:e0] = True
-    for mode in (2, 5, 6, 7):
+    for mode in (2, 3, 5, 6, 7):
         fwd, bwd = _run(se, d["alpha"], d["rgb"], d["z"], d, mode)
         o = oc.fused_composite_forward(se.numpy(), d["alpha"].numpy(), d["rgb"].numpy(), d["z"].numpy(), dtype=np.float64)
         for got, key in zip(fwd[:4], ("rgb", "depth", "acc", "bgT")):

@@ -191,7 +191,8 @@ def test_next_ops_sdf2alpha_median_cdf():
     beta = torch.full((S, 1), 64.0) + torch.rand(S, 1, generator=g) * 200
     alpha = VR.sdf2alpha(rsp, sdf.cuda(), beta.cuda())
     want = oc.packed_sdf2alpha(sen, p["dt"].numpy(), sdf.numpy(), beta.numpy())
-    assert rel_err(alpha.cpu().numpy(), want, floor=1e-4) < 1e-4  # expf (2 ulp) vs the oracle's double exp near saturated sigmoids
+    # expf (2 ulp) vs the oracle's double exp; alpha = (pc - nc + 1e-6)/(pc + 1e-6) cancels when pc ~ nc: absolute 1e-6 on [0,1]
+    assert rel_err(alpha.cpu().numpy(), want, floor=1e-2) < 1e-4
     n = sen[:, 1] - sen[:, 0]
     last = sen[n > 0, 1] - 1
     assert np.all(alpha.cpu().numpy()[last] == 0)  # a ray's last sample keeps alpha 0

@@ -845,9 +845,10 @@ using namespace vs;
 
 extern "C" {
 
-// mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = coarsened scan family (quad per lane, W from the mean ray length),
-// 3 = one-sample-per-lane scan family, 4 = tile family with LDG/STS staging, 5/6/7 = coarsened scan with W = 8/16/32
-// (3..7 exist for A/B measurements)
+// mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = scan family (one sample per lane, W from the mean ray length),
+// 3 = coarsened scan family (aligned quad per lane, float4 loads; W auto), 4 = tile family with LDG/STS staging,
+// 5/6/7 = coarsened scan with W = 8/16/32.  3..7 exist for A/B measurements: on B200 the coarsened kernels measured SLOWER
+// than the one-sample-per-lane ones (profiles/r01_bench_composite_scan_variants.jsonl), so auto never picks them.
 int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, float* out_rgb, float* out_depth,
                      float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples, int mode,
                      void* stream) {
@@ -874,7 +875,7 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
         }
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z);
-    if (mode != 3 && a16) {  // coarsened scan kernels (quad per lane)
+    if ((mode == 3 || mode >= 5) && a16) {  // coarsened scan kernels (quad per lane)
         const int W4 = mode == 5 ? 8 : mode == 6 ? 16 : mode == 7 ? 32 : pick_scan4_width(n_rays, n_samples);
         const unsigned grid4 = (unsigned)div_up(n_rays * W4, kScanThreads);
         switch (W4) {
@@ -933,7 +934,7 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
         }
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z));
-    if (mode != 3 && a16) {
+    if ((mode == 3 || mode >= 5) && a16) {
         const int W4 = mode == 5 ? 8 : mode == 6 ? 16 : mode == 7 ? 32 : pick_scan4_width(n_rays, n_samples);
         const unsigned grid4 = (unsigned)div_up(n_rays * W4, kScanThreads);
         switch (W4) {
