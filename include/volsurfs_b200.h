@@ -177,6 +177,22 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
                    int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, int64_t n_samples,
                    const int64_t* n_valid_dev, int variant, void* stream);
 
+/* ---- appearance head, backward (training) -------------------------------------------------------------------------------------
+ * Replaces torch autograd through RGB.forward / MLP.forward (models/rgb.py:104-149, models/mlp.py:38-52) in the training step of
+ * volsurfs_py/methods/volsurfs.py (loss.backward() in trainer.py): gradients of the Linear weights/biases and of the positional
+ * features (the permutohedral encoder's output).  SH features, normals and the alpha decay carry no gradient (no_grad in the
+ * reference).  The forward pass is recomputed inside the kernel; nothing has to be saved by vs_mlp_forward. */
+/* number of fp32 parameter gradients, laid out [W_0 | b_0 | W_1 | b_1 | ...] with torch.nn.Linear layouts; < 0 on error */
+int64_t vs_mlp_num_params(int n_layers, const int* dims);
+/* bytes of 16-byte aligned device scratch for vs_mlp_backward on n_samples samples; < 0 on error / unsupported widths */
+int64_t vs_mlp_backward_workspace_bytes(int n_layers, const int* dims, int pos_dim, int sh_degree, int normal_dep, int64_t n_samples);
+/* d_out [n_samples,out] upstream gradient of vs_mlp_forward's output; d_pos [n_samples,pos_dim] or NULL; d_params flat fp32
+ * (overwritten, or added to when accumulate != 0).  Deterministic (fixed summation order for a given grid). */
+int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
+                    int alpha_decay, const float* pos, const float* dirs, const float* normals, const float* d_out, float* d_pos,
+                    float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, int variant,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,93 @@ def test_repack_on_parameter_update_and_capacity_mode():
     nv = torch.tensor([300], dtype=torch.int64, device="cuda")
     head(pos, dirs, n_valid_dev=nv, out=out)
     assert torch.equal(out[:300], b[:300]) and bool((out[300:] == -7.0).all())
+
+
+# ---- backward (csrc/mlp_bwd.cu) -------------------------------------------------------------------------------------------------
+# The kernel multiplies fp16 operands (activations, loss-scaled dZ) with fp32 accumulation; the torch fp32 autograd of the oracle is
+# the reference.  Tolerance (stated here): every gradient tensor within 1e-2 under conftest.grad_err (relative to
+# max(|entry|, rms of the tensor)) for the parameter gradients (sums over all samples: rounding averages out; observed ~4e-3); the
+# per-sample input gradient has no such averaging, its WORST entry out of millions is held to 3e-2 and its rms error to 5e-3 of the
+# tensor's rms (observed 1e-2 / 1e-3).  Observed values are printed.
+GRAD_TOL = 1e-2
+DPOS_TOL_MAX, DPOS_TOL_RMS = 3e-2, 5e-3
+
+
+def _check_grad_errs(errs):
+    assert max(v for k, v in errs.items() if not k.startswith("dpos")) < GRAD_TOL, errs
+    assert errs["dpos"] < DPOS_TOL_MAX and errs["dpos_rms"] < DPOS_TOL_RMS, errs
+
+
+def _bwd_case(hidden, out_dim, normal_dep, act, n, g_scale, alpha_decay, variant=0, n_valid=None):
+    from conftest import grad_err
+    from volsurfs_b200.appearance import AppearanceHead
+
+    g = torch.Generator().manual_seed(n + 7)
+    pos = (torch.rand(n, 51, generator=g) * 2 - 1)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+    normals = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+    g_out = torch.randn(n, out_dim, generator=g) * g_scale
+    in_dim = 51 + 16 + (3 if normal_dep else 0)
+    Ws, bs = oa.init_linear_stack(in_dim, hidden, out_dim, seed=n + 1)
+    m = n if n_valid is None else n_valid
+    # oracle: torch fp32 autograd through the restated head (decay is a constant factor: no_grad in the reference)
+    Wo = [w.clone().requires_grad_(True) for w in Ws]
+    bo = [b.clone().requires_grad_(True) for b in bs]
+    po = pos[:m].clone().requires_grad_(True)
+    want = oa.head_forward(po, dirs[:m], normals[:m], Wo, bo, 3, normal_dep, act)
+    if alpha_decay:
+        with torch.no_grad():
+            dec = oa.alpha_decay(torch.ones_like(want), dirs[:m], normals[:m])
+        want = want * dec
+    (want * g_out[:m]).sum().backward()
+
+    head = AppearanceHead(51, hidden, out_dim, 3, normal_dep, act, alpha_decay=alpha_decay).cuda().load_linear_stack(Ws, bs)
+    pg = pos.cuda().requires_grad_(True)
+    nv = None if n_valid is None else torch.tensor([n_valid], dtype=torch.int64, device="cuda")
+    out = head(pg, dirs.cuda(), normals.cuda(), n_valid_dev=nv, _variant=variant)
+    assert out.requires_grad
+    (out[:m] * g_out[:m].cuda()).sum().backward()
+    torch.cuda.synchronize()
+    errs = {}
+    for i, lin in enumerate(head.layers):
+        errs[f"dW{i}"] = grad_err(lin.weight.grad.cpu().numpy(), Wo[i].grad.numpy())
+        errs[f"db{i}"] = grad_err(lin.bias.grad.cpu().numpy(), bo[i].grad.numpy())
+    errs["dpos"] = grad_err(pg.grad[:m].cpu().numpy(), po.grad.numpy())
+    errs["dpos_rms"] = float((pg.grad[:m].cpu() - po.grad).double().pow(2).mean().sqrt() / po.grad.double().pow(2).mean().sqrt())
+    if n_valid is not None:
+        assert float(pg.grad[m:].abs().max()) == 0.0
+    return errs
+
+
+@pytest.mark.parametrize("hidden,out_dim,normal_dep,act,n,g_scale,decay", [
+    ((128, 128, 64), 3, False, "gelu", 40000, 1.0, False),       # reference default widths (hyper_params.py:15)
+    ((64, 64, 64), 1, True, "gelu", 30001, 1e-6, True),          # config C4 "64-wide", alpha head, tiny upstream gradients
+    ((64, 64), 3, False, "relu", 129, 1e3, False),
+    ((32,), 1, False, "relu", 5, 1.0, False),
+])
+def test_backward_vs_torch_autograd(hidden, out_dim, normal_dep, act, n, g_scale, decay):
+    errs = {v: _bwd_case(hidden, out_dim, normal_dep, act, n, g_scale, decay, variant=v) for v in (0,)}
+    for v, e in errs.items():
+        print(f"variant {v}: " + ", ".join(f"{k}={x:.1e}" for k, x in e.items()))
+    _check_grad_errs(errs[0])
+
+
+def test_backward_capacity_mode_and_accumulate():
+    errs = _bwd_case((64, 64, 64), 3, False, "gelu", 5000, 1.0, False, n_valid=3333)
+    print(errs)
+    _check_grad_errs(errs)
+    from volsurfs_b200.appearance import AppearanceHead
+
+    head = AppearanceHead(51, (64, 64, 64), 3).cuda()
+    g = torch.Generator().manual_seed(11)
+    pos = torch.rand(1000, 51, generator=g).cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(1000, 3, generator=g), dim=1).cuda()
+    d_out = torch.randn(1000, 3, generator=g).cuda()
+    a = torch.zeros(head.num_params(), device="cuda")
+    head.backward_into(pos, dirs, None, d_out, a)
+    b = a.clone()
+    head.backward_into(pos, dirs, None, d_out, b, accumulate=True)
+    assert torch.allclose(b, 2 * a, rtol=1e-6, atol=0)            # accumulate adds; the kernel is deterministic
+    c = torch.zeros_like(a)
+    head.backward_into(pos, dirs, None, d_out, c)
+    assert torch.equal(a, c)

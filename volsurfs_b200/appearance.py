@@ -63,9 +63,18 @@ class AppearanceHead(torch.nn.Module):
             self._blob_key = key
         return self._blob
 
-    @torch.no_grad()
     def forward(self, pos_features, dirs, normals=None, n_valid_dev=None, out=None, _variant: int = 0):
-        """pos_features [S,F] f32, dirs [S,3] f32, normals [S,3] f32 (needed for normal_dep / alpha_decay) -> [S,out_dim] f32"""
+        """pos_features [S,F] f32, dirs [S,3] f32, normals [S,3] f32 (needed for normal_dep / alpha_decay) -> [S,out_dim] f32.
+
+        Differentiable w.r.t. the Linear parameters and ``pos_features`` (fused backward kernel, csrc/mlp_bwd.cu); ``dirs`` and
+        ``normals`` carry no gradient, as in the reference (rgb.py:123-124, volsurfs.py:583-594)."""
+        if torch.is_grad_enabled() and (pos_features.requires_grad or any(p.requires_grad for p in self.parameters())):
+            params = [p for lin in self.layers for p in (lin.weight, lin.bias)]
+            return _HeadFunction.apply(self, pos_features, dirs, normals, n_valid_dev, _variant, *params)
+        with torch.no_grad():
+            return self._forward_impl(pos_features, dirs, normals, n_valid_dev, out, _variant)
+
+    def _forward_impl(self, pos_features, dirs, normals=None, n_valid_dev=None, out=None, _variant: int = 0):
         S = int(pos_features.shape[0])
         pos_features = pos_features.contiguous()
         assert pos_features.dtype == torch.float32 and pos_features.shape[1] == self.pos_dim
@@ -82,3 +91,72 @@ class AppearanceHead(torch.nn.Module):
             "vs_mlp_forward",
         )
         return out
+
+    # ---- backward ----------------------------------------------------------------------------------------------------
+    def num_params(self) -> int:
+        return int(_lib.lib().vs_mlp_num_params(len(self.layers), self._dims_c()))
+
+    def split_flat(self, flat):
+        """views of a flat [W_0 | b_0 | W_1 | b_1 ...] vector shaped like the Linear parameters"""
+        out, o = [], 0
+        for lin in self.layers:
+            n, k = lin.weight.shape
+            out.append(flat[o:o + n * k].view(n, k))
+            o += n * k
+            out.append(flat[o:o + n])
+            o += n
+        return out
+
+    @torch.no_grad()
+    def backward_into(self, pos_features, dirs, normals, d_out, d_params, d_pos=None, accumulate=False, n_valid_dev=None,
+                      _variant: int = 0):
+        """One launch sequence of the fused backward: fills ``d_params`` (flat fp32, ``num_params()`` entries) and, when given,
+        ``d_pos`` [S, pos_dim].  Recomputes the forward pass from the inputs."""
+        L = _lib.lib()
+        S = int(pos_features.shape[0])
+        pos_features = pos_features.contiguous()
+        d_out = d_out.contiguous()
+        assert d_out.dtype == torch.float32 and tuple(d_out.shape) == (S, self.out_dim)
+        assert d_params.dtype == torch.float32 and d_params.numel() == self.num_params() and d_params.is_contiguous()
+        sh = self.sh_degree
+        ws_bytes = int(L.vs_mlp_backward_workspace_bytes(len(self.layers), self._dims_c(), self.pos_dim, sh, int(self.normal_dep), S))
+        if ws_bytes < 0:
+            check(ws_bytes, "vs_mlp_backward_workspace_bytes")
+        ws = getattr(self, "_bwd_ws", None)
+        if ws is None or ws.numel() < ws_bytes or ws.device != pos_features.device:
+            ws = self._bwd_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pos_features.device)
+        check(
+            L.vs_mlp_backward(
+                len(self.layers), self._dims_c(), ptr(self.packed()), self.pos_dim, sh, int(self.normal_dep),
+                1 if self.activation == "gelu" else 0, int(self.alpha_decay), ptr(pos_features),
+                ptr(None if dirs is None else dirs.contiguous()), ptr(None if normals is None else normals.contiguous()), ptr(d_out),
+                ptr(d_pos), ptr(d_params), int(bool(accumulate)), ptr(ws), S, ptr(n_valid_dev), int(_variant), _stream(),
+            ),
+            "vs_mlp_backward",
+        )
+        return d_params, d_pos
+
+
+class _HeadFunction(torch.autograd.Function):
+    """autograd glue: forward = vs_mlp_forward, backward = vs_mlp_backward (parameter gradients returned as views of one flat buffer)"""
+
+    @staticmethod
+    def forward(ctx, head, pos_features, dirs, normals, n_valid_dev, variant, *params):
+        out = head._forward_impl(pos_features, dirs, normals, n_valid_dev, None, variant)
+        ctx.head = head
+        ctx.variant = variant
+        ctx.n_valid_dev = n_valid_dev
+        ctx.need_pos = pos_features.requires_grad
+        ctx.save_for_backward(pos_features, dirs, normals)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        head = ctx.head
+        pos_features, dirs, normals = ctx.saved_tensors
+        flat = torch.empty(head.num_params(), dtype=torch.float32, device=g_out.device)
+        d_pos = torch.zeros_like(pos_features) if ctx.need_pos and ctx.n_valid_dev is not None else (
+            torch.empty_like(pos_features) if ctx.need_pos else None)
+        head.backward_into(pos_features, dirs, normals, g_out, flat, d_pos, False, ctx.n_valid_dev, ctx.variant)
+        ctx.head = None
+        return (None, d_pos, None, None, None, None, *head.split_flat(flat))

@@ -18,71 +18,9 @@
 //
 // Precision: fp16 operands, fp32 accumulation (the reference's default appearance path runs tiny-cuda-nn's fp16 FullyFusedMLP;
 // the legacy torch path is fp32) — parity tolerance for this stage is stated in tests/test_gpu_mlp.py (abs 4e-3 on sigmoid outputs).
-#include <cuda_fp16.h>
-
-#include <algorithm>
-#include <cstring>
-
-#include "vs_common.cuh"
+#include "mlp_common.cuh"
 
 namespace vs {
-
-constexpr int kMlpThreads = 512;   // 16 warps: 4 column groups x 4 lane quarters work on one 128-sample tile
-constexpr int kTileM = 128;
-constexpr int kMaxLayers = 6;
-constexpr int kMaxWidth = 128;     // widest layer (TMEM columns allocated, A1 buffer)
-constexpr int kExtraStride = 21;   // per-row scratch: 16 SH + 3 normal (+ pad to an odd stride: conflict-free)
-
-struct MlpConfig {
-    int n_layers;            // Linear layers (hidden + output)
-    int k_pad[kMaxLayers];   // padded fan-in  (multiple of 16)
-    int n_pad[kMaxLayers];   // padded fan-out (multiple of 16)
-    int w_off[kMaxLayers];   // byte offsets into the packed blob
-    int b_off[kMaxLayers];
-    int blob_bytes;
-    int pos_dim, n_sh, normal_dep, in_dim, out_dim;
-    int activation;          // 0 relu, 1 gelu
-    int alpha_decay;
-    int variant;             // debug: bit0 swaps LBO/SBO in the shared-memory descriptors
-    int a1_width;            // widest hidden layer (size of the activation buffer), tmem_cols: power of two >= widest layer
-    int tmem_cols;
-    int prefetch;            // 1: the feature tile of the CTA's next tile is fetched while the current one is processed
-};
-
-static inline int pad16(int x) { return (x + 15) / 16 * 16; }
-
-// dims = [in, h1, ..., h_{L-1}, out]
-static int mlp_layout(int n_layers, const int* dims, MlpConfig* c) {
-    if (n_layers < 1 || n_layers > kMaxLayers) return VS_ERR_UNSUPPORTED;
-    std::memset(c, 0, sizeof(*c));
-    c->n_layers = n_layers;
-    int off = 0;
-    for (int l = 0; l < n_layers; ++l) {
-        if (dims[l] <= 0 || dims[l + 1] <= 0) return VS_ERR_INVALID_ARG;
-        c->k_pad[l] = pad16(dims[l]);
-        c->n_pad[l] = pad16(dims[l + 1]);
-        if (c->k_pad[l] > kMaxWidth || c->n_pad[l] > kMaxWidth) return VS_ERR_UNSUPPORTED;
-        if (l > 0 && dims[l] % 16 != 0) return VS_ERR_UNSUPPORTED;  // hidden widths must be multiples of 16
-        c->w_off[l] = off;
-        off += c->k_pad[l] * c->n_pad[l] * 2;
-    }
-    for (int l = 0; l < n_layers; ++l) {
-        c->b_off[l] = off;
-        off += c->n_pad[l] * 4;
-    }
-    c->blob_bytes = (off + 15) / 16 * 16;
-    int widest = 16, widest_hidden = 16;
-    for (int l = 0; l < n_layers; ++l) {
-        widest = std::max(widest, c->n_pad[l]);
-        if (l + 1 < n_layers) widest_hidden = std::max(widest_hidden, c->n_pad[l]);
-    }
-    c->a1_width = widest_hidden;
-    c->tmem_cols = widest <= 32 ? 32 : (widest <= 64 ? 64 : 128);
-    c->in_dim = dims[0];
-    c->out_dim = dims[n_layers];
-    if (c->out_dim > 8) return VS_ERR_UNSUPPORTED;
-    return VS_OK;
-}
 
 // ---- packing: torch.nn.Linear weight [N,K] fp32 row-major -> fp16 [K_pad/8][N_pad][8] (UMMA K-major core matrices) ------
 __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K, int n_pad, int k_pad,
@@ -102,102 +40,6 @@ __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __rest
     if (i < n_pad) b_out[i] = (i < N && b != nullptr) ? b[i] : 0.f;
 }
 
-// ---- tcgen05 wrappers -----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T ; fp16 inputs, fp32 accumulate; one instruction covers K = 16
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 16 consecutive fp32 accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor, K-major, no swizzle: element (row, k) of a [rows x K] fp16 operand lives at
-//   (k/8) * LBO + (row/8) * SBO + (row%8) * 16 + (k%8) * 2     with LBO = rows*16 bytes, SBO = 128 bytes
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version of sm_100
-    return d;                // layout_type (bits 61-63) = 0: no swizzle
-}
-__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
-    return (1u << 4)                      // D format: f32
-           | (0u << 7) | (0u << 10)       // A, B format: f16
-           | (0u << 15) | (0u << 16)      // A, B K-major
-           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float gelu_erf(float x) {
-    // 0.5 x (1 + erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.28: 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7 — far below
-    // the fp16 rounding of the result; one MUFU (reciprocal) per activation, everything else on the FMA pipe
-    const float z = fabsf(x) * 0.70710678118f;
-    float p = fmaf(z, 0.0000430638f, 0.0002765672f);
-    p = fmaf(p, z, 0.0001520143f);
-    p = fmaf(p, z, 0.0092705272f);
-    p = fmaf(p, z, 0.0422820123f);
-    p = fmaf(p, z, 0.0705230784f);
-    p = fmaf(p, z, 1.0f);
-    p = p * p;
-    p = p * p;
-    p = p * p;
-    p = p * p;
-    const float e = 1.f - __fdividef(1.f, p);
-    return 0.5f * x * (1.f + copysignf(e, x));
-}
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-
-__device__ __forceinline__ void sh_eval(float x, float y, float z, int n_sh, float* o) {
-    // sphericalharmonics.py:103-150
-    o[0] = 0.28209479177387814f;
-    if (n_sh > 1) {
-        o[1] = -0.4886025119029199f * y;
-        o[2] = 0.4886025119029199f * z;
-        o[3] = -0.4886025119029199f * x;
-    }
-    if (n_sh > 4) {
-        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        o[4] = 1.0925484305920792f * xy;
-        o[5] = -1.0925484305920792f * yz;
-        o[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-        o[7] = -1.0925484305920792f * xz;
-        o[8] = 0.5462742152960396f * (xx - yy);
-        if (n_sh > 9) {
-            o[9] = -0.5900435899266435f * y * (3 * xx - yy);
-            o[10] = 2.890611442640554f * xy * z;
-            o[11] = -0.4570457994644658f * y * (4 * zz - xx - yy);
-            o[12] = 0.3731763325901154f * z * (2 * zz - 3 * xx - 3 * yy);
-            o[13] = -0.4570457994644658f * x * (4 * zz - xx - yy);
-            o[14] = 1.445305721320277f * z * (xx - yy);
-            o[15] = -0.5900435899266435f * x * (xx - 3 * yy);
-        }
-    }
-}
 
 template <int ACT>  // 0 ReLU, 1 GELU: compile-time so the epilogue loop carries no branch
 __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cfg, const uint8_t* __restrict__ blob,

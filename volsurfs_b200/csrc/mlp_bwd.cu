@@ -1,0 +1,613 @@
+// volsurfs_b200 — fused appearance head, BACKWARD, on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Replaces what torch autograd does for the reference's legacy RGB / alpha head in a training step
+//   volsurfs_py/models/rgb.py:104-149, models/mlp.py:8-52 (Linear + GELU stack, sigmoid output), alpha decay volsurfs.py:583-594 (no_grad)
+// i.e. per hidden layer: dZ = dA * act'(Z); dW += dZ^T A; db += sum dZ; dA_prev = dZ W   (cuBLAS SGEMMs + elementwise kernels there)
+// with ONE persistent kernel.  A CTA owns tiles of 128 samples; per tile
+//   1. the forward pass is recomputed exactly like mlp.cu (nothing was saved by the forward kernel), but every layer's fp16
+//      input activations A_l stay resident in shared memory;
+//   2. the output epilogue turns dOut into dZ_last = dOut * decay * s(1-s) * scale (fp16, loss-scaled by a power of two chosen from
+//      max|dOut| on the device);
+//   3. walking the layers backwards, one elected thread issues
+//        dW_l^T (+)= A_l^T dZ_l      M = fan-in (TMEM lanes), N = fan-out, K = the tile's 128 samples — both operands are read
+//                                     MN-major from the very buffers the forward GEMMs read K-major (no transposes in shared memory);
+//                                     the accumulators stay in TMEM for ALL tiles of the CTA (persistent split over CTAs);
+//        db_l: a column of ones appended to A_l (fan-in < 128: the bias gradient is lane K_l of dW_l^T) or a 16-column side GEMM;
+//        Z_{l-1} = A_{l-1} W_{l-1}^T  (recomputed pre-activations, fp32 in TMEM — shared memory cannot hold them next to A_l);
+//      the epilogue reads Z_{l-1}, keeps act'(Z_{l-1}) in registers, then
+//        dA_l = dZ_l W_l             W_l read MN-major from the forward blob (no transposed copy of the weights);
+//      and dZ_{l-1} = dA_l * act'(Z_{l-1}) goes back to shared memory as fp16;
+//   4. the input gradient (first pos_dim columns of dA_0, un-scaled) leaves through shared memory as one TMA bulk store per tile.
+// After its last tile a CTA writes its dW/db accumulators to a per-CTA slice of the workspace; mlp_bwd_reduce_kernel sums the slices
+// in a fixed order (deterministic), removes the loss scale and writes / accumulates the fp32 parameter gradients.
+#include "mlp_common.cuh"
+
+namespace vs {
+
+constexpr int kOnesBytes = kTileM * 16;  // one 8-channel chunk: [128 samples][8 halves], channel 0 == 1
+constexpr int kChunkBytes = kTileM * 16;
+
+struct MlpBwdPlan {
+    int dims[kMaxLayers + 1];  // true layer widths
+    int a_off[kMaxLayers];     // byte offset of A_l (fp16 [k_pad/8][128][8]) from the start of the activation area
+    int fold_bias[kMaxLayers]; // 1: a ones chunk follows A_l, db_l = lane k_pad[l] of dW_l^T; 0: side GEMM into db_col
+    int dw_col[kMaxLayers];    // TMEM column of dW_l^T (n_pad[l] columns)
+    int db_col[kMaxLayers];    // TMEM column of the bias side GEMM (16 columns) or -1
+    int p_off_w[kMaxLayers];   // offsets into the flat parameter-gradient vector [W_0 | b_0 | W_1 | b_1 ...] (torch layouts)
+    int p_off_b[kMaxLayers];
+    int n_params;
+    int act_bytes;             // activation area
+    int dz_bytes;              // dZ buffer (also the TMA landing zone of the features and the staging of the input gradient)
+    int work_cols, tmem_cols;
+    int smem_bytes;
+};
+
+static inline int mlp_bwd_plan(const MlpConfig& c, const int* dims, int pos_dim, MlpBwdPlan* p) {
+    std::memset(p, 0, sizeof(*p));
+    const int L = c.n_layers;
+    for (int l = 0; l <= L; ++l) p->dims[l] = dims[l];
+    int off = 0, col = 0, work = 16, po = 0;
+    for (int l = 0; l < L; ++l) {
+        work = std::max(work, std::max(c.k_pad[l], c.n_pad[l]));
+        p->a_off[l] = off;
+        off += kTileM * c.k_pad[l] * 2;
+        p->fold_bias[l] = c.k_pad[l] + 8 <= kMaxWidth ? 1 : 0;
+        if (p->fold_bias[l]) off += kOnesBytes;
+        p->p_off_w[l] = po;
+        po += dims[l] * dims[l + 1];
+        p->p_off_b[l] = po;
+        po += dims[l + 1];
+    }
+    p->n_params = po;
+    p->act_bytes = off;
+    p->work_cols = work;
+    col = work;
+    for (int l = 0; l < L; ++l) {
+        p->dw_col[l] = col;
+        col += c.n_pad[l];
+        p->db_col[l] = -1;
+        if (!p->fold_bias[l]) {
+            p->db_col[l] = col;
+            col += 16;
+        }
+    }
+    if (col > 512) return VS_ERR_UNSUPPORTED;
+    p->tmem_cols = col <= 32 ? 32 : (col <= 64 ? 64 : (col <= 128 ? 128 : (col <= 256 ? 256 : 512)));
+    int widest = 16;
+    for (int l = 0; l < L; ++l) widest = std::max(widest, c.n_pad[l]);
+    const int stage = ((kTileM * pos_dim + 3) & ~3) * 4;
+    p->dz_bytes = std::max(kTileM * widest * 2, stage);
+    p->dz_bytes = (p->dz_bytes + 127) & ~127;
+    // blob | activations | ones (side GEMM operand) | dZ | extras.  An M = 128 (or N = 16) MN-major operand reads a fixed window
+    // of 16 (2) chunks from its base whatever the true width is: the windows of every buffer must stay inside the allocation.
+    int total = c.blob_bytes + p->act_bytes + kOnesBytes + p->dz_bytes + kTileM * kExtraStride * 4;
+    for (int l = 0; l < L; ++l) total = std::max(total, c.blob_bytes + p->a_off[l] + 16 * kChunkBytes);
+    total = std::max(total, c.blob_bytes + p->act_bytes + kOnesBytes + 16 * kChunkBytes);
+    p->smem_bytes = total + 128;
+    return VS_OK;
+}
+
+// D[tmem] (+)= A * B over nk K-steps of 16; descriptors advance by a_step / b_step bytes per K-step
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t b_addr,
+                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, uint32_t idesc, int nk, bool accumulate) {
+    for (int ks = 0; ks < nk; ++ks) {
+        const uint64_t ad = umma_desc(a_addr + (uint32_t)ks * a_step, a_lbo, a_sbo);
+        const uint64_t bd = umma_desc(b_addr + (uint32_t)ks * b_step, b_lbo, b_sbo);
+        tc_mma_f16(tmem_d, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+    }
+}
+constexpr uint32_t kIdescAMn = 1u << 15, kIdescBMn = 1u << 16;  // operand is MN-major (read "transposed")
+
+__device__ __forceinline__ float gelu_grad(float x) {
+    // d/dx [x Phi(x)] = Phi(x) + x phi(x); Phi from the same erf approximation as gelu_erf
+    const float z = fabsf(x) * 0.70710678118f;
+    float p = fmaf(z, 0.0000430638f, 0.0002765672f);
+    p = fmaf(p, z, 0.0001520143f);
+    p = fmaf(p, z, 0.0092705272f);
+    p = fmaf(p, z, 0.0422820123f);
+    p = fmaf(p, z, 0.0705230784f);
+    p = fmaf(p, z, 1.0f);
+    p = p * p;
+    p = p * p;
+    p = p * p;
+    p = p * p;
+    const float e = 1.f - __fdividef(1.f, p);
+    const float Phi = 0.5f * (1.f + copysignf(e, x));
+    const float phi = 0.3989422804f * __expf(-0.5f * x * x);
+    return fmaf(x, phi, Phi);
+}
+
+// power-of-two loss scale from max|dOut|: max * scale lands in [512, 1024) (fp16 keeps 24 binades below that)
+__device__ __forceinline__ int scale_exponent(float amax) {
+    if (!(amax > 0.f)) return 0;
+    const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+    return max(-100, min(100, 9 - e));
+}
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(127 + e) << 23); }
+
+__global__ void mlp_absmax_kernel(const float* __restrict__ x, int64_t n_rows, int width, const int64_t* __restrict__ n_valid_dev,
+                                  float* __restrict__ out) {
+    int64_t n = n_rows;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    n *= width;
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(VS_FULL_MASK, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));  // non-negative floats order as uints
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kMlpThreads) mlp_bwd_kernel(const MlpConfig cfg, const MlpBwdPlan plan, const uint8_t* __restrict__ blob,
+                                                              const float* __restrict__ pos, const float* __restrict__ dirs,
+                                                              const float* __restrict__ normals, const float* __restrict__ d_out,
+                                                              const float* __restrict__ absmax_dev, float* __restrict__ d_pos,
+                                                              float* __restrict__ partials, int64_t n_samples,
+                                                              const int64_t* __restrict__ n_valid_dev) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_w, bar_in, bar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int row = tid & (kTileM - 1);
+    const int cg = tid >> 7;
+    const int F = cfg.pos_dim;
+    const int L = cfg.n_layers;
+    const int k0 = cfg.k_pad[0];
+
+    uint8_t* s_blob = smem;
+    uint8_t* s_act = s_blob + cfg.blob_bytes;
+    uint8_t* s_ones = s_act + plan.act_bytes;
+    uint8_t* s_dz = s_ones + kOnesBytes;
+    float* s_stage = reinterpret_cast<float*>(s_dz);
+    float* s_extra = reinterpret_cast<float*>(s_dz + plan.dz_bytes);
+
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int64_t n_tiles = (n + kTileM - 1) / kTileM;
+    const int sexp = scale_exponent(*absmax_dev);
+    const float scale = pow2i(sexp), inv_scale = pow2i(-sexp);
+
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_in, 1);
+        mbar_init(&bar_mma, 1);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)plan.tmem_cols);
+    // constant "ones" chunks: channel 0 of every sample is 1
+    if (tid < kTileM) {
+        const uint4 one = make_uint4(0x00003C00u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(s_ones + tid * 16) = one;
+        for (int l = 0; l < L; ++l)
+            if (plan.fold_bias[l]) *reinterpret_cast<uint4*>(s_act + plan.a_off[l] + kTileM * cfg.k_pad[l] * 2 + tid * 16) = one;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tmem_work = tmem_base + lane_off;  // this warp's lanes of the working region (columns 0..work_cols)
+
+    if ((int64_t)blockIdx.x < n_tiles && tid == 0) {
+        mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
+        bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
+    }
+    bool weights_ready = false;
+    uint32_t par_in = 0, par_mma = 0;
+    const bool mn_swap = (cfg.variant & 2) != 0;  // debug: swap LBO/SBO of the MN-major descriptors
+    const uint32_t mn_lbo = mn_swap ? (uint32_t)kChunkBytes : 128u;  // K 8-group stride (8 samples x 16 bytes)
+    const uint32_t mn_sbo = mn_swap ? 128u : (uint32_t)kChunkBytes;  // MN 8-group stride (one chunk of 8 channels)
+    bool first_tile = true;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kTileM;
+        const int rows = (int)min((int64_t)kTileM, n - row0);
+        const bool full = rows == kTileM;
+        const int64_t r = row0 + row;
+        const bool live = row < rows;
+
+        // ---- forward recomputation -------------------------------------------------------------------------------------
+        if (full) {
+            if (tid == 0) {
+                bulk_wait_read_all();  // the previous tile's input-gradient store has finished reading this buffer
+                mbar_arrive_expect_tx(&bar_in, (uint32_t)(kTileM * F * 4));
+                bulk_g2s(s_stage, pos + row0 * F, (uint32_t)(kTileM * F * 4), &bar_in);
+            }
+        } else {
+            if (tid == 0) bulk_wait_read_all();
+            __syncthreads();
+            for (int e = tid; e < rows * F; e += kMlpThreads) s_stage[e] = __ldg(pos + row0 * F + e);
+        }
+        float dx = 0.f, dy = 0.f, dz_ = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+        if (live) {
+            if (dirs != nullptr) {
+                dx = __ldg(dirs + 3 * r);
+                dy = __ldg(dirs + 3 * r + 1);
+                dz_ = __ldg(dirs + 3 * r + 2);
+            }
+            if (normals != nullptr) {
+                nx = __ldg(normals + 3 * r);
+                ny = __ldg(normals + 3 * r + 1);
+                nz = __ldg(normals + 3 * r + 2);
+            }
+        }
+        if (cg == 0) {
+            float sh[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+            sh_eval(dx, dy, dz_, cfg.n_sh, sh);
+            float* ex = s_extra + row * kExtraStride;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ex[i] = sh[i];
+            if (cfg.normal_dep) {
+                ex[cfg.n_sh] = nx;
+                ex[cfg.n_sh + 1] = ny;
+                ex[cfg.n_sh + 2] = nz;
+            }
+        }
+        __syncthreads();
+        if (full) {
+            mbar_wait(&bar_in, par_in);
+            par_in ^= 1;
+        }
+        {
+            __half* s_a0 = reinterpret_cast<__half*>(s_act + plan.a_off[0]);
+            const float* srow = s_stage + row * F;
+            const float* ex = s_extra + row * kExtraStride;
+            const int in_dim = cfg.in_dim;
+            for (int kc = cg; kc < k0 / 8; kc += 4) {
+                __half2 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v2[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = kc * 8 + 2 * j + q;
+                        float v = 0.f;
+                        if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
+                        v2[q] = v;
+                    }
+                    h[j] = __floats2half2_rn(v2[0], v2[1]);
+                }
+                *reinterpret_cast<uint4*>(s_a0 + ((size_t)kc * kTileM + row) * 8) = *reinterpret_cast<const uint4*>(h);
+            }
+        }
+        if (!weights_ready) {
+            mbar_wait(&bar_w, 0);
+            weights_ready = true;
+        }
+
+        for (int l = 0; l < L; ++l) {
+            const int K = cfg.k_pad[l], N = cfg.n_pad[l];
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_gemm(tmem_base, smem_u32(s_act + plan.a_off[l]), kChunkBytes, 128, 2 * kChunkBytes, smem_u32(s_blob + cfg.w_off[l]),
+                           (uint32_t)N * 16, 128, 2 * (uint32_t)N * 16, umma_idesc_f16(kTileM, N), K / 16, false);
+                tc_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, par_mma);
+            par_mma ^= 1;
+            tc_fence_after();
+            const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l]);
+            if (l + 1 < L) {
+                __half* s_next = reinterpret_cast<__half*>(s_act + plan.a_off[l + 1]);
+                for (int c0 = cg * 16; c0 < N; c0 += 64) {
+                    float v[16];
+                    tmem_ld16(tmem_work + (uint32_t)c0, v);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+                    __half2 h[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = b4[q];
+                        float a0 = v[4 * q] + bb.x, a1 = v[4 * q + 1] + bb.y, a2 = v[4 * q + 2] + bb.z, a3 = v[4 * q + 3] + bb.w;
+                        if (ACT == 1) {
+                            a0 = gelu_erf(a0);
+                            a1 = gelu_erf(a1);
+                            a2 = gelu_erf(a2);
+                            a3 = gelu_erf(a3);
+                        } else {
+                            a0 = fmaxf(a0, 0.f);
+                            a1 = fmaxf(a1, 0.f);
+                            a2 = fmaxf(a2, 0.f);
+                            a3 = fmaxf(a3, 0.f);
+                        }
+                        h[2 * q] = __floats2half2_rn(a0, a1);
+                        h[2 * q + 1] = __floats2half2_rn(a2, a3);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(s_next + ((size_t)(c0 / 8) * kTileM + row) * 8);
+                    dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+                    dst[kTileM] = *reinterpret_cast<const uint4*>(&h[4]);
+                }
+            } else if (cg == 0) {
+                // output layer: dZ = dOut * decay * s (1 - s) * scale, fp16, columns >= out_dim are zero (N == 16: two chunks)
+                float v[16];
+                tmem_ld16(tmem_work, v);
+                float decay = 1.f;
+                if (cfg.alpha_decay) {
+                    const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz_ * nz), 0.f), 1.f);
+                    decay = 2.f * sigmoid_f(10.f * dot) - 1.f;
+                }
+                float g[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    g[j] = 0.f;
+                    if (live && j < cfg.out_dim) {
+                        const float s = sigmoid_f(v[j] + bias[j]);
+                        g[j] = __ldg(d_out + r * cfg.out_dim + j) * decay * s * (1.f - s) * scale;
+                    }
+                }
+                __half2 h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(s_dz + (size_t)row * 16);
+                dst[0] = *reinterpret_cast<const uint4*>(h);
+                dst[kTileM] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+
+        // ---- backward ----------------------------------------------------------------------------------------------------
+        for (int l = L - 1; l >= 0; --l) {
+            const int K = cfg.k_pad[l], N = cfg.n_pad[l];
+            const uint32_t a_addr = smem_u32(s_act + plan.a_off[l]);
+            const uint32_t dz_addr = smem_u32(s_dz);
+            const bool want_dx = (l == 0) && d_pos != nullptr;
+            // W_l read MN-major from the forward blob ([k/8][n_pad][8] halves): fan-in groups are n_pad*16 bytes apart, groups of
+            // 8 fan-out rows 128 bytes
+            const uint32_t w_lbo = mn_swap ? (uint32_t)N * 16 : 128u, w_sbo = mn_swap ? 128u : (uint32_t)N * 16;
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                // dW_l^T (+)= A_l^T dZ_l: lanes = fan-in (+ the ones chunk: bias gradient), columns = fan-out
+                issue_gemm(tmem_base + (uint32_t)plan.dw_col[l], a_addr, mn_lbo, mn_sbo, 256, dz_addr, mn_lbo, mn_sbo, 256,
+                           umma_idesc_f16(kTileM, N) | kIdescAMn | kIdescBMn, kTileM / 16, !first_tile);
+                if (!plan.fold_bias[l])  // db_l (+)= dZ_l^T 1: lanes = fan-out, column 0
+                    issue_gemm(tmem_base + (uint32_t)plan.db_col[l], dz_addr, mn_lbo, mn_sbo, 256, smem_u32(s_ones), mn_lbo, mn_sbo, 256,
+                               umma_idesc_f16(kTileM, 16) | kIdescAMn | kIdescBMn, kTileM / 16, !first_tile);
+                if (l > 0) {  // Z_{l-1} again (pre-activations of the layer below)
+                    const int Kp = cfg.k_pad[l - 1], Np = cfg.n_pad[l - 1];
+                    issue_gemm(tmem_base, smem_u32(s_act + plan.a_off[l - 1]), kChunkBytes, 128, 2 * kChunkBytes,
+                               smem_u32(s_blob + cfg.w_off[l - 1]), (uint32_t)Np * 16, 128, 2 * (uint32_t)Np * 16, umma_idesc_f16(kTileM, Np),
+                               Kp / 16, false);
+                } else if (want_dx) {  // dA_0 = dZ_0 W_0 (input gradient)
+                    issue_gemm(tmem_base, dz_addr, kChunkBytes, 128, 2 * kChunkBytes, smem_u32(s_blob + cfg.w_off[0]), w_lbo, w_sbo, 256,
+                               umma_idesc_f16(kTileM, K) | kIdescBMn, N / 16, false);
+                }
+                tc_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, par_mma);
+            par_mma ^= 1;
+            tc_fence_after();
+
+            if (l > 0) {
+                // act'(Z_{l-1}) into registers (this thread's row, its 16-column slices)
+                const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l - 1]);
+                __half2 gq[2][8];
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int c0 = cg * 16 + 64 * it;
+                    if (c0 < K) {
+                        float v[16];
+                        tmem_ld16(tmem_work + (uint32_t)c0, v);
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bb = b4[q];
+                            float a0 = v[4 * q] + bb.x, a1 = v[4 * q + 1] + bb.y, a2 = v[4 * q + 2] + bb.z, a3 = v[4 * q + 3] + bb.w;
+                            if (ACT == 1) {
+                                a0 = gelu_grad(a0);
+                                a1 = gelu_grad(a1);
+                                a2 = gelu_grad(a2);
+                                a3 = gelu_grad(a3);
+                            } else {
+                                a0 = a0 > 0.f ? 1.f : 0.f;
+                                a1 = a1 > 0.f ? 1.f : 0.f;
+                                a2 = a2 > 0.f ? 1.f : 0.f;
+                                a3 = a3 > 0.f ? 1.f : 0.f;
+                            }
+                            gq[it][2 * q] = __floats2half2_rn(a0, a1);
+                            gq[it][2 * q + 1] = __floats2half2_rn(a2, a3);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();  // everyone has read Z: the working columns may be overwritten
+                if (tid == 0) {
+                    tc_fence_after();
+                    // dA_l = dZ_l W_l: A = dZ_l K-major (K = fan-out), B = W_l read MN-major (N = fan-in)
+                    issue_gemm(tmem_base, dz_addr, kChunkBytes, 128, 2 * kChunkBytes, smem_u32(s_blob + cfg.w_off[l]), w_lbo, w_sbo, 256,
+                               umma_idesc_f16(kTileM, K) | kIdescBMn, N / 16, false);
+                    tc_commit(&bar_mma);
+                }
+                mbar_wait(&bar_mma, par_mma);
+                par_mma ^= 1;
+                tc_fence_after();
+                // dZ_{l-1} = dA_l * act'(Z_{l-1}) -> fp16 (every MMA that read dZ_l has completed)
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int c0 = cg * 16 + 64 * it;
+                    if (c0 < K) {
+                        float v[16];
+                        tmem_ld16(tmem_work + (uint32_t)c0, v);
+                        __half2 h[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float2 gg = __half22float2(gq[it][q]);
+                            h[q] = __floats2half2_rn(v[2 * q] * gg.x, v[2 * q + 1] * gg.y);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(s_dz + ((size_t)(c0 / 8) * kTileM + row) * 16);
+                        dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+                        dst[kTileM] = *reinterpret_cast<const uint4*>(&h[4]);
+                    }
+                }
+            } else if (want_dx) {
+                // input gradient: first pos_dim columns of dA_0, un-scaled, through shared memory (dZ_0 is dead now)
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int c0 = cg * 16 + 64 * it;
+                    if (c0 < F) {
+                        float v[16];
+                        tmem_ld16(tmem_work + (uint32_t)c0, v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < F) s_stage[row * F + c0 + j] = v[j] * inv_scale;
+                    }
+                }
+                fence_proxy_async();
+                __syncthreads();
+                if (full) {
+                    if (tid == 0) {
+                        bulk_s2g(d_pos + row0 * F, s_stage, (uint32_t)(kTileM * F * 4));
+                        bulk_commit();
+                    }
+                } else {
+                    for (int e = tid; e < rows * F; e += kMlpThreads) d_pos[row0 * F + e] = s_stage[e];
+                }
+            }
+        }
+        first_tile = false;
+        fence_proxy_async();  // generic writes to the dZ / staging buffer before the next tile's TMA load lands there
+        tc_fence_before();
+        __syncthreads();
+    }
+
+    // ---- this CTA's parameter-gradient accumulators -> its slice of the workspace ---------------------------------------
+    if ((int64_t)blockIdx.x < n_tiles) {
+        tc_fence_after();
+        float* mine = partials + (size_t)blockIdx.x * plan.n_params;
+        for (int l = 0; l < L; ++l) {
+            const int N = cfg.n_pad[l], Kt = plan.dims[l], Nt = plan.dims[l + 1];
+            for (int c0 = cg * 16; c0 < N; c0 += 64) {
+                float v[16];
+                tmem_ld16(tmem_work + (uint32_t)(plan.dw_col[l] + c0), v);
+                if (row < Kt) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < Nt) mine[plan.p_off_w[l] + (c0 + j) * Kt + row] = v[j];
+                } else if (plan.fold_bias[l] && row == cfg.k_pad[l]) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < Nt) mine[plan.p_off_b[l] + c0 + j] = v[j];
+                }
+            }
+            if (!plan.fold_bias[l] && cg == 0) {
+                float v[16];
+                tmem_ld16(tmem_work + (uint32_t)plan.db_col[l], v);
+                if (row < Nt) mine[plan.p_off_b[l] + row] = v[0];
+            }
+        }
+        if (tid == 0) bulk_wait_read_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)plan.tmem_cols);
+}
+
+// d_params[p] (+)= 2^-scale_exp * sum over CTA slices, in slice order
+__global__ void mlp_bwd_reduce_kernel(const float* __restrict__ partials, int n_slices, int n_params, const float* __restrict__ absmax_dev,
+                                      const int64_t* __restrict__ n_valid_dev, int64_t n_samples, float* __restrict__ d_params, int accumulate) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_params) return;
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int64_t tiles = (n + kTileM - 1) / kTileM;
+    const int live = (int)min((int64_t)n_slices, tiles);  // CTAs without a tile wrote nothing
+    float s = 0.f;
+    for (int i = 0; i < live; ++i) s += partials[(size_t)i * n_params + p];
+    s *= pow2i(-scale_exponent(*absmax_dev));
+    d_params[p] = accumulate ? d_params[p] + s : s;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+static int bwd_setup(int n_layers, const int* dims, int pos_dim, int sh_degree, int normal_dep, MlpConfig* c, MlpBwdPlan* p) {
+    if (!dims || pos_dim < 0 || sh_degree > 3) return VS_ERR_INVALID_ARG;
+    int e = mlp_layout(n_layers, dims, c);
+    if (e != VS_OK) return e;
+    const int n_sh = sh_degree < 0 ? 0 : (sh_degree + 1) * (sh_degree + 1);
+    if (dims[0] != pos_dim + n_sh + 3 * (normal_dep ? 1 : 0)) return VS_ERR_INVALID_ARG;
+    c->pos_dim = pos_dim;
+    c->n_sh = n_sh;
+    c->normal_dep = normal_dep ? 1 : 0;
+    e = mlp_bwd_plan(*c, dims, pos_dim, p);
+    if (e != VS_OK) return e;
+    if (p->smem_bytes > 227 * 1024) return VS_ERR_UNSUPPORTED;
+    return VS_OK;
+}
+
+static int bwd_grid(int64_t n_samples) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::min<int64_t>(std::max<int64_t>(div_up(n_samples, kTileM), 1), sms);
+}
+
+// number of fp32 parameter gradients: sum_l dims[l]*dims[l+1] + dims[l+1], laid out [W_0 | b_0 | W_1 | b_1 | ...]; < 0 on error
+int64_t vs_mlp_num_params(int n_layers, const int* dims) {
+    if (!dims || n_layers < 1 || n_layers > kMaxLayers) return VS_ERR_INVALID_ARG;
+    int64_t n = 0;
+    for (int l = 0; l < n_layers; ++l) n += (int64_t)dims[l] * dims[l + 1] + dims[l + 1];
+    return n;
+}
+
+// bytes of device scratch vs_mlp_backward needs for n_samples samples (per-CTA gradient slices + the loss-scale cell); < 0 on error
+int64_t vs_mlp_backward_workspace_bytes(int n_layers, const int* dims, int pos_dim, int sh_degree, int normal_dep, int64_t n_samples) {
+    MlpConfig c;
+    MlpBwdPlan p;
+    int e = bwd_setup(n_layers, dims, pos_dim, sh_degree, normal_dep, &c, &p);
+    if (e != VS_OK) return e;
+    return 256 + (int64_t)bwd_grid(n_samples) * p.n_params * 4;
+}
+
+// Backward of vs_mlp_forward for the same arguments.  d_out: [n_samples, out_dim] upstream gradient.  d_pos: [n_samples, pos_dim]
+// gradient of the positional features (NULL: not needed).  d_params: flat fp32 [vs_mlp_num_params] (overwritten, or added to
+// when accumulate != 0).  workspace: vs_mlp_backward_workspace_bytes bytes, 16-byte aligned.  The alpha decay, the SH features and
+// the normals carry no gradient (the reference evaluates them under no_grad, rgb.py:123-124, volsurfs.py:583-594).
+int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
+                    int alpha_decay, const float* pos, const float* dirs, const float* normals, const float* d_out, float* d_pos,
+                    float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, int variant,
+                    void* stream) {
+    VS_CHECK_ARG(blob && n_samples >= 0 && d_params && workspace);
+    MlpConfig c;
+    MlpBwdPlan p;
+    int e = bwd_setup(n_layers, dims, pos_dim, sh_degree, normal_dep, &c, &p);
+    if (e != VS_OK) return e;
+    VS_CHECK_ARG((c.n_sh == 0 || dirs) && (!(normal_dep || alpha_decay) || normals) && (!alpha_decay || dirs));
+    VS_CHECK_ARG(pos_dim == 0 || pos);
+    VS_CHECK_ARG(n_samples == 0 || d_out);
+    VS_CHECK_ARG((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d_pos) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
+    c.activation = activation;
+    c.alpha_decay = alpha_decay ? 1 : 0;
+    c.variant = variant;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* absmax = reinterpret_cast<float*>(workspace);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+    const int grid = bwd_grid(n_samples);
+    cudaError_t ce = cudaMemsetAsync(absmax, 0, 256, st);
+    if (ce != cudaSuccess) return (int)ce;
+    int launches = 0;
+    if (n_samples > 0) {
+        mlp_absmax_kernel<<<296, 256, 0, st>>>(d_out, n_samples, c.out_dim, n_valid_dev, absmax);
+        auto kern = activation == 1 ? mlp_bwd_kernel<1> : mlp_bwd_kernel<0>;
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+        if (ce != cudaSuccess) return (int)ce;
+        kern<<<grid, kMlpThreads, p.smem_bytes, st>>>(c, p, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, d_out, absmax, d_pos,
+                                                      partials, n_samples, n_valid_dev);
+        launches += 2;
+    }
+    mlp_bwd_reduce_kernel<<<(p.n_params + 255) / 256, 256, 0, st>>>(partials, n_samples > 0 ? grid : 0, p.n_params, absmax, n_valid_dev, n_samples,
+                                                                    d_params, accumulate);
+    return launched(launches + 1);
+}
+
+}  // extern "C"
