@@ -6,7 +6,8 @@
 
 One "step" = one pass of the hot path over one batch of synthetic rays on every rank (rays are sharded, weak scaling):
   K-layer shell intersection (one launch) -> hit packing -> face normals -> rgb head + alpha head (tcgen05 MLPs) ->
-  fused compositing forward -> L1 loss gradient -> fused compositing backward (d_alpha, d_rgb per hit).
+  fused compositing forward -> L1 loss gradient -> fused compositing backward (d_alpha, d_rgb per hit) -> backward of both heads
+  (tcgen05: Linear weight/bias gradients + gradients of the positional features) -> (N > 1) NCCL all-reduce of the head gradients.
 Workload at every N: BASELINE config[1] per GPU — 800x800 camera rays against 5 nested ~100k-triangle shells, legacy
 [128,128,64] GELU heads on 51 positional features (synthetic stand-in for the permutohedral encoder) + SH deg 3.
 
@@ -130,7 +131,11 @@ class CpuReferencePath:
         self.rgb_w = oa.init_linear_stack(POS_DIM + 16, HIDDEN, 3, seed=11)
         self.alpha_w = oa.init_linear_stack(POS_DIM + 16, HIDDEN, 1, seed=12)
         g = torch.Generator().manual_seed(13)
-        self.feats = torch.rand(n_rays, K_LAYERS, POS_DIM, generator=g) * 2 - 1
+        self.feats = (torch.rand(n_rays, K_LAYERS, POS_DIM, generator=g) * 2 - 1).requires_grad_(True)
+        for stack in (self.rgb_w, self.alpha_w):
+            for lst in stack:
+                for t in lst:
+                    t.requires_grad_(True)
         self.gt = torch.rand(n_rays, 3, generator=g)
         self.cores = os.cpu_count() or 1
 
@@ -149,16 +154,16 @@ class CpuReferencePath:
             hits = torch.from_numpy(res["is_hit"])
             normals = torch.from_numpy(res["normals"])[hits]
             dirs = self.d[hits]
-            with torch.no_grad():                                 # heads are evaluated, not differentiated, in this step
-                rgb = oa.head_forward(self.feats[hits, i], dirs, normals, *self.rgb_w)
-                alpha = oa.alpha_decay(oa.head_forward(self.feats[hits, i], dirs, normals, *self.alpha_w), dirs, normals)
-            surfs_rgb[hits, i] = rgb
-            surfs_alpha[hits, i] = alpha
-        surfs_rgb.requires_grad_(True)
-        surfs_alpha.requires_grad_(True)
+            f = self.feats[hits, i]                               # leaf [N,K,F] requires grad: encoder-output gradient
+            rgb = oa.head_forward(f, dirs, normals, *self.rgb_w)
+            alpha = oa.alpha_decay(oa.head_forward(f, dirs, normals, *self.alpha_w), dirs, normals)
+            surfs_rgb = surfs_rgb.index_put((hits, torch.tensor(i)), rgb)
+            surfs_alpha = surfs_alpha.index_put((hits, torch.tensor(i)), alpha)
         out = dense_composite_torch(surfs_alpha, surfs_rgb, rgb_bg=torch.ones(N, 3))   # volsurfs.py:601-640,708 (fp32 variant)
         loss = (out["rgb"] - self.gt).abs().mean()                                       # utils/losses.py:14-19
-        loss.backward()
+        for t in [self.feats, *self.rgb_w[0], *self.rgb_w[1], *self.alpha_w[0], *self.alpha_w[1]]:
+            t.grad = None
+        loss.backward()                                           # autograd: compositing + both heads (weights, biases, features)
         return float(loss.detach())
 
 
@@ -191,8 +196,9 @@ def workload_config(args, world):
         "workload": f"BASELINE config[1]: 5-mesh volsurf render of kitten-shaped synthetic shells (~100k tris/layer), {IMG}x{IMG} rays per GPU",
         "rays_per_gpu": IMG * IMG, "layers": K_LAYERS, "triangles_per_layer": 99904, "heads": f"rgb+alpha legacy MLP {list(HIDDEN)} GELU, "
         f"{POS_DIM} positional features (synthetic encoder output) + SH deg 3",
-        "step": "trace(K layers, 1 launch) + pack + normals + 2 MLP heads fwd + composite fwd + L1 grad + composite bwd",
-        "parallelism": f"rays sharded over {world} GPU(s), no data-path collective", "l2": "inputs_larger_than_l2 (653 MB features + 200 MB packed arrays per step)",
+        "step": "trace(K layers, 1 launch) + pack + normals + 2 MLP heads fwd + composite fwd + L1 grad + composite bwd + 2 MLP heads bwd "
+                "(dW, db, d_features)" + (" + NCCL all-reduce of the head gradients" if world > 1 else ""),
+        "parallelism": f"rays sharded over {world} GPU(s); no data-path collective in rendering, one gradient all-reduce per step in training", "l2": "inputs_larger_than_l2 (653 MB features + 200 MB packed arrays per step)",
     }
 
 
@@ -225,9 +231,18 @@ def run_ours(args, rank, world, local_rank):
     img_pin = torch.empty((N, 3), dtype=torch.float32).pin_memory()
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
 
-    stage_names = ["trace", "pack+normals", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad", "composite_bwd"]
+    from volsurfs_b200.dist import GradAllReducer
+
+    stage_names = ["trace", "pack+normals", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad", "composite_bwd", "mlp_bwd_rgb",
+                   "mlp_bwd_alpha", "grad_allreduce"]
+    n_marks = len(stage_names) + 1
+    grad_rgb = torch.zeros(renderer.rgb_head.num_params(), device=dev)
+    grad_alpha = torch.zeros(renderer.alpha_head.num_params(), device=dev)
+    dfeat_rgb, dfeat_alpha = torch.empty_like(feats), torch.empty_like(feats)
+    reducer = GradAllReducer()
     ev = None
 
+    @torch.no_grad()  # forward and backward kernels are driven explicitly; no autograd graph in the timed region
     def step(record=None):
         def mark(i):
             if record is not None:
@@ -258,6 +273,14 @@ def run_ours(args, rank, world, local_rank):
         mark(6)
         d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
         mark(7)
+        renderer.rgb_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_rgb, grad_rgb, dfeat_rgb, False, rsp.total_dev)
+        reducer.launch([grad_rgb])       # overlaps the alpha head's backward
+        mark(8)
+        renderer.alpha_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_alpha, grad_alpha, dfeat_alpha, False, rsp.total_dev)
+        reducer.launch([grad_alpha])
+        mark(9)
+        reducer.wait()
+        mark(10)
         return out, loss, rsp
 
     def barrier():
@@ -273,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
     assert not renderer.tracer.overflowed()
 
     # ---- timed region: device-resident inputs
-    records = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(args.steps)]
+    records = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     barrier()
     launches0 = lib.vs_launch_count()
@@ -287,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
     launches = lib.vs_launch_count() - launches0
     ms_total = t_start.elapsed_time(t_end)
-    stage_ms = [statistics.mean(records[s][i].elapsed_time(records[s][i + 1]) for s in range(args.steps)) for i in range(7)]
+    stage_ms = [statistics.mean(records[s][i].elapsed_time(records[s][i + 1]) for s in range(args.steps)) for i in range(n_marks - 1)]
 
     # ---- e2e: pinned host rays in, image + loss out, every step
     def e2e_step():
@@ -336,6 +359,9 @@ def run_ours(args, rank, world, local_rank):
         "composite_fwd": ("hbm", 32 * N + 20 * n_hits),
         "loss_grad": ("hbm", N * 12 * 6),
         "composite_bwd": ("hbm", 32 * N + 36 * n_hits),
+        "mlp_bwd_rgb": ("tensor", 2.0 * flops_head(3)),                               # dA + dW GEMMs (the recomputation is not counted)
+        "mlp_bwd_alpha": ("tensor", 2.0 * flops_head(1)),
+        "grad_allreduce": ("hbm", 0.0),
     }
     stages = {}
     for name, ms in zip(stage_names, stage_ms):
@@ -354,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the headline compositing kernels at the size SURVEY 8d prescribes (2^24 rays x 5, traffic >> L2)
     comp = None
     if not args.skip_composite_roofline:
-        del feats
+        del feats, dfeat_rgb, dfeat_alpha
         torch.cuda.empty_cache()
         n_big = 1 << 24
         d = all_hit_packed(n_big, K_LAYERS)
@@ -392,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
         dt = time.perf_counter() - t0
         cpu = {"value": round(path.n_rays * reps / dt / 1e6, 4), "unit": UNIT, "cores": path.cores, "kind": "port",
                "sample": f"{reps} steps x {path.n_rays} rays (rows through the image centre) of the same workload; oracle port of the "
-                         "reference algorithm (C BVH tracer with OpenMP, torch CPU heads, dense torch compositing + autograd)"}
+                         "reference algorithm (C BVH tracer with OpenMP, torch CPU heads, dense torch compositing, autograd through compositing and heads)"}
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

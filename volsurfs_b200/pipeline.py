@@ -29,8 +29,9 @@ class ShellRenderer:
     def shade(self, rsp, pos_features):
         """stage 3: per-hit colour and alpha (volsurfs.py:544-599).  ``pos_features`` [N*K, F]: output of the positional
         encoder for ``rsp.samples_3d`` (the permutohedral encoding is the stage before this path; synthetic in benchmarks)."""
-        rgb = self.rgb_head(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
-        alpha = self.alpha_head(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
+        with torch.no_grad():  # this class drives forward and backward explicitly (render_fwd_bwd); no autograd graph
+            rgb = self.rgb_head(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
+            alpha = self.alpha_head(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
         return rgb, alpha
 
     def composite(self, rsp, alpha, rgb):
@@ -54,15 +55,40 @@ class ShellRenderer:
         out.update(ray_samples_packed=rsp, samples_rgb=rgb, samples_alpha=alpha)
         return out
 
-    def render_fwd_bwd(self, rays_o, rays_d, pos_features, gt_rgb):
+    def heads_backward(self, rsp, pos_features, d_rgb, d_alpha, want_feature_grads=True):
+        """stage 3 backward: per-sample colour / alpha gradients -> Linear parameter gradients of both heads (flat fp32 buffers
+        ``grad_rgb`` / ``grad_alpha``, layout of AppearanceHead.split_flat) and, per head, the gradient of its positional features
+        (every reference RGB model owns its encoder, rgb.py:40-60, so the two feature gradients stay separate)."""
+        out = {}
+        for name, head, g in (("rgb", self.rgb_head, d_rgb), ("alpha", self.alpha_head, d_alpha)):
+            flat = getattr(self, "_grad_" + name, None)
+            if flat is None or flat.device != pos_features.device:
+                flat = torch.zeros(head.num_params(), dtype=torch.float32, device=pos_features.device)
+                setattr(self, "_grad_" + name, flat)
+            d_feat = None
+            if want_feature_grads:
+                d_feat = getattr(self, "_dfeat_" + name, None)
+                if d_feat is None or d_feat.shape != pos_features.shape or d_feat.device != pos_features.device:
+                    d_feat = torch.zeros_like(pos_features)
+                    setattr(self, "_dfeat_" + name, d_feat)
+            head.backward_into(pos_features, rsp.samples_dirs, rsp.samples_normals, g, flat, d_feat, False, rsp.total_dev)
+            out["grad_" + name] = flat
+            out["d_features_" + name] = d_feat
+        return out
+
+    def render_fwd_bwd(self, rays_o, rays_d, pos_features, gt_rgb, heads_backward=True):
         """one pass of the hot path with the L1 photometric loss of the reference (utils/losses.py:14-19):
-        forward, d loss / d pred, compositing backward down to per-sample colour and alpha gradients"""
+        forward, d loss / d pred, compositing backward down to per-sample colour and alpha gradients, then the backward of both
+        appearance heads (parameter gradients + gradients of their positional features)"""
         out = self.render(rays_o, rays_d, pos_features)
         diff = out["rgb"] - gt_rgb
         loss = diff.abs().mean()
         g_pred = torch.sign(diff) / diff.numel()
-        d_alpha, d_rgb = self.composite_backward(out["ray_samples_packed"], out["samples_alpha"], out["samples_rgb"], g_pred)
+        rsp = out["ray_samples_packed"]
+        d_alpha, d_rgb = self.composite_backward(rsp, out["samples_alpha"], out["samples_rgb"], g_pred)
         out.update(loss=loss, d_alpha=d_alpha, d_rgb=d_rgb)
+        if heads_backward:
+            out.update(self.heads_backward(rsp, pos_features, d_rgb, d_alpha))
         return out
 
 
