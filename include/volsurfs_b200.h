@@ -177,6 +177,26 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
                    int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, int64_t n_samples,
                    const int64_t* n_valid_dev, int variant, void* stream);
 
+/* ---- importance sampling chain ------------------------------------------------------------------------------
+ * VolumeRendering::importance_sample (src/VolumeRendering.cu:466-548; kernel VolumeRenderingGPU.cuh:507-678): n_imp samples per ray
+ * drawn from the per-ray cdf (compute_cdf) by inverse-transform sampling, optionally jittered with the reference's pcg32 stream
+ * (rng_state / rng_inc = the generator passed by value; default state 0x853c49e6748fea9b, inc 0xda3e39cb94b95bdb; the caller advances
+ * it by 2^32 after a jittered call, VolumeRendering.cu:520-523).  Output = the UNCOMPACTED packet: ray r owns rows
+ * [r*n_imp, (r+1)*n_imp); rows and out_se of rays without uniform samples are left untouched (pre-fill -1). */
+int vs_importance_sample(const float* rays_o, const float* rays_d, const int32_t* se, const float* z, const float* cdf, int64_t n_rays,
+                         int64_t n_samples, int n_imp, uint64_t rng_state, uint64_t rng_inc, int jitter, float* out_3d, float* out_dirs,
+                         float* out_z, int32_t* out_se, void* stream);
+/* VolumeRendering::combine_ray_samples_packets (src/VolumeRendering.cu:550-669; kernel VolumeRenderingGPU.cuh:680-894).
+ * vs_combine_offsets: out_start[r] = exclusive prefix sum of count1[r]+count2[r] (VolumeRendering.cu:595-603), *total_dev = grand total.
+ * vs_combine_merge: z-ordered merge with the min-distance filter into rows [out_start[r], out_start[r]+written_r) of the combined
+ * (uncompacted) packet; c_se of rays without samples is left untouched (pre-fill -1). */
+int vs_combine_offsets(const int32_t* se1, const int32_t* se2, int64_t n_rays, int32_t* out_start, int64_t* total_dev, void* scratch,
+                       void* stream);
+int vs_combine_merge(int64_t n_rays, float min_dist, int values_dim, const int32_t* se1, const int32_t* idx1, const float* p1, const float* d1,
+                     const float* z1, const float* v1, const int32_t* se2, const int32_t* idx2, const float* p2, const float* d2,
+                     const float* z2, const float* v2, const int32_t* out_start, int32_t* c_idx, float* c_3d, float* c_dirs, float* c_z,
+                     float* c_val, int32_t* c_se, void* stream);
+
 /* ---- appearance head, backward (training) -------------------------------------------------------------------------------------
  * Replaces torch autograd through RGB.forward / MLP.forward (models/rgb.py:104-149, models/mlp.py:38-52) in the training step of
  * volsurfs_py/methods/volsurfs.py (loss.backward() in trainer.py): gradients of the Linear weights/biases and of the positional

@@ -27,5 +27,40 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+# ---- oracle/_ref: the reference's own packed volume-rendering kernels behind a C harness -------------------------------------
+REFERENCE = Path("/root/reference")
+REF_SRC = HERE / "ref_harness.cu"
+REF_DIR = HERE / "_ref"
+REF_LIB = REF_DIR / "libvolsurfs_ref.so"
+
+
+def ref_available() -> bool:
+    return REF_LIB.exists()
+
+
+def build_ref(force: bool = False):
+    """nvcc-compile oracle/ref_harness.cu, which #includes kernels/volsurfs/VolumeRenderingGPU.cuh + pcg32.h from the sources where
+    they lie under /root/reference (nothing is copied), for sm_100a into oracle/_ref/ (git-ignored, travels to the GPU box).
+    Needs only the torch HEADERS (PackedTensorAccessor32); the result links against cudart alone.  Returns None when the
+    reference tree is not mounted (GPU box): the prebuilt .so is used as is.  Takes ~2.5 min (torch/torch.h)."""
+    if not (REFERENCE / "kernels/volsurfs/VolumeRenderingGPU.cuh").exists():
+        return REF_LIB if REF_LIB.exists() else None
+    deps = [REF_SRC, REFERENCE / "kernels/volsurfs/VolumeRenderingGPU.cuh", REFERENCE / "kernels/volsurfs/pcg32.h"]
+    if REF_LIB.exists() and not force and all(REF_LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return REF_LIB
+    from torch.utils.cpp_extension import include_paths
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    REF_DIR.mkdir(exist_ok=True)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+           "-shared", "-w", f"-I{REFERENCE / 'kernels'}", f"-I{REFERENCE / 'include'}", *[f"-I{p}" for p in include_paths()],
+           "-D_GLIBCXX_USE_CXX11_ABI=1", str(REF_SRC), "-o", str(REF_LIB), "-lcudart"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on the reference harness:\n{res.stdout[-4000:]}")
+    return REF_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_ref())

@@ -50,6 +50,14 @@ __global__ void __launch_bounds__(kScanBlock) counts_from_segments_kernel(const 
     counts[r] = load_segment(se, r, start);
 }
 
+__global__ void __launch_bounds__(kScanBlock) counts_from_two_segments_kernel(const int32_t* __restrict__ se1, const int32_t* __restrict__ se2,
+                                                                              int32_t* __restrict__ counts, int64_t n_rays) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    int s1, s2;
+    counts[r] = load_segment(se1, r, s1) + load_segment(se2, r, s2);
+}
+
 // hit counts of the K-layer trace: depth is layer-major [K, n_rays]; a layer is hit iff depth <= t_far
 // (raytracelib/raytracer.py:100: is_hit = depth <= t_far)
 __global__ void __launch_bounds__(kScanBlock) counts_from_hits_kernel(const float* __restrict__ depth, int32_t* __restrict__ counts,
@@ -298,6 +306,24 @@ int vs_compact_offsets(const int32_t* se_in, int64_t n_rays, int64_t* total_dev,
     counts_from_segments_kernel<<<(unsigned)div_up(n_rays, kScanBlock), kScanBlock, 0, st>>>(se_in, counts, n_rays);
     launched(1);
     return launch_scan(counts, n_rays, offsets, reinterpret_cast<long long*>(total_dev), bs, st);
+}
+
+// Start offsets of combine_ray_samples_packets (src/VolumeRendering.cu:595-603: cumsum of count1+count2, shifted): out_start[r] =
+// exclusive prefix sum of the two packets' per-ray counts, *total_dev = their grand total.  scratch: vs_pack_scratch_bytes(n_rays).
+int vs_combine_offsets(const int32_t* se1, const int32_t* se2, int64_t n_rays, int32_t* out_start, int64_t* total_dev, void* scratch,
+                       void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && total_dev && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rays == 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(int64_t), st);
+    VS_CHECK_ARG(se1 && se2 && out_start);
+    long long* bs;
+    int32_t *counts, *offsets;
+    carve_scratch(scratch, n_rays, &bs, &counts, &offsets);
+    counts_from_two_segments_kernel<<<(unsigned)div_up(n_rays, kScanBlock), kScanBlock, 0, st>>>(se1, se2, counts, n_rays);
+    launched(1);
+    int e = launch_scan(counts, n_rays, offsets, reinterpret_cast<long long*>(total_dev), bs, st);
+    if (e != VS_OK) return e;
+    return (int)cudaMemcpyAsync(out_start, offsets, sizeof(int32_t) * n_rays, cudaMemcpyDeviceToDevice, st);
 }
 
 int vs_compact_gather(const int32_t* se_in, const void* scratch, const int32_t* idx_in, const float* p3d_in, const float* dirs_in,

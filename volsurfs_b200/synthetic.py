@@ -77,13 +77,13 @@ def all_hit_packed(n_rays: int, K: int, seed_offset: int = 2):
 
 
 def nerf_packets(n_rays: int, seed_offset: int = 3, max_per_ray: int = 1024, p_empty: float = 0.35, mean: float = 96.0,
-                 sigma: float = 0.9):
+                 sigma: float = 0.9, min_per_ray: int = 1):
     """Config C3: per-ray sample counts: p_empty rays with 0 samples, the rest min(max, ceil(LogNormal(ln mean, sigma)));
     sigma_density ~ Exp(20) with 70 % zeros, dt ~ 2/1024; alpha = 1 - exp(-density*dt); x = 1 - alpha + 1e-6."""
     g = gen(seed_offset)
     empty = torch.rand(n_rays, generator=g) < p_empty
     ln = torch.exp(torch.randn(n_rays, generator=g) * sigma + math.log(mean))
-    cnt = torch.clamp(torch.ceil(ln), max=max_per_ray).to(torch.int64)
+    cnt = torch.clamp(torch.ceil(ln), min=min_per_ray, max=max_per_ray).to(torch.int64)
     cnt[empty] = 0
     S = int(cnt.sum())
     start = torch.cumsum(cnt, 0) - cnt

@@ -381,6 +381,114 @@ class VolumeRendering:
         check(_lib.lib().vs_compute_cdf(ptr(se), ptr(w), ptr(cdf), n_rays, w.shape[0], _stream()), "vs_compute_cdf")
         return cdf
 
+    # ---- importance sampling chain ----------------------------------------------------------------------
+    #: host copy of the reference's static ``pcg32 m_rng`` (kernels/volsurfs/pcg32.h:32-34 defaults), passed by value to the
+    #: jittered launch and advanced by 2^32 afterwards (src/VolumeRendering.cu:520-523)
+    _rng_state = 0x853C49E6748FEA9B
+    _rng_inc = 0xDA3E39CB94B95BDB
+
+    @staticmethod
+    def _rng_advance(delta: int = 1 << 32) -> None:
+        m64 = (1 << 64) - 1
+        cur_mult, cur_plus, acc_mult, acc_plus = 0x5851F42D4C957F2D, VolumeRendering._rng_inc, 1, 0
+        delta &= m64
+        while delta > 0:
+            if delta & 1:
+                acc_mult = (acc_mult * cur_mult) & m64
+                acc_plus = (acc_plus * cur_mult + cur_plus) & m64
+            cur_plus = ((cur_mult + 1) * cur_plus) & m64
+            cur_mult = (cur_mult * cur_mult) & m64
+            delta >>= 1
+        VolumeRendering._rng_state = (acc_mult * VolumeRendering._rng_state + acc_plus) & m64
+
+    @staticmethod
+    def importance_sample(ray_samples_packed, samples_cdf, nr_importance_samples, jitter_samples):
+        """src/VolumeRendering.cu:466-548: ``nr_importance_samples`` new samples per ray placed by inverting the per-ray cdf,
+        returned as a compacted packet (samples_idx numbered from the input packet's sample count, like the reference)."""
+        rsp = ray_samples_packed
+        se, n_rays = VolumeRendering._prep(rsp, "importance_sample")
+        n_imp = int(nr_importance_samples)
+        S = rsp.get_max_nr_samples()
+        if n_rays == 0 or S == 0:
+            raise RuntimeError("RaySamplesPacked should not be empty")
+        cdf = _f32c(samples_cdf, "samples_cdf", 1)
+        if cdf.shape[0] != S:
+            raise RuntimeError(f"CDF should have size of nr_samples_total x 1. but it has {tuple(cdf.shape)}")
+        if n_imp <= 0:
+            raise RuntimeError("nr_importance_samples must be positive")
+        imp = RaySamplesPacked(n_rays, n_rays * n_imp, S, rsp.get_values_dim())
+        imp.is_compacted = False
+        check(
+            _lib.lib().vs_importance_sample(
+                ptr(_f32c(rsp.ray_o, "ray_o", 3)), ptr(_f32c(rsp.ray_d, "ray_d", 3)), ptr(se), ptr(_f32c(rsp.samples_z, "samples_z", 1)),
+                ptr(cdf), n_rays, S, n_imp, VolumeRendering._rng_state, VolumeRendering._rng_inc, int(bool(jitter_samples)),
+                ptr(imp.samples_3d), ptr(imp.samples_dirs), ptr(imp.samples_z), ptr(imp.ray_start_end_idx), _stream(),
+            ),
+            "vs_importance_sample",
+        )
+        if jitter_samples:
+            VolumeRendering._rng_advance()
+        out = imp.compact_to_valid_samples()
+        if out.get_max_nr_samples() <= 0:
+            raise RuntimeError("nr_samples_imp should be > 0")
+        return out
+
+    @staticmethod
+    def combine_ray_samples_packets(ray_samples_packed_1, ray_samples_packed_2, min_dist_between_samples):
+        """src/VolumeRendering.cu:550-669: per-ray z-ordered merge of two compacted packets; a sample closer than
+        ``min_dist_between_samples`` to the previously kept one is dropped.  Returns a compacted packet (has_dt False)."""
+        a, b = ray_samples_packed_1, ray_samples_packed_2
+        se1, n_rays = VolumeRendering._prep(a, "combine_ray_samples_packets")
+        se2, n_rays2 = VolumeRendering._prep(b, "combine_ray_samples_packets")
+        if a.has_samples_values != b.has_samples_values:
+            raise RuntimeError("They are supposed to both has or not have samples values")
+        if a.get_values_dim() != b.get_values_dim():
+            raise RuntimeError("They are supposed to have the same values dims")
+        if n_rays != n_rays2:
+            raise RuntimeError("They are supposed to have the same number of rays")
+        if a.is_empty() and b.is_empty():
+            raise RuntimeError("Both ray_samples_packed are empty")
+        if a.is_empty():
+            return b
+        if b.is_empty():
+            return a
+        L = _lib.lib()
+        st = _stream()
+        dev = se1.device
+        vd = a.get_values_dim()
+        n1, n2 = a.get_max_nr_samples(), b.get_max_nr_samples()
+        comb = RaySamplesPacked(n_rays, n1 + n2, 0, vd)
+        comb.ray_o, comb.ray_d = a.ray_o.clone(), a.ray_d.clone()
+        comb.ray_enter, comb.ray_exit, comb.ray_max_dt = a.ray_enter.clone(), a.ray_exit.clone(), a.ray_max_dt.clone()
+        comb.has_samples_values = a.has_samples_values
+        comb.has_dt = False
+        comb.is_compacted = False
+        scratch = torch.empty(max(int(L.vs_pack_scratch_bytes(n_rays)), 8), dtype=torch.uint8, device=dev)
+        out_start = torch.empty(n_rays, dtype=torch.int32, device=dev)
+        total_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(L.vs_combine_offsets(ptr(se1), ptr(se2), n_rays, ptr(out_start), ptr(total_dev), ptr(scratch), st), "vs_combine_offsets")
+
+        def f(t, name, cols):
+            return _f32c(t, name, cols)
+
+        i1, i2 = a.samples_idx.contiguous(), b.samples_idx.contiguous()
+        check(
+            L.vs_combine_merge(
+                n_rays, float(min_dist_between_samples), vd,
+                ptr(se1), ptr(i1), ptr(f(a.samples_3d, "samples_3d", 3)), ptr(f(a.samples_dirs, "samples_dirs", 3)),
+                ptr(f(a.samples_z, "samples_z", 1)), ptr(f(a.samples_values, "samples_values", vd)),
+                ptr(se2), ptr(i2), ptr(f(b.samples_3d, "samples_3d", 3)), ptr(f(b.samples_dirs, "samples_dirs", 3)),
+                ptr(f(b.samples_z, "samples_z", 1)), ptr(f(b.samples_values, "samples_values", vd)),
+                ptr(out_start), ptr(comb.samples_idx), ptr(comb.samples_3d), ptr(comb.samples_dirs), ptr(comb.samples_z),
+                ptr(comb.samples_values), ptr(comb.ray_start_end_idx), st,
+            ),
+            "vs_combine_merge",
+        )
+        out = comb.compact_to_valid_samples()
+        if out.get_max_nr_samples() <= 0:
+            raise RuntimeError("total_nr_samples should be > 0")
+        return out
+
     # ---- backward ops --------------------------------------------------------------------------------------------
     @staticmethod
     def cumprod_one_minus_alpha_to_transmittance_backward(
