@@ -239,6 +239,8 @@ def run_ours(args, rank, world, local_rank):
     grad_rgb = torch.zeros(renderer.rgb_head.num_params(), device=dev)
     grad_alpha = torch.zeros(renderer.alpha_head.num_params(), device=dev)
     dfeat_rgb, dfeat_alpha = torch.empty_like(feats), torch.empty_like(feats)
+    stash_rgb = renderer.rgb_head.new_stash(N * K_LAYERS, dev)        # activations kept by the training-mode forward for the backward
+    stash_alpha = renderer.alpha_head.new_stash(N * K_LAYERS, dev)
     reducer = GradAllReducer()
     ev = None
 
@@ -261,9 +263,9 @@ def run_ours(args, rank, world, local_rank):
                                                 rsp.total_dev.data_ptr(), rsp.samples_normals.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream), "normals")
         mark(2)
-        rgb = renderer.rgb_head(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
+        rgb, _ = renderer.rgb_head.forward_train(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash_rgb)
         mark(3)
-        alpha = renderer.alpha_head(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
+        alpha, _ = renderer.alpha_head.forward_train(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash_alpha)
         mark(4)
         out = renderer.composite(rsp, alpha, rgb)
         mark(5)
@@ -273,10 +275,12 @@ def run_ours(args, rank, world, local_rank):
         mark(6)
         d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
         mark(7)
-        renderer.rgb_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_rgb, grad_rgb, dfeat_rgb, False, rsp.total_dev)
+        renderer.rgb_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_rgb, grad_rgb, dfeat_rgb, False, rsp.total_dev,
+                                        stash=stash_rgb, fwd_out=rgb)
         reducer.launch([grad_rgb])       # overlaps the alpha head's backward
         mark(8)
-        renderer.alpha_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_alpha, grad_alpha, dfeat_alpha, False, rsp.total_dev)
+        renderer.alpha_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_alpha, grad_alpha, dfeat_alpha, False, rsp.total_dev,
+                                          stash=stash_alpha, fwd_out=alpha)
         reducer.launch([grad_alpha])
         mark(9)
         reducer.wait()
@@ -380,7 +384,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the headline compositing kernels at the size SURVEY 8d prescribes (2^24 rays x 5, traffic >> L2)
     comp = None
     if not args.skip_composite_roofline:
-        del feats, dfeat_rgb, dfeat_alpha
+        del feats, dfeat_rgb, dfeat_alpha, stash_rgb, stash_alpha
         torch.cuda.empty_cache()
         n_big = 1 << 24
         d = all_hit_packed(n_big, K_LAYERS)

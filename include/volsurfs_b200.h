@@ -174,8 +174,12 @@ int vs_mlp_pack(int n_layers, const int* dims, const float* const* weights, cons
 /* out[s,:out] = sigmoid(MLP([pos[s] | SH_deg(dirs[s]) | normals[s] if normal_dep])) * (alpha_decay ? 2*sigmoid(10*clamp(-d.n,0,1))-1 : 1)
  * activation: 0 ReLU, 1 GELU(erf).  n_valid_dev: optional device int64 capping n_samples.  variant: 0 (debug knob). */
 int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
-                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, int64_t n_samples,
+                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, void* stash, int64_t n_samples,
                    const int64_t* n_valid_dev, int variant, void* stream);
+/* Training mode: pass `stash` (vs_mlp_stash_bytes(n_samples) bytes, 16-byte aligned) to vs_mlp_forward and it also keeps, per
+ * 128-sample tile, every layer's fp16 input operand and every hidden layer's activation derivative for vs_mlp_backward_stashed
+ * (what torch autograd saves for backward in the reference).  NULL: inference. */
+int64_t vs_mlp_stash_bytes(int n_layers, const int* dims, int64_t n_samples);
 
 /* ---- importance sampling chain ------------------------------------------------------------------------------
  * VolumeRendering::importance_sample (src/VolumeRendering.cu:466-548; kernel VolumeRenderingGPU.cuh:507-678): n_imp samples per ray
@@ -212,6 +216,10 @@ int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim
                     int alpha_decay, const float* pos, const float* dirs, const float* normals, const float* d_out, float* d_pos,
                     float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, int variant,
                     void* stream);
+/* Backward from the stash of a training-mode vs_mlp_forward (no recomputation; HBM-bound).  fwd_out: the output that forward wrote. */
+int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree, int normal_dep,
+                            int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
+                            float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream);
 
 #ifdef __cplusplus
 }

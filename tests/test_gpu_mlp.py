@@ -30,12 +30,26 @@ def test_golden_reference_classes(name):
     g = np.load(GOLDEN / f"{name}.npz")
     head = _head_from_golden(g)
     args = [torch.from_numpy(g[k]).cuda() for k in ("pos", "dirs", "normals")]
-    errs = {}
-    for variant in (0, 1):
-        out = head(*args, _variant=variant).detach().cpu().numpy()
-        errs[variant] = float(np.abs(out - g["out"]).max())
-    print("max abs err per descriptor variant:", errs)
-    assert errs[0] < ATOL, errs
+    with torch.no_grad():
+        out = head(*args).cpu().numpy()
+    err = float(np.abs(out - g["out"]).max())
+    print("max abs err:", err)
+    assert err < ATOL, err
+    # gradients recorded from the reference's own MLP / SHEncoder classes through torch autograd (tests/golden/make_golden.py):
+    # both backward kernels (activation stash; recompute) against them
+    from conftest import grad_err
+
+    n_layers = len(head.layers)
+    for variant in (0, 4):
+        head.zero_grad()
+        pos = args[0].clone().requires_grad_(True)
+        o = head(pos, args[1], args[2], _variant=variant)
+        (o * torch.from_numpy(g["g_out"]).cuda()).sum().backward()
+        errs = {f"dW{i}": grad_err(head.layers[i].weight.grad.cpu().numpy(), g[f"dW{i}"]) for i in range(n_layers)}
+        errs.update({f"db{i}": grad_err(head.layers[i].bias.grad.cpu().numpy(), g[f"db{i}"]) for i in range(n_layers)})
+        errs["dpos"] = grad_err(pos.grad.cpu().numpy(), g["d_pos"])
+        print(f"variant {variant}:", {k: f"{v:.1e}" for k, v in errs.items()})
+        assert max(errs.values()) < 3e-2, errs   # 300 samples: little averaging of the fp16 operand rounding
     if name == "appearance_alpha_64":
         dec = _head_from_golden(g, alpha_decay=True)(*args).detach().cpu().numpy()
         assert np.abs(dec - g["alpha_decayed"]).max() < ATOL
@@ -170,10 +184,12 @@ def _bwd_case(hidden, out_dim, normal_dep, act, n, g_scale, alpha_decay, variant
     ((32,), 1, False, "relu", 5, 1.0, False),
 ])
 def test_backward_vs_torch_autograd(hidden, out_dim, normal_dep, act, n, g_scale, decay):
-    errs = {v: _bwd_case(hidden, out_dim, normal_dep, act, n, g_scale, decay, variant=v) for v in (0,)}
+    # variant 0: backward from the activation stash of the training-mode forward; variant 4: recompute-in-backward kernel
+    errs = {v: _bwd_case(hidden, out_dim, normal_dep, act, n, g_scale, decay, variant=v) for v in (0, 4)}
     for v, e in errs.items():
         print(f"variant {v}: " + ", ".join(f"{k}={x:.1e}" for k, x in e.items()))
     _check_grad_errs(errs[0])
+    _check_grad_errs(errs[4])
 
 
 def test_backward_capacity_mode_and_accumulate():

@@ -51,12 +51,14 @@ SIGNATURES = {
     "vs_shells_sample_normals": (c_int, [_P, _P, _P, _I64, _P, _P, _P]),
     "vs_mlp_blob_bytes": (_I64, [c_int, _P]),
     "vs_mlp_pack": (c_int, [c_int, _P, _P, _P, _P, _P]),
-    "vs_mlp_forward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _I64, _P, c_int, _P]),
+    "vs_mlp_forward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _I64, _P, c_int, _P]),
+    "vs_mlp_stash_bytes": (_I64, [c_int, _P, _I64]),
     "vs_importance_sample": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, c_int, ctypes.c_uint64, ctypes.c_uint64, c_int, _P, _P, _P, _P, _P]),
     "vs_combine_offsets": (c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "vs_combine_merge": (c_int, [_I64, c_float, c_int] + [_P] * 19 + [_P]),
     "vs_mlp_num_params": (_I64, [c_int, _P]),
     "vs_mlp_backward_workspace_bytes": (_I64, [c_int, _P, c_int, c_int, c_int, _I64]),
+    "vs_mlp_backward_stashed": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, _P]),
     "vs_mlp_backward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, c_int, _P]),
 }
 

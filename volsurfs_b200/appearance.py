@@ -74,7 +74,27 @@ class AppearanceHead(torch.nn.Module):
         with torch.no_grad():
             return self._forward_impl(pos_features, dirs, normals, n_valid_dev, out, _variant)
 
-    def _forward_impl(self, pos_features, dirs, normals=None, n_valid_dev=None, out=None, _variant: int = 0):
+    def stash_bytes(self, n_samples: int) -> int:
+        n = int(_lib.lib().vs_mlp_stash_bytes(len(self.layers), self._dims_c(), int(n_samples)))
+        if n < 0:
+            check(n, "vs_mlp_stash_bytes")
+        return n
+
+    def new_stash(self, n_samples: int, device=None):
+        """activation stash for a training-mode forward of ``n_samples`` samples (per 128-sample tile: every layer's fp16 operand
+        and every hidden layer's activation derivative)"""
+        dev = device if device is not None else self.layers[0].weight.device
+        return torch.empty(max(self.stash_bytes(n_samples), 16), dtype=torch.uint8, device=dev)
+
+    @torch.no_grad()
+    def forward_train(self, pos_features, dirs, normals=None, n_valid_dev=None, out=None, stash=None):
+        """forward that also fills ``stash`` (allocated when None) for ``backward_into(..., stash=, fwd_out=)``; returns (out, stash)"""
+        if stash is None:
+            stash = self.new_stash(int(pos_features.shape[0]), pos_features.device)
+        out = self._forward_impl(pos_features, dirs, normals, n_valid_dev, out, 0, stash)
+        return out, stash
+
+    def _forward_impl(self, pos_features, dirs, normals=None, n_valid_dev=None, out=None, _variant: int = 0, stash=None):
         S = int(pos_features.shape[0])
         pos_features = pos_features.contiguous()
         assert pos_features.dtype == torch.float32 and pos_features.shape[1] == self.pos_dim
@@ -85,8 +105,8 @@ class AppearanceHead(torch.nn.Module):
             _lib.lib().vs_mlp_forward(
                 len(self.layers), self._dims_c(), ptr(blob), self.pos_dim, self.sh_degree, int(self.normal_dep),
                 1 if self.activation == "gelu" else 0, int(self.alpha_decay), ptr(pos_features),
-                ptr(None if dirs is None else dirs.contiguous()), ptr(None if normals is None else normals.contiguous()), ptr(out), S,
-                ptr(n_valid_dev), int(_variant), _stream(),
+                ptr(None if dirs is None else dirs.contiguous()), ptr(None if normals is None else normals.contiguous()), ptr(out),
+                ptr(stash), S, ptr(n_valid_dev), int(_variant), _stream(),
             ),
             "vs_mlp_forward",
         )
@@ -109,9 +129,10 @@ class AppearanceHead(torch.nn.Module):
 
     @torch.no_grad()
     def backward_into(self, pos_features, dirs, normals, d_out, d_params, d_pos=None, accumulate=False, n_valid_dev=None,
-                      _variant: int = 0):
+                      _variant: int = 0, stash=None, fwd_out=None):
         """One launch sequence of the fused backward: fills ``d_params`` (flat fp32, ``num_params()`` entries) and, when given,
-        ``d_pos`` [S, pos_dim].  Recomputes the forward pass from the inputs."""
+        ``d_pos`` [S, pos_dim].  With ``stash`` + ``fwd_out`` (from ``forward_train``) the kernel streams the saved activations
+        (HBM-bound); without them it recomputes the forward pass from the inputs."""
         L = _lib.lib()
         S = int(pos_features.shape[0])
         pos_features = pos_features.contiguous()
@@ -125,6 +146,18 @@ class AppearanceHead(torch.nn.Module):
         ws = getattr(self, "_bwd_ws", None)
         if ws is None or ws.numel() < ws_bytes or ws.device != pos_features.device:
             ws = self._bwd_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pos_features.device)
+        if stash is not None:
+            assert fwd_out is not None and fwd_out.is_contiguous() and tuple(fwd_out.shape) == (S, self.out_dim)
+            check(
+                L.vs_mlp_backward_stashed(
+                    len(self.layers), self._dims_c(), ptr(self.packed()), ptr(stash), self.pos_dim, sh, int(self.normal_dep),
+                    int(self.alpha_decay), ptr(None if dirs is None else dirs.contiguous()),
+                    ptr(None if normals is None else normals.contiguous()), ptr(fwd_out), ptr(d_out), ptr(d_pos), ptr(d_params),
+                    int(bool(accumulate)), ptr(ws), S, ptr(n_valid_dev), _stream(),
+                ),
+                "vs_mlp_backward_stashed",
+            )
+            return d_params, d_pos
         check(
             L.vs_mlp_backward(
                 len(self.layers), self._dims_c(), ptr(self.packed()), self.pos_dim, sh, int(self.normal_dep),
@@ -142,21 +175,25 @@ class _HeadFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, head, pos_features, dirs, normals, n_valid_dev, variant, *params):
-        out = head._forward_impl(pos_features, dirs, normals, n_valid_dev, None, variant)
+        # variant bit 2 (debug / tests): recompute-in-backward path instead of the activation stash
+        stash = None if (variant & 4) else head.new_stash(int(pos_features.shape[0]), pos_features.device)
+        out = head._forward_impl(pos_features, dirs, normals, n_valid_dev, None, variant & 3, stash)
+        ctx.stash = stash
         ctx.head = head
         ctx.variant = variant
         ctx.n_valid_dev = n_valid_dev
         ctx.need_pos = pos_features.requires_grad
-        ctx.save_for_backward(pos_features, dirs, normals)
+        ctx.save_for_backward(pos_features, dirs, normals, out)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         head = ctx.head
-        pos_features, dirs, normals = ctx.saved_tensors
+        pos_features, dirs, normals, fwd_out = ctx.saved_tensors
         flat = torch.empty(head.num_params(), dtype=torch.float32, device=g_out.device)
         d_pos = torch.zeros_like(pos_features) if ctx.need_pos and ctx.n_valid_dev is not None else (
             torch.empty_like(pos_features) if ctx.need_pos else None)
-        head.backward_into(pos_features, dirs, normals, g_out, flat, d_pos, False, ctx.n_valid_dev, ctx.variant)
-        ctx.head = None
+        head.backward_into(pos_features, dirs, normals, g_out, flat, d_pos, False, ctx.n_valid_dev, ctx.variant & 3, ctx.stash,
+                           fwd_out if ctx.stash is not None else None)
+        ctx.head = ctx.stash = None
         return (None, d_pos, None, None, None, None, *head.split_flat(flat))

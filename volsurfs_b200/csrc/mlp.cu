@@ -41,13 +41,18 @@ __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __rest
 }
 
 
-template <int ACT>  // 0 ReLU, 1 GELU: compile-time so the epilogue loop carries no branch
-__global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cfg, const uint8_t* __restrict__ blob,
+// One CTA keeps TWO 128-sample tiles in flight (slots 0 and 1, each with its own operand buffers and TMEM accumulator): while the
+// 16 warps run the epilogue of one slot's layer, the tensor core works on the other slot's next layer, so neither the MMA latency
+// nor the barrier that hands the operands over is exposed.  STASH: training mode — every layer's input operand and every hidden
+// layer's activation derivative also go to global memory (16-byte stores, a warp covers 512 contiguous bytes) for the backward.
+template <int ACT, bool STASH>  // ACT: 0 ReLU, 1 GELU (compile-time: the epilogue loop carries no branch)
+__global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cfg, const MlpStash stash_cfg, const uint8_t* __restrict__ blob,
                                                               const float* __restrict__ pos, const float* __restrict__ dirs,
                                                               const float* __restrict__ normals, float* __restrict__ out,
-                                                              int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
+                                                              uint8_t* __restrict__ stash, int64_t n_samples,
+                                                              const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_mma;
+    __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_mma[2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -55,15 +60,16 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
     const int row = tid & (kTileM - 1);  // sample of the tile this thread works on (== its TMEM lane)
     const int cg = tid >> 7;             // column group 0..3: which quarter of the columns / K-chunks this thread handles
     const int F = cfg.pos_dim;
+    const int L = cfg.n_layers;
     const int k0 = cfg.k_pad[0];
 
-    // carve shared memory
-    uint8_t* s_blob = smem;                                                         // blob_bytes (multiple of 16)
-    __half* s_a0 = reinterpret_cast<__half*>(s_blob + cfg.blob_bytes);              // 128 x k0 fp16 (layer-0 operand)
-    __half* s_a1 = s_a0 + kTileM * k0;                                              // 128 x a1_width fp16 (hidden activations)
-    const int stage_floats = (kTileM * F + 3) & ~3;
-    float* s_stage0 = reinterpret_cast<float*>(s_a1 + kTileM * cfg.a1_width);       // 128 x F fp32 (TMA landing zone) x 1 or 2
-    float* s_extra = s_stage0 + (cfg.prefetch ? 2 : 1) * stage_floats;              // 128 x kExtraStride
+    // carve shared memory: blob | per slot: A0 (layer-0 operand) | H (hidden activations; also the TMA landing zone of the fp32
+    // features, which are consumed before the first hidden activation is written) | extras (SH, normals)
+    const int a0_bytes = kTileM * k0 * 2;
+    const int h_bytes = cfg.h_bytes;
+    const int slot_bytes = a0_bytes + h_bytes + kTileM * kExtraStride * 4;
+    uint8_t* s_blob = smem;
+    uint8_t* s_slots = s_blob + cfg.blob_bytes;
 
     int64_t n = n_samples;
     if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
@@ -73,55 +79,45 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
         mbar_init(&bar_w, 1);
         mbar_init(&bar_in[0], 1);
         mbar_init(&bar_in[1], 1);
-        mbar_init(&bar_mma, 1);
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)cfg.tmem_cols);
+    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)(cfg.n_slots * cfg.tmem_cols));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // a warp may only touch lanes 32*(warp%4)..+31
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch lanes 32*(warp%4)..+31
 
     if ((int64_t)blockIdx.x < n_tiles && tid == 0) {  // weights + biases: resident for the whole kernel
         mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
         bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
     }
     bool weights_ready = false;
-    uint32_t par_in_bits = 0, par_mma = 0;  // bit b of par_in_bits: phase parity of bar_in[b]
-    int buf = 0;
-    bool have_prefetched = false;  // the current tile's features were requested during the previous iteration
+    uint32_t par_in[2] = {0, 0}, par_mma[2] = {0, 0};
     const uint32_t lbo_sel = (cfg.variant & 1);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto slot_a0 = [&](int s) { return reinterpret_cast<__half*>(s_slots + (size_t)s * slot_bytes); };
+    auto slot_h = [&](int s) { return reinterpret_cast<__half*>(s_slots + (size_t)s * slot_bytes + a0_bytes); };
+    auto slot_extra = [&](int s) { return reinterpret_cast<float*>(s_slots + (size_t)s * slot_bytes + a0_bytes + h_bytes); };
+
+    // features of a full tile -> the slot's landing zone (one TMA bulk copy); partial tiles are read straight from global memory
+    auto request_features = [&](int s, int64_t tile) {
+        if (tid == 0 && tile < n_tiles && (tile + 1) * kTileM <= n && F > 0) {
+            mbar_arrive_expect_tx(&bar_in[s], (uint32_t)(kTileM * F * 4));
+            bulk_g2s(slot_h(s), pos + tile * kTileM * F, (uint32_t)(kTileM * F * 4), &bar_in[s]);
+        }
+    };
+
+    // per-row state kept in registers between build and the output epilogue (alpha decay)
+    float decay[2] = {1.f, 1.f};
+
+    auto build_a0 = [&](int s, int64_t tile) {
         const int64_t row0 = tile * kTileM;
         const int rows = (int)min((int64_t)kTileM, n - row0);
         const bool full = rows == kTileM;
         const int64_t r = row0 + row;
         const bool live = row < rows;
-
-        // ---- 1. features -> shared memory
-        float* s_stage = s_stage0 + buf * stage_floats;
-        if (full) {
-            if (tid == 0 && !have_prefetched) {
-                mbar_arrive_expect_tx(&bar_in[buf], (uint32_t)(kTileM * F * 4));
-                bulk_g2s(s_stage, pos + row0 * F, (uint32_t)(kTileM * F * 4), &bar_in[buf]);
-            }
-        } else {
-            for (int e = tid; e < rows * F; e += kMlpThreads) s_stage[e] = __ldg(pos + row0 * F + e);
-        }
-        // prefetch the next tile of this CTA into the other buffer (its previous contents were consumed an iteration ago)
-        bool next_prefetched = false;
-        if (cfg.prefetch) {
-            const int64_t nt = tile + gridDim.x;
-            if (nt < n_tiles && (nt + 1) * kTileM <= n) {
-                next_prefetched = true;
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(&bar_in[buf ^ 1], (uint32_t)(kTileM * F * 4));
-                    bulk_g2s(s_stage0 + (buf ^ 1) * stage_floats, pos + nt * kTileM * F, (uint32_t)(kTileM * F * 4), &bar_in[buf ^ 1]);
-                }
-            }
-        }
-        // ---- 2. per-row extras: SH(dir), normal
         float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
         if (live) {
             if (dirs != nullptr) {
@@ -135,145 +131,196 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
                 nz = __ldg(normals + 3 * r + 2);
             }
         }
-        {
+        decay[s] = 1.f;
+        if (cfg.alpha_decay) {
+            const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
+            decay[s] = 2.f * sigmoid_f(10.f * dot) - 1.f;
+        }
+        float* ex = slot_extra(s) + row * kExtraStride;
+        if (cg == 0) {
             float sh[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) sh[i] = 0.f;
             sh_eval(dx, dy, dz, cfg.n_sh, sh);
-            if (cg == 0) {
-                float* ex = s_extra + row * kExtraStride;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) ex[i] = sh[i];
-                // with n_sh < 16 the normal follows the SH block directly
-                if (cfg.normal_dep) {
-                    ex[cfg.n_sh] = nx;
-                    ex[cfg.n_sh + 1] = ny;
-                    ex[cfg.n_sh + 2] = nz;
-                }
+            for (int i = 0; i < 16; ++i) ex[i] = sh[i];
+            if (cfg.normal_dep) {  // with n_sh < 16 the normal follows the SH block directly
+                ex[cfg.n_sh] = nx;
+                ex[cfg.n_sh + 1] = ny;
+                ex[cfg.n_sh + 2] = nz;
             }
         }
         __syncthreads();
-        if (full) {
-            mbar_wait(&bar_in[buf], (par_in_bits >> buf) & 1u);
-            par_in_bits ^= (1u << buf);
+        if (full && F > 0) {
+            mbar_wait(&bar_in[s], par_in[s]);
+            par_in[s] ^= 1;
         }
-        // ---- 3. row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes; the four column
-        //         groups split the K-chunks of a row
-        {
-            const float* srow = s_stage + row * F;
-            const float* ex = s_extra + row * kExtraStride;
-            const int in_dim = cfg.in_dim;
-            for (int kc = cg; kc < k0 / 8; kc += 4) {
-                __half2 h[4];
+        // row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes; the four column groups split
+        // the K-chunks of a row
+        const float* srow = full ? reinterpret_cast<const float*>(slot_h(s)) + row * F : pos + r * F;
+        __half* a0 = slot_a0(s);
+        uint8_t* st_a0 = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[0] : nullptr;
+        const int in_dim = cfg.in_dim;
+        for (int kc = cg; kc < k0 / 8; kc += 4) {
+            __half2 h[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float v2[2];
+            for (int j = 0; j < 4; ++j) {
+                float v2[2];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int c = kc * 8 + 2 * j + q;
-                        float v = 0.f;
-                        if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
-                        v2[q] = v;
-                    }
-                    h[j] = __floats2half2_rn(v2[0], v2[1]);
+                for (int q = 0; q < 2; ++q) {
+                    const int c = kc * 8 + 2 * j + q;
+                    float v = 0.f;
+                    if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
+                    v2[q] = v;
                 }
-                *reinterpret_cast<uint4*>(s_a0 + ((size_t)kc * kTileM + row) * 8) = *reinterpret_cast<const uint4*>(h);
+                h[j] = __floats2half2_rn(v2[0], v2[1]);
+            }
+            const uint4 pk = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
+            if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+        }
+        if (STASH && stash_cfg.fold[0] && cg == 1)  // the "ones" chunk behind A_0 (bias gradient row of the backward's dW GEMM)
+            *reinterpret_cast<uint4*>(st_a0 + ((size_t)(k0 / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+    };
+
+    // hand the slot's operand over to the tensor core and start layer l: D[slot] = A_l W_l^T
+    auto issue_layer = [&](int s, int l) {
+        fence_proxy_async();  // this thread's operand writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const int K = cfg.k_pad[l], N = cfg.n_pad[l];
+            const uint32_t a_base = smem_u32(l == 0 ? slot_a0(s) : slot_h(s));
+            const uint32_t b_base = smem_u32(s_blob + cfg.w_off[l]);
+            const uint32_t a_lbo = kTileM * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
+            const uint32_t idesc = umma_idesc_f16(kTileM, N);
+            const uint32_t d = tmem_base + (uint32_t)(s * cfg.tmem_cols);
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint32_t a_addr = a_base + (uint32_t)ks * 2 * a_lbo;
+                const uint32_t b_addr = b_base + (uint32_t)ks * 2 * b_lbo;
+                const uint64_t ad = lbo_sel ? umma_desc(a_addr, sbo, a_lbo) : umma_desc(a_addr, a_lbo, sbo);
+                const uint64_t bd = lbo_sel ? umma_desc(b_addr, sbo, b_lbo) : umma_desc(b_addr, b_lbo, sbo);
+                tc_mma_f16(d, ad, bd, idesc, ks > 0 ? 1u : 0u);
+            }
+            tc_commit(&bar_mma[s]);  // arrives when the MMAs above have completed
+        }
+    };
+
+    // layer l of slot s has landed in TMEM: bias + activation -> next operand (hidden) or sigmoid -> out (last layer)
+    auto epilogue = [&](int s, int l, int64_t tile, int64_t next_tile) {
+        mbar_wait(&bar_mma[s], par_mma[s]);
+        par_mma[s] ^= 1;
+        tc_fence_after();
+        const int N = cfg.n_pad[l];
+        const uint32_t tmem_lane = tmem_base + lane_off + (uint32_t)(s * cfg.tmem_cols);
+        const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l]);
+        const int64_t r = tile * kTileM + row;
+        if (l + 1 < L) {
+            __half* hbuf = slot_h(s);
+            uint8_t* st_a = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[l + 1] : nullptr;
+            uint8_t* st_g = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.g_off[l] : nullptr;
+            if (STASH && stash_cfg.fold[l + 1] && cg == 1)
+                *reinterpret_cast<uint4*>(st_a + ((size_t)(N / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+            for (int c0 = cg * 16; c0 < N; c0 += 64) {
+                float v[16];
+                tmem_ld16(tmem_lane + (uint32_t)c0, v);
+                const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+                __half2 h[8], gh[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bb = b4[q];
+                    const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
+                    float a0, a1, a2, a3, g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+                    if (ACT == 1) {
+                        gelu_pair<STASH>(x0, x1, a0, a1, g0, g1);
+                        gelu_pair<STASH>(x2, x3, a2, a3, g2, g3);
+                    } else {
+                        a0 = fmaxf(x0, 0.f);
+                        a1 = fmaxf(x1, 0.f);
+                        a2 = fmaxf(x2, 0.f);
+                        a3 = fmaxf(x3, 0.f);
+                        if (STASH) {
+                            g0 = x0 > 0.f ? 1.f : 0.f;
+                            g1 = x1 > 0.f ? 1.f : 0.f;
+                            g2 = x2 > 0.f ? 1.f : 0.f;
+                            g3 = x3 > 0.f ? 1.f : 0.f;
+                        }
+                    }
+                    h[2 * q] = __floats2half2_rn(a0, a1);
+                    h[2 * q + 1] = __floats2half2_rn(a2, a3);
+                    if (STASH) {
+                        gh[2 * q] = __floats2half2_rn(g0, g1);
+                        gh[2 * q + 1] = __floats2half2_rn(g2, g3);
+                    }
+                }
+                const size_t off = ((size_t)(c0 / 8) * kTileM + row) * 16;  // next 8-column chunk: +128 rows * 16 bytes
+                const uint4 lo = *reinterpret_cast<const uint4*>(&h[0]), hi = *reinterpret_cast<const uint4*>(&h[4]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hbuf) + off) = lo;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hbuf) + off + kTileM * 16) = hi;
+                if (STASH) {
+                    *reinterpret_cast<uint4*>(st_a + off) = lo;
+                    *reinterpret_cast<uint4*>(st_a + off + kTileM * 16) = hi;
+                    *reinterpret_cast<uint4*>(st_g + off) = *reinterpret_cast<const uint4*>(&gh[0]);
+                    *reinterpret_cast<uint4*>(st_g + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&gh[4]);
+                }
+            }
+        } else {
+            // the MMAs that read H have completed: the slot's landing zone is free for the features of its next tile
+            request_features(s, next_tile);
+            if (cg == 0) {
+                float v[16];
+                tmem_ld16(tmem_lane, v);
+                if (r < n) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < cfg.out_dim) out[r * cfg.out_dim + j] = sigmoid_f(v[j] + bias[j]) * decay[s];
+                }
             }
         }
+    };
+
+    const int64_t stride = gridDim.x;
+    const bool two = cfg.n_slots == 2;
+    const int64_t step = two ? 2 * stride : stride;
+    int64_t tA = blockIdx.x, tB = two ? tA + stride : n_tiles;
+    request_features(0, tA);
+    request_features(1, tB);
+    while (tA < n_tiles) {
+        const bool hasB = tB < n_tiles;
+        build_a0(0, tA);
         if (!weights_ready) {
             mbar_wait(&bar_w, 0);
             weights_ready = true;
         }
-
-        // ---- 4. layers
-        for (int l = 0; l < cfg.n_layers; ++l) {
-            const int K = cfg.k_pad[l], N = cfg.n_pad[l];
-            fence_proxy_async();  // this thread's operand writes -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(l == 0 ? s_a0 : s_a1);
-                const uint32_t b_base = smem_u32(s_blob + cfg.w_off[l]);
-                const uint32_t a_lbo = kTileM * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
-                const uint32_t idesc = umma_idesc_f16(kTileM, N);
-                for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint32_t a_addr = a_base + (uint32_t)ks * 2 * a_lbo;
-                    const uint32_t b_addr = b_base + (uint32_t)ks * 2 * b_lbo;
-                    const uint64_t ad = lbo_sel ? umma_desc(a_addr, sbo, a_lbo) : umma_desc(a_addr, a_lbo, sbo);
-                    const uint64_t bd = lbo_sel ? umma_desc(b_addr, sbo, b_lbo) : umma_desc(b_addr, b_lbo, sbo);
-                    tc_mma_f16(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
-                }
-                tc_commit(&bar_mma);  // arrives when the MMAs above have completed
-            }
-            mbar_wait(&bar_mma, par_mma);
-            par_mma ^= 1;
-            tc_fence_after();
-
-            const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l]);
-            if (l + 1 < cfg.n_layers) {
-                // hidden layer epilogue: bias + activation -> fp16 -> next A operand (row = tid)
-                for (int c0 = cg * 16; c0 < N; c0 += 64) {
-                    float v[16];
-                    tmem_ld16(tmem_lane + (uint32_t)c0, v);
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-                    __half2 h[8];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bb = b4[q];
-                        float a0 = v[4 * q] + bb.x, a1 = v[4 * q + 1] + bb.y, a2 = v[4 * q + 2] + bb.z, a3 = v[4 * q + 3] + bb.w;
-                        if (ACT == 1) {
-                            a0 = gelu_erf(a0);
-                            a1 = gelu_erf(a1);
-                            a2 = gelu_erf(a2);
-                            a3 = gelu_erf(a3);
-                        } else {
-                            a0 = fmaxf(a0, 0.f);
-                            a1 = fmaxf(a1, 0.f);
-                            a2 = fmaxf(a2, 0.f);
-                            a3 = fmaxf(a3, 0.f);
-                        }
-                        h[2 * q] = __floats2half2_rn(a0, a1);
-                        h[2 * q + 1] = __floats2half2_rn(a2, a3);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(s_a1 + ((size_t)(c0 / 8) * kTileM + row) * 8);
-                    dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
-                    dst[kTileM] = *reinterpret_cast<const uint4*>(&h[4]);  // next 8-column chunk: +128 rows * 16 bytes
-                }
-            } else if (cg == 0) {
-                float v[16];
-                tmem_ld16(tmem_lane, v);
-                if (live) {
-                    float decay = 1.f;
-                    if (cfg.alpha_decay) {
-                        const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
-                        decay = 2.f * sigmoid_f(10.f * dot) - 1.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < cfg.out_dim) out[r * cfg.out_dim + j] = sigmoid_f(v[j] + bias[j]) * decay;
-                }
+        issue_layer(0, 0);
+        if (hasB) {
+            build_a0(1, tB);
+            issue_layer(1, 0);
+        }
+        for (int l = 0; l < L; ++l) {
+            epilogue(0, l, tA, tA + step);
+            if (l + 1 < L) issue_layer(0, l + 1);
+            if (hasB) {
+                epilogue(1, l, tB, tB + step);
+                if (l + 1 < L) issue_layer(1, l + 1);
             }
         }
-        // the next tile overwrites s_stage / s_extra / s_a0 and TMEM: everyone must be done reading them
+        // the next pair overwrites A0 / extras and both TMEM accumulators: everyone must be done reading them
         tc_fence_before();
         __syncthreads();
-        have_prefetched = next_prefetched;
-        if (cfg.prefetch) buf ^= 1;
+        tA += step;
+        if (two) tB += step;
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)cfg.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)(cfg.n_slots * cfg.tmem_cols));
 }
 
 static size_t mlp_smem_bytes(const MlpConfig& c) {
-    size_t b = (size_t)c.blob_bytes;
-    b += (size_t)kTileM * c.k_pad[0] * 2;
-    b += (size_t)kTileM * c.a1_width * 2;
-    b += (size_t)((kTileM * c.pos_dim + 3) & ~3) * 4 * (c.prefetch ? 2 : 1);
-    b += (size_t)kTileM * kExtraStride * 4;
-    return b + 128;
+    const size_t slot = (size_t)kTileM * c.k_pad[0] * 2 + (size_t)c.h_bytes + (size_t)kTileM * kExtraStride * 4;
+    return (size_t)c.blob_bytes + c.n_slots * slot + 128;
 }
 
 }  // namespace vs
@@ -308,10 +355,22 @@ int vs_mlp_pack(int n_layers, const int* dims, const float* const* weights, cons
     return launched(n_layers);
 }
 
+// bytes of the activation stash a training-mode vs_mlp_forward writes for n_samples samples (0 samples -> 0); < 0 on error
+int64_t vs_mlp_stash_bytes(int n_layers, const int* dims, int64_t n_samples) {
+    MlpConfig c;
+    if (!dims || n_samples < 0) return VS_ERR_INVALID_ARG;
+    int e = mlp_layout(n_layers, dims, &c);
+    if (e != VS_OK) return e;
+    MlpStash s;
+    mlp_stash_layout(c, &s);
+    return div_up(n_samples, kTileM) * (int64_t)s.tile_bytes;
+}
+
 // out[s, :out_dim] = sigmoid(MLP([pos[s] | SH_deg(dirs[s]) | normals[s]?])) (* alpha decay).  dims[0] must equal
 // pos_dim + (sh_degree+1)^2 (0 if sh_degree < 0) + 3*normal_dep.  n_valid_dev (optional device int64) caps the sample count.
+// stash (optional, vs_mlp_stash_bytes bytes, 16-byte aligned): training mode, activations are kept for vs_mlp_backward_stashed.
 int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
-                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, int64_t n_samples,
+                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, void* stash, int64_t n_samples,
                    const int64_t* n_valid_dev, int variant, void* stream) {
     VS_CHECK_ARG(dims && blob && n_samples >= 0 && pos_dim >= 0 && sh_degree <= 3);
     MlpConfig c;
@@ -323,31 +382,35 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
     VS_CHECK_ARG(pos_dim == 0 || pos);
     if (n_samples == 0) return VS_OK;
     VS_CHECK_ARG(out);
-    VS_CHECK_ARG((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
+    VS_CHECK_ARG((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(stash) & 15) == 0);
     c.pos_dim = pos_dim;
     c.n_sh = n_sh;
     c.normal_dep = normal_dep ? 1 : 0;
     c.activation = activation;
     c.alpha_decay = alpha_decay ? 1 : 0;
     c.variant = variant;
-    size_t smem = mlp_smem_bytes(c);
+    c.h_bytes = (std::max(kTileM * c.a1_width * 2, kTileM * pos_dim * 4) + 127) & ~127;
+    MlpStash sc;
+    mlp_stash_layout(c, &sc);
+    c.n_slots = 2;
+    if (mlp_smem_bytes(c) > 227 * 1024) c.n_slots = 1;
+    const size_t smem = mlp_smem_bytes(c);
     if (smem > 227 * 1024) return VS_ERR_UNSUPPORTED;
-    if (smem > 113 * 1024) {  // one CTA per SM anyway: spend the spare shared memory on a second feature buffer
-        c.prefetch = 1;
-        if (mlp_smem_bytes(c) > 227 * 1024) c.prefetch = 0;
-        smem = mlp_smem_bytes(c);
-    }
-    auto kern = activation == 1 ? mlp_fwd_kernel<1> : mlp_fwd_kernel<0>;
+    void (*kern)(MlpConfig, MlpStash, const uint8_t*, const float*, const float*, const float*, float*, uint8_t*, int64_t, const int64_t*);
+    if (stash)
+        kern = activation == 1 ? mlp_fwd_kernel<1, true> : mlp_fwd_kernel<0, true>;
+    else
+        kern = activation == 1 ? mlp_fwd_kernel<1, false> : mlp_fwd_kernel<0, false>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return (int)ce;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     const int64_t tiles = div_up(n_samples, kTileM);
-    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * ctas_per_sm);
-    kern<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(c, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
-                                                                     n_samples, n_valid_dev);
+    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>((tiles + c.n_slots - 1) / c.n_slots, 1), (int64_t)sms);
+    kern<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(c, sc, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
+                                                             reinterpret_cast<uint8_t*>(stash), n_samples, n_valid_dev);
     return launched(1);
 }
 

@@ -26,6 +26,20 @@ class ShellRenderer:
         """stage 1+2: all K layers in one launch, hits packed outer -> inner, face normals gathered"""
         return self.tracer.render_samples(rays_o, rays_d, exact_size=False, with_normals=True)
 
+    def shade_train(self, rsp, pos_features):
+        """stage 3 in training mode: like ``shade`` but both heads keep their activations (per-head stash buffers owned by the
+        renderer, re-used across steps) for ``heads_backward``"""
+        S = int(pos_features.shape[0])
+        outs = []
+        for name, head in (("rgb", self.rgb_head), ("alpha", self.alpha_head)):
+            stash = getattr(self, "_stash_" + name, None)
+            if stash is None or stash.numel() < head.stash_bytes(S) or stash.device != pos_features.device:
+                stash = head.new_stash(S, pos_features.device)
+                setattr(self, "_stash_" + name, stash)
+            out, _ = head.forward_train(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash)
+            outs.append(out)
+        return outs[0], outs[1]
+
     def shade(self, rsp, pos_features):
         """stage 3: per-hit colour and alpha (volsurfs.py:544-599).  ``pos_features`` [N*K, F]: output of the positional
         encoder for ``rsp.samples_3d`` (the permutohedral encoding is the stage before this path; synthetic in benchmarks)."""
@@ -55,7 +69,7 @@ class ShellRenderer:
         out.update(ray_samples_packed=rsp, samples_rgb=rgb, samples_alpha=alpha)
         return out
 
-    def heads_backward(self, rsp, pos_features, d_rgb, d_alpha, want_feature_grads=True):
+    def heads_backward(self, rsp, pos_features, d_rgb, d_alpha, want_feature_grads=True, fwd_outs=None):
         """stage 3 backward: per-sample colour / alpha gradients -> Linear parameter gradients of both heads (flat fp32 buffers
         ``grad_rgb`` / ``grad_alpha``, layout of AppearanceHead.split_flat) and, per head, the gradient of its positional features
         (every reference RGB model owns its encoder, rgb.py:40-60, so the two feature gradients stay separate)."""
@@ -71,7 +85,9 @@ class ShellRenderer:
                 if d_feat is None or d_feat.shape != pos_features.shape or d_feat.device != pos_features.device:
                     d_feat = torch.zeros_like(pos_features)
                     setattr(self, "_dfeat_" + name, d_feat)
-            head.backward_into(pos_features, rsp.samples_dirs, rsp.samples_normals, g, flat, d_feat, False, rsp.total_dev)
+            stash = getattr(self, "_stash_" + name, None) if fwd_outs is not None else None
+            head.backward_into(pos_features, rsp.samples_dirs, rsp.samples_normals, g, flat, d_feat, False, rsp.total_dev,
+                               stash=stash, fwd_out=None if stash is None else fwd_outs[name])
             out["grad_" + name] = flat
             out["d_features_" + name] = d_feat
         return out
@@ -80,7 +96,13 @@ class ShellRenderer:
         """one pass of the hot path with the L1 photometric loss of the reference (utils/losses.py:14-19):
         forward, d loss / d pred, compositing backward down to per-sample colour and alpha gradients, then the backward of both
         appearance heads (parameter gradients + gradients of their positional features)"""
-        out = self.render(rays_o, rays_d, pos_features)
+        if heads_backward:
+            rsp = self.intersect_and_pack(rays_o, rays_d)
+            rgb, alpha = self.shade_train(rsp, pos_features)
+            out = self.composite(rsp, alpha, rgb)
+            out.update(ray_samples_packed=rsp, samples_rgb=rgb, samples_alpha=alpha)
+        else:
+            out = self.render(rays_o, rays_d, pos_features)
         diff = out["rgb"] - gt_rgb
         loss = diff.abs().mean()
         g_pred = torch.sign(diff) / diff.numel()
@@ -88,7 +110,8 @@ class ShellRenderer:
         d_alpha, d_rgb = self.composite_backward(rsp, out["samples_alpha"], out["samples_rgb"], g_pred)
         out.update(loss=loss, d_alpha=d_alpha, d_rgb=d_rgb)
         if heads_backward:
-            out.update(self.heads_backward(rsp, pos_features, d_rgb, d_alpha))
+            out.update(self.heads_backward(rsp, pos_features, d_rgb, d_alpha,
+                                           fwd_outs={"rgb": out["samples_rgb"], "alpha": out["samples_alpha"]}))
         return out
 
 
