@@ -41,30 +41,40 @@ __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __rest
 }
 
 
-// One CTA keeps TWO 128-sample tiles in flight (slots 0 and 1, each with its own operand buffers and TMEM accumulator): while the
-// 16 warps run the epilogue of one slot's layer, the tensor core works on the other slot's next layer, so neither the MMA latency
-// nor the barrier that hands the operands over is exposed.  STASH: training mode — every layer's input operand and every hidden
-// layer's activation derivative also go to global memory (16-byte stores, a warp covers 512 contiguous bytes) for the backward.
+// One CTA keeps TWO 128-sample tiles in flight (slots 0 and 1, each with its own operand buffers and TMEM accumulator) and is
+// warp-specialised:
+//   * warps 0..15 (512 threads) are epilogue warps: they build the layer-0 operand and, per layer, read the accumulator back
+//     (tcgen05.ld), apply bias + activation and write the next operand.  They never synchronise with each other: a warp that is
+//     done announces it on the slot's `ready` mbarrier and moves on to the other slot;
+//   * warp 16 is the control warp: one lane waits for `ready`, issues the layer's tcgen05.mma sequence, commits it to the slot's
+//     `full` mbarrier (which the epilogue warps wait on) and requests the features of the slot's next tile by TMA as soon as the
+//     landing zone is free.
+// While the epilogue warps work on one slot the tensor core works on the other, so neither the MMA latency nor the hand-over is
+// exposed.  STASH: training mode — every layer's input operand and every hidden layer's activation derivative also go to global
+// memory (16-byte stores, a warp covers 512 contiguous bytes) for the backward.
+constexpr int kFwdThreads = kMlpThreads + 32;
+
 template <int ACT, bool STASH>  // ACT: 0 ReLU, 1 GELU (compile-time: the epilogue loop carries no branch)
-__global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cfg, const MlpStash stash_cfg, const uint8_t* __restrict__ blob,
+__global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cfg, const MlpStash stash_cfg, const uint8_t* __restrict__ blob,
                                                               const float* __restrict__ pos, const float* __restrict__ dirs,
                                                               const float* __restrict__ normals, float* __restrict__ out,
                                                               uint8_t* __restrict__ stash, int64_t n_samples,
                                                               const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_mma[2];
+    __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_full[2], bar_ready[2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int lane = tid & 31;
     const int row = tid & (kTileM - 1);  // sample of the tile this thread works on (== its TMEM lane)
-    const int cg = tid >> 7;             // column group 0..3: which quarter of the columns / K-chunks this thread handles
+    const int cg = (tid >> 7) & 3;       // column group 0..3: which quarter of the columns this thread handles
     const int F = cfg.pos_dim;
     const int L = cfg.n_layers;
     const int k0 = cfg.k_pad[0];
 
     // carve shared memory: blob | per slot: A0 (layer-0 operand) | H (hidden activations; also the TMA landing zone of the fp32
-    // features, which are consumed before the first hidden activation is written) | extras (SH, normals)
+    // features, which are consumed before the first hidden activation is written) | extras (per-row scratch of the row's owner)
     const int a0_bytes = kTileM * k0 * 2;
     const int h_bytes = cfg.h_bytes;
     const int slot_bytes = a0_bytes + h_bytes + kTileM * kExtraStride * 4;
@@ -77,198 +87,217 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
-        mbar_init(&bar_in[0], 1);
-        mbar_init(&bar_in[1], 1);
-        mbar_init(&bar_mma[0], 1);
-        mbar_init(&bar_mma[1], 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_in[s], 1);
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_ready[s], kMlpThreads / 32);  // one arrival per epilogue warp
+        }
     }
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)(cfg.n_slots * cfg.tmem_cols));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch lanes 32*(warp%4)..+31
-
-    if ((int64_t)blockIdx.x < n_tiles && tid == 0) {  // weights + biases: resident for the whole kernel
-        mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
-        bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
-    }
-    bool weights_ready = false;
-    uint32_t par_in[2] = {0, 0}, par_mma[2] = {0, 0};
-    const uint32_t lbo_sel = (cfg.variant & 1);
 
     auto slot_a0 = [&](int s) { return reinterpret_cast<__half*>(s_slots + (size_t)s * slot_bytes); };
     auto slot_h = [&](int s) { return reinterpret_cast<__half*>(s_slots + (size_t)s * slot_bytes + a0_bytes); };
     auto slot_extra = [&](int s) { return reinterpret_cast<float*>(s_slots + (size_t)s * slot_bytes + a0_bytes + h_bytes); };
 
-    // features of a full tile -> the slot's landing zone (one TMA bulk copy); partial tiles are read straight from global memory
-    auto request_features = [&](int s, int64_t tile) {
-        if (tid == 0 && tile < n_tiles && (tile + 1) * kTileM <= n && F > 0) {
-            mbar_arrive_expect_tx(&bar_in[s], (uint32_t)(kTileM * F * 4));
-            bulk_g2s(slot_h(s), pos + tile * kTileM * F, (uint32_t)(kTileM * F * 4), &bar_in[s]);
-        }
-    };
+    const int64_t stride = gridDim.x;
+    const bool two = cfg.n_slots == 2;
+    const int64_t step = two ? 2 * stride : stride;
 
-    // per-row state kept in registers between build and the output epilogue (alpha decay)
-    float decay[2] = {1.f, 1.f};
-
-    auto build_a0 = [&](int s, int64_t tile) {
-        const int64_t row0 = tile * kTileM;
-        const int rows = (int)min((int64_t)kTileM, n - row0);
-        const bool full = rows == kTileM;
-        const int64_t r = row0 + row;
-        const bool live = row < rows;
-        float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-        if (live) {
-            if (dirs != nullptr) {
-                dx = __ldg(dirs + 3 * r);
-                dy = __ldg(dirs + 3 * r + 1);
-                dz = __ldg(dirs + 3 * r + 2);
-            }
-            if (normals != nullptr) {
-                nx = __ldg(normals + 3 * r);
-                ny = __ldg(normals + 3 * r + 1);
-                nz = __ldg(normals + 3 * r + 2);
-            }
-        }
-        decay[s] = 1.f;
-        if (cfg.alpha_decay) {
-            const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
-            decay[s] = 2.f * sigmoid_f(10.f * dot) - 1.f;
-        }
-        float* ex = slot_extra(s) + row * kExtraStride;
-        if (cg == 0) {
-            float sh[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sh[i] = 0.f;
-            sh_eval(dx, dy, dz, cfg.n_sh, sh);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ex[i] = sh[i];
-            if (cfg.normal_dep) {  // with n_sh < 16 the normal follows the SH block directly
-                ex[cfg.n_sh] = nx;
-                ex[cfg.n_sh + 1] = ny;
-                ex[cfg.n_sh + 2] = nz;
-            }
-        }
-        __syncthreads();
-        if (full && F > 0) {
-            mbar_wait(&bar_in[s], par_in[s]);
-            par_in[s] ^= 1;
-        }
-        // row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes; the four column groups split
-        // the K-chunks of a row
-        const float* srow = full ? reinterpret_cast<const float*>(slot_h(s)) + row * F : pos + r * F;
-        __half* a0 = slot_a0(s);
-        uint8_t* st_a0 = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[0] : nullptr;
-        const int in_dim = cfg.in_dim;
-        for (int kc = cg; kc < k0 / 8; kc += 4) {
-            __half2 h[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float v2[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int c = kc * 8 + 2 * j + q;
-                    float v = 0.f;
-                    if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
-                    v2[q] = v;
+    if (warp == kMlpThreads / 32) {
+        // ================= control warp =================
+        if (lane == 0 && (int64_t)blockIdx.x < n_tiles) {
+            mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);  // weights + biases: resident for the whole kernel
+            bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
+            // features of a full tile -> the slot's landing zone (one TMA bulk copy); partial tiles are read from global memory
+            auto request_features = [&](int s, int64_t tile) {
+                if (tile < n_tiles && (tile + 1) * kTileM <= n && F > 0) {
+                    mbar_arrive_expect_tx(&bar_in[s], (uint32_t)(kTileM * F * 4));
+                    bulk_g2s(slot_h(s), pos + tile * kTileM * F, (uint32_t)(kTileM * F * 4), &bar_in[s]);
                 }
-                h[j] = __floats2half2_rn(v2[0], v2[1]);
-            }
-            const uint4 pk = *reinterpret_cast<const uint4*>(h);
-            *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
-            if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
-        }
-        if (STASH && stash_cfg.fold[0] && cg == 1)  // the "ones" chunk behind A_0 (bias gradient row of the backward's dW GEMM)
-            *reinterpret_cast<uint4*>(st_a0 + ((size_t)(k0 / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
-    };
-
-    // hand the slot's operand over to the tensor core and start layer l: D[slot] = A_l W_l^T
-    auto issue_layer = [&](int s, int l) {
-        fence_proxy_async();  // this thread's operand writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const int K = cfg.k_pad[l], N = cfg.n_pad[l];
-            const uint32_t a_base = smem_u32(l == 0 ? slot_a0(s) : slot_h(s));
-            const uint32_t b_base = smem_u32(s_blob + cfg.w_off[l]);
-            const uint32_t a_lbo = kTileM * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
-            const uint32_t idesc = umma_idesc_f16(kTileM, N);
-            const uint32_t d = tmem_base + (uint32_t)(s * cfg.tmem_cols);
-            for (int ks = 0; ks < K / 16; ++ks) {
-                const uint32_t a_addr = a_base + (uint32_t)ks * 2 * a_lbo;
-                const uint32_t b_addr = b_base + (uint32_t)ks * 2 * b_lbo;
-                const uint64_t ad = lbo_sel ? umma_desc(a_addr, sbo, a_lbo) : umma_desc(a_addr, a_lbo, sbo);
-                const uint64_t bd = lbo_sel ? umma_desc(b_addr, sbo, b_lbo) : umma_desc(b_addr, b_lbo, sbo);
-                tc_mma_f16(d, ad, bd, idesc, ks > 0 ? 1u : 0u);
-            }
-            tc_commit(&bar_mma[s]);  // arrives when the MMAs above have completed
-        }
-    };
-
-    // layer l of slot s has landed in TMEM: bias + activation -> next operand (hidden) or sigmoid -> out (last layer)
-    auto epilogue = [&](int s, int l, int64_t tile, int64_t next_tile) {
-        mbar_wait(&bar_mma[s], par_mma[s]);
-        par_mma[s] ^= 1;
-        tc_fence_after();
-        const int N = cfg.n_pad[l];
-        const uint32_t tmem_lane = tmem_base + lane_off + (uint32_t)(s * cfg.tmem_cols);
-        const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l]);
-        const int64_t r = tile * kTileM + row;
-        if (l + 1 < L) {
-            __half* hbuf = slot_h(s);
-            uint8_t* st_a = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[l + 1] : nullptr;
-            uint8_t* st_g = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.g_off[l] : nullptr;
-            if (STASH && stash_cfg.fold[l + 1] && cg == 1)
-                *reinterpret_cast<uint4*>(st_a + ((size_t)(N / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
-            for (int c0 = cg * 16; c0 < N; c0 += 64) {
-                float v[16];
-                tmem_ld16(tmem_lane + (uint32_t)c0, v);
-                const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-                __half2 h[8], gh[8];
+            };
+            int64_t t[2] = {(int64_t)blockIdx.x, two ? (int64_t)blockIdx.x + stride : n_tiles};
+            request_features(0, t[0]);
+            request_features(1, t[1]);
+            mbar_wait(&bar_w, 0);
+            uint32_t par_ready[2] = {0, 0}, par_full[2] = {0, 0};
+            while (t[0] < n_tiles) {
+                for (int l = 0; l < L; ++l) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 bb = b4[q];
-                    const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
-                    float a0, a1, a2, a3, g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-                    if (ACT == 1) {
-                        gelu_pair<STASH>(x0, x1, a0, a1, g0, g1);
-                        gelu_pair<STASH>(x2, x3, a2, a3, g2, g3);
-                    } else {
-                        a0 = fmaxf(x0, 0.f);
-                        a1 = fmaxf(x1, 0.f);
-                        a2 = fmaxf(x2, 0.f);
-                        a3 = fmaxf(x3, 0.f);
+                    for (int s = 0; s < 2; ++s) {
+                        if (t[s] >= n_tiles) continue;
+                        mbar_wait(&bar_ready[s], par_ready[s]);  // every epilogue warp has written its part of the operand
+                        par_ready[s] ^= 1;
+                        tc_fence_after();
+                        const int K = cfg.k_pad[l], N = cfg.n_pad[l];
+                        const uint32_t a_base = smem_u32(l == 0 ? slot_a0(s) : slot_h(s));
+                        const uint32_t b_base = smem_u32(s_blob + cfg.w_off[l]);
+                        const uint32_t a_lbo = kTileM * 16, b_lbo = (uint32_t)N * 16;
+                        umma_gemm_f16(tmem_base + (uint32_t)(s * cfg.tmem_cols), a_base, a_lbo, 128, 2 * a_lbo, b_base, b_lbo, 128, 2 * b_lbo,
+                                      umma_idesc_f16(kTileM, N), K / 16, false);
+                        tc_commit(&bar_full[s]);  // arrives when the MMAs above have completed
+                        if (l == L - 1) {
+                            // the (short) output-layer GEMM was the last reader of H: fetch the slot's next features under the
+                            // other slot's epilogue
+                            mbar_wait(&bar_full[s], par_full[s]);
+                            request_features(s, t[s] + step);
+                        }
+                        par_full[s] ^= 1;
+                    }
+                }
+                t[0] += step;
+                if (two) t[1] += step;
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        uint32_t par_in[2] = {0, 0}, par_full[2] = {0, 0};
+        float decay[2] = {1.f, 1.f};  // alpha decay of this thread's row (used by the row's cg == 0 thread in the output epilogue)
+
+        auto announce = [&](int s) {  // this warp's writes to the slot's next operand are done
+            fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_ready[s]);
+        };
+
+        auto build_a0 = [&](int s, int64_t tile) {
+            const int64_t row0 = tile * kTileM;
+            const int rows = (int)min((int64_t)kTileM, n - row0);
+            const bool full = rows == kTileM;
+            const int64_t r = row0 + row;
+            const bool live = row < rows;
+            if (full && F > 0) {
+                mbar_wait(&bar_in[s], par_in[s]);
+                par_in[s] ^= 1;
+            }
+            const float* srow = full ? reinterpret_cast<const float*>(slot_h(s)) + row * F : pos + r * F;
+            __half* a0 = slot_a0(s);
+            uint8_t* st_a0 = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[0] : nullptr;
+            const int in_dim = cfg.in_dim;
+            const int tail0 = F / 8;  // first chunk that holds SH / normal / padding columns: those belong to the row's cg == 0 thread
+            float* ex = slot_extra(s) + row * kExtraStride;
+            if (cg == 0) {
+                float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+                if (live) {
+                    if (dirs != nullptr) {
+                        dx = __ldg(dirs + 3 * r);
+                        dy = __ldg(dirs + 3 * r + 1);
+                        dz = __ldg(dirs + 3 * r + 2);
+                    }
+                    if (normals != nullptr) {
+                        nx = __ldg(normals + 3 * r);
+                        ny = __ldg(normals + 3 * r + 1);
+                        nz = __ldg(normals + 3 * r + 2);
+                    }
+                }
+                decay[s] = 1.f;
+                if (cfg.alpha_decay) {
+                    const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
+                    decay[s] = 2.f * sigmoid_f(10.f * dot) - 1.f;
+                }
+                float sh[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+                sh_eval(dx, dy, dz, cfg.n_sh, sh);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ex[i] = sh[i];  // private scratch row: written and read back by this thread only
+                if (cfg.normal_dep) {                        // with n_sh < 16 the normal follows the SH block directly
+                    ex[cfg.n_sh] = nx;
+                    ex[cfg.n_sh + 1] = ny;
+                    ex[cfg.n_sh + 2] = nz;
+                }
+            }
+            // row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes.  Pure feature chunks are
+            // split over column groups 1..3, the tail chunks go to column group 0.
+            const int kc_begin = cg == 0 ? tail0 : cg - 1, kc_end = cg == 0 ? k0 / 8 : tail0, kc_step = cg == 0 ? 1 : 3;
+            for (int kc = kc_begin; kc < kc_end; kc += kc_step) {
+                __half2 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v2[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = kc * 8 + 2 * j + q;
+                        float v = 0.f;
+                        if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
+                        v2[q] = v;
+                    }
+                    h[j] = __floats2half2_rn(v2[0], v2[1]);
+                }
+                const uint4 pk = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
+                if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+            }
+            if (STASH && stash_cfg.fold[0] && cg == 1)  // the "ones" chunk behind A_0 (bias gradient row of the backward's dW GEMM)
+                *reinterpret_cast<uint4*>(st_a0 + ((size_t)(k0 / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+            announce(s);
+        };
+
+        // layer l of slot s has landed in TMEM: bias + activation -> next operand (hidden) or sigmoid -> out (last layer)
+        auto epilogue = [&](int s, int l, int64_t tile) {
+            mbar_wait(&bar_full[s], par_full[s]);
+            par_full[s] ^= 1;
+            tc_fence_after();
+            const int N = cfg.n_pad[l];
+            const uint32_t tmem_lane = tmem_base + lane_off + (uint32_t)(s * cfg.tmem_cols);
+            const float* bias = reinterpret_cast<const float*>(s_blob + cfg.b_off[l]);
+            const int64_t r = tile * kTileM + row;
+            if (l + 1 < L) {
+                uint8_t* hbuf = reinterpret_cast<uint8_t*>(slot_h(s));
+                uint8_t* st_a = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[l + 1] : nullptr;
+                uint8_t* st_g = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.g_off[l] : nullptr;
+                if (STASH && stash_cfg.fold[l + 1] && cg == 1)
+                    *reinterpret_cast<uint4*>(st_a + ((size_t)(N / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+                for (int c0 = cg * 16; c0 < N; c0 += 64) {
+                    float v[16];
+                    tmem_ld16(tmem_lane + (uint32_t)c0, v);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+                    __half2 h[8], gh[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = b4[q];
+                        const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
+                        float a0, a1, a2, a3, g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+                        if (ACT == 1) {
+                            gelu_pair<STASH>(x0, x1, a0, a1, g0, g1);
+                            gelu_pair<STASH>(x2, x3, a2, a3, g2, g3);
+                        } else {
+                            a0 = fmaxf(x0, 0.f);
+                            a1 = fmaxf(x1, 0.f);
+                            a2 = fmaxf(x2, 0.f);
+                            a3 = fmaxf(x3, 0.f);
+                            if (STASH) {
+                                g0 = x0 > 0.f ? 1.f : 0.f;
+                                g1 = x1 > 0.f ? 1.f : 0.f;
+                                g2 = x2 > 0.f ? 1.f : 0.f;
+                                g3 = x3 > 0.f ? 1.f : 0.f;
+                            }
+                        }
+                        h[2 * q] = __floats2half2_rn(a0, a1);
+                        h[2 * q + 1] = __floats2half2_rn(a2, a3);
                         if (STASH) {
-                            g0 = x0 > 0.f ? 1.f : 0.f;
-                            g1 = x1 > 0.f ? 1.f : 0.f;
-                            g2 = x2 > 0.f ? 1.f : 0.f;
-                            g3 = x3 > 0.f ? 1.f : 0.f;
+                            gh[2 * q] = __floats2half2_rn(g0, g1);
+                            gh[2 * q + 1] = __floats2half2_rn(g2, g3);
                         }
                     }
-                    h[2 * q] = __floats2half2_rn(a0, a1);
-                    h[2 * q + 1] = __floats2half2_rn(a2, a3);
+                    const size_t off = ((size_t)(c0 / 8) * kTileM + row) * 16;  // next 8-column chunk: +128 rows * 16 bytes
+                    const uint4 lo = *reinterpret_cast<const uint4*>(&h[0]), hi = *reinterpret_cast<const uint4*>(&h[4]);
+                    *reinterpret_cast<uint4*>(hbuf + off) = lo;
+                    *reinterpret_cast<uint4*>(hbuf + off + kTileM * 16) = hi;
                     if (STASH) {
-                        gh[2 * q] = __floats2half2_rn(g0, g1);
-                        gh[2 * q + 1] = __floats2half2_rn(g2, g3);
+                        *reinterpret_cast<uint4*>(st_a + off) = lo;
+                        *reinterpret_cast<uint4*>(st_a + off + kTileM * 16) = hi;
+                        *reinterpret_cast<uint4*>(st_g + off) = *reinterpret_cast<const uint4*>(&gh[0]);
+                        *reinterpret_cast<uint4*>(st_g + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&gh[4]);
                     }
                 }
-                const size_t off = ((size_t)(c0 / 8) * kTileM + row) * 16;  // next 8-column chunk: +128 rows * 16 bytes
-                const uint4 lo = *reinterpret_cast<const uint4*>(&h[0]), hi = *reinterpret_cast<const uint4*>(&h[4]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hbuf) + off) = lo;
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hbuf) + off + kTileM * 16) = hi;
-                if (STASH) {
-                    *reinterpret_cast<uint4*>(st_a + off) = lo;
-                    *reinterpret_cast<uint4*>(st_a + off + kTileM * 16) = hi;
-                    *reinterpret_cast<uint4*>(st_g + off) = *reinterpret_cast<const uint4*>(&gh[0]);
-                    *reinterpret_cast<uint4*>(st_g + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&gh[4]);
-                }
-            }
-        } else {
-            // the MMAs that read H have completed: the slot's landing zone is free for the features of its next tile
-            request_features(s, next_tile);
-            if (cg == 0) {
+                announce(s);
+            } else if (cg == 0) {
                 float v[16];
                 tmem_ld16(tmem_lane, v);
                 if (r < n) {
@@ -277,40 +306,21 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpConfig cf
                         if (j < cfg.out_dim) out[r * cfg.out_dim + j] = sigmoid_f(v[j] + bias[j]) * decay[s];
                 }
             }
-        }
-    };
+        };
 
-    const int64_t stride = gridDim.x;
-    const bool two = cfg.n_slots == 2;
-    const int64_t step = two ? 2 * stride : stride;
-    int64_t tA = blockIdx.x, tB = two ? tA + stride : n_tiles;
-    request_features(0, tA);
-    request_features(1, tB);
-    while (tA < n_tiles) {
-        const bool hasB = tB < n_tiles;
-        build_a0(0, tA);
-        if (!weights_ready) {
-            mbar_wait(&bar_w, 0);
-            weights_ready = true;
-        }
-        issue_layer(0, 0);
-        if (hasB) {
-            build_a0(1, tB);
-            issue_layer(1, 0);
-        }
-        for (int l = 0; l < L; ++l) {
-            epilogue(0, l, tA, tA + step);
-            if (l + 1 < L) issue_layer(0, l + 1);
-            if (hasB) {
-                epilogue(1, l, tB, tB + step);
-                if (l + 1 < L) issue_layer(1, l + 1);
+        int64_t tA = blockIdx.x, tB = two ? tA + stride : n_tiles;
+        if (tA < n_tiles) mbar_wait(&bar_w, 0);  // biases live in the blob
+        while (tA < n_tiles) {
+            const bool hasB = tB < n_tiles;
+            build_a0(0, tA);
+            if (hasB) build_a0(1, tB);
+            for (int l = 0; l < L; ++l) {
+                epilogue(0, l, tA);
+                if (hasB) epilogue(1, l, tB);
             }
+            tA += step;
+            if (two) tB += step;
         }
-        // the next pair overwrites A0 / extras and both TMEM accumulators: everyone must be done reading them
-        tc_fence_before();
-        __syncthreads();
-        tA += step;
-        if (two) tB += step;
     }
 
     tc_fence_before();
@@ -409,7 +419,7 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = div_up(n_samples, kTileM);
     const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>((tiles + c.n_slots - 1) / c.n_slots, 1), (int64_t)sms);
-    kern<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(c, sc, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
+    kern<<<grid, kFwdThreads, smem, (cudaStream_t)stream>>>(c, sc, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
                                                              reinterpret_cast<uint8_t*>(stash), n_samples, n_valid_dev);
     return launched(1);
 }

@@ -526,14 +526,17 @@ __global__ void mlp_bwd_reduce_kernel(const float* __restrict__ partials, int n_
 // =====================================================================================================================
 // Backward from the activation stash (training-mode vs_mlp_forward): no recomputation, no activation-derivative math.
 //
-// Per 128-sample tile the kernel needs, in this order: dZ_last (built from dOut and the forward output), A_{L-1}, G_{L-2}, A_{L-2}, ...,
-// G_0, A_0 and a staging area for the input gradient.  Lifetimes are first-in-first-out, so the operands live in ONE shared-memory
-// ring: thread 0 runs ahead along the item sequence (across tile boundaries) and fetches every stash item with a TMA bulk copy as
-// soon as the ring has room; an item's mbarrier tells the consumers it has landed.  Every thread replays the same allocator
-// arithmetic, so offsets need no communication.  Per layer, one elected thread issues
-//     dA_l  = dZ_l W_l        (commit -> bar_da: the epilogue waits for this one only)
-//     dW_l^T (+)= A_l^T dZ_l  (+ bias side GEMM; commit -> bar_dw: runs under the epilogue; frees the layer's ring items)
-// and the epilogue turns dA_l into dZ_{l-1} = dA_l * G_{l-1} IN PLACE in G_{l-1}'s ring slot (fp16).
+// Per 128-sample tile the kernel needs, in this order: dZ_last (built from dOut and the forward output), A_{L-1}, dZ_{L-2}, A_{L-2},
+// ..., dZ_0, A_0 and a staging area for the input gradient.  Lifetimes are first-in-first-out, so the operands live in ONE
+// shared-memory ring.  The CTA is warp-specialised:
+//   * the control warp (one lane) walks the item sequence ahead of everybody else (across tile boundaries): it reserves ring space,
+//     fetches every A_l with a TMA bulk copy as soon as there is room, and per layer issues
+//         dA_l  = dZ_l W_l        (commit -> bar_da: the epilogue warps wait for this one only)
+//         dW_l^T (+)= A_l^T dZ_l  (+ bias side GEMM; commit -> bar_dw: runs under the epilogue; then dZ_l and A_l leave the ring)
+//   * the 16 epilogue warps fetch their own elements of G_{l-1} (the saved activation derivative) straight from global memory into
+//     registers BEFORE they wait for dA_l, multiply and write dZ_{l-1} (fp16) into its ring slot, and announce it on `ready`.
+// Every thread replays the same allocator arithmetic, so ring offsets need no communication; an item's mbarrier says "landed" (TMA
+// items) or "this space is yours" (items the kernel produces itself).
 struct MlpBwd2Plan {
     int n_items;                        // items per tile: 2L (+1 with the input gradient)
     int item_bytes[2 * kMaxLayers + 2];
@@ -544,6 +547,7 @@ struct MlpBwd2Plan {
 };
 
 constexpr int kItemBars = 16;
+constexpr int kBwdThreads = kMlpThreads + 32;
 
 static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_dim, int want_dx, MlpBwd2Plan* p) {
     std::memset(p, 0, sizeof(*p));
@@ -555,8 +559,8 @@ static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_
         p->item_bytes[i] = st.a_bytes[l];
         p->item_src[i++] = st.a_off[l];
         if (l >= 1) {
-            p->item_bytes[i] = kTileM * c.n_pad[l - 1] * 2;
-            p->item_src[i++] = st.g_off[l - 1];
+            p->item_bytes[i] = kTileM * c.n_pad[l - 1] * 2;  // dZ_{l-1}
+            p->item_src[i++] = -1;
         }
     }
     if (want_dx) {
@@ -568,14 +572,14 @@ static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_
     // ring | ones (bias side-GEMM operand) | blob.  MN-major operands read a fixed 16-chunk (32 KB) window from their base: what
     // lies behind the ring must cover it.
     const int tail = kOnesBytes + std::max(c.blob_bytes, 16 * kChunkBytes);
-    int ring = (227 * 1024 - 256 - tail) / 2048 * 2048;
-    int need = 0, top3[3] = {0, 0, 0};
+    int ring = (227 * 1024 - 512 - tail) / 2048 * 2048;
+    int top3[3] = {0, 0, 0};
     for (int k = 0; k < p->n_items; ++k) {
         int b = p->item_bytes[k];
         for (int t = 0; t < 3; ++t)
             if (b > top3[t]) std::swap(b, top3[t]);
     }
-    need = 2 * (top3[0] + top3[1] + top3[2]);  // three live operands + the next layer's prefetch + wrap fragments
+    const int need = 2 * (top3[0] + top3[1] + top3[2]);  // three live operands + the next layer's prefetch + wrap fragments
     ring = std::min(ring, std::max(need, 64 * 1024));
     if (ring < top3[0] + top3[1] + top3[2] + top3[0]) return VS_ERR_UNSUPPORTED;
     p->ring_bytes = ring;
@@ -585,20 +589,15 @@ static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_
 
 struct RingCursor {
     int head;
-    __device__ __forceinline__ int alloc(int bytes, int ring_bytes, int* skipped = nullptr) {
-        int skip = 0;
-        if (head + bytes > ring_bytes) {
-            skip = ring_bytes - head;
-            head = 0;
-        }
+    __device__ __forceinline__ int alloc(int bytes, int ring_bytes) {
+        if (head + bytes > ring_bytes) head = 0;
         const int off = head;
         head += bytes;
-        if (skipped) *skipped = skip;
         return off;
     }
 };
 
-__global__ void __launch_bounds__(kMlpThreads) mlp_bwd_stashed_kernel(const MlpConfig cfg, const MlpBwdPlan plan, const MlpBwd2Plan p2,
+__global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpConfig cfg, const MlpBwdPlan plan, const MlpBwd2Plan p2,
                                                                       const MlpStash st, const uint8_t* __restrict__ blob,
                                                                       const uint8_t* __restrict__ stash, const float* __restrict__ dirs,
                                                                       const float* __restrict__ normals, const float* __restrict__ fwd_out,
@@ -606,13 +605,14 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_stashed_kernel(const MlpC
                                                                       float* __restrict__ d_pos, float* __restrict__ partials,
                                                                       int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw, bar_item[kItemBars];
+    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw, bar_ready, bar_x, bar_item[kItemBars];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int lane = tid & 31;
     const int row = tid & (kTileM - 1);
-    const int cg = tid >> 7;
+    const int cg = (tid >> 7) & 3;
     const int F = cfg.pos_dim;
     const int L = cfg.n_layers;
     const int R = p2.ring_bytes;
@@ -632,6 +632,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_stashed_kernel(const MlpC
         mbar_init(&bar_w, 1);
         mbar_init(&bar_da, 1);
         mbar_init(&bar_dw, 1);
+        mbar_init(&bar_ready, kMlpThreads / 32);
+        mbar_init(&bar_x, kMlpThreads / 32);
         for (int i = 0; i < kItemBars; ++i) mbar_init(&bar_item[i], 1);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)plan.tmem_cols);
@@ -641,74 +643,140 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_stashed_kernel(const MlpC
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tmem_work = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-
-    // ---- producer state (thread 0): runs ahead of the consumers along the global item sequence ---------------------------------
-    const int64_t total_items = my_tiles * p2.n_items;
-    int64_t prod_seq = 0, free_seq = 0;   // items [free_seq, prod_seq) are live
-    RingCursor prod{0};
-    int used = 0;                          // bytes of the ring held by live items (including wrap fragments)
-    int live_cost[kItemBars];
-    auto produce = [&]() {                 // thread 0 only
-        while (prod_seq < total_items && prod_seq - free_seq < kItemBars - 1) {
-            const int i = (int)(prod_seq % p2.n_items);
-            const int bytes = p2.item_bytes[i];
-            const int skip = (prod.head + bytes > R) ? R - prod.head : 0;
-            if (used + skip + bytes > R) break;
-            const int off = prod.alloc(bytes, R);
-            used += skip + bytes;
-            live_cost[prod_seq % kItemBars] = skip + bytes;
-            uint64_t* bar = &bar_item[prod_seq % kItemBars];
-            if (p2.item_src[i] >= 0) {
-                const int64_t tile = blockIdx.x + (prod_seq / p2.n_items) * gridDim.x;
-                mbar_arrive_expect_tx(bar, (uint32_t)bytes);
-                bulk_g2s(s_ring + off, stash + tile * (int64_t)st.tile_bytes + p2.item_src[i], (uint32_t)bytes, bar);
-            } else {
-                mbar_arrive(bar);  // produced by the kernel itself: the completed phase only says "this ring space is yours"
-            }
-            ++prod_seq;
-        }
-    };
-    auto release = [&](int count) {        // thread 0 only: the oldest `count` items are dead
-        for (int k = 0; k < count; ++k) {
-            used -= live_cost[free_seq % kItemBars];
-            ++free_seq;
-        }
-    };
-
-    if (my_tiles > 0 && tid == 0) {
-        mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
-        bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
-        produce();
-    }
-    if (my_tiles > 0) mbar_wait(&bar_w, 0);
-
-    // ---- consumer state (every thread) ---------------------------------------------------------------------------------------
-    RingCursor cons{0};
-    int64_t cons_seq = 0;
-    uint32_t par_da = 0, par_dw = 0;
     const uint32_t mn_lbo = 128u, mn_sbo = (uint32_t)kChunkBytes;
-    bool first_tile = true;
-    bool store_pending = false;            // thread 0: an input-gradient bulk store may still be reading its ring item
-    auto wait_item = [&](int64_t seq) { mbar_wait(&bar_item[seq % kItemBars], (uint32_t)((seq / kItemBars) & 1)); };
+    auto item_bar = [&](uint32_t seq) { return &bar_item[seq & (kItemBars - 1)]; };
+    auto item_parity = [&](uint32_t seq) { return (seq / kItemBars) & 1u; };
 
-    for (int64_t k = 0; k < my_tiles; ++k) {
-        const int64_t tile = blockIdx.x + k * gridDim.x;
-        const int64_t row0 = tile * kTileM;
-        const int rows = (int)min((int64_t)kTileM, n - row0);
-        const bool full = rows == kTileM;
-        const int64_t r = row0 + row;
-        const bool live = row < rows;
+    if (warp == kMlpThreads / 32) {
+        // ================= control warp: ring producer + MMA issuer =================
+        if (lane == 0 && my_tiles > 0) {
+            mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
+            bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
+            // producer / release cursors replay the allocator; counters are kept incrementally (no division on this lane's path)
+            const int n_items = p2.n_items;
+            int64_t prod_seq = 0, free_seq = 0;  // items [free_seq, prod_seq) are live
+            const int64_t total_items = my_tiles * n_items;
+            int prod_item = 0, free_item = 0;    // position inside the tile's item list
+            int64_t prod_tile = blockIdx.x;
+            RingCursor prod{0}, freed{0};
+            int used = 0;                         // ring bytes held by live items (including wrap fragments)
+            auto produce = [&]() {
+                while (prod_seq < total_items && prod_seq - free_seq < kItemBars - 1) {
+                    const int bytes = p2.item_bytes[prod_item];
+                    const int skip = (prod.head + bytes > R) ? R - prod.head : 0;
+                    if (used + skip + bytes > R) break;
+                    const int off = prod.alloc(bytes, R);
+                    used += skip + bytes;
+                    uint64_t* bar = &bar_item[prod_seq & (kItemBars - 1)];
+                    const int src = p2.item_src[prod_item];
+                    if (src >= 0) {
+                        mbar_arrive_expect_tx(bar, (uint32_t)bytes);
+                        bulk_g2s(s_ring + off, stash + prod_tile * (int64_t)st.tile_bytes + src, (uint32_t)bytes, bar);
+                    } else {
+                        mbar_arrive(bar);  // produced by the kernel itself: "this ring space is yours"
+                    }
+                    ++prod_seq;
+                    if (++prod_item == n_items) {
+                        prod_item = 0;
+                        prod_tile += gridDim.x;
+                    }
+                }
+            };
+            auto release = [&](int count) {
+                for (int k = 0; k < count; ++k) {
+                    const int bytes = p2.item_bytes[free_item];
+                    const int skip = (freed.head + bytes > R) ? R - freed.head : 0;
+                    freed.alloc(bytes, R);
+                    used -= skip + bytes;
+                    ++free_seq;
+                    if (++free_item == n_items) free_item = 0;
+                }
+            };
+            produce();
+            mbar_wait(&bar_w, 0);
+            RingCursor cur{0};
+            uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
+            uint32_t par_ready = 0, par_dw = 0, par_x = 0;
+            const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
+            for (int64_t k = 0; k < my_tiles; ++k) {
+                const int64_t tile = blockIdx.x + k * gridDim.x;
+                const bool full = (tile + 1) * kTileM <= n;
+                int off_dz = cur.alloc(p2.item_bytes[0], R);
+                ++seq;
+                for (int l = L - 1; l >= 0; --l) {
+                    const int K = cfg.k_pad[l], N = cfg.n_pad[l];
+                    const int off_a = cur.alloc(st.a_bytes[l], R);
+                    const uint32_t seq_a = seq++;
+                    int off_next = 0;
+                    if (l >= 1) {
+                        off_next = cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
+                        ++seq;
+                    }
+                    const bool want_dx = (l == 0) && p2.want_dx;
+                    const uint32_t a_addr = ring_addr + (uint32_t)off_a, dz_addr = ring_addr + (uint32_t)off_dz;
+                    mbar_wait(&bar_ready, par_ready);  // dZ_l is complete (and the work columns have been read)
+                    par_ready ^= 1;
+                    tc_fence_after();
+                    if (l >= 1 || want_dx) {  // dA_l = dZ_l W_l: A = dZ_l K-major (K = fan-out), B = W_l read MN-major from the blob
+                        umma_gemm_f16(tmem_base, dz_addr, kChunkBytes, 128, 2 * kChunkBytes, blob_addr + (uint32_t)cfg.w_off[l], 128u,
+                                      (uint32_t)N * 16, 256, umma_idesc_f16(kTileM, K) | kIdescBMn, N / 16, false);
+                        tc_commit(&bar_da);
+                    }
+                    mbar_wait(&bar_item[seq_a & (kItemBars - 1)], (seq_a / kItemBars) & 1u);  // A_l has landed
+                    umma_gemm_f16(tmem_base + (uint32_t)plan.dw_col[l], a_addr, mn_lbo, mn_sbo, 256, dz_addr, mn_lbo, mn_sbo, 256,
+                                  umma_idesc_f16(kTileM, N) | kIdescAMn | kIdescBMn, kTileM / 16, k > 0);
+                    if (!plan.fold_bias[l])
+                        umma_gemm_f16(tmem_base + (uint32_t)plan.db_col[l], dz_addr, mn_lbo, mn_sbo, 256, ones_addr, mn_lbo, mn_sbo, 256,
+                                      umma_idesc_f16(kTileM, 16) | kIdescAMn | kIdescBMn, kTileM / 16, k > 0);
+                    tc_commit(&bar_dw);
+                    // the dW / db GEMMs run under the epilogue; once they are done dZ_l and A_l leave the ring
+                    mbar_wait(&bar_dw, par_dw);
+                    par_dw ^= 1;
+                    release(2);
+                    produce();
+                    if (want_dx) {
+                        const int off_x = cur.alloc(p2.item_bytes[n_items - 1], R);
+                        ++seq;
+                        mbar_wait(&bar_x, par_x);  // every epilogue warp has staged its part of the input gradient
+                        par_x ^= 1;
+                        if (full) {
+                            bulk_s2g(d_pos + tile * kTileM * F, s_ring + off_x, (uint32_t)(kTileM * F * 4));
+                            bulk_commit();
+                            bulk_wait_read_all();
+                        }
+                        release(1);
+                        produce();
+                    }
+                    off_dz = off_next;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const uint32_t tmem_work = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        RingCursor cur{0};
+        uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
+        uint32_t par_da = 0;
+        auto announce = [&](uint64_t* bar) {
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
+        for (int64_t k = 0; k < my_tiles; ++k) {
+            const int64_t tile = blockIdx.x + k * gridDim.x;
+            const int64_t row0 = tile * kTileM;
+            const int rows = (int)min((int64_t)kTileM, n - row0);
+            const bool full = rows == kTileM;
+            const int64_t r = row0 + row;
+            const bool live = row < rows;
 
-        // item 0: dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z))
-        int off_dz = cons.alloc(p2.item_bytes[0], R);
-        wait_item(cons_seq);  // the producer has reserved the space (everything that lived there has been released)
-        ++cons_seq;
-        if (cg == 0) {
+            // item 0: dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z))
+            const int off_last = cur.alloc(p2.item_bytes[0], R);
             float g[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = 0.f;
-            if (live) {
+            if (cg == 0 && live) {
                 float decay = 1.f;
                 if (cfg.alpha_decay) {
                     const float dx = __ldg(dirs + 3 * r), dy = __ldg(dirs + 3 * r + 1), dz = __ldg(dirs + 3 * r + 2);
@@ -720,131 +788,103 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_stashed_kernel(const MlpC
                 for (int j = 0; j < 8; ++j)
                     if (j < cfg.out_dim) {
                         const float o = __ldg(fwd_out + r * cfg.out_dim + j);
-                        const float ds = decay != 0.f ? o * (1.f - o / decay) : 0.f;
+                        const float ds = decay != 0.f ? o * (1.f - __fdividef(o, decay)) : 0.f;
                         g[j] = __ldg(d_out + r * cfg.out_dim + j) * ds * scale;
                     }
             }
-            __half2 h[4];
+            mbar_wait(item_bar(seq), item_parity(seq));  // the ring space is reserved (its previous tenants have been released)
+            ++seq;
+            if (cg == 0) {
+                __half2 h[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(s_ring + off_dz + (size_t)row * 16);
-            dst[0] = *reinterpret_cast<const uint4*>(h);
-            for (int c = 1; c < cfg.n_pad[L - 1] / 8; ++c) dst[c * kTileM] = make_uint4(0u, 0u, 0u, 0u);
-        }
+                for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(s_ring + off_last + (size_t)row * 16);
+                dst[0] = *reinterpret_cast<const uint4*>(h);
+                for (int c = 1; c < cfg.n_pad[L - 1] / 8; ++c) dst[c * kTileM] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            announce(&bar_ready);
 
-        for (int l = L - 1; l >= 0; --l) {
-            const int K = cfg.k_pad[l], N = cfg.n_pad[l];
-            const int64_t seq_a = cons_seq++;
-            const int off_a = cons.alloc(st.a_bytes[l], R);
-            int off_g = 0;
-            int64_t seq_g = 0;
-            if (l >= 1) {
-                seq_g = cons_seq++;
-                off_g = cons.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
-            }
-            const bool want_dx = (l == 0) && p2.want_dx;
-            const bool has_da = l >= 1 || want_dx;
-            fence_proxy_async();  // dZ_l was written with ordinary stores
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                wait_item(seq_a);  // A_l has landed (TMA writes are visible to the tensor core once the mbarrier completes)
-                const uint32_t a_addr = smem_u32(s_ring + off_a), dz_addr = smem_u32(s_ring + off_dz);
-                if (has_da) {  // dA_l = dZ_l W_l: A = dZ_l K-major (K = fan-out), B = W_l read MN-major from the forward blob
-                    issue_gemm(tmem_base, dz_addr, kChunkBytes, 128, 2 * kChunkBytes, smem_u32(s_blob + cfg.w_off[l]), 128u, (uint32_t)N * 16,
-                               256, umma_idesc_f16(kTileM, K) | kIdescBMn, N / 16, false);
-                    tc_commit(&bar_da);
-                }
-                issue_gemm(tmem_base + (uint32_t)plan.dw_col[l], a_addr, mn_lbo, mn_sbo, 256, dz_addr, mn_lbo, mn_sbo, 256,
-                           umma_idesc_f16(kTileM, N) | kIdescAMn | kIdescBMn, kTileM / 16, !first_tile);
-                if (!plan.fold_bias[l])
-                    issue_gemm(tmem_base + (uint32_t)plan.db_col[l], dz_addr, mn_lbo, mn_sbo, 256, smem_u32(s_ones), mn_lbo, mn_sbo, 256,
-                               umma_idesc_f16(kTileM, 16) | kIdescAMn | kIdescBMn, kTileM / 16, !first_tile);
-                tc_commit(&bar_dw);
-            }
-            int off_x = 0;
-            if (l >= 1) {
-                wait_item(seq_g);
-                mbar_wait(&bar_da, par_da);
-                par_da ^= 1;
-                tc_fence_after();
-                // dZ_{l-1} = dA_l * G_{l-1}, in place
+            for (int l = L - 1; l >= 0; --l) {
+                const int K = cfg.k_pad[l];
+                cur.alloc(st.a_bytes[l], R);  // A_l: consumed by the tensor core only
+                ++seq;
+                if (l >= 1) {
+                    // this thread's elements of G_{l-1}: global -> registers, in flight while dA_l is being computed
+                    const uint8_t* gsrc = stash + tile * (int64_t)st.tile_bytes + st.g_off[l - 1];
+                    uint4 gq[2][2];
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int c0 = cg * 16 + 64 * it;
-                    if (c0 < K) {
-                        float v[16];
-                        tmem_ld16(tmem_work + (uint32_t)c0, v);
-                        uint4* slot = reinterpret_cast<uint4*>(s_ring + off_g + ((size_t)(c0 / 8) * kTileM + row) * 16);
-                        uint4 g_lo = slot[0], g_hi = slot[kTileM];
-                        const __half2* gl = reinterpret_cast<const __half2*>(&g_lo);
-                        const __half2* gh = reinterpret_cast<const __half2*>(&g_hi);
-                        __half2 h[8];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 a = __half22float2(gl[q]), b = __half22float2(gh[q]);
-                            h[q] = __floats2half2_rn(v[2 * q] * a.x, v[2 * q + 1] * a.y);
-                            h[4 + q] = __floats2half2_rn(v[8 + 2 * q] * b.x, v[8 + 2 * q + 1] * b.y);
+                    for (int it = 0; it < 2; ++it) {
+                        const int c0 = cg * 16 + 64 * it;
+                        if (c0 < K) {
+                            const uint4* src = reinterpret_cast<const uint4*>(gsrc + ((size_t)(c0 / 8) * kTileM + row) * 16);
+                            gq[it][0] = __ldcs(src);
+                            gq[it][1] = __ldcs(src + kTileM);
                         }
-                        slot[0] = *reinterpret_cast<const uint4*>(&h[0]);
-                        slot[kTileM] = *reinterpret_cast<const uint4*>(&h[4]);
                     }
-                }
-            } else if (want_dx) {
-                off_x = cons.alloc(p2.item_bytes[p2.n_items - 1], R);
-                wait_item(cons_seq);
-                ++cons_seq;
-                float* xs = reinterpret_cast<float*>(s_ring + off_x);
-                mbar_wait(&bar_da, par_da);
-                par_da ^= 1;
-                tc_fence_after();
+                    const int off_next = cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
+                    mbar_wait(item_bar(seq), item_parity(seq));
+                    ++seq;
+                    mbar_wait(&bar_da, par_da);
+                    par_da ^= 1;
+                    tc_fence_after();
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int c0 = cg * 16 + 64 * it;
-                    if (c0 < F) {
-                        float v[16];
-                        tmem_ld16(tmem_work + (uint32_t)c0, v);
+                    for (int it = 0; it < 2; ++it) {
+                        const int c0 = cg * 16 + 64 * it;
+                        if (c0 < K) {
+                            float v[16];
+                            tmem_ld16(tmem_work + (uint32_t)c0, v);
+                            const __half2* gl = reinterpret_cast<const __half2*>(&gq[it][0]);
+                            const __half2* gh = reinterpret_cast<const __half2*>(&gq[it][1]);
+                            __half2 h[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < F) xs[row * F + c0 + j] = v[j] * inv_scale;
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 a = __half22float2(gl[q]), b = __half22float2(gh[q]);
+                                h[q] = __floats2half2_rn(v[2 * q] * a.x, v[2 * q + 1] * a.y);
+                                h[4 + q] = __floats2half2_rn(v[8 + 2 * q] * b.x, v[8 + 2 * q + 1] * b.y);
+                            }
+                            uint4* slot = reinterpret_cast<uint4*>(s_ring + off_next + ((size_t)(c0 / 8) * kTileM + row) * 16);
+                            slot[0] = *reinterpret_cast<const uint4*>(&h[0]);
+                            slot[kTileM] = *reinterpret_cast<const uint4*>(&h[4]);
+                        }
                     }
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                if (full) {
-                    if (tid == 0) {
-                        bulk_s2g(d_pos + row0 * F, xs, (uint32_t)(kTileM * F * 4));
-                        bulk_commit();
-                        store_pending = true;
+                    announce(&bar_ready);
+                } else if (p2.want_dx) {
+                    const int off_x = cur.alloc(p2.item_bytes[p2.n_items - 1], R);
+                    mbar_wait(item_bar(seq), item_parity(seq));
+                    ++seq;
+                    float* xs = reinterpret_cast<float*>(s_ring + off_x);
+                    mbar_wait(&bar_da, par_da);
+                    par_da ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const int c0 = cg * 16 + 64 * it;
+                        if (c0 < F) {
+                            float v[16];
+                            tmem_ld16(tmem_work + (uint32_t)c0, v);
+                            if (full) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < F) xs[row * F + c0 + j] = v[j] * inv_scale;
+                            } else if (live) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < F) d_pos[r * F + c0 + j] = v[j] * inv_scale;
+                            }
+                        }
                     }
-                } else {
-                    for (int e = tid; e < rows * F; e += kMlpThreads) d_pos[row0 * F + e] = xs[e];
+                    announce(&bar_x);
                 }
             }
-            if (tid == 0) {
-                // the layer's dW / db GEMMs ran under the epilogue; once they are done dZ_l and A_l leave the ring
-                mbar_wait(&bar_dw, par_dw);
-                par_dw ^= 1;
-                release(2);
-                if (l == 0 && p2.want_dx) {  // (a partial tile is the CTA's last one: nothing is fetched over its staging area)
-                    bulk_wait_read_all();
-                    store_pending = false;
-                    release(1);
-                }
-                produce();
-            }
-            off_dz = off_g;
         }
-        first_tile = false;
     }
 
     // ---- this CTA's parameter-gradient accumulators -> its slice of the workspace ---------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (my_tiles > 0) {
+    if (my_tiles > 0 && warp < kMlpThreads / 32) {
         tc_fence_after();
+        const uint32_t tmem_work = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         float* mine = partials + (size_t)blockIdx.x * plan.n_params;
         for (int l = 0; l < L; ++l) {
             const int N = cfg.n_pad[l], Kt = plan.dims[l], Nt = plan.dims[l + 1];
@@ -867,7 +907,6 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_stashed_kernel(const MlpC
                 if (row < Nt) mine[plan.p_off_b[l] + row] = v[0];
             }
         }
-        if (tid == 0 && store_pending) bulk_wait_read_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -994,7 +1033,7 @@ int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, con
         mlp_absmax_kernel<<<296, 256, 0, s>>>(d_out, n_samples, c.out_dim, n_valid_dev, absmax);
         ce = cudaFuncSetAttribute(mlp_bwd_stashed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2.smem_bytes);
         if (ce != cudaSuccess) return (int)ce;
-        mlp_bwd_stashed_kernel<<<grid, kMlpThreads, p2.smem_bytes, s>>>(c, p, p2, st, reinterpret_cast<const uint8_t*>(blob),
+        mlp_bwd_stashed_kernel<<<grid, kBwdThreads, p2.smem_bytes, s>>>(c, p, p2, st, reinterpret_cast<const uint8_t*>(blob),
                                                                         reinterpret_cast<const uint8_t*>(stash), dirs, normals, fwd_out, d_out,
                                                                         absmax, d_pos, partials, n_samples, n_valid_dev);
         launches += 2;

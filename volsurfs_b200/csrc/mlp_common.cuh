@@ -139,11 +139,36 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     d |= (uint64_t)1 << 46;  // descriptor version of sm_100
     return d;                // layout_type (bits 61-63) = 0: no swizzle
 }
+// The same descriptor split into 32-bit halves: a GEMM's K-steps only advance the address field of the low word
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+// D[tmem] (+)= A * B over nk K-steps of 16 (one elected thread); the operand descriptors advance by a_step / b_step BYTES per K-step
+__device__ __forceinline__ void umma_gemm_f16(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t b_addr,
+                                              uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, uint32_t idesc, int nk, bool accumulate);
 __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4)                      // D format: f32
            | (0u << 7) | (0u << 10)       // A, B format: f16
            | (0u << 15) | (0u << 16)      // A, B K-major
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_gemm_f16(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t b_addr,
+                                              uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, uint32_t idesc, int nk, bool accumulate) {
+    uint32_t a_lo = umma_desc_lo(a_addr, a_lbo), b_lo = umma_desc_lo(b_addr, b_lbo);
+    const uint32_t a_hi = umma_desc_hi(a_sbo), b_hi = umma_desc_hi(b_sbo);
+    const uint32_t a_inc = a_step >> 4, b_inc = b_step >> 4;
+    uint32_t acc = accumulate ? 1u : 0u;
+    for (int ks = 0; ks < nk; ++ks) {
+        tc_mma_f16(tmem_d, umma_desc_join(a_lo, a_hi), umma_desc_join(b_lo, b_hi), idesc, acc);
+        a_lo += a_inc;  // operand buffers never cross the 256 KB window of the 14-bit address field
+        b_lo += b_inc;
+        acc = 1u;
+    }
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -205,15 +230,20 @@ __device__ __forceinline__ void gelu_pair(float x0, float x1, float& a0, float& 
     p = f2_mul(p, p);
     float p0, p1;
     f2_unpack(p, p0, p1);
-    const float e0 = copysignf(1.f - __fdividef(1.f, p0), x0), e1 = copysignf(1.f - __fdividef(1.f, p1), x1);  // erf(x/sqrt2)
+    // erf(x/sqrt2) = sign(x) (1 - p^-16): 1 - r >= 0, so the sign is one bit operation
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+    const float e0 = __uint_as_float(__float_as_uint(1.f - r0) | (__float_as_uint(x0) & 0x80000000u));
+    const float e1 = __uint_as_float(__float_as_uint(1.f - r1) | (__float_as_uint(x1) & 0x80000000u));
     const uint64_t e = f2_pack(e0, e1);
     const uint64_t h = f2_mul(x, f2_splat(0.5f));
     f2_unpack(f2_fma(h, e, h), a0, a1);
     if (GRAD) {
         const uint64_t Phi = f2_fma(e, f2_splat(0.5f), f2_splat(0.5f));
         float t0, t1;
-        f2_unpack(f2_mul(x, x), t0, t1);
-        const uint64_t ex = f2_pack(ex2_approx(t0 * -0.72134752044f), ex2_approx(t1 * -0.72134752044f));  // exp(-x^2/2)
+        f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.72134752044f)), t0, t1);
+        const uint64_t ex = f2_pack(ex2_approx(t0), ex2_approx(t1));  // exp(-x^2/2)
         f2_unpack(f2_fma(f2_mul(x, ex), f2_splat(0.3989422804f), Phi), g0, g1);
     }
 }
