@@ -245,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
     ev = None
 
     @torch.no_grad()  # forward and backward kernels are driven explicitly; no autograd graph in the timed region
-    def step(record=None):
+    def step(record=None, reduce=True):
         def mark(i):
             if record is not None:
                 record[i].record()
@@ -277,13 +277,16 @@ def run_ours(args, rank, world, local_rank):
         mark(7)
         renderer.rgb_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_rgb, grad_rgb, dfeat_rgb, False, rsp.total_dev,
                                         stash=stash_rgb, fwd_out=rgb)
-        reducer.launch([grad_rgb])       # overlaps the alpha head's backward
+        if reduce:
+            reducer.launch([grad_rgb])   # overlaps the alpha head's backward
         mark(8)
         renderer.alpha_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_alpha, grad_alpha, dfeat_alpha, False, rsp.total_dev,
                                           stash=stash_alpha, fwd_out=alpha)
-        reducer.launch([grad_alpha])
+        if reduce:
+            reducer.launch([grad_alpha])
         mark(9)
-        reducer.wait()
+        if reduce:
+            reducer.wait()
         mark(10)
         return out, loss, rsp
 
@@ -299,6 +302,52 @@ def run_ours(args, rank, world, local_rank):
     n_hits = int(rsp.total_dev.item())
     assert not renderer.tracer.overflowed()
 
+    # ---- the step as ONE CUDA graph: ~45 launches of 3-700 us each leave the device waiting for the Python host otherwise
+    # (measured: 3.02 ms per eager step against 2.6 ms of kernel time).  Stage boundaries are external event-record nodes inside
+    # the graph.  With N > 1 the gradient all-reduce (NCCL) follows the graph on the same stream.
+    use_graph = not args.no_graph
+    graph = graph_e2e = None
+    ext = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(n_marks)]
+    kernels_per_step = None
+    if use_graph:
+        try:
+            c0 = lib.vs_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_out, g_loss, g_rsp = step(ext, reduce=False)
+            kernels_per_step = lib.vs_launch_count() - c0
+            graph_e2e = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_e2e):
+                rays_o.copy_(o_pin, non_blocking=True)
+                rays_d.copy_(d_pin, non_blocking=True)
+                e_out, e_loss, _ = step(None, reduce=False)
+                img_pin.copy_(e_out["rgb"], non_blocking=True)
+                loss_pin.copy_(e_loss, non_blocking=True)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed ({exc!r}); running eagerly", file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+            use_graph, graph, graph_e2e = False, None, None
+
+    def all_reduce_grads():
+        if world > 1:
+            reducer.launch([grad_rgb, grad_alpha])
+            reducer.wait()
+
+    def run_step(record=None):
+        if use_graph:
+            graph.replay()
+            all_reduce_grads()
+        else:
+            step(record)
+
+    for _ in range(3):
+        run_step()
+    torch.cuda.synchronize()
+    if use_graph:
+        n_hits_graph = int(g_rsp.total_dev.item())
+        assert n_hits_graph == n_hits, (n_hits_graph, n_hits)
+        assert torch.allclose(g_out["rgb"], out["rgb"]), "graph replay differs from the eager step"
+
     # ---- timed region: device-resident inputs
     records = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
@@ -308,16 +357,36 @@ def run_ours(args, rank, world, local_rank):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for s in range(args.steps):
-        step(records[s])
+        run_step(records[s])
     t_end.record()
     barrier()
     clocks = sampler.stop()
-    launches = lib.vs_launch_count() - launches0
+    launches = (kernels_per_step * args.steps) if use_graph else (lib.vs_launch_count() - launches0)
     ms_total = t_start.elapsed_time(t_end)
-    stage_ms = [statistics.mean(records[s][i].elapsed_time(records[s][i + 1]) for s in range(args.steps)) for i in range(n_marks - 1)]
+    if use_graph:
+        # stage times: the graph's own event nodes, read after single replays (the nodes are part of every timed replay too)
+        per = []
+        for _ in range(10):
+            graph.replay()
+            torch.cuda.synchronize()
+            per.append([ext[i].elapsed_time(ext[i + 1]) for i in range(n_marks - 1)])
+        stage_ms = [statistics.mean(p[i] for p in per) for i in range(n_marks - 1)]
+        if world > 1:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            all_reduce_grads()
+            a1.record()
+            torch.cuda.synchronize()
+            stage_ms[-1] = a0.elapsed_time(a1)
+    else:
+        stage_ms = [statistics.mean(records[s][i].elapsed_time(records[s][i + 1]) for s in range(args.steps)) for i in range(n_marks - 1)]
 
     # ---- e2e: pinned host rays in, image + loss out, every step
     def e2e_step():
+        if use_graph:
+            graph_e2e.replay()
+            all_reduce_grads()
+            return
         rays_o.copy_(o_pin, non_blocking=True)
         rays_d.copy_(d_pin, non_blocking=True)
         out, loss, _ = step()
@@ -334,6 +403,9 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    if use_graph:
+        torch.cuda.synchronize()
+        assert torch.allclose(img_pin, out["rgb"].cpu()), "e2e graph: image read back differs from the eager step"
 
     # ---- max over ranks
     if world > 1:
@@ -376,10 +448,32 @@ def run_ours(args, rank, world, local_rank):
             ach, peak, unit = alg / (ms * 1e-3) / 1e12, pk["tflops_sustained"], "TFLOP/s"
         stages[name] = {"ms": round(ms, 4), "share": round(ms / sum(stage_ms), 3), "bound": bound, "achieved": round(ach, 2), "peak": peak,
                         "unit": unit, "frac": round(ach / peak, 4)}
-    dominant = max(stages, key=lambda k: stages[k]["ms"])
-    roofline = {k: stages[dominant][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-    roofline.update(kernel=dominant, traffic=None, peak_source=pk["source"],
-                    note="algorithmic bytes/flops per launch over the kernel's mean CUDA-event duration inside the timed region")
+    # the dominant KERNEL of the step: stages that launch the same kernel are summed (both heads run mlp_fwd_kernel / mlp_bwd_stashed_kernel)
+    kernel_of = {"trace": "shells_trace_kernel", "mlp_rgb": "mlp_fwd_kernel", "mlp_alpha": "mlp_fwd_kernel",
+                 "mlp_bwd_rgb": "mlp_bwd_stashed_kernel", "mlp_bwd_alpha": "mlp_bwd_stashed_kernel"}
+    per_kernel = {}
+    for name, kern in kernel_of.items():
+        per_kernel.setdefault(kern, []).append(name)
+    dom_kernel = max(per_kernel, key=lambda k: sum(stages[n]["ms"] for n in per_kernel[k]))
+    dom_stages = per_kernel[dom_kernel]
+    dominant = dom_stages[0]
+    dom_ms = statistics.mean(stages[n]["ms"] for n in dom_stages)               # average launch duration
+    dom_alg = statistics.mean(stage_alg[n][1] for n in dom_stages)              # algorithmic flops / bytes of one launch
+    dom_bound = stage_alg[dominant][0]
+    if dom_kernel == "shells_trace_kernel":
+        dom_bound = "hbm"  # BVH traversal is latency / L2 bound; against the HBM roofline its compulsory bytes are a lower bound only
+    dom_peak, dom_unit, dom_div = (pk["hbm_gbs"], "GB/s", 1e9) if dom_bound == "hbm" else (pk["tflops_sustained"], "TFLOP/s", 1e12)
+    dom_ach = dom_alg / (dom_ms * 1e-3) / dom_div
+    roofline = {"bound": dom_bound, "achieved": round(dom_ach, 2), "peak": dom_peak, "unit": dom_unit, "frac": round(dom_ach / dom_peak, 4),
+                "launches_per_step": len(dom_stages), "ms_per_launch": round(dom_ms, 4),
+                "share_of_step": round(sum(stages[n]["ms"] for n in dom_stages) / sum(stage_ms), 3)}
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the stage's kernel from the ncu --set full captures of
+    # this same workload (profiles/r01_mlp_fwd_v4.md, r01_mlp_bwd_v3.md, r01_shells_trace_v2.md); None where no capture exists
+    ncu_traffic = {"mlp_rgb": 212.285952e6 + 1.274396e9, "mlp_alpha": 212.285952e6 + 1.274396e9, "mlp_bwd_rgb": 1.335758e9 + 188.86016e6,
+                   "mlp_bwd_alpha": 1.335758e9 + 188.86016e6, "trace": 45.03552e6 + 22.207488e6}
+    roofline.update(kernel=dom_kernel, traffic=ncu_traffic.get(dominant), peak_source=pk["source"],
+                    note="algorithmic flops (or bytes) of one launch over the stage's mean CUDA-event duration inside the timed region "
+                         "(event-record nodes of the replayed graph); traffic = DRAM bytes of one launch from the ncu capture in profiles/")
 
     # ---- the headline compositing kernels at the size SURVEY 8d prescribes (2^24 rays x 5, traffic >> L2)
     comp = None
@@ -435,6 +529,8 @@ def run_ours(args, rank, world, local_rank):
                 "note": "pinned host rays -> device every step, composited image + loss -> pinned host every step; the positional "
                         "features are produced on the device by the encoder stage and stay device-resident"},
         "gpu_launches": int(launches),
+        "launch_mode": ("one CUDA graph per step (%d kernels of this library per step + torch elementwise ops)" % kernels_per_step) if use_graph
+                       else "eager (one Python call per kernel)",
         "roofline": roofline,
         "stages": stages,
         "compositing_roofline": comp,
@@ -449,6 +545,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-composite-roofline", action="store_true")
     args = ap.parse_args()

@@ -20,6 +20,8 @@
 //   4. the input gradient (first pos_dim columns of dA_0, un-scaled) leaves through shared memory as one TMA bulk store per tile.
 // After its last tile a CTA writes its dW/db accumulators to a per-CTA slice of the workspace; mlp_bwd_reduce_kernel sums the slices
 // in a fixed order (deterministic), removes the loss scale and writes / accumulates the fp32 parameter gradients.
+#include <cstdlib>
+
 #include "mlp_common.cuh"
 
 namespace vs {
@@ -544,6 +546,7 @@ struct MlpBwd2Plan {
     int ring_bytes;
     int want_dx;
     int smem_bytes;
+    int prefetch_tiles;                 // whole stash tiles the control thread pulls into L2 ahead of the ring (0: off)
 };
 
 constexpr int kItemBars = 16;
@@ -584,6 +587,7 @@ static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_
     if (ring < top3[0] + top3[1] + top3[2] + top3[0]) return VS_ERR_UNSUPPORTED;
     p->ring_bytes = ring;
     p->smem_bytes = ring + tail + 128;
+    p->prefetch_tiles = 2;
     return VS_OK;
 }
 
@@ -698,9 +702,17 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
             uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
             uint32_t par_ready = 0, par_dw = 0, par_x = 0;
             const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
+            const int pf_depth = p2.prefetch_tiles;
+            for (int64_t j = 0; j < pf_depth && j < my_tiles; ++j)
+                bulk_prefetch_l2(stash + (blockIdx.x + j * gridDim.x) * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
             for (int64_t k = 0; k < my_tiles; ++k) {
                 const int64_t tile = blockIdx.x + k * gridDim.x;
                 const bool full = (tile + 1) * kTileM <= n;
+                // the ring holds less than one tile: the DRAM latency of the saved operands (TMA items) and of the activation
+                // derivatives (read by the epilogue warps) is taken off the critical path by pulling whole tile images into L2
+                // `pf_depth` tiles ahead
+                if (pf_depth > 0 && k + pf_depth < my_tiles)
+                    bulk_prefetch_l2(stash + (tile + pf_depth * gridDim.x) * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
                 int off_dz = cur.alloc(p2.item_bytes[0], R);
                 ++seq;
                 for (int l = L - 1; l >= 0; --l) {
@@ -1022,6 +1034,7 @@ int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, con
     e = mlp_bwd2_plan(c, st, pos_dim, d_pos != nullptr && pos_dim > 0, &p2);
     if (e != VS_OK) return e;
     if (p2.smem_bytes > 227 * 1024) return VS_ERR_UNSUPPORTED;
+    if (const char* env = std::getenv("VS_MLP_BWD_PREFETCH")) p2.prefetch_tiles = std::max(0, std::atoi(env));  // A/B knob
     cudaStream_t s = (cudaStream_t)stream;
     float* absmax = reinterpret_cast<float*>(workspace);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);

@@ -115,6 +115,36 @@ class ShellRenderer:
         return out
 
 
+class GraphedTrainingStep:
+    """``ShellRenderer.render_fwd_bwd`` captured once into a CUDA graph and replayed with one launch per step.
+
+    The path has no host synchronisation (capacity-sized packed arrays, sample count on the device), so the ~45 kernels of a step
+    can be replayed back to back; launched one by one from Python the device waits for the host between the short ones.  The
+    tensors passed here are the graph's static inputs: copy new rays / features / targets INTO them before ``replay()``.  Results
+    (``out`` of render_fwd_bwd, including the heads' flat gradient buffers) live in graph-owned memory and are overwritten by the
+    next replay."""
+
+    def __init__(self, renderer: "ShellRenderer", rays_o, rays_d, pos_features, gt_rgb, warmup: int = 2):
+        self.renderer = renderer
+        self.inputs = (rays_o, rays_d, pos_features, gt_rgb)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # allocates the renderer's cached buffers (stashes, workspaces, packed weights) outside the graph
+            for _ in range(max(warmup, 1)):
+                renderer.render_fwd_bwd(*self.inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        assert not renderer.tracer.overflowed()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = renderer.render_fwd_bwd(*self.inputs)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    __call__ = replay
+
+
 def make_synthetic_renderer(K=5, n_lat=224, n_lon=224, hidden=(128, 128, 64), pos_dim=51, seed=0, offset=0.01, device=None):
     """C2/C5-shaped scene: K nested lumpy shells (~100k triangles each) + fixed-seed legacy heads (rgb: 3 outputs, alpha: 1 output
     with alpha decay, both normal-independent, GELU)"""
