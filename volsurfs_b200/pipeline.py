@@ -145,6 +145,74 @@ class GraphedTrainingStep:
     __call__ = replay
 
 
+class PipelinedTrainingStep:
+    """End-to-end training step fed from pinned HOST ray buffers, software-pipelined over the copy engines.
+
+    Two CUDA graphs alternate.  Graph p runs ``render_fwd_bwd`` on device ray buffers p; forked inside the same graph, one side
+    stream copies the NEXT step's rays (pinned host -> device buffers 1-p) and another copies the PREVIOUS step's image and loss
+    (device buffers 1-p -> pinned host), so both transfers hide under the ~2.6 ms of compute instead of preceding / following it.
+    Every step still moves one step's inputs in and one step's results out.
+
+        loop = PipelinedTrainingStep(renderer, o_pin, d_pin, feats, gt, img_pin, loss_pin)
+        loop.prime()                      # rays of step 0 -> device
+        for i in range(steps):            # (write the rays of step i+1 into o_pin / d_pin before calling step(i))
+            loop.step(i)                  # results of step i-1 are in img_pin / loss_pin once step(i) has completed
+        loop.drain(steps)                 # results of the last step
+    """
+
+    def __init__(self, renderer: "ShellRenderer", o_pin, d_pin, pos_features, gt_rgb, img_pin, loss_pin, warmup: int = 2):
+        dev = pos_features.device
+        self.renderer = renderer
+        self.o_pin, self.d_pin, self.img_pin, self.loss_pin = o_pin, d_pin, img_pin, loss_pin
+        self.rays_o = [torch.empty(o_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.rays_d = [torch.empty(d_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.img = [torch.empty(img_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.loss = [torch.empty((), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.copy_in, self.copy_out = torch.cuda.Stream(), torch.cuda.Stream()
+        for b in range(2):
+            self.rays_o[b].copy_(o_pin)
+            self.rays_d[b].copy_(d_pin)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                renderer.render_fwd_bwd(self.rays_o[0], self.rays_d[0], pos_features, gt_rgb)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graphs, self.outs = [], []
+        for b in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream()
+                self.copy_in.wait_stream(main)
+                self.copy_out.wait_stream(main)
+                with torch.cuda.stream(self.copy_in):
+                    self.rays_o[1 - b].copy_(o_pin, non_blocking=True)
+                    self.rays_d[1 - b].copy_(d_pin, non_blocking=True)
+                with torch.cuda.stream(self.copy_out):
+                    img_pin.copy_(self.img[1 - b], non_blocking=True)
+                    loss_pin.copy_(self.loss[1 - b], non_blocking=True)
+                out = renderer.render_fwd_bwd(self.rays_o[b], self.rays_d[b], pos_features, gt_rgb)
+                self.img[b].copy_(out["rgb"])
+                self.loss[b].copy_(out["loss"])
+                main.wait_stream(self.copy_in)
+                main.wait_stream(self.copy_out)
+            self.graphs.append(g)
+            self.outs.append(out)
+
+    def prime(self):
+        self.rays_o[0].copy_(self.o_pin, non_blocking=True)
+        self.rays_d[0].copy_(self.d_pin, non_blocking=True)
+
+    def step(self, i: int):
+        self.graphs[i & 1].replay()
+        return self.outs[i & 1]
+
+    def drain(self, n_steps: int):
+        b = (n_steps - 1) & 1
+        self.img_pin.copy_(self.img[b], non_blocking=True)
+        self.loss_pin.copy_(self.loss[b], non_blocking=True)
+
+
 def make_synthetic_renderer(K=5, n_lat=224, n_lon=224, hidden=(128, 128, 64), pos_dim=51, seed=0, offset=0.01, device=None):
     """C2/C5-shaped scene: K nested lumpy shells (~100k triangles each) + fixed-seed legacy heads (rgb: 3 outputs, alpha: 1 output
     with alpha decay, both normal-independent, GELU)"""
