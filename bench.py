@@ -40,6 +40,27 @@ POS_DIM = 51
 CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything libraries print on fd 1 (NCCL's version banner, OpenMP notices) goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -188,7 +209,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -558,7 +579,7 @@ def run_ours(args, rank, world, local_rank):
         "compositing_roofline": comp,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -576,11 +597,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
 
     if world > 1:
+        # NCCL prints its version banner on STDOUT when the box exports NCCL_DEBUG=VERSION; stdout carries the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
 

@@ -221,6 +221,28 @@ int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, con
                             int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
                             float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream);
 
+/* ---- permutohedral-lattice hash encoding ---------------------------------------------------------------------
+ * Replaces permutohedral_encoding's Encoding<POS_DIM,2>::forward / ::backward (submodules/permutohedral_encoding/src/Encoding.cu:55-113,
+ * 116-217; kernels forward_gpu / backward_gpu / backward_gpu_only_pos, kernels/permutohedral_encoding/EncodingGPU.cuh:68-261,264-416,
+ * 534-700), the row permute of PermutoEncoding.forward (src/pytorch_modules/modules.py:85) and — when bb_sides is given — the point
+ * normalisation and out-of-bounds mask of volsurfs_py/encodings/permutohash.py:77-86.
+ *   lattice [n_levels, capacity, 2] f32 · scale, shift [n_levels, pos_dim] f32 · window [n_levels] f32: DEVICE pointers
+ *   bb_sides: HOST pointer to pos_dim floats (points are mapped from [-bb/2, bb/2] onto [0,1]) or NULL (positions used as they are)
+ *   out [n, out_stride] f32: the first out_cols of the 2*(n_levels + extra) encoded columns of every row, column = level*2 + feature
+ *     (out_cols = output_dims - 1 is the reference's remove_last_element); out_of_bounds [n] u8 or NULL
+ *   n_valid_dev: device int64 — only rows < min(n, *n_valid_dev) are processed — or NULL.
+ * pos_dim 2..4, 2 features per level, n_levels <= 32. */
+int vs_permuto_output_dims(int pos_dim, int n_levels, int concat_points);
+int vs_permuto_forward(int pos_dim, int n_levels, int64_t capacity, int concat_points, float points_scaling, const float* bb_sides,
+                       const float* positions, const float* lattice, const float* scale, const float* shift, const float* window, float* out,
+                       int out_cols, int64_t out_stride, uint8_t* out_of_bounds, int64_t n, const int64_t* n_valid_dev, void* stream);
+/* d_out [n, in_stride]: upstream gradient of the first in_cols encoded columns.  d_lattice [n_levels, capacity, 2] is ADDED to (zero it
+ * for a fresh gradient; the reference returns zeros + atomics permuted to this layout) or NULL; d_positions [n, pos_dim] is overwritten,
+ * or NULL.  As in the reference the concat-points columns pass no gradient to the positions. */
+int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
+                        const float* lattice, const float* scale, const float* shift, const float* window, const float* d_out, int in_cols,
+                        int64_t in_stride, float* d_lattice, float* d_positions, int64_t n, const int64_t* n_valid_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,40 @@ def build_ref(force: bool = False):
     return REF_LIB
 
 
+# ---- oracle/_ref: the reference's permutohedral-encoding kernels behind a C harness -----------------------------------------
+PERMUTO_SRC = HERE / "ref_permuto_harness.cu"
+PERMUTO_LIB = REF_DIR / "libpermuto_ref.so"
+PERMUTO_HDR = REFERENCE / "submodules/permutohedral_encoding/kernels/permutohedral_encoding/EncodingGPU.cuh"
+
+
+def permuto_ref_available() -> bool:
+    return PERMUTO_LIB.exists()
+
+
+def build_ref_permuto(force: bool = False):
+    """nvcc-compile oracle/ref_permuto_harness.cu, which #includes the reference's EncodingGPU.cuh from where it lies under
+    /root/reference/submodules/permutohedral_encoding (nothing is copied), for sm_100a into oracle/_ref/libpermuto_ref.so.
+    Default nvcc floating-point flags (FMA contraction on), as in the reference's own build (setup.py passes only -O3-style flags).
+    Returns None when the reference tree is not mounted (GPU box): the prebuilt .so is used as is."""
+    if not PERMUTO_HDR.exists():
+        return PERMUTO_LIB if PERMUTO_LIB.exists() else None
+    deps = [PERMUTO_SRC, PERMUTO_HDR]
+    if PERMUTO_LIB.exists() and not force and all(PERMUTO_LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return PERMUTO_LIB
+    from torch.utils.cpp_extension import include_paths
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    REF_DIR.mkdir(exist_ok=True)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+           "-shared", "-w", f"-I{PERMUTO_HDR.parent.parent}", *[f"-I{p}" for p in include_paths()], "-D_GLIBCXX_USE_CXX11_ABI=1",
+           str(PERMUTO_SRC), "-o", str(PERMUTO_LIB), "-lcudart"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on the permutohedral reference harness:\n{res.stdout[-4000:]}")
+    return PERMUTO_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_ref())
+    print(build_ref_permuto())

@@ -59,6 +59,9 @@ SIGNATURES = {
     "vs_mlp_num_params": (_I64, [c_int, _P]),
     "vs_mlp_backward_workspace_bytes": (_I64, [c_int, _P, c_int, c_int, c_int, _I64]),
     "vs_mlp_backward_stashed": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, _P]),
+    "vs_permuto_output_dims": (c_int, [c_int, c_int, c_int]),
+    "vs_permuto_forward": (c_int, [c_int, c_int, _I64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _I64, _P, _P]),
+    "vs_permuto_backward": (c_int, [c_int, c_int, _I64, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _P, _I64, _P, _P]),
     "vs_mlp_backward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, c_int, _P]),
 }
 

@@ -1,0 +1,414 @@
+// Permutohedral-lattice hash encoding, forward and backward.
+//
+// Replaces (reference, relative to /root/reference/submodules/permutohedral_encoding/):
+//   forward_gpu              kernels/permutohedral_encoding/EncodingGPU.cuh:68-261   (host src/Encoding.cu:55-113)
+//   backward_gpu             kernels/permutohedral_encoding/EncodingGPU.cuh:264-416  (host src/Encoding.cu:116-217)
+//   backward_gpu_only_pos    kernels/permutohedral_encoding/EncodingGPU.cuh:534-700
+// and the point normalisation + out-of-bounds mask of volsurfs_py/encodings/permutohash.py:77-86.
+//
+// Layout / mapping (B200): the reference launches one thread per (position, level) with the level in blockIdx.y and writes a
+// level-major [levels, 2, N] tensor that Python then permutes into rows.  Here a CTA owns a tile of 128 consecutive positions for ALL
+// levels: 256 threads = 128 positions x 2 level-halves, a warp = 32 consecutive positions of one level (same 2 MB table, coherent
+// simplices on the coarse levels -> broadcast loads / aggregated atomics).  The tile is staged in shared memory (column-major, padded)
+// and leaves as complete rows [N, out_cols] — exactly the operand layout of the appearance MLP (vs_mlp_forward `pos`), so no permute,
+// slice or concat kernel runs in between.  The lattice tables (levels x 2 MB) live in the 126 MB L2: the kernel is bound by L2
+// gathers (4 x 8 B per position and level), not by HBM.
+//
+// Arithmetic follows the reference expression by expression (same association, nvcc contracts the same a*b+c pairs), so the
+// forward output agrees bit for bit with the reference kernels wherever the discrete simplex choice agrees.  The lattice
+// gradient is accumulated with fp32 atomics (as in the reference: order, hence last-ulp rounding, is unspecified).
+#include "volsurfs_b200.h"
+#include "vs_common.cuh"
+
+namespace vs {
+
+constexpr int PM_TILE = 128;       // positions per CTA
+constexpr int PM_THREADS = 256;    // 2 level-halves
+constexpr int PM_PAD = PM_TILE + 1;
+constexpr int PM_MAX_COLS = 72;    // 2 * (levels + extra) <= 72  (levels <= 32)
+
+struct PermutoArgs {
+    int n_levels, n_extra, concat_points, pow2;
+    uint32_t capacity;
+    float points_scaling;
+    int has_bb;
+    float bb_half[8], bb_inv_half[8];   // permutohash.py:77-86
+};
+
+template <int D>
+struct Simplex {
+    int rem0[D + 1];
+    int rank[D + 1];
+    float bary[D + 1];   // weight of the vertex with remainder r
+};
+
+// EncodingGPU.cuh:128-205 (same in the three reference kernels)
+template <int D>
+__device__ __forceinline__ void locate(const float (&pos)[D], const float* __restrict__ shift, const float* __restrict__ scale, Simplex<D>& s) {
+    float elevated[D + 1];
+    float sm = 0;
+#pragma unroll
+    for (int i = D; i > 0; i--) {
+        float cf = (pos[i - 1] + __ldg(shift + i - 1)) * __ldg(scale + i - 1);
+        elevated[i] = sm - i * cf;
+        sm += cf;
+    }
+    elevated[0] = sm;
+
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        float v = elevated[i] * (1.0f / (D + 1));
+        float up = ceilf(v) * (D + 1);
+        float down = floorf(v) * (D + 1);
+        s.rem0[i] = (up - elevated[i] < elevated[i] - down) ? (int)up : (int)down;
+        sum += s.rem0[i];
+        s.rank[i] = 0;
+    }
+    sum /= D + 1;
+
+    float diff[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; i++) diff[i] = elevated[i] - s.rem0[i];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+        for (int j = i + 1; j <= D; j++) {
+            if (diff[i] < diff[j])
+                s.rank[i]++;
+            else
+                s.rank[j]++;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        s.rank[i] += sum;
+        if (s.rank[i] < 0) {
+            s.rank[i] += D + 1;
+            s.rem0[i] += D + 1;
+        } else if (s.rank[i] > D) {
+            s.rank[i] -= D + 1;
+            s.rem0[i] -= D + 1;
+        }
+    }
+    // barycentric weights.  The reference scatters +delta_i into slot D-rank_i and -delta_i into slot D+1-rank_i of a zeroed array;
+    // rank is a permutation, so slot t holds delta[rank == D-t] - delta[rank == D+1-t], one rounding whichever term came first.
+    float by_rank[D + 1];
+#pragma unroll
+    for (int k = 0; k <= D; k++) by_rank[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        float delta = (elevated[i] - s.rem0[i]) * (1.0f / (D + 1));
+#pragma unroll
+        for (int k = 0; k <= D; k++)
+            if (s.rank[i] == k) by_rank[k] = delta;
+    }
+#pragma unroll
+    for (int t = 1; t <= D; t++) s.bary[t] = by_rank[D - t] - by_rank[D + 1 - t];
+    s.bary[0] = by_rank[D] + (1.0f + (0.0f - by_rank[0]));
+}
+
+// EncodingGPU.cuh:22-45,216-227: hash slot of the simplex vertex with this remainder
+template <int D>
+__device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, int remainder, uint32_t capacity, int pow2) {
+    uint32_t k = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        int key = s.rem0[i] + remainder;
+        if (s.rank[i] > D - remainder) key -= (D + 1);
+        k += (uint32_t)key;
+        k *= 2531011u;
+    }
+    return pow2 ? (k & (capacity - 1u)) : (k % capacity);
+}
+
+template <int D>
+__device__ __forceinline__ bool load_position(const PermutoArgs& a, const float* __restrict__ positions, int64_t idx, bool valid, float (&pos)[D]) {
+    bool oob = false;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        float p = valid ? __ldg(positions + idx * D + i) : 0.f;
+        if (a.has_bb) {
+            oob = oob || (p <= -a.bb_half[i]) || (p >= a.bb_half[i]);
+            p = __fdiv_rn(__fadd_rn(__fmul_rn(p, a.bb_inv_half[i]), 1.0f), 2.0f);   // torch: (points * scaling + 1) / 2, op by op
+        }
+        pos[i] = p;
+    }
+    return oob;
+}
+
+__device__ __forceinline__ void red_add_f32x2(float2* addr, float x, float y) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(x), "f"(y) : "memory");
+}
+
+// One (x, y) contribution per lane into table[slot].  Lanes of a warp are consecutive positions: on the coarse levels long runs of
+// lanes hit the same vertex, and 32 same-address atomics serialise in L2 — so runs of equal slots are summed with shuffles first and
+// the run's first lane issues one vector reduction.  When most lanes differ (fine levels) the atomics go out directly.
+__device__ __forceinline__ void red_add_runs(float2* table, uint32_t slot, float x, float y, bool valid, int lane) {
+    uint32_t prev = __shfl_up_sync(VS_FULL_MASK, slot, 1);
+    bool head = (lane == 0) || (prev != slot);
+    uint32_t heads = __ballot_sync(VS_FULL_MASK, head);
+    if (__popc(heads) > 20) {
+        if (valid) red_add_f32x2(table + slot, x, y);
+        return;
+    }
+    uint32_t above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+    int end = above ? (__ffs(above) - 1) : 32;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float ox = __shfl_down_sync(VS_FULL_MASK, x, d);
+        float oy = __shfl_down_sync(VS_FULL_MASK, y, d);
+        if (lane + d < end) {
+            x += ox;
+            y += oy;
+        }
+    }
+    if (head && valid) red_add_f32x2(table + slot, x, y);
+}
+
+template <int D>
+__global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, const float* __restrict__ positions,
+                                                                 const float2* __restrict__ lattice, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, const float* __restrict__ window,
+                                                                 float* __restrict__ out, int out_cols, int64_t out_stride,
+                                                                 uint8_t* __restrict__ oob_out, int64_t n, const int64_t* __restrict__ n_valid_dev) {
+    extern __shared__ float tile[];   // [cols][PM_PAD]
+    const int64_t n_eff = n_valid_dev ? min(n, *n_valid_dev) : n;
+    const int64_t base = (int64_t)blockIdx.x * PM_TILE;
+    if (base >= n_eff) return;
+    const int p = threadIdx.x & (PM_TILE - 1), half = threadIdx.x >> 7;
+    const int64_t idx = base + p;
+    const bool valid = idx < n_eff;
+
+    float pos[D];
+    const bool oob = load_position<D>(a, positions, idx, valid, pos);
+    if (oob_out && half == 0 && valid) oob_out[idx] = oob ? 1 : 0;
+
+    for (int lvl = half; lvl < a.n_levels; lvl += 2) {
+        Simplex<D> s;
+        locate<D>(pos, shift + lvl * D, scale + lvl * D, s);
+        const float w_lvl = __ldg(window + lvl);
+        const float2* table = lattice + (size_t)lvl * a.capacity;
+        float2 v[D + 1];
+#pragma unroll
+        for (int r = 0; r <= D; r++) v[r] = __ldg(table + vertex_slot<D>(s, r, a.capacity, a.pow2));
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            float w = s.bary[r] * w_lvl;
+            ax = ax + v[r].x * w;
+            ay = ay + v[r].y * w;
+        }
+        tile[(2 * lvl) * PM_PAD + p] = ax;
+        tile[(2 * lvl + 1) * PM_PAD + p] = ay;
+    }
+    // concat-points levels (EncodingGPU.cuh:104-124): raw (normalised) coordinates, zero padded
+    for (int e = half; e < a.n_extra; e += 2) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            int src = i + e * 2;
+            float val = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; k++)
+                if (k == src) val = pos[k] * a.points_scaling;
+            tile[(2 * (a.n_levels + e) + i) * PM_PAD + p] = val;
+        }
+    }
+    __syncthreads();
+    const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
+    const int total = rows * out_cols;
+    for (int i = threadIdx.x; i < total; i += PM_THREADS) {
+        int r = i / out_cols, c = i - r * out_cols;
+        out[(base + r) * out_stride + c] = tile[c * PM_PAD + r];
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, const float* __restrict__ positions,
+                                                                 const float2* __restrict__ lattice, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, const float* __restrict__ window,
+                                                                 const float* __restrict__ d_out, int in_cols, int64_t in_stride,
+                                                                 float2* __restrict__ d_lattice, float* __restrict__ d_positions, int64_t n,
+                                                                 const int64_t* __restrict__ n_valid_dev) {
+    extern __shared__ float tile[];   // [cols][PM_PAD] upstream gradient, then [D][PM_PAD] position gradient of the upper half
+    const int64_t n_eff = n_valid_dev ? min(n, *n_valid_dev) : n;
+    const int64_t base = (int64_t)blockIdx.x * PM_TILE;
+    if (base >= n_eff) return;
+    const int p = threadIdx.x & (PM_TILE - 1), half = threadIdx.x >> 7, lane = threadIdx.x & 31;
+    const int64_t idx = base + p;
+    const bool valid = idx < n_eff;
+    const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
+    const int n_cols = 2 * a.n_levels;   // the concat-points columns pass no gradient (Encoding.cu:135-139,163)
+
+    for (int i = threadIdx.x; i < PM_TILE * in_cols; i += PM_THREADS) {
+        int r = i / in_cols, c = i - r * in_cols;
+        if (c < n_cols) tile[c * PM_PAD + r] = (r < rows) ? __ldg(d_out + (base + r) * in_stride + c) : 0.f;
+    }
+    float pos[D];
+    load_position<D>(a, positions, idx, valid, pos);
+    __syncthreads();
+
+    float d_pos[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) d_pos[i] = 0.f;
+
+    for (int lvl = half; lvl < a.n_levels; lvl += 2) {
+        // columns beyond in_cols (a caller that dropped trailing columns, e.g. remove_last_element) carry zero gradient
+        const float gx = (2 * lvl < in_cols) ? tile[(2 * lvl) * PM_PAD + p] : 0.f;
+        const float gy = (2 * lvl + 1 < in_cols) ? tile[(2 * lvl + 1) * PM_PAD + p] : 0.f;
+        Simplex<D> s;
+        locate<D>(pos, shift + lvl * D, scale + lvl * D, s);
+        const float w_lvl = __ldg(window + lvl);
+        uint32_t slot[D + 1];
+#pragma unroll
+        for (int r = 0; r <= D; r++) slot[r] = vertex_slot<D>(s, r, a.capacity, a.pow2);
+        if (d_lattice) {
+            float2* table = d_lattice + (size_t)lvl * a.capacity;
+#pragma unroll
+            for (int r = 0; r <= D; r++) {
+                float w = s.bary[r] * w_lvl;
+                red_add_runs(table, slot[r], gx * w, gy * w, valid, lane);
+            }
+        }
+        if (d_positions) {   // EncodingGPU.cuh:630-690
+            const float2* table = lattice + (size_t)lvl * a.capacity;
+            float dl_db[D + 2];
+#pragma unroll
+            for (int r = 0; r <= D; r++) {
+                float2 v = __ldg(table + slot[r]);
+                float t = 0.f;
+                t += v.x * w_lvl * gx;
+                t += v.y * w_lvl * gy;
+                dl_db[r] = t;
+            }
+            dl_db[D + 1] = 0.f + dl_db[0];
+            float dl_de[D + 1];
+#pragma unroll
+            for (int i = 0; i <= D; i++) {
+                float plus = 0.f, minus = 0.f;   // dl_db[D - rank_i], dl_db[D + 1 - rank_i]
+#pragma unroll
+                for (int t = 0; t <= D + 1; t++) {
+                    if (D - s.rank[i] == t) plus = dl_db[t];
+                    if (D + 1 - s.rank[i] == t) minus = dl_db[t];
+                }
+                float e = 0.f;
+                e += plus * (1.0f / (D + 1));
+                e -= minus * (1.0f / (D + 1));
+                dl_de[i] = e;
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                const float sc = __ldg(scale + lvl * D + i);
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j <= i; j++) acc += dl_de[j] * sc;
+                acc -= dl_de[i + 1] * sc * (i + 1);
+                d_pos[i] += acc;
+            }
+        }
+    }
+    if (d_positions) {
+        __syncthreads();   // every thread is done reading the gradient tile
+        if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < D; i++) tile[i * PM_PAD + p] = d_pos[i];
+        }
+        __syncthreads();
+        if (half == 0 && valid) {
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                float g = d_pos[i] + tile[i * PM_PAD + p];
+                if (a.has_bb) g = g * a.bb_inv_half[i] * 0.5f;   // chain rule through (p * inv_half + 1) / 2
+                d_positions[idx * D + i] = g;
+            }
+        }
+    }
+}
+
+static int fill_args(PermutoArgs& a, int pos_dim, int n_levels, int64_t capacity, int concat_points, float points_scaling, const float* bb_sides) {
+    if (pos_dim < 2 || pos_dim > 4) return VS_ERR_UNSUPPORTED;
+    if (n_levels < 1 || n_levels > 32 || capacity < 1 || capacity > (int64_t)0x7fffffff) return VS_ERR_INVALID_ARG;
+    a.n_levels = n_levels;
+    a.concat_points = concat_points != 0;
+    a.n_extra = concat_points ? (pos_dim + 1) / 2 : 0;   // ceil(pos_dim / 2), Encoding.cu:72-75
+    a.capacity = (uint32_t)capacity;
+    a.pow2 = (capacity & (capacity - 1)) == 0;
+    a.points_scaling = points_scaling;
+    a.has_bb = bb_sides != nullptr;
+    for (int i = 0; i < 8; i++) {
+        a.bb_half[i] = 1.f;
+        a.bb_inv_half[i] = 1.f;
+    }
+    if (bb_sides)
+        for (int i = 0; i < pos_dim; i++) {
+            a.bb_half[i] = bb_sides[i] / 2.0f;
+            a.bb_inv_half[i] = 1.0f / a.bb_half[i];
+        }
+    return VS_OK;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+int vs_permuto_output_dims(int pos_dim, int n_levels, int concat_points) {
+    return 2 * (n_levels + (concat_points ? (pos_dim + 1) / 2 : 0));
+}
+
+int vs_permuto_forward(int pos_dim, int n_levels, int64_t capacity, int concat_points, float points_scaling, const float* bb_sides,
+                       const float* positions, const float* lattice, const float* scale, const float* shift, const float* window, float* out,
+                       int out_cols, int64_t out_stride, uint8_t* out_of_bounds, int64_t n, const int64_t* n_valid_dev, void* stream) {
+    PermutoArgs a;
+    int rc = fill_args(a, pos_dim, n_levels, capacity, concat_points, points_scaling, bb_sides);
+    if (rc != VS_OK) return rc;
+    const int cols = 2 * (a.n_levels + a.n_extra);
+    VS_CHECK_ARG(n >= 0 && out_cols >= 1 && out_cols <= cols && out_stride >= out_cols && cols <= PM_MAX_COLS);
+    if (n == 0) return VS_OK;
+    VS_CHECK_ARG(positions && lattice && scale && shift && window && out);
+    VS_CHECK_ARG(div_up(n, PM_TILE) <= 0x7fffffff);
+    const dim3 grid((unsigned)div_up(n, PM_TILE));
+    const size_t smem = (size_t)cols * PM_PAD * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VS_PM_FWD(D)                                                                                                                       \
+    permuto_fwd_kernel<D><<<grid, PM_THREADS, smem, st>>>(a, positions, (const float2*)lattice, scale, shift, window, out, out_cols,       \
+                                                           out_stride, out_of_bounds, n, n_valid_dev)
+    if (pos_dim == 2)
+        VS_PM_FWD(2);
+    else if (pos_dim == 3)
+        VS_PM_FWD(3);
+    else
+        VS_PM_FWD(4);
+#undef VS_PM_FWD
+    return launched(1);
+}
+
+int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
+                        const float* lattice, const float* scale, const float* shift, const float* window, const float* d_out, int in_cols,
+                        int64_t in_stride, float* d_lattice, float* d_positions, int64_t n, const int64_t* n_valid_dev, void* stream) {
+    PermutoArgs a;
+    int rc = fill_args(a, pos_dim, n_levels, capacity, concat_points, 1.0f, bb_sides);
+    if (rc != VS_OK) return rc;
+    const int cols = 2 * (a.n_levels + a.n_extra);
+    VS_CHECK_ARG(n >= 0 && in_cols >= 1 && in_cols <= cols && in_stride >= in_cols && cols <= PM_MAX_COLS);
+    if (n == 0 || (!d_lattice && !d_positions)) return VS_OK;
+    VS_CHECK_ARG(positions && lattice && scale && shift && window && d_out);
+    VS_CHECK_ARG(div_up(n, PM_TILE) <= 0x7fffffff);
+    const dim3 grid((unsigned)div_up(n, PM_TILE));
+    const size_t smem = (size_t)cols * PM_PAD * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VS_PM_BWD(D)                                                                                                                       \
+    permuto_bwd_kernel<D><<<grid, PM_THREADS, smem, st>>>(a, positions, (const float2*)lattice, scale, shift, window, d_out, in_cols,      \
+                                                           in_stride, (float2*)d_lattice, d_positions, n, n_valid_dev)
+    if (pos_dim == 2)
+        VS_PM_BWD(2);
+    else if (pos_dim == 3)
+        VS_PM_BWD(3);
+    else
+        VS_PM_BWD(4);
+#undef VS_PM_BWD
+    return launched(1);
+}
+
+}  // extern "C"
