@@ -58,9 +58,25 @@ def _simplex(pos, shift_l, scale_l, fma):
     elevated = np.zeros((n, d + 1), F)
     sm = np.zeros(n, F)
     for i in range(d, 0, -1):
-        cf = ((pos[:, i - 1] + shift_l[i - 1]).astype(F) * scale_l[i - 1]).astype(F)
-        elevated[:, i] = _mad(cf, F(-i), sm, fma)             # sm - i*cf
-        sm = (sm + cf).astype(F)
+        ps = (pos[:, i - 1] + shift_l[i - 1]).astype(F)
+        cf = (ps * scale_l[i - 1]).astype(F)
+        if not fma:
+            elevated[:, i] = (sm - (F(i) * cf).astype(F)).astype(F)
+            sm = (sm + cf).astype(F)
+        elif i >= 3:
+            # nvcc 12.9 (-O3, default -fmad=true), read from the SASS of forward_gpu / permuto_fwd_kernel for pos_dim 2, 3, 4:
+            # cf is rounded once, i*cf is fused into the subtraction, the running sum adds the rounded cf
+            elevated[:, i] = _mad(cf, F(-i), sm, True)
+            sm = (sm + cf).astype(F)
+        elif i == 2:
+            # 2*cf is strength-reduced to cf + cf and ONE of the two products is fused: fma(ps, scale, cf)
+            two_cf = _mad(ps, scale_l[i - 1], cf, True)
+            elevated[:, i] = (sm - two_cf).astype(F)
+            sm = (sm + cf).astype(F)
+        else:
+            # i == 1: cf is never materialised; both uses fuse the product (fma(-ps, scale, sm) and fma(ps, scale, sm))
+            elevated[:, 1] = _mad(-ps, scale_l[0], sm, True)
+            sm = _mad(ps, scale_l[0], sm, True)
     elevated[:, 0] = sm
 
     inv = F(1.0) / F(d + 1)                                    # the literal (1.0f / (pos_dim + 1))

@@ -3,10 +3,12 @@
     compiled unmodified behind a C harness (oracle/ref_permuto_harness.cu, recipe oracle/build.py:build_ref_permuto), and
 (2) the numpy restatement oracle/permuto.py.
 
-Bars: forward bit-exact against the reference kernels (same expressions, same compiler contractions); gradients within 1e-5 under
-grad_err (both sides accumulate with unordered fp32 atomics); restatement vs kernels within 2e-6 absolute on unit-scale tables
-(numpy cannot contract a*b+c exactly like nvcc; a position that lands within rounding of a simplex face may pick the neighbouring
-simplex, which is harmless because the interpolant is continuous across faces)."""
+Bars: forward BIT-EXACT three ways — product == reference kernels == numpy restatement (the restatement emulates the a*b+c
+contractions nvcc makes in the elevation, read from the SASS; at the fine levels the elevated coordinates are ~1e5 with an ulp of
+0.008, so one differently rounded sum moves a barycentric weight by 1e-3: nothing short of the same roundings agrees there).
+Position gradients bit-exact per level against the reference kernels; lattice gradients (unordered fp32 atomics on both sides, so
+only the accumulation order differs) within 1e-5 under grad_err where slots receive few terms, and judged against the
+fp64-accumulated restatement where thousands of mixed-sign terms meet in one slot (coarse levels)."""
 import ctypes
 
 import numpy as np
@@ -80,13 +82,10 @@ def test_forward_bit_exact_vs_reference_kernels(ref):
 
 def test_forward_vs_restatement():
     enc, pos = _setup(n=6000)
-    ours = enc(pos).cpu().numpy()
+    ours = enc(pos).detach().cpu().numpy()
     want = op.to_rows(op.forward(pos.cpu().numpy(), enc.lattice_values.detach().cpu().numpy(), enc.scale_factor.cpu().numpy(),
                                  enc.random_shift_per_level.detach().cpu().numpy(), np.ones(24, np.float32), True, 1.0, fma=True))
-    assert np.array_equal(ours[:, 48:], want[:, 48:])
-    d = np.abs(ours - want)
-    assert d.max() < 2e-6, d.max()
-    assert (ours == want).mean() > 0.98
+    assert np.array_equal(ours, want), f"{(ours != want).sum()} entries differ, max {np.abs(ours - want).max():.3e}"
 
 
 def test_restatement_vs_reference_kernels(ref):
@@ -94,8 +93,7 @@ def test_restatement_vs_reference_kernels(ref):
     theirs = _ref_forward(ref, enc, pos, enc.anneal_window).cpu().numpy()
     want = op.forward(pos.cpu().numpy(), enc.lattice_values.detach().cpu().numpy(), enc.scale_factor.cpu().numpy(),
                       enc.random_shift_per_level.detach().cpu().numpy(), np.ones(24, np.float32), True, 1.0, fma=True)
-    assert np.abs(theirs - want).max() < 2e-6
-    assert (theirs == want).mean() > 0.98
+    assert np.array_equal(theirs, want), f"{(theirs != want).sum()} entries differ, max {np.abs(theirs - want).max():.3e}"
 
 
 def test_backward_vs_reference_kernels_and_restatement(ref):
@@ -106,17 +104,28 @@ def test_backward_vs_reference_kernels_and_restatement(ref):
     window = torch.from_numpy(op.cosine_easing_window(24, 0.8 * 24)).cuda()
     d_lat, d_pos = enc._launch_backward(enc.lattice_values, pos, window, grad, None, None, want_lattice=True, want_positions=True)
     r_lat, r_pos = _ref_backward(ref, enc, pos, window, grad)
-    assert grad_err(d_lat.cpu().numpy(), r_lat.cpu().numpy()) < 1e-5
-    assert grad_err(d_pos.cpu().numpy(), r_pos.cpu().numpy()) < 1e-5
     # fp64-accumulated restatement
     o_lat, o_pos = op.backward(pos.cpu().numpy(), enc.lattice_values.detach().cpu().numpy(), enc.scale_factor.cpu().numpy(),
                                enc.random_shift_per_level.detach().cpu().numpy(), window.cpu().numpy(), op.from_rows(grad.cpu().numpy()),
                                fma=True, dtype=np.float64)
-    assert grad_err(d_lat.cpu().numpy(), o_lat) < 1e-5
-    assert grad_err(r_lat.cpu().numpy(), o_lat) < 1e-5
-    # the position gradient is a difference of table values times ~1/scale: compare where the simplices agree (all but a few points)
-    e = np.abs(d_pos.cpu().numpy() - o_pos) / np.maximum(np.abs(o_pos), np.sqrt(np.mean(o_pos ** 2)))
-    assert np.quantile(e, 0.99) < 1e-5
+    d_lat, r_lat = d_lat.cpu().numpy(), r_lat.cpu().numpy()
+    # fine levels: a slot receives a handful of terms, the order of the atomics is immaterial
+    assert grad_err(d_lat[12:], r_lat[12:]) < 1e-5
+    assert grad_err(d_lat[12:], o_lat[12:]) < 1e-5
+    # coarse levels: thousands of O(1) mixed-sign terms per slot in fp32, in an unspecified order on both sides — each side is
+    # judged against fp64 (the product aggregates runs before the atomic, so it is usually the closer one)
+    ours_err, ref_err = grad_err(d_lat, o_lat), grad_err(r_lat, o_lat)
+    assert ours_err < max(1e-5, 2 * ref_err), (ours_err, ref_err)
+    assert ref_err < 5e-3, ref_err
+    # position gradient: per level bit-exact (one-hot windows), summed over levels in a different order (registers vs atomics)
+    for lvl in (0, 7, 19):
+        w1 = torch.zeros(24, device="cuda")
+        w1[lvl] = 0.625
+        _, a = enc._launch_backward(enc.lattice_values, pos, w1, grad, None, None, want_lattice=False, want_positions=True)
+        _, b = _ref_backward(ref, enc, pos, w1, grad)
+        assert torch.equal(a, b), lvl
+    assert grad_err(d_pos.cpu().numpy(), r_pos.cpu().numpy()) < 1e-5
+    assert grad_err(d_pos.cpu().numpy(), o_pos) < 1e-5
 
 
 def test_coherent_positions_use_the_aggregated_atomics(ref):
@@ -139,18 +148,17 @@ def test_coherent_positions_use_the_aggregated_atomics(ref):
 @pytest.mark.parametrize("pos_dim,cap,L", [(2, 1 << 12, 6), (4, 5003, 5), (3, 1000003, 4)])
 def test_other_dims_and_capacities_vs_restatement(pos_dim, cap, L):
     enc, pos = _setup(n=3000, L=L, cap=cap, pos_dim=pos_dim, fine=1e-2, seed=pos_dim)
-    ours = enc(pos).cpu().numpy()
+    ours = enc(pos).detach().cpu().numpy()
     args = (pos.cpu().numpy(), enc.lattice_values.detach().cpu().numpy(), enc.scale_factor.cpu().numpy(),
             enc.random_shift_per_level.detach().cpu().numpy(), np.ones(L, np.float32))
     want = op.to_rows(op.forward(*args, True, 1.0, fma=True))
     assert ours.shape == want.shape == (3000, 2 * (L + (pos_dim + 1) // 2))
-    assert np.abs(ours - want).max() < 2e-6
+    assert np.array_equal(ours, want), f"{(ours != want).sum()} entries differ, max {np.abs(ours - want).max():.3e}"
     grad = torch.randn(*ours.shape, generator=torch.Generator().manual_seed(2)).cuda()
     d_lat, d_pos = enc._launch_backward(enc.lattice_values, pos, enc.anneal_window, grad, None, None, want_lattice=True, want_positions=True)
     o_lat, o_pos = op.backward(*args, op.from_rows(grad.cpu().numpy()), fma=True, dtype=np.float64)
     assert grad_err(d_lat.cpu().numpy(), o_lat) < 1e-5
-    e = np.abs(d_pos.cpu().numpy() - o_pos) / np.maximum(np.abs(o_pos), np.sqrt(np.mean(o_pos ** 2)))
-    assert np.quantile(e, 0.99) < 1e-5
+    assert grad_err(d_pos.cpu().numpy(), o_pos) < 1e-5
 
 
 def test_permutohash_encoder_matches_the_reference_wrapper_semantics():
@@ -212,7 +220,7 @@ def test_full_size_adjoint_property():
     """size-independent property at the benchmark's scale (2^20 positions, 24 levels, 2^18 slots): <g, E(V)> == <E^T(g), V>"""
     enc, pos = _setup(n=1 << 20, seed=11)
     grad = torch.randn(1 << 20, 48, generator=torch.Generator().manual_seed(3)).cuda()
-    out = enc(pos, out_cols=48)
+    out = enc(pos, out_cols=48).detach()
     d_lat, _ = enc._launch_backward(enc.lattice_values, pos, enc.anneal_window, grad, None, None)
     lhs = float((out.double() * grad.double()).sum())
     rhs = float((d_lat.double() * enc.lattice_values.detach().double()).sum())
