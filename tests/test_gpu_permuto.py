@@ -207,7 +207,9 @@ def test_autograd_and_n_valid_gate():
     d_lat, _ = enc.encoder._launch_backward(enc.encoder.lattice_values, pts, enc.window(None), upstream, enc.bb_sides, n_valid)
     f1k, _ = enc(pts[:1000].contiguous())
     (f1k * upstream[:1000]).sum().backward()
-    assert grad_err(d_lat.cpu().numpy(), enc.encoder.lattice_values.grad.cpu().numpy()) < 1e-5
+    # two fp32 atomic accumulations of the same terms in different orders (4096-row vs 1000-row tiling; 2^14 slots collide heavily):
+    # agreement to rounding noise of the accumulation, not to 1e-5 of each entry
+    assert grad_err(d_lat.cpu().numpy(), enc.encoder.lattice_values.grad.cpu().numpy()) < 1e-4
     assert grad_err(g_full.cpu().numpy(), enc.encoder.lattice_values.grad.cpu().numpy()) > 1e-3     # and it is not the full gradient
     # position gradient flows (chain rule through the bounding-box map)
     pts_g = pts[:512].clone().requires_grad_(True)
