@@ -166,7 +166,8 @@ int vs_shells_sample_normals(const void* handle, const int32_t* layer_of, const 
  * Replaces RGB.forward (volsurfs_py/models/rgb.py:104-149: [pos features | SH(dirs) | normals?] -> MLP -> sigmoid), MLP.forward
  * (models/mlp.py:8-52), SHEncoder.__call__ (encodings/sphericalharmonics.py:84-153) and the alpha decay of
  * volsurfs_py/methods/volsurfs.py:583-594 at their call sites volsurfs.py:544-549,575-594.
- * dims = [in, h1, ..., out] (n_layers + 1 entries): in <= 128, hidden widths multiples of 16 and <= 128, out <= 8. */
+ * dims = [in, h1, ..., out] (n_layers + 1 entries): in <= 128, hidden widths multiples of 16 and <= 128, out <= 8
+ * (sigmoid heads; the linear-output variants below take out <= 32). */
 int64_t vs_mlp_blob_bytes(int n_layers, const int* dims);
 /* weights[l]: DEVICE fp32 [dims[l+1], dims[l]] (torch.nn.Linear layout), biases[l]: DEVICE fp32 [dims[l+1]] or NULL; the pointer
  * arrays themselves are HOST arrays.  Writes the fp16 tensor-core layout + fp32 biases into `blob` (device, 16-byte aligned). */
@@ -242,6 +243,45 @@ int vs_permuto_forward(int pos_dim, int n_levels, int64_t capacity, int concat_p
 int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
                         const float* lattice, const float* scale, const float* shift, const float* window, const float* d_out, int in_cols,
                         int64_t in_stride, float* d_lattice, float* d_positions, int64_t n, const int64_t* n_valid_dev, void* stream);
+
+/* ---- SH neural textures: the default appearance (SURVEY 8a row a6' / 8f row 4) ------------------------------------------------------
+ * Replaces SHNeuralTextures.forward (volsurfs_py/models/sh_neural_textures.py:64-97), NeuralTexture.forward
+ * (volsurfs_py/models/neural_texture.py:81-197), the uv helpers it calls (submodules/mvdatasets/mvdatasets/utils/images.py:30-117),
+ * SHEncoder.eval (volsurfs_py/encodings/sphericalharmonics.py:156-229) and the tiny-cuda-nn modules built at neural_texture.py:54-79
+ * (HashGrid encoding + FullyFusedMLP; un-vendored dependency, restated from its published algorithm: "parity unpinned") at their call
+ * sites volsurfs_py/methods/volsurfs.py:539-541,570-572.  Pipeline per SH degree g: vs_hashgrid_forward (texel queries -> features) ->
+ * vs_mlp_forward_raw (features -> C*(2g+1) raw outputs) ; then one vs_shtex_combine_forward over all degrees. */
+/* tiny-cuda-nn HashGrid level table (2-D): HOST arrays of n_levels entries (any may be NULL); returns the total entry count or < 0 */
+int64_t vs_hashgrid_levels(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, float* scale, int32_t* res,
+                           int32_t* size, int32_t* offset);
+/* features [rows, 2*n_levels] f32 (fp16-representable), rows = n_samples * (mode == 1 ? 4 : 1), row = sample*corners + corner.
+ * mode 0: anchor (texel centre), 1: lerp (4 texel corners), 2: uv as given (bake); align: align_to_webgl; uv [n_samples,2]; table [entries,2] f32 (DEVICE). */
+int vs_hashgrid_forward(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, int mode, int align, int res_h,
+                        int res_w, const float* uv, const float* table, float* features, int64_t n_samples, const int64_t* n_valid_dev,
+                        void* stream);
+/* d_table [entries,2] f32 is ADDED to (zero it for a fresh gradient) */
+int vs_hashgrid_backward(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, int mode, int align, int res_h,
+                         int res_w, const float* uv, const float* d_features, float* d_table, int64_t n_samples, const int64_t* n_valid_dev,
+                         void* stream);
+/* MLP with a LINEAR last layer (tiny-cuda-nn "output_activation": "None"), out <= 32, no SH / normal columns: out[r,:] = MLP(in[r,:]).
+ * dims, blob, activation, stash as vs_mlp_forward. */
+int vs_mlp_forward_raw(int n_layers, const int* dims, const void* blob, int activation, const float* in, float* out, void* stash,
+                       int64_t n_rows, const int64_t* n_valid_dev, void* stream);
+/* backward of a training-mode vs_mlp_forward_raw; workspace: vs_mlp_backward_workspace_bytes(n_layers, dims, dims[0], -1, 0, n_rows) */
+int vs_mlp_backward_stashed_raw(int n_layers, const int* dims, const void* blob, const void* stash, const float* d_out, float* d_in,
+                                float* d_params, int accumulate, void* workspace, int64_t n_rows, const int64_t* n_valid_dev, void* stream);
+/* raw: HOST array of sh_deg+1 DEVICE pointers, raw[g] = [n_samples*corners, C*(2g+1)] f32; res_hw: HOST [sh_deg+1][2] (height, width);
+ * range_lo / range_hi: HOST [sh_deg+1] val_range per degree (needed with squeeze); coeffs [n_samples,C,(sh_deg+1)^2] f32 or NULL;
+ * dirs [n_samples,3] and out [n_samples,C], or both NULL (view_dirs=None: coefficients only). */
+int vs_shtex_combine_forward(int sh_deg, int nr_channels, int mode, int align, const int* res_hw, const float* range_lo, const float* range_hi,
+                             int squeeze, int quantize, const float* uv, const float* dirs, const float* const* raw, float* coeffs, float* out,
+                             int64_t n_samples, const int64_t* n_valid_dev, void* stream);
+/* d_raw: HOST array of DEVICE pointers shaped like raw (overwritten) from g_out [n_samples,C] (+ dirs and the forward's out) or, with
+ * dirs == NULL, from g_coeffs [n_samples,C,(sh_deg+1)^2]; gradients of fp16 tensors are rounded to fp16 where torch autograd does. */
+int vs_shtex_combine_backward(int sh_deg, int nr_channels, int mode, int align, const int* res_hw, const float* range_lo, const float* range_hi,
+                              int squeeze, int quantize, const float* uv, const float* dirs, const float* const* raw, const float* out,
+                              const float* g_out, const float* g_coeffs, float* const* d_raw, int64_t n_samples, const int64_t* n_valid_dev,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,234 @@
+"""GPU parity of the SH-neural-texture appearance (SURVEY 8a row a6') through the C ABI, stage by stage and end to end, against
+oracle/shtex.py and the vectors recorded from the reference's own SHNeuralTextures / NeuralTexture classes (tests/golden/shtex_*.npz).
+
+Bars:
+  * hash-grid level table and feature rows ........ bit-exact (fp32 round-to-nearest contract, fp16-rounded features)
+  * texture network (tcgen05, fp16 x fp16 -> fp32) . <= 1 fp16 ulp-ish: |diff| <= 2e-3 * max(1, |x|) against the fp16-operand oracle
+  * glue given the oracle's network outputs ........ coefficients bit-exact except quantisation flips (an ulp of sigmoid() at a .5
+                                                     boundary of round(255 s)): <= 0.1 % of entries may differ; outputs <= 2e-6 abs
+                                                     where the coefficients agree; gradients of the network outputs likewise
+  * end to end (module vs the reference classes) ... 99 % of outputs within 2e-3, all within 4e-2 (one flipped 8-bit level moves a
+                                                     +-15 coefficient by 0.118); parameter gradients <= 3e-2 under grad_err
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, grad_err
+from oracle import shtex as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(name):
+    d = np.load(GOLDEN / f"{name}.npz")
+    C, deg = int(d["nr_channels"]), int(d["sh_deg"])
+    nets = [O.TextureNet(C * O.DEG_NR_COEFFS[g], seed=int(d["seeds"][g]), table_init=0.5) for g in range(deg + 1)]
+    return d, nets, C, deg
+
+
+def _module_from(d, nets, C, deg):
+    from volsurfs_b200.textures import SHNeuralTextures
+
+    m = SHNeuralTextures(sh_deg=deg, nr_channels=C, sh_range=[float(v) for v in d["sh_range"]], anchor=bool(d["anchor"]), lerp=bool(d["lerp"]),
+                         deg_res=[int(v) for v in d["deg_res"]], quantize_output=True, squeeze_output=True, align_to_webgl=True)
+    with torch.no_grad():
+        for nt, net in zip(m.neural_textures, nets):
+            nt.model.table.copy_(net.table.detach())
+            for w, W in zip(nt.model.weights, net.weights):
+                w.copy_(W.detach())
+    return m.cuda()
+
+
+def test_level_table_matches_oracle(lib):
+    from volsurfs_b200.textures import TextureNetwork
+
+    net = TextureNetwork(3)
+    scale, res, size, off = net.level_table()
+    levels, total = O.hashgrid_levels()
+    assert net.n_entries == total
+    assert [np.float32(s) for s in scale] == [l["scale"] for l in levels]
+    assert res == [l["res"] for l in levels] and size == [l["size"] for l in levels] and off == [l["offset"] for l in levels]
+
+
+@pytest.mark.parametrize("mode,align,res", [(1, True, [64, 32]), (1, False, [2048, 2048]), (0, True, [16, 16]), (0, False, [256, 128]), (2, False, [8, 8])])
+def test_hashgrid_features_bit_exact(mode, align, res):
+    from volsurfs_b200.textures import TextureNetwork
+
+    torch.manual_seed(5)
+    net = TextureNetwork(3).cuda()
+    with torch.no_grad():
+        net.table.copy_((torch.rand_like(net.table) * 2 - 1) * 0.5)
+    n = 3001
+    uv = torch.rand(n, 2)
+    uv[:6] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.0, 1.0], [1.0, 0.0], [0.5, 0.5], [1e-5, 0.99999]])
+    feat = net.encode(uv.cuda(), mode, align, res).cpu()
+    if mode == 2:
+        q = uv
+    else:
+        q, _ = O.texel_queries(uv.clone(), res, anchor=mode == 0, lerp=mode == 1, align_to_webgl=align)
+    levels, _ = O.hashgrid_levels()
+    want = O.hashgrid_forward(net.table.detach().cpu(), q, levels)
+    assert feat.shape == want.shape
+    assert torch.equal(feat, want), float((feat - want).abs().max())
+
+
+def test_hashgrid_backward_matches_autograd():
+    from volsurfs_b200 import _lib
+    from volsurfs_b200.textures import TextureNetwork
+    from volsurfs_b200.volsurfs import _stream
+
+    torch.manual_seed(6)
+    net = TextureNetwork(3).cuda()
+    n, res = 2000, [128, 128]
+    uv = torch.rand(n, 2)
+    q, _ = O.texel_queries(uv.clone(), res, anchor=False, lerp=True, align_to_webgl=True)
+    levels, _ = O.hashgrid_levels()
+    table = net.table.detach().cpu().clone().requires_grad_()
+    feat = O.hashgrid_forward(table, q, levels)
+    g = torch.randn_like(feat)
+    (feat * g).sum().backward()
+    d_table = torch.zeros_like(net.table)
+    uv_d, g_d = uv.cuda(), g.cuda()
+    code = _lib.lib().vs_hashgrid_backward(*net.grid_cfg, 1, 1, res[0], res[1], uv_d.data_ptr(), g_d.data_ptr(), d_table.data_ptr(), n, None, _stream())
+    assert code == 0
+    err = grad_err(d_table.cpu().numpy(), table.grad.numpy())
+    print("hashgrid backward grad_err", err)
+    assert err < 1e-5
+
+
+@pytest.mark.parametrize("n_out", [1, 3, 7, 9, 15, 21])
+def test_texture_network_against_fp16_oracle(n_out):
+    from volsurfs_b200.textures import TextureNetwork
+
+    torch.manual_seed(7 + n_out)
+    net = TextureNetwork(n_out).cuda()
+    rows = 1000
+    feat = (torch.randn(rows, 32) * 0.5).half().float()
+    raw = net.mlp_raw(feat.cuda()).cpu()
+    want = O.mlp_half_forward(feat, [w.detach().cpu() for w in net.weights]).detach()
+    err = ((raw - want).abs() / want.abs().clamp(min=1.0)).max().item()
+    print("texture network max err", err)
+    assert raw.shape == (rows, n_out) and err < 2e-3
+
+
+def _oracle_stage_outputs(d, nets, C, deg):
+    """the oracle's fp16 network outputs per degree (with gradients after backward), coefficients and outputs"""
+    keep = []
+    out = O.sh_neural_textures_forward(nets, torch.from_numpy(d["uv"]).clone(), torch.from_numpy(d["dirs"]), sh_deg=deg, nr_channels=C,
+                                       sh_range=[float(v) for v in d["sh_range"]], deg_res=[int(v) for v in d["deg_res"]],
+                                       anchor=bool(d["anchor"]), lerp=bool(d["lerp"]), keep=keep)
+    return out, keep
+
+
+def _combine_args(d, C, deg):
+    from volsurfs_b200.textures import _combine_args
+
+    res = [[int(v), int(v)] for v in d["deg_res"][: deg + 1]]
+    ranges = [(-float(v), float(v)) for v in d["sh_range"][: deg + 1]]
+    return _combine_args(deg, C, 0 if bool(d["anchor"]) else 1, True, res, ranges, True, True)
+
+
+@pytest.mark.parametrize("name", ["shtex_rgb_lerp", "shtex_alpha_lerp", "shtex_rgb_anchor"])
+def test_glue_given_oracle_network_outputs(name, lib):
+    """combine forward + backward fed with the ORACLE's network outputs: isolates the reference glue (pinned by the goldens)"""
+    from volsurfs_b200.volsurfs import _stream
+
+    d, nets, C, deg = _case(name)
+    out_o, keep = _oracle_stage_outputs(d, nets, C, deg)
+    (out_o * torch.from_numpy(d["g_out"])).sum().backward()
+    assert np.array_equal(out_o.detach().numpy(), d["out"])
+    n = d["uv"].shape[0]
+    raws = [k.detach().float().cuda().contiguous() for k in keep]
+    uv, dirs = torch.from_numpy(d["uv"]).cuda(), torch.from_numpy(d["dirs"]).cuda()
+    nc = (deg + 1) ** 2
+    coeffs = torch.empty(n, C, nc, device="cuda")
+    out = torch.empty(n, C, device="cuda")
+    rp = (ctypes.c_void_p * (deg + 1))(*[r.data_ptr() for r in raws])
+    args = _combine_args(d, C, deg)
+    assert lib.vs_shtex_combine_forward(*args, uv.data_ptr(), None, rp, coeffs.data_ptr(), None, n, None, _stream()) == 0
+    assert lib.vs_shtex_combine_forward(*args, uv.data_ptr(), dirs.data_ptr(), rp, None, out.data_ptr(), n, None, _stream()) == 0
+    co, want_co = coeffs.cpu().numpy(), d["coeffs"]
+    same = co == want_co
+    print(name, "coefficient mismatches:", int((~same).sum()), "of", same.size)
+    assert (~same).mean() <= 1e-3
+    ok_rows = same.all(axis=2)
+    assert np.abs(out.cpu().numpy() - d["out"])[ok_rows].max() <= 2e-6
+    # backward: gradient of every network output
+    g_out = torch.from_numpy(d["g_out"]).cuda()
+    out_ref = torch.from_numpy(d["out"]).cuda()
+    d_raws = [torch.full_like(r, float("nan")) for r in raws]
+    dp = (ctypes.c_void_p * (deg + 1))(*[r.data_ptr() for r in d_raws])
+    assert lib.vs_shtex_combine_backward(*args, uv.data_ptr(), dirs.data_ptr(), rp, out_ref.data_ptr(), g_out.data_ptr(), None, dp, n, None,
+                                         _stream()) == 0
+    for g in range(deg + 1):
+        got, want = d_raws[g].cpu().numpy(), keep[g].grad.float().numpy()
+        assert np.isfinite(got).all()
+        bad = np.abs(got - want) > 1e-6 * np.maximum(np.abs(want), 1e-3)
+        print(name, "deg", g, "d_raw mismatches:", int(bad.sum()), "of", bad.size, "max", float(np.abs(got - want).max()))
+        assert bad.mean() <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["shtex_rgb_lerp", "shtex_alpha_lerp", "shtex_rgb_anchor"])
+def test_module_end_to_end_against_reference_classes(name):
+    d, nets, C, deg = _case(name)
+    m = _module_from(d, nets, C, deg)
+    uv, dirs = torch.from_numpy(d["uv"]).cuda(), torch.from_numpy(d["dirs"]).cuda()
+    out = m(uv_coords=uv, view_dirs=dirs)
+    err = np.abs(out.detach().cpu().numpy() - d["out"])
+    print(name, "end-to-end |err| p99 %.2e max %.2e" % (np.quantile(err, 0.99), err.max()))
+    assert np.quantile(err, 0.99) < 2e-3 and err.max() < 4e-2
+    coeffs = m(uv_coords=uv, view_dirs=None).detach().cpu().numpy()
+    assert coeffs.shape == d["coeffs"].shape
+    step = 2 * float(d["sh_range"][0]) / 255.0
+    assert np.mean(np.abs(coeffs - d["coeffs"]) > 0.05 * step) < 0.02  # a few texels land on the neighbouring 8-bit level
+    (out * torch.from_numpy(d["g_out"]).cuda()).sum().backward()
+    for g, nt in enumerate(m.neural_textures):
+        for i, w in enumerate(nt.model.weights):
+            e = grad_err(w.grad.cpu().numpy(), d[f"dW{g}_{i}"])
+            print(name, f"dW{g}_{i} grad_err {e:.2e}")
+            assert e < 3e-2
+        rows = torch.from_numpy(d[f"d_table{g}_rows"])
+        gt = nt.model.table.grad.cpu()
+        e = grad_err(gt[rows].numpy(), d[f"d_table{g}_vals"])
+        print(name, f"d_table{g} grad_err {e:.2e}")
+        assert e < 3e-2
+        mask = torch.ones(gt.shape[0], dtype=torch.bool)
+        mask[rows] = False
+        assert float(gt[mask].abs().max()) <= 1e-4 * float(gt.abs().max())
+
+
+def test_neural_texture_single_and_bake():
+    """NeuralTexture on its own (neural_texture.py:81-197): lerp output == coefficient path with one degree; bake returns the squeezed
+    8-bit values of the texel-centre queries"""
+    from volsurfs_b200.textures import NeuralTexture
+
+    torch.manual_seed(11)
+    nt = NeuralTexture(res=[32, 32], nr_channels=5, val_range=(-2.0, 2.0), lerp=True, quantize_output=True, squeeze_output=True,
+                       align_to_webgl=True).cuda()
+    with torch.no_grad():
+        nt.model.table.copy_((torch.rand_like(nt.model.table) * 2 - 1) * 0.5)
+    uv = torch.rand(500, 2)
+    net = O.TextureNet(5, seed=0)
+    net.table = nt.model.table.detach().cpu()
+    net.weights = [w.detach().cpu() for w in nt.model.weights]
+    want = O.neural_texture_forward(net, uv.clone(), [32, 32], (-2.0, 2.0), anchor=False, lerp=True).numpy()
+    got = nt(uv.cuda()).detach().cpu().numpy()
+    assert got.shape == (500, 5)
+    assert np.mean(np.abs(got - want) > 1e-3) < 0.02 and np.abs(got - want).max() < 0.05
+    baked = nt(uv.cuda(), bake=True).cpu().numpy()
+    q = baked * 255.0
+    assert baked.shape == (500, 5) and np.abs(q - np.round(q)).max() < 1e-3 and baked.min() >= 0 and baked.max() <= 1
+
+
+def test_argument_errors(lib):
+    from volsurfs_b200.textures import SHNeuralTextures
+
+    with pytest.raises(ValueError):
+        SHNeuralTextures(sh_deg=4)
+    with pytest.raises(ValueError):
+        SHNeuralTextures(sh_deg=1, quantize_output=True, squeeze_output=False)
+    assert lib.vs_hashgrid_forward(17, 15, 16, ctypes.c_float(1.5), 1, 1, 8, 8, None, None, None, 0, None, None) != 0
+    assert lib.vs_shtex_combine_forward(5, 3, 1, 1, None, None, None, 1, 1, None, None, None, None, None, 0, None, None) != 0

@@ -297,13 +297,20 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
                     }
                 }
                 announce(s);
-            } else if (cg == 0) {
+            } else if (cg * 16 < N) {  // output layer: N is 16 (sigmoid heads, <= 8 outputs) or up to 32 (linear texture nets)
+                const int c0 = cg * 16;
                 float v[16];
-                tmem_ld16(tmem_lane, v);
+                tmem_ld16(tmem_lane + (uint32_t)c0, v);
                 if (r < n) {
+                    if (cfg.out_linear) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < cfg.out_dim) out[r * cfg.out_dim + j] = sigmoid_f(v[j] + bias[j]) * decay[s];
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < cfg.out_dim) out[r * cfg.out_dim + c0 + j] = v[j] + bias[c0 + j];
+                    } else if (cg == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < cfg.out_dim) out[r * cfg.out_dim + j] = sigmoid_f(v[j] + bias[j]) * decay[s];
+                    }
                 }
             }
         };
@@ -376,16 +383,20 @@ int64_t vs_mlp_stash_bytes(int n_layers, const int* dims, int64_t n_samples) {
     return div_up(n_samples, kTileM) * (int64_t)s.tile_bytes;
 }
 
+}  // extern "C"
+
 // out[s, :out_dim] = sigmoid(MLP([pos[s] | SH_deg(dirs[s]) | normals[s]?])) (* alpha decay).  dims[0] must equal
 // pos_dim + (sh_degree+1)^2 (0 if sh_degree < 0) + 3*normal_dep.  n_valid_dev (optional device int64) caps the sample count.
 // stash (optional, vs_mlp_stash_bytes bytes, 16-byte aligned): training mode, activations are kept for vs_mlp_backward_stashed.
-int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
-                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, void* stash, int64_t n_samples,
-                   const int64_t* n_valid_dev, int variant, void* stream) {
+static int mlp_forward_impl(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
+                            int alpha_decay, int out_linear, const float* pos, const float* dirs, const float* normals, float* out,
+                            void* stash, int64_t n_samples, const int64_t* n_valid_dev, int variant, void* stream) {
     VS_CHECK_ARG(dims && blob && n_samples >= 0 && pos_dim >= 0 && sh_degree <= 3);
     MlpConfig c;
     int e = mlp_layout(n_layers, dims, &c);
     if (e != VS_OK) return e;
+    if (!out_linear && c.out_dim > 8) return VS_ERR_UNSUPPORTED;
+    c.out_linear = out_linear ? 1 : 0;
     const int n_sh = sh_degree < 0 ? 0 : (sh_degree + 1) * (sh_degree + 1);
     VS_CHECK_ARG(dims[0] == pos_dim + n_sh + 3 * (normal_dep ? 1 : 0));
     VS_CHECK_ARG((n_sh == 0 || dirs) && (!(normal_dep || alpha_decay) || normals) && (!alpha_decay || dirs));
@@ -422,6 +433,24 @@ int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim,
     kern<<<grid, kFwdThreads, smem, (cudaStream_t)stream>>>(c, sc, reinterpret_cast<const uint8_t*>(blob), pos, dirs, normals, out,
                                                              reinterpret_cast<uint8_t*>(stash), n_samples, n_valid_dev);
     return launched(1);
+}
+
+extern "C" {
+
+int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
+                   int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, void* stash, int64_t n_samples,
+                   const int64_t* n_valid_dev, int variant, void* stream) {
+    return mlp_forward_impl(n_layers, dims, blob, pos_dim, sh_degree, normal_dep, activation, alpha_decay, 0, pos, dirs, normals, out, stash,
+                            n_samples, n_valid_dev, variant, stream);
+}
+
+// out[r, :out] = MLP(in[r, :dims[0]]) with a LINEAR last layer (no sigmoid), out <= 32: the texture networks of the default appearance
+// (tiny-cuda-nn FullyFusedMLP with "output_activation": "None", volsurfs_py/models/neural_texture.py:65-77).  stash as vs_mlp_forward.
+int vs_mlp_forward_raw(int n_layers, const int* dims, const void* blob, int activation, const float* in, float* out, void* stash,
+                       int64_t n_rows, const int64_t* n_valid_dev, void* stream) {
+    VS_CHECK_ARG(dims);
+    return mlp_forward_impl(n_layers, dims, blob, dims[0], -1, 0, activation, 0, 1, in, nullptr, nullptr, out, stash, n_rows, n_valid_dev, 0,
+                            stream);
 }
 
 }  // extern "C"

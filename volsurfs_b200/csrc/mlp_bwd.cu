@@ -785,10 +785,20 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
 
             // item 0: dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z))
             const int off_last = cur.alloc(p2.item_bytes[0], R);
+            // each 8-column chunk of dZ_last belongs to one column group (the output layer is 16 or 32 columns wide)
+            const int n_chunks_last = cfg.n_pad[L - 1] / 8;
             float g[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = 0.f;
-            if (cg == 0 && live) {
+            if (cfg.out_linear) {
+                if (cg < n_chunks_last && live) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = cg * 8 + j;
+                        if (col < cfg.out_dim) g[j] = __ldg(d_out + r * cfg.out_dim + col) * scale;
+                    }
+                }
+            } else if (cg == 0 && live) {
                 float decay = 1.f;
                 if (cfg.alpha_decay) {
                     const float dx = __ldg(dirs + 3 * r), dy = __ldg(dirs + 3 * r + 1), dz = __ldg(dirs + 3 * r + 2);
@@ -806,13 +816,12 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
             }
             mbar_wait(item_bar(seq), item_parity(seq));  // the ring space is reserved (its previous tenants have been released)
             ++seq;
-            if (cg == 0) {
+            if (cg < n_chunks_last) {
                 __half2 h[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
                 uint4* dst = reinterpret_cast<uint4*>(s_ring + off_last + (size_t)row * 16);
-                dst[0] = *reinterpret_cast<const uint4*>(h);
-                for (int c = 1; c < cfg.n_pad[L - 1] / 8; ++c) dst[c * kTileM] = make_uint4(0u, 0u, 0u, 0u);
+                dst[cg * kTileM] = *reinterpret_cast<const uint4*>(h);
             }
             announce(&bar_ready);
 
@@ -984,6 +993,7 @@ int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim
     MlpBwdPlan p;
     int e = bwd_setup(n_layers, dims, pos_dim, sh_degree, normal_dep, &c, &p);
     if (e != VS_OK) return e;
+    if (c.out_dim > 8) return VS_ERR_UNSUPPORTED;  // sigmoid heads only; linear outputs go through vs_mlp_backward_stashed_raw
     VS_CHECK_ARG((c.n_sh == 0 || dirs) && (!(normal_dep || alpha_decay) || normals) && (!alpha_decay || dirs));
     VS_CHECK_ARG(pos_dim == 0 || pos);
     VS_CHECK_ARG(n_samples == 0 || d_out);
@@ -1013,18 +1023,23 @@ int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim
     return launched(launches + 1);
 }
 
+}  // extern "C"
+
 // Backward of a training-mode vs_mlp_forward from its activation stash (no recomputation).  fwd_out: the [n_samples,out] output
 // that forward wrote; other arguments as vs_mlp_backward.  workspace: vs_mlp_backward_workspace_bytes bytes.
-int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree, int normal_dep,
-                            int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
-                            float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream) {
+static int mlp_backward_stashed_impl(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree,
+                                     int normal_dep, int alpha_decay, int out_linear, const float* dirs, const float* normals,
+                                     const float* fwd_out, const float* d_out, float* d_pos, float* d_params, int accumulate,
+                                     void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream) {
     VS_CHECK_ARG(blob && stash && n_samples >= 0 && d_params && workspace);
     MlpConfig c;
     MlpBwdPlan p;
     int e = bwd_setup(n_layers, dims, pos_dim, sh_degree, normal_dep, &c, &p, false);
     if (e != VS_OK) return e;
+    if (!out_linear && c.out_dim > 8) return VS_ERR_UNSUPPORTED;
+    c.out_linear = out_linear ? 1 : 0;
     VS_CHECK_ARG(!alpha_decay || (dirs && normals));
-    VS_CHECK_ARG(n_samples == 0 || (d_out && fwd_out));
+    VS_CHECK_ARG(n_samples == 0 || (d_out && (fwd_out || out_linear)));
     VS_CHECK_ARG((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(stash) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(d_pos) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
     c.alpha_decay = alpha_decay ? 1 : 0;
@@ -1054,6 +1069,24 @@ int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, con
     mlp_bwd_reduce_kernel<<<(p.n_params + 255) / 256, 256, 0, s>>>(partials, n_samples > 0 ? grid : 0, p.n_params, absmax, n_valid_dev, n_samples,
                                                                     d_params, accumulate);
     return launched(launches + 1);
+}
+
+extern "C" {
+
+int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree, int normal_dep,
+                            int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
+                            float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream) {
+    return mlp_backward_stashed_impl(n_layers, dims, blob, stash, pos_dim, sh_degree, normal_dep, alpha_decay, 0, dirs, normals, fwd_out, d_out,
+                                     d_pos, d_params, accumulate, workspace, n_samples, n_valid_dev, stream);
+}
+
+// Backward of a training-mode vs_mlp_forward_raw (linear last layer): d_out [n_rows,out] -> d_in [n_rows,dims[0]] (or NULL) and the flat
+// parameter gradients; workspace: vs_mlp_backward_workspace_bytes(n_layers, dims, dims[0], -1, 0, n_rows) bytes.
+int vs_mlp_backward_stashed_raw(int n_layers, const int* dims, const void* blob, const void* stash, const float* d_out, float* d_in,
+                                float* d_params, int accumulate, void* workspace, int64_t n_rows, const int64_t* n_valid_dev, void* stream) {
+    VS_CHECK_ARG(dims);
+    return mlp_backward_stashed_impl(n_layers, dims, blob, stash, dims[0], -1, 0, 0, 1, nullptr, nullptr, nullptr, d_out, d_in, d_params,
+                                     accumulate, workspace, n_rows, n_valid_dev, stream);
 }
 
 }  // extern "C"

@@ -26,6 +26,7 @@ struct MlpConfig {
     int pos_dim, n_sh, normal_dep, in_dim, out_dim;
     int activation;          // 0 relu, 1 gelu
     int alpha_decay;
+    int out_linear;          // 1: the last layer's output is written as it is (tiny-cuda-nn "output_activation": "None"); 0: sigmoid
     int variant;             // debug: bit0 swaps LBO/SBO in the shared-memory descriptors
     int a1_width;            // widest hidden layer (size of the activation buffer), tmem_cols: power of two >= widest layer
     int tmem_cols;
@@ -75,7 +76,7 @@ static inline int mlp_layout(int n_layers, const int* dims, MlpConfig* c) {
     c->tmem_cols = widest <= 32 ? 32 : (widest <= 64 ? 64 : 128);
     c->in_dim = dims[0];
     c->out_dim = dims[n_layers];
-    if (c->out_dim > 8) return VS_ERR_UNSUPPORTED;
+    if (c->out_dim > 32) return VS_ERR_UNSUPPORTED;  // sigmoid heads: <= 8 (checked by the callers); linear outputs: <= 32
     return VS_OK;
 }
 

@@ -1,0 +1,493 @@
+// volsurfs_b200 — SH neural textures: the reference's DEFAULT appearance (config/volsurfs/base_5.cfg:11-20), SURVEY 8a row a6'.
+//
+// Replaces, per layer hit,
+//   volsurfs_py/models/sh_neural_textures.py:64-97   one texture network per SH degree -> coefficient tensor [S,C,16] -> fp16 ->
+//                                                    SHEncoder.eval (encodings/sphericalharmonics.py:156-229) -> sigmoid
+//   volsurfs_py/models/neural_texture.py:81-197      uv -> texel corners (mvdatasets/utils/images.py:46-117), align_to_webgl rotation,
+//                                                    4 network queries, sigmoid, 8-bit quantisation (STE), fp16 re-expansion, lerp
+//   tiny-cuda-nn HashGrid encoding (neural_texture.py:54-63; 2-D, 16 levels x 2 features, 2^15 entries, base 16, scale 1.5)
+// with three kinds of kernels around the tensor-core network (vs_mlp_forward_raw / vs_mlp_backward_stashed_raw, csrc/mlp*.cu):
+//   hashgrid_encode_kernel   thread per (query row, level): texel-corner uv computed on the fly from the hit's uv, 4 gathers from the
+//                            L2-resident table (<= 2.8 MB per network), fp32 interpolation, fp16-rounded feature rows [rows, 32]
+//                            written as full 128-byte lines (16 consecutive threads = the 16 levels of one row)
+//   hashgrid_backward_kernel same mapping, vector atomics (red.global.add.v2.f32) into the table gradient
+//   shtex_combine_*          thread per hit: the 4 corner outputs of every degree -> sigmoid -> quantise -> fp16 expansion -> lerp ->
+//                            fp16 coefficients -> mixed-precision SH evaluation -> sigmoid; the backward replays the same chain
+//                            including the fp16 roundings torch autograd applies to the gradients of fp16 tensors.
+// Arithmetic contract: every fp32 operation of the glue is written with round-to-nearest intrinsics (no FMA contraction) in the
+// reference's operand order, so the coefficient tensor is bit-exact against the CPU restatement (oracle/shtex.py), up to the rare
+// quantisation flips an ulp of sigmoid() can cause.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "vs_common.cuh"
+
+namespace vs {
+
+constexpr int kHgMaxLevels = 16;
+constexpr int kShMaxDeg = 3;
+
+struct HgLevels {
+    int n_levels;
+    float scale[kHgMaxLevels];
+    uint32_t res[kHgMaxLevels], size[kHgMaxLevels], offset[kHgMaxLevels], hashed[kHgMaxLevels];
+    uint32_t total;
+};
+
+struct TexGeom {
+    int mode;   // 0 anchor (texel centre), 1 lerp (4 texel corners), 2 direct (bake: uv as given; encode / backward kernels only)
+    int align;  // align_to_webgl rotation (neural_texture.py:103-109, 124-130)
+    int res_h, res_w;
+};
+
+// tiny-cuda-nn grid.h: grid_scale / grid_resolution / the per-level parameter count.  The scale is evaluated in double on the host and
+// rounded to fp32 once (oracle/shtex.py:hashgrid_levels evaluates the same expression).
+static int hg_layout(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, HgLevels* lv) {
+    if (n_levels < 1 || n_levels > kHgMaxLevels || log2_hashmap_size < 3 || log2_hashmap_size > 28 || base_resolution < 1) return VS_ERR_INVALID_ARG;
+    lv->n_levels = n_levels;
+    uint64_t offset = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const float scale = (float)(std::pow((double)per_level_scale, (double)l) * (double)base_resolution - 1.0);
+        const uint32_t res = (uint32_t)std::ceil((double)scale) + 1u;
+        uint64_t dense = (uint64_t)res * res;
+        uint64_t size = std::min<uint64_t>(dense, 0x7fffffffu);
+        size = (size + 7) / 8 * 8;
+        size = std::min<uint64_t>(size, 1ull << log2_hashmap_size);
+        lv->scale[l] = scale;
+        lv->res[l] = res;
+        lv->size[l] = (uint32_t)size;
+        lv->offset[l] = (uint32_t)offset;
+        lv->hashed[l] = dense > size ? 1u : 0u;
+        offset += size;
+        if (offset > 0x7fffffffu) return VS_ERR_UNSUPPORTED;
+    }
+    lv->total = (uint32_t)offset;
+    return VS_OK;
+}
+
+// uv of query row (sample s, corner k) in the texture's normalised space, exactly as torch evaluates the reference's expressions:
+// images.py:54-61 (uv * flip(res)), :70-81 (floor(uv - 0.5) + corner + 0.5), :46-51 (/ flip(res)); neural_texture.py:98-111 (anchor)
+__device__ __forceinline__ float2 texel_query(const TexGeom& tg, float u, float v, int k, float* lerp_w) {
+    const float W = (float)tg.res_w, H = (float)tg.res_h;
+    if (tg.mode == 2) {  // bake: uv is used as it is (neural_texture.py:83-86)
+        if (lerp_w) *lerp_w = 1.f;
+        return make_float2(u, v);
+    }
+    if (tg.mode == 0) {
+        long long px = (long long)floorf(__fmul_rn(u, W)), py = (long long)floorf(__fmul_rn(v, H));
+        if (tg.align) {
+            const long long t = px;
+            px = (long long)(tg.res_w - 1) - py;
+            py = t;
+        }
+        if (lerp_w) *lerp_w = 1.f;
+        return make_float2(__fdiv_rn(__fadd_rn((float)px, 0.5f), W), __fdiv_rn(__fadd_rn((float)py, 0.5f), H));
+    }
+    float a = __fmul_rn(u, W), b = __fmul_rn(v, H);
+    if (tg.align) {
+        const float t = a;
+        a = __fsub_rn(W, b);  // `width - uv_nn[:, 1]` with width = res[1]
+        b = t;
+    }
+    const float cx = __fadd_rn(floorf(__fsub_rn(a, 0.5f)), 0.5f), cy = __fadd_rn(floorf(__fsub_rn(b, 0.5f)), 0.5f);  // corner 0
+    if (lerp_w) {
+        const float dx = __fsub_rn(a, cx), dy = __fsub_rn(b, cy);
+        const float wx = (k & 1) ? dx : __fsub_rn(1.f, dx), wy = (k & 2) ? dy : __fsub_rn(1.f, dy);
+        *lerp_w = __fmul_rn(wx, wy);
+    }
+    // corners are (floor + offset) + 0.5 with the integer offset added BEFORE the half texel (images.py:30-43, 79)
+    const float qx = __fadd_rn(__fadd_rn(floorf(__fsub_rn(a, 0.5f)), (float)(k & 1)), 0.5f);
+    const float qy = __fadd_rn(__fadd_rn(floorf(__fsub_rn(b, 0.5f)), (float)((k >> 1) & 1)), 0.5f);
+    return make_float2(__fdiv_rn(qx, W), __fdiv_rn(qy, H));
+}
+
+// the 4 interpolation corners of one level at x: entry index (level-relative + offset) and fp32 weight (grid.h: kernel_grid, grid_index)
+__device__ __forceinline__ void hg_corners(const HgLevels& lv, int level, float2 x, uint32_t idx[4], float w[4]) {
+    const float scale = lv.scale[level];
+    const float px = __fadd_rn(__fmul_rn(x.x, scale), 0.5f), py = __fadd_rn(__fmul_rn(x.y, scale), 0.5f);
+    const float fx = floorf(px), fy = floorf(py);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy;
+    const float rx = __fsub_rn(px, fx), ry = __fsub_rn(py, fy);
+    const uint32_t res = lv.res[level], size = lv.size[level], off = lv.offset[level];
+    const bool hashed = lv.hashed[level] != 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t cx = gx + (uint32_t)(c & 1), cy = gy + (uint32_t)((c >> 1) & 1);
+        const float wx = (c & 1) ? rx : __fsub_rn(1.f, rx), wy = (c & 2) ? ry : __fsub_rn(1.f, ry);
+        w[c] = __fmul_rn(wx, wy);
+        const uint32_t h = hashed ? (cx ^ (cy * 2654435761u)) : (cx + cy * res);
+        idx[c] = off + h % size;
+    }
+}
+
+__device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
+
+__global__ void __launch_bounds__(256) hashgrid_encode_kernel(const HgLevels lv, const TexGeom tg, const float* __restrict__ uv,
+                                                              const float2* __restrict__ table, float* __restrict__ feat, int64_t n_samples,
+                                                              const int64_t* __restrict__ n_valid_dev) {
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int corners = tg.mode == 1 ? 4 : 1;
+    const int L = lv.n_levels;
+    const int64_t total = n * corners * L;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int level = (int)(t % L);
+        const int64_t row = t / L;
+        const int64_t s = row / corners;
+        const int k = (int)(row % corners);
+        const float2 q = texel_query(tg, __ldg(uv + 2 * s), __ldg(uv + 2 * s + 1), k, nullptr);
+        uint32_t idx[4];
+        float w[4];
+        hg_corners(lv, level, q, idx, w);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float2 e = __ldg(table + idx[c]);
+            const float t0 = __fmul_rn(w[c], round_half(e.x)), t1 = __fmul_rn(w[c], round_half(e.y));
+            a0 = c == 0 ? t0 : __fadd_rn(a0, t0);
+            a1 = c == 0 ? t1 : __fadd_rn(a1, t1);
+        }
+        __stcs(reinterpret_cast<float2*>(feat + row * (2 * L) + 2 * level), make_float2(round_half(a0), round_half(a1)));
+    }
+}
+
+__global__ void __launch_bounds__(256) hashgrid_backward_kernel(const HgLevels lv, const TexGeom tg, const float* __restrict__ uv,
+                                                                const float* __restrict__ d_feat, float2* __restrict__ d_table,
+                                                                int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int corners = tg.mode == 1 ? 4 : 1;
+    const int L = lv.n_levels;
+    const int64_t total = n * corners * L;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int level = (int)(t % L);
+        const int64_t row = t / L;
+        const int64_t s = row / corners;
+        const int k = (int)(row % corners);
+        const float2 g = __ldcs(reinterpret_cast<const float2*>(d_feat + row * (2 * L) + 2 * level));
+        if (g.x == 0.f && g.y == 0.f) continue;
+        const float2 q = texel_query(tg, __ldg(uv + 2 * s), __ldg(uv + 2 * s + 1), k, nullptr);
+        uint32_t idx[4];
+        float w[4];
+        hg_corners(lv, level, q, idx, w);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(d_table + idx[c], make_float2(w[c] * g.x, w[c] * g.y));
+    }
+}
+
+// ---- coefficient assembly + SH evaluation ----------------------------------------------------------------------------------------
+struct ShTexConfig {
+    int sh_deg, nr_channels, n_coeffs;
+    int squeeze, quantize;
+    TexGeom geom[kShMaxDeg + 1];
+    float range_mul[kShMaxDeg + 1];  // (hi - lo) as torch passes it to mul(half, Scalar): kept in fp32
+    float range_lo[kShMaxDeg + 1];   // lo as torch passes it to add(half, Scalar): rounded to fp16 first
+    const float* raw[kShMaxDeg + 1]; // network outputs [rows, C*(2g+1)] fp32
+    float* d_raw[kShMaxDeg + 1];
+};
+
+__device__ __forceinline__ float sigmoid_precise(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// SH basis factors P_k of sphericalharmonics.py:183-215 in torch's evaluation order (python scalars are fp32 factors)
+__device__ __forceinline__ void sh_factors(float x, float y, float z, int deg, float* P) {
+    P[0] = 0.28209479177387814f;
+    if (deg > 0) {
+        const float C1 = 0.4886025119029199f;
+        P[1] = __fmul_rn(C1, y);
+        P[2] = __fmul_rn(C1, z);
+        P[3] = __fmul_rn(C1, x);
+    }
+    if (deg > 1) {
+        const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+        const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+        P[4] = __fmul_rn(1.0925484305920792f, xy);
+        P[5] = __fmul_rn(-1.0925484305920792f, yz);
+        P[6] = __fmul_rn(0.31539156525252005f, __fsub_rn(__fsub_rn(__fmul_rn(2.0f, zz), xx), yy));
+        P[7] = __fmul_rn(-1.0925484305920792f, xz);
+        P[8] = __fmul_rn(0.5462742152960396f, __fsub_rn(xx, yy));
+        if (deg > 2) {
+            P[9] = __fmul_rn(__fmul_rn(-0.5900435899266435f, y), __fsub_rn(__fmul_rn(3.f, xx), yy));
+            P[10] = __fmul_rn(__fmul_rn(2.890611442640554f, xy), z);
+            P[11] = __fmul_rn(__fmul_rn(-0.4570457994644658f, y), __fsub_rn(__fsub_rn(__fmul_rn(4.f, zz), xx), yy));
+            P[12] = __fmul_rn(__fmul_rn(0.3731763325901154f, z), __fsub_rn(__fsub_rn(__fmul_rn(2.f, zz), __fmul_rn(3.f, xx)), __fmul_rn(3.f, yy)));
+            P[13] = __fmul_rn(__fmul_rn(-0.4570457994644658f, x), __fsub_rn(__fsub_rn(__fmul_rn(4.f, zz), xx), yy));
+            P[14] = __fmul_rn(__fmul_rn(1.445305721320277f, z), __fsub_rn(xx, yy));
+            P[15] = __fmul_rn(__fmul_rn(-0.5900435899266435f, x), __fsub_rn(xx, __fmul_rn(3.f, yy)));
+        }
+    }
+}
+
+// one texel value: network output -> (sigmoid -> quantise) -> fp16 -> expansion to [lo, hi] in fp16 (neural_texture.py:152-181)
+__device__ __forceinline__ float texel_value(const ShTexConfig& c, int g, float raw, float* s_out) {
+    float o = round_half(raw);  // tiny-cuda-nn returns fp16
+    float s = 0.f;
+    if (c.squeeze) {
+        s = sigmoid_precise(o);
+        o = s;
+        if (c.quantize) o = __fdiv_rn(rintf(__fmul_rn(o, 255.0f)), 255.0f);
+    }
+    if (s_out) *s_out = s;
+    float h = round_half(o);
+    if (c.squeeze) {
+        h = round_half(__fmul_rn(c.range_mul[g], h));
+        h = round_half(__fadd_rn(c.range_lo[g], h));
+    }
+    return h;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) shtex_combine_kernel(const ShTexConfig cfg, const float* __restrict__ uv, const float* __restrict__ dirs,
+                                                            float* __restrict__ coeffs, float* __restrict__ out,
+                                                            const float* __restrict__ g_out, const float* __restrict__ g_coeffs,
+                                                            int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int C = cfg.nr_channels, NC = cfg.n_coeffs, deg = cfg.sh_deg;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        const float u = __ldg(uv + 2 * s), v = __ldg(uv + 2 * s + 1);
+        float lw[kShMaxDeg + 1][4];
+        int corners[kShMaxDeg + 1];
+#pragma unroll
+        for (int g = 0; g <= kShMaxDeg; ++g) {
+            if (g > deg) continue;
+            corners[g] = cfg.geom[g].mode == 1 ? 4 : 1;
+            for (int k = 0; k < corners[g]; ++k) texel_query(cfg.geom[g], u, v, k, &lw[g][k]);
+        }
+        float P[16];
+        if (dirs != nullptr) sh_factors(__ldg(dirs + 3 * s), __ldg(dirs + 3 * s + 1), __ldg(dirs + 3 * s + 2), deg, P);
+
+        for (int ch = 0; ch < C; ++ch) {
+            // ---- forward: coefficients of this channel
+            float co[16];
+#pragma unroll
+            for (int g = 0; g <= kShMaxDeg; ++g) {
+                if (g > deg) continue;
+                const int nm = 2 * g + 1, width = C * nm;
+                const float* raw = cfg.raw[g] + (s * corners[g]) * width + ch * nm;
+#pragma unroll
+                for (int m = 0; m < 2 * kShMaxDeg + 1; ++m) {
+                    if (m >= nm) continue;
+                    float acc = 0.f;
+                    if (corners[g] == 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float t = __fmul_rn(texel_value(cfg, g, __ldg(raw + k * width + m), nullptr), lw[g][k]);
+                            acc = k == 0 ? t : __fadd_rn(acc, t);
+                        }
+                    } else {
+                        acc = texel_value(cfg, g, __ldg(raw + m), nullptr);
+                    }
+                    co[g * g + m] = acc;
+                }
+            }
+            if (!BWD && coeffs != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < NC) coeffs[(s * C + ch) * NC + k] = co[k];
+            }
+            if (dirs == nullptr && !BWD) continue;
+
+            float d_co[16];  // gradient of the fp32 coefficient tensor
+            if (dirs != nullptr) {
+                // SHEncoder.eval on fp16 coefficients: the degree-0 term is an fp16 product, everything after it is fp32
+                float r = round_half(__fmul_rn(round_half(co[0]), P[0]));
+                if (deg > 0) {
+                    r = __fsub_rn(r, __fmul_rn(P[1], round_half(co[1])));
+                    r = __fadd_rn(r, __fmul_rn(P[2], round_half(co[2])));
+                    r = __fsub_rn(r, __fmul_rn(P[3], round_half(co[3])));
+                }
+#pragma unroll
+                for (int k = 4; k < 16; ++k)
+                    if (k < NC) r = __fadd_rn(r, __fmul_rn(P[k], round_half(co[k])));
+                if (!BWD) {
+                    // sh_deg == 0: the result is still an fp16 tensor when it reaches torch.sigmoid
+                    const float o = sigmoid_precise(r);
+                    out[s * C + ch] = deg == 0 ? round_half(o) : o;
+                    continue;
+                }
+                // sigmoid backward (grad * (1 - y)) * y (in fp16 for sh_deg == 0), then the fp16 gradients of the fp16 coefficients
+                const float y = __ldg(out + s * C + ch);
+                float gr = __ldg(g_out + s * C + ch);
+                if (deg == 0) gr = round_half(gr);
+                gr = __fmul_rn(__fmul_rn(gr, __fsub_rn(1.f, y)), y);
+                if (deg == 0) gr = round_half(gr);
+                d_co[0] = round_half(__fmul_rn(round_half(gr), P[0]));
+#pragma unroll
+                for (int k = 1; k < 16; ++k)
+                    if (k < NC) {
+                        const float t = round_half(__fmul_rn(gr, P[k]));
+                        d_co[k] = (k == 1 || k == 3) ? -t : t;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < NC) d_co[k] = __ldg(g_coeffs + (s * C + ch) * NC + k);
+            }
+            // ---- backward through lerp / expansion / quantisation (STE) / sigmoid, per texel
+#pragma unroll
+            for (int g = 0; g <= kShMaxDeg; ++g) {
+                if (g > deg) continue;
+                const int nm = 2 * g + 1, width = C * nm;
+                const int64_t base = (s * corners[g]) * width + ch * nm;
+#pragma unroll
+                for (int m = 0; m < 2 * kShMaxDeg + 1; ++m) {
+                    if (m >= nm) continue;
+                    const float dc = d_co[g * g + m];
+                    for (int k = 0; k < corners[g]; ++k) {
+                        float gh = corners[g] == 4 ? round_half(__fmul_rn(dc, lw[g][k])) : round_half(dc);
+                        float sg = 0.f;
+                        if (cfg.squeeze) {
+                            texel_value(cfg, g, __ldg(cfg.raw[g] + base + k * width + m), &sg);
+                            gh = round_half(__fmul_rn(gh, cfg.range_mul[g]));
+                            if (cfg.quantize) gh = __fmul_rn(__fdiv_rn(gh, 255.0f), 255.0f);
+                            gh = __fmul_rn(__fmul_rn(gh, __fsub_rn(1.f, sg)), sg);
+                        }
+                        cfg.d_raw[g][base + k * width + m] = round_half(gh);  // the network's output is fp16: so is its gradient
+                    }
+                }
+            }
+        }
+    }
+}
+
+static int grid_for(int64_t work, int threads) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::min<int64_t>(std::max<int64_t>(div_up(work, threads), 1), (int64_t)sms * 16);
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+// Level table of the tiny-cuda-nn HashGrid (2-D): HOST arrays of n_levels entries (any may be NULL); returns the total number of
+// table entries (each n_features = 2 floats) or < 0.
+int64_t vs_hashgrid_levels(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, float* scale, int32_t* res,
+                           int32_t* size, int32_t* offset) {
+    HgLevels lv;
+    int e = hg_layout(n_levels, log2_hashmap_size, base_resolution, per_level_scale, &lv);
+    if (e != VS_OK) return e;
+    for (int l = 0; l < n_levels; ++l) {
+        if (scale) scale[l] = lv.scale[l];
+        if (res) res[l] = (int32_t)lv.res[l];
+        if (size) size[l] = (int32_t)lv.size[l];
+        if (offset) offset[l] = (int32_t)lv.offset[l];
+    }
+    return lv.total;
+}
+
+// features [rows, 2*n_levels] fp32 (fp16-representable), rows = n_samples * (mode == 1 ? 4 : 1), row = sample*corners + corner:
+// the hash-grid encoding of every texel query of NeuralTexture.forward (neural_texture.py:96-150).
+//   mode 0: anchor (texel centre)  1: lerp (4 corners)  2: uv as given (bake) · align: align_to_webgl · res_h/res_w: texture resolution
+//   uv [n_samples,2] fp32 · table [total_entries,2] fp32 master parameters (rounded to fp16 on the fly)
+int vs_hashgrid_forward(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, int mode, int align, int res_h,
+                        int res_w, const float* uv, const float* table, float* features, int64_t n_samples, const int64_t* n_valid_dev,
+                        void* stream) {
+    VS_CHECK_ARG(n_samples >= 0 && mode >= 0 && mode <= 2 && res_h > 0 && res_w > 0);
+    HgLevels lv;
+    int e = hg_layout(n_levels, log2_hashmap_size, base_resolution, per_level_scale, &lv);
+    if (e != VS_OK) return e;
+    if (n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(uv && table && features);
+    VS_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 7) == 0 && (reinterpret_cast<uintptr_t>(features) & 7) == 0);
+    const TexGeom tg{mode, align ? 1 : 0, res_h, res_w};
+    const int64_t work = n_samples * (mode == 1 ? 4 : 1) * n_levels;
+    hashgrid_encode_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(lv, tg, uv, reinterpret_cast<const float2*>(table), features,
+                                                                                  n_samples, n_valid_dev);
+    return launched(1);
+}
+
+// d_table [total_entries,2] fp32 += scatter of d_features (ACCUMULATES: zero it first).  Same arguments as vs_hashgrid_forward.
+int vs_hashgrid_backward(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale, int mode, int align, int res_h,
+                         int res_w, const float* uv, const float* d_features, float* d_table, int64_t n_samples, const int64_t* n_valid_dev,
+                         void* stream) {
+    VS_CHECK_ARG(n_samples >= 0 && mode >= 0 && mode <= 2 && res_h > 0 && res_w > 0);
+    HgLevels lv;
+    int e = hg_layout(n_levels, log2_hashmap_size, base_resolution, per_level_scale, &lv);
+    if (e != VS_OK) return e;
+    if (n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(uv && d_features && d_table);
+    VS_CHECK_ARG((reinterpret_cast<uintptr_t>(d_table) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_features) & 7) == 0);
+    const TexGeom tg{mode, align ? 1 : 0, res_h, res_w};
+    const int64_t work = n_samples * (mode == 1 ? 4 : 1) * n_levels;
+    hashgrid_backward_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(lv, tg, uv, d_features, reinterpret_cast<float2*>(d_table),
+                                                                                    n_samples, n_valid_dev);
+    return launched(1);
+}
+
+static int shtex_config(int sh_deg, int nr_channels, int mode, int align, const int* res_hw, const float* sh_range_lo,
+                        const float* sh_range_hi, int squeeze, int quantize, ShTexConfig* c) {
+    if (sh_deg < 0 || sh_deg > kShMaxDeg || nr_channels < 1 || nr_channels * (2 * sh_deg + 1) > 32 || !(mode == 0 || mode == 1) || !res_hw) return VS_ERR_INVALID_ARG;
+    if (squeeze && (!sh_range_lo || !sh_range_hi)) return VS_ERR_INVALID_ARG;
+    if (quantize && !squeeze) return VS_ERR_INVALID_ARG;  // sh_neural_textures.py:33-37
+    std::memset(c, 0, sizeof(*c));
+    c->sh_deg = sh_deg;
+    c->nr_channels = nr_channels;
+    c->n_coeffs = (sh_deg + 1) * (sh_deg + 1);
+    c->squeeze = squeeze ? 1 : 0;
+    c->quantize = quantize ? 1 : 0;
+    for (int g = 0; g <= sh_deg; ++g) {
+        if (res_hw[2 * g] <= 0 || res_hw[2 * g + 1] <= 0) return VS_ERR_INVALID_ARG;
+        c->geom[g] = TexGeom{mode, align ? 1 : 0, res_hw[2 * g], res_hw[2 * g + 1]};
+        if (squeeze) {
+            // val_range[0] + (val_range[1] - val_range[0]) * output on an fp16 tensor: python evaluates hi - lo in double; torch keeps the
+            // multiplier in fp32 and rounds the addend to fp16 (measured on torch 2.11 CPU; oracle/shtex.py runs the very expression)
+            c->range_mul[g] = (float)((double)sh_range_hi[g] - (double)sh_range_lo[g]);
+            c->range_lo[g] = __half2float(__float2half_rn(sh_range_lo[g]));
+        }
+    }
+    return VS_OK;
+}
+
+// SHNeuralTextures.forward after the networks (sh_neural_textures.py:71-97 + neural_texture.py:152-195).
+//   raw: HOST array of sh_deg+1 DEVICE pointers, raw[g] = [n_samples*corners, C*(2g+1)] fp32 network outputs (row = sample*corners + k)
+//   res_hw: HOST [sh_deg+1][2] (height, width) · range_lo/hi: HOST [sh_deg+1] val_range of every degree (NULL without squeeze)
+//   coeffs: [n_samples, C, (sh_deg+1)^2] fp32 or NULL · dirs [n_samples,3] + out [n_samples,C] or both NULL (view_dirs=None)
+int vs_shtex_combine_forward(int sh_deg, int nr_channels, int mode, int align, const int* res_hw, const float* range_lo, const float* range_hi,
+                             int squeeze, int quantize, const float* uv, const float* dirs, const float* const* raw, float* coeffs, float* out,
+                             int64_t n_samples, const int64_t* n_valid_dev, void* stream) {
+    VS_CHECK_ARG(n_samples >= 0 && raw);
+    ShTexConfig c;
+    int e = shtex_config(sh_deg, nr_channels, mode, align, res_hw, range_lo, range_hi, squeeze, quantize, &c);
+    if (e != VS_OK) return e;
+    if (n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(uv && (coeffs || out) && ((dirs == nullptr) == (out == nullptr)));
+    for (int g = 0; g <= sh_deg; ++g) {
+        VS_CHECK_ARG(raw[g]);
+        c.raw[g] = raw[g];
+    }
+    shtex_combine_kernel<false><<<grid_for(n_samples, 128), 128, 0, (cudaStream_t)stream>>>(c, uv, dirs, coeffs, out, nullptr, nullptr, n_samples,
+                                                                                            n_valid_dev);
+    return launched(1);
+}
+
+// Backward of vs_shtex_combine_forward: d_raw[g] (same shapes as raw[g], fully overwritten for live rows) from g_out [n_samples,C] (with
+// dirs + the forward's `out`) or, when dirs == NULL, from g_coeffs [n_samples,C,(sh_deg+1)^2].  Gradients of fp16 tensors are rounded
+// to fp16 where torch autograd rounds them.
+int vs_shtex_combine_backward(int sh_deg, int nr_channels, int mode, int align, const int* res_hw, const float* range_lo, const float* range_hi,
+                              int squeeze, int quantize, const float* uv, const float* dirs, const float* const* raw, const float* out,
+                              const float* g_out, const float* g_coeffs, float* const* d_raw, int64_t n_samples, const int64_t* n_valid_dev,
+                              void* stream) {
+    VS_CHECK_ARG(n_samples >= 0 && raw && d_raw);
+    ShTexConfig c;
+    int e = shtex_config(sh_deg, nr_channels, mode, align, res_hw, range_lo, range_hi, squeeze, quantize, &c);
+    if (e != VS_OK) return e;
+    if (n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(uv && (dirs ? (out && g_out) : g_coeffs != nullptr));
+    for (int g = 0; g <= sh_deg; ++g) {
+        VS_CHECK_ARG(raw[g] && d_raw[g]);
+        c.raw[g] = raw[g];
+        c.d_raw[g] = d_raw[g];
+    }
+    shtex_combine_kernel<true><<<grid_for(n_samples, 128), 128, 0, (cudaStream_t)stream>>>(c, uv, dirs, nullptr, const_cast<float*>(out), g_out,
+                                                                                           g_coeffs, n_samples, n_valid_dev);
+    return launched(1);
+}
+
+}  // extern "C"
