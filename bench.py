@@ -514,6 +514,16 @@ def run_ours(args, rank, world, local_rank):
     # this same workload (profiles/r01_mlp_fwd_v4.md, r01_mlp_bwd_v3.md, r01_shells_trace_v2.md); None where no capture exists
     ncu_traffic = {"mlp_rgb": 212.285952e6 + 1.274396e9, "mlp_alpha": 212.285952e6 + 1.274396e9, "mlp_bwd_rgb": 1.335758e9 + 188.86016e6,
                    "mlp_bwd_alpha": 1.335758e9 + 188.86016e6, "trace": 45.03552e6 + 22.207488e6}
+    if dom_kernel in ("mlp_fwd_kernel", "mlp_bwd_stashed_kernel"):
+        # the training-mode head kernels also stream the activation stash (what autograd keeps for the backward): their HBM view.
+        # forward: features in + stash out + outputs; backward: stash in + upstream gradient + forward output in, feature gradient out
+        stash_b = renderer.rgb_head.stash_bytes(n_hits)
+        io = n_hits * POS_DIM * 4 + n_hits * 2 * 4 * 2  # features (or their gradient) + rgb/alpha outputs or gradients (3 + 1 floats, mean 2)
+        hb = (stash_b + io) / (dom_ms * 1e-3) / 1e9
+        roofline["hbm_view"] = {"bound": "hbm", "achieved": round(hb, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(hb / pk["hbm_gbs"], 4),
+                                "bytes_per_launch": int(stash_b + io),
+                                "note": "same launch against the HBM roofline: activation stash + features + outputs (algorithmic bytes of a "
+                                        "training-mode launch); the kernel sits between its two rooflines (epilogue ALU bound)"}
     roofline.update(kernel=dom_kernel, traffic=ncu_traffic.get(dominant), peak_source=pk["source"],
                     note="algorithmic flops (or bytes) of one launch over the stage's mean CUDA-event duration inside the timed region "
                          "(event-record nodes of the replayed graph); traffic = DRAM bytes of one launch from the ncu capture in profiles/")

@@ -7,10 +7,11 @@
 //                                                    4 network queries, sigmoid, 8-bit quantisation (STE), fp16 re-expansion, lerp
 //   tiny-cuda-nn HashGrid encoding (neural_texture.py:54-63; 2-D, 16 levels x 2 features, 2^15 entries, base 16, scale 1.5)
 // with three kinds of kernels around the tensor-core network (vs_mlp_forward_raw / vs_mlp_backward_stashed_raw, csrc/mlp*.cu):
-//   hashgrid_encode_kernel   thread per (query row, level): texel-corner uv computed on the fly from the hit's uv, 4 gathers from the
-//                            L2-resident table (<= 2.8 MB per network), fp32 interpolation, fp16-rounded feature rows [rows, 32]
-//                            written as full 128-byte lines (16 consecutive threads = the 16 levels of one row)
-//   hashgrid_backward_kernel same mapping, vector atomics (red.global.add.v2.f32) into the table gradient
+//   hashgrid_encode_kernel   thread per query row: texel-corner uv computed on the fly from the hit's uv, 16 levels x 4 gathers from
+//                            the L2-resident table (<= 2.8 MB per network) in flight, fp32 interpolation, fp16-rounded feature row
+//                            [32] written as the thread's own 128-byte line
+//   hashgrid_backward_*      hashed levels: vector atomics (red.global.add.v2.f32) into the table gradient; coarse dense levels: one
+//                            shared-memory image of the levels per CTA (shared atomics), flushed once
 //   shtex_combine_*          thread per hit: the 4 corner outputs of every degree -> sigmoid -> quantise -> fp16 expansion -> lerp ->
 //                            fp16 coefficients -> mixed-precision SH evaluation -> sigmoid; the backward replays the same chain
 //                            including the fp16 roundings torch autograd applies to the gradients of fp16 tensors.
@@ -21,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "vs_common.cuh"
@@ -118,63 +120,119 @@ __device__ __forceinline__ void hg_corners(const HgLevels& lv, int level, float2
         const uint32_t cx = gx + (uint32_t)(c & 1), cy = gy + (uint32_t)((c >> 1) & 1);
         const float wx = (c & 1) ? rx : __fsub_rn(1.f, rx), wy = (c & 2) ? ry : __fsub_rn(1.f, ry);
         w[c] = __fmul_rn(wx, wy);
-        const uint32_t h = hashed ? (cx ^ (cy * 2654435761u)) : (cx + cy * res);
-        idx[c] = off + h % size;
+        // hashed levels own exactly 2^log2_hashmap_size entries; a dense index leaves [0, size) only at the texture border
+        uint32_t h;
+        if (hashed) {
+            h = (cx ^ (cy * 2654435761u)) & (size - 1u);
+        } else {
+            h = cx + cy * res;
+            if (h >= size) h %= size;
+        }
+        idx[c] = off + h;
     }
 }
 
 __device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
 
+// One thread per query row walks the levels: the texel query is evaluated once, the 4 x n_levels gathers of a row are independent
+// loads in flight, and the thread writes its own 128-byte feature row.
 __global__ void __launch_bounds__(256) hashgrid_encode_kernel(const HgLevels lv, const TexGeom tg, const float* __restrict__ uv,
                                                               const float2* __restrict__ table, float* __restrict__ feat, int64_t n_samples,
                                                               const int64_t* __restrict__ n_valid_dev) {
     int64_t n = n_samples;
     if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
-    const int corners = tg.mode == 1 ? 4 : 1;
+    const int csh = tg.mode == 1 ? 2 : 0;
     const int L = lv.n_levels;
-    const int64_t total = n * corners * L;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int level = (int)(t % L);
-        const int64_t row = t / L;
-        const int64_t s = row / corners;
-        const int k = (int)(row % corners);
+    const int64_t rows = n << csh;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = row >> csh;
+        const int k = (int)(row & ((1 << csh) - 1));
         const float2 q = texel_query(tg, __ldg(uv + 2 * s), __ldg(uv + 2 * s + 1), k, nullptr);
-        uint32_t idx[4];
-        float w[4];
-        hg_corners(lv, level, q, idx, w);
-        float a0 = 0.f, a1 = 0.f;
+        float2* dst = reinterpret_cast<float2*>(feat + row * (2 * L));
+#pragma unroll 4
+        for (int level = 0; level < L; ++level) {
+            uint32_t idx[4];
+            float w[4];
+            hg_corners(lv, level, q, idx, w);
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float2 e = __ldg(table + idx[c]);
-            const float t0 = __fmul_rn(w[c], round_half(e.x)), t1 = __fmul_rn(w[c], round_half(e.y));
-            a0 = c == 0 ? t0 : __fadd_rn(a0, t0);
-            a1 = c == 0 ? t1 : __fadd_rn(a1, t1);
+            for (int c = 0; c < 4; ++c) {
+                const float2 e = __ldg(table + idx[c]);
+                const float t0 = __fmul_rn(w[c], round_half(e.x)), t1 = __fmul_rn(w[c], round_half(e.y));
+                a0 = c == 0 ? t0 : __fadd_rn(a0, t0);
+                a1 = c == 0 ? t1 : __fadd_rn(a1, t1);
+            }
+            __stcs(dst + level, make_float2(round_half(a0), round_half(a1)));
         }
-        __stcs(reinterpret_cast<float2*>(feat + row * (2 * L) + 2 * level), make_float2(round_half(a0), round_half(a1)));
     }
 }
 
+// Backward, levels [lv_begin, lv_end) with atomics straight into the table gradient (the hashed levels: 2^15 entries each, collisions
+// between the threads of a warp are rare).
 __global__ void __launch_bounds__(256) hashgrid_backward_kernel(const HgLevels lv, const TexGeom tg, const float* __restrict__ uv,
                                                                 const float* __restrict__ d_feat, float2* __restrict__ d_table,
-                                                                int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
+                                                                int64_t n_samples, const int64_t* __restrict__ n_valid_dev, int lv_begin,
+                                                                int lv_end) {
     int64_t n = n_samples;
     if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
-    const int corners = tg.mode == 1 ? 4 : 1;
+    const int csh = tg.mode == 1 ? 2 : 0;
     const int L = lv.n_levels;
-    const int64_t total = n * corners * L;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int level = (int)(t % L);
-        const int64_t row = t / L;
-        const int64_t s = row / corners;
-        const int k = (int)(row % corners);
-        const float2 g = __ldcs(reinterpret_cast<const float2*>(d_feat + row * (2 * L) + 2 * level));
-        if (g.x == 0.f && g.y == 0.f) continue;
+    const int64_t rows = n << csh;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = row >> csh;
+        const int k = (int)(row & ((1 << csh) - 1));
         const float2 q = texel_query(tg, __ldg(uv + 2 * s), __ldg(uv + 2 * s + 1), k, nullptr);
-        uint32_t idx[4];
-        float w[4];
-        hg_corners(lv, level, q, idx, w);
+        const float2* src = reinterpret_cast<const float2*>(d_feat + row * (2 * L));
+#pragma unroll 2
+        for (int level = lv_begin; level < lv_end; ++level) {
+            const float2 g = __ldg(src + level);
+            if (g.x == 0.f && g.y == 0.f) continue;
+            uint32_t idx[4];
+            float w[4];
+            hg_corners(lv, level, q, idx, w);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(d_table + idx[c], make_float2(w[c] * g.x, w[c] * g.y));
+            for (int c = 0; c < 4; ++c) atomicAdd(d_table + idx[c], make_float2(w[c] * g.x, w[c] * g.y));
+        }
+    }
+}
+
+// Backward, the coarse (dense) levels [0, lv_end): a level with 256 entries receives rows*4 contributions, i.e. millions of atomics per
+// address if they go to global memory.  One persistent CTA per SM accumulates its share of the rows in a shared-memory image of those
+// levels (26 504 entries x 8 B = 207 KB for the reference's grid: levels 0-5) and flushes the image once.
+__global__ void __launch_bounds__(1024, 1) hashgrid_backward_dense_kernel(const HgLevels lv, const TexGeom tg, const float* __restrict__ uv,
+                                                                          const float* __restrict__ d_feat, float* __restrict__ d_table,
+                                                                          int64_t n_samples, const int64_t* __restrict__ n_valid_dev,
+                                                                          int lv_end, int n_entries) {
+    extern __shared__ float acc[];  // [n_entries][2]
+    for (int i = threadIdx.x; i < 2 * n_entries; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int csh = tg.mode == 1 ? 2 : 0;
+    const int L = lv.n_levels;
+    const int64_t rows = n << csh;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = row >> csh;
+        const int k = (int)(row & ((1 << csh) - 1));
+        const float2 q = texel_query(tg, __ldg(uv + 2 * s), __ldg(uv + 2 * s + 1), k, nullptr);
+        const float2* src = reinterpret_cast<const float2*>(d_feat + row * (2 * L));
+        for (int level = 0; level < lv_end; ++level) {
+            const float2 g = __ldg(src + level);
+            if (g.x == 0.f && g.y == 0.f) continue;
+            uint32_t idx[4];
+            float w[4];
+            hg_corners(lv, level, q, idx, w);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                atomicAdd(acc + 2 * idx[c], w[c] * g.x);
+                atomicAdd(acc + 2 * idx[c] + 1, w[c] * g.y);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * n_entries; i += blockDim.x) {
+        const float v = acc[i];
+        if (v != 0.f) atomicAdd(d_table + i, v);
     }
 }
 
@@ -238,119 +296,183 @@ __device__ __forceinline__ float texel_value(const ShTexConfig& c, int g, float 
     return h;
 }
 
+// One warp owns 32 consecutive hits.  Their network outputs are ONE contiguous chunk of every raw[g] (rows 4*s0 .. 4*s0+127, all
+// columns), so the warp copies the chunks into shared memory with unit-stride loads, every lane then works on its own hit out of shared
+// memory, and (backward) the gradients — written over the values they were computed from — leave as unit-stride stores.
+constexpr int kCombineWarps = 2;
+
 template <bool BWD>
-__global__ void __launch_bounds__(128) shtex_combine_kernel(const ShTexConfig cfg, const float* __restrict__ uv, const float* __restrict__ dirs,
-                                                            float* __restrict__ coeffs, float* __restrict__ out,
-                                                            const float* __restrict__ g_out, const float* __restrict__ g_coeffs,
-                                                            int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
+__global__ void __launch_bounds__(32 * kCombineWarps) shtex_combine_kernel(const ShTexConfig cfg, const float* __restrict__ uv,
+                                                                           const float* __restrict__ dirs, float* __restrict__ coeffs,
+                                                                           float* __restrict__ out, const float* __restrict__ g_out,
+                                                                           const float* __restrict__ g_coeffs, int64_t n_samples,
+                                                                           const int64_t* __restrict__ n_valid_dev, int warp_floats) {
+    extern __shared__ __align__(16) float sm_all[];
     int64_t n = n_samples;
     if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
     const int C = cfg.nr_channels, NC = cfg.n_coeffs, deg = cfg.sh_deg;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
-        const float u = __ldg(uv + 2 * s), v = __ldg(uv + 2 * s + 1);
-        float lw[kShMaxDeg + 1][4];
-        int corners[kShMaxDeg + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sm = sm_all + (size_t)warp * warp_floats;
+    int corners[kShMaxDeg + 1], chunk[kShMaxDeg + 1], soff[kShMaxDeg + 1];  // per hit: floats of degree g; start of the degree's image
+    {
+        int off = 0;
+#pragma unroll
+        for (int g = 0; g <= kShMaxDeg; ++g) {
+            corners[g] = chunk[g] = soff[g] = 0;
+            if (g > deg) continue;
+            corners[g] = cfg.geom[g].mode == 1 ? 4 : 1;
+            chunk[g] = corners[g] * C * (2 * g + 1);
+            soff[g] = off;
+            off += 32 * chunk[g];
+        }
+    }
+    const int64_t warp_stride = (int64_t)gridDim.x * kCombineWarps * 32;
+    for (int64_t s0 = ((int64_t)blockIdx.x * kCombineWarps + warp) * 32; s0 < n; s0 += warp_stride) {
+        const int cnt = (int)min((int64_t)32, n - s0);
+        // ---- network outputs of the warp's hits -> shared memory (unit stride)
 #pragma unroll
         for (int g = 0; g <= kShMaxDeg; ++g) {
             if (g > deg) continue;
-            corners[g] = cfg.geom[g].mode == 1 ? 4 : 1;
-            for (int k = 0; k < corners[g]; ++k) texel_query(cfg.geom[g], u, v, k, &lw[g][k]);
-        }
-        float P[16];
-        if (dirs != nullptr) sh_factors(__ldg(dirs + 3 * s), __ldg(dirs + 3 * s + 1), __ldg(dirs + 3 * s + 2), deg, P);
-
-        for (int ch = 0; ch < C; ++ch) {
-            // ---- forward: coefficients of this channel
-            float co[16];
-#pragma unroll
-            for (int g = 0; g <= kShMaxDeg; ++g) {
-                if (g > deg) continue;
-                const int nm = 2 * g + 1, width = C * nm;
-                const float* raw = cfg.raw[g] + (s * corners[g]) * width + ch * nm;
-#pragma unroll
-                for (int m = 0; m < 2 * kShMaxDeg + 1; ++m) {
-                    if (m >= nm) continue;
-                    float acc = 0.f;
-                    if (corners[g] == 4) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float t = __fmul_rn(texel_value(cfg, g, __ldg(raw + k * width + m), nullptr), lw[g][k]);
-                            acc = k == 0 ? t : __fadd_rn(acc, t);
-                        }
-                    } else {
-                        acc = texel_value(cfg, g, __ldg(raw + m), nullptr);
-                    }
-                    co[g * g + m] = acc;
-                }
-            }
-            if (!BWD && coeffs != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < NC) coeffs[(s * C + ch) * NC + k] = co[k];
-            }
-            if (dirs == nullptr && !BWD) continue;
-
-            float d_co[16];  // gradient of the fp32 coefficient tensor
-            if (dirs != nullptr) {
-                // SHEncoder.eval on fp16 coefficients: the degree-0 term is an fp16 product, everything after it is fp32
-                float r = round_half(__fmul_rn(round_half(co[0]), P[0]));
-                if (deg > 0) {
-                    r = __fsub_rn(r, __fmul_rn(P[1], round_half(co[1])));
-                    r = __fadd_rn(r, __fmul_rn(P[2], round_half(co[2])));
-                    r = __fsub_rn(r, __fmul_rn(P[3], round_half(co[3])));
-                }
-#pragma unroll
-                for (int k = 4; k < 16; ++k)
-                    if (k < NC) r = __fadd_rn(r, __fmul_rn(P[k], round_half(co[k])));
-                if (!BWD) {
-                    // sh_deg == 0: the result is still an fp16 tensor when it reaches torch.sigmoid
-                    const float o = sigmoid_precise(r);
-                    out[s * C + ch] = deg == 0 ? round_half(o) : o;
-                    continue;
-                }
-                // sigmoid backward (grad * (1 - y)) * y (in fp16 for sh_deg == 0), then the fp16 gradients of the fp16 coefficients
-                const float y = __ldg(out + s * C + ch);
-                float gr = __ldg(g_out + s * C + ch);
-                if (deg == 0) gr = round_half(gr);
-                gr = __fmul_rn(__fmul_rn(gr, __fsub_rn(1.f, y)), y);
-                if (deg == 0) gr = round_half(gr);
-                d_co[0] = round_half(__fmul_rn(round_half(gr), P[0]));
-#pragma unroll
-                for (int k = 1; k < 16; ++k)
-                    if (k < NC) {
-                        const float t = round_half(__fmul_rn(gr, P[k]));
-                        d_co[k] = (k == 1 || k == 3) ? -t : t;
-                    }
+            const float* src = cfg.raw[g] + s0 * chunk[g];
+            const int total = cnt * chunk[g];
+            if ((chunk[g] & 3) == 0) {
+                const float4* src4 = reinterpret_cast<const float4*>(src);
+                float4* dst4 = reinterpret_cast<float4*>(sm + soff[g]);
+                for (int i = lane; i < total / 4; i += 32) dst4[i] = __ldcs(src4 + i);
             } else {
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < NC) d_co[k] = __ldg(g_coeffs + (s * C + ch) * NC + k);
+                for (int i = lane; i < total; i += 32) sm[soff[g] + i] = __ldcs(src + i);
             }
-            // ---- backward through lerp / expansion / quantisation (STE) / sigmoid, per texel
+        }
+        __syncwarp();
+        const int64_t s = s0 + lane;
+        if (lane < cnt) {
+            const float u = __ldg(uv + 2 * s), v = __ldg(uv + 2 * s + 1);
+            float lw[kShMaxDeg + 1][4];
 #pragma unroll
             for (int g = 0; g <= kShMaxDeg; ++g) {
                 if (g > deg) continue;
-                const int nm = 2 * g + 1, width = C * nm;
-                const int64_t base = (s * corners[g]) * width + ch * nm;
+                for (int k = 0; k < corners[g]; ++k) texel_query(cfg.geom[g], u, v, k, &lw[g][k]);
+            }
+            float P[16];
+            if (dirs != nullptr) sh_factors(__ldg(dirs + 3 * s), __ldg(dirs + 3 * s + 1), __ldg(dirs + 3 * s + 2), deg, P);
+
+            for (int ch = 0; ch < C; ++ch) {
+                // ---- forward: coefficients of this channel
+                float co[16];
 #pragma unroll
-                for (int m = 0; m < 2 * kShMaxDeg + 1; ++m) {
-                    if (m >= nm) continue;
-                    const float dc = d_co[g * g + m];
-                    for (int k = 0; k < corners[g]; ++k) {
-                        float gh = corners[g] == 4 ? round_half(__fmul_rn(dc, lw[g][k])) : round_half(dc);
-                        float sg = 0.f;
-                        if (cfg.squeeze) {
-                            texel_value(cfg, g, __ldg(cfg.raw[g] + base + k * width + m), &sg);
-                            gh = round_half(__fmul_rn(gh, cfg.range_mul[g]));
-                            if (cfg.quantize) gh = __fmul_rn(__fdiv_rn(gh, 255.0f), 255.0f);
-                            gh = __fmul_rn(__fmul_rn(gh, __fsub_rn(1.f, sg)), sg);
+                for (int g = 0; g <= kShMaxDeg; ++g) {
+                    if (g > deg) continue;
+                    const int nm = 2 * g + 1, width = C * nm;
+                    const float* raw = sm + soff[g] + lane * chunk[g] + ch * nm;
+#pragma unroll
+                    for (int m = 0; m < 2 * kShMaxDeg + 1; ++m) {
+                        if (m >= nm) continue;
+                        float acc = 0.f;
+                        if (corners[g] == 4) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float t = __fmul_rn(texel_value(cfg, g, raw[k * width + m], nullptr), lw[g][k]);
+                                acc = k == 0 ? t : __fadd_rn(acc, t);
+                            }
+                        } else {
+                            acc = texel_value(cfg, g, raw[m], nullptr);
                         }
-                        cfg.d_raw[g][base + k * width + m] = round_half(gh);  // the network's output is fp16: so is its gradient
+                        co[g * g + m] = acc;
+                    }
+                }
+                if (!BWD && coeffs != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < NC) coeffs[(s * C + ch) * NC + k] = co[k];
+                }
+                if (dirs == nullptr && !BWD) continue;
+
+                float d_co[16];  // gradient of the fp32 coefficient tensor
+                if (dirs != nullptr) {
+                    // SHEncoder.eval on fp16 coefficients: the degree-0 term is an fp16 product, everything after it is fp32
+                    float r = round_half(__fmul_rn(round_half(co[0]), P[0]));
+                    if (deg > 0) {
+                        r = __fsub_rn(r, __fmul_rn(P[1], round_half(co[1])));
+                        r = __fadd_rn(r, __fmul_rn(P[2], round_half(co[2])));
+                        r = __fsub_rn(r, __fmul_rn(P[3], round_half(co[3])));
+                    }
+#pragma unroll
+                    for (int k = 4; k < 16; ++k)
+                        if (k < NC) r = __fadd_rn(r, __fmul_rn(P[k], round_half(co[k])));
+                    if (!BWD) {
+                        // sh_deg == 0: the result is still an fp16 tensor when it reaches torch.sigmoid
+                        const float o = sigmoid_precise(r);
+                        out[s * C + ch] = deg == 0 ? round_half(o) : o;
+                        continue;
+                    }
+                    // sigmoid backward (grad * (1 - y)) * y (in fp16 for sh_deg == 0), then the fp16 gradients of the fp16 coefficients
+                    const float y = __ldg(out + s * C + ch);
+                    float gr = __ldg(g_out + s * C + ch);
+                    if (deg == 0) gr = round_half(gr);
+                    gr = __fmul_rn(__fmul_rn(gr, __fsub_rn(1.f, y)), y);
+                    if (deg == 0) gr = round_half(gr);
+                    d_co[0] = round_half(__fmul_rn(round_half(gr), P[0]));
+#pragma unroll
+                    for (int k = 1; k < 16; ++k)
+                        if (k < NC) {
+                            const float t = round_half(__fmul_rn(gr, P[k]));
+                            d_co[k] = (k == 1 || k == 3) ? -t : t;
+                        }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < NC) d_co[k] = __ldg(g_coeffs + (s * C + ch) * NC + k);
+                }
+                // ---- backward through lerp / expansion / quantisation (STE) / sigmoid, per texel; the gradient replaces the value
+#pragma unroll
+                for (int g = 0; g <= kShMaxDeg; ++g) {
+                    if (g > deg) continue;
+                    const int nm = 2 * g + 1, width = C * nm;
+                    float* raw = sm + soff[g] + lane * chunk[g] + ch * nm;
+#pragma unroll
+                    for (int m = 0; m < 2 * kShMaxDeg + 1; ++m) {
+                        if (m >= nm) continue;
+                        const float dc = d_co[g * g + m];
+                        for (int k = 0; k < corners[g]; ++k) {
+                            float gh = corners[g] == 4 ? round_half(__fmul_rn(dc, lw[g][k])) : round_half(dc);
+                            float sg = 0.f;
+                            if (cfg.squeeze) {
+                                texel_value(cfg, g, raw[k * width + m], &sg);
+                                gh = round_half(__fmul_rn(gh, cfg.range_mul[g]));
+                                if (cfg.quantize) gh = __fmul_rn(__fdiv_rn(gh, 255.0f), 255.0f);
+                                gh = __fmul_rn(__fmul_rn(gh, __fsub_rn(1.f, sg)), sg);
+                            }
+                            raw[k * width + m] = round_half(gh);  // the network's output is fp16: so is its gradient
+                        }
                     }
                 }
             }
+        }
+        __syncwarp();
+        if (BWD) {
+#pragma unroll
+            for (int g = 0; g <= kShMaxDeg; ++g) {
+                if (g > deg) continue;
+                float* dst = cfg.d_raw[g] + s0 * chunk[g];
+                const int total = cnt * chunk[g];
+                if ((chunk[g] & 3) == 0) {
+                    float4* dst4 = reinterpret_cast<float4*>(dst);
+                    const float4* src4 = reinterpret_cast<const float4*>(sm + soff[g]);
+                    for (int i = lane; i < total / 4; i += 32) __stcs(dst4 + i, src4[i]);
+                } else {
+                    for (int i = lane; i < total; i += 32) __stcs(dst + i, sm[soff[g] + i]);
+                }
+            }
+            __syncwarp();
         }
     }
+}
+
+// shared memory of one warp: the network outputs of its 32 hits, all degrees
+static int combine_warp_floats(const ShTexConfig& c) {
+    int f = 0;
+    for (int g = 0; g <= c.sh_deg; ++g) f += 32 * (c.geom[g].mode == 1 ? 4 : 1) * c.nr_channels * (2 * g + 1);
+    return (f + 3) & ~3;
 }
 
 static int grid_for(int64_t work, int threads) {
@@ -397,7 +519,7 @@ int vs_hashgrid_forward(int n_levels, int log2_hashmap_size, int base_resolution
     VS_CHECK_ARG(uv && table && features);
     VS_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 7) == 0 && (reinterpret_cast<uintptr_t>(features) & 7) == 0);
     const TexGeom tg{mode, align ? 1 : 0, res_h, res_w};
-    const int64_t work = n_samples * (mode == 1 ? 4 : 1) * n_levels;
+    const int64_t work = n_samples * (mode == 1 ? 4 : 1);
     hashgrid_encode_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(lv, tg, uv, reinterpret_cast<const float2*>(table), features,
                                                                                   n_samples, n_valid_dev);
     return launched(1);
@@ -415,10 +537,37 @@ int vs_hashgrid_backward(int n_levels, int log2_hashmap_size, int base_resolutio
     VS_CHECK_ARG(uv && d_features && d_table);
     VS_CHECK_ARG((reinterpret_cast<uintptr_t>(d_table) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_features) & 7) == 0);
     const TexGeom tg{mode, align ? 1 : 0, res_h, res_w};
-    const int64_t work = n_samples * (mode == 1 ? 4 : 1) * n_levels;
-    hashgrid_backward_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(lv, tg, uv, d_features, reinterpret_cast<float2*>(d_table),
-                                                                                    n_samples, n_valid_dev);
-    return launched(1);
+    const int corners = mode == 1 ? 4 : 1;
+    // the leading dense levels whose shared-memory image fits one CTA go through the accumulating kernel
+    int dense_end = 0, dense_entries = 0;
+    while (dense_end < n_levels && !lv.hashed[dense_end] && (int64_t)(dense_entries + lv.size[dense_end]) * 8 <= 216 * 1024) {
+        dense_entries += (int)lv.size[dense_end];
+        ++dense_end;
+    }
+    if (const char* env = std::getenv("VS_HASHGRID_BWD_DENSE")) {  // A/B knob: 0 = everything through global atomics
+        if (std::atoi(env) == 0) dense_end = dense_entries = 0;
+    }
+    int launches = 0;
+    if (dense_end > 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int smem = dense_entries * 8;
+        cudaError_t ce = cudaFuncSetAttribute(hashgrid_backward_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (ce != cudaSuccess) return (int)ce;
+        const int64_t work = n_samples * corners;
+        const int grid = (int)std::min<int64_t>(std::max<int64_t>(div_up(work, 1024), 1), sms);
+        hashgrid_backward_dense_kernel<<<grid, 1024, smem, (cudaStream_t)stream>>>(lv, tg, uv, d_features, d_table, n_samples, n_valid_dev,
+                                                                                   dense_end, dense_entries);
+        ++launches;
+    }
+    if (dense_end < n_levels) {
+        const int64_t work = n_samples * corners;
+        hashgrid_backward_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(lv, tg, uv, d_features, reinterpret_cast<float2*>(d_table),
+                                                                                        n_samples, n_valid_dev, dense_end, n_levels);
+        ++launches;
+    }
+    return launched(launches);
 }
 
 static int shtex_config(int sh_deg, int nr_channels, int mode, int align, const int* res_hw, const float* sh_range_lo,
@@ -462,8 +611,11 @@ int vs_shtex_combine_forward(int sh_deg, int nr_channels, int mode, int align, c
         VS_CHECK_ARG(raw[g]);
         c.raw[g] = raw[g];
     }
-    shtex_combine_kernel<false><<<grid_for(n_samples, 128), 128, 0, (cudaStream_t)stream>>>(c, uv, dirs, coeffs, out, nullptr, nullptr, n_samples,
-                                                                                            n_valid_dev);
+    const int wf = combine_warp_floats(c), smem = wf * 4 * kCombineWarps;
+    cudaError_t ce = cudaFuncSetAttribute(shtex_combine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) return (int)ce;
+    shtex_combine_kernel<false><<<grid_for(n_samples, 32 * kCombineWarps), 32 * kCombineWarps, smem, (cudaStream_t)stream>>>(
+        c, uv, dirs, coeffs, out, nullptr, nullptr, n_samples, n_valid_dev, wf);
     return launched(1);
 }
 
@@ -485,8 +637,11 @@ int vs_shtex_combine_backward(int sh_deg, int nr_channels, int mode, int align, 
         c.raw[g] = raw[g];
         c.d_raw[g] = d_raw[g];
     }
-    shtex_combine_kernel<true><<<grid_for(n_samples, 128), 128, 0, (cudaStream_t)stream>>>(c, uv, dirs, nullptr, const_cast<float*>(out), g_out,
-                                                                                           g_coeffs, n_samples, n_valid_dev);
+    const int wf = combine_warp_floats(c), smem = wf * 4 * kCombineWarps;
+    cudaError_t ce = cudaFuncSetAttribute(shtex_combine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) return (int)ce;
+    shtex_combine_kernel<true><<<grid_for(n_samples, 32 * kCombineWarps), 32 * kCombineWarps, smem, (cudaStream_t)stream>>>(
+        c, uv, dirs, nullptr, const_cast<float*>(out), g_out, g_coeffs, n_samples, n_valid_dev, wf);
     return launched(1);
 }
 
