@@ -94,7 +94,42 @@ def build_ref_permuto(force: bool = False):
     return PERMUTO_LIB
 
 
+# ---- oracle/_ref: the reference's ray-sampler / occupancy-grid kernels behind a C harness -------------------------------------
+SAMPLER_SRC = HERE / "ref_sampler_harness.cu"
+SAMPLER_LIB = REF_DIR / "libsampler_ref.so"
+SAMPLER_HDRS = [REFERENCE / "kernels/volsurfs/RaySamplerGPU.cuh", REFERENCE / "kernels/volsurfs/OccupancyGridGPU.cuh",
+                REFERENCE / "kernels/volsurfs/occ_grid_helpers.h"]
+
+
+def sampler_ref_available() -> bool:
+    return SAMPLER_LIB.exists()
+
+
+def build_ref_sampler(force: bool = False):
+    """nvcc-compile oracle/ref_sampler_harness.cu, which #includes the reference's RaySamplerGPU.cuh and OccupancyGridGPU.cuh from where
+    they lie (nothing is copied; Eigen::Vector3f is replaced by a 3-float stand-in declared in the harness), for sm_100a into
+    oracle/_ref/libsampler_ref.so.  Default nvcc floating-point flags (FMA contraction on), as in the reference's CMake build.
+    Returns None when the reference tree is not mounted (GPU box): the prebuilt .so is used as is."""
+    if not SAMPLER_HDRS[0].exists():
+        return SAMPLER_LIB if SAMPLER_LIB.exists() else None
+    deps = [SAMPLER_SRC, *SAMPLER_HDRS]
+    if SAMPLER_LIB.exists() and not force and all(SAMPLER_LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return SAMPLER_LIB
+    from torch.utils.cpp_extension import include_paths
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    REF_DIR.mkdir(exist_ok=True)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+           "-shared", "-w", f"-I{REFERENCE / 'kernels'}", f"-I{REFERENCE / 'include'}", *[f"-I{p}" for p in include_paths()],
+           "-D_GLIBCXX_USE_CXX11_ABI=1", str(SAMPLER_SRC), "-o", str(SAMPLER_LIB), "-lcudart"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on the sampler reference harness:\n{res.stdout[-4000:]}")
+    return SAMPLER_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_ref())
     print(build_ref_permuto())
+    print(build_ref_sampler())

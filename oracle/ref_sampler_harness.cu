@@ -1,0 +1,132 @@
+// ORACLE (test infrastructure only — never linked into or loaded by the product).
+//
+// A thin C harness around the REFERENCE's own ray-sampling and occupancy-grid kernels: it #includes
+//   /root/reference/kernels/volsurfs/RaySamplerGPU.cuh        (compute_samples_bg / _fg / _fg_in_grid_occupied_regions)
+//   /root/reference/kernels/volsurfs/OccupancyGridGPU.cuh     (get_rays_t_near_t_far, check_occupancy)
+//   /root/reference/kernels/volsurfs/occ_grid_helpers.h       (pos_to_lin_idx, distance_to_next_voxel; pulled in by the two above)
+// unmodified, where they lie, and launches them with the launch shape of src/RaySampler.cu / src/OccupancyGrid.cu
+// (blocks = div_round_up(n, 256), 256 threads, legacy stream, device synchronise).
+// Those headers use Eigen::Vector3f only as a 3-float parameter type (x(), y(), z()); Eigen is not installed in this image and cannot
+// be downloaded, so a 3-float stand-in with those three accessors is declared below — it is the harness's own code, not a copy.
+// Built by oracle/build.py into oracle/_ref/libsampler_ref.so (git-ignored; travels to the GPU box with the snapshot), with nvcc's
+// default floating-point flags (FMA contraction on), as the reference's own CMake build does.
+#include <cstdint>
+
+namespace Eigen {
+struct Vector3f {
+    float v[3];
+    __host__ __device__ Vector3f() : v{0.f, 0.f, 0.f} {}
+    __host__ __device__ Vector3f(float a, float b, float c) : v{a, b, c} {}
+    __host__ __device__ float x() const { return v[0]; }
+    __host__ __device__ float y() const { return v[1]; }
+    __host__ __device__ float z() const { return v[2]; }
+    // used by a kernel this harness never launches (update_grid_occupancy_with_sdf_values); needed for the header to compile
+    __host__ __device__ Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
+};
+}  // namespace Eigen
+
+#include "volsurfs/RaySamplerGPU.cuh"
+#undef BLOCK_SIZE
+#include "volsurfs/OccupancyGridGPU.cuh"
+
+namespace {
+
+template <typename T, int N>
+using Acc = torch::PackedTensorAccessor32<T, N, torch::RestrictPtrTraits>;
+
+template <typename T>
+Acc<T, 1> acc1(const T* p, int64_t n) {
+    const int64_t sizes[1] = {n}, strides[1] = {1};
+    return Acc<T, 1>(const_cast<T*>(p), sizes, strides);
+}
+template <typename T>
+Acc<T, 2> acc2(const T* p, int64_t rows, int64_t cols) {
+    const int64_t sizes[2] = {rows, cols}, strides[2] = {cols, 1};
+    return Acc<T, 2>(const_cast<T*>(p), sizes, strides);
+}
+template <typename T>
+Acc<T, 3> acc3(const T* p, int64_t a, int64_t b, int64_t c) {
+    const int64_t sizes[3] = {a, b, c}, strides[3] = {b * c, c, 1};
+    return Acc<T, 3>(const_cast<T*>(p), sizes, strides);
+}
+
+inline dim3 grid_for(int n) { return dim3((unsigned)((n + 255) / 256), 1, 1); }
+
+inline int finish() {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return (int)e;
+}
+
+inline pcg32 make_rng(uint64_t state, uint64_t inc) {
+    pcg32 rng;
+    rng.state = state;
+    rng.inc = inc;
+    return rng;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_sampler_abi_version() { return 1; }
+
+// RaySampler.cu:72-157
+int ref_samples_bg(const float* rays_o, const float* rays_d, const float* t_start, float t_far, int nr_samples_per_ray, uint64_t rng_state,
+                   uint64_t rng_inc, int jitter, float* ray_max_dt, float* s3d, float* sdirs, float* sz, float* sdt, int* se, int nr_rays) {
+    RaySamplerGPU::compute_samples_bg_gpu<<<grid_for(nr_rays), 256>>>(
+        nr_rays, nr_samples_per_ray, acc2(rays_o, nr_rays, 3), acc2(rays_d, nr_rays, 3), acc2(t_start, nr_rays, 1), t_far,
+        make_rng(rng_state, rng_inc), jitter != 0, acc2(ray_max_dt, nr_rays, 1), acc3(s3d, nr_rays, nr_samples_per_ray, 3),
+        acc3(sdirs, nr_rays, nr_samples_per_ray, 3), acc2(sz, nr_rays, nr_samples_per_ray), acc2(sdt, nr_rays, nr_samples_per_ray),
+        acc2(se, nr_rays, 2));
+    return finish();
+}
+
+// RaySampler.cu:159-245 (before compact_to_valid_samples)
+int ref_samples_fg(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, float min_dist, int min_nr, int max_nr,
+                   uint64_t rng_state, uint64_t rng_inc, int jitter, float* ray_max_dt, int* sidx, float* s3d, float* sdirs, float* sz,
+                   float* sdt, int* se, int nr_rays) {
+    const int64_t cap = (int64_t)nr_rays * max_nr;
+    RaySamplerGPU::compute_samples_fg_gpu<<<grid_for(nr_rays), 256>>>(
+        nr_rays, acc2(rays_o, nr_rays, 3), acc2(rays_d, nr_rays, 3), acc2(t_entry, nr_rays, 1), acc2(t_exit, nr_rays, 1), min_dist, min_nr,
+        max_nr, (int)cap, make_rng(rng_state, rng_inc), jitter != 0, acc2(ray_max_dt, nr_rays, 1), acc2(sidx, cap, 1), acc2(s3d, cap, 3),
+        acc2(sdirs, cap, 3), acc2(sz, cap, 1), acc2(sdt, cap, 1), acc2(se, nr_rays, 2));
+    return finish();
+}
+
+// RaySampler.cu:247-340 (before compact_to_valid_samples)
+int ref_samples_fg_occupied(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, float min_dist, int min_nr,
+                            int max_nr, uint64_t rng_state, uint64_t rng_inc, int jitter, int nr_voxels_per_dim, const float* extent,
+                            const bool* occupancy, const bool* roi, float* ray_max_dt, int* sidx, float* s3d, float* sdirs, float* sz,
+                            float* sdt, int* se, int nr_rays) {
+    const int64_t cap = (int64_t)nr_rays * max_nr;
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    RaySamplerGPU::compute_samples_fg_in_grid_occupied_regions_gpu<<<grid_for(nr_rays), 256>>>(
+        nr_rays, acc2(rays_o, nr_rays, 3), acc2(rays_d, nr_rays, 3), acc2(t_entry, nr_rays, 1), acc2(t_exit, nr_rays, 1), min_dist, min_nr,
+        max_nr, (int)cap, make_rng(rng_state, rng_inc), jitter != 0, nr_voxels_per_dim, Eigen::Vector3f(extent[0], extent[1], extent[2]),
+        acc1(occupancy, nv), acc1(roi, nv), acc2(ray_max_dt, nr_rays, 1), acc2(sidx, cap, 1), acc2(s3d, cap, 3), acc2(sdirs, cap, 3),
+        acc2(sz, cap, 1), acc2(sdt, cap, 1), acc2(se, nr_rays, 2));
+    return finish();
+}
+
+// OccupancyGrid.cu: get_rays_t_near_t_far
+int ref_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
+                          const float* extent, const bool* occupancy, const bool* roi, float* t_near, float* t_far, int nr_rays) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::get_rays_t_near_t_far_gpu<<<grid_for(nr_rays), 256>>>(
+        nr_rays, acc2(rays_o, nr_rays, 3), acc2(rays_d, nr_rays, 3), acc2(t_entry, nr_rays, 1), acc2(t_exit, nr_rays, 1), nr_voxels_per_dim,
+        Eigen::Vector3f(extent[0], extent[1], extent[2]), acc1(occupancy, nv), acc1(roi, nv), acc2(t_near, nr_rays, 1), acc2(t_far, nr_rays, 1));
+    return finish();
+}
+
+// OccupancyGrid.cu: check_occupancy
+int ref_check_occupancy(const float* points, int nr_voxels_per_dim, const float* extent, const float* values, const bool* occupancy,
+                        const bool* roi, bool* out_occ, float* out_val, int nr_points) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::check_occupancy_gpu<<<grid_for(nr_points), 256>>>(
+        nr_points, nr_voxels_per_dim, Eigen::Vector3f(extent[0], extent[1], extent[2]), acc1(values, nv), acc1(occupancy, nv), acc1(roi, nv),
+        acc2(points, nr_points, 3), acc2(out_occ, nr_points, 1), acc2(out_val, nr_points, 1));
+    return finish();
+}
+
+}  // extern "C"

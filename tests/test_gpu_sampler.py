@@ -1,0 +1,228 @@
+"""GPU parity of the ray samplers and occupancy-grid queries through the PyBridge-shaped shim / C ABI:
+
+  * against the numpy restatement (oracle/sampler.py) on small cases ............................ bit-exact, every field
+  * against the REFERENCE'S OWN KERNELS (oracle/_ref/libsampler_ref.so = RaySamplerGPU.cuh + OccupancyGridGPU.cuh compiled unmodified
+    behind oracle/ref_sampler_harness.cu) at 20k rays x 64^3 voxels, compacted like the reference does ......... bit-exact, every field
+
+Index work (ray_start_end_idx, samples_idx) and fp32 sample positions / depths are all held to bit equality: the product follows the
+reference's operation order including the contractions nvcc applies to it."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import sampler as osamp
+from oracle.importance import PCG_DEFAULT_INC, PCG_DEFAULT_STATE, Pcg32
+from sampler_scene import make_scene
+
+pytestmark = pytest.mark.gpu
+REF_PATH = ROOT / "oracle" / "_ref" / "libsampler_ref.so"
+FIELDS = ("ray_start_end_idx", "samples_idx", "samples_3d", "samples_dirs", "samples_z", "samples_dt", "ray_max_dt")
+
+
+def _reset_rng():
+    from volsurfs_b200.volsurfs import RaySampler
+
+    RaySampler._rng_state, RaySampler._rng_inc = PCG_DEFAULT_STATE, PCG_DEFAULT_INC
+
+
+def _cuda_scene(sc):
+    t = {k: torch.from_numpy(np.ascontiguousarray(sc[k])).cuda() for k in ("o", "d", "t_entry", "t_exit", "occ", "roi", "vals")}
+    return t
+
+
+def _assert_packet_equal(got, want, what):
+    for k in FIELDS:
+        g = getattr(got, k).cpu().numpy() if not isinstance(got, dict) else got[k]
+        w = want[k]
+        assert g.shape == w.shape, (what, k, g.shape, w.shape)
+        assert np.array_equal(g, w), (what, k, int((g != w).sum()), "of", g.size)
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("use_grid", [False, True])
+def test_fg_samplers_match_restatement(use_grid, jitter):
+    from volsurfs_b200.volsurfs import RaySampler
+
+    sc = make_scene(300, 16, seed=11)
+    t = _cuda_scene(sc)
+    _reset_rng()
+    min_dist, min_nr, max_nr = 0.03, 2, 48
+    if use_grid:
+        got = RaySampler.compute_samples_fg_in_grid_occupied_regions(t["o"], t["d"], t["t_entry"], t["t_exit"], min_dist, min_nr, max_nr, jitter,
+                                                                    sc["n"], sc["extent"], t["occ"], t["roi"], 1)
+        grid = osamp.Grid(sc["n"], sc["extent"], sc["occ"], sc["roi"])
+    else:
+        got = RaySampler.compute_samples_fg(t["o"], t["d"], t["t_entry"], t["t_exit"], min_dist, min_nr, max_nr, jitter, 1)
+        grid = None
+    want = osamp.compact(osamp.samples_fg(sc["o"], sc["d"], sc["t_entry"], sc["t_exit"], min_dist, min_nr, max_nr, jitter=jitter, rng=Pcg32(),
+                                          grid=grid))
+    assert got.is_compacted and got.get_total_nr_samples() == want["samples_z"].shape[0] > 100
+    _assert_packet_equal(got, want, f"grid={use_grid} jitter={jitter}")
+    assert np.array_equal(got.ray_o.cpu().numpy(), sc["o"]) and np.array_equal(got.ray_exit.cpu().numpy(), sc["t_exit"])
+    assert got.samples_values.shape == (got.get_total_nr_samples(), 1) and float(got.samples_values.max()) == -1.0
+    # the static generator moves on by 2^32 after a jittered call (RaySampler.cu:228-231)
+    g = Pcg32()
+    if jitter:
+        g.advance(1 << 32)
+    assert RaySampler._rng_state == g.state
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+def test_bg_sampler_matches_restatement(jitter):
+    from volsurfs_b200.volsurfs import RaySampler
+
+    sc = make_scene(200, 16, seed=12)
+    t = _cuda_scene(sc)
+    _reset_rng()
+    got = RaySampler.compute_samples_bg(t["o"], t["d"], t["t_exit"], 40.0, 24, jitter)
+    want = osamp.samples_bg(sc["o"], sc["d"], sc["t_exit"], 40.0, 24, jitter=jitter, rng=Pcg32())
+    for k in ("ray_start_end_idx", "samples_3d", "samples_dirs", "samples_z", "ray_max_dt"):
+        assert np.array_equal(getattr(got, k).cpu().numpy(), want[k]), k
+    assert float(got.ray_exit.min()) == 40.0 and got.get_values_dim() == 0
+
+
+def test_occupancy_grid_queries_match_restatement():
+    from volsurfs_b200.volsurfs import OccupancyGrid
+
+    sc = make_scene(300, 16, seed=13)
+    t = _cuda_scene(sc)
+    og = OccupancyGrid(sc["n"], sc["extent"])
+    assert og.get_nr_voxels() == 16 ** 3 and og.get_nr_occupied_voxels() == 16 ** 3
+    og.set_grid_occupancy(t["occ"])
+    og.set_grid_roi(t["roi"])
+    og.set_grid_values(t["vals"])
+    assert og.get_nr_occupied_voxels_in_roi() == int((sc["occ"] & sc["roi"]).sum())
+    grid = osamp.Grid(sc["n"], sc["extent"], sc["occ"], sc["roi"], sc["vals"])
+    near, far = og.get_rays_t_near_t_far(t["o"], t["d"], t["t_entry"], t["t_exit"])
+    wn, wf = osamp.rays_t_near_t_far(sc["o"], sc["d"], sc["t_entry"], sc["t_exit"], grid)
+    assert np.array_equal(near.cpu().numpy(), wn) and np.array_equal(far.cpu().numpy(), wf)
+    pts = (np.random.RandomState(1).rand(2000, 3).astype(np.float32) - 0.5) * 1.6
+    occ, val = og.check_occupancy(torch.from_numpy(pts).cuda())
+    wo, wv = osamp.check_occupancy(pts, grid)
+    assert occ.dtype == torch.bool and np.array_equal(occ.cpu().numpy(), wo) and np.array_equal(val.cpu().numpy(), wv)
+    with pytest.raises(RuntimeError):
+        OccupancyGrid(12, [1, 1, 1])
+
+
+# ---- the reference's own kernels ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref():
+    if not REF_PATH.exists():
+        pytest.skip("oracle/_ref/libsampler_ref.so not built (python -m oracle.build where /root/reference is mounted)")
+    lib = ctypes.CDLL(str(REF_PATH))
+    assert lib.ref_sampler_abi_version() == 1
+    return lib
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _ref_fg(ref, sc, t, min_dist, min_nr, max_nr, jitter, use_grid):
+    """the reference kernel into an uncompacted packet (constructor fills of src/RaySamplesPacked.cu:13-48), then compacted"""
+    from volsurfs_b200.volsurfs import RaySamplesPacked
+
+    n = sc["o"].shape[0]
+    unc = RaySamplesPacked(n, n * max_nr, 0, 1)
+    unc.is_compacted = False
+    unc.ray_o, unc.ray_d, unc.ray_enter, unc.ray_exit = t["o"].clone(), t["d"].clone(), t["t_entry"].clone(), t["t_exit"].clone()
+    common = [P(t["o"]), P(t["d"]), P(t["t_entry"]), P(t["t_exit"]), ctypes.c_float(min_dist), min_nr, max_nr, ctypes.c_uint64(PCG_DEFAULT_STATE),
+              ctypes.c_uint64(PCG_DEFAULT_INC), int(jitter)]
+    outs = [P(unc.ray_max_dt), P(unc.samples_idx), P(unc.samples_3d), P(unc.samples_dirs), P(unc.samples_z), P(unc.samples_dt),
+            P(unc.ray_start_end_idx), n]
+    if use_grid:
+        ext = (ctypes.c_float * 3)(*[float(v) for v in sc["extent"]])
+        code = ref.ref_samples_fg_occupied(*common, sc["n"], ext, P(t["occ"]), P(t["roi"]), *outs)
+    else:
+        code = ref.ref_samples_fg(*common, *outs)
+    assert code == 0, f"reference harness returned CUDA error {code}"
+    return unc.compact_to_valid_samples()
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("use_grid", [False, True])
+def test_fg_samplers_match_reference_kernels(ref, use_grid, jitter):
+    from volsurfs_b200.volsurfs import RaySampler
+
+    sc = make_scene(20000, 64, seed=21)
+    t = _cuda_scene(sc)
+    min_dist, min_nr, max_nr = 0.004, 1, 256
+    want = _ref_fg(ref, sc, t, min_dist, min_nr, max_nr, jitter, use_grid)
+    _reset_rng()
+    if use_grid:
+        got = RaySampler.compute_samples_fg_in_grid_occupied_regions(t["o"], t["d"], t["t_entry"], t["t_exit"], min_dist, min_nr, max_nr, jitter,
+                                                                    sc["n"], sc["extent"], t["occ"], t["roi"], 1)
+    else:
+        got = RaySampler.compute_samples_fg(t["o"], t["d"], t["t_entry"], t["t_exit"], min_dist, min_nr, max_nr, jitter, 1)
+    S = want.get_total_nr_samples()
+    print(f"grid={use_grid} jitter={jitter}: {S} samples over {int((want.get_nr_samples_per_ray() > 0).sum())} rays")
+    assert S > 100000 and got.get_total_nr_samples() == S
+    for k in FIELDS:
+        assert torch.equal(getattr(got, k), getattr(want, k)), (k, int((getattr(got, k) != getattr(want, k)).sum()))
+
+
+def test_bg_and_grid_queries_match_reference_kernels(ref):
+    from volsurfs_b200.volsurfs import OccupancyGrid, RaySampler
+
+    sc = make_scene(20000, 64, seed=22)
+    t = _cuda_scene(sc)
+    n, nr = 20000, 32
+    ext = (ctypes.c_float * 3)(*[float(v) for v in sc["extent"]])
+    for jitter in (False, True):
+        z = torch.empty(n * nr, 1, device="cuda")
+        p3, dr = torch.empty(n * nr, 3, device="cuda"), torch.empty(n * nr, 3, device="cuda")
+        dt, mdt, se = torch.empty(n * nr, 1, device="cuda"), torch.empty(n, 1, device="cuda"), torch.empty(n, 2, dtype=torch.int32, device="cuda")
+        assert ref.ref_samples_bg(P(t["o"]), P(t["d"]), P(t["t_exit"]), ctypes.c_float(30.0), nr, ctypes.c_uint64(PCG_DEFAULT_STATE),
+                                  ctypes.c_uint64(PCG_DEFAULT_INC), int(jitter), P(mdt), P(p3), P(dr), P(z), P(dt), P(se), n) == 0
+        _reset_rng()
+        got = RaySampler.compute_samples_bg(t["o"], t["d"], t["t_exit"], 30.0, nr, jitter)
+        assert torch.equal(got.samples_z, z) and torch.equal(got.samples_3d, p3) and torch.equal(got.samples_dirs, dr)
+        assert torch.equal(got.ray_max_dt, mdt) and torch.equal(got.ray_start_end_idx, se)
+    og = OccupancyGrid(sc["n"], sc["extent"])
+    og.set_grid_occupancy(t["occ"])
+    og.set_grid_roi(t["roi"])
+    og.set_grid_values(t["vals"])
+    near, far = og.get_rays_t_near_t_far(t["o"], t["d"], t["t_entry"], t["t_exit"])
+    rn, rf = torch.empty_like(near), torch.empty_like(far)
+    assert ref.ref_rays_t_near_t_far(P(t["o"]), P(t["d"]), P(t["t_entry"]), P(t["t_exit"]), sc["n"], ext, P(t["occ"]), P(t["roi"]), P(rn), P(rf), n) == 0
+    assert torch.equal(near, rn) and torch.equal(far, rf)
+    pts = ((torch.rand(50000, 3, device="cuda") - 0.5) * 1.5).contiguous()
+    occ, val = og.check_occupancy(pts)
+    ro, rv = torch.ones(50000, 1, dtype=torch.bool, device="cuda"), torch.ones(50000, 1, device="cuda")
+    assert ref.ref_check_occupancy(P(pts), sc["n"], ext, P(t["vals"]), P(t["occ"]), P(t["roi"]), P(ro), P(rv), 50000) == 0
+    assert torch.equal(occ, ro) and torch.equal(val, rv)
+
+
+def test_sampler_feeds_packed_compositing():
+    """the sampler's packet goes straight into update_dt and the packed operators (the NeRF path of volsurfs_py/methods/nerf.py:280-334)"""
+    from volsurfs_b200.volsurfs import RaySampler, VolumeRendering
+
+    sc = make_scene(5000, 32, seed=23)
+    t = _cuda_scene(sc)
+    _reset_rng()
+    rsp = RaySampler.compute_samples_fg_in_grid_occupied_regions(t["o"], t["d"], t["t_entry"], t["t_exit"], 0.01, 1, 128, True, sc["n"], sc["extent"],
+                                                                 t["occ"], t["roi"], 1)
+    rsp.update_dt(False)
+    S = rsp.get_total_nr_samples()
+    assert S > 0 and float(rsp.samples_dt.min()) >= 0.0
+    sigma = torch.rand(S, 1, device="cuda") * 20
+    alpha = 1.0 - torch.exp(-sigma * rsp.samples_dt)
+    T, bg = VolumeRendering.cumprod_one_minus_alpha_to_transmittance(rsp, 1.0 - alpha + 1e-6)
+    w = alpha * T
+    acc = VolumeRendering.integrate_with_weights_1d(rsp, torch.ones_like(w), w)
+    assert float(acc.max()) <= 1.0 + 1e-4 and torch.isfinite(acc).all() and bg.shape == (5000, 1)
+
+
+def test_argument_errors():
+    from volsurfs_b200.volsurfs import RaySampler
+
+    o = torch.zeros(4, 3, device="cuda")
+    with pytest.raises(RuntimeError):
+        RaySampler.compute_samples_fg(o, o[:3], torch.zeros(4, 1, device="cuda"), torch.ones(4, 1, device="cuda"), 0.1, 1, 8, False, 1)
+    with pytest.raises(RuntimeError):
+        RaySampler.compute_samples_fg_in_grid_occupied_regions(o, o, torch.zeros(4, 1, device="cuda"), torch.ones(4, 1, device="cuda"), 0.1, 1, 8, False,
+                                                              8, [1, 1, 1], torch.ones(10, dtype=torch.bool, device="cuda"),
+                                                              torch.ones(512, dtype=torch.bool, device="cuda"), 1)

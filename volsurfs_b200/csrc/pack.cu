@@ -308,6 +308,23 @@ int vs_compact_offsets(const int32_t* se_in, int64_t n_rays, int64_t* total_dev,
     return launch_scan(counts, n_rays, offsets, reinterpret_cast<long long*>(total_dev), bs, st);
 }
 
+// Compacted start of every ray's segment for producers that write straight into compacted form (csrc/sampler.cu): out_start[r] =
+// exclusive prefix sum of (end - start) over se_in, *total_dev = the grand total.  scratch: vs_pack_scratch_bytes(n_rays).
+int vs_segment_offsets(const int32_t* se_in, int64_t n_rays, int32_t* out_start, int64_t* total_dev, void* scratch, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && total_dev && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rays == 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(int64_t), st);
+    VS_CHECK_ARG(se_in && out_start);
+    long long* bs;
+    int32_t *counts, *offsets;
+    carve_scratch(scratch, n_rays, &bs, &counts, &offsets);
+    counts_from_segments_kernel<<<(unsigned)div_up(n_rays, kScanBlock), kScanBlock, 0, st>>>(se_in, counts, n_rays);
+    launched(1);
+    int e = launch_scan(counts, n_rays, offsets, reinterpret_cast<long long*>(total_dev), bs, st);
+    if (e != VS_OK) return e;
+    return (int)cudaMemcpyAsync(out_start, offsets, sizeof(int32_t) * n_rays, cudaMemcpyDeviceToDevice, st);
+}
+
 // Start offsets of combine_ray_samples_packets (src/VolumeRendering.cu:595-603: cumsum of count1+count2, shifted): out_start[r] =
 // exclusive prefix sum of the two packets' per-ray counts, *total_dev = their grand total.  scratch: vs_pack_scratch_bytes(n_rays).
 int vs_combine_offsets(const int32_t* se1, const int32_t* se2, int64_t n_rays, int32_t* out_start, int64_t* total_dev, void* scratch,

@@ -613,3 +613,241 @@ class VolumeRendering:
             "vs_composite_bwd",
         )
         return d_alpha, d_rgb, d_z
+
+
+def _pcg_advance(state: int, inc: int, delta: int = 1 << 32) -> int:
+    """pcg32::advance (kernels/volsurfs/pcg32.h:158-180) on a host copy of the generator"""
+    m64 = (1 << 64) - 1
+    cur_mult, cur_plus, acc_mult, acc_plus = 0x5851F42D4C957F2D, inc, 1, 0
+    delta &= m64
+    while delta > 0:
+        if delta & 1:
+            acc_mult = (acc_mult * cur_mult) & m64
+            acc_plus = (acc_plus * cur_mult + cur_plus) & m64
+        cur_plus = ((cur_mult + 1) * cur_plus) & m64
+        cur_mult = (cur_mult * cur_mult) & m64
+        delta >>= 1
+    return (acc_mult * state + acc_plus) & m64
+
+
+def _rays_args(rays_o, rays_d, t_a, t_b=None):
+    o, d = _f32c(rays_o, "rays_o", 3), _f32c(rays_d, "rays_d", 3)
+    a = _f32c(t_a, "ray_t_entry", 1)
+    b = None if t_b is None else _f32c(t_b, "ray_t_exit", 1)
+    n = int(o.shape[0])
+    if d.shape[0] != n or a.shape[0] != n or (b is not None and b.shape[0] != n):
+        raise RuntimeError("rays_o, rays_d and the ray t tensors must have one row per ray")
+    return o, d, a, b, n
+
+
+class OccupancyGrid:
+    """Occupancy grid in Morton order (include/volsurfs/OccupancyGrid.cuh:9-68, bound at PyBridge.cxx:33-68): the container and the
+    two queries the samplers rest on.  The grid-maintenance methods of training (update_grid_values / update_grid_occupancy_with_*,
+    get_*_grid_samples*) are outside the rendering path and are not provided."""
+
+    def __init__(self, nr_voxels_per_dim: int, grid_extent):
+        self.m_nr_voxels_per_dim = int(nr_voxels_per_dim)
+        ext = [float(v) for v in (grid_extent.tolist() if hasattr(grid_extent, "tolist") else grid_extent)]
+        if len(ext) != 3:
+            raise ValueError("grid_extent must have 3 entries")
+        self.m_grid_extent = ext
+        self.m_grid_values = OccupancyGrid.make_grid_values(nr_voxels_per_dim)
+        self.m_grid_occupancy = OccupancyGrid.make_grid_occupancy(nr_voxels_per_dim)
+        self.m_grid_roi = OccupancyGrid.make_grid_occupancy(nr_voxels_per_dim)
+
+    @staticmethod
+    def _check_n(n: int) -> int:
+        n = int(n)
+        if n <= 0 or n % 2 != 0 or (n & (n - 1)) != 0:  # src/OccupancyGrid.cu:166-167 (CHECK-abort in the reference)
+            raise RuntimeError("Nr of voxels should be an even power of 2 because we are using morton codes")
+        return n
+
+    @staticmethod
+    def make_grid_values(nr_voxels_per_dim: int) -> torch.Tensor:
+        n = OccupancyGrid._check_n(nr_voxels_per_dim)
+        return torch.ones(n * n * n, dtype=torch.float32, device=_device())
+
+    @staticmethod
+    def make_grid_occupancy(nr_voxels_per_dim: int) -> torch.Tensor:
+        n = OccupancyGrid._check_n(nr_voxels_per_dim)
+        return torch.ones(n * n * n, dtype=torch.bool, device=_device())
+
+    def get_grid_values(self):
+        return self.m_grid_values
+
+    def get_grid_occupancy(self):
+        return self.m_grid_occupancy
+
+    def get_grid_roi(self):
+        return self.m_grid_roi
+
+    def get_grid_occupancy_in_roi(self):
+        return self.m_grid_occupancy.masked_select(self.m_grid_roi)
+
+    def set_grid_values(self, grid_values):
+        self.m_grid_values = grid_values
+
+    def set_grid_occupancy(self, grid_occupancy):
+        self.m_grid_occupancy = grid_occupancy
+
+    def set_grid_roi(self, grid_roi):
+        """extension: the reference only sets the region of interest through init_sphere_roi"""
+        self.m_grid_roi = grid_roi
+
+    def set_grid_occupancy_full(self):
+        self.m_grid_occupancy.fill_(True)
+
+    def set_grid_occupancy_empty(self):
+        self.m_grid_occupancy.fill_(False)
+
+    def get_nr_voxels(self) -> int:
+        return self.m_nr_voxels_per_dim ** 3
+
+    def get_nr_voxels_per_dim(self) -> int:
+        return self.m_nr_voxels_per_dim
+
+    def get_grid_extent(self):
+        return list(self.m_grid_extent)
+
+    def get_nr_voxels_in_roi(self) -> int:
+        return int(self.m_grid_roi.sum().item())
+
+    def get_nr_occupied_voxels(self) -> int:
+        return int(self.m_grid_occupancy.sum().item())
+
+    def get_nr_occupied_voxels_in_roi(self) -> int:
+        return int(self.get_grid_occupancy_in_roi().sum().item())
+
+    def get_grid_max_value(self) -> float:
+        return float(self.m_grid_values.max().item())
+
+    def get_grid_min_value(self) -> float:
+        return float(self.m_grid_values.min().item())
+
+    def _masks(self):
+        n3 = self.get_nr_voxels()
+        occ, roi = self.m_grid_occupancy, self.m_grid_roi
+        for name, t in (("grid_occupancy", occ), ("grid_roi", roi)):
+            if t.dtype != torch.bool or t.numel() != n3 or not t.is_cuda:
+                raise RuntimeError(f"{name} must be a bool CUDA tensor with nr_voxels_per_dim^3 entries")
+        return occ.contiguous(), roi.contiguous()
+
+    def _extent_c(self):
+        import ctypes
+
+        return (ctypes.c_float * 3)(*self.m_grid_extent)
+
+    def get_rays_t_near_t_far(self, rays_o, rays_d, ray_t_entry, ray_t_exit):
+        """first / last t inside occupied voxels of the region of interest (src/OccupancyGrid.cu:349-399) -> ([N,1], [N,1])"""
+        o, d, a, b, n = _rays_args(rays_o, rays_d, ray_t_entry, ray_t_exit)
+        occ, roi = self._masks()
+        near = torch.empty((n, 1), dtype=torch.float32, device=o.device)
+        far = torch.empty((n, 1), dtype=torch.float32, device=o.device)
+        check(_lib.lib().vs_occgrid_rays_t_near_t_far(ptr(o), ptr(d), ptr(a), ptr(b), self.m_nr_voxels_per_dim, self._extent_c(), ptr(occ),
+                                                      ptr(roi), ptr(near), ptr(far), n, _stream()), "vs_occgrid_rays_t_near_t_far")
+        return near, far
+
+    def check_occupancy(self, points):
+        """(occupied && in roi [P,1] bool, grid value [P,1]) per point; outside the grid -> (False, 0) (src/OccupancyGrid.cu:402-447)"""
+        p = _f32c(points, "points", 3)
+        occ, roi = self._masks()
+        vals = self.m_grid_values
+        if vals.dtype != torch.float32 or vals.numel() != self.get_nr_voxels():
+            raise RuntimeError("grid_values must be a float32 tensor with nr_voxels_per_dim^3 entries")
+        n = int(p.shape[0])
+        out_occ = torch.empty((n, 1), dtype=torch.bool, device=p.device)
+        out_val = torch.empty((n, 1), dtype=torch.float32, device=p.device)
+        check(_lib.lib().vs_occgrid_check_occupancy(ptr(p), self.m_nr_voxels_per_dim, self._extent_c(), ptr(vals.contiguous()), ptr(occ), ptr(roi),
+                                                    ptr(out_occ), ptr(out_val), n, _stream()), "vs_occgrid_check_occupancy")
+        return out_occ, out_val
+
+
+class RaySampler:
+    """Static ray samplers (include/volsurfs/RaySampler.cuh:9-64, bound at PyBridge.cxx:131-139).  The foreground samplers return the
+    COMPACTED packet, like the reference after its closing compact_to_valid_samples (src/RaySampler.cu:236,340), but never build the
+    nr_rays x max_nr_samples_per_ray staging packet (csrc/sampler.cu)."""
+
+    #: host copy of the reference's static ``pcg32 m_rng``: passed by value to a jittered launch, advanced by 2^32 afterwards
+    _rng_state = 0x853C49E6748FEA9B
+    _rng_inc = 0xDA3E39CB94B95BDB
+
+    @staticmethod
+    def _fg(rays_o, rays_d, ray_t_entry, ray_t_exit, min_dist, min_nr, max_nr, jitter, values_dim, grid):
+        import ctypes
+
+        L = _lib.lib()
+        o, d, a, b, n = _rays_args(rays_o, rays_d, ray_t_entry, ray_t_exit)
+        dev, st = o.device, _stream()
+        min_nr, max_nr = int(min_nr), int(max_nr)
+        if n * max_nr > 2**31 - 1:
+            raise RuntimeError("nr_rays * max_nr_samples_per_ray must fit int32 sample indices")
+        if grid is None:
+            nv, ext, occ, roi = 0, None, None, None
+        else:
+            nv, ext_list, occ, roi = grid
+            ext = (ctypes.c_float * 3)(*[float(v) for v in ext_list])
+        se_virtual = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        ray_max_dt = torch.full((n, 1), -1.0, dtype=torch.float32, device=dev)
+        n_create = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        rng = (RaySampler._rng_state, RaySampler._rng_inc)
+        common = [ptr(o), ptr(d), ptr(a), ptr(b), float(min_dist), min_nr, max_nr, rng[0], rng[1], int(bool(jitter)), int(nv), ext, ptr(occ), ptr(roi)]
+        check(L.vs_sampler_fg_count(*common, ptr(se_virtual), ptr(ray_max_dt), ptr(n_create), n, st), "vs_sampler_fg_count")
+        scratch = torch.empty(max(int(L.vs_pack_scratch_bytes(n)), 8), dtype=torch.uint8, device=dev)
+        out_start = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        total_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(L.vs_segment_offsets(ptr(se_virtual), n, ptr(out_start), ptr(total_dev), ptr(scratch), st), "vs_segment_offsets")
+        total = int(total_dev.item())  # sizes the outputs exactly, like the reference's compaction
+        f = dict(dtype=torch.float32, device=dev)
+        out = RaySamplesPacked._from_tensors(
+            samples_idx=torch.empty((total, 1), dtype=torch.int32, device=dev),
+            samples_3d=torch.empty((total, 3), **f),
+            samples_dirs=torch.empty((total, 3), **f),
+            samples_z=torch.empty((total, 1), **f),
+            samples_dt=torch.full((total, 1), -1.0, **f),                 # the samplers never write dt (update_dt does)
+            samples_values=torch.full((total, int(values_dim)), -1.0, **f),
+            ray_start_end_idx=torch.empty((n, 2), dtype=torch.int32, device=dev),
+            ray_o=o.clone(), ray_d=d.clone(), ray_enter=a.clone(), ray_exit=b.clone(), ray_max_dt=ray_max_dt,
+        )
+        check(L.vs_sampler_fg_write(*common, ptr(se_virtual), ptr(ray_max_dt), ptr(n_create), ptr(out_start), ptr(out.ray_start_end_idx),
+                                    ptr(out.samples_idx), ptr(out.samples_3d), ptr(out.samples_dirs), ptr(out.samples_z), n, st),
+              "vs_sampler_fg_write")
+        if jitter:
+            RaySampler._rng_state = _pcg_advance(RaySampler._rng_state, RaySampler._rng_inc)
+        return out
+
+    @staticmethod
+    def compute_samples_fg(rays_o, rays_d, ray_t_entry, ray_t_exit, min_dist_between_samples, min_nr_samples_per_ray, max_nr_samples_per_ray,
+                           jitter_samples, values_dim):
+        """equidistant samples between ray entry and exit (src/RaySampler.cu:159-245)"""
+        return RaySampler._fg(rays_o, rays_d, ray_t_entry, ray_t_exit, min_dist_between_samples, min_nr_samples_per_ray,
+                              max_nr_samples_per_ray, jitter_samples, values_dim, None)
+
+    @staticmethod
+    def compute_samples_fg_in_grid_occupied_regions(rays_o, rays_d, ray_t_entry, ray_t_exit, min_dist_between_samples, min_nr_samples_per_ray,
+                                                    max_nr_samples_per_ray, jitter_samples, nr_voxels_per_dim, grid_extent, grid_occupancy,
+                                                    grid_roi, values_dim):
+        """samples spread over the occupied voxels a ray crosses (src/RaySampler.cu:247-345)"""
+        n3 = int(nr_voxels_per_dim) ** 3
+        for name, t in (("grid_occupancy", grid_occupancy), ("grid_roi", grid_roi)):
+            if t.dtype != torch.bool or t.numel() != n3 or not t.is_cuda:
+                raise RuntimeError(f"{name} must be a bool CUDA tensor with nr_voxels_per_dim^3 entries")
+        ext = grid_extent.tolist() if hasattr(grid_extent, "tolist") else list(grid_extent)
+        return RaySampler._fg(rays_o, rays_d, ray_t_entry, ray_t_exit, min_dist_between_samples, min_nr_samples_per_ray,
+                              max_nr_samples_per_ray, jitter_samples, values_dim,
+                              (int(nr_voxels_per_dim), ext, grid_occupancy.contiguous(), grid_roi.contiguous()))
+
+    @staticmethod
+    def compute_samples_bg(rays_o, rays_d, ray_t_exit, ray_t_far, nr_samples, jitter_samples):
+        """``nr_samples`` samples per ray from the foreground exit to ``ray_t_far``, uniform in inverse depth (src/RaySampler.cu:72-157)"""
+        o, d, a, _, n = _rays_args(rays_o, rays_d, ray_t_exit)
+        nr = int(nr_samples)
+        out = RaySamplesPacked(n, n * nr, 0, 0)
+        out.ray_o, out.ray_d, out.ray_enter = o.clone(), d.clone(), a.clone()
+        out.ray_exit = torch.full((n, 1), float(ray_t_far), dtype=torch.float32, device=o.device)
+        out.is_compacted = True
+        check(_lib.lib().vs_sampler_bg(ptr(o), ptr(d), ptr(a), float(ray_t_far), nr, RaySampler._rng_state, RaySampler._rng_inc,
+                                       int(bool(jitter_samples)), ptr(out.ray_max_dt), ptr(out.samples_3d), ptr(out.samples_dirs),
+                                       ptr(out.samples_z), ptr(out.ray_start_end_idx), n, _stream()), "vs_sampler_bg")
+        if jitter_samples:
+            RaySampler._rng_state = _pcg_advance(RaySampler._rng_state, RaySampler._rng_inc)
+        return out
