@@ -288,22 +288,24 @@ int vs_shtex_combine_backward(int sh_deg, int nr_channels, int mode, int align, 
  * kernels kernels/volsurfs/RaySamplerGPU.cuh:39-488) and OccupancyGrid::get_rays_t_near_t_far / check_occupancy
  * (kernels/volsurfs/OccupancyGridGPU.cuh:318-441; helpers kernels/volsurfs/occ_grid_helpers.h).  The foreground samplers produce the
  * COMPACTED packet directly (what the reference returns after compact_to_valid_samples) in two launches around one prefix sum:
- *   vs_sampler_fg_count -> vs_segment_offsets -> (host reads the total, sizes the outputs) -> vs_sampler_fg_write.
+ *   vs_sampler_fg_count (marches; stages 4 bytes of depth per sample) -> vs_segment_offsets -> (host reads the total, sizes the
+ *   outputs) -> vs_sampler_fg_write (depth -> rows at their compacted position).
  * nr_voxels_per_dim == 0 selects compute_samples_fg (no grid; extent / occupancy / roi ignored).  extent: HOST float[3];
  * occupancy, roi: DEVICE u8 [nr_voxels_per_dim^3] in Morton order (torch.bool storage).  rng_state / rng_inc: the class's static pcg32
  * (the caller advances it by 2^32 after a jittered call, RaySampler.cu:228-231). */
 int vs_segment_offsets(const int32_t* se_in, int64_t n_rays, int32_t* out_start, int64_t* total_dev, void* scratch, void* stream);
 /* se_virtual [n,2]: the segment each ray would own in the reference's uncompacted packet ((-1,-1): none); ray_max_dt [n,1] pre-filled
- * with -1 by the caller; n_create [n] i32 scratch handed to vs_sampler_fg_write */
+ * with -1 by the caller; z_stage [n * max_nr] f32: depth of sample i of ray r at r*max_nr + i (handed to vs_sampler_fg_write; only the
+ * slots of real samples are touched).  roi == NULL: `occupancy` already holds occupancy && roi. */
 int vs_sampler_fg_count(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, float min_dist, int min_nr,
                         int max_nr, uint64_t rng_state, uint64_t rng_inc, int jitter, int nr_voxels_per_dim, const float* extent,
-                        const uint8_t* occupancy, const uint8_t* roi, int32_t* se_virtual, float* ray_max_dt, int32_t* n_create, int64_t n_rays,
+                        const uint8_t* occupancy, const uint8_t* roi, int32_t* se_virtual, float* ray_max_dt, float* z_stage, int64_t n_rays,
                         void* stream);
-int vs_sampler_fg_write(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, float min_dist, int min_nr,
-                        int max_nr, uint64_t rng_state, uint64_t rng_inc, int jitter, int nr_voxels_per_dim, const float* extent,
-                        const uint8_t* occupancy, const uint8_t* roi, const int32_t* se_virtual, const float* ray_max_dt,
-                        const int32_t* n_create, const int32_t* out_start, int32_t* se_out, int32_t* samples_idx, float* samples_3d,
-                        float* samples_dirs, float* samples_z, int64_t n_rays, void* stream);
+/* out_start [n] from vs_segment_offsets(se_virtual): rows of every sample (samples_idx = its slot in the reference's uncompacted packet,
+ * samples_3d = o + z d, samples_dirs, samples_z) at their compacted position + the compacted se_out [n,2] */
+int vs_sampler_fg_write(const float* rays_o, const float* rays_d, int max_nr, const int32_t* se_virtual, const float* z_stage,
+                        const int32_t* out_start, int32_t* se_out, int32_t* samples_idx, float* samples_3d, float* samples_dirs,
+                        float* samples_z, int64_t n_rays, void* stream);
 /* compute_samples_bg: nr_samples_per_ray samples per ray, uniform in inverse depth; samples_* hold n_rays*nr_samples_per_ray rows */
 int vs_sampler_bg(const float* rays_o, const float* rays_d, const float* t_start, float t_far, int nr_samples_per_ray, uint64_t rng_state,
                   uint64_t rng_inc, int jitter, float* ray_max_dt, float* samples_3d, float* samples_dirs, float* samples_z, int32_t* se,

@@ -8,21 +8,24 @@
 //   OccupancyGrid::get_rays_t_near_t_far / check_occupancy    kernels/volsurfs/OccupancyGridGPU.cuh:318-441
 //   pos_to_lin_idx / distance_to_next_voxel / morton3D        kernels/volsurfs/occ_grid_helpers.h:13-33,55-79,126-190
 //
-// The reference marches every ray into an UNCOMPACTED packet (nr_rays x max_nr_samples_per_ray slots: 23 GB of staging at 640k rays x
-// 1024) and then gathers it (compact_to_valid_samples).  Here the foreground samplers run in two launches around one prefix sum:
-//   sampler_fg_kernel<GRID, false>   per ray: length of the occupied stretch -> sample count and spacing (ray_max_dt), then a dry run
-//                                    of the sampling march: the count the reference would have created (0 below min_nr_samples_per_ray)
-//   (vs_segment_offsets)             exclusive scan of the counts -> compacted start of every ray + the total
-//   sampler_fg_kernel<GRID, true>    the sampling march again, storing samples straight at their compacted position
-// so the result equals the reference's compacted packet (samples_idx = the slot the sample would have had, samples_dt untouched) and
-// nothing of size nr_rays x max_nr_samples_per_ray ever exists.  The marches are sequential per ray (every step depends on the
-// position the previous one reached), so a thread owns a ray; the occupancy and region-of-interest masks (1 byte per voxel, Morton
-// order) are L2 resident.
+// The reference marches every ray into an UNCOMPACTED packet (nr_rays x max_nr_samples_per_ray slots of 36 bytes: 23 GB of staging at
+// 640k rays x 1024) and then gathers it (compact_to_valid_samples).  Here the foreground samplers are two launches around one prefix sum:
+//   sampler_fg_march_kernel<GRID>   thread per ray (the marches are sequential: every step depends on the position the previous one
+//                                   reached): length of the occupied stretch -> sample count and spacing (ray_max_dt), then the sampling
+//                                   march, which records only the DEPTH of every sample in a 4-byte-per-slot staging array
+//   (vs_segment_offsets)            exclusive scan of the counts -> compacted start of every ray + the total
+//   sampler_fg_expand_kernel        warp per ray, lanes over its samples: depth -> o + z d, rows stored at their compacted position
+// so the result equals the reference's compacted packet (samples_idx = the slot the sample would have had, samples_dt untouched).  The
+// marches are instruction bound (a step is ~25 dependent fp32 operations + a Morton code); the step shares p / extent between the voxel
+// index and the boundary distance, spreads Morton bits in 32-bit arithmetic (the 64-bit path only outside the grid), and divides by
+// the voxel count with an exact multiply when it is a power of two.  The occupancy && roi mask (1 byte per voxel) is L2 resident.
 //
 // Arithmetic contract (bit parity with the reference kernels as nvcc compiles them, pinned on the GPU against oracle/_ref/
 // libsampler_ref.so): IEEE fp32 with the contractions nvcc applies to the reference source — `ray_o + t * ray_d`, `t + c * rnd` and
 // helper_math's lerp are fused multiply-adds; everything else is separate round-to-nearest operations; the background sampler's
 // `1.0 / (s + eps) - 1.0` is evaluated in double like the reference's double literals make it.
+#include <algorithm>
+
 #include "vs_common.cuh"
 
 namespace vs {
@@ -57,12 +60,13 @@ struct Pcg {
 struct Grid {
     int n;             // voxels per dimension
     float ex, ey, ez;  // extent of the cuboid, centred at the origin
+    float inv_n;       // 1/n when n is a power of two (x / n == x * (1/n) exactly), else 0: divide
     const uint8_t* occ;
-    const uint8_t* roi;
+    const uint8_t* roi;  // NULL: `occ` already holds occupancy && roi
 };
 
 // 21-bit Morton spreading; the reference keeps only the low 32 bits of the 64-bit spread (uint32_t xx = expand_bits(x))
-__device__ __forceinline__ uint32_t spread_bits(uint32_t v) {
+__device__ __forceinline__ uint32_t spread_bits64(uint32_t v) {
     uint64_t w = v;
     w &= 0x00000000001fffffULL;
     w = (w | w << 32) & 0x001f00000000ffffULL;
@@ -72,52 +76,89 @@ __device__ __forceinline__ uint32_t spread_bits(uint32_t v) {
     w = (w | w << 2) & 0x1249249249249249ULL;
     return (uint32_t)w;
 }
-
-__device__ __forceinline__ int pos_to_lin_idx(float px, float py, float pz, const Grid& g) {
-    const float n = (float)g.n;
-    const float x = __fmul_rn(__fadd_rn(__fdiv_rn(px, g.ex), 0.5f), n);
-    const float y = __fmul_rn(__fadd_rn(__fdiv_rn(py, g.ey), 0.5f), n);
-    const float z = __fmul_rn(__fadd_rn(__fdiv_rn(pz, g.ez), 0.5f), n);
-    // float -> uint32_t as the hardware converts it: truncation, negatives and NaN to 0, saturation above
-    const uint32_t xx = spread_bits(__float2uint_rz(x)), yy = spread_bits(__float2uint_rz(y)), zz = spread_bits(__float2uint_rz(z));
-    return (int)(xx | (yy << 1) | (zz << 2));
+// the same bits for v < 1024 in 32-bit arithmetic (the marches spend most of their instructions here)
+__device__ __forceinline__ uint32_t spread_bits10(uint32_t v) {
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
 }
 
-__device__ __forceinline__ int sign_of(float x) { return x > 0.f ? 1 : (x < 0.f ? -1 : 0); }
+// voxel-space coordinate p / extent, shared by the index and the step computation (the reference evaluates it in both)
+__device__ __forceinline__ float unit_coord(float p, float e) { return __fdiv_rn(p, e); }
+
+__device__ __forceinline__ int lin_idx_from_unit(float ux, float uy, float uz, const Grid& g) {
+    const float n = (float)g.n;
+    // float -> uint32_t as the hardware converts it: truncation, negatives and NaN to 0, saturation above
+    const uint32_t x = __float2uint_rz(__fmul_rn(__fadd_rn(ux, 0.5f), n)), y = __float2uint_rz(__fmul_rn(__fadd_rn(uy, 0.5f), n)),
+                   z = __float2uint_rz(__fmul_rn(__fadd_rn(uz, 0.5f), n));
+    if ((x | y | z) < 1024u) return (int)(spread_bits10(x) | (spread_bits10(y) << 1) | (spread_bits10(z) << 2));
+    return (int)(spread_bits64(x) | (spread_bits64(y) << 1) | (spread_bits64(z) << 2));
+}
+
+__device__ __forceinline__ int pos_to_lin_idx(float px, float py, float pz, const Grid& g) {
+    return lin_idx_from_unit(unit_coord(px, g.ex), unit_coord(py, g.ey), unit_coord(pz, g.ez), g);
+}
 
 // the reference's "DDA like step": distance (measured along the AXIS, not along the ray) to the next voxel boundary, + 1e-6
-__device__ __forceinline__ float distance_to_next_voxel(float px, float py, float pz, float dx, float dy, float dz, const Grid& g) {
+__device__ __forceinline__ float step_from_unit(float ux, float uy, float uz, float dx, float dy, float dz, const Grid& g) {
     const float eps = 1e-6f, n = (float)g.n;
     if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps) return 1e10f;
     float t3[3];
-    const float p[3] = {px, py, pz}, d[3] = {dx, dy, dz}, e[3] = {g.ex, g.ey, g.ez};
+    const float u[3] = {ux, uy, uz}, d[3] = {dx, dy, dz}, e[3] = {g.ex, g.ey, g.ez};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         t3[a] = 1e10f;
         if (fabsf(d[a]) > eps) {
-            const float q = __fmul_rn(__fdiv_rn(p[a], e[a]), n);
-            const float prime = floorf(__fadd_rn(q, (float)sign_of(d[a])));
-            t3[a] = __fmul_rn(__fdiv_rn(fabsf(__fsub_rn(prime, q)), n), e[a]);
+            const float q = __fmul_rn(u[a], n);
+            const float sgn = d[a] > 0.f ? 1.f : -1.f;  // |d| > eps here
+            const float prime = floorf(__fadd_rn(q, sgn));
+            const float dq = fabsf(__fsub_rn(prime, q));
+            t3[a] = __fmul_rn(g.inv_n != 0.f ? __fmul_rn(dq, g.inv_n) : __fdiv_rn(dq, n), e[a]);
         }
     }
     return __fadd_rn(fminf(fminf(t3[0], t3[1]), t3[2]), eps);
 }
 
+__device__ __forceinline__ float distance_to_next_voxel(float px, float py, float pz, float dx, float dy, float dz, const Grid& g) {
+    return step_from_unit(unit_coord(px, g.ex), unit_coord(py, g.ey), unit_coord(pz, g.ez), dx, dy, dz, g);
+}
+
 __device__ __forceinline__ bool in_grid(int idx_voxel, const Grid& g) { return idx_voxel >= 0 && idx_voxel < g.n * g.n * g.n; }
-__device__ __forceinline__ bool occupied(int idx_voxel, const Grid& g) { return __ldg(g.roi + idx_voxel) && __ldg(g.occ + idx_voxel); }
+__device__ __forceinline__ bool occupied(int idx_voxel, const Grid& g) {
+    if (g.roi == nullptr) return __ldg(g.occ + idx_voxel) != 0;
+    return __ldg(g.roi + idx_voxel) && __ldg(g.occ + idx_voxel);
+}
 __device__ __forceinline__ float clampf(float v, float a, float b) { return fmaxf(a, fminf(b, v)); }
 
+// one step of a march: voxel of the position and the distance to the next boundary from one evaluation of p / extent
+struct Probe {
+    int voxel;
+    float px, py, pz, ux, uy, uz;
+};
+__device__ __forceinline__ Probe probe(float t, float ox, float oy, float oz, float dx, float dy, float dz, const Grid& g) {
+    Probe p;
+    p.px = __fmaf_rn(t, dx, ox);
+    p.py = __fmaf_rn(t, dy, oy);
+    p.pz = __fmaf_rn(t, dz, oz);
+    p.ux = unit_coord(p.px, g.ex);
+    p.uy = unit_coord(p.py, g.ey);
+    p.uz = unit_coord(p.pz, g.ez);
+    p.voxel = lin_idx_from_unit(p.ux, p.uy, p.uz, g);
+    return p;
+}
+
 // ---- foreground samplers -----------------------------------------------------------------------------------------------------------
-// WRITE = false: writes the ray's virtual uncompacted segment (ray*max_nr, ray*max_nr + created) or (-1,-1), ray_max_dt and n_create.
-// WRITE = true : stores the samples of rays with a non-empty segment at out_start[ray] + i and the compacted segment.
-template <bool GRID, bool WRITE>
-__global__ void __launch_bounds__(128) sampler_fg_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                         const float* __restrict__ t_entry, const float* __restrict__ t_exit_p, float min_dist,
-                                                         int min_nr, int max_nr, Pcg rng, int jitter, Grid g, int32_t* __restrict__ se_virtual,
-                                                         float* __restrict__ ray_max_dt, int32_t* __restrict__ n_create,
-                                                         const int32_t* __restrict__ out_start, int32_t* __restrict__ se_out,
-                                                         int32_t* __restrict__ s_idx, float* __restrict__ s_3d, float* __restrict__ s_dirs,
-                                                         float* __restrict__ s_z, int64_t n_rays) {
+// Pass 1 (one thread per ray): length of the occupied stretch -> sample count and spacing, then the sampling march.  It writes the
+// ray's virtual uncompacted segment (ray*max_nr, ray*max_nr + created) or (-1,-1), ray_max_dt, and the depth of every sample into the
+// ray's slots of `z_stage` (4 bytes per slot; only the slots of real samples are touched).
+template <bool GRID>
+__global__ void __launch_bounds__(128) sampler_fg_march_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                               const float* __restrict__ t_entry, const float* __restrict__ t_exit_p,
+                                                               float min_dist, int min_nr, int max_nr, Pcg rng, int jitter, Grid g,
+                                                               int32_t* __restrict__ se_virtual, float* __restrict__ ray_max_dt,
+                                                               float* __restrict__ z_stage, int64_t n_rays) {
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= n_rays) return;
     const float eps = 1e-6f;
@@ -125,50 +166,35 @@ __global__ void __launch_bounds__(128) sampler_fg_kernel(const float* __restrict
     const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
     const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
 
+    // ---- how far does the ray travel through occupied space -> number of samples and their spacing
+    float dist = 0.f;
+    if (GRID) {
+        float t = t_start, step = 0.f;
+        while (t < t_exit) {
+            const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
+            if (!in_grid(p.voxel, g)) break;
+            if (occupied(p.voxel, g)) dist = __fadd_rn(dist, step);  // the step that LED here (reference quirk: lags one voxel)
+            step = step_from_unit(p.ux, p.uy, p.uz, dx, dy, dz, g);
+            t = __fadd_rn(t, step);
+        }
+        dist = clampf(dist, 0.f, __fsub_rn(t_exit, t_start));
+    } else {
+        dist = __fsub_rn(t_exit, t_start);
+    }
     int to_create = 0;
     float spacing = 0.f;
-    int64_t dst = 0;
-    if (WRITE) {
-        const int2 sv = __ldg(reinterpret_cast<const int2*>(se_virtual) + ray);
-        const int cnt = sv.y - sv.x;
-        if (cnt <= 0) {
-            reinterpret_cast<int2*>(se_out)[ray] = make_int2(-1, -1);
-            return;
-        }
-        dst = __ldg(out_start + ray);
-        reinterpret_cast<int2*>(se_out)[ray] = make_int2((int)dst, (int)dst + cnt);
-        to_create = __ldg(n_create + ray);
-        spacing = __ldg(ray_max_dt + ray);
+    if (dist <= 0.f) {
+        to_create = 0;
+    } else if (dist > min_dist) {
+        to_create = (int)__fdiv_rn(dist, min_dist);
+        to_create = max(0, min(to_create, max_nr));
+        spacing = __fdiv_rn(dist, (float)to_create);
     } else {
-        // ---- how far does the ray travel through occupied space -> number of samples and their spacing
-        float dist = 0.f;
-        if (GRID) {
-            float t = t_start, step = 0.f;
-            while (t < t_exit) {
-                const float px = __fmaf_rn(t, dx, ox), py = __fmaf_rn(t, dy, oy), pz = __fmaf_rn(t, dz, oz);
-                const int v = pos_to_lin_idx(px, py, pz, g);
-                if (!in_grid(v, g)) break;
-                if (occupied(v, g)) dist = __fadd_rn(dist, step);  // the step that LED here (reference quirk: lags one voxel)
-                step = distance_to_next_voxel(px, py, pz, dx, dy, dz, g);
-                t = __fadd_rn(t, step);
-            }
-            dist = clampf(dist, 0.f, __fsub_rn(t_exit, t_start));
-        } else {
-            dist = __fsub_rn(t_exit, t_start);
-        }
-        if (dist <= 0.f) {
-            to_create = 0;
-        } else if (dist > min_dist) {
-            to_create = (int)__fdiv_rn(dist, min_dist);
-            to_create = max(0, min(to_create, max_nr));
-            spacing = __fdiv_rn(dist, (float)to_create);
-        } else {
-            to_create = 1;
-            spacing = dist;
-        }
+        to_create = 1;
+        spacing = dist;
     }
 
-    // ---- the sampling march (dry when !WRITE)
+    // ---- the sampling march
     int created = 0;
     const int64_t slot0 = ray * (int64_t)max_nr;
     if (to_create > 0 && to_create >= min_nr) {
@@ -183,57 +209,72 @@ __global__ void __launch_bounds__(128) sampler_fg_kernel(const float* __restrict
         }
         while (t < t_exit) {
             t = clampf(t, t_start, t_exit);
-            const float px = __fmaf_rn(t, dx, ox), py = __fmaf_rn(t, dy, oy), pz = __fmaf_rn(t, dz, oz);
             if (created >= to_create) break;
-            bool emit = true, occ = true;
-            int v = 0;
             if (GRID) {
-                v = pos_to_lin_idx(px, py, pz, g);
-                if (!in_grid(v, g)) break;
-                occ = occupied(v, g);
-                emit = occ && to_next == 0.f;
-            }
-            if (emit) {
-                if (WRITE) {
-                    const int64_t o = dst + created;
-                    s_idx[o] = (int32_t)(slot0 + created);
-                    s_3d[3 * o] = px;
-                    s_3d[3 * o + 1] = py;
-                    s_3d[3 * o + 2] = pz;
-                    s_dirs[3 * o] = dx;
-                    s_dirs[3 * o + 1] = dy;
-                    s_dirs[3 * o + 2] = dz;
-                    s_z[o] = t;
+                const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
+                if (!in_grid(p.voxel, g)) break;
+                const bool occ = occupied(p.voxel, g);
+                if (occ && to_next == 0.f) {
+                    z_stage[slot0 + created] = t;
+                    ++created;
+                    to_next = spacing;
                 }
-                ++created;
-                if (GRID) to_next = spacing;
-            }
-            if (GRID) {
-                const float to_voxel = distance_to_next_voxel(px, py, pz, dx, dy, dz, g);
-                float step;
+                const float to_voxel = step_from_unit(p.ux, p.uy, p.uz, dx, dy, dz, g);
+                float step = to_voxel;
                 if (occ) {
                     step = fminf(to_voxel, to_next);
                     to_next = __fsub_rn(to_next, step);
                     if (to_next <= eps) to_next = 0.f;
-                } else {
-                    step = to_voxel;
                 }
                 t = __fadd_rn(t, step);
             } else {
+                z_stage[slot0 + created] = t;
+                ++created;
                 t = __fadd_rn(t, spacing);
             }
         }
     }
-    if (!WRITE) {
-        // fewer than min_nr samples: the ray keeps (-1,-1) and ray_max_dt = -1 (the RaySamplesPacked constructor fill); otherwise its
-        // spacing is recorded — also for a ray with zero samples when min_nr == 0 (reference behaviour, RaySamplerGPU.cuh:253-262)
-        if (created >= min_nr) {
-            ray_max_dt[ray] = spacing;
-            reinterpret_cast<int2*>(se_virtual)[ray] = make_int2((int)slot0, (int)slot0 + created);
-        } else {
-            reinterpret_cast<int2*>(se_virtual)[ray] = make_int2(-1, -1);
+    // fewer than min_nr samples: the ray keeps (-1,-1) and ray_max_dt = -1 (the RaySamplesPacked constructor fill); otherwise its
+    // spacing is recorded — also for a ray with zero samples when min_nr == 0 (reference behaviour, RaySamplerGPU.cuh:253-262)
+    if (created >= min_nr) {
+        ray_max_dt[ray] = spacing;
+        reinterpret_cast<int2*>(se_virtual)[ray] = make_int2((int)slot0, (int)slot0 + created);
+    } else {
+        reinterpret_cast<int2*>(se_virtual)[ray] = make_int2(-1, -1);
+    }
+}
+
+// Pass 2 (one warp per ray, lanes over its samples): depth -> position, rows stored at the ray's compacted offset with unit stride.
+__global__ void __launch_bounds__(256) sampler_fg_expand_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int max_nr,
+                                                                const int32_t* __restrict__ se_virtual, const float* __restrict__ z_stage,
+                                                                const int32_t* __restrict__ out_start, int32_t* __restrict__ se_out,
+                                                                int32_t* __restrict__ s_idx, float* __restrict__ s_3d, float* __restrict__ s_dirs,
+                                                                float* __restrict__ s_z, int64_t n_rays) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = warp0; ray < n_rays; ray += n_warps) {
+        const int2 sv = __ldg(reinterpret_cast<const int2*>(se_virtual) + ray);
+        const int cnt = sv.y - sv.x;
+        if (cnt <= 0) {
+            if (lane == 0) reinterpret_cast<int2*>(se_out)[ray] = make_int2(-1, -1);
+            continue;
         }
-        n_create[ray] = to_create;
+        const int64_t dst = __ldg(out_start + ray), slot0 = ray * (int64_t)max_nr;
+        if (lane == 0) reinterpret_cast<int2*>(se_out)[ray] = make_int2((int)dst, (int)dst + cnt);
+        const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
+        const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
+        for (int i = lane; i < cnt; i += 32) {
+            const float t = __ldcs(z_stage + slot0 + i);
+            const int64_t o = dst + i;
+            __stcs(s_idx + o, (int32_t)(slot0 + i));
+            __stcs(s_z + o, t);
+            __stcs(s_3d + 3 * o, __fmaf_rn(t, dx, ox));
+            __stcs(s_3d + 3 * o + 1, __fmaf_rn(t, dy, oy));
+            __stcs(s_3d + 3 * o + 2, __fmaf_rn(t, dz, oz));
+            __stcs(s_dirs + 3 * o, dx);
+            __stcs(s_dirs + 3 * o + 1, dy);
+            __stcs(s_dirs + 3 * o + 2, dz);
+        }
     }
 }
 
@@ -288,15 +329,14 @@ __global__ void __launch_bounds__(128) occgrid_t_near_t_far_kernel(const float* 
     float near = t_start, far = t_start, t = t_start;
     bool first = true;
     while (t < t_exit) {
-        const float px = __fmaf_rn(t, dx, ox), py = __fmaf_rn(t, dy, oy), pz = __fmaf_rn(t, dz, oz);
-        const int v = pos_to_lin_idx(px, py, pz, g);
-        if (!in_grid(v, g)) break;
-        const bool occ = occupied(v, g);
+        const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
+        if (!in_grid(p.voxel, g)) break;
+        const bool occ = occupied(p.voxel, g);
         if (occ && first) {
             near = t;
             first = false;
         }
-        t = __fadd_rn(t, distance_to_next_voxel(px, py, pz, dx, dy, dz, g));
+        t = __fadd_rn(t, step_from_unit(p.ux, p.uy, p.uz, dx, dy, dz, g));
         if (occ) far = clampf(t, t_start, t_exit);
     }
     t_near[ray] = near;
@@ -324,67 +364,55 @@ using namespace vs;
 extern "C" {
 
 static int make_grid(int nr_voxels_per_dim, const float* extent, const uint8_t* occ, const uint8_t* roi, Grid* g) {
-    if (nr_voxels_per_dim < 1 || nr_voxels_per_dim > 1024 || !extent || !occ || !roi) return VS_ERR_INVALID_ARG;
+    if (nr_voxels_per_dim < 1 || nr_voxels_per_dim > 1024 || !extent || !occ) return VS_ERR_INVALID_ARG;
     if (!(extent[0] > 0.f && extent[1] > 0.f && extent[2] > 0.f)) return VS_ERR_INVALID_ARG;
-    *g = Grid{nr_voxels_per_dim, extent[0], extent[1], extent[2], occ, roi};
+    const bool pow2 = (nr_voxels_per_dim & (nr_voxels_per_dim - 1)) == 0;
+    *g = Grid{nr_voxels_per_dim, extent[0], extent[1], extent[2], pow2 ? 1.0f / (float)nr_voxels_per_dim : 0.f, occ, roi};
     return VS_OK;
 }
 
 // Pass 1 of compute_samples_fg (nr_voxels_per_dim == 0: no grid) / compute_samples_fg_in_grid_occupied_regions.
-//   rays_o, rays_d [n,3], t_entry, t_exit [n,1] f32 · extent: HOST float[3] · occupancy, roi: DEVICE u8 [nr_voxels_per_dim^3] (torch.bool)
+//   rays_o, rays_d [n,3], t_entry, t_exit [n,1] f32 · extent: HOST float[3] · occupancy, roi: DEVICE u8 [nr_voxels_per_dim^3] (torch.bool);
+//   roi == NULL: `occupancy` already holds occupancy && roi
 //   se_virtual [n,2] i32: the segment each ray WOULD own in the reference's uncompacted packet, (-1,-1) for rays without samples
-//   ray_max_dt [n,1] f32: pre-filled -1 by the caller (constructor fill), written for rays with samples · n_create [n] i32 scratch
+//   ray_max_dt [n,1] f32: pre-filled -1 by the caller (constructor fill), written for rays with samples
+//   z_stage [n * max_nr] f32: depth of sample i of ray r at r*max_nr + i (slots of real samples only; no initialisation needed)
 int vs_sampler_fg_count(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, float min_dist, int min_nr,
                         int max_nr, uint64_t rng_state, uint64_t rng_inc, int jitter, int nr_voxels_per_dim, const float* extent,
-                        const uint8_t* occupancy, const uint8_t* roi, int32_t* se_virtual, float* ray_max_dt, int32_t* n_create, int64_t n_rays,
+                        const uint8_t* occupancy, const uint8_t* roi, int32_t* se_virtual, float* ray_max_dt, float* z_stage, int64_t n_rays,
                         void* stream) {
     VS_CHECK_ARG(n_rays >= 0 && max_nr >= 0 && min_nr >= 0 && n_rays * (int64_t)max_nr <= 0x7fffffffLL);
     if (n_rays == 0) return VS_OK;
-    VS_CHECK_ARG(rays_o && rays_d && t_entry && t_exit && se_virtual && ray_max_dt && n_create);
-    Grid g{0, 1.f, 1.f, 1.f, nullptr, nullptr};
+    VS_CHECK_ARG(rays_o && rays_d && t_entry && t_exit && se_virtual && ray_max_dt && (z_stage || max_nr == 0));
+    Grid g{0, 1.f, 1.f, 1.f, 0.f, nullptr, nullptr};
     const Pcg rng{rng_state, rng_inc};
     const unsigned grid = (unsigned)div_up(n_rays, 128);
     if (nr_voxels_per_dim > 0) {
         int e = make_grid(nr_voxels_per_dim, extent, occupancy, roi, &g);
         if (e != VS_OK) return e;
-        sampler_fg_kernel<true, false><<<grid, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, min_dist, min_nr, max_nr, rng,
-                                                                                jitter, g, se_virtual, ray_max_dt, n_create, nullptr, nullptr,
-                                                                                nullptr, nullptr, nullptr, nullptr, n_rays);
+        sampler_fg_march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, min_dist, min_nr, max_nr, rng, jitter,
+                                                                               g, se_virtual, ray_max_dt, z_stage, n_rays);
     } else {
-        sampler_fg_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, min_dist, min_nr, max_nr, rng,
-                                                                                 jitter, g, se_virtual, ray_max_dt, n_create, nullptr, nullptr,
-                                                                                 nullptr, nullptr, nullptr, nullptr, n_rays);
+        sampler_fg_march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, min_dist, min_nr, max_nr, rng,
+                                                                                jitter, g, se_virtual, ray_max_dt, z_stage, n_rays);
     }
     return launched(1);
 }
 
 // Pass 2: out_start [n] i32 from vs_segment_offsets(se_virtual); writes se_out [n,2] and, for every sample, samples_idx (the slot of the
-// reference's uncompacted packet), samples_3d, samples_dirs, samples_z at its compacted position.
-int vs_sampler_fg_write(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, float min_dist, int min_nr,
-                        int max_nr, uint64_t rng_state, uint64_t rng_inc, int jitter, int nr_voxels_per_dim, const float* extent,
-                        const uint8_t* occupancy, const uint8_t* roi, const int32_t* se_virtual, const float* ray_max_dt,
-                        const int32_t* n_create, const int32_t* out_start, int32_t* se_out, int32_t* samples_idx, float* samples_3d,
-                        float* samples_dirs, float* samples_z, int64_t n_rays, void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && max_nr >= 0 && min_nr >= 0);
+// reference's uncompacted packet), samples_3d = o + z d, samples_dirs, samples_z at its compacted position.
+int vs_sampler_fg_write(const float* rays_o, const float* rays_d, int max_nr, const int32_t* se_virtual, const float* z_stage,
+                        const int32_t* out_start, int32_t* se_out, int32_t* samples_idx, float* samples_3d, float* samples_dirs,
+                        float* samples_z, int64_t n_rays, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && max_nr >= 0);
     if (n_rays == 0) return VS_OK;
-    VS_CHECK_ARG(rays_o && rays_d && t_entry && t_exit && se_virtual && ray_max_dt && n_create && out_start && se_out);
-    Grid g{0, 1.f, 1.f, 1.f, nullptr, nullptr};
-    const Pcg rng{rng_state, rng_inc};
-    const unsigned grid = (unsigned)div_up(n_rays, 128);
-    int32_t* sv = const_cast<int32_t*>(se_virtual);
-    float* md = const_cast<float*>(ray_max_dt);
-    int32_t* nc = const_cast<int32_t*>(n_create);
-    if (nr_voxels_per_dim > 0) {
-        int e = make_grid(nr_voxels_per_dim, extent, occupancy, roi, &g);
-        if (e != VS_OK) return e;
-        sampler_fg_kernel<true, true><<<grid, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, min_dist, min_nr, max_nr, rng,
-                                                                               jitter, g, sv, md, nc, out_start, se_out, samples_idx, samples_3d,
-                                                                               samples_dirs, samples_z, n_rays);
-    } else {
-        sampler_fg_kernel<false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, min_dist, min_nr, max_nr, rng,
-                                                                                jitter, g, sv, md, nc, out_start, se_out, samples_idx,
-                                                                                samples_3d, samples_dirs, samples_z, n_rays);
-    }
+    VS_CHECK_ARG(rays_o && rays_d && se_virtual && out_start && se_out);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)std::min<int64_t>(div_up(n_rays, 8), (int64_t)sms * 8);
+    sampler_fg_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, max_nr, se_virtual, z_stage, out_start, se_out, samples_idx,
+                                                                     samples_3d, samples_dirs, samples_z, n_rays);
     return launched(1);
 }
 

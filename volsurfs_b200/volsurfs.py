@@ -765,7 +765,7 @@ class OccupancyGrid:
 class RaySampler:
     """Static ray samplers (include/volsurfs/RaySampler.cuh:9-64, bound at PyBridge.cxx:131-139).  The foreground samplers return the
     COMPACTED packet, like the reference after its closing compact_to_valid_samples (src/RaySampler.cu:236,340), but never build the
-    nr_rays x max_nr_samples_per_ray staging packet (csrc/sampler.cu)."""
+    nr_rays x max_nr_samples_per_ray staging packet of 36-byte rows: only 4 bytes of depth per slot are staged (csrc/sampler.cu)."""
 
     #: host copy of the reference's static ``pcg32 m_rng``: passed by value to a jittered launch, advanced by 2^32 afterwards
     _rng_state = 0x853C49E6748FEA9B
@@ -788,10 +788,10 @@ class RaySampler:
             ext = (ctypes.c_float * 3)(*[float(v) for v in ext_list])
         se_virtual = torch.empty((n, 2), dtype=torch.int32, device=dev)
         ray_max_dt = torch.full((n, 1), -1.0, dtype=torch.float32, device=dev)
-        n_create = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        rng = (RaySampler._rng_state, RaySampler._rng_inc)
-        common = [ptr(o), ptr(d), ptr(a), ptr(b), float(min_dist), min_nr, max_nr, rng[0], rng[1], int(bool(jitter)), int(nv), ext, ptr(occ), ptr(roi)]
-        check(L.vs_sampler_fg_count(*common, ptr(se_virtual), ptr(ray_max_dt), ptr(n_create), n, st), "vs_sampler_fg_count")
+        z_stage = torch.empty(max(n * max_nr, 1), dtype=torch.float32, device=dev)  # 4 B per slot; only real samples are touched
+        check(L.vs_sampler_fg_count(ptr(o), ptr(d), ptr(a), ptr(b), float(min_dist), min_nr, max_nr, RaySampler._rng_state, RaySampler._rng_inc,
+                                    int(bool(jitter)), int(nv), ext, ptr(occ), ptr(roi), ptr(se_virtual), ptr(ray_max_dt), ptr(z_stage), n, st),
+              "vs_sampler_fg_count")
         scratch = torch.empty(max(int(L.vs_pack_scratch_bytes(n)), 8), dtype=torch.uint8, device=dev)
         out_start = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         total_dev = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -808,7 +808,7 @@ class RaySampler:
             ray_start_end_idx=torch.empty((n, 2), dtype=torch.int32, device=dev),
             ray_o=o.clone(), ray_d=d.clone(), ray_enter=a.clone(), ray_exit=b.clone(), ray_max_dt=ray_max_dt,
         )
-        check(L.vs_sampler_fg_write(*common, ptr(se_virtual), ptr(ray_max_dt), ptr(n_create), ptr(out_start), ptr(out.ray_start_end_idx),
+        check(L.vs_sampler_fg_write(ptr(o), ptr(d), max_nr, ptr(se_virtual), ptr(z_stage), ptr(out_start), ptr(out.ray_start_end_idx),
                                     ptr(out.samples_idx), ptr(out.samples_3d), ptr(out.samples_dirs), ptr(out.samples_z), n, st),
               "vs_sampler_fg_write")
         if jitter:
@@ -834,7 +834,7 @@ class RaySampler:
         ext = grid_extent.tolist() if hasattr(grid_extent, "tolist") else list(grid_extent)
         return RaySampler._fg(rays_o, rays_d, ray_t_entry, ray_t_exit, min_dist_between_samples, min_nr_samples_per_ray,
                               max_nr_samples_per_ray, jitter_samples, values_dim,
-                              (int(nr_voxels_per_dim), ext, grid_occupancy.contiguous(), grid_roi.contiguous()))
+                              (int(nr_voxels_per_dim), ext, torch.logical_and(grid_occupancy, grid_roi).contiguous(), None))
 
     @staticmethod
     def compute_samples_bg(rays_o, rays_d, ray_t_exit, ray_t_far, nr_samples, jitter_samples):
