@@ -65,6 +65,29 @@ def test_pybridge_list_matches_reference_if_mounted():
     assert sorted(set(re.findall(r'\.def_readwrite\("(\w+)"', block))) == sorted(RSP_ATTRS)
 
 
+def test_sampler_and_grid_surface_against_pybridge_if_mounted():
+    """RaySampler / OccupancyGrid (PyBridge.cxx:33-68,131-139): every method the shim offers is bound by the reference under the same
+    name, and what is left out is exactly the documented set"""
+    src = Path("/root/reference/src/PyBridge.cxx")
+    if not src.exists():
+        pytest.skip("reference not mounted")
+    from volsurfs_b200.volsurfs import OccupancyGrid, RaySampler
+
+    text = "\n".join(ln for ln in src.read_text().splitlines() if not ln.strip().startswith("//"))
+    og = text[text.index("py::class_<OccupancyGrid>"):text.index("py::class_<RaySamplesPacked>")]
+    rs = text[text.index("py::class_<RaySampler>"):]
+    og_ref = set(re.findall(r'\.def(?:_static)?\("(\w+)"', og))
+    rs_ref = set(re.findall(r'\.def(?:_static)?\("(\w+)"', rs))
+    og_have = {n for n in dir(OccupancyGrid) if not n.startswith("_") and callable(getattr(OccupancyGrid, n))} - {"set_grid_roi"}
+    rs_have = {n for n in dir(RaySampler) if not n.startswith("_") and callable(getattr(RaySampler, n))}
+    assert og_have <= og_ref and rs_have <= rs_ref
+    assert og_ref - og_have == {"init_sphere_roi", "get_grid_max_value_in_roi", "get_grid_min_value_in_roi", "get_grid_lower_left_voxels_vertices",
+                                "get_grid_samples", "get_random_grid_samples", "get_random_grid_samples_in_roi", "update_grid_values",
+                                "update_grid_occupancy_with_density_values", "update_grid_occupancy_with_sdf_values",
+                                "get_first_rays_sample_start_of_grid_occupied_regions", "advance_ray_sample_to_next_occupied_voxel"}
+    assert {"compute_samples_fg", "compute_samples_fg_in_grid_occupied_regions", "compute_samples_bg"} <= rs_have
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
 

@@ -226,3 +226,13 @@ def test_argument_errors():
         RaySampler.compute_samples_fg_in_grid_occupied_regions(o, o, torch.zeros(4, 1, device="cuda"), torch.ones(4, 1, device="cuda"), 0.1, 1, 8, False,
                                                               8, [1, 1, 1], torch.ones(10, dtype=torch.bool, device="cuda"),
                                                               torch.ones(512, dtype=torch.bool, device="cuda"), 1)
+
+
+def test_init_with_one_sample_per_ray():
+    from volsurfs_b200.volsurfs import RaySampler
+
+    p, d = torch.rand(100, 3, device="cuda"), torch.rand(100, 3, device="cuda")
+    rsp = RaySampler.init_with_one_sample_per_ray(p, d)
+    assert rsp.get_total_nr_samples() == 100 and torch.equal(rsp.samples_3d, p) and torch.equal(rsp.samples_dirs, d)
+    assert float(rsp.samples_z.abs().max()) == 0.0 and float(rsp.samples_dt.abs().max()) == 0.0
+    assert rsp.ray_start_end_idx[7].tolist() == [7, 8]

@@ -851,3 +851,17 @@ class RaySampler:
         if jitter_samples:
             RaySampler._rng_state = _pcg_advance(RaySampler._rng_state, RaySampler._rng_inc)
         return out
+
+    @staticmethod
+    def init_with_one_sample_per_ray(samples_3d, samples_dirs):
+        """one sample per ray at z = 0 (src/RaySampler.cu:28-70; kernel RaySamplerGPU.cuh:490-526): a packet of copies, built from device
+        tensor copies — there is no arithmetic to put in a kernel"""
+        p, d = _f32c(samples_3d, "samples_3d", 3), _f32c(samples_dirs, "samples_dirs", 3)
+        n = int(p.shape[0])
+        out = RaySamplesPacked(n, n, 0, 1)
+        out.samples_3d, out.samples_dirs = p.clone(), d.clone()
+        out.samples_z.zero_()
+        out.samples_dt.zero_()
+        idx = torch.arange(n, dtype=torch.int32, device=p.device)
+        out.ray_start_end_idx = torch.stack([idx, idx + 1], dim=1).contiguous()
+        return out
