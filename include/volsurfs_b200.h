@@ -162,6 +162,12 @@ int vs_shells_expand(const void* handle, int layer, const float* rays_o, const f
 int vs_shells_sample_normals(const void* handle, const int32_t* layer_of, const int32_t* tri, int64_t n_samples,
                              const int64_t* n_valid_dev, float* normals, void* stream);
 
+/* Texture coordinates of packed hits (volsurfs_py/methods/volsurfs.py:509-516: uv = sum_j barycentric_j * face_uv_j, barycentric =
+ * (1-u-v, u, v)).  bary_uv [n,2]: the packer's samples_uv; face_uvs [sum_l F_l, 3, 2]: per-face-vertex uvs of all layers back to back;
+ * face_offset [n_layers] i32: first face row of every layer.  All DEVICE pointers.  n_valid_dev may be NULL. */
+int vs_shells_sample_uvs(const int32_t* layer_of, const int32_t* tri, const float* bary_uv, const float* face_uvs, const int32_t* face_offset,
+                         int64_t n_samples, const int64_t* n_valid_dev, float* out_uv, void* stream);
+
 /* ---- fused appearance head (tensor cores) ----------------------------------------------------------------------------
  * Replaces RGB.forward (volsurfs_py/models/rgb.py:104-149: [pos features | SH(dirs) | normals?] -> MLP -> sigmoid), MLP.forward
  * (models/mlp.py:8-52), SHEncoder.__call__ (encodings/sphericalharmonics.py:84-153) and the alpha decay of

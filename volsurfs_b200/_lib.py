@@ -49,6 +49,7 @@ SIGNATURES = {
     "vs_shells_trace": (c_int, [_P, _P, _P, _I64, c_int, c_int, _P, _P, _P, _P, _P]),
     "vs_shells_expand": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "vs_shells_sample_normals": (c_int, [_P, _P, _P, _I64, _P, _P, _P]),
+    "vs_shells_sample_uvs": (c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "vs_mlp_blob_bytes": (_I64, [c_int, _P]),
     "vs_mlp_pack": (c_int, [c_int, _P, _P, _P, _P, _P]),
     "vs_mlp_forward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _I64, _P, c_int, _P]),

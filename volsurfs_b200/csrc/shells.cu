@@ -643,6 +643,28 @@ static void free_layer(Layer& L) {
     L = Layer();
 }
 
+// Texture coordinates of packed hits (volsurfs_py/methods/volsurfs.py:509-516: uv = sum_j barycentric_j * face_uv_j with barycentric =
+// (1-(u+v), u, v) as raytracelib returns it), evaluated in torch's order: ((b0*uv0) + (b1*uv1)) + (b2*uv2) per component, separate
+// roundings.  face_uvs: [sum_l F_l, 3, 2] per-face-vertex uvs of all layers back to back, face_offset[l]: first face row of layer l.
+__global__ void __launch_bounds__(256) shells_uvs_kernel(const int32_t* __restrict__ layer_of, const int32_t* __restrict__ tri,
+                                                         const float* __restrict__ bary_uv, const float* __restrict__ face_uvs,
+                                                         const int32_t* __restrict__ face_offset, int64_t n_samples,
+                                                         const int64_t* __restrict__ n_valid_dev, float* __restrict__ out_uv) {
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float2 b = __ldg(reinterpret_cast<const float2*>(bary_uv) + s);
+    const float b0 = __fsub_rn(1.f, __fadd_rn(b.x, b.y));  // raytracelib: Vector3f(1 - (u + v), u, v), src/bvh.cu:460
+    const int64_t row = (int64_t)__ldg(face_offset + __ldg(layer_of + s)) + __ldg(tri + s);
+    const float2* f = reinterpret_cast<const float2*>(face_uvs) + 3 * row;
+    const float2 u0 = __ldg(f), u1 = __ldg(f + 1), u2 = __ldg(f + 2);
+    float2 o;
+    o.x = __fadd_rn(__fadd_rn(__fmul_rn(b0, u0.x), __fmul_rn(b.x, u1.x)), __fmul_rn(b.y, u2.x));
+    o.y = __fadd_rn(__fadd_rn(__fmul_rn(b0, u0.y), __fmul_rn(b.x, u1.y)), __fmul_rn(b.y, u2.y));
+    reinterpret_cast<float2*>(out_uv)[s] = o;
+}
+
 }  // namespace vs
 
 using namespace vs;
@@ -795,6 +817,17 @@ int vs_shells_sample_normals(const void* handle, const int32_t* layer_of, const 
     const Shells* S = reinterpret_cast<const Shells*>(handle);
     shells_normals_kernel<<<(unsigned)div_up(n_samples, 256), 256, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_of, tri, n_samples,
                                                                                               n_valid_dev, normals);
+    return launched(1);
+}
+
+// Texture coordinates of packed hits from their barycentric (u, v): see shells_uvs_kernel.  All pointers DEVICE.
+int vs_shells_sample_uvs(const int32_t* layer_of, const int32_t* tri, const float* bary_uv, const float* face_uvs, const int32_t* face_offset,
+                         int64_t n_samples, const int64_t* n_valid_dev, float* out_uv, void* stream) {
+    VS_CHECK_ARG(n_samples >= 0);
+    if (n_samples == 0) return VS_OK;
+    VS_CHECK_ARG(layer_of && tri && bary_uv && face_uvs && face_offset && out_uv);
+    shells_uvs_kernel<<<(unsigned)div_up(n_samples, 256), 256, 0, (cudaStream_t)stream>>>(layer_of, tri, bary_uv, face_uvs, face_offset, n_samples,
+                                                                                          n_valid_dev, out_uv);
     return launched(1);
 }
 

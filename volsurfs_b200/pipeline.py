@@ -213,6 +213,104 @@ class PipelinedTrainingStep:
         self.loss_pin.copy_(self.loss[b], non_blocking=True)
 
 
+class TexturedShellRenderer:
+    """The same path with the reference's DEFAULT appearance (config/volsurfs/base_5.cfg: using_neural_textures, per-surface independent
+    colour and transparency models): every layer k owns an ``SHNeuralTextures`` for rgb (3 channels) and one for alpha (1 channel),
+    queried with the hit's texture coordinates and the ray direction (volsurfs.py:535-599), alpha modulated by the no-grad decay of
+    volsurfs.py:583-594, then composited.  Differentiable end to end through torch autograd: ``CompositeFunc`` (fused compositing
+    backward) -> per-layer routing -> ``SHNeuralTextures`` (texture-network backward kernels).
+
+    Hits are routed to their layer's models with one stable sort by layer per step (one host read of the per-layer counts; the
+    reference reads ``any_hit`` on the host once per mesh)."""
+
+    def __init__(self, tracer: ShellTracer, rgb_models, alpha_models, bg_color=(1.0, 1.0, 1.0), with_alpha_decay: bool = True):
+        assert len(rgb_models) == tracer.nr_meshes and len(alpha_models) == tracer.nr_meshes
+        self.tracer = tracer
+        self.rgb_models = torch.nn.ModuleList(rgb_models)
+        self.alpha_models = torch.nn.ModuleList(alpha_models)
+        self.K = tracer.nr_meshes
+        self.with_alpha_decay = bool(with_alpha_decay)
+        self.bg_color = torch.tensor(bg_color, dtype=torch.float32, device=tracer.device)
+
+    def parameters(self):
+        return list(self.rgb_models.parameters()) + list(self.alpha_models.parameters())
+
+    def intersect_and_pack(self, rays_o, rays_d):
+        rsp = self.tracer.render_samples(rays_o, rays_d, exact_size=True, with_normals=True)
+        rsp.samples_tex_uv = self.tracer.sample_uvs(rsp)
+        return rsp
+
+    def shade(self, rsp):
+        """per-hit colour [S,3] and alpha [S,1]"""
+        S = rsp.get_max_nr_samples()
+        dev = rsp.samples_z.device
+        if S == 0:
+            return torch.zeros((0, 3), device=dev), torch.zeros((0, 1), device=dev)
+        layer = rsp.samples_layer.view(-1).long()
+        order = torch.argsort(layer, stable=True)
+        counts = torch.bincount(layer, minlength=self.K).tolist()
+        uv_s, dirs_s = rsp.samples_tex_uv[order], rsp.samples_dirs[order]
+        rgb_parts, alpha_parts, o = [], [], 0
+        for k in range(self.K):
+            n = counts[k]
+            if n:
+                rgb_parts.append(self.rgb_models[k](uv_coords=uv_s[o:o + n], view_dirs=dirs_s[o:o + n]))
+                alpha_parts.append(self.alpha_models[k](uv_coords=uv_s[o:o + n], view_dirs=dirs_s[o:o + n]))
+            o += n
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(S, device=dev)
+        rgb = torch.cat(rgb_parts)[inv]
+        alpha = torch.cat(alpha_parts)[inv]
+        if self.with_alpha_decay:
+            with torch.no_grad():  # volsurfs.py:583-594
+                dot = torch.sum(-rsp.samples_dirs * rsp.samples_normals, dim=1, keepdim=True).clamp(0.0, 1.0)
+                decay = torch.sigmoid(10.0 * dot) * 2.0 - 1.0
+            alpha = alpha * decay
+        return rgb, alpha
+
+    def render(self, rays_o, rays_d):
+        from .volume_rendering import composite
+
+        rsp = self.intersect_and_pack(rays_o, rays_d)
+        rgb, alpha = self.shade(rsp)
+        rgb_fg, depth, acc, bgT = composite(rsp, alpha, rgb)
+        pred = rgb_fg + bgT * self.bg_color.view(1, 3)  # volsurfs.py:708
+        return {"rgb": pred, "rgb_fg": rgb_fg, "depth": depth, "acc": acc, "bg_transmittance": bgT, "ray_samples_packed": rsp,
+                "samples_rgb": rgb, "samples_alpha": alpha}
+
+    def render_fwd_bwd(self, rays_o, rays_d, gt_rgb):
+        """forward, L1 photometric loss (utils/losses.py:14-19), backward to every texture network's parameters (``.grad``)"""
+        out = self.render(rays_o, rays_d)
+        loss = (out["rgb"] - gt_rgb).abs().mean()
+        loss.backward()
+        out["loss"] = loss.detach()
+        return out
+
+
+def make_synthetic_textured_renderer(K=5, n_lat=224, n_lon=224, deg_res=(2048, 1024, 512, 256), sh_range=(15.0, 15.0, 15.0, 15.0), seed=0,
+                                     offset=0.01, table_init=None):
+    """C2-shaped scene with the default appearance: K nested shells with a lat/lon texture chart, per-layer SHNeuralTextures for colour
+    and transparency configured like config/volsurfs/base_5.cfg (sh_degree 3, lerp, squeezing + 8-bit quantisation, align_to_webgl)"""
+    from .synthetic import shell_face_uvs, shell_meshes
+    from .textures import SHNeuralTextures
+
+    meshes = shell_meshes(K=K, n_lat=n_lat, n_lon=n_lon, offset=offset)
+    tracer = ShellTracer(meshes)
+    tracer.set_face_uvs([shell_face_uvs(n_lat, n_lon)] * K)
+    torch.manual_seed(4321 + seed)
+
+    def model(c):
+        m = SHNeuralTextures(sh_deg=3, nr_channels=c, sh_range=list(sh_range), anchor=False, lerp=True, deg_res=list(deg_res),
+                             quantize_output=True, squeeze_output=True, align_to_webgl=True)
+        if table_init is not None:  # tiny-cuda-nn starts at U(-1e-4, 1e-4): every texel equal; tests want some structure
+            with torch.no_grad():
+                for nt in m.neural_textures:
+                    nt.model.table.copy_((torch.rand_like(nt.model.table) * 2 - 1) * table_init)
+        return m.cuda()
+
+    return TexturedShellRenderer(tracer, [model(3) for _ in range(K)], [model(1) for _ in range(K)]), meshes
+
+
 def make_synthetic_renderer(K=5, n_lat=224, n_lon=224, hidden=(128, 128, 64), pos_dim=51, seed=0, offset=0.01, device=None):
     """C2/C5-shaped scene: K nested lumpy shells (~100k triangles each) + fixed-seed legacy heads (rgb: 3 outputs, alpha: 1 output
     with alpha decay, both normal-independent, GELU)"""

@@ -175,6 +175,30 @@ class ShellTracer:
         return rsp
 
     @torch.no_grad()
+    def set_face_uvs(self, face_uvs_per_layer):
+        """per-face-vertex texture coordinates of every layer ([F_l,3,2] each; ``TensorMesh.get_faces_uvs()`` in the reference)"""
+        dev = self.device
+        tabs = [torch.as_tensor(t, dtype=torch.float32).reshape(-1, 3, 2) for t in face_uvs_per_layer]
+        assert len(tabs) == self.nr_meshes
+        offs, o = [], 0
+        for t in tabs:
+            offs.append(o)
+            o += int(t.shape[0])
+        self._face_uvs = torch.cat(tabs).contiguous().to(dev)
+        self._face_uv_offset = torch.tensor(offs, dtype=torch.int32, device=dev)
+
+    @torch.no_grad()
+    def sample_uvs(self, rsp):
+        """texture coordinates of the packed hits, uv = sum_j barycentric_j * face_uv_j (volsurfs.py:509-516) -> [S,2]"""
+        assert getattr(self, "_face_uvs", None) is not None, "call set_face_uvs first"
+        S = rsp.get_max_nr_samples()
+        out = torch.zeros((S, 2), dtype=torch.float32, device=self.device)
+        check(_lib.lib().vs_shells_sample_uvs(ptr(rsp.samples_layer), ptr(rsp.samples_triangle), ptr(rsp.samples_uv), ptr(self._face_uvs),
+                                              ptr(self._face_uv_offset), S, ptr(getattr(rsp, "total_dev", None)), ptr(out), _stream()),
+              "vs_shells_sample_uvs")
+        return out
+
+    @torch.no_grad()
     def trace(self, rays_o, rays_d, mesh_id: int = 0, **_unused):
         """Reference-compatible single-mesh trace (raytracer.py:35-113): same dict keys / dtypes / shapes."""
         assert mesh_id < self.nr_meshes, "mesh_id must be smaller than the number of meshes in the scene"

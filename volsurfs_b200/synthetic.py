@@ -149,6 +149,26 @@ def shell_meshes(K: int = 5, n_lat: int = 224, n_lon: int = 224, r_base: float =
     return meshes
 
 
+def shell_face_uvs(n_lat: int = 224, n_lon: int = 224) -> np.ndarray:
+    """Per-face-vertex texture coordinates [F,3,2] for the faces of ``shell_meshes`` (what ``TensorMesh.get_faces_uvs()`` returns in the
+    reference, volsurfs.py:511): the lat/lon chart u = phi / 2pi, v = theta / pi, with the seam column unwrapped (u = 1 instead of 0) and
+    the poles pinned to the u of the cap triangle's first ring vertex."""
+    theta = np.linspace(0.0, np.pi, n_lat + 1)[1:-1]
+    rows, cols = n_lat - 1, n_lon
+    v_ring = (theta / np.pi).astype(np.float64)
+    r, c = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+
+    def uv(rr, cc):  # cc may be == cols (the unwrapped seam)
+        return np.stack([cc / cols, v_ring[rr]], -1)
+
+    qa = np.stack([uv(r[:-1], c[:-1]), uv(r[1:], c[1:]), uv(r[1:], c[1:] + 1)], -2).reshape(-1, 3, 2)
+    qb = np.stack([uv(r[:-1], c[:-1]), uv(r[1:], c[1:] + 1), uv(r[:-1], c[:-1] + 1)], -2).reshape(-1, 3, 2)
+    cc = np.arange(cols)
+    cap_n = np.stack([np.stack([cc / cols, np.zeros(cols)], -1), uv(np.zeros(cols, int), cc), uv(np.zeros(cols, int), cc + 1)], -2)
+    cap_s = np.stack([np.stack([cc / cols, np.ones(cols)], -1), uv(np.full(cols, rows - 1), cc + 1), uv(np.full(cols, rows - 1), cc)], -2)
+    return np.ascontiguousarray(np.concatenate([qa, qb, cap_n, cap_s]).astype(np.float32))
+
+
 def camera_rays(height: int = 800, width: int = 800, fov_deg: float = 40.0, radius: float = 1.5, azimuth_deg: float = 30.0,
                 elevation_deg: float = 20.0, shuffle_seed=None):
     """Pinhole camera on an orbit looking at the origin; rays in scanline order, directions normalised
