@@ -44,7 +44,7 @@ def _check(se, alpha, rgb, z, grads, mode):
         assert grad_err(got, ob[key]) < TOL, key
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_c1_shells_vs_oracle(mode):
     """BASELINE config 1: 4096 rays x 5 layers, Bernoulli(0.8) hits, exact 0/1 alphas, empty rays."""
     d = dense_layers(4096, 5, seed_offset=1)
@@ -75,7 +75,7 @@ def test_golden_reference_lines(mode):
         assert grad_err(bwd[1], g["fp32_d_rgb"][ray, lay]) < TOL
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3, 5, 6, 7])
+@pytest.mark.parametrize("mode", [0, 2, 3, 5, 6, 7, 8])
 def test_c3_nerf_packets_vs_oracle(mode):
     """Variable-length packets up to 1024 samples/ray with 35 % empty rays (config 3 shape, 6k-ray subset)."""
     p = nerf_packets(6000, seed_offset=3)
@@ -87,14 +87,14 @@ def test_long_rays_spill_path():
     """rays longer than W*W = 1024 samples exercise the scratch path of the backward scan kernel"""
     p = nerf_packets(40, seed_offset=4, max_per_ray=3000, mean=1500.0, sigma=0.4, p_empty=0.1)
     assert int(p["counts"].max()) > 1024
-    for mode in (2, 3, 5):  # 2: one sample per lane (spills beyond 32*32), 5: quad per lane with 8 lanes (spills beyond 4*8*8)
+    for mode in (2, 3, 5, 8):  # 8: ring family (spills beyond 32 chunks of 128); 2: one sample per lane (spills beyond 32*32), 5: quad per lane with 8 lanes (spills beyond 4*8*8)
         _check(p["se"], p["alpha"], p["rgb"], p["z"], p, mode)
 
 
 @pytest.mark.parametrize("n_rays,K", [(1, 5), (255, 5), (257, 9), (1000, 1)])
 def test_edge_sizes(n_rays, K):
     d = all_hit_packed(n_rays, K)
-    for mode in (1, 2, 3, 4, 5, 7):
+    for mode in (1, 2, 3, 4, 5, 7, 8):
         _check(d["se"], d["alpha"], d["rgb"], d["z"], d, mode)
 
 
@@ -103,7 +103,7 @@ def test_all_empty_and_zero_rays():
 
     se = torch.full((300, 2), -1, dtype=torch.int32)
     e1, e3 = torch.zeros(0, 1), torch.zeros(0, 3)
-    for mode in (0, 1, 2, 3, 4, 6):
+    for mode in (0, 1, 2, 3, 4, 6, 8):
         rgb, depth, acc, bgT = VR.composite(_rsp(se), e1.cuda(), e3.cuda(), e1.cuda(), mode=mode)
         assert torch.all(rgb == 0) and torch.all(depth == 0) and torch.all(acc == 0) and torch.all(bgT == 1)
     rgb, depth, acc, bgT = VR.composite(_rsp(torch.zeros((0, 2), dtype=torch.int32)), e1.cuda(), e3.cuda(), e1.cuda())

@@ -25,6 +25,9 @@
 //   * "scan" (longer rays, NeRF-style packets): a group of W lanes per ray (W = 16/32), W-wide chunks read straight
 //     from global memory (contiguous per chunk), shuffle-based exclusive cumprod forward, shuffle-based reverse affine
 //     scan backward, running values carried between chunks.
+#include <algorithm>
+#include <cstdlib>
+
 #include "vs_common.cuh"
 
 namespace vs {
@@ -495,6 +498,390 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan4_kernel(
 }
 
 // =============================================================================================
+// ring family (long, variable-length rays: NeRF-style packets)
+// =============================================================================================
+// What bounds the scan kernels above on long rays is bytes in flight: a warp waits a full memory latency for every chunk it has
+// prefetched one iteration earlier, and most rays are one or two chunks long, so nothing is in flight while a ray starts or ends.
+// Here a warp owns 32 consecutive rays and streams ALL their chunks (128 samples: an aligned quad per lane, as in the coarsened scan
+// kernels) through its own shared-memory ring with cp.async — kRingDepth chunks of 2.5 KB in flight per warp, across ray boundaries,
+// at no register cost.  Every lane copies exactly the bytes it later reads, so the ring needs no barrier: cp.async.wait_group is
+// per thread.  The arithmetic is that of the coarsened scan kernels (serial 4-sample products + one shuffle scan per chunk).
+constexpr int kRingWarps = 8;
+constexpr int kRingDepth = 3;
+constexpr int kRingStageFloats = 640;  // 128 alpha | 128 z | 384 rgb
+constexpr int kRingChunk = 128;        // samples per chunk (4 per lane)
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_full(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// the 32 rays of a warp's batch, one per lane; chunks are anchored at the ray's start rounded down to a multiple of four samples
+// (sample indices fit 32 bits: ray_start_end_idx is int32)
+struct RingRays {
+    int start, end, nch;
+};
+__device__ __forceinline__ RingRays ring_load_rays(const int32_t* __restrict__ se, int64_t ray, int64_t n_rays) {
+    RingRays r{0, 0, 0};
+    if (ray < n_rays) {
+        int st = 0;
+        const int n = load_segment(se, ray, st);
+        if (n > 0) {
+            r.start = st;
+            r.end = st + n;
+            r.nch = (r.end - (st & ~3) + kRingChunk - 1) / kRingChunk;
+        }
+    }
+    return r;
+}
+
+// warp-uniform cursor over the (ray, item) pairs of a batch: the current ray's segment is cached and re-fetched (three shuffles) only
+// when the cursor moves to another ray
+struct RingCursor2 {
+    int r, k, items, start, end, nch;
+};
+template <bool BWD>
+__device__ __forceinline__ void ring_cursor_load(RingCursor2& c, const RingRays& mine) {
+    // first ray at or after c.r that has items (BWD: one reverse item for single-chunk rays, else nch alpha-only + nch reverse items)
+    const unsigned has = __ballot_sync(VS_FULL_MASK, mine.nch > 0);
+    const unsigned rest = c.r < 32 ? (has >> c.r) : 0u;
+    if (rest == 0u) {
+        c.r = 32;
+        return;
+    }
+    c.r += __ffs(rest) - 1;
+    c.k = 0;
+    c.start = __shfl_sync(VS_FULL_MASK, mine.start, c.r);
+    c.end = __shfl_sync(VS_FULL_MASK, mine.end, c.r);
+    c.nch = __shfl_sync(VS_FULL_MASK, mine.nch, c.r);
+    c.items = BWD ? (c.nch == 1 ? 1 : 2 * c.nch) : c.nch;
+}
+template <bool BWD>
+__device__ __forceinline__ void ring_cursor_next(RingCursor2& c, const RingRays& mine) {
+    if (++c.k >= c.items) {
+        ++c.r;
+        ring_cursor_load<BWD>(c, mine);
+    }
+}
+
+// this lane's quad of chunk c of the ray [start, end): 16-byte async copies (zero fill past the end of the arrays); ALPHA_ONLY for
+// the backward's transmittance pass
+template <bool ALPHA_ONLY>
+__device__ __forceinline__ void ring_issue(float* stage, const float* __restrict__ alpha, const float* __restrict__ rgb,
+                                           const float* __restrict__ z, int start, int end, int c, int lane, int n_samples) {
+    const int q0 = (start & ~3) + c * kRingChunk + 4 * lane;
+    if (q0 >= end) return;  // nothing of this ray in the lane's quad: the consumer masks it without reading
+    if (q0 + 4 <= n_samples) {
+        cp_async16_full(stage + 4 * lane, alpha + q0);
+        if (!ALPHA_ONLY) {
+            cp_async16_full(stage + 128 + 4 * lane, z + q0);
+            const float* c3 = rgb + 3 * (size_t)q0;
+            cp_async16_full(stage + 256 + 12 * lane, c3);
+            cp_async16_full(stage + 256 + 12 * lane + 4, c3 + 4);
+            cp_async16_full(stage + 256 + 12 * lane + 8, c3 + 8);
+        }
+        return;
+    }
+    const int valid = n_samples - q0;  // 1..3 samples of the quad inside the arrays
+    cp_async16(stage + 4 * lane, alpha + q0, 4 * valid);
+    if (!ALPHA_ONLY) {
+        cp_async16(stage + 128 + 4 * lane, z + q0, 4 * valid);
+        const int cb = 12 * valid;
+        const float* c3 = rgb + 3 * (size_t)q0;
+        cp_async16(stage + 256 + 12 * lane, c3, min(16, cb));
+        cp_async16(stage + 256 + 12 * lane + 4, cb > 16 ? c3 + 4 : rgb, max(0, min(16, cb - 16)));
+        cp_async16(stage + 256 + 12 * lane + 8, cb > 32 ? c3 + 8 : rgb, max(0, min(16, cb - 32)));
+    }
+}
+
+// quad out of the ring; samples outside [start, end) become identities (alpha = 0).  Their colour / depth are the neighbouring rays'
+// (finite) values and meet a zero weight.
+template <bool ALPHA_ONLY>
+__device__ __forceinline__ void ring_read(Quad& q, const float* stage, int q0, int start, int end, int lane) {
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = a4, c0 = a4, c1 = a4, c2 = a4;
+    if (q0 < end) {
+        a4 = *reinterpret_cast<const float4*>(stage + 4 * lane);
+        if (!ALPHA_ONLY) {
+            z4 = *reinterpret_cast<const float4*>(stage + 128 + 4 * lane);
+            c0 = *reinterpret_cast<const float4*>(stage + 256 + 12 * lane);
+            c1 = *reinterpret_cast<const float4*>(stage + 256 + 12 * lane + 4);
+            c2 = *reinterpret_cast<const float4*>(stage + 256 + 12 * lane + 8);
+        }
+    }
+    const int lo = start - q0, hi = end - q0;  // sample j of the quad belongs to the ray iff lo <= j < hi
+    q.a[0] = (0 >= lo && 0 < hi) ? a4.x : 0.f;
+    q.a[1] = (1 >= lo && 1 < hi) ? a4.y : 0.f;
+    q.a[2] = (2 >= lo && 2 < hi) ? a4.z : 0.f;
+    q.a[3] = (3 >= lo && 3 < hi) ? a4.w : 0.f;
+    if (!ALPHA_ONLY) {
+        q.z[0] = z4.x, q.z[1] = z4.y, q.z[2] = z4.z, q.z[3] = z4.w;
+        q.c[0] = c0.x, q.c[1] = c0.y, q.c[2] = c0.z, q.c[3] = c0.w, q.c[4] = c1.x, q.c[5] = c1.y;
+        q.c[6] = c1.z, q.c[7] = c1.w, q.c[8] = c2.x, q.c[9] = c2.y, q.c[10] = c2.z, q.c[11] = c2.w;
+    }
+}
+
+// WT: also store per-sample weights / transmittance (out_w, out_T may each be NULL)
+template <bool WT>
+__global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
+    float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays, int n_samples) {
+    extern __shared__ __align__(16) float ring_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring = ring_smem + (size_t)warp * kRingDepth * kRingStageFloats;
+    const int64_t n_batches = (n_rays + 31) / 32;
+    for (int64_t b = (int64_t)blockIdx.x * kRingWarps + warp; b < n_batches; b += (int64_t)gridDim.x * kRingWarps) {
+        const int64_t ray0 = b * 32;
+        const RingRays mine = ring_load_rays(se, ray0 + lane, n_rays);
+        if (ray0 + lane < n_rays && mine.nch == 0) {  // empty ray: nothing composited, full transmittance
+            const int64_t r = ray0 + lane;
+            out_rgb[3 * r] = out_rgb[3 * r + 1] = out_rgb[3 * r + 2] = 0.f;
+            out_depth[r] = 0.f;
+            out_acc[r] = 0.f;
+            out_bgT[r] = 1.f;
+        }
+        RingCursor2 pc{0, 0, 0, 0, 0, 0};
+        ring_cursor_load<false>(pc, mine);
+        RingCursor2 cc = pc;
+        int issued = 0, consumed = 0;
+        auto issue_one = [&]() {
+            if (pc.r < 32) {
+                ring_issue<false>(ring + (issued % kRingDepth) * kRingStageFloats, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
+                ++issued;
+                ring_cursor_next<false>(pc, mine);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < kRingDepth - 1; ++i) issue_one();
+
+        float carry = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+        while (cc.r < 32) {
+            issue_one();
+            cp_async_wait<kRingDepth - 1>();
+            const int q0 = (cc.start & ~3) + cc.k * kRingChunk + 4 * lane;
+            Quad cur;
+            ring_read<false>(cur, ring + (consumed % kRingDepth) * kRingStageFloats, q0, cc.start, cc.end, lane);
+            ++consumed;
+            float tl[4];
+            float p = 1.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                tl[j] = p;
+                p *= (1.f - cur.a[j]);
+            }
+            const float incl = group_scan_mul<32>(p, lane);
+            const float baseT = carry * group_shift_up<32>(incl, lane, 1.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float Tj = baseT * tl[j];
+                const float w = Tj * cur.a[j];
+                ar = fmaf(w, cur.c[3 * j], ar);
+                ag = fmaf(w, cur.c[3 * j + 1], ag);
+                ab = fmaf(w, cur.c[3 * j + 2], ab);
+                ad = fmaf(w, cur.z[j], ad);
+                aa += w;
+                if (WT && q0 + j >= cc.start && q0 + j < cc.end) {
+                    if (out_w) out_w[q0 + j] = w;
+                    if (out_T) out_T[q0 + j] = Tj;
+                }
+            }
+            carry *= group_bcast<32>(incl, 31);
+            if (cc.k == cc.nch - 1) {  // the ray is complete
+                ar = group_reduce_add<32>(ar);
+                ag = group_reduce_add<32>(ag);
+                ab = group_reduce_add<32>(ab);
+                ad = group_reduce_add<32>(ad);
+                aa = group_reduce_add<32>(aa);
+                if (lane == 0) {
+                    const int64_t r = ray0 + cc.r;
+                    out_rgb[3 * r] = ar;
+                    out_rgb[3 * r + 1] = ag;
+                    out_rgb[3 * r + 2] = ab;
+                    out_depth[r] = ad;
+                    out_acc[r] = aa;
+                    out_bgT[r] = carry;
+                }
+                carry = 1.f;
+                ar = ag = ab = ad = aa = 0.f;
+            }
+            ring_cursor_next<false>(cc, mine);
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// Backward: a ray with one chunk is a single item (transmittance and reverse recurrence from the same quad); a longer ray is a
+// left-to-right pass over alpha (transmittance at every chunk start, kept by lane c for chunk c) followed by the right-to-left pass.
+template <bool DZ>
+__global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
+    const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
+    float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays, int n_samples) {
+    extern __shared__ __align__(16) float ring_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring = ring_smem + (size_t)warp * kRingDepth * kRingStageFloats;
+    const int64_t n_batches = (n_rays + 31) / 32;
+    for (int64_t b = (int64_t)blockIdx.x * kRingWarps + warp; b < n_batches; b += (int64_t)gridDim.x * kRingWarps) {
+        const int64_t ray0 = b * 32;
+        const RingRays mine = ring_load_rays(se, ray0 + lane, n_rays);
+        float m_gr = 0.f, m_gg = 0.f, m_gb = 0.f, m_gd = 0.f, m_ga = 0.f, m_gT = 0.f;
+        if (mine.nch > 0) {
+            const int64_t r = ray0 + lane;
+            m_gr = __ldg(g_rgb + 3 * r);
+            m_gg = __ldg(g_rgb + 3 * r + 1);
+            m_gb = __ldg(g_rgb + 3 * r + 2);
+            m_gd = __ldg(g_depth + r);
+            m_ga = __ldg(g_acc + r);
+            m_gT = __ldg(g_bgT + r);
+        }
+        RingCursor2 pc{0, 0, 0, 0, 0, 0};
+        ring_cursor_load<true>(pc, mine);
+        RingCursor2 cc = pc;
+        int issued = 0, consumed = 0;
+        auto issue_one = [&]() {
+            if (pc.r < 32) {
+                float* stage = ring + (issued % kRingDepth) * kRingStageFloats;
+                if (pc.nch > 1 && pc.k < pc.nch)
+                    ring_issue<true>(stage, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
+                else
+                    ring_issue<false>(stage, alpha, rgb, z, pc.start, pc.end, pc.nch > 1 ? 2 * pc.nch - 1 - pc.k : 0, lane, n_samples);
+                ++issued;
+                ring_cursor_next<true>(pc, mine);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < kRingDepth - 1; ++i) issue_one();
+
+        float carry = 1.f, my_chunk_T = 1.f, Rcarry = 0.f;
+        float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
+        while (cc.r < 32) {
+            issue_one();
+            cp_async_wait<kRingDepth - 1>();
+            const int s = cc.start, e = cc.end, nch = cc.nch;
+            const bool spill = nch > 32;  // more chunk starts than lanes: per-sample T parked in d_alpha (overwritten by the reverse pass)
+            const float* stage = ring + (consumed % kRingDepth) * kRingStageFloats;
+            ++consumed;
+            if (cc.k == 0) {  // a new ray: its upstream gradients, fresh carries
+                gr = __shfl_sync(VS_FULL_MASK, m_gr, cc.r);
+                gg = __shfl_sync(VS_FULL_MASK, m_gg, cc.r);
+                gb = __shfl_sync(VS_FULL_MASK, m_gb, cc.r);
+                gd = __shfl_sync(VS_FULL_MASK, m_gd, cc.r);
+                ga = __shfl_sync(VS_FULL_MASK, m_ga, cc.r);
+                Rcarry = __shfl_sync(VS_FULL_MASK, m_gT, cc.r);
+                carry = 1.f;
+                my_chunk_T = 1.f;
+            }
+            if (nch > 1 && cc.k < nch) {
+                // ---- transmittance pass, chunk cc.k
+                const int c = cc.k;
+                const int q0 = (s & ~3) + c * kRingChunk + 4 * lane;
+                Quad cur;
+                ring_read<true>(cur, stage, q0, s, e, lane);
+                float tl[4];
+                float p = 1.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tl[j] = p;
+                    p *= (1.f - cur.a[j]);
+                }
+                const float incl = group_scan_mul<32>(p, lane);
+                if (spill) {
+                    const float baseT = carry * group_shift_up<32>(incl, lane, 1.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (q0 + j >= s && q0 + j < e) d_alpha[q0 + j] = baseT * tl[j];
+                } else if (lane == c) {
+                    my_chunk_T = carry;
+                }
+                carry *= group_bcast<32>(incl, 31);
+            } else {
+                // ---- reverse pass, chunk c
+                const int c = nch > 1 ? 2 * nch - 1 - cc.k : 0;
+                const int q0 = (s & ~3) + c * kRingChunk + 4 * lane;
+                Quad cur;
+                ring_read<false>(cur, stage, q0, s, e, lane);
+                bool valid[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) valid[j] = q0 + j >= s && q0 + j < e;
+                float T[4];
+                if (spill) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) T[j] = valid[j] ? d_alpha[q0 + j] : 0.f;
+                } else {
+                    float p = 1.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        T[j] = p;
+                        p *= (1.f - cur.a[j]);
+                    }
+                    const float incl = group_scan_mul<32>(p, lane);
+                    const float baseT = group_bcast<32>(my_chunk_T, c & 31) * group_shift_up<32>(incl, lane, 1.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) T[j] *= baseT;
+                }
+                float g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    g[j] = fmaf(gr, cur.c[3 * j], fmaf(gg, cur.c[3 * j + 1], fmaf(gb, cur.c[3 * j + 2], fmaf(gd, cur.z[j], ga))));
+                float MA = 1.f, MB = 0.f;
+#pragma unroll
+                for (int j = 3; j >= 0; --j) {
+                    const float Aj = 1.f - cur.a[j], Bj = cur.a[j] * g[j];
+                    MB = fmaf(Aj, MB, Bj);
+                    MA = Aj * MA;
+                }
+                group_rscan_affine<32>(MA, MB, lane);
+                const float V = fmaf(MA, Rcarry, MB);
+                float R = __shfl_down_sync(VS_FULL_MASK, V, 1, 32);
+                if (lane == 31) R = Rcarry;
+                float da[4], dc[12], dz[4];
+#pragma unroll
+                for (int j = 3; j >= 0; --j) {
+                    const float w = T[j] * cur.a[j];
+                    da[j] = T[j] * (g[j] - R);
+                    dc[3 * j] = gr * w;
+                    dc[3 * j + 1] = gg * w;
+                    dc[3 * j + 2] = gb * w;
+                    dz[j] = gd * w;
+                    R = fmaf(1.f - cur.a[j], R, cur.a[j] * g[j]);
+                }
+                if (valid[0] && valid[3] && q0 + 4 <= n_samples) {
+                    st_stream4(reinterpret_cast<float4*>(d_alpha + q0), make_float4(da[0], da[1], da[2], da[3]));
+                    float* c3 = d_rgb + 3 * (size_t)q0;
+                    st_stream4(reinterpret_cast<float4*>(c3), make_float4(dc[0], dc[1], dc[2], dc[3]));
+                    st_stream4(reinterpret_cast<float4*>(c3 + 4), make_float4(dc[4], dc[5], dc[6], dc[7]));
+                    st_stream4(reinterpret_cast<float4*>(c3 + 8), make_float4(dc[8], dc[9], dc[10], dc[11]));
+                    if (DZ) st_stream4(reinterpret_cast<float4*>(d_z + q0), make_float4(dz[0], dz[1], dz[2], dz[3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (valid[j]) {
+                            d_alpha[q0 + j] = da[j];
+                            d_rgb[3 * (size_t)(q0 + j)] = dc[3 * j];
+                            d_rgb[3 * (size_t)(q0 + j) + 1] = dc[3 * j + 1];
+                            d_rgb[3 * (size_t)(q0 + j) + 2] = dc[3 * j + 2];
+                            if (DZ) d_z[q0 + j] = dz[j];
+                        }
+                    }
+                }
+                Rcarry = group_bcast<32>(V, 0);
+            }
+            ring_cursor_next<true>(cc, mine);
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// =============================================================================================
 // tile family (short segments)
 // =============================================================================================
 // copy src[first, first+count) -> dst[(first - align4(first)) ...] with 16-byte loads for the aligned body.
@@ -831,6 +1218,19 @@ static inline int pick_scan4_width(int64_t n_rays, int64_t n_samples) {
 }
 
 // shared-memory capacity (in samples) of a tile: 1.25x the mean load of 256 rays, at least 256
+// ring family: one warp per 32 rays; a few CTAs per SM, the rest of the batches are walked grid-stride
+static inline unsigned ring_grid(int64_t n_rays) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t batches = (n_rays + 31) / 32;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((batches + kRingWarps - 1) / kRingWarps, (int64_t)sms * 8));
+}
+static inline bool ring_in_auto() {
+    static const bool off = std::getenv("VS_COMPOSITE_NO_RING") != nullptr;  // A/B knob: auto falls back to the scan family
+    return !off;
+}
+
 static inline int tile_cap(int64_t n_rays, int64_t n_samples) {
     double mean = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
     int cap = (int)(mean * kTileRays * 1.25) + 64;
@@ -847,12 +1247,13 @@ extern "C" {
 
 // mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = scan family (one sample per lane, W from the mean ray length),
 // 3 = coarsened scan family (aligned quad per lane, float4 loads; W auto), 4 = tile family with LDG/STS staging,
-// 5/6/7 = coarsened scan with W = 8/16/32.  3..7 exist for A/B measurements: on B200 the coarsened kernels measured SLOWER
+// 5/6/7 = coarsened scan with W = 8/16/32, 8 = ring family (cp.async-pipelined quads, a warp per 32 rays; what auto picks for
+// mean ray lengths above 8).  3..7 exist for A/B measurements: on B200 the coarsened kernels measured SLOWER
 // than the one-sample-per-lane ones (profiles/r01_bench_composite_scan_variants.jsonl), so auto never picks them.
 int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, float* out_rgb, float* out_depth,
                      float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples, int mode,
                      void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 7);
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 8);
     if (n_rays == 0) return VS_OK;
     VS_CHECK_ARG(se && out_rgb && out_depth && out_acc && out_bgT);
     VS_CHECK_ARG(n_samples == 0 || (alpha && rgb && z));
@@ -875,7 +1276,16 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
         }
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z);
-    if ((mode == 3 || mode >= 5) && a16) {  // coarsened scan kernels (quad per lane)
+    if ((mode == 8 || (mode == 0 && ring_in_auto())) && a16 && n_samples > 0 && n_samples <= 0x7fffffffLL) {  // ring family: cp.async-pipelined quads, 32 rays per warp
+        const size_t smem = sizeof(float) * kRingWarps * kRingDepth * kRingStageFloats;
+        auto kern = (out_w || out_T) ? composite_fwd_ring_kernel<true> : composite_fwd_ring_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<ring_grid(n_rays), 32 * kRingWarps, smem, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays,
+                                                              (int)n_samples);
+        return launched(1);
+    }
+    if ((mode == 3 || (mode >= 5 && mode <= 7)) && a16) {  // coarsened scan kernels (quad per lane)
         const int W4 = mode == 5 ? 8 : mode == 6 ? 16 : mode == 7 ? 32 : pick_scan4_width(n_rays, n_samples);
         const unsigned grid4 = (unsigned)div_up(n_rays * W4, kScanThreads);
         switch (W4) {
@@ -911,7 +1321,7 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
 int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, const float* z, const float* g_rgb, const float* g_depth,
                      const float* g_acc, const float* g_bgT, float* d_alpha, float* d_rgb, float* d_z, int64_t n_rays, int64_t n_samples,
                      int mode, void* stream) {
-    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 7);
+    VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0 && mode >= 0 && mode <= 8);
     if (n_rays == 0 || n_samples == 0) return VS_OK;
     VS_CHECK_ARG(se && alpha && rgb && z && g_rgb && g_depth && g_acc && g_bgT && d_alpha && d_rgb);
     cudaStream_t st = (cudaStream_t)stream;
@@ -934,7 +1344,16 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
         }
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z));
-    if ((mode == 3 || mode >= 5) && a16) {
+    if ((mode == 8 || (mode == 0 && ring_in_auto())) && a16 && n_samples <= 0x7fffffffLL) {
+        const size_t smem = sizeof(float) * kRingWarps * kRingDepth * kRingStageFloats;
+        auto kern = d_z ? composite_bwd_ring_kernel<true> : composite_bwd_ring_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<ring_grid(n_rays), 32 * kRingWarps, smem, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays,
+                                                              (int)n_samples);
+        return launched(1);
+    }
+    if ((mode == 3 || (mode >= 5 && mode <= 7)) && a16) {
         const int W4 = mode == 5 ? 8 : mode == 6 ? 16 : mode == 7 ? 32 : pick_scan4_width(n_rays, n_samples);
         const unsigned grid4 = (unsigned)div_up(n_rays * W4, kScanThreads);
         switch (W4) {
