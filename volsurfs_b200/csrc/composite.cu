@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan4_kernel(
 // at no register cost.  Every lane copies exactly the bytes it later reads, so the ring needs no barrier: cp.async.wait_group is
 // per thread.  The arithmetic is that of the coarsened scan kernels (serial 4-sample products + one shuffle scan per chunk).
 constexpr int kRingWarps = 8;
-constexpr int kRingDepth = 3;
+constexpr int kRingDepthDefault = 3;
 constexpr int kRingStageFloats = 640;  // 128 alpha | 128 z | 384 rgb
 constexpr int kRingChunk = 128;        // samples per chunk (4 per lane)
 
@@ -628,14 +628,14 @@ __device__ __forceinline__ void ring_read(Quad& q, const float* stage, int q0, i
 }
 
 // WT: also store per-sample weights / transmittance (out_w, out_T may each be NULL)
-template <bool WT>
+template <bool WT, int D>
 __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
     float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays, int n_samples) {
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring = ring_smem + (size_t)warp * kRingDepth * kRingStageFloats;
+    float* ring = ring_smem + (size_t)warp * D * kRingStageFloats;
     const int64_t n_batches = (n_rays + 31) / 32;
     for (int64_t b = (int64_t)blockIdx.x * kRingWarps + warp; b < n_batches; b += (int64_t)gridDim.x * kRingWarps) {
         const int64_t ray0 = b * 32;
@@ -653,22 +653,22 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
         int issued = 0, consumed = 0;
         auto issue_one = [&]() {
             if (pc.r < 32) {
-                ring_issue<false>(ring + (issued % kRingDepth) * kRingStageFloats, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
+                ring_issue<false>(ring + (issued % D) * kRingStageFloats, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
                 ++issued;
                 ring_cursor_next<false>(pc, mine);
             }
             cp_async_commit();
         };
 #pragma unroll
-        for (int i = 0; i < kRingDepth - 1; ++i) issue_one();
+        for (int i = 0; i < D - 1; ++i) issue_one();
 
         float carry = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
         while (cc.r < 32) {
             issue_one();
-            cp_async_wait<kRingDepth - 1>();
+            cp_async_wait<D - 1>();
             const int q0 = (cc.start & ~3) + cc.k * kRingChunk + 4 * lane;
             Quad cur;
-            ring_read<false>(cur, ring + (consumed % kRingDepth) * kRingStageFloats, q0, cc.start, cc.end, lane);
+            ring_read<false>(cur, ring + (consumed % D) * kRingStageFloats, q0, cc.start, cc.end, lane);
             ++consumed;
             float tl[4];
             float p = 1.f;
@@ -720,14 +720,14 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
 
 // Backward: a ray with one chunk is a single item (transmittance and reverse recurrence from the same quad); a longer ray is a
 // left-to-right pass over alpha (transmittance at every chunk start, kept by lane c for chunk c) followed by the right-to-left pass.
-template <bool DZ>
+template <bool DZ, int D>
 __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
     float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays, int n_samples) {
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring = ring_smem + (size_t)warp * kRingDepth * kRingStageFloats;
+    float* ring = ring_smem + (size_t)warp * D * kRingStageFloats;
     const int64_t n_batches = (n_rays + 31) / 32;
     for (int64_t b = (int64_t)blockIdx.x * kRingWarps + warp; b < n_batches; b += (int64_t)gridDim.x * kRingWarps) {
         const int64_t ray0 = b * 32;
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
         int issued = 0, consumed = 0;
         auto issue_one = [&]() {
             if (pc.r < 32) {
-                float* stage = ring + (issued % kRingDepth) * kRingStageFloats;
+                float* stage = ring + (issued % D) * kRingStageFloats;
                 if (pc.nch > 1 && pc.k < pc.nch)
                     ring_issue<true>(stage, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
                 else
@@ -759,16 +759,16 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
             cp_async_commit();
         };
 #pragma unroll
-        for (int i = 0; i < kRingDepth - 1; ++i) issue_one();
+        for (int i = 0; i < D - 1; ++i) issue_one();
 
         float carry = 1.f, my_chunk_T = 1.f, Rcarry = 0.f;
         float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
         while (cc.r < 32) {
             issue_one();
-            cp_async_wait<kRingDepth - 1>();
+            cp_async_wait<D - 1>();
             const int s = cc.start, e = cc.end, nch = cc.nch;
             const bool spill = nch > 32;  // more chunk starts than lanes: per-sample T parked in d_alpha (overwritten by the reverse pass)
-            const float* stage = ring + (consumed % kRingDepth) * kRingStageFloats;
+            const float* stage = ring + (consumed % D) * kRingStageFloats;
             ++consumed;
             if (cc.k == 0) {  // a new ray: its upstream gradients, fresh carries
                 gr = __shfl_sync(VS_FULL_MASK, m_gr, cc.r);
@@ -1209,6 +1209,13 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
     }
 }
 
+// auto mode (measured on B200, profiles/r01_bench_composite_ring.jsonl): tile family up to a mean of 16 samples per ray (K = 9 shells:
+// 75 % of the HBM peak against 26 % for the scan family), ring family beyond (C3: 61 % against 47 %), except the FORWARD of very long
+// rays (mean > 256), where the one-sample-per-lane scan keeps more loads in flight per instruction (4.8 against 4.3 TB/s at mean 400)
+constexpr double kTileMaxMean = 16.0;     // backward
+constexpr double kTileMaxMeanFwd = 32.0;  // forward (mean 24: tile 0.128 ms, ring 0.167 ms; backward: tile 0.298 ms, ring 0.230 ms)
+constexpr double kRingFwdMaxMean = 256.0;
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // lanes per ray of the coarsened scan kernels (4 samples per lane): a chunk of 4W samples should be of the order of the mean ray
@@ -1225,6 +1232,14 @@ static inline unsigned ring_grid(int64_t n_rays) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t batches = (n_rays + 31) / 32;
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((batches + kRingWarps - 1) / kRingWarps, (int64_t)sms * 8));
+}
+static inline int ring_depth() {
+    static const int d = [] {
+        const char* env = std::getenv("VS_RING_DEPTH");  // A/B knob: stages of the per-warp ring (2, 3 or 4)
+        const int v = env ? std::atoi(env) : kRingDepthDefault;
+        return (v == 2 || v == 4) ? v : 3;
+    }();
+    return d;
 }
 static inline bool ring_in_auto() {
     static const bool off = std::getenv("VS_COMPOSITE_NO_RING") != nullptr;  // A/B knob: auto falls back to the scan family
@@ -1245,7 +1260,7 @@ using namespace vs;
 
 extern "C" {
 
-// mode: 0 = auto, 1 = tile family (TMA bulk staging), 2 = scan family (one sample per lane, W from the mean ray length),
+// mode: 0 = auto (rules above kTileMaxMean), 1 = tile family (TMA bulk staging), 2 = scan family (one sample per lane, W from the mean ray length),
 // 3 = coarsened scan family (aligned quad per lane, float4 loads; W auto), 4 = tile family with LDG/STS staging,
 // 5/6/7 = coarsened scan with W = 8/16/32, 8 = ring family (cp.async-pipelined quads, a warp per 32 rays; what auto picks for
 // mean ray lengths above 8).  3..7 exist for A/B measurements: on B200 the coarsened kernels measured SLOWER
@@ -1259,7 +1274,7 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
     VS_CHECK_ARG(n_samples == 0 || (alpha && rgb && z));
     cudaStream_t st = (cudaStream_t)stream;
     const double mean = (double)n_samples / (double)n_rays;
-    bool tile = (mode == 1) || (mode == 4) || (mode == 0 && mean <= 8.0);
+    bool tile = (mode == 1) || (mode == 4) || (mode == 0 && mean <= kTileMaxMeanFwd);
     if (tile && !(aligned16(alpha) && aligned16(rgb) && aligned16(z))) tile = false;
     if (tile) {
         const int cap = tile_cap(n_rays, n_samples);
@@ -1276,9 +1291,14 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
         }
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z);
-    if ((mode == 8 || (mode == 0 && ring_in_auto())) && a16 && n_samples > 0 && n_samples <= 0x7fffffffLL) {  // ring family: cp.async-pipelined quads, 32 rays per warp
-        const size_t smem = sizeof(float) * kRingWarps * kRingDepth * kRingStageFloats;
-        auto kern = (out_w || out_T) ? composite_fwd_ring_kernel<true> : composite_fwd_ring_kernel<false>;
+    // ring family: cp.async-pipelined quads, 32 rays per warp.  Forward: on very long rays the one-sample-per-lane scan streams better
+    if ((mode == 8 || (mode == 0 && ring_in_auto() && mean <= kRingFwdMaxMean)) && a16 && n_samples > 0 && n_samples <= 0x7fffffffLL) {
+        const int depth = ring_depth();
+        const size_t smem = sizeof(float) * kRingWarps * depth * kRingStageFloats;
+        const bool wt = out_w || out_T;
+        auto kern = depth == 2 ? (wt ? composite_fwd_ring_kernel<true, 2> : composite_fwd_ring_kernel<false, 2>)
+                    : depth == 4 ? (wt ? composite_fwd_ring_kernel<true, 4> : composite_fwd_ring_kernel<false, 4>)
+                                 : (wt ? composite_fwd_ring_kernel<true, 3> : composite_fwd_ring_kernel<false, 3>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<ring_grid(n_rays), 32 * kRingWarps, smem, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays,
@@ -1326,7 +1346,7 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
     VS_CHECK_ARG(se && alpha && rgb && z && g_rgb && g_depth && g_acc && g_bgT && d_alpha && d_rgb);
     cudaStream_t st = (cudaStream_t)stream;
     const double mean = (double)n_samples / (double)n_rays;
-    bool tile = (mode == 1) || (mode == 4) || (mode == 0 && mean <= 8.0);
+    bool tile = (mode == 1) || (mode == 4) || (mode == 0 && mean <= kTileMaxMean);
     if (tile && !(aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z))))
         tile = false;
     if (tile) {
@@ -1345,8 +1365,11 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z));
     if ((mode == 8 || (mode == 0 && ring_in_auto())) && a16 && n_samples <= 0x7fffffffLL) {
-        const size_t smem = sizeof(float) * kRingWarps * kRingDepth * kRingStageFloats;
-        auto kern = d_z ? composite_bwd_ring_kernel<true> : composite_bwd_ring_kernel<false>;
+        const int depth = ring_depth();
+        const size_t smem = sizeof(float) * kRingWarps * depth * kRingStageFloats;
+        auto kern = depth == 2 ? (d_z ? composite_bwd_ring_kernel<true, 2> : composite_bwd_ring_kernel<false, 2>)
+                    : depth == 4 ? (d_z ? composite_bwd_ring_kernel<true, 4> : composite_bwd_ring_kernel<false, 4>)
+                                 : (d_z ? composite_bwd_ring_kernel<true, 3> : composite_bwd_ring_kernel<false, 3>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<ring_grid(n_rays), 32 * kRingWarps, smem, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays,
