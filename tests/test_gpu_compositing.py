@@ -91,6 +91,29 @@ def test_long_rays_spill_path():
         _check(p["se"], p["alpha"], p["rgb"], p["z"], p, mode)
 
 
+def _packets_from_counts(counts, seed):
+    g = torch.Generator().manual_seed(seed)
+    cnt = torch.tensor(counts, dtype=torch.int64)
+    n, S = cnt.numel(), int(cnt.sum())
+    start = torch.cumsum(cnt, 0) - cnt
+    se = torch.stack([start, start + cnt], 1).to(torch.int32)
+    se[cnt == 0] = -1
+    alpha = (torch.rand(S, 1, generator=g) * (torch.rand(S, 1, generator=g) > 0.5) * 0.2).contiguous()
+    return {"se": se.contiguous(), "alpha": alpha, "rgb": torch.rand(S, 3, generator=g), "z": torch.rand(S, 1, generator=g) + 0.5,
+            "g_rgb": torch.randn(n, 3, generator=g), "g_depth": torch.randn(n, 1, generator=g), "g_acc": torch.randn(n, 1, generator=g),
+            "g_bgT": torch.randn(n, 1, generator=g)}
+
+
+@pytest.mark.parametrize("counts", [
+    [5] * 1000 + [700] * 10 + [0] * 7 + [3] * 50,       # mean 12: 8-lane groups, the 700-sample rays spill (more than 8 chunks of 32)
+    [90] * 300 + [0] * 100 + [1500] * 4 + [1] * 33,     # mean 76: 16-lane groups, 1500-sample rays spill (more than 16 chunks of 64)
+    [5000] * 3 + [300] * 40 + [0] * 5,                  # mean 562: 32-lane groups, 5000-sample rays spill (more than 32 chunks of 128)
+], ids=["w8", "w16", "w32"])
+def test_ring_family_group_widths_and_spill(counts):
+    p = _packets_from_counts(counts, seed=len(counts))
+    _check(p["se"], p["alpha"], p["rgb"], p["z"], p, 8)
+
+
 @pytest.mark.parametrize("n_rays,K", [(1, 5), (255, 5), (257, 9), (1000, 1)])
 def test_edge_sizes(n_rays, K):
     d = all_hit_packed(n_rays, K)

@@ -523,11 +523,46 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// the 32 rays of a warp's batch, one per lane; chunks are anchored at the ray's start rounded down to a multiple of four samples
-// (sample indices fit 32 bits: ray_start_end_idx is int32)
+// group-masked shuffle primitives: the W-lane groups of a warp walk different rays and diverge from each other, so every shuffle
+// names only its own group's lanes
+template <int W>
+__device__ __forceinline__ unsigned ring_group_mask(int lane) {
+    return W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1)));
+}
+template <int W>
+__device__ __forceinline__ float ring_scan_mul(unsigned m, float v, int gl) {
+#pragma unroll
+    for (int d = 1; d < W; d <<= 1) {
+        const float o = __shfl_up_sync(m, v, d, W);
+        if (gl >= d) v *= o;
+    }
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float ring_reduce_add(unsigned m, float v) {
+#pragma unroll
+    for (int d = W / 2; d > 0; d >>= 1) v += __shfl_xor_sync(m, v, d, W);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ void ring_rscan_affine(unsigned m, float& A, float& B, int gl) {
+#pragma unroll
+    for (int d = 1; d < W; d <<= 1) {
+        const float Ao = __shfl_down_sync(m, A, d, W);
+        const float Bo = __shfl_down_sync(m, B, d, W);
+        if (gl + d < W) {
+            B = fmaf(A, Bo, B);
+            A = A * Ao;
+        }
+    }
+}
+
+// A warp's batch is 32 consecutive rays, one per lane; group g (W lanes) walks rays g*W .. g*W+W-1.  Chunks are 4W samples (an aligned
+// quad per lane), anchored at the ray's start rounded down to a multiple of four samples (sample indices fit 32 bits: int32 segments).
 struct RingRays {
     int start, end, nch;
 };
+template <int W>
 __device__ __forceinline__ RingRays ring_load_rays(const int32_t* __restrict__ se, int64_t ray, int64_t n_rays) {
     RingRays r{0, 0, 0};
     if (ray < n_rays) {
@@ -536,83 +571,86 @@ __device__ __forceinline__ RingRays ring_load_rays(const int32_t* __restrict__ s
         if (n > 0) {
             r.start = st;
             r.end = st + n;
-            r.nch = (r.end - (st & ~3) + kRingChunk - 1) / kRingChunk;
+            r.nch = (r.end - (st & ~3) + 4 * W - 1) / (4 * W);
         }
     }
     return r;
 }
 
-// warp-uniform cursor over the (ray, item) pairs of a batch: the current ray's segment is cached and re-fetched (three shuffles) only
-// when the cursor moves to another ray
+// group-uniform cursor over the (ray, item) pairs of a group: the current ray's segment is cached and re-fetched (three shuffles) only
+// when the cursor moves to another ray.  r == W: the group is done (start = end = 0, so every quad reads as empty).
 struct RingCursor2 {
     int r, k, items, start, end, nch;
 };
-template <bool BWD>
-__device__ __forceinline__ void ring_cursor_load(RingCursor2& c, const RingRays& mine) {
+template <bool BWD, int W>
+__device__ __forceinline__ void ring_cursor_load(RingCursor2& c, const RingRays& mine, unsigned m, int lane) {
     // first ray at or after c.r that has items (BWD: one reverse item for single-chunk rays, else nch alpha-only + nch reverse items)
-    const unsigned has = __ballot_sync(VS_FULL_MASK, mine.nch > 0);
-    const unsigned rest = c.r < 32 ? (has >> c.r) : 0u;
+    const unsigned has = (__ballot_sync(m, mine.nch > 0) >> (lane & ~(W - 1))) & (W == 32 ? 0xffffffffu : ((1u << W) - 1u));
+    const unsigned rest = c.r < W ? (has >> c.r) : 0u;
     if (rest == 0u) {
-        c.r = 32;
+        c.r = W;
+        c.k = c.items = c.start = c.end = c.nch = 0;
         return;
     }
     c.r += __ffs(rest) - 1;
     c.k = 0;
-    c.start = __shfl_sync(VS_FULL_MASK, mine.start, c.r);
-    c.end = __shfl_sync(VS_FULL_MASK, mine.end, c.r);
-    c.nch = __shfl_sync(VS_FULL_MASK, mine.nch, c.r);
+    c.start = __shfl_sync(m, mine.start, c.r, W);
+    c.end = __shfl_sync(m, mine.end, c.r, W);
+    c.nch = __shfl_sync(m, mine.nch, c.r, W);
     c.items = BWD ? (c.nch == 1 ? 1 : 2 * c.nch) : c.nch;
 }
-template <bool BWD>
-__device__ __forceinline__ void ring_cursor_next(RingCursor2& c, const RingRays& mine) {
+template <bool BWD, int W>
+__device__ __forceinline__ void ring_cursor_next(RingCursor2& c, const RingRays& mine, unsigned m, int lane) {
     if (++c.k >= c.items) {
         ++c.r;
-        ring_cursor_load<BWD>(c, mine);
+        ring_cursor_load<BWD, W>(c, mine, m, lane);
     }
 }
 
 // this lane's quad of chunk c of the ray [start, end): 16-byte async copies (zero fill past the end of the arrays); ALPHA_ONLY for
-// the backward's transmittance pass
-template <bool ALPHA_ONLY>
+// the backward's transmittance pass.  `stage` is the GROUP's stage: alpha [4W] | z [4W] | rgb [12W]
+template <bool ALPHA_ONLY, int W>
 __device__ __forceinline__ void ring_issue(float* stage, const float* __restrict__ alpha, const float* __restrict__ rgb,
-                                           const float* __restrict__ z, int start, int end, int c, int lane, int n_samples) {
-    const int q0 = (start & ~3) + c * kRingChunk + 4 * lane;
+                                           const float* __restrict__ z, int start, int end, int c, int gl, int n_samples) {
+    const int q0 = (start & ~3) + c * 4 * W + 4 * gl;
     if (q0 >= end) return;  // nothing of this ray in the lane's quad: the consumer masks it without reading
+    float* sa = stage + 4 * gl;
+    float* sz = stage + 4 * W + 4 * gl;
+    float* sc = stage + 8 * W + 12 * gl;
+    const float* c3 = rgb + 3 * (size_t)q0;
     if (q0 + 4 <= n_samples) {
-        cp_async16_full(stage + 4 * lane, alpha + q0);
+        cp_async16_full(sa, alpha + q0);
         if (!ALPHA_ONLY) {
-            cp_async16_full(stage + 128 + 4 * lane, z + q0);
-            const float* c3 = rgb + 3 * (size_t)q0;
-            cp_async16_full(stage + 256 + 12 * lane, c3);
-            cp_async16_full(stage + 256 + 12 * lane + 4, c3 + 4);
-            cp_async16_full(stage + 256 + 12 * lane + 8, c3 + 8);
+            cp_async16_full(sz, z + q0);
+            cp_async16_full(sc, c3);
+            cp_async16_full(sc + 4, c3 + 4);
+            cp_async16_full(sc + 8, c3 + 8);
         }
         return;
     }
     const int valid = n_samples - q0;  // 1..3 samples of the quad inside the arrays
-    cp_async16(stage + 4 * lane, alpha + q0, 4 * valid);
+    cp_async16(sa, alpha + q0, 4 * valid);
     if (!ALPHA_ONLY) {
-        cp_async16(stage + 128 + 4 * lane, z + q0, 4 * valid);
+        cp_async16(sz, z + q0, 4 * valid);
         const int cb = 12 * valid;
-        const float* c3 = rgb + 3 * (size_t)q0;
-        cp_async16(stage + 256 + 12 * lane, c3, min(16, cb));
-        cp_async16(stage + 256 + 12 * lane + 4, cb > 16 ? c3 + 4 : rgb, max(0, min(16, cb - 16)));
-        cp_async16(stage + 256 + 12 * lane + 8, cb > 32 ? c3 + 8 : rgb, max(0, min(16, cb - 32)));
+        cp_async16(sc, c3, min(16, cb));
+        cp_async16(sc + 4, cb > 16 ? c3 + 4 : rgb, max(0, min(16, cb - 16)));
+        cp_async16(sc + 8, cb > 32 ? c3 + 8 : rgb, max(0, min(16, cb - 32)));
     }
 }
 
 // quad out of the ring; samples outside [start, end) become identities (alpha = 0).  Their colour / depth are the neighbouring rays'
 // (finite) values and meet a zero weight.
-template <bool ALPHA_ONLY>
-__device__ __forceinline__ void ring_read(Quad& q, const float* stage, int q0, int start, int end, int lane) {
+template <bool ALPHA_ONLY, int W>
+__device__ __forceinline__ void ring_read(Quad& q, const float* stage, int q0, int start, int end, int gl) {
     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = a4, c0 = a4, c1 = a4, c2 = a4;
     if (q0 < end) {
-        a4 = *reinterpret_cast<const float4*>(stage + 4 * lane);
+        a4 = *reinterpret_cast<const float4*>(stage + 4 * gl);
         if (!ALPHA_ONLY) {
-            z4 = *reinterpret_cast<const float4*>(stage + 128 + 4 * lane);
-            c0 = *reinterpret_cast<const float4*>(stage + 256 + 12 * lane);
-            c1 = *reinterpret_cast<const float4*>(stage + 256 + 12 * lane + 4);
-            c2 = *reinterpret_cast<const float4*>(stage + 256 + 12 * lane + 8);
+            z4 = *reinterpret_cast<const float4*>(stage + 4 * W + 4 * gl);
+            c0 = *reinterpret_cast<const float4*>(stage + 8 * W + 12 * gl);
+            c1 = *reinterpret_cast<const float4*>(stage + 8 * W + 12 * gl + 4);
+            c2 = *reinterpret_cast<const float4*>(stage + 8 * W + 12 * gl + 8);
         }
     }
     const int lo = start - q0, hi = end - q0;  // sample j of the quad belongs to the ray iff lo <= j < hi
@@ -628,18 +666,20 @@ __device__ __forceinline__ void ring_read(Quad& q, const float* stage, int q0, i
 }
 
 // WT: also store per-sample weights / transmittance (out_w, out_T may each be NULL)
-template <bool WT, int D>
+template <bool WT, int D, int W>
 __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     float* __restrict__ out_rgb, float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ out_bgT,
     float* __restrict__ out_w, float* __restrict__ out_T, int64_t n_rays, int n_samples) {
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring = ring_smem + (size_t)warp * D * kRingStageFloats;
+    const int gl = lane & (W - 1), gbase = lane & ~(W - 1);
+    const unsigned m = ring_group_mask<W>(lane);
+    float* ring = ring_smem + (size_t)warp * D * kRingStageFloats + (gbase / W) * 20 * W;  // this group's slice of every stage
     const int64_t n_batches = (n_rays + 31) / 32;
     for (int64_t b = (int64_t)blockIdx.x * kRingWarps + warp; b < n_batches; b += (int64_t)gridDim.x * kRingWarps) {
         const int64_t ray0 = b * 32;
-        const RingRays mine = ring_load_rays(se, ray0 + lane, n_rays);
+        const RingRays mine = ring_load_rays<W>(se, ray0 + lane, n_rays);
         if (ray0 + lane < n_rays && mine.nch == 0) {  // empty ray: nothing composited, full transmittance
             const int64_t r = ray0 + lane;
             out_rgb[3 * r] = out_rgb[3 * r + 1] = out_rgb[3 * r + 2] = 0.f;
@@ -648,14 +688,14 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
             out_bgT[r] = 1.f;
         }
         RingCursor2 pc{0, 0, 0, 0, 0, 0};
-        ring_cursor_load<false>(pc, mine);
+        ring_cursor_load<false, W>(pc, mine, m, lane);
         RingCursor2 cc = pc;
-        int issued = 0, consumed = 0;
+        int ps = 0, cs = 0;  // producer / consumer stage
         auto issue_one = [&]() {
-            if (pc.r < 32) {
-                ring_issue<false>(ring + (issued % D) * kRingStageFloats, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
-                ++issued;
-                ring_cursor_next<false>(pc, mine);
+            if (pc.r < W) {
+                ring_issue<false, W>(ring + ps * kRingStageFloats, alpha, rgb, z, pc.start, pc.end, pc.k, gl, n_samples);
+                ps = ps + 1 == D ? 0 : ps + 1;
+                ring_cursor_next<false, W>(pc, mine, m, lane);
             }
             cp_async_commit();
         };
@@ -663,13 +703,13 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
         for (int i = 0; i < D - 1; ++i) issue_one();
 
         float carry = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
-        while (cc.r < 32) {
+        while (cc.r < W) {
             issue_one();
             cp_async_wait<D - 1>();
-            const int q0 = (cc.start & ~3) + cc.k * kRingChunk + 4 * lane;
+            const int q0 = (cc.start & ~3) + cc.k * 4 * W + 4 * gl;
             Quad cur;
-            ring_read<false>(cur, ring + (consumed % D) * kRingStageFloats, q0, cc.start, cc.end, lane);
-            ++consumed;
+            ring_read<false, W>(cur, ring + cs * kRingStageFloats, q0, cc.start, cc.end, gl);
+            cs = cs + 1 == D ? 0 : cs + 1;
             float tl[4];
             float p = 1.f;
 #pragma unroll
@@ -677,8 +717,10 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
                 tl[j] = p;
                 p *= (1.f - cur.a[j]);
             }
-            const float incl = group_scan_mul<32>(p, lane);
-            const float baseT = carry * group_shift_up<32>(incl, lane, 1.f);
+            const float incl = ring_scan_mul<W>(m, p, gl);
+            float excl = __shfl_up_sync(m, incl, 1, W);
+            if (gl == 0) excl = 1.f;
+            const float baseT = carry * excl;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float Tj = baseT * tl[j];
@@ -693,15 +735,15 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
                     if (out_T) out_T[q0 + j] = Tj;
                 }
             }
-            carry *= group_bcast<32>(incl, 31);
+            carry *= __shfl_sync(m, incl, W - 1, W);
             if (cc.k == cc.nch - 1) {  // the ray is complete
-                ar = group_reduce_add<32>(ar);
-                ag = group_reduce_add<32>(ag);
-                ab = group_reduce_add<32>(ab);
-                ad = group_reduce_add<32>(ad);
-                aa = group_reduce_add<32>(aa);
-                if (lane == 0) {
-                    const int64_t r = ray0 + cc.r;
+                ar = ring_reduce_add<W>(m, ar);
+                ag = ring_reduce_add<W>(m, ag);
+                ab = ring_reduce_add<W>(m, ab);
+                ad = ring_reduce_add<W>(m, ad);
+                aa = ring_reduce_add<W>(m, aa);
+                if (gl == 0) {
+                    const int64_t r = ray0 + gbase + cc.r;
                     out_rgb[3 * r] = ar;
                     out_rgb[3 * r + 1] = ag;
                     out_rgb[3 * r + 2] = ab;
@@ -712,26 +754,29 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_fwd_ring_kernel(
                 carry = 1.f;
                 ar = ag = ab = ad = aa = 0.f;
             }
-            ring_cursor_next<false>(cc, mine);
+            ring_cursor_next<false, W>(cc, mine, m, lane);
         }
         cp_async_wait<0>();
+        __syncwarp();
     }
 }
 
 // Backward: a ray with one chunk is a single item (transmittance and reverse recurrence from the same quad); a longer ray is a
 // left-to-right pass over alpha (transmittance at every chunk start, kept by lane c for chunk c) followed by the right-to-left pass.
-template <bool DZ, int D>
+template <bool DZ, int D, int W>
 __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
     const int32_t* __restrict__ se, const float* __restrict__ alpha, const float* __restrict__ rgb, const float* __restrict__ z,
     const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_bgT,
     float* __restrict__ d_alpha, float* __restrict__ d_rgb, float* __restrict__ d_z, int64_t n_rays, int n_samples) {
     extern __shared__ __align__(16) float ring_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring = ring_smem + (size_t)warp * D * kRingStageFloats;
+    const int gl = lane & (W - 1), gbase = lane & ~(W - 1);
+    const unsigned m = ring_group_mask<W>(lane);
+    float* ring = ring_smem + (size_t)warp * D * kRingStageFloats + (gbase / W) * 20 * W;
     const int64_t n_batches = (n_rays + 31) / 32;
     for (int64_t b = (int64_t)blockIdx.x * kRingWarps + warp; b < n_batches; b += (int64_t)gridDim.x * kRingWarps) {
         const int64_t ray0 = b * 32;
-        const RingRays mine = ring_load_rays(se, ray0 + lane, n_rays);
+        const RingRays mine = ring_load_rays<W>(se, ray0 + lane, n_rays);
         float m_gr = 0.f, m_gg = 0.f, m_gb = 0.f, m_gd = 0.f, m_ga = 0.f, m_gT = 0.f;
         if (mine.nch > 0) {
             const int64_t r = ray0 + lane;
@@ -743,18 +788,18 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
             m_gT = __ldg(g_bgT + r);
         }
         RingCursor2 pc{0, 0, 0, 0, 0, 0};
-        ring_cursor_load<true>(pc, mine);
+        ring_cursor_load<true, W>(pc, mine, m, lane);
         RingCursor2 cc = pc;
-        int issued = 0, consumed = 0;
+        int ps = 0, cs = 0;
         auto issue_one = [&]() {
-            if (pc.r < 32) {
-                float* stage = ring + (issued % D) * kRingStageFloats;
+            if (pc.r < W) {
+                float* stage = ring + ps * kRingStageFloats;
                 if (pc.nch > 1 && pc.k < pc.nch)
-                    ring_issue<true>(stage, alpha, rgb, z, pc.start, pc.end, pc.k, lane, n_samples);
+                    ring_issue<true, W>(stage, alpha, rgb, z, pc.start, pc.end, pc.k, gl, n_samples);
                 else
-                    ring_issue<false>(stage, alpha, rgb, z, pc.start, pc.end, pc.nch > 1 ? 2 * pc.nch - 1 - pc.k : 0, lane, n_samples);
-                ++issued;
-                ring_cursor_next<true>(pc, mine);
+                    ring_issue<false, W>(stage, alpha, rgb, z, pc.start, pc.end, pc.nch > 1 ? 2 * pc.nch - 1 - pc.k : 0, gl, n_samples);
+                ps = ps + 1 == D ? 0 : ps + 1;
+                ring_cursor_next<true, W>(pc, mine, m, lane);
             }
             cp_async_commit();
         };
@@ -763,29 +808,29 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
 
         float carry = 1.f, my_chunk_T = 1.f, Rcarry = 0.f;
         float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
-        while (cc.r < 32) {
+        while (cc.r < W) {
             issue_one();
             cp_async_wait<D - 1>();
             const int s = cc.start, e = cc.end, nch = cc.nch;
-            const bool spill = nch > 32;  // more chunk starts than lanes: per-sample T parked in d_alpha (overwritten by the reverse pass)
-            const float* stage = ring + (consumed % D) * kRingStageFloats;
-            ++consumed;
+            const bool spill = nch > W;  // more chunk starts than lanes: per-sample T parked in d_alpha (overwritten by the reverse pass)
+            const float* stage = ring + cs * kRingStageFloats;
+            cs = cs + 1 == D ? 0 : cs + 1;
             if (cc.k == 0) {  // a new ray: its upstream gradients, fresh carries
-                gr = __shfl_sync(VS_FULL_MASK, m_gr, cc.r);
-                gg = __shfl_sync(VS_FULL_MASK, m_gg, cc.r);
-                gb = __shfl_sync(VS_FULL_MASK, m_gb, cc.r);
-                gd = __shfl_sync(VS_FULL_MASK, m_gd, cc.r);
-                ga = __shfl_sync(VS_FULL_MASK, m_ga, cc.r);
-                Rcarry = __shfl_sync(VS_FULL_MASK, m_gT, cc.r);
+                gr = __shfl_sync(m, m_gr, cc.r, W);
+                gg = __shfl_sync(m, m_gg, cc.r, W);
+                gb = __shfl_sync(m, m_gb, cc.r, W);
+                gd = __shfl_sync(m, m_gd, cc.r, W);
+                ga = __shfl_sync(m, m_ga, cc.r, W);
+                Rcarry = __shfl_sync(m, m_gT, cc.r, W);
                 carry = 1.f;
                 my_chunk_T = 1.f;
             }
             if (nch > 1 && cc.k < nch) {
                 // ---- transmittance pass, chunk cc.k
                 const int c = cc.k;
-                const int q0 = (s & ~3) + c * kRingChunk + 4 * lane;
+                const int q0 = (s & ~3) + c * 4 * W + 4 * gl;
                 Quad cur;
-                ring_read<true>(cur, stage, q0, s, e, lane);
+                ring_read<true, W>(cur, stage, q0, s, e, gl);
                 float tl[4];
                 float p = 1.f;
 #pragma unroll
@@ -793,22 +838,24 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
                     tl[j] = p;
                     p *= (1.f - cur.a[j]);
                 }
-                const float incl = group_scan_mul<32>(p, lane);
+                const float incl = ring_scan_mul<W>(m, p, gl);
                 if (spill) {
-                    const float baseT = carry * group_shift_up<32>(incl, lane, 1.f);
+                    float excl = __shfl_up_sync(m, incl, 1, W);
+                    if (gl == 0) excl = 1.f;
+                    const float baseT = carry * excl;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (q0 + j >= s && q0 + j < e) d_alpha[q0 + j] = baseT * tl[j];
-                } else if (lane == c) {
+                } else if (gl == c) {
                     my_chunk_T = carry;
                 }
-                carry *= group_bcast<32>(incl, 31);
+                carry *= __shfl_sync(m, incl, W - 1, W);
             } else {
                 // ---- reverse pass, chunk c
                 const int c = nch > 1 ? 2 * nch - 1 - cc.k : 0;
-                const int q0 = (s & ~3) + c * kRingChunk + 4 * lane;
+                const int q0 = (s & ~3) + c * 4 * W + 4 * gl;
                 Quad cur;
-                ring_read<false>(cur, stage, q0, s, e, lane);
+                ring_read<false, W>(cur, stage, q0, s, e, gl);
                 bool valid[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) valid[j] = q0 + j >= s && q0 + j < e;
@@ -823,8 +870,10 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
                         T[j] = p;
                         p *= (1.f - cur.a[j]);
                     }
-                    const float incl = group_scan_mul<32>(p, lane);
-                    const float baseT = group_bcast<32>(my_chunk_T, c & 31) * group_shift_up<32>(incl, lane, 1.f);
+                    const float incl = ring_scan_mul<W>(m, p, gl);
+                    float excl = __shfl_up_sync(m, incl, 1, W);
+                    if (gl == 0) excl = 1.f;
+                    const float baseT = __shfl_sync(m, my_chunk_T, c & (W - 1), W) * excl;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) T[j] *= baseT;
                 }
@@ -839,10 +888,10 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
                     MB = fmaf(Aj, MB, Bj);
                     MA = Aj * MA;
                 }
-                group_rscan_affine<32>(MA, MB, lane);
+                ring_rscan_affine<W>(m, MA, MB, gl);
                 const float V = fmaf(MA, Rcarry, MB);
-                float R = __shfl_down_sync(VS_FULL_MASK, V, 1, 32);
-                if (lane == 31) R = Rcarry;
+                float R = __shfl_down_sync(m, V, 1, W);
+                if (gl == W - 1) R = Rcarry;
                 float da[4], dc[12], dz[4];
 #pragma unroll
                 for (int j = 3; j >= 0; --j) {
@@ -873,11 +922,12 @@ __global__ void __launch_bounds__(32 * kRingWarps) composite_bwd_ring_kernel(
                         }
                     }
                 }
-                Rcarry = group_bcast<32>(V, 0);
+                Rcarry = __shfl_sync(m, V, 0, W);
             }
-            ring_cursor_next<true>(cc, mine);
+            ring_cursor_next<true, W>(cc, mine, m, lane);
         }
         cp_async_wait<0>();
+        __syncwarp();
     }
 }
 
@@ -1213,7 +1263,7 @@ __global__ void __launch_bounds__(kTileRays) composite_bwd_tile_kernel(
 // 75 % of the HBM peak against 26 % for the scan family), ring family beyond (C3: 61 % against 47 %), except the FORWARD of very long
 // rays (mean > 256), where the one-sample-per-lane scan keeps more loads in flight per instruction (4.8 against 4.3 TB/s at mean 400)
 constexpr double kTileMaxMean = 16.0;     // backward
-constexpr double kTileMaxMeanFwd = 32.0;  // forward (mean 24: tile 0.128 ms, ring 0.167 ms; backward: tile 0.298 ms, ring 0.230 ms)
+constexpr double kTileMaxMeanFwd = 16.0;  // forward (mean 24: tile 0.128 ms, ring with 8-lane groups 0.120 ms)
 constexpr double kRingFwdMaxMean = 256.0;
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1233,13 +1283,21 @@ static inline unsigned ring_grid(int64_t n_rays) {
     const int64_t batches = (n_rays + 31) / 32;
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((batches + kRingWarps - 1) / kRingWarps, (int64_t)sms * 8));
 }
-static inline int ring_depth() {
-    static const int d = [] {
-        const char* env = std::getenv("VS_RING_DEPTH");  // A/B knob: stages of the per-warp ring (2, 3 or 4)
-        const int v = env ? std::atoi(env) : kRingDepthDefault;
-        return (v == 2 || v == 4) ? v : 3;
+// lanes per ray of the ring kernels: a chunk (4W samples) should not be much longer than the typical ray, or most lanes of a chunk are
+// masked; VS_RING_WIDTH overrides (A/B knob)
+static inline int ring_width(int64_t n_rays, int64_t n_samples, bool backward) {
+    static const int forced = [] {
+        const char* env = std::getenv("VS_RING_WIDTH");
+        const int v = env ? std::atoi(env) : 0;
+        return (v == 8 || v == 16 || v == 32) ? v : 0;
     }();
-    return d;
+    if (forced) return forced;
+    // measured (profiles/r01_bench_composite_ring.jsonl): narrow groups pay off in the forward pass of short rays (mean 24: 0.120 ms with
+    // W = 8, 0.167 ms with W = 32); in the backward pass the groups of a warp sit in different passes (transmittance / reverse) most of
+    // the time and serialise (mean 24: 0.264 ms with W = 8, 0.232 ms with W = 32; C3: 0.649 ms with W = 16, 0.533 ms with W = 32)
+    if (backward) return 32;
+    const double mean = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
+    return mean <= 40.0 ? 8 : 32;
 }
 static inline bool ring_in_auto() {
     static const bool off = std::getenv("VS_COMPOSITE_NO_RING") != nullptr;  // A/B knob: auto falls back to the scan family
@@ -1293,12 +1351,13 @@ int vs_composite_fwd(const int32_t* se, const float* alpha, const float* rgb, co
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z);
     // ring family: cp.async-pipelined quads, 32 rays per warp.  Forward: on very long rays the one-sample-per-lane scan streams better
     if ((mode == 8 || (mode == 0 && ring_in_auto() && mean <= kRingFwdMaxMean)) && a16 && n_samples > 0 && n_samples <= 0x7fffffffLL) {
-        const int depth = ring_depth();
-        const size_t smem = sizeof(float) * kRingWarps * depth * kRingStageFloats;
+        const size_t smem = sizeof(float) * kRingWarps * kRingDepthDefault * kRingStageFloats;
         const bool wt = out_w || out_T;
-        auto kern = depth == 2 ? (wt ? composite_fwd_ring_kernel<true, 2> : composite_fwd_ring_kernel<false, 2>)
-                    : depth == 4 ? (wt ? composite_fwd_ring_kernel<true, 4> : composite_fwd_ring_kernel<false, 4>)
-                                 : (wt ? composite_fwd_ring_kernel<true, 3> : composite_fwd_ring_kernel<false, 3>);
+        const int W = ring_width(n_rays, n_samples, false);
+        constexpr int D = kRingDepthDefault;
+        auto kern = W == 8    ? (wt ? composite_fwd_ring_kernel<true, D, 8> : composite_fwd_ring_kernel<false, D, 8>)
+                    : W == 16 ? (wt ? composite_fwd_ring_kernel<true, D, 16> : composite_fwd_ring_kernel<false, D, 16>)
+                              : (wt ? composite_fwd_ring_kernel<true, D, 32> : composite_fwd_ring_kernel<false, D, 32>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<ring_grid(n_rays), 32 * kRingWarps, smem, st>>>(se, alpha, rgb, z, out_rgb, out_depth, out_acc, out_bgT, out_w, out_T, n_rays,
@@ -1365,11 +1424,12 @@ int vs_composite_bwd(const int32_t* se, const float* alpha, const float* rgb, co
     }
     const bool a16 = aligned16(alpha) && aligned16(rgb) && aligned16(z) && aligned16(d_alpha) && aligned16(d_rgb) && (!d_z || aligned16(d_z));
     if ((mode == 8 || (mode == 0 && ring_in_auto())) && a16 && n_samples <= 0x7fffffffLL) {
-        const int depth = ring_depth();
-        const size_t smem = sizeof(float) * kRingWarps * depth * kRingStageFloats;
-        auto kern = depth == 2 ? (d_z ? composite_bwd_ring_kernel<true, 2> : composite_bwd_ring_kernel<false, 2>)
-                    : depth == 4 ? (d_z ? composite_bwd_ring_kernel<true, 4> : composite_bwd_ring_kernel<false, 4>)
-                                 : (d_z ? composite_bwd_ring_kernel<true, 3> : composite_bwd_ring_kernel<false, 3>);
+        const size_t smem = sizeof(float) * kRingWarps * kRingDepthDefault * kRingStageFloats;
+        const int W = ring_width(n_rays, n_samples, true);
+        constexpr int D = kRingDepthDefault;
+        auto kern = W == 8    ? (d_z ? composite_bwd_ring_kernel<true, D, 8> : composite_bwd_ring_kernel<false, D, 8>)
+                    : W == 16 ? (d_z ? composite_bwd_ring_kernel<true, D, 16> : composite_bwd_ring_kernel<false, D, 16>)
+                              : (d_z ? composite_bwd_ring_kernel<true, D, 32> : composite_bwd_ring_kernel<false, D, 32>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<ring_grid(n_rays), 32 * kRingWarps, smem, st>>>(se, alpha, rgb, z, g_rgb, g_depth, g_acc, g_bgT, d_alpha, d_rgb, d_z, n_rays,
