@@ -232,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
 
     from volsurfs_b200 import _lib
     from volsurfs_b200.pipeline import make_synthetic_renderer
-    from volsurfs_b200.synthetic import all_hit_packed, camera_rays, composite_bytes
+    from volsurfs_b200.synthetic import all_hit_packed, camera_rays, composite_bytes, nerf_packets
     from volsurfs_b200.volsurfs import RaySamplesPacked, VolumeRendering as VR
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for the default arm (no CPU fallback)"
@@ -556,6 +556,37 @@ def run_ours(args, rank, world, local_rank):
         comp = {"workload": "fused compositing fwd+bwd, 2^24 rays x 5 samples (5.8 GB algorithmic traffic per pair of launches)",
                 "mrays_s": round(n_big / (ms_c * 1e-3) / 1e6, 1), "bound": "hbm", "achieved": round(nbytes / (ms_c * 1e-3) / 1e9, 1),
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(nbytes / (ms_c * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "ms_per_fwd_bwd": round(ms_c, 4)}
+
+        # the long-ray case (BASELINE config[2]: NeRF-style packets, <= 1024 samples per ray): ring / scan kernel families
+        del a, c, z, gs, d, rsp_b
+        torch.cuda.empty_cache()
+        p3 = nerf_packets(640000, seed_offset=3)
+        rsp_l = RaySamplesPacked(0, 0, 0, 1)
+        rsp_l.ray_start_end_idx = p3["se"].to(dev)
+        a, c, z = p3["alpha"].to(dev), p3["rgb"].to(dev), p3["z"].to(dev)
+        gs = [p3[k].to(dev) for k in ("g_rgb", "g_depth", "g_acc", "g_bgT")]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            VR.composite(rsp_l, a, c, z)
+            VR.composite_backward(rsp_l, a, c, z, *gs)
+        ts = []
+        for _ in range(7):
+            flush.zero_()  # 1.2 GB of inputs per pass, but keep L2 cold between the timed pairs all the same
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            VR.composite(rsp_l, a, c, z)
+            VR.composite_backward(rsp_l, a, c, z, *gs)
+            c1.record()
+            torch.cuda.synchronize()
+            ts.append(c0.elapsed_time(c1))
+        ms_l = sorted(ts)[len(ts) // 2]
+        S_l = int(a.shape[0])
+        nbytes_l = composite_bytes(640000, S_l)
+        comp["long_rays"] = {"workload": f"fused compositing fwd+bwd, BASELINE config[2]: 640000 rays, {S_l} samples (<= 1024 per ray, 35 % empty rays)",
+                             "mrays_s": round(640000 / (ms_l * 1e-3) / 1e6, 1), "bound": "hbm", "achieved": round(nbytes_l / (ms_l * 1e-3) / 1e9, 1),
+                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(nbytes_l / (ms_l * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+                             "ms_per_fwd_bwd": round(ms_l, 4)}
+        del a, c, z, gs, p3, rsp_l, flush
 
     # ---- cpu baseline (bounded sample, rank 0, N=1 only)
     cpu = None
