@@ -95,7 +95,9 @@ int vs_compute_cdf(const int32_t* ray_start_end_idx, const float* weights, float
  * Replaces the chain cumprod -> alpha*T -> sum_over_rays -> integrate_3d -> integrate_1d of nerf.py:308-334 and equals
  * the dense K-layer torch path volsurfs_py/methods/volsurfs.py:601-640,708.  bgT is the FULL product of (1-alpha).
  * out_w / out_T (per-sample weights and transmittance) may be NULL.  d_z may be NULL.
- * mode: 0 auto, 1 force tile kernels, 2 force scan kernels, 3 scan kernels with 8-lane groups (for A/B measurements). */
+ * mode: 0 auto (tile kernels up to a mean of 16 samples per ray, cp.async ring kernels beyond, scan kernels for the forward pass above
+ * 256); 1 tile kernels (TMA staging), 2 scan kernels (one sample per lane), 3 / 5 / 6 / 7 coarsened scan kernels (auto / 8 / 16 / 32 lanes
+ * per ray), 4 tile kernels with LDG staging, 8 ring kernels — 1..8 exist for A/B measurements. */
 int vs_composite_fwd(const int32_t* ray_start_end_idx, const float* alpha, const float* rgb, const float* z, float* out_rgb,
                      float* out_depth, float* out_acc, float* out_bgT, float* out_w, float* out_T, int64_t n_rays, int64_t n_samples,
                      int mode, void* stream);
