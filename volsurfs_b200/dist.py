@@ -46,6 +46,11 @@ class GradAllReducer:
         bucket, size = [], 0
         for t in tensors:
             nbytes = t.numel() * t.element_size()
+            if nbytes * 2 >= self.bucket_bytes and t.is_contiguous():
+                # a tensor of bucket size on its own (a hash-table gradient: 50 MB): reduced in place, no staging copy in or out
+                work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._pending.append((work, t, None, world))
+                continue
             if bucket and size + nbytes > self.bucket_bytes:
                 self._flush(bucket, world)
                 bucket, size = [], 0
@@ -63,6 +68,8 @@ class GradAllReducer:
         for work, flat, bucket, world in self._pending:
             work.wait()
             flat.div_(world)
+            if bucket is None:
+                continue
             off = 0
             for t in bucket:
                 n = t.numel()
