@@ -509,10 +509,9 @@ __global__ void __launch_bounds__(kScanThreads) composite_bwd_scan4_kernel(
 constexpr int kRingWarps = 8;
 constexpr int kRingDepthDefault = 3;
 constexpr int kRingStageFloats = 640;  // 128 alpha | 128 z | 384 rgb
-constexpr int kRingChunk = 128;        // samples per chunk (4 per lane)
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async16_full(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -628,14 +627,26 @@ __device__ __forceinline__ void ring_issue(float* stage, const float* __restrict
         }
         return;
     }
-    const int valid = n_samples - q0;  // 1..3 samples of the quad inside the arrays
-    cp_async16(sa, alpha + q0, 4 * valid);
-    if (!ALPHA_ONLY) {
-        cp_async16(sz, z + q0, 4 * valid);
-        const int cb = 12 * valid;
-        cp_async16(sc, c3, min(16, cb));
-        cp_async16(sc + 4, cb > 16 ? c3 + 4 : rgb, max(0, min(16, cb - 16)));
-        cp_async16(sc + 8, cb > 32 ? c3 + 8 : rgb, max(0, min(16, cb - 32)));
+    // the last quad of the arrays (1..3 samples inside them): element-wise copies, the rest of the quad zeroed — no byte past the end
+    // of an array is ever addressed
+    const int valid = n_samples - q0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < valid) {
+            cp_async4(sa + j, alpha + q0 + j);
+            if (!ALPHA_ONLY) {
+                cp_async4(sz + j, z + q0 + j);
+                cp_async4(sc + 3 * j, c3 + 3 * j);
+                cp_async4(sc + 3 * j + 1, c3 + 3 * j + 1);
+                cp_async4(sc + 3 * j + 2, c3 + 3 * j + 2);
+            }
+        } else {
+            sa[j] = 0.f;
+            if (!ALPHA_ONLY) {
+                sz[j] = 0.f;
+                sc[3 * j] = sc[3 * j + 1] = sc[3 * j + 2] = 0.f;
+            }
+        }
     }
 }
 
