@@ -117,7 +117,7 @@ def test_ring_family_group_widths_and_spill(counts):
 @pytest.mark.parametrize("n_rays,K", [(1, 5), (255, 5), (257, 9), (1000, 1)])
 def test_edge_sizes(n_rays, K):
     d = all_hit_packed(n_rays, K)
-    for mode in (1, 2, 3, 4, 5, 7, 8):
+    for mode in (0, 1, 2, 3, 4, 5, 7, 8):
         _check(d["se"], d["alpha"], d["rgb"], d["z"], d, mode)
 
 
