@@ -236,6 +236,104 @@ __global__ void __launch_bounds__(1024, 1) hashgrid_backward_dense_kernel(const 
     }
 }
 
+// Dense levels in lerp mode, one thread per HIT: the 4 texel corners of a hit are neighbouring texels, and on the coarse (dense) levels
+// they fall into the same grid cell most of the time, i.e. they update the SAME 4 entries — the thread adds ONE combined contribution
+// per entry: up to 4x fewer shared-memory atomics on exactly the levels where they collide most.
+struct HgCell {
+    uint32_t gx, gy;
+    float rx, ry;
+};
+__device__ __forceinline__ HgCell hg_cell(const HgLevels& lv, int level, float2 x) {
+    const float scale = lv.scale[level];
+    const float px = __fadd_rn(__fmul_rn(x.x, scale), 0.5f), py = __fadd_rn(__fmul_rn(x.y, scale), 0.5f);
+    const float fx = floorf(px), fy = floorf(py);
+    return HgCell{(uint32_t)(int)fx, (uint32_t)(int)fy, __fsub_rn(px, fx), __fsub_rn(py, fy)};
+}
+__device__ __forceinline__ void hg_dense_entries(const HgLevels& lv, int level, const HgCell& c, uint32_t idx[4]) {
+    const uint32_t res = lv.res[level], size = lv.size[level], off = lv.offset[level];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t h = (c.gx + (uint32_t)(k & 1)) + (c.gy + (uint32_t)((k >> 1) & 1)) * res;
+        if (h >= size) h %= size;
+        idx[k] = off + h;
+    }
+}
+__device__ __forceinline__ void hg_cell_weights(const HgCell& c, float w[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float wx = (k & 1) ? c.rx : 1.f - c.rx, wy = (k & 2) ? c.ry : 1.f - c.ry;
+        w[k] = wx * wy;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) hashgrid_backward_dense_lerp_kernel(const HgLevels lv, const TexGeom tg, const float* __restrict__ uv,
+                                                                               const float* __restrict__ d_feat, float* __restrict__ d_table,
+                                                                               int64_t n_samples, const int64_t* __restrict__ n_valid_dev,
+                                                                               int lv_end, int n_entries) {
+    extern __shared__ float acc[];  // [n_entries][2]
+    for (int i = threadIdx.x; i < 2 * n_entries; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    int64_t n = n_samples;
+    if (n_valid_dev != nullptr) n = min(n, *n_valid_dev);
+    const int L = lv.n_levels;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        const float u = __ldg(uv + 2 * s), v = __ldg(uv + 2 * s + 1);
+        float2 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = texel_query(tg, u, v, k, nullptr);
+        const float2* src = reinterpret_cast<const float2*>(d_feat + (4 * s) * (2 * L));
+        for (int level = 0; level < lv_end; ++level) {
+            HgCell c[4];
+            float2 g[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                c[k] = hg_cell(lv, level, q[k]);
+                g[k] = __ldg(src + k * L + level);
+            }
+            const bool same = c[1].gx == c[0].gx && c[1].gy == c[0].gy && c[2].gx == c[0].gx && c[2].gy == c[0].gy && c[3].gx == c[0].gx &&
+                              c[3].gy == c[0].gy;
+            uint32_t idx[4];
+            if (same) {
+                float2 sum[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float w[4];
+                    hg_cell_weights(c[k], w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        sum[j].x = fmaf(w[j], g[k].x, sum[j].x);
+                        sum[j].y = fmaf(w[j], g[k].y, sum[j].y);
+                    }
+                }
+                hg_dense_entries(lv, level, c[0], idx);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (sum[j].x != 0.f) atomicAdd(acc + 2 * idx[j], sum[j].x);
+                    if (sum[j].y != 0.f) atomicAdd(acc + 2 * idx[j] + 1, sum[j].y);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (g[k].x == 0.f && g[k].y == 0.f) continue;
+                    float w[4];
+                    hg_cell_weights(c[k], w);
+                    hg_dense_entries(lv, level, c[k], idx);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        atomicAdd(acc + 2 * idx[j], w[j] * g[k].x);
+                        atomicAdd(acc + 2 * idx[j] + 1, w[j] * g[k].y);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * n_entries; i += blockDim.x) {
+        const float v = acc[i];
+        if (v != 0.f) atomicAdd(d_table + i, v);
+    }
+}
+
 // ---- coefficient assembly + SH evaluation ----------------------------------------------------------------------------------------
 struct ShTexConfig {
     int sh_deg, nr_channels, n_coeffs;
@@ -555,10 +653,19 @@ int vs_hashgrid_backward(int n_levels, int log2_hashmap_size, int base_resolutio
         const int smem = dense_entries * 8;
         cudaError_t ce = cudaFuncSetAttribute(hashgrid_backward_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (ce != cudaSuccess) return (int)ce;
-        const int64_t work = n_samples * corners;
-        const int grid = (int)std::min<int64_t>(std::max<int64_t>(div_up(work, 1024), 1), sms);
-        hashgrid_backward_dense_kernel<<<grid, 1024, smem, (cudaStream_t)stream>>>(lv, tg, uv, d_features, d_table, n_samples, n_valid_dev,
-                                                                                   dense_end, dense_entries);
+        static const bool per_row = std::getenv("VS_HASHGRID_DENSE_PER_ROW") != nullptr;  // A/B knob
+        if (mode == 1 && !per_row) {
+            ce = cudaFuncSetAttribute(hashgrid_backward_dense_lerp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (ce != cudaSuccess) return (int)ce;
+            const int grid = (int)std::min<int64_t>(std::max<int64_t>(div_up(n_samples, 1024), 1), sms);
+            hashgrid_backward_dense_lerp_kernel<<<grid, 1024, smem, (cudaStream_t)stream>>>(lv, tg, uv, d_features, d_table, n_samples,
+                                                                                            n_valid_dev, dense_end, dense_entries);
+        } else {
+            const int64_t work = n_samples * corners;
+            const int grid = (int)std::min<int64_t>(std::max<int64_t>(div_up(work, 1024), 1), sms);
+            hashgrid_backward_dense_kernel<<<grid, 1024, smem, (cudaStream_t)stream>>>(lv, tg, uv, d_features, d_table, n_samples, n_valid_dev,
+                                                                                       dense_end, dense_entries);
+        }
         ++launches;
     }
     if (dense_end < n_levels) {
