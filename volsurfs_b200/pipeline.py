@@ -223,8 +223,12 @@ class TexturedShellRenderer:
     Hits are routed to their layer's models with one stable sort by layer per step (one host read of the per-layer counts; the
     reference reads ``any_hit`` on the host once per mesh)."""
 
-    def __init__(self, tracer: ShellTracer, rgb_models, alpha_models, bg_color=(1.0, 1.0, 1.0), with_alpha_decay: bool = True):
+    def __init__(self, tracer: ShellTracer, rgb_models, alpha_models, bg_color=(1.0, 1.0, 1.0), with_alpha_decay: bool = True,
+                 n_streams: int = 4):
         assert len(rgb_models) == tracer.nr_meshes and len(alpha_models) == tracer.nr_meshes
+        # the 2K models are independent and their kernels (narrow networks, atomics) leave most of an SM idle: spread them over a few
+        # CUDA streams so that kernels of different models overlap; autograd replays every backward on its forward's stream
+        self.streams = [torch.cuda.Stream(device=tracer.device) for _ in range(max(int(n_streams), 0))]
         self.tracer = tracer
         self.rgb_models = torch.nn.ModuleList(rgb_models)
         self.alpha_models = torch.nn.ModuleList(alpha_models)
@@ -251,12 +255,29 @@ class TexturedShellRenderer:
         counts = torch.bincount(layer, minlength=self.K).tolist()
         uv_s, dirs_s = rsp.samples_tex_uv[order], rsp.samples_dirs[order]
         rgb_parts, alpha_parts, o = [], [], 0
+        main = torch.cuda.current_stream()
+        jobs = []
         for k in range(self.K):
             n = counts[k]
             if n:
-                rgb_parts.append(self.rgb_models[k](uv_coords=uv_s[o:o + n], view_dirs=dirs_s[o:o + n]))
-                alpha_parts.append(self.alpha_models[k](uv_coords=uv_s[o:o + n], view_dirs=dirs_s[o:o + n]))
+                jobs.append((self.rgb_models[k], rgb_parts, uv_s[o:o + n], dirs_s[o:o + n]))
+                jobs.append((self.alpha_models[k], alpha_parts, uv_s[o:o + n], dirs_s[o:o + n]))
             o += n
+        if self.streams:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for i, (model, dst, uv_k, dirs_k) in enumerate(jobs):
+                st = self.streams[i % len(self.streams)]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    out_k = model(uv_coords=uv_k, view_dirs=dirs_k)
+                out_k.record_stream(main)
+                dst.append(out_k)
+            for st in self.streams:
+                main.wait_stream(st)
+        else:
+            for model, dst, uv_k, dirs_k in jobs:
+                dst.append(model(uv_coords=uv_k, view_dirs=dirs_k))
         inv = torch.empty_like(order)
         inv[order] = torch.arange(S, device=dev)
         rgb = torch.cat(rgb_parts)[inv]
