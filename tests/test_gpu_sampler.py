@@ -236,3 +236,39 @@ def test_init_with_one_sample_per_ray():
     assert rsp.get_total_nr_samples() == 100 and torch.equal(rsp.samples_3d, p) and torch.equal(rsp.samples_dirs, d)
     assert float(rsp.samples_z.abs().max()) == 0.0 and float(rsp.samples_dt.abs().max()) == 0.0
     assert rsp.ray_start_end_idx[7].tolist() == [7, 8]
+
+
+def test_full_size_properties():
+    """BASELINE config[2] size (640k rays, 128^3 voxels, <= 1024 samples per ray): size-independent properties of the sampler's packet"""
+    from volsurfs_b200.volsurfs import OccupancyGrid, RaySampler
+
+    sc = make_scene(640000, 128, seed=41)
+    t = _cuda_scene(sc)
+    _reset_rng()
+    rsp = RaySampler.compute_samples_fg_in_grid_occupied_regions(t["o"], t["d"], t["t_entry"], t["t_exit"], 0.0015, 1, 1024, True, sc["n"],
+                                                                 sc["extent"], t["occ"], t["roi"], 1)
+    S = rsp.get_total_nr_samples()
+    se = rsp.ray_start_end_idx
+    cnt = rsp.get_nr_samples_per_ray().long()
+    assert S > 10_000_000 and int(cnt.max()) <= 1024 and int(cnt.sum()) == S
+    has = cnt > 0
+    # segments are the exclusive prefix sum of the counts, empty rays carry (-1,-1)
+    start = torch.cumsum(cnt, 0) - cnt
+    assert torch.equal(se[has, 0].long(), start[has]) and torch.equal(se[has, 1].long(), (start + cnt)[has]) and bool((se[~has] == -1).all())
+    # depths strictly increase inside a ray and stay inside [t_entry, t_exit]
+    ray_of = torch.repeat_interleave(torch.arange(cnt.numel(), device="cuda"), cnt)
+    z = rsp.samples_z.view(-1)
+    same_ray = ray_of[1:] == ray_of[:-1]
+    assert bool((z[1:][same_ray] > z[:-1][same_ray]).all())
+    assert bool((z >= t["t_entry"].view(-1)[ray_of]).all()) and bool((z <= t["t_exit"].view(-1)[ray_of]).all())
+    # every sample sits in an occupied voxel of the region of interest; positions are o + z d
+    og = OccupancyGrid(sc["n"], sc["extent"])
+    og.set_grid_occupancy(t["occ"])
+    og.set_grid_roi(t["roi"])
+    occ, _ = og.check_occupancy(rsp.samples_3d)
+    assert bool(occ.all())
+    want = torch.addcmul(t["o"][ray_of], z.unsqueeze(1), t["d"][ray_of])
+    assert float((rsp.samples_3d - want).abs().max()) < 1e-6
+    # samples_idx = slot in the reference's uncompacted packet
+    pos_in_ray = torch.arange(S, device="cuda") - start[ray_of]
+    assert torch.equal(rsp.samples_idx.view(-1).long(), ray_of * 1024 + pos_in_ray)

@@ -232,3 +232,43 @@ def test_argument_errors(lib):
         SHNeuralTextures(sh_deg=1, quantize_output=True, squeeze_output=False)
     assert lib.vs_hashgrid_forward(17, 15, 16, ctypes.c_float(1.5), 1, 1, 8, 8, None, None, None, 0, None, None) != 0
     assert lib.vs_shtex_combine_forward(5, 3, 1, 1, None, None, None, 1, 1, None, None, None, None, None, 0, None, None) != 0
+
+
+def test_full_size_properties():
+    """one layer's hits at BASELINE config[1] size (178k hits, default 2048..256 textures): size-independent properties"""
+    from volsurfs_b200.textures import SHNeuralTextures
+
+    torch.manual_seed(21)
+    m = SHNeuralTextures(sh_deg=3, nr_channels=3, sh_range=[15.0] * 4, lerp=True, deg_res=[2048, 1024, 512, 256], quantize_output=True,
+                         squeeze_output=True, align_to_webgl=True).cuda()
+    with torch.no_grad():
+        for nt in m.neural_textures:
+            nt.model.table.copy_((torch.rand_like(nt.model.table) * 2 - 1) * 0.5)
+    n = 178548
+    uv = torch.rand(n, 2, device="cuda")
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda"), dim=1)
+    coeffs = m(uv_coords=uv, view_dirs=None).detach()
+    assert coeffs.shape == (n, 3, 16) and float(coeffs.abs().max()) <= 15.0 + 1e-2
+    out = m(uv_coords=uv, view_dirs=dirs)
+    assert out.shape == (n, 3) and float(out.detach().min()) > 0.0 and float(out.detach().max()) < 1.0
+    # the output is sigmoid(SH(fp16 coefficients, dirs)): recompute it from the coefficient tensor in fp64
+    from oracle.appearance import sh_encode
+
+    basis = sh_encode(dirs.double().cpu(), 3)                                     # [n,16]
+    want = torch.sigmoid((coeffs.half().double().cpu() * basis.unsqueeze(1)).sum(-1))
+    assert float((out.detach().cpu().double() - want).abs().max()) < 2e-3          # degree-0 term is an fp16 product in the reference
+    # backward: linear in the upstream gradient, and only table rows the batch touches receive gradient
+    g = torch.randn(n, 3, device="cuda")
+    (out * g).sum().backward()
+    g1 = [nt.model.table.grad.clone() for nt in m.neural_textures]
+    w1 = [w.grad.clone() for nt in m.neural_textures for w in nt.model.weights]
+    for p in m.parameters():
+        p.grad = None
+    out2 = m(uv_coords=uv, view_dirs=dirs)
+    (out2 * (2.0 * g)).sum().backward()
+    for a, nt in zip(g1, m.neural_textures):
+        b = nt.model.table.grad
+        assert float((b - 2 * a).abs().max()) <= 2e-2 * float(a.abs().max())
+    for a, w in zip(w1, [w for nt in m.neural_textures for w in nt.model.weights]):
+        assert float((w.grad - 2 * a).abs().max()) <= 2e-2 * float(a.abs().max())
+    assert all(torch.isfinite(t).all() for t in g1 + w1)
