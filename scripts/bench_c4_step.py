@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--rays-per-gpu", type=int, default=32768)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="explicit-kernel step replayed as one CUDA graph")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -71,6 +72,34 @@ def main():
         return loss, rsp.get_total_nr_samples()
 
     batches = [batch() for _ in range(4)]
+    if args.graph:
+        # the same step through EncodedShellRenderer (explicit forward / backward kernels, capacity-sized buffers, no host read),
+        # captured once into a CUDA graph; the gradient exchange runs on the replayed graph's outputs
+        from volsurfs_b200.pipeline import EncodedShellRenderer
+
+        er = EncodedShellRenderer(tracer, heads[0], heads[1], encs[0], encs[1])
+        s_o, s_d, s_gt = (t.clone() for t in batches[0])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                er.render_fwd_bwd(s_o, s_d, s_gt)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_out = er.render_fwd_bwd(s_o, s_d, s_gt)
+        grads = [g_out["grad_lattice_rgb"], g_out["grad_lattice_alpha"], g_out["grad_rgb"], g_out["grad_alpha"]]
+
+        def step(o, d, gt, exchange=True):  # noqa: F811
+            s_o.copy_(o)
+            s_d.copy_(d)
+            s_gt.copy_(gt)
+            graph.replay()
+            if exchange and world > 1:
+                reducer.launch(grads)
+                reducer.wait()
+            return g_out["loss"], 0
+
     for i in range(args.warmup):
         step(*batches[i % 4])
 
@@ -99,7 +128,8 @@ def main():
             "n_gpus": world, "rays_per_gpu": args.rays_per_gpu, "rays_per_step": args.rays_per_gpu * world, "hits_per_gpu": round(hits),
             "ms_per_step": round(ms_step, 3), "mrays_s": round(args.rays_per_gpu * world / ms_step / 1e3, 2),
             "ms_per_step_without_exchange": round(ms_noex, 3), "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-            "note": "autograd-driven (eager) step with one host read per step (exact-size packing); all-reduce = fp32 sum of every lattice "
+            "mode": "EncodedShellRenderer step replayed as one CUDA graph" if args.graph else "autograd-driven (eager)",
+            "note": "eager mode reads the sample count on the host once per step (exact-size packing); all-reduce = fp32 sum of every lattice "
                     "and head gradient, 64 MB buckets, mean over ranks"}), flush=True)
     if world > 1:
         dist.destroy_process_group()

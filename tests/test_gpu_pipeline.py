@@ -79,3 +79,45 @@ def test_pipelined_host_fed_loop_matches_eager(lib):
     loop.drain(len(views))
     torch.cuda.synchronize()
     assert torch.equal(img_pin, want[-1][0]) and float(loss_pin) == want[-1][1]
+
+
+def test_encoded_renderer_matches_the_autograd_path():
+    """EncodedShellRenderer (explicit forward / backward kernels, graph-capturable; BASELINE config[3]) against the same step driven by
+    torch autograd through the library's Function wrappers: loss, image, head and lattice gradients"""
+    from conftest import grad_err
+    from volsurfs_b200.appearance import AppearanceHead
+    from volsurfs_b200.encoding import PermutoHashEncoder
+    from volsurfs_b200.pipeline import EncodedShellRenderer
+    from volsurfs_b200.raytracer import ShellTracer
+    from volsurfs_b200.synthetic import camera_rays, shell_meshes
+    from volsurfs_b200.volume_rendering import composite
+
+    dev = torch.device("cuda", 0)
+    tracer = ShellTracer(shell_meshes(K=3, n_lat=48, n_lon=48))
+    torch.manual_seed(5)
+    encs = [PermutoHashEncoder(log2_hashmap_size=14, bb_sides=2.0, device=dev) for _ in range(2)]
+    heads = [AppearanceHead(encs[0].output_dim, (64, 64, 64), 3, 3, False, "gelu", False).to(dev),
+             AppearanceHead(encs[1].output_dim, (64, 64, 64), 1, 3, False, "gelu", True).to(dev)]
+    o, d = camera_rays(64, 64)
+    o, d = o.cuda(), d.cuda()
+    gt = torch.rand(o.shape[0], 3, device=dev)
+    r = EncodedShellRenderer(tracer, heads[0], heads[1], encs[0], encs[1])
+    got = r.render_fwd_bwd(o, d, gt)
+    # autograd path
+    rsp = tracer.render_samples(o, d, exact_size=True, with_normals=True)
+    f_rgb, _ = encs[0](rsp.samples_3d)
+    f_alpha, _ = encs[1](rsp.samples_3d)
+    rgb = heads[0](f_rgb, rsp.samples_dirs, rsp.samples_normals)
+    alpha = heads[1](f_alpha, rsp.samples_dirs, rsp.samples_normals)
+    rgb_fg, _, _, bgT = composite(rsp, alpha, rgb)
+    pred = rgb_fg + bgT
+    loss = (pred - gt).abs().mean()
+    loss.backward()
+    assert rsp.get_total_nr_samples() > 500
+    assert torch.allclose(got["rgb"], pred.detach(), atol=1e-6) and abs(float(got["loss"]) - float(loss.detach())) < 1e-6
+    for name, head, enc in (("rgb", heads[0], encs[0]), ("alpha", heads[1], encs[1])):
+        want_flat = torch.cat([p.grad.reshape(-1) for lin in head.layers for p in (lin.weight, lin.bias)])
+        e1 = grad_err(got["grad_" + name].cpu().numpy(), want_flat.cpu().numpy())
+        e2 = grad_err(got["grad_lattice_" + name].cpu().numpy(), enc.encoder.lattice_values.grad.cpu().numpy())
+        print(name, "head grad_err %.2e lattice grad_err %.2e" % (e1, e2))
+        assert e1 < 1e-4 and e2 < 1e-4

@@ -115,6 +115,69 @@ class ShellRenderer:
         return out
 
 
+class EncodedShellRenderer(ShellRenderer):
+    """The legacy appearance with its real positional encoders: every head owns a permutohedral hash encoder (rgb.py:40-60,
+    encodings/permutohash.py), so a training step is trace -> pack -> 2 x encode -> 2 x head -> composite -> loss -> composite backward
+    -> 2 x head backward -> 2 x lattice scatter.  Like ShellRenderer it drives forward and backward explicitly, keeps capacity-sized
+    buffers and the sample count on the device, and can therefore be captured into one CUDA graph (BASELINE config[3])."""
+
+    def __init__(self, tracer: ShellTracer, rgb_head: AppearanceHead, alpha_head: AppearanceHead, rgb_encoder, alpha_encoder,
+                 bg_color=(1.0, 1.0, 1.0)):
+        super().__init__(tracer, rgb_head, alpha_head, bg_color)
+        self.encoders = {"rgb": rgb_encoder, "alpha": alpha_encoder}
+        self._bufs = {}
+
+    def _buf(self, key, shape, zero=False):
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.tracer.device)
+            self._bufs[key] = t
+        return t
+
+    def parameters(self):
+        return ([p for e in self.encoders.values() for p in e.parameters()] + list(self.rgb_head.parameters())
+                + list(self.alpha_head.parameters()))
+
+    def render_fwd_bwd(self, rays_o, rays_d, gt_rgb):
+        """one training step; returns loss, image and the gradients: ``grad_<head>`` (flat Linear gradients, AppearanceHead.split_flat
+        layout) and ``grad_lattice_<head>`` (shaped like the encoder's lattice_values)"""
+        rsp = self.intersect_and_pack(rays_o, rays_d)
+        cap = rsp.get_max_nr_samples()
+        heads = {"rgb": self.rgb_head, "alpha": self.alpha_head}
+        feats, outs, stashes = {}, {}, {}
+        for name, head in heads.items():
+            enc = self.encoders[name]
+            e = enc.encoder
+            feats[name] = self._buf("feat_" + name, (cap, enc.output_dim), zero=True)
+            e._launch_forward(e.lattice_values, rsp.samples_3d, enc.window(None), enc.output_dim, enc.bb_sides, rsp.total_dev, out=feats[name])
+            stash = self._bufs.get("stash_" + name)
+            if stash is None or stash.numel() < head.stash_bytes(cap):
+                stash = self._bufs["stash_" + name] = head.new_stash(cap, self.tracer.device)
+            stashes[name] = stash
+            outs[name], _ = head.forward_train(feats[name], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash,
+                                               out=self._buf("out_" + name, (cap, head.out_dim)))
+        comp = self.composite(rsp, outs["alpha"], outs["rgb"])
+        diff = comp["rgb"] - gt_rgb
+        loss = diff.abs().mean()
+        g_pred = torch.sign(diff) / diff.numel()
+        d_alpha, d_rgb = self.composite_backward(rsp, outs["alpha"], outs["rgb"], g_pred)
+        result = {"loss": loss, "rgb": comp["rgb"], "ray_samples_packed": rsp}
+        for name, head, g in (("rgb", heads["rgb"], d_rgb), ("alpha", heads["alpha"], d_alpha)):
+            enc = self.encoders[name]
+            e = enc.encoder
+            flat = self._buf("grad_" + name, (head.num_params(),), zero=True)
+            d_feat = self._buf("dfeat_" + name, (cap, enc.output_dim), zero=True)
+            head.backward_into(feats[name], rsp.samples_dirs, rsp.samples_normals, g, flat, d_feat, False, rsp.total_dev, stash=stashes[name],
+                               fwd_out=outs[name])
+            d_lat = self._buf("dlat_" + name, tuple(e.lattice_values.shape), zero=True)
+            d_lat.zero_()
+            e._launch_backward(e.lattice_values, rsp.samples_3d, enc.window(None), d_feat, enc.bb_sides, rsp.total_dev, want_lattice=True,
+                               d_lattice=d_lat)
+            result["grad_" + name] = flat
+            result["grad_lattice_" + name] = d_lat
+        return result
+
+
 class GraphedTrainingStep:
     """``ShellRenderer.render_fwd_bwd`` captured once into a CUDA graph and replayed with one launch per step.
 
