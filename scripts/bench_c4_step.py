@@ -85,18 +85,25 @@ def main():
             for _ in range(2):
                 er.render_fwd_bwd(s_o, s_d, s_gt)
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            g_out = er.render_fwd_bwd(s_o, s_d, s_gt)
-        grads = [g_out["grad_lattice_rgb"], g_out["grad_lattice_alpha"], g_out["grad_rgb"], g_out["grad_alpha"]]
+        # two graphs: everything up to the colour branch's gradients, then the transparency branch's backward — the all-reduce of the
+        # first 50 MB lattice gradient runs on NCCL's stream under the second graph
+        pool = torch.cuda.graph_pool_handle()
+        graph1, graph2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph1, pool=pool):
+            g_out = er.render_fwd_bwd(s_o, s_d, s_gt, rgb_branch_only=True)
+        with torch.cuda.graph(graph2, pool=pool):
+            g_out.update(er.branch_backward("alpha"))
 
         def step(o, d, gt, exchange=True):  # noqa: F811
             s_o.copy_(o)
             s_d.copy_(d)
             s_gt.copy_(gt)
-            graph.replay()
+            graph1.replay()
             if exchange and world > 1:
-                reducer.launch(grads)
+                reducer.launch([g_out["grad_lattice_rgb"], g_out["grad_rgb"]])
+            graph2.replay()
+            if exchange and world > 1:
+                reducer.launch([g_out["grad_lattice_alpha"], g_out["grad_alpha"]])
                 reducer.wait()
             return g_out["loss"], 0
 

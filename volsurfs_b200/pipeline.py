@@ -138,7 +138,7 @@ class EncodedShellRenderer(ShellRenderer):
         return ([p for e in self.encoders.values() for p in e.parameters()] + list(self.rgb_head.parameters())
                 + list(self.alpha_head.parameters()))
 
-    def render_fwd_bwd(self, rays_o, rays_d, gt_rgb):
+    def render_fwd_bwd(self, rays_o, rays_d, gt_rgb, rgb_branch_only: bool = False):
         """one training step; returns loss, image and the gradients: ``grad_<head>`` (flat Linear gradients, AppearanceHead.split_flat
         layout) and ``grad_lattice_<head>`` (shaped like the encoder's lattice_values)"""
         rsp = self.intersect_and_pack(rays_o, rays_d)
@@ -162,20 +162,29 @@ class EncodedShellRenderer(ShellRenderer):
         g_pred = torch.sign(diff) / diff.numel()
         d_alpha, d_rgb = self.composite_backward(rsp, outs["alpha"], outs["rgb"], g_pred)
         result = {"loss": loss, "rgb": comp["rgb"], "ray_samples_packed": rsp}
-        for name, head, g in (("rgb", heads["rgb"], d_rgb), ("alpha", heads["alpha"], d_alpha)):
-            enc = self.encoders[name]
-            e = enc.encoder
-            flat = self._buf("grad_" + name, (head.num_params(),), zero=True)
-            d_feat = self._buf("dfeat_" + name, (cap, enc.output_dim), zero=True)
-            head.backward_into(feats[name], rsp.samples_dirs, rsp.samples_normals, g, flat, d_feat, False, rsp.total_dev, stash=stashes[name],
-                               fwd_out=outs[name])
-            d_lat = self._buf("dlat_" + name, tuple(e.lattice_values.shape), zero=True)
-            d_lat.zero_()
-            e._launch_backward(e.lattice_values, rsp.samples_3d, enc.window(None), d_feat, enc.bb_sides, rsp.total_dev, want_lattice=True,
-                               d_lattice=d_lat)
-            result["grad_" + name] = flat
-            result["grad_lattice_" + name] = d_lat
+        self._state = (rsp, feats, outs, stashes, {"rgb": d_rgb, "alpha": d_alpha})
+        for name in (("rgb",) if rgb_branch_only else ("rgb", "alpha")):
+            result.update(self.branch_backward(name))
         return result
+
+    def branch_backward(self, name):
+        """backward of one head and its encoder from the state the forward part left behind: ``grad_<name>`` and ``grad_lattice_<name>``.
+        ``render_fwd_bwd(..., rgb_branch_only=True)`` followed by ``branch_backward("alpha")`` lets a caller start the gradient exchange
+        of the colour branch while the transparency branch is still computing."""
+        rsp, feats, outs, stashes, d_out = self._state
+        head = self.rgb_head if name == "rgb" else self.alpha_head
+        enc = self.encoders[name]
+        e = enc.encoder
+        cap = rsp.get_max_nr_samples()
+        flat = self._buf("grad_" + name, (head.num_params(),), zero=True)
+        d_feat = self._buf("dfeat_" + name, (cap, enc.output_dim), zero=True)
+        head.backward_into(feats[name], rsp.samples_dirs, rsp.samples_normals, d_out[name], flat, d_feat, False, rsp.total_dev,
+                           stash=stashes[name], fwd_out=outs[name])
+        d_lat = self._buf("dlat_" + name, tuple(e.lattice_values.shape), zero=True)
+        d_lat.zero_()
+        e._launch_backward(e.lattice_values, rsp.samples_3d, enc.window(None), d_feat, enc.bb_sides, rsp.total_dev, want_lattice=True,
+                           d_lattice=d_lat)
+        return {"grad_" + name: flat, "grad_lattice_" + name: d_lat}
 
 
 class GraphedTrainingStep:
