@@ -318,6 +318,10 @@ int vs_sampler_fg_write(const float* rays_o, const float* rays_d, int max_nr, co
 int vs_sampler_bg(const float* rays_o, const float* rays_d, const float* t_start, float t_far, int nr_samples_per_ray, uint64_t rng_state,
                   uint64_t rng_inc, int jitter, float* ray_max_dt, float* samples_3d, float* samples_dirs, float* samples_z, int32_t* se,
                   int64_t n_rays, void* stream);
+/* RaySampler::contract_samples / uncontract_samples (src/RaySampler.cu:336-427; kernels RaySamplerGPU.cuh:528-658) without the closing
+ * update_dt: scene contraction x -> (2 - 1/|2x|) x/|2x| for |2x| > 1 (uncontract: its inverse), depth re-measured from ray_o */
+int vs_sampler_contract(const float* ray_o, const int32_t* se, const float* samples_3d, const float* samples_z, float* out_3d, float* out_z,
+                        int uncontract, int64_t n_rays, void* stream);
 int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* t_near, float* t_far, int64_t n_rays,
                                  void* stream);

@@ -109,6 +109,20 @@ int ref_samples_fg_occupied(const float* rays_o, const float* rays_d, const floa
     return finish();
 }
 
+// RaySampler.cu:336-427: contract_samples / uncontract_samples (before the closing update_dt)
+int ref_contract_samples(const float* ray_o, const int* se, const float* s3d, const float* sz, float* out_3d, float* out_z, int nr_rays,
+                         int nr_samples, int uncontract) {
+    if (uncontract)
+        RaySamplerGPU::uncontract_samples_gpu<<<grid_for(nr_rays), 256>>>(nr_rays, acc2(ray_o, nr_rays, 3), acc2(se, nr_rays, 2),
+                                                                          acc2(s3d, nr_samples, 3), acc2(sz, nr_samples, 1),
+                                                                          acc2(out_3d, nr_samples, 3), acc2(out_z, nr_samples, 1));
+    else
+        RaySamplerGPU::contract_samples_gpu<<<grid_for(nr_rays), 256>>>(nr_rays, acc2(ray_o, nr_rays, 3), acc2(se, nr_rays, 2),
+                                                                        acc2(s3d, nr_samples, 3), acc2(sz, nr_samples, 1),
+                                                                        acc2(out_3d, nr_samples, 3), acc2(out_z, nr_samples, 1));
+    return finish();
+}
+
 // OccupancyGrid.cu: get_rays_t_near_t_far
 int ref_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                           const float* extent, const bool* occupancy, const bool* roi, float* t_near, float* t_far, int nr_rays) {

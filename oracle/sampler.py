@@ -7,6 +7,7 @@ occupancy-grid queries under them:
 * compute_samples_fg .................................. kernels/volsurfs/RaySamplerGPU.cuh:141-271 (+ compaction, src/RaySampler.cu:236)
 * compute_samples_fg_in_grid_occupied_regions .......... RaySamplerGPU.cuh:273-488
 * compute_samples_bg .................................. RaySamplerGPU.cuh:39-139
+* contract_samples / uncontract_samples ............... RaySamplerGPU.cuh:528-658 (before update_dt, src/RaySampler.cu:378,425)
 * get_rays_t_near_t_far / check_occupancy ............. kernels/volsurfs/OccupancyGridGPU.cuh:318-441
 * pcg32 ............................................... oracle/importance.py:Pcg32 (kernels/volsurfs/pcg32.h)
 
@@ -275,3 +276,40 @@ def check_occupancy(points, grid: Grid):
             occ[i, 0] = grid.occupied(v)
             val[i, 0] = grid.values[v]
     return occ, val
+
+
+def _length3(x, y, z):
+    """helper_math length() = sqrtf(dot) with the dot product x*x + y*y + z*z as nvcc contracts it in the reference build (read off the SASS of
+    oracle/_ref/libsampler_ref.so: FMUL y*y, FFMA x, FFMA z): fma(z,z, fma(x,x, y*y)).  fp64 product + one rounding per fma: products of
+    fp32 values are exact in fp64"""
+    x, y, z = (np.asarray(v, np.float32).astype(np.float64) for v in (x, y, z))
+    t = (y * y).astype(np.float32).astype(np.float64)
+    t = (x * x + t).astype(np.float32).astype(np.float64)
+    t = (z * z + t).astype(np.float32)
+    return np.sqrt(t, dtype=np.float32)
+
+
+def contract_samples(ray_o, ray_start_end_idx, samples_3d, samples_z, uncontract=False):
+    """contract_samples_gpu / uncontract_samples_gpu (RaySamplerGPU.cuh:528-592, 594-658): points with |2x| > 1 are mapped to
+    (2 - 1/|2x|) x / |2x| (inverse: 1 / (2 - |2x|)) and their depth re-measured from the ray origin; the rest is copied.
+    Returns (samples_3d, samples_z) before the closing update_dt (src/RaySampler.cu:378,425)."""
+    ray_o = np.asarray(ray_o, np.float32)
+    se = np.asarray(ray_start_end_idx, np.int32)
+    p = np.array(samples_3d, np.float32, copy=True)
+    z = np.array(samples_z, np.float32, copy=True).reshape(-1, 1)
+    if p.shape[0] == 0:
+        return p, z
+    ray_of = np.repeat(np.arange(se.shape[0]), np.maximum(se[:, 1] - se[:, 0], 0))
+    idx = np.concatenate([np.arange(a, b) for a, b in se if b > a]) if ray_of.size else np.zeros(0, np.int64)
+    q = p[idx]
+    cam = ray_o[ray_of]
+    two = F(2.0)
+    norm = _length3(q[:, 0] * two, q[:, 1] * two, q[:, 2] * two)
+    m = norm > F(1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        factor = (F(1.0) / (two - norm)) if uncontract else (two - F(1.0) / norm)
+        qn = ((factor[:, None] * q) / norm[:, None]).astype(np.float32)
+    zn = _length3(qn[:, 0] - cam[:, 0], qn[:, 1] - cam[:, 1], qn[:, 2] - cam[:, 2])
+    p[idx[m]] = qn[m]
+    z[idx[m], 0] = zn[m]
+    return p, z

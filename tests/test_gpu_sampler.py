@@ -196,6 +196,83 @@ def test_bg_and_grid_queries_match_reference_kernels(ref):
     assert torch.equal(occ, ro) and torch.equal(val, rv)
 
 
+def _bg_packet(n, nr, t_far, seed):
+    from volsurfs_b200.volsurfs import RaySampler
+
+    sc = make_scene(n, 16, seed=seed)
+    t = _cuda_scene(sc)
+    _reset_rng()
+    return RaySampler.compute_samples_bg(t["o"], t["d"], t["t_exit"], t_far, nr, True)
+
+
+def test_contract_samples_match_restatement_and_reference_kernels(ref):
+    """RaySampler.contract_samples / uncontract_samples (src/RaySampler.cu:336-427) on a background packet whose samples straddle the
+    |2x| = 1 sphere: bit-exact against the restatement AND the reference's kernels, dt as the reference's closing update_dt(true)"""
+    from volsurfs_b200.volsurfs import RaySampler
+
+    n, nr = 3000, 24
+    rsp = _bg_packet(n, nr, 40.0, 31)
+    rsp.update_dt(True)
+    norm2 = (2 * rsp.samples_3d).norm(dim=1)
+    assert int((norm2 > 1).sum()) > n and int((norm2 <= 1).sum()) > 0  # both branches
+    got_c = RaySampler.contract_samples(rsp)
+    got_u = RaySampler.uncontract_samples(got_c)
+    o, se = rsp.ray_o.cpu().numpy(), rsp.ray_start_end_idx.cpu().numpy()
+    src = rsp
+    for unc, got in ((0, got_c), (1, got_u)):
+        w3, wz = osamp.contract_samples(o, se, src.samples_3d.cpu().numpy(), src.samples_z.cpu().numpy(), uncontract=bool(unc))
+        assert np.array_equal(got.samples_3d.cpu().numpy(), w3) and np.array_equal(got.samples_z.cpu().numpy(), wz), unc
+        r3, rz = torch.full_like(src.samples_3d, -7.0), torch.full_like(src.samples_z, -7.0)
+        assert ref.ref_contract_samples(P(src.ray_o), P(src.ray_start_end_idx), P(src.samples_3d), P(src.samples_z), P(r3), P(rz), n, n * nr,
+                                        unc) == 0
+        assert torch.equal(got.samples_3d, r3) and torch.equal(got.samples_z, rz), unc
+        # the rest of the packet is a copy; dt re-derived from the new depths as for a background packet
+        for k in ("ray_start_end_idx", "samples_dirs", "ray_o", "ray_d", "ray_enter", "ray_exit", "ray_max_dt"):
+            assert torch.equal(getattr(got, k), getattr(src, k)), k
+        want_dt = src.copy()
+        want_dt.samples_z = got.samples_z.clone()
+        want_dt.update_dt(True)
+        assert got.has_dt and torch.equal(got.samples_dt, want_dt.samples_dt)
+        assert got.samples_3d.data_ptr() != src.samples_3d.data_ptr()
+        src = got
+    # contraction lands inside the unit ball of the scaled coordinates (radius 1 in x, i.e. |2x'| < 2) and the round trip returns
+    assert float((2 * got_c.samples_3d).norm(dim=1).max()) < 2.0
+    far = (2 * got_c.samples_3d).norm(dim=1) < 1.9  # 1 / (2 - |2x|) amplifies rounding next to the rim
+    assert torch.allclose(got_u.samples_3d[far], rsp.samples_3d[far], rtol=1e-4, atol=1e-6)
+
+
+def test_contract_samples_ragged_and_errors():
+    from volsurfs_b200.volsurfs import RaySampler, RaySamplesPacked
+
+    # ragged packet with empty rays: rays of 0, 1, 33 and 70 samples (more than one warp pass)
+    counts = np.array([0, 1, 33, 0, 70, 5], np.int32)
+    ends = np.cumsum(counts).astype(np.int32)
+    se = np.stack([ends - counts, ends], 1).astype(np.int32)
+    tot = int(ends[-1])
+    rs = np.random.RandomState(5)
+    rsp = RaySamplesPacked(len(counts), tot, 0, 1)
+    rsp.ray_start_end_idx = torch.from_numpy(se).cuda()
+    rsp.ray_o = torch.from_numpy((rs.randn(len(counts), 3) * 0.2).astype(np.float32)).cuda()
+    rsp.samples_3d = torch.from_numpy((rs.randn(tot, 3) * 1.5).astype(np.float32)).cuda()
+    rsp.samples_z = torch.from_numpy(np.sort(rs.rand(tot, 1).astype(np.float32) * 9, axis=0)).cuda()
+    rsp.ray_max_dt = torch.full((len(counts), 1), 0.5, device="cuda")
+    rsp.is_compacted = True
+    got = RaySampler.contract_samples(rsp)
+    w3, wz = osamp.contract_samples(rsp.ray_o.cpu().numpy(), se, rsp.samples_3d.cpu().numpy(), rsp.samples_z.cpu().numpy())
+    assert np.array_equal(got.samples_3d.cpu().numpy(), w3) and np.array_equal(got.samples_z.cpu().numpy(), wz)
+    back = RaySampler.uncontract_samples(got)
+    w3, wz = osamp.contract_samples(rsp.ray_o.cpu().numpy(), se, w3, wz, uncontract=True)
+    assert np.array_equal(back.samples_3d.cpu().numpy(), w3) and np.array_equal(back.samples_z.cpu().numpy(), wz)
+    # error behaviour of the reference's CHECKs (src/RaySampler.cu:342-343, 389-390)
+    rsp.is_compacted = False
+    with pytest.raises(RuntimeError, match="compacted"):
+        RaySampler.contract_samples(rsp)
+    with pytest.raises(RuntimeError, match="compacted"):
+        RaySampler.uncontract_samples(rsp)
+    with pytest.raises(RuntimeError, match="empty"):
+        RaySampler.contract_samples(RaySamplesPacked(0, 0, 0, 1))
+
+
 def test_sampler_feeds_packed_compositing():
     """the sampler's packet goes straight into update_dt and the packed operators (the NeRF path of volsurfs_py/methods/nerf.py:280-334)"""
     from volsurfs_b200.volsurfs import RaySampler, VolumeRendering

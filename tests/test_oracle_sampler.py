@@ -94,3 +94,26 @@ def test_check_occupancy():
     v0 = S.pos_to_lin_idx(pts[0], 16, sc["extent"])
     assert occ[0, 0] == (sc["occ"][v0] and sc["roi"][v0]) and val[0, 0] == sc["vals"][v0]
     assert occ.shape == (4, 1) and val.shape == (4, 1)
+
+
+def test_contract_samples_known_answers_and_round_trip():
+    """RaySamplerGPU.cuh:528-658: points inside |2x| <= 1 are copied; outside they land in the ball of radius 1 (|2x'| = 2 - 1/|2x|)"""
+    o = np.array([[0.0, 0.0, 0.0], [0.1, -0.2, 0.3], [0.0, 0.0, 0.0]], F)
+    se = np.array([[0, 3], [3, 3], [3, 7]], np.int32)  # ragged, with an empty ray
+    p = np.array([[0.25, 0, 0], [1.0, 0, 0], [0, 4.0, 0], [0.5, 0, 0], [0, 0, -2.0], [3.0, 4.0, 0], [0.1, 0.1, 0.1]], F)
+    z = np.arange(7, dtype=F).reshape(-1, 1)
+    c, cz = S.contract_samples(o, se, p, z)
+    # |2x| = 0.5 -> copy; |2x| = 2 -> factor 1.5, x' = 1.5 * 1 / 2 = 0.75; |2x| = 8 -> factor 1.875, y' = 1.875 * 4 / 8
+    assert np.array_equal(c[0], p[0]) and cz[0, 0] == 0.0
+    assert np.array_equal(c[1], np.array([0.75, 0, 0], F)) and cz[1, 0] == F(0.75)
+    assert np.array_equal(c[2], np.array([0, 0.9375, 0], F)) and cz[2, 0] == F(0.9375)
+    assert np.array_equal(c[3], p[3]) and cz[3, 0] == 3.0  # |2x| == 1 exactly: not contracted
+    assert np.array_equal(c[4], np.array([0, 0, -0.875], F))  # |2x| = 4 -> factor 1.75, z' = 1.75 * -2 / 4
+    assert np.array_equal(c[6], p[6]) and cz[6, 0] == 6.0
+    assert (np.linalg.norm(c.astype(np.float64), axis=1) < 1.0).all()
+    u, uz = S.contract_samples(o, se, c, cz, uncontract=True)
+    assert np.allclose(u, p, rtol=2e-6, atol=0) and np.array_equal(u[[0, 3, 6]], p[[0, 3, 6]])
+    # depths are distances from the ray's origin after the map
+    assert np.allclose(uz[[1, 2, 4, 5], 0], np.linalg.norm(u[[1, 2, 4, 5]] - o[[0, 0, 2, 2]], axis=1), rtol=1e-6)
+    e3, ez = S.contract_samples(o, np.zeros((3, 2), np.int32), np.zeros((0, 3), F), np.zeros((0, 1), F))
+    assert e3.shape == (0, 3) and ez.shape == (0, 1)

@@ -74,6 +74,7 @@ SIGNATURES = {
     "vs_sampler_fg_count": (c_int, [_P, _P, _P, _P, c_float, c_int, c_int, ctypes.c_uint64, ctypes.c_uint64, c_int, c_int, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_sampler_fg_write": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_sampler_bg": (c_int, [_P, _P, _P, c_float, c_int, ctypes.c_uint64, ctypes.c_uint64, c_int, _P, _P, _P, _P, _P, _I64, _P]),
+    "vs_sampler_contract": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _I64, _P]),
     "vs_occgrid_rays_t_near_t_far": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_occgrid_check_occupancy": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_mlp_backward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, c_int, _P]),

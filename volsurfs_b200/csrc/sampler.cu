@@ -316,6 +316,42 @@ __global__ void __launch_bounds__(128) sampler_bg_kernel(const float* __restrict
     reinterpret_cast<int2*>(se)[ray] = make_int2((int)(ray * nr), (int)(ray * nr + nr));
 }
 
+// ---- scene contraction of background samples (RaySamplerGPU.cuh:528-658) -----------------------------------------------------------
+// x -> (2 - 1/|2x|) x / |2x| for |2x| > 1 (and its inverse), depth re-measured from the camera.  Pointwise per sample; a warp walks a
+// ray's samples with unit stride.  length() is sqrt of the dot product as nvcc contracts it in the reference (read off its SASS): fma(z,z, fma(x,x, y*y)).
+__device__ __forceinline__ float length3(float x, float y, float z) { return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)))); }
+
+template <bool UNCONTRACT>
+__global__ void __launch_bounds__(256) sampler_contract_kernel(const float* __restrict__ ray_o, const int32_t* __restrict__ se,
+                                                               const float* __restrict__ s_3d, const float* __restrict__ s_z,
+                                                               float* __restrict__ out_3d, float* __restrict__ out_z, int64_t n_rays) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = warp0; ray < n_rays; ray += n_warps) {
+        int start = 0;
+        const int n = load_segment(se, ray, start);
+        if (n <= 0) continue;
+        const float cx = __ldg(ray_o + 3 * ray), cy = __ldg(ray_o + 3 * ray + 1), cz = __ldg(ray_o + 3 * ray + 2);
+        for (int i = lane; i < n; i += 32) {
+            const int64_t s = (int64_t)start + i;
+            float px = __ldcs(s_3d + 3 * s), py = __ldcs(s_3d + 3 * s + 1), pz = __ldcs(s_3d + 3 * s + 2);
+            float zz = __ldcs(s_z + s);
+            const float norm = length3(__fmul_rn(px, 2.f), __fmul_rn(py, 2.f), __fmul_rn(pz, 2.f));
+            if (norm > 1.0f) {
+                const float factor = UNCONTRACT ? __fdiv_rn(1.0f, __fsub_rn(2.0f, norm)) : __fsub_rn(2.0f, __fdiv_rn(1.0f, norm));
+                px = __fdiv_rn(__fmul_rn(factor, px), norm);
+                py = __fdiv_rn(__fmul_rn(factor, py), norm);
+                pz = __fdiv_rn(__fmul_rn(factor, pz), norm);
+                zz = length3(__fsub_rn(px, cx), __fsub_rn(py, cy), __fsub_rn(pz, cz));
+            }
+            __stcs(out_3d + 3 * s, px);
+            __stcs(out_3d + 3 * s + 1, py);
+            __stcs(out_3d + 3 * s + 2, pz);
+            __stcs(out_z + s, zz);
+        }
+    }
+}
+
 // ---- occupancy-grid queries ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) occgrid_t_near_t_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                    const float* __restrict__ t_entry, const float* __restrict__ t_exit_p,
@@ -426,6 +462,24 @@ int vs_sampler_bg(const float* rays_o, const float* rays_d, const float* t_start
     sampler_bg_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_start, t_far, nr_samples_per_ray,
                                                                                        Pcg{rng_state, rng_inc}, jitter, ray_max_dt, samples_3d,
                                                                                        samples_dirs, samples_z, se, n_rays);
+    return launched(1);
+}
+
+// RaySampler::contract_samples / uncontract_samples without the closing update_dt: samples_3d, samples_z of a compacted packet ->
+// out_3d, out_z (same shapes; may alias the inputs)
+int vs_sampler_contract(const float* ray_o, const int32_t* se, const float* samples_3d, const float* samples_z, float* out_3d, float* out_z,
+                        int uncontract, int64_t n_rays, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0);
+    if (n_rays == 0) return VS_OK;
+    VS_CHECK_ARG(ray_o && se && samples_3d && samples_z && out_3d && out_z);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)std::min<int64_t>(div_up(n_rays, 8), (int64_t)sms * 8);
+    if (uncontract)
+        sampler_contract_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ray_o, se, samples_3d, samples_z, out_3d, out_z, n_rays);
+    else
+        sampler_contract_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(ray_o, se, samples_3d, samples_z, out_3d, out_z, n_rays);
     return launched(1);
 }
 

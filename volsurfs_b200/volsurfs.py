@@ -865,3 +865,28 @@ class RaySampler:
         idx = torch.arange(n, dtype=torch.int32, device=p.device)
         out.ray_start_end_idx = torch.stack([idx, idx + 1], dim=1).contiguous()
         return out
+
+    @staticmethod
+    def _contract(rsp, uncontract: bool, what: str):
+        if rsp.is_empty():
+            raise RuntimeError(f"RaySamplesPacked must not be empty before calling {what}")
+        if not rsp.is_compacted:
+            raise RuntimeError(f"RaySamplesPacked should be compacted at the beginning of {what}")
+        out = rsp.copy()
+        n = rsp.get_nr_rays()
+        check(_lib.lib().vs_sampler_contract(ptr(_f32c(rsp.ray_o, "ray_o", 3)), ptr(rsp.ray_start_end_idx.contiguous()),
+                                             ptr(_f32c(rsp.samples_3d, "samples_3d", 3)), ptr(_f32c(rsp.samples_z, "samples_z", 1)),
+                                             ptr(out.samples_3d), ptr(out.samples_z), int(uncontract), n, _stream()), "vs_sampler_contract")
+        out.update_dt(True)  # src/RaySampler.cu:378,425
+        return out
+
+    @staticmethod
+    def contract_samples(uncontracted_ray_samples_packed):
+        """background scene contraction (src/RaySampler.cu:336-381): positions beyond |2x| = 1 are pulled into the unit ball, depths
+        re-measured from the ray origin, dt updated as for a background packet"""
+        return RaySampler._contract(uncontracted_ray_samples_packed, False, "contract_samples")
+
+    @staticmethod
+    def uncontract_samples(contracted_ray_samples_packed):
+        """inverse of contract_samples (src/RaySampler.cu:383-427)"""
+        return RaySampler._contract(contracted_ray_samples_packed, True, "uncontract_samples")
