@@ -294,26 +294,29 @@ __global__ void __launch_bounds__(kThreads) update_dt_kernel(const int32_t* __re
 // discrete, order-sensitive decisions (first sample whose running sum crosses a threshold, snapping of the last cdf entry), so
 // they keep the reference's one-thread-per-ray left-to-right order instead of a re-associated scan.
 // ---------------------------------------------------------------------------------------------
-// VolumeRenderingGPU.cuh:185-243.  The reference mixes float variables with double literals; C's promotion rules are kept.
+// VolumeRenderingGPU.cuh:185-243.  The reference mixes float variables with double literals; C's promotion rules are kept.  Every sample's
+// alpha depends on its own dt / beta and on sdf[s], sdf[s+1] only (no running state), so a W-lane group walks the ray with unit stride
+// and the per-sample arithmetic — hence the result — is the one of the reference's thread-per-ray loop, bit for bit.
+template <int W>
 __global__ void __launch_bounds__(kThreads) sdf2alpha_kernel(const int32_t* __restrict__ se, const float* __restrict__ dt,
                                                              const float* __restrict__ sdf, const float* __restrict__ beta,
                                                              float* __restrict__ alpha, int64_t n_rays) {
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= n_rays) return;
-    int start;
-    const int n = load_segment(se, ray, start);
-    for (int i = 0; i + 1 < n; ++i) {
-        const int64_t s = (int64_t)start + i;
-        const float d = dt[s], prev = sdf[s], next = sdf[s + 1];
-        const float mid = (float)((double)(prev + next) * 0.5);
-        float c = (float)((double)(next - prev) / ((double)d + 1e-6));
-        c = fminf(fmaxf(c, -1e3f), 0.0f);
-        const double half_step = (double)(c * d) * 0.5;
-        const float prev_e = (float)((double)mid - half_step), next_e = (float)((double)mid + half_step);
-        const float b = beta[s];
-        const float pc = (float)(1.0 / (1.0 + (double)expf(-(prev_e * b))));
-        const float nc = (float)(1.0 / (1.0 + (double)expf(-(next_e * b))));
-        alpha[s] = (float)(((double)(pc - nc) + 1e-6) / ((double)pc + 1e-6));
+    VS_GROUP_SETUP(W)
+    for (int base = 0; base < n_max; base += W) {
+        const int i = base + gl;
+        if (i + 1 < n) {
+            const int64_t s = (int64_t)start + i;
+            const float d = ld_stream(dt + s), prev = ld_stream(sdf + s), next = __ldg(sdf + s + 1);
+            const float mid = (float)((double)(prev + next) * 0.5);
+            float c = (float)((double)(next - prev) / ((double)d + 1e-6));
+            c = fminf(fmaxf(c, -1e3f), 0.0f);
+            const double half_step = (double)(c * d) * 0.5;
+            const float prev_e = (float)((double)mid - half_step), next_e = (float)((double)mid + half_step);
+            const float b = ld_stream(beta + s);
+            const float pc = (float)(1.0 / (1.0 + (double)expf(-(prev_e * b))));
+            const float nc = (float)(1.0 / (1.0 + (double)expf(-(next_e * b))));
+            st_stream(alpha + s, (float)(((double)(pc - nc) + 1e-6) / ((double)pc + 1e-6)));
+        }
     }
 }
 
@@ -504,8 +507,9 @@ int vs_sdf2alpha(const int32_t* se, const float* samples_dt, const float* sample
     VS_CHECK_ARG(n_rays >= 0 && n_samples >= 0);
     if (n_rays == 0 || n_samples == 0) return VS_OK;
     VS_CHECK_ARG(se && samples_dt && samples_sdf && logistic_beta && alpha);
-    sdf2alpha_kernel<<<(unsigned)div_up(n_rays, kThreads), kThreads, 0, (cudaStream_t)stream>>>(se, samples_dt, samples_sdf, logistic_beta,
-                                                                                              alpha, n_rays);
+    cudaStream_t st = (cudaStream_t)stream;
+    int Wsel = pick_group_width(n_rays, n_samples);
+    VS_DISPATCH_W(Wsel, sdf2alpha_kernel<W><<<grid_for(n_rays, W), kThreads, 0, st>>>(se, samples_dt, samples_sdf, logistic_beta, alpha, n_rays));
     return launched(1);
 }
 

@@ -322,32 +322,57 @@ __global__ void __launch_bounds__(128) sampler_bg_kernel(const float* __restrict
 __device__ __forceinline__ float length3(float x, float y, float z) { return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)))); }
 
 template <bool UNCONTRACT>
-__global__ void __launch_bounds__(256) sampler_contract_kernel(const float* __restrict__ ray_o, const int32_t* __restrict__ se,
+__global__ void __launch_bounds__(256, 6) sampler_contract_kernel(const float* __restrict__ ray_o, const int32_t* __restrict__ se,
                                                                const float* __restrict__ s_3d, const float* __restrict__ s_z,
                                                                float* __restrict__ out_3d, float* __restrict__ out_z, int64_t n_rays) {
+    __shared__ float tiles[8][96];
     const int lane = threadIdx.x & 31;
+    float* tile = tiles[threadIdx.x >> 5];
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // the next ray's segment and origin are fetched while the current ray's samples are in flight (one DRAM round trip per ray, not two)
+    int start_nx = 0, n_nx = 0;
+    float cx_nx = 0.f, cy_nx = 0.f, cz_nx = 0.f;
+    if (warp0 < n_rays) {
+        n_nx = load_segment(se, warp0, start_nx);
+        cx_nx = __ldg(ray_o + 3 * warp0), cy_nx = __ldg(ray_o + 3 * warp0 + 1), cz_nx = __ldg(ray_o + 3 * warp0 + 2);
+    }
     for (int64_t ray = warp0; ray < n_rays; ray += n_warps) {
-        int start = 0;
-        const int n = load_segment(se, ray, start);
-        if (n <= 0) continue;
-        const float cx = __ldg(ray_o + 3 * ray), cy = __ldg(ray_o + 3 * ray + 1), cz = __ldg(ray_o + 3 * ray + 2);
-        for (int i = lane; i < n; i += 32) {
-            const int64_t s = (int64_t)start + i;
-            float px = __ldcs(s_3d + 3 * s), py = __ldcs(s_3d + 3 * s + 1), pz = __ldcs(s_3d + 3 * s + 2);
-            float zz = __ldcs(s_z + s);
+        const int start = start_nx, n = n_nx;
+        const float cx = cx_nx, cy = cy_nx, cz = cz_nx;
+        const int64_t nx = ray + n_warps;
+        if (nx < n_rays) {
+            n_nx = load_segment(se, nx, start_nx);
+            cx_nx = __ldg(ray_o + 3 * nx), cy_nx = __ldg(ray_o + 3 * nx + 1), cz_nx = __ldg(ray_o + 3 * nx + 2);
+        }
+        for (int base = 0; base < n; base += 32) {
+            // 32 samples = 96 consecutive floats of the [S,3] array: moved with unit stride, transposed through shared memory (reads at
+            // stride 3 are conflict-free)
+            const int cnt = min(32, n - base), i = base + lane;
+            const int64_t s0 = (int64_t)start + base, s = s0 + lane;
+            const float* src = s_3d + 3 * s0;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (lane + 32 * k < 3 * cnt) tile[lane + 32 * k] = __ldcs(src + lane + 32 * k);
+            float zz = i < n ? __ldcs(s_z + s) : 0.f;
+            __syncwarp();
+            float px = tile[3 * lane], py = tile[3 * lane + 1], pz = tile[3 * lane + 2];
             const float norm = length3(__fmul_rn(px, 2.f), __fmul_rn(py, 2.f), __fmul_rn(pz, 2.f));
-            if (norm > 1.0f) {
+            if (i < n && norm > 1.0f) {
                 const float factor = UNCONTRACT ? __fdiv_rn(1.0f, __fsub_rn(2.0f, norm)) : __fsub_rn(2.0f, __fdiv_rn(1.0f, norm));
                 px = __fdiv_rn(__fmul_rn(factor, px), norm);
                 py = __fdiv_rn(__fmul_rn(factor, py), norm);
                 pz = __fdiv_rn(__fmul_rn(factor, pz), norm);
                 zz = length3(__fsub_rn(px, cx), __fsub_rn(py, cy), __fsub_rn(pz, cz));
             }
-            __stcs(out_3d + 3 * s, px);
-            __stcs(out_3d + 3 * s + 1, py);
-            __stcs(out_3d + 3 * s + 2, pz);
-            __stcs(out_z + s, zz);
+            __syncwarp();
+            tile[3 * lane] = px, tile[3 * lane + 1] = py, tile[3 * lane + 2] = pz;
+            __syncwarp();
+            float* dst = out_3d + 3 * s0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (lane + 32 * k < 3 * cnt) __stcs(dst + lane + 32 * k, tile[lane + 32 * k]);
+            if (i < n) __stcs(out_z + s, zz);
         }
     }
 }
@@ -475,7 +500,15 @@ int vs_sampler_contract(const float* ray_o, const int32_t* se, const float* samp
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)std::min<int64_t>(div_up(n_rays, 8), (int64_t)sms * 8);
+    // persistent grid: exactly the blocks that are resident at once (a grid sized past residency runs a second, partly empty wave)
+    static int resident[2] = {0, 0};
+    if (!resident[uncontract != 0]) {
+        int b = 0;
+        cudaError_t e = uncontract ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sampler_contract_kernel<true>, 256, 0)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sampler_contract_kernel<false>, 256, 0);
+        resident[uncontract != 0] = (e == cudaSuccess && b > 0) ? b : 4;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(div_up(n_rays, 8), (int64_t)sms * resident[uncontract != 0]);
     if (uncontract)
         sampler_contract_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ray_o, se, samples_3d, samples_z, out_3d, out_z, n_rays);
     else
