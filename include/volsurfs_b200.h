@@ -322,6 +322,16 @@ int vs_sampler_bg(const float* rays_o, const float* rays_d, const float* t_start
  * update_dt: scene contraction x -> (2 - 1/|2x|) x/|2x| for |2x| > 1 (uncontract: its inverse), depth re-measured from ray_o */
 int vs_sampler_contract(const float* ray_o, const int32_t* se, const float* samples_3d, const float* samples_z, float* out_3d, float* out_z,
                         int uncontract, int64_t n_rays, void* stream);
+/* OccupancyGrid::get_grid_lower_left_voxels_vertices (centre = 0, src/OccupancyGrid.cu:206-234; kernel OccupancyGridGPU.cuh:31-60) and
+ * get_grid_samples / get_random_grid_samples / get_random_grid_samples_in_roi (centre = 1, :236-347; kernel :62-120): world position of
+ * the voxels point_indices [n] (Morton order) -> out [n,3]; jitter draws pcg32 floats as the reference (advance(3 * i), 3 draws) */
+int vs_occgrid_points(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, int centre, uint64_t rng_state, uint64_t rng_inc,
+                      int jitter, float* out, int64_t n_points, void* stream);
+/* OccupancyGrid::update_grid_values (src/OccupancyGrid.cu:446-474; kernel OccupancyGridGPU.cuh:122-147) */
+int vs_occgrid_update_values(const int32_t* point_indices, const float* values, float decay, float* grid_values, int64_t n_points, void* stream);
+/* OccupancyGrid::update_grid_occupancy_with_density_values (src/OccupancyGrid.cu:476-503; kernel OccupancyGridGPU.cuh:149-218) */
+int vs_occgrid_update_occupancy_density(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, float occupancy_thresh,
+                                        int check_neighbours, const float* grid_values, uint8_t* occupancy, int64_t n_points, void* stream);
 int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* t_near, float* t_far, int64_t n_rays,
                                  void* stream);

@@ -123,6 +123,37 @@ int ref_contract_samples(const float* ray_o, const int* se, const float* s3d, co
     return finish();
 }
 
+// OccupancyGrid.cu:206-347: get_grid_lower_left_voxels_vertices (centre = 0) / get_grid_samples, get_random_grid_samples[_in_roi] (centre = 1)
+int ref_grid_points(const int* point_indices, int nr_voxels_per_dim, const float* extent, int centre, uint64_t rng_state, uint64_t rng_inc,
+                    int jitter, float* out, int nr_points) {
+    const Eigen::Vector3f e(extent[0], extent[1], extent[2]);
+    if (centre)
+        OccupancyGridGPU::get_grid_samples_gpu<<<grid_for(nr_points), 256>>>(nr_points, nr_voxels_per_dim, e, acc1(point_indices, nr_points),
+                                                                            make_rng(rng_state, rng_inc), jitter != 0, acc2(out, nr_points, 3));
+    else
+        OccupancyGridGPU::get_grid_lower_left_voxels_vertices_gpu<<<grid_for(nr_points), 256>>>(nr_points, nr_voxels_per_dim, e,
+                                                                                               acc1(point_indices, nr_points), acc2(out, nr_points, 3));
+    return finish();
+}
+
+// OccupancyGrid.cu:446-474: update_grid_values
+int ref_update_grid_values(const int* point_indices, const float* values, float decay, int nr_voxels_per_dim, float* grid_values, int nr_points) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::update_grid_values_gpu<<<grid_for(nr_points), 256>>>(nr_points, acc2(values, nr_points, 1), nr_voxels_per_dim,
+                                                                          acc1(point_indices, nr_points), decay, acc1(grid_values, nv));
+    return finish();
+}
+
+// OccupancyGrid.cu:476-503: update_grid_occupancy_with_density_values
+int ref_update_grid_occupancy_density(const int* point_indices, int nr_voxels_per_dim, const float* extent, float occupancy_thresh,
+                                      int check_neighbours, const float* grid_values, bool* grid_occupancy, int nr_points) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::update_grid_occupancy_with_density_values_gpu<<<grid_for(nr_points), 256>>>(
+        nr_points, nr_voxels_per_dim, Eigen::Vector3f(extent[0], extent[1], extent[2]), acc1(point_indices, nr_points), occupancy_thresh,
+        check_neighbours != 0, acc1(grid_values, nv), acc1(grid_occupancy, nv));
+    return finish();
+}
+
 // OccupancyGrid.cu: get_rays_t_near_t_far
 int ref_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                           const float* extent, const bool* occupancy, const bool* roi, float* t_near, float* t_far, int nr_rays) {

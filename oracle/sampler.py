@@ -313,3 +313,77 @@ def contract_samples(ray_o, ray_start_end_idx, samples_3d, samples_z, uncontract
     p[idx[m]] = qn[m]
     z[idx[m], 0] = zn[m]
     return p, z
+
+
+# ---- occupancy-grid maintenance (OccupancyGridGPU.cuh:31-218, src/OccupancyGrid.cu:206-347,446-503) ------------------------------------
+def compact_bits(x):
+    """morton3D_invert (occ_grid_helpers.h:45-53), vectorised"""
+    x = np.asarray(x, np.uint32) & np.uint32(0x49249249)
+    x = (x | (x >> np.uint32(2))) & np.uint32(0xC30C30C3)
+    x = (x | (x >> np.uint32(4))) & np.uint32(0x0F00F00F)
+    x = (x | (x >> np.uint32(8))) & np.uint32(0xFF0000FF)
+    x = (x | (x >> np.uint32(16))) & np.uint32(0x0000FFFF)
+    return x
+
+
+def _voxel_axis(c, n, extent, centre_grid, centre_of_voxel):
+    """one axis of lin_idx_to_3D (occ_grid_helpers.h:74-113)"""
+    x = (c.astype(np.float32) / F(n)).astype(np.float32)
+    if centre_grid:
+        x = (x - F(0.5)).astype(np.float32)
+    if centre_of_voxel:
+        x = (x + F(F(1.0 / float(n)) / F(2))).astype(np.float32)
+    return (x * F(extent)).astype(np.float32)
+
+
+def grid_points(point_indices, n, extent, centre=True, jitter=False, rng: Pcg32 | None = None):
+    """get_grid_lower_left_voxels_vertices_gpu (centre=False) / get_grid_samples_gpu (centre=True): voxel indices (Morton) -> [P,3].
+    Jitter: thread i advances a copy of the generator by 3 i and draws x, y, z; mov = fma(voxel_size, rand, -half_voxel_size)."""
+    v = np.asarray(point_indices, np.int32).astype(np.uint32)
+    out = np.stack([_voxel_axis(compact_bits(v >> np.uint32(a)), n, extent[a], True, centre) for a in range(3)], axis=1)
+    if centre and jitter:
+        rng = rng if rng is not None else Pcg32()
+        size = [F(F(extent[a]) / F(n)) for a in range(3)]
+        for i in range(v.shape[0]):
+            g = rng.copy()
+            g.advance(3 * i)
+            for a in range(3):
+                out[i, a] = F(out[i, a] + _mad(size[a], g.next_float(), F(-(size[a] / F(2)))))
+    return out
+
+
+def update_grid_values(point_indices, values, decay, grid_values):
+    """update_grid_values_gpu (OccupancyGridGPU.cuh:122-147) for UNIQUE indices (duplicates race in the reference); returns the new grid"""
+    g = np.array(grid_values, np.float32, copy=True)
+    idx = np.asarray(point_indices, np.int64)
+    g[idx] = np.maximum(np.asarray(values, np.float32).reshape(-1), (g[idx] * F(decay)).astype(np.float32))
+    return g
+
+
+def update_grid_occupancy_density(point_indices, n, extent, thresh, check_neighbours, grid_values, occupancy):
+    """update_grid_occupancy_with_density_values_gpu (OccupancyGridGPU.cuh:149-218); the neighbourhood is addressed through
+    lin_idx_to_3D(.., centre_grid=false, ..) * n, i.e. integer voxel coordinates times the extent, as the reference does"""
+    occ = np.array(occupancy, bool, copy=True)
+    g = np.asarray(grid_values, np.float32)
+    thresh = F(thresh)
+    for v in np.asarray(point_indices, np.int64):
+        if not check_neighbours:
+            occ[v] = not (g[v] <= thresh)
+            continue
+        p = [F(_voxel_axis(compact_bits(np.uint32(v) >> np.uint32(a)), n, extent[a], False, False) * F(n)) for a in range(3)]
+        empty = True
+        for i in (-1, 0, 1):
+            qx = F(p[0] + F(i))
+            if qx < 0 or qx > n - 1:
+                continue
+            for j in (-1, 0, 1):
+                qy = F(p[1] + F(j))
+                if qy < 0 or qy > n - 1:
+                    continue
+                for k in (-1, 0, 1):
+                    qz = F(p[2] + F(k))
+                    if qz < 0 or qz > n - 1:
+                        continue
+                    empty = empty and bool(g[morton3d(int(qx), int(qy), int(qz))] <= thresh)
+        occ[v] = not empty
+    return occ

@@ -273,6 +273,86 @@ def test_contract_samples_ragged_and_errors():
         RaySampler.contract_samples(RaySamplesPacked(0, 0, 0, 1))
 
 
+def test_grid_maintenance_matches_restatement_and_reference_kernels(ref):
+    """voxel sample points, update_grid_values, update_grid_occupancy_with_density_values (src/OccupancyGrid.cu:206-347,446-503):
+    bit-exact against the reference's kernels at 64^3 voxels and against the restatement on a subset"""
+    from volsurfs_b200.volsurfs import OccupancyGrid
+
+    n, extent = 64, [1.0, 1.2, 0.9]
+    ext = (ctypes.c_float * 3)(*extent)
+    og = OccupancyGrid(n, extent)
+    OccupancyGrid._rng_state, OccupancyGrid._rng_inc = PCG_DEFAULT_STATE, PCG_DEFAULT_INC
+    V = n ** 3
+    ll, idx = og.get_grid_lower_left_voxels_vertices()
+    assert idx.dtype == torch.int32 and torch.equal(idx, torch.arange(V, dtype=torch.int32, device="cuda")) and ll.shape == (V, 3)
+    r = torch.empty_like(ll)
+    assert ref.ref_grid_points(P(idx), n, ext, 0, ctypes.c_uint64(0), ctypes.c_uint64(1), 0, P(r), V) == 0
+    assert torch.equal(ll, r)
+    for jitter in (False, True, True):  # twice jittered: the generator advances between calls like the reference's static m_rng
+        state = OccupancyGrid._rng_state
+        pts, idx2 = og.get_grid_samples(jitter)
+        assert ref.ref_grid_points(P(idx2), n, ext, 1, ctypes.c_uint64(state), ctypes.c_uint64(PCG_DEFAULT_INC), int(jitter), P(r), V) == 0
+        assert torch.equal(pts, r), jitter
+        assert (OccupancyGrid._rng_state != state) == jitter
+        sub = slice(0, 3000)
+        rng = Pcg32()
+        rng.state = state
+        want = osamp.grid_points(idx2[sub].cpu().numpy(), n, extent, centre=True, jitter=jitter, rng=rng)
+        assert np.array_equal(pts[sub].cpu().numpy(), want), jitter
+        occ, _ = og.check_occupancy(pts)  # every sample lies in its own voxel: all inside the (full) grid
+        assert bool(occ.all())
+    state = OccupancyGrid._rng_state
+    pts, ridx = og.get_random_grid_samples(5000, True)
+    assert ridx.shape == (5000,) and ridx.dtype == torch.int32 and int(ridx.min()) >= 0 and int(ridx.max()) < V
+    r5 = torch.empty_like(pts)
+    assert ref.ref_grid_points(P(ridx), n, ext, 1, ctypes.c_uint64(state), ctypes.c_uint64(PCG_DEFAULT_INC), 1, P(r5), 5000) == 0
+    assert torch.equal(pts, r5)
+    og.init_sphere_roi(0.5, 0.05)
+    roi = og.get_grid_roi()
+    assert roi.dtype == torch.bool and 0 < og.get_nr_voxels_in_roi() < V
+    corners_far = (ll.norm(dim=1) >= 0.45)
+    assert not bool((roi & corners_far).any())  # a voxel whose lower-left corner is outside the sphere is not in the roi
+    pts, ridx = og.get_random_grid_samples_in_roi(4000, False)
+    assert bool(roi[ridx.long()].all()) and pts.shape == (4000, 3)
+
+    # update_grid_values on unique indices (duplicates race in the reference), then the two occupancy rules
+    g = torch.Generator(device="cuda").manual_seed(4)
+    vals0 = torch.rand(V, device="cuda", generator=g)
+    og.set_grid_values(vals0.clone())
+    pick = torch.randperm(V, device="cuda", generator=g)[:100000].to(torch.int32)
+    new = torch.rand(100000, 1, device="cuda", generator=g)
+    og.update_grid_values(pick, new, 0.95)
+    rv = vals0.clone()
+    assert ref.ref_update_grid_values(P(pick), P(new), ctypes.c_float(0.95), n, P(rv), 100000) == 0
+    assert torch.equal(og.get_grid_values(), rv)
+    assert np.array_equal(osamp.update_grid_values(pick.cpu().numpy(), new.cpu().numpy(), 0.95, vals0.cpu().numpy()), rv.cpu().numpy())
+    assert og.get_grid_max_value_in_roi() <= og.get_grid_max_value() and og.get_grid_min_value_in_roi() >= og.get_grid_min_value()
+    sparse = torch.where(torch.rand(V, device="cuda", generator=g) < 0.02, vals0, torch.zeros_like(vals0))  # isolated dense voxels
+    og.set_grid_values(sparse)
+    for unit_extent in (True, False):
+        e = [1.0, 1.0, 1.0] if unit_extent else extent
+        og2 = OccupancyGrid(n, e)
+        og2.set_grid_values(sparse)
+        ec = (ctypes.c_float * 3)(*e)
+        for neigh in (False, True):
+            og2.set_grid_occupancy(torch.rand(V, device="cuda", generator=g) < 0.5)
+            ro = og2.get_grid_occupancy().clone()
+            og2.update_grid_occupancy_with_density_values(pick, 0.3, neigh)
+            assert ref.ref_update_grid_occupancy_density(P(pick), n, ec, ctypes.c_float(0.3), int(neigh), P(sparse), P(ro), 100000) == 0
+            assert torch.equal(og2.get_grid_occupancy(), ro), (unit_extent, neigh)
+            sub = pick[:1500]
+            before = og2.get_grid_occupancy().clone()
+            want = osamp.update_grid_occupancy_density(sub.cpu().numpy(), n, e, 0.3, neigh, sparse.cpu().numpy(), before.cpu().numpy())
+            og2.update_grid_occupancy_with_density_values(sub, 0.3, neigh)
+            assert np.array_equal(og2.get_grid_occupancy().cpu().numpy(), want), (unit_extent, neigh)
+    with pytest.raises(RuntimeError):
+        og.update_grid_values(pick, new.reshape(-1), 0.95)
+    with pytest.raises(RuntimeError):
+        og.update_grid_values(pick, new, 1.5)
+    with pytest.raises(RuntimeError):
+        og.update_grid_occupancy_with_density_values(pick.reshape(-1, 1), 0.3, False)
+
+
 def test_sampler_feeds_packed_compositing():
     """the sampler's packet goes straight into update_dt and the packed operators (the NeRF path of volsurfs_py/methods/nerf.py:280-334)"""
     from volsurfs_b200.volsurfs import RaySampler, VolumeRendering

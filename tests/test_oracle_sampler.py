@@ -117,3 +117,29 @@ def test_contract_samples_known_answers_and_round_trip():
     assert np.allclose(uz[[1, 2, 4, 5], 0], np.linalg.norm(u[[1, 2, 4, 5]] - o[[0, 0, 2, 2]], axis=1), rtol=1e-6)
     e3, ez = S.contract_samples(o, np.zeros((3, 2), np.int32), np.zeros((0, 3), F), np.zeros((0, 1), F))
     assert e3.shape == (0, 3) and ez.shape == (0, 1)
+
+
+def test_grid_points_and_density_maintenance_known_answers():
+    """OccupancyGridGPU.cuh:31-218: voxel 0 sits at the lower-left corner of a grid centred at the origin; centres are half a voxel in;
+    the centre of voxel i maps back to i; a single dense voxel occupies its 3x3x3 neighbourhood"""
+    n, ext = 4, [1.0, 1.2, 0.9]
+    idx = np.arange(n ** 3, dtype=np.int32)
+    ll = S.grid_points(idx, n, ext, centre=False)
+    c = S.grid_points(idx, n, ext, centre=True)
+    assert np.array_equal(ll[0], np.array([-0.5, -0.6, -0.45], F)) and np.array_equal(ll[1], np.array([-0.25, -0.6, -0.45], F))
+    assert np.array_equal(ll[2], np.array([-0.5, F(-0.25) * F(1.2), -0.45], F))  # Morton order: bit 1 is y
+    assert np.array_equal(c[0], np.array([-0.375, F(-0.375) * F(1.2), F(-0.375) * F(0.9)], F))
+    assert all(S.pos_to_lin_idx(c[i], n, ext) == i for i in range(n ** 3))
+    j = S.grid_points(idx, n, ext, centre=True, jitter=True, rng=Pcg32())
+    assert (np.abs(j - c) <= np.array(ext, F) / n / 2 + 1e-7).all() and np.abs(j - c).max() > 0.05
+    assert all(S.pos_to_lin_idx(j[i], n, ext) == i for i in range(n ** 3))  # jitter stays inside the voxel
+    g = np.zeros(n ** 3, F)
+    g[S.morton3d(1, 1, 1)] = 1.0
+    g2 = S.update_grid_values(idx[:8], np.full((8, 1), 0.25, F), 0.5, g)
+    assert g2[S.morton3d(1, 1, 1)] == 0.5 and g2[0] == 0.25 and g2[8] == 0.0  # max(new, decay * old); untouched beyond the indices
+    occ = S.update_grid_occupancy_density(idx, n, [1, 1, 1], 0.5, True, g, np.zeros(n ** 3, bool))
+    assert occ.sum() == 27 and occ[S.morton3d(2, 2, 2)] and not occ[S.morton3d(3, 1, 1)]
+    occ = S.update_grid_occupancy_density(idx, n, [1, 1, 1], 0.5, False, g, np.ones(n ** 3, bool))
+    assert occ.sum() == 1 and occ[S.morton3d(1, 1, 1)]
+    occ = S.update_grid_occupancy_density(idx[:4], n, [1, 1, 1], 0.5, False, g, np.ones(n ** 3, bool))
+    assert occ.sum() == n ** 3 - 4  # only the listed voxels are rewritten

@@ -377,6 +377,90 @@ __global__ void __launch_bounds__(256, 6) sampler_contract_kernel(const float* _
     }
 }
 
+// ---- occupancy-grid maintenance (OccupancyGridGPU.cuh:31-196) ------------------------------------------------------------------------
+// Morton inverse of one axis (occ_grid_helpers.h:45-53)
+__device__ __forceinline__ uint32_t compact_bits(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+// lin_idx_to_3D (occ_grid_helpers.h:74-113) for one axis: index / n [- 0.5] [+ half a voxel], times the extent
+__device__ __forceinline__ float voxel_axis(uint32_t c, int n, float extent, bool centre_grid, bool centre_of_voxel) {
+    float x = __fdiv_rn((float)c, (float)n);
+    if (centre_grid) x = __fsub_rn(x, 0.5f);
+    if (centre_of_voxel) x = __fadd_rn(x, (float)(1.0 / (double)n) * 0.5f);
+    return __fmul_rn(x, extent);
+}
+
+// get_grid_lower_left_voxels_vertices_gpu (centre = 0) / get_grid_samples_gpu (centre = 1, optional jitter inside the voxel)
+__global__ void __launch_bounds__(256) occgrid_points_kernel(const int32_t* __restrict__ point_indices, int n, float ex, float ey, float ez,
+                                                             int centre, Pcg rng, int jitter, float* __restrict__ out, int64_t n_points) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_points) return;
+    const uint32_t v = (uint32_t)__ldg(point_indices + idx);
+    float px = voxel_axis(compact_bits(v), n, ex, true, centre != 0);
+    float py = voxel_axis(compact_bits(v >> 1), n, ey, true, centre != 0);
+    float pz = voxel_axis(compact_bits(v >> 2), n, ez, true, centre != 0);
+    if (centre && jitter) {
+        const float nf = (float)n;
+        const float sx = __fdiv_rn(ex, nf), sy = __fdiv_rn(ey, nf), sz = __fdiv_rn(ez, nf);
+        rng.advance((uint64_t)(int64_t)((int)idx * 3));
+        px = __fadd_rn(px, __fmaf_rn(sx, rng.next_float(), -(sx * 0.5f)));  // voxel_size * rand - half_voxel_size, contracted by nvcc
+        py = __fadd_rn(py, __fmaf_rn(sy, rng.next_float(), -(sy * 0.5f)));
+        pz = __fadd_rn(pz, __fmaf_rn(sz, rng.next_float(), -(sz * 0.5f)));
+    }
+    out[3 * idx] = px, out[3 * idx + 1] = py, out[3 * idx + 2] = pz;
+}
+
+// update_grid_values_gpu: grid[v] = max(new, grid[v] * decay) (duplicate indices race exactly as in the reference)
+__global__ void __launch_bounds__(256) occgrid_update_values_kernel(const int32_t* __restrict__ point_indices, const float* __restrict__ values,
+                                                                    float decay, float* __restrict__ grid_values, int64_t n_points) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_points) return;
+    const int v = __ldg(point_indices + idx);
+    grid_values[v] = fmaxf(__ldg(values + idx), __fmul_rn(grid_values[v], decay));
+}
+
+// update_grid_occupancy_with_density_values_gpu: occupied unless the voxel (or, with check_neighbours, its whole 3x3x3 neighbourhood)
+// is at or below the threshold.  The neighbourhood is addressed as the reference does: the voxel's corner in UNIT-grid coordinates
+// times the extent times n (so it is the voxel's integer coordinate only for a unit extent).
+__global__ void __launch_bounds__(256) occgrid_update_occupancy_kernel(const int32_t* __restrict__ point_indices, int n, float ex, float ey,
+                                                                       float ez, float thresh, int check_neighbours,
+                                                                       const float* __restrict__ grid_values, uint8_t* __restrict__ occupancy,
+                                                                       int64_t n_points) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_points) return;
+    const int v = __ldg(point_indices + idx);
+    bool is_empty = true;
+    if (check_neighbours) {
+        const float nf = (float)n, top = (float)(n - 1);
+        const float px = __fmul_rn(voxel_axis(compact_bits((uint32_t)v), n, ex, false, false), nf);
+        const float py = __fmul_rn(voxel_axis(compact_bits((uint32_t)v >> 1), n, ey, false, false), nf);
+        const float pz = __fmul_rn(voxel_axis(compact_bits((uint32_t)v >> 2), n, ez, false, false), nf);
+        for (int i = -1; i <= 1; ++i) {
+            const float qx = __fadd_rn(px, (float)i);
+            if (qx < 0.f || qx > top) continue;
+            for (int j = -1; j <= 1; ++j) {
+                const float qy = __fadd_rn(py, (float)j);
+                if (qy < 0.f || qy > top) continue;
+                for (int k = -1; k <= 1; ++k) {
+                    const float qz = __fadd_rn(pz, (float)k);
+                    if (qz < 0.f || qz > top) continue;
+                    const uint32_t nb = spread_bits64(__float2uint_rz(qx)) | (spread_bits64(__float2uint_rz(qy)) << 1) |
+                                        (spread_bits64(__float2uint_rz(qz)) << 2);
+                    is_empty = is_empty && __ldg(grid_values + nb) <= thresh;
+                }
+            }
+        }
+    } else {
+        is_empty = __ldg(grid_values + v) <= thresh;
+    }
+    occupancy[v] = is_empty ? 0 : 1;
+}
+
 // ---- occupancy-grid queries ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) occgrid_t_near_t_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                    const float* __restrict__ t_entry, const float* __restrict__ t_exit_p,
@@ -513,6 +597,40 @@ int vs_sampler_contract(const float* ray_o, const int32_t* se, const float* samp
         sampler_contract_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ray_o, se, samples_3d, samples_z, out_3d, out_z, n_rays);
     else
         sampler_contract_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(ray_o, se, samples_3d, samples_z, out_3d, out_z, n_rays);
+    return launched(1);
+}
+
+// OccupancyGrid::get_grid_lower_left_voxels_vertices (centre = 0; src/OccupancyGrid.cu:206-234) and get_grid_samples /
+// get_random_grid_samples[_in_roi] (centre = 1; :236-347): world position of voxels point_indices [n] (Morton order) -> out [n,3]
+int vs_occgrid_points(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, int centre, uint64_t rng_state, uint64_t rng_inc,
+                      int jitter, float* out, int64_t n_points, void* stream) {
+    VS_CHECK_ARG(n_points >= 0 && nr_voxels_per_dim > 0);
+    if (n_points == 0) return VS_OK;
+    VS_CHECK_ARG(point_indices && extent && out);
+    Pcg rng{rng_state, rng_inc};
+    occgrid_points_kernel<<<(unsigned)div_up(n_points, 256), 256, 0, (cudaStream_t)stream>>>(point_indices, nr_voxels_per_dim, extent[0], extent[1],
+                                                                                           extent[2], centre, rng, jitter, out, n_points);
+    return launched(1);
+}
+
+// OccupancyGrid::update_grid_values (src/OccupancyGrid.cu:446-474): grid_values[point_indices[i]] = max(values[i], decay * old)
+int vs_occgrid_update_values(const int32_t* point_indices, const float* values, float decay, float* grid_values, int64_t n_points, void* stream) {
+    VS_CHECK_ARG(n_points >= 0);
+    if (n_points == 0) return VS_OK;
+    VS_CHECK_ARG(point_indices && values && grid_values);
+    occgrid_update_values_kernel<<<(unsigned)div_up(n_points, 256), 256, 0, (cudaStream_t)stream>>>(point_indices, values, decay, grid_values,
+                                                                                                  n_points);
+    return launched(1);
+}
+
+// OccupancyGrid::update_grid_occupancy_with_density_values (src/OccupancyGrid.cu:476-503)
+int vs_occgrid_update_occupancy_density(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, float occupancy_thresh,
+                                        int check_neighbours, const float* grid_values, uint8_t* occupancy, int64_t n_points, void* stream) {
+    VS_CHECK_ARG(n_points >= 0 && nr_voxels_per_dim > 0);
+    if (n_points == 0) return VS_OK;
+    VS_CHECK_ARG(point_indices && extent && grid_values && occupancy);
+    occgrid_update_occupancy_kernel<<<(unsigned)div_up(n_points, 256), 256, 0, (cudaStream_t)stream>>>(
+        point_indices, nr_voxels_per_dim, extent[0], extent[1], extent[2], occupancy_thresh, check_neighbours, grid_values, occupancy, n_points);
     return launched(1);
 }
 

@@ -641,9 +641,14 @@ def _rays_args(rays_o, rays_d, t_a, t_b=None):
 
 
 class OccupancyGrid:
-    """Occupancy grid in Morton order (include/volsurfs/OccupancyGrid.cuh:9-68, bound at PyBridge.cxx:33-68): the container and the
-    two queries the samplers rest on.  The grid-maintenance methods of training (update_grid_values / update_grid_occupancy_with_*,
-    get_*_grid_samples*) are outside the rendering path and are not provided."""
+    """Occupancy grid in Morton order (include/volsurfs/OccupancyGrid.cuh:9-68, bound at PyBridge.cxx:33-68): the container, the two
+    queries the samplers rest on, and the density-grid maintenance of training (voxel sample points, update_grid_values,
+    update_grid_occupancy_with_density_values, init_sphere_roi).  Not provided: update_grid_occupancy_with_sdf_values and the two
+    sphere-tracing helpers (get_first_rays_sample_start_of_grid_occupied_regions, advance_ray_sample_to_next_occupied_voxel)."""
+
+    #: host copy of the reference's static ``pcg32 m_rng`` (src/OccupancyGrid.cu:19)
+    _rng_state = 0x853C49E6748FEA9B
+    _rng_inc = 0xDA3E39CB94B95BDB
 
     def __init__(self, nr_voxels_per_dim: int, grid_extent):
         self.m_nr_voxels_per_dim = int(nr_voxels_per_dim)
@@ -723,6 +728,96 @@ class OccupancyGrid:
 
     def get_grid_min_value(self) -> float:
         return float(self.m_grid_values.min().item())
+
+    def get_grid_max_value_in_roi(self) -> float:
+        return float(self.m_grid_values.masked_select(self.m_grid_roi).max().item())
+
+    def get_grid_min_value_in_roi(self) -> float:
+        return float(self.m_grid_values.masked_select(self.m_grid_roi).min().item())
+
+    # ---- voxel sample points (src/OccupancyGrid.cu:206-347) -----------------------------------------------------------------------
+    def _points(self, point_indices, centre: bool, jitter: bool):
+        idx = point_indices
+        if idx.dtype != torch.int32 or idx.dim() != 1 or not idx.is_cuda:
+            raise RuntimeError("point_indices must be a 1-d int32 CUDA tensor")
+        idx = idx.contiguous()
+        n = int(idx.shape[0])
+        out = torch.empty((n, 3), dtype=torch.float32, device=idx.device)
+        check(_lib.lib().vs_occgrid_points(ptr(idx), self.m_nr_voxels_per_dim, self._extent_c(), int(centre), OccupancyGrid._rng_state,
+                                           OccupancyGrid._rng_inc, int(bool(jitter)), ptr(out), n, _stream()), "vs_occgrid_points")
+        if centre and jitter:
+            OccupancyGrid._rng_state = _pcg_advance(OccupancyGrid._rng_state, OccupancyGrid._rng_inc)
+        return out, idx
+
+    def get_grid_lower_left_voxels_vertices(self):
+        """(lower-left corner of every voxel [V,3], voxel indices [V] int32), Morton order (src/OccupancyGrid.cu:206-234)"""
+        return self._points(torch.arange(0, self.get_nr_voxels(), dtype=torch.int32, device=_device()), False, False)
+
+    def get_grid_samples(self, jitter_samples):
+        """(centre of every voxel, optionally jittered inside it [V,3], voxel indices [V]) (src/OccupancyGrid.cu:236-271)"""
+        return self._points(torch.arange(0, self.get_nr_voxels(), dtype=torch.int32, device=_device()), True, jitter_samples)
+
+    def get_random_grid_samples(self, nr_voxels_to_select, jitter_samples):
+        """nr_voxels_to_select voxels drawn with replacement (torch.randint, as the reference) (src/OccupancyGrid.cu:273-308)"""
+        idx = torch.randint(0, self.get_nr_voxels(), (int(nr_voxels_to_select),), dtype=torch.int32, device=_device())
+        return self._points(idx, True, jitter_samples)
+
+    def get_random_grid_samples_in_roi(self, nr_voxels_to_select, jitter_samples):
+        """the same, among the voxels of the region of interest (src/OccupancyGrid.cu:310-347)"""
+        roi_idx = torch.nonzero(self.m_grid_roi).to(torch.int32)
+        pick = torch.randint(0, int(roi_idx.shape[0]), (int(nr_voxels_to_select),), dtype=torch.int32, device=roi_idx.device)
+        return self._points(roi_idx.index_select(0, pick).squeeze(1), True, jitter_samples)
+
+    def init_sphere_roi(self, radius, padding):
+        """region of interest = voxels whose 8 corners lie inside the sphere of radius - padding (src/OccupancyGrid.cu:117-151, the
+        reference's torch expressions)"""
+        ll, _ = self.get_grid_lower_left_voxels_vertices()
+        n = float(self.m_nr_voxels_per_dim)
+        voxel = torch.tensor(self.m_grid_extent, dtype=torch.float32, device=ll.device) / n
+        offs = torch.tensor([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], dtype=torch.float32,
+                            device=ll.device) * voxel
+        corners = (ll.view(-1, 1, 3) + offs.view(1, -1, 3)).reshape(-1, 3)
+        inside = corners.norm(2, 1, True) < (float(radius) - float(padding))
+        self.m_grid_roi = inside.reshape(-1, 8).all(-1)
+
+    # ---- density-grid maintenance (src/OccupancyGrid.cu:446-503) ---------------------------------------------------------------------
+    def update_grid_values(self, point_indices, values, decay):
+        """grid_values[point_indices[i]] = max(values[i], decay * grid_values[point_indices[i]])"""
+        if values.dim() != 2:
+            raise RuntimeError(f"values should have shape nr_pointsx1. However it has sizes {tuple(values.shape)}")
+        if float(decay) > 1.0:
+            raise RuntimeError(f"We except the decay to be < 1.0 but it is {decay}")
+        if point_indices.dim() != 1:
+            raise RuntimeError(f"point_indices should have dim 1 correspondin to nr_points. However it has sizes {tuple(point_indices.shape)}")
+        idx, v = self._indices(point_indices), _f32c(values, "values", 1)
+        if v.shape[0] != idx.shape[0]:
+            raise RuntimeError("values and point_indices must have the same number of rows")
+        g = self._values_inplace()
+        check(_lib.lib().vs_occgrid_update_values(ptr(idx), ptr(v), float(decay), ptr(g), int(idx.shape[0]), _stream()), "vs_occgrid_update_values")
+
+    def update_grid_occupancy_with_density_values(self, point_indices, occupancy_tresh, check_neighbours):
+        """occupancy[point_indices[i]] = value (or any value of the 3x3x3 neighbourhood) > occupancy_tresh"""
+        if point_indices.dim() != 1:
+            raise RuntimeError(f"point_indices should have dim 1 correspondin to nr_points. However it has sizes {tuple(point_indices.shape)}")
+        idx = self._indices(point_indices)
+        g = self._values_inplace()
+        occ = self.m_grid_occupancy
+        if occ.dtype != torch.bool or occ.numel() != self.get_nr_voxels() or not occ.is_cuda or not occ.is_contiguous():
+            raise RuntimeError("grid_occupancy must be a contiguous bool CUDA tensor with nr_voxels_per_dim^3 entries")
+        check(_lib.lib().vs_occgrid_update_occupancy_density(ptr(idx), self.m_nr_voxels_per_dim, self._extent_c(), float(occupancy_tresh),
+                                                             int(bool(check_neighbours)), ptr(g), ptr(occ), int(idx.shape[0]), _stream()),
+              "vs_occgrid_update_occupancy_density")
+
+    def _indices(self, point_indices):
+        if point_indices.dtype != torch.int32 or not point_indices.is_cuda:
+            raise RuntimeError("point_indices must be an int32 CUDA tensor")
+        return point_indices.contiguous()
+
+    def _values_inplace(self):
+        g = self.m_grid_values
+        if g.dtype != torch.float32 or g.numel() != self.get_nr_voxels() or not g.is_cuda or not g.is_contiguous():
+            raise RuntimeError("grid_values must be a contiguous float32 CUDA tensor with nr_voxels_per_dim^3 entries")
+        return g
 
     def _masks(self):
         n3 = self.get_nr_voxels()
