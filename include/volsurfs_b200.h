@@ -332,6 +332,15 @@ int vs_occgrid_update_values(const int32_t* point_indices, const float* values, 
 /* OccupancyGrid::update_grid_occupancy_with_density_values (src/OccupancyGrid.cu:476-503; kernel OccupancyGridGPU.cuh:149-218) */
 int vs_occgrid_update_occupancy_density(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, float occupancy_thresh,
                                         int check_neighbours, const float* grid_values, uint8_t* occupancy, int64_t n_points, void* stream);
+/* OccupancyGrid::update_grid_occupancy_with_sdf_values (src/OccupancyGrid.cu:505-533; kernel OccupancyGridGPU.cuh:220-316);
+ * logistic_beta [n_points,1]; the reference's check_neighbours argument is unused by its kernel and has no counterpart here */
+int vs_occgrid_update_occupancy_sdf(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, const float* logistic_beta,
+                                    float occupancy_thresh, const float* grid_values, uint8_t* occupancy, int64_t n_points, void* stream);
+/* OccupancyGrid::get_first_rays_sample_start_of_grid_occupied_regions (src/OccupancyGrid.cu:536-573; kernel OccupancyGridGPU.cuh:505-582):
+ * samples_* [n_rays, .] and se [n_rays,2] of a RaySamplesPacked(n_rays, n_rays, 0, 1) preset by the caller */
+int vs_occgrid_first_sample_start(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
+                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* samples_3d, float* samples_dirs,
+                                  float* samples_z, float* samples_dt, int32_t* se, int64_t n_rays, void* stream);
 int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* t_near, float* t_far, int64_t n_rays,
                                  void* stream);

@@ -20,7 +20,7 @@ struct Vector3f {
     __host__ __device__ float x() const { return v[0]; }
     __host__ __device__ float y() const { return v[1]; }
     __host__ __device__ float z() const { return v[2]; }
-    // used by a kernel this harness never launches (update_grid_occupancy_with_sdf_values); needed for the header to compile
+    // grid_extent / nr_voxels_per_dim in update_grid_occupancy_with_sdf_values: Eigen's vector / scalar is a per-component division
     __host__ __device__ Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
 };
 }  // namespace Eigen
@@ -151,6 +151,29 @@ int ref_update_grid_occupancy_density(const int* point_indices, int nr_voxels_pe
     OccupancyGridGPU::update_grid_occupancy_with_density_values_gpu<<<grid_for(nr_points), 256>>>(
         nr_points, nr_voxels_per_dim, Eigen::Vector3f(extent[0], extent[1], extent[2]), acc1(point_indices, nr_points), occupancy_thresh,
         check_neighbours != 0, acc1(grid_values, nv), acc1(grid_occupancy, nv));
+    return finish();
+}
+
+// OccupancyGrid.cu:505-533: update_grid_occupancy_with_sdf_values
+int ref_update_grid_occupancy_sdf(const int* point_indices, int nr_voxels_per_dim, const float* extent, const float* logistic_beta,
+                                  float occupancy_thresh, int check_neighbours, const float* grid_values, bool* grid_occupancy, int nr_points) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::update_grid_occupancy_with_sdf_values_gpu<<<grid_for(nr_points), 256>>>(
+        nr_points, Eigen::Vector3f(extent[0], extent[1], extent[2]), nr_voxels_per_dim, acc1(point_indices, nr_points),
+        acc2(logistic_beta, nr_points, 1), occupancy_thresh, check_neighbours != 0, acc1(grid_values, nv), acc1(grid_occupancy, nv));
+    return finish();
+}
+
+// OccupancyGrid.cu:536-573: get_first_rays_sample_start_of_grid_occupied_regions (outputs preset by the caller as the RaySamplesPacked
+// constructor does: the kernel leaves the rows of rays without a hit untouched)
+int ref_first_sample_start(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
+                           const float* extent, const bool* occupancy, const bool* roi, float* samples_3d, float* samples_dirs, float* samples_z,
+                           float* samples_dt, int* se, int nr_rays) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::get_first_rays_sample_start_of_grid_occupied_regions_gpu<<<grid_for(nr_rays), 256>>>(
+        nr_rays, nr_voxels_per_dim, Eigen::Vector3f(extent[0], extent[1], extent[2]), acc2(rays_o, nr_rays, 3), acc2(rays_d, nr_rays, 3),
+        acc2(t_entry, nr_rays, 1), acc2(t_exit, nr_rays, 1), acc1(occupancy, nv), acc1(roi, nv), acc2(samples_3d, nr_rays, 3),
+        acc2(samples_dirs, nr_rays, 3), acc2(samples_z, nr_rays, 1), acc2(samples_dt, nr_rays, 1), acc2(se, nr_rays, 2));
     return finish();
 }
 

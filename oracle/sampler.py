@@ -387,3 +387,23 @@ def update_grid_occupancy_density(point_indices, n, extent, thresh, check_neighb
                     empty = empty and bool(g[morton3d(int(qx), int(qy), int(qz))] <= thresh)
         occ[v] = not empty
     return occ
+
+
+def update_grid_occupancy_sdf(point_indices, n, extent, logistic_beta, thresh, grid_values, occupancy, return_weight=False):
+    """update_grid_occupancy_with_sdf_values_gpu (OccupancyGridGPU.cuh:220-316): occupied when the logistic density
+    beta e / (1 + e)^2, e = exp(-beta d), at d = max(|sdf| - half the voxel diagonal, 0) exceeds the threshold.  numpy's float32 exp may
+    differ from CUDA's expf in the last bit, so the decision can differ only for weights within an ulp of the threshold (the GPU test
+    excludes those; the product itself is compared bit for bit with the reference kernel)."""
+    occ = np.array(occupancy, bool, copy=True)
+    idx = np.asarray(point_indices, np.int64)
+    g = np.asarray(grid_values, np.float32)
+    beta = np.asarray(logistic_beta, np.float32).reshape(-1)
+    s = [F(F(extent[a]) / F(n)) for a in range(3)]
+    diagonal = np.sqrt(F(F(F(s[0] * s[0]) + F(s[1] * s[1])) + F(s[2] * s[2])), dtype=np.float32)
+    d = np.clip((np.abs(g[idx]) - F(diagonal / F(2))).astype(np.float32), F(0), F(1e10))
+    with np.errstate(over="ignore"):
+        e = np.clip(np.exp((-beta * d).astype(np.float32), dtype=np.float32), F(-1e6), F(1e6))
+        one_e = (F(1) + e).astype(np.float32)
+        w = ((beta * e).astype(np.float32) / (one_e * one_e).astype(np.float32)).astype(np.float32)
+    occ[idx] = w > F(thresh)
+    return (occ, w) if return_weight else occ

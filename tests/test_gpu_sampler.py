@@ -353,6 +353,77 @@ def test_grid_maintenance_matches_restatement_and_reference_kernels(ref):
         og.update_grid_occupancy_with_density_values(pick.reshape(-1, 1), 0.3, False)
 
 
+def test_sdf_occupancy_rule_matches_reference_kernel_and_restatement(ref):
+    """OccupancyGrid.update_grid_occupancy_with_sdf_values (src/OccupancyGrid.cu:505-533) as surf.py:297 calls it: grid values = SDF at
+    the voxel centres, one beta per index; bit-exact against the reference's kernel, restatement equal away from the threshold"""
+    from volsurfs_b200.volsurfs import OccupancyGrid
+
+    n, extent = 64, [1.0, 1.2, 0.9]
+    V = n ** 3
+    ext = (ctypes.c_float * 3)(*extent)
+    og = OccupancyGrid(n, extent)
+    pts, idx = og.get_grid_samples(False)
+    sdf = (pts.norm(dim=1) - 0.3).contiguous()  # a sphere of radius 0.3
+    og.update_grid_values(idx, sdf.reshape(-1, 1), 0.0)  # decay 0: max(new, 0 * old) keeps negative sdf at 0 ...
+    og.set_grid_values(sdf.clone())                     # ... so the methods write the SDF itself, like surf.py does after its own update
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for beta_scale, thresh in ((50.0, 1e-4), (400.0, 1e-2)):
+        beta = (beta_scale * (0.5 + torch.rand(V, 1, device="cuda", generator=g))).contiguous()
+        og.set_grid_occupancy(torch.rand(V, device="cuda", generator=g) < 0.5)
+        ro = og.get_grid_occupancy().clone()
+        before = ro.clone()
+        og.update_grid_occupancy_with_sdf_values(idx, beta, thresh, False)
+        assert ref.ref_update_grid_occupancy_sdf(P(idx), n, ext, P(beta), ctypes.c_float(thresh), 0, P(sdf), P(ro), V) == 0
+        got = og.get_grid_occupancy()
+        assert torch.equal(got, ro), (beta_scale, int((got != ro).sum()))
+        assert 0 < int(got.sum()) < V  # a shell around the sphere
+        want, w = osamp.update_grid_occupancy_sdf(idx.cpu().numpy(), n, extent, beta.cpu().numpy(), thresh, sdf.cpu().numpy(),
+                                                  before.cpu().numpy(), return_weight=True)
+        clear = np.abs(w - np.float32(thresh)) > 1e-4 * thresh
+        assert clear.mean() > 0.999 and np.array_equal(got.cpu().numpy()[clear], want[clear])
+    # a subset of indices rewrites only those voxels
+    og.set_grid_occupancy_full()
+    sub = idx[::7].contiguous()
+    og.update_grid_occupancy_with_sdf_values(sub, torch.full((sub.shape[0], 1), 200.0, device="cuda"), 1e-3, True)
+    occ = og.get_grid_occupancy()
+    mask = torch.zeros(V, dtype=torch.bool, device="cuda")
+    mask[sub.long()] = True
+    assert bool(occ[~mask].all()) and not bool(occ[mask].all())
+    with pytest.raises(RuntimeError):
+        og.update_grid_occupancy_with_sdf_values(sub, torch.full((3, 1), 200.0, device="cuda"), 1e-3, True)
+
+
+def test_first_sample_start_matches_reference_kernel(ref):
+    """OccupancyGrid.get_first_rays_sample_start_of_grid_occupied_regions (src/OccupancyGrid.cu:536-573, called by
+    utils/sphere_tracing.py:42): every field of the one-sample-per-ray packet bit-exact against the reference's kernel"""
+    from volsurfs_b200.volsurfs import OccupancyGrid, RaySamplesPacked
+
+    sc = make_scene(20000, 64, seed=41)
+    t = _cuda_scene(sc)
+    n = 20000
+    og = OccupancyGrid(sc["n"], sc["extent"])
+    og.set_grid_occupancy(t["occ"])
+    og.set_grid_roi(t["roi"])
+    got = og.get_first_rays_sample_start_of_grid_occupied_regions(t["o"], t["d"], t["t_entry"], t["t_exit"])
+    want = RaySamplesPacked(n, n, 0, 1)  # the reference's constructor fills (src/RaySamplesPacked.cu:13-48)
+    ext = (ctypes.c_float * 3)(*[float(v) for v in sc["extent"]])
+    assert ref.ref_first_sample_start(P(t["o"]), P(t["d"]), P(t["t_entry"]), P(t["t_exit"]), sc["n"], ext, P(t["occ"]), P(t["roi"]),
+                                      P(want.samples_3d), P(want.samples_dirs), P(want.samples_z), P(want.samples_dt),
+                                      P(want.ray_start_end_idx), n) == 0
+    for k in ("ray_start_end_idx", "samples_3d", "samples_dirs", "samples_z", "samples_dt"):
+        assert torch.equal(getattr(got, k), getattr(want, k)), k
+    se = got.ray_start_end_idx
+    hit = se[:, 1] > se[:, 0]
+    assert 0 < int(hit.sum()) < n
+    rows = torch.arange(n, dtype=torch.int32, device="cuda")
+    assert torch.equal(se[hit, 0], rows[hit]) and torch.equal(se[hit, 1], rows[hit] + 1) and not bool(se[~hit].any())
+    occ, _ = og.check_occupancy(got.samples_3d[hit])
+    assert bool(occ.all())  # the stored position lies in an occupied voxel of the roi
+    near, _ = og.get_rays_t_near_t_far(t["o"], t["d"], t["t_entry"], t["t_exit"])
+    assert bool((got.samples_z[hit] > near[hit]).all())  # depth = t after stepping out of that voxel
+    assert bool((got.samples_3d[~hit] == -1).all())  # rays without a hit keep the constructor's fill
+
+
 def test_sampler_feeds_packed_compositing():
     """the sampler's packet goes straight into update_dt and the packed operators (the NeRF path of volsurfs_py/methods/nerf.py:280-334)"""
     from volsurfs_b200.volsurfs import RaySampler, VolumeRendering

@@ -143,3 +143,18 @@ def test_grid_points_and_density_maintenance_known_answers():
     assert occ.sum() == 1 and occ[S.morton3d(1, 1, 1)]
     occ = S.update_grid_occupancy_density(idx[:4], n, [1, 1, 1], 0.5, False, g, np.ones(n ** 3, bool))
     assert occ.sum() == n ** 3 - 4  # only the listed voxels are rewritten
+
+
+def test_sdf_occupancy_rule_known_answers():
+    """OccupancyGridGPU.cuh:220-316: at the surface (|sdf| below half the voxel diagonal) the weight is beta / 4; far away it vanishes"""
+    n = 8
+    idx = np.arange(6, dtype=np.int32)
+    g = np.zeros(n ** 3, F)
+    g[:6] = [0.0, 0.05, -0.05, 0.5, -0.5, 0.2]
+    beta = np.full((6, 1), 100.0, F)
+    occ, w = S.update_grid_occupancy_sdf(idx, n, [1, 1, 1], beta, 1e-4, g, np.zeros(n ** 3, bool), return_weight=True)
+    half_diag = np.sqrt(3.0) / 8 / 2  # 0.108
+    assert w[0] == 25.0 and w[1] == 25.0 and w[2] == 25.0  # inside half a diagonal of the surface: d = 0 -> beta / 4
+    want = 100.0 * np.exp(-100.0 * (0.2 - half_diag)) / (1 + np.exp(-100.0 * (0.2 - half_diag))) ** 2
+    assert abs(w[5] - want) < 1e-4 * want and w[3] == w[4] and w[3] < 1e-12
+    assert occ[:6].tolist() == [True, True, True, False, False, True] and not occ[6:].any()

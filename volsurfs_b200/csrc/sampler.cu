@@ -461,6 +461,58 @@ __global__ void __launch_bounds__(256) occgrid_update_occupancy_kernel(const int
     occupancy[v] = is_empty ? 0 : 1;
 }
 
+// update_grid_occupancy_with_sdf_values_gpu (OccupancyGridGPU.cuh:220-316): a voxel stays occupied when the logistic density
+// beta e^(-beta d) / (1 + e^(-beta d))^2 at the smallest distance d the surface can have inside the voxel (|sdf| minus half the voxel
+// diagonal, at least 0) exceeds the threshold.  expf / powf / sqrtf as in the reference, so the same libdevice code decides.
+__global__ void __launch_bounds__(256) occgrid_update_occupancy_sdf_kernel(const int32_t* __restrict__ point_indices, int n, float ex, float ey,
+                                                                           float ez, const float* __restrict__ logistic_beta, float thresh,
+                                                                           const float* __restrict__ grid_values,
+                                                                           uint8_t* __restrict__ occupancy, int64_t n_points) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_points) return;
+    const int v = __ldg(point_indices + idx);
+    const float df = fabsf(__ldg(grid_values + v));
+    const float nf = (float)n;
+    const float sx = __fdiv_rn(ex, nf), sy = __fdiv_rn(ey, nf), sz = __fdiv_rn(ez, nf);
+    // max_distance_in_cuboid: the longest vertex-to-vertex distance of the voxel is its diagonal
+    const float diagonal = sqrtf(__fadd_rn(__fadd_rn(powf(sx, 2), powf(sy, 2)), powf(sz, 2)));
+    const float d = fmaxf(0.0f, fminf(__fsub_rn(df, diagonal * 0.5f), 1e10f));
+    const float beta = __ldg(logistic_beta + idx);
+    const float e = fmaxf(-1e6f, fminf(expf(__fmul_rn(-beta, d)), 1e6f));
+    const float weight = __fdiv_rn(__fmul_rn(beta, e), powf(__fadd_rn(1.0f, e), 2));
+    occupancy[v] = weight > thresh ? 1 : 0;
+}
+
+// get_first_rays_sample_start_of_grid_occupied_regions_gpu (OccupancyGridGPU.cuh:505-582): the sphere tracer's starting point — the
+// position at which each ray first probes an occupied voxel of the region of interest (one sample per hit ray at row = ray index, depth =
+// the t AFTER that voxel's step, as the reference stores it); rays without one get the segment (0,0) and keep the packet's fill values
+__global__ void __launch_bounds__(128) occgrid_first_sample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                   const float* __restrict__ t_entry, const float* __restrict__ t_exit_p,
+                                                                   Grid g, float* __restrict__ s_3d, float* __restrict__ s_dirs,
+                                                                   float* __restrict__ s_z, float* __restrict__ s_dt, int32_t* __restrict__ se,
+                                                                   int64_t n_rays) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const float t_exit = __ldg(t_exit_p + ray);
+    const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
+    const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
+    float t = __ldg(t_entry + ray);
+    while (t < t_exit) {
+        const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
+        if (!in_grid(p.voxel, g)) break;
+        t = __fadd_rn(__fadd_rn(t, step_from_unit(p.ux, p.uy, p.uz, dx, dy, dz, g)), 1e-6f);
+        if (occupied(p.voxel, g)) {
+            reinterpret_cast<int2*>(se)[ray] = make_int2((int)ray, (int)ray + 1);
+            s_3d[3 * ray] = p.px, s_3d[3 * ray + 1] = p.py, s_3d[3 * ray + 2] = p.pz;
+            s_dirs[3 * ray] = dx, s_dirs[3 * ray + 1] = dy, s_dirs[3 * ray + 2] = dz;
+            s_z[ray] = t;
+            s_dt[ray] = 0.f;
+            return;
+        }
+    }
+    reinterpret_cast<int2*>(se)[ray] = make_int2(0, 0);
+}
+
 // ---- occupancy-grid queries ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) occgrid_t_near_t_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                    const float* __restrict__ t_entry, const float* __restrict__ t_exit_p,
@@ -634,6 +686,17 @@ int vs_occgrid_update_occupancy_density(const int32_t* point_indices, int nr_vox
     return launched(1);
 }
 
+// OccupancyGrid::update_grid_occupancy_with_sdf_values (src/OccupancyGrid.cu:505-533); logistic_beta [n_points,1]
+int vs_occgrid_update_occupancy_sdf(const int32_t* point_indices, int nr_voxels_per_dim, const float* extent, const float* logistic_beta,
+                                    float occupancy_thresh, const float* grid_values, uint8_t* occupancy, int64_t n_points, void* stream) {
+    VS_CHECK_ARG(n_points >= 0 && nr_voxels_per_dim > 0);
+    if (n_points == 0) return VS_OK;
+    VS_CHECK_ARG(point_indices && extent && logistic_beta && grid_values && occupancy);
+    occgrid_update_occupancy_sdf_kernel<<<(unsigned)div_up(n_points, 256), 256, 0, (cudaStream_t)stream>>>(
+        point_indices, nr_voxels_per_dim, extent[0], extent[1], extent[2], logistic_beta, occupancy_thresh, grid_values, occupancy, n_points);
+    return launched(1);
+}
+
 // OccupancyGrid::get_rays_t_near_t_far: first / last t inside occupied voxels of the region of interest along every ray
 int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* t_near, float* t_far, int64_t n_rays,
@@ -646,6 +709,22 @@ int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const
     VS_CHECK_ARG(rays_o && rays_d && t_entry && t_exit && t_near && t_far);
     occgrid_t_near_t_far_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, g, t_near, t_far,
                                                                                                  n_rays);
+    return launched(1);
+}
+
+// OccupancyGrid::get_first_rays_sample_start_of_grid_occupied_regions (src/OccupancyGrid.cu:536-573): one-sample-per-ray packet of the
+// first occupied voxel each ray probes; the caller presets the packet's fill values (rows of rays without a hit are left untouched)
+int vs_occgrid_first_sample_start(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
+                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* samples_3d, float* samples_dirs,
+                                  float* samples_z, float* samples_dt, int32_t* se, int64_t n_rays, void* stream) {
+    VS_CHECK_ARG(n_rays >= 0);
+    Grid g;
+    int e = make_grid(nr_voxels_per_dim, extent, occupancy, roi, &g);
+    if (e != VS_OK) return e;
+    if (n_rays == 0) return VS_OK;
+    VS_CHECK_ARG(rays_o && rays_d && t_entry && t_exit && samples_3d && samples_dirs && samples_z && samples_dt && se);
+    occgrid_first_sample_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, g, samples_3d,
+                                                                                                 samples_dirs, samples_z, samples_dt, se, n_rays);
     return launched(1);
 }
 

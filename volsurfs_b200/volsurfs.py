@@ -643,8 +643,7 @@ def _rays_args(rays_o, rays_d, t_a, t_b=None):
 class OccupancyGrid:
     """Occupancy grid in Morton order (include/volsurfs/OccupancyGrid.cuh:9-68, bound at PyBridge.cxx:33-68): the container, the two
     queries the samplers rest on, and the density-grid maintenance of training (voxel sample points, update_grid_values,
-    update_grid_occupancy_with_density_values, init_sphere_roi).  Not provided: update_grid_occupancy_with_sdf_values and the two
-    sphere-tracing helpers (get_first_rays_sample_start_of_grid_occupied_regions, advance_ray_sample_to_next_occupied_voxel)."""
+    update_grid_occupancy_with_density_values / _with_sdf_values, init_sphere_roi).  Not provided: advance_ray_sample_to_next_occupied_voxel (its only call site in the reference is commented out) (get_first_rays_sample_start_of_grid_occupied_regions, advance_ray_sample_to_next_occupied_voxel)."""
 
     #: host copy of the reference's static ``pcg32 m_rng`` (src/OccupancyGrid.cu:19)
     _rng_state = 0x853C49E6748FEA9B
@@ -808,6 +807,22 @@ class OccupancyGrid:
                                                              int(bool(check_neighbours)), ptr(g), ptr(occ), int(idx.shape[0]), _stream()),
               "vs_occgrid_update_occupancy_density")
 
+    def update_grid_occupancy_with_sdf_values(self, point_indices, logistic_beta, occupancy_thresh, check_neighbours):
+        """occupancy[point_indices[i]] = logistic density (beta_i) at the closest the surface can be inside the voxel > occupancy_thresh
+        (src/OccupancyGrid.cu:505-533; check_neighbours is accepted and unused, as in the reference's kernel)"""
+        if point_indices.dim() != 1:
+            raise RuntimeError(f"point_indices should have dim 1 correspondin to nr_points. However it has sizes {tuple(point_indices.shape)}")
+        idx = self._indices(point_indices)
+        beta = _f32c(logistic_beta, "logistic_beta", 1)
+        if beta.shape[0] != idx.shape[0]:
+            raise RuntimeError("logistic_beta must have one row per point index")
+        g = self._values_inplace()
+        occ = self.m_grid_occupancy
+        if occ.dtype != torch.bool or occ.numel() != self.get_nr_voxels() or not occ.is_cuda or not occ.is_contiguous():
+            raise RuntimeError("grid_occupancy must be a contiguous bool CUDA tensor with nr_voxels_per_dim^3 entries")
+        check(_lib.lib().vs_occgrid_update_occupancy_sdf(ptr(idx), self.m_nr_voxels_per_dim, self._extent_c(), ptr(beta), float(occupancy_thresh),
+                                                         ptr(g), ptr(occ), int(idx.shape[0]), _stream()), "vs_occgrid_update_occupancy_sdf")
+
     def _indices(self, point_indices):
         if point_indices.dtype != torch.int32 or not point_indices.is_cuda:
             raise RuntimeError("point_indices must be an int32 CUDA tensor")
@@ -841,6 +856,18 @@ class OccupancyGrid:
         check(_lib.lib().vs_occgrid_rays_t_near_t_far(ptr(o), ptr(d), ptr(a), ptr(b), self.m_nr_voxels_per_dim, self._extent_c(), ptr(occ),
                                                       ptr(roi), ptr(near), ptr(far), n, _stream()), "vs_occgrid_rays_t_near_t_far")
         return near, far
+
+    def get_first_rays_sample_start_of_grid_occupied_regions(self, rays_o, rays_d, ray_t_entry, ray_t_exit):
+        """the sphere tracer's starting packet (src/OccupancyGrid.cu:536-573): RaySamplesPacked(nr_rays, nr_rays, 0, 1) holding, at row =
+        ray index, the point where the ray first probes an occupied voxel of the roi; rays without one have the segment (0, 0)"""
+        o, d, a, b, n = _rays_args(rays_o, rays_d, ray_t_entry, ray_t_exit)
+        occ, roi = self._masks()
+        out = RaySamplesPacked(n, n, 0, 1)
+        check(_lib.lib().vs_occgrid_first_sample_start(ptr(o), ptr(d), ptr(a), ptr(b), self.m_nr_voxels_per_dim, self._extent_c(), ptr(occ),
+                                                       ptr(roi), ptr(out.samples_3d), ptr(out.samples_dirs), ptr(out.samples_z),
+                                                       ptr(out.samples_dt), ptr(out.ray_start_end_idx), n, _stream()),
+              "vs_occgrid_first_sample_start")
+        return out
 
     def check_occupancy(self, points):
         """(occupied && in roi [P,1] bool, grid value [P,1]) per point; outside the grid -> (False, 0) (src/OccupancyGrid.cu:402-447)"""
