@@ -341,6 +341,11 @@ int vs_occgrid_update_occupancy_sdf(const int32_t* point_indices, int nr_voxels_
 int vs_occgrid_first_sample_start(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                                   const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* samples_3d, float* samples_dirs,
                                   float* samples_z, float* samples_dt, int32_t* se, int64_t n_rays, void* stream);
+/* OccupancyGrid::advance_ray_sample_to_next_occupied_voxel (src/OccupancyGrid.cu:575-607; kernel OccupancyGridGPU.cuh:443-503):
+ * new_samples_3d [n,3] may alias samples_3d (the reference updates its input in place); is_within_bounds [n,1] bool */
+int vs_occgrid_advance_to_next_occupied(const float* samples_dirs, const float* samples_3d, int nr_voxels_per_dim, const float* extent,
+                                        const uint8_t* occupancy, const uint8_t* roi, float* new_samples_3d, uint8_t* is_within_bounds,
+                                        int64_t n_points, void* stream);
 int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                                  const float* extent, const uint8_t* occupancy, const uint8_t* roi, float* t_near, float* t_far, int64_t n_rays,
                                  void* stream);

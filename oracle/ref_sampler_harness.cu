@@ -177,6 +177,16 @@ int ref_first_sample_start(const float* rays_o, const float* rays_d, const float
     return finish();
 }
 
+// OccupancyGrid.cu:575-607: advance_ray_sample_to_next_occupied_voxel (the reference passes the input tensor as the output too)
+int ref_advance_to_next_occupied(const float* samples_dirs, const float* samples_3d, int nr_voxels_per_dim, const float* extent,
+                                 const bool* occupancy, const bool* roi, float* new_samples_3d, bool* is_within_bounds, int nr_points) {
+    const int64_t nv = (int64_t)nr_voxels_per_dim * nr_voxels_per_dim * nr_voxels_per_dim;
+    OccupancyGridGPU::advance_ray_sample_to_next_occupied_voxel_gpu<<<grid_for(nr_points), 256>>>(
+        nr_points, nr_voxels_per_dim, Eigen::Vector3f(extent[0], extent[1], extent[2]), acc2(samples_dirs, nr_points, 3),
+        acc2(samples_3d, nr_points, 3), acc1(occupancy, nv), acc1(roi, nv), acc2(new_samples_3d, nr_points, 3), acc2(is_within_bounds, nr_points, 1));
+    return finish();
+}
+
 // OccupancyGrid.cu: get_rays_t_near_t_far
 int ref_rays_t_near_t_far(const float* rays_o, const float* rays_d, const float* t_entry, const float* t_exit, int nr_voxels_per_dim,
                           const float* extent, const bool* occupancy, const bool* roi, float* t_near, float* t_far, int nr_rays) {

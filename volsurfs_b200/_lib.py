@@ -80,6 +80,7 @@ SIGNATURES = {
     "vs_occgrid_update_occupancy_density": (c_int, [_P, c_int, _P, c_float, c_int, _P, _P, _I64, _P]),
     "vs_occgrid_update_occupancy_sdf": (c_int, [_P, c_int, _P, _P, c_float, _P, _P, _I64, _P]),
     "vs_occgrid_first_sample_start": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "vs_occgrid_advance_to_next_occupied": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_occgrid_rays_t_near_t_far": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_occgrid_check_occupancy": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_mlp_backward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, c_int, _P]),

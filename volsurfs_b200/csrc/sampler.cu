@@ -513,6 +513,34 @@ __global__ void __launch_bounds__(128) occgrid_first_sample_kernel(const float* 
     reinterpret_cast<int2*>(se)[ray] = make_int2(0, 0);
 }
 
+// advance_ray_sample_to_next_occupied_voxel_gpu (OccupancyGridGPU.cuh:443-503): each point marches along its direction to the first
+// occupied voxel of the roi (position where that voxel was probed) or, when it leaves the grid, to the last position probed inside it
+// (within = false).  out may alias points (the reference writes in place).
+__global__ void __launch_bounds__(128) occgrid_advance_kernel(const float* __restrict__ dirs, const float* points, Grid g, float* out,
+                                                              uint8_t* __restrict__ within, int64_t n_points) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    const float ox = points[3 * i], oy = points[3 * i + 1], oz = points[3 * i + 2];
+    const float dx = __ldg(dirs + 3 * i), dy = __ldg(dirs + 3 * i + 1), dz = __ldg(dirs + 3 * i + 2);
+    float t = 0.f, prec_t = 0.f;
+    bool inside = true;
+    while (true) {
+        const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
+        if (!in_grid(p.voxel, g)) {
+            inside = false;
+            out[3 * i] = __fmaf_rn(prec_t, dx, ox), out[3 * i + 1] = __fmaf_rn(prec_t, dy, oy), out[3 * i + 2] = __fmaf_rn(prec_t, dz, oz);
+            break;
+        }
+        prec_t = t;
+        t = __fadd_rn(__fadd_rn(t, step_from_unit(p.ux, p.uy, p.uz, dx, dy, dz, g)), 1e-6f);
+        if (occupied(p.voxel, g)) {
+            out[3 * i] = p.px, out[3 * i + 1] = p.py, out[3 * i + 2] = p.pz;
+            break;
+        }
+    }
+    within[i] = inside ? 1 : 0;
+}
+
 // ---- occupancy-grid queries ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) occgrid_t_near_t_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                    const float* __restrict__ t_entry, const float* __restrict__ t_exit_p,
@@ -725,6 +753,21 @@ int vs_occgrid_first_sample_start(const float* rays_o, const float* rays_d, cons
     VS_CHECK_ARG(rays_o && rays_d && t_entry && t_exit && samples_3d && samples_dirs && samples_z && samples_dt && se);
     occgrid_first_sample_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_entry, t_exit, g, samples_3d,
                                                                                                  samples_dirs, samples_z, samples_dt, se, n_rays);
+    return launched(1);
+}
+
+// OccupancyGrid::advance_ray_sample_to_next_occupied_voxel (src/OccupancyGrid.cu:575-607); new_samples_3d may alias samples_3d
+int vs_occgrid_advance_to_next_occupied(const float* samples_dirs, const float* samples_3d, int nr_voxels_per_dim, const float* extent,
+                                        const uint8_t* occupancy, const uint8_t* roi, float* new_samples_3d, uint8_t* is_within_bounds,
+                                        int64_t n_points, void* stream) {
+    VS_CHECK_ARG(n_points >= 0);
+    Grid g;
+    int e = make_grid(nr_voxels_per_dim, extent, occupancy, roi, &g);
+    if (e != VS_OK) return e;
+    if (n_points == 0) return VS_OK;
+    VS_CHECK_ARG(samples_dirs && samples_3d && new_samples_3d && is_within_bounds);
+    occgrid_advance_kernel<<<(unsigned)div_up(n_points, 128), 128, 0, (cudaStream_t)stream>>>(samples_dirs, samples_3d, g, new_samples_3d,
+                                                                                            is_within_bounds, n_points);
     return launched(1);
 }
 

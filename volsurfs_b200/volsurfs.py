@@ -643,7 +643,7 @@ def _rays_args(rays_o, rays_d, t_a, t_b=None):
 class OccupancyGrid:
     """Occupancy grid in Morton order (include/volsurfs/OccupancyGrid.cuh:9-68, bound at PyBridge.cxx:33-68): the container, the two
     queries the samplers rest on, and the density-grid maintenance of training (voxel sample points, update_grid_values,
-    update_grid_occupancy_with_density_values / _with_sdf_values, init_sphere_roi).  Not provided: advance_ray_sample_to_next_occupied_voxel (its only call site in the reference is commented out) (get_first_rays_sample_start_of_grid_occupied_regions, advance_ray_sample_to_next_occupied_voxel)."""
+    update_grid_occupancy_with_density_values / _with_sdf_values, init_sphere_roi). (get_first_rays_sample_start_of_grid_occupied_regions, advance_ray_sample_to_next_occupied_voxel)."""
 
     #: host copy of the reference's static ``pcg32 m_rng`` (src/OccupancyGrid.cu:19)
     _rng_state = 0x853C49E6748FEA9B
@@ -868,6 +868,20 @@ class OccupancyGrid:
                                                        ptr(out.samples_dt), ptr(out.ray_start_end_idx), n, _stream()),
               "vs_occgrid_first_sample_start")
         return out
+
+    def advance_ray_sample_to_next_occupied_voxel(self, samples_dirs, samples_3d):
+        """every point marched along its direction to the first occupied voxel of the roi, or to the last position inside the grid
+        (is_within_bounds False).  As in the reference (src/OccupancyGrid.cu:575-607, ``new_samples_3d = samples_3d``) a contiguous
+        float32 input is updated IN PLACE and returned -> (new_samples_3d [P,3], is_within_bounds [P,1] bool)"""
+        p, d = _f32c(samples_3d, "samples_3d", 3), _f32c(samples_dirs, "samples_dirs", 3)
+        if d.shape[0] != p.shape[0]:
+            raise RuntimeError("samples_dirs and samples_3d must have the same number of rows")
+        occ, roi = self._masks()
+        n = int(p.shape[0])
+        within = torch.ones((n, 1), dtype=torch.bool, device=p.device)
+        check(_lib.lib().vs_occgrid_advance_to_next_occupied(ptr(d), ptr(p), self.m_nr_voxels_per_dim, self._extent_c(), ptr(occ), ptr(roi), ptr(p),
+                                                             ptr(within), n, _stream()), "vs_occgrid_advance_to_next_occupied")
+        return p, within
 
     def check_occupancy(self, points):
         """(occupied && in roi [P,1] bool, grid value [P,1]) per point; outside the grid -> (False, 0) (src/OccupancyGrid.cu:402-447)"""
