@@ -84,6 +84,12 @@ def test_sampler_and_grid_surface_against_pybridge_if_mounted():
     assert og_ref == og_have  # every OccupancyGrid method of the binding
     assert rs_ref == rs_have  # every RaySampler method of the binding, contraction included
     assert {"compute_samples_fg", "compute_samples_fg_in_grid_occupied_regions", "compute_samples_bg"} <= rs_have
+    from volsurfs_b200.volsurfs import VolumeRendering
+
+    vr = text[text.index("py::class_<VolumeRendering>"):text.index("py::class_<RaySampler>")]
+    vr_ref = set(re.findall(r'\.def(?:_static)?\("(\w+)"', vr))
+    vr_have = {n for n in dir(VolumeRendering) if not n.startswith("_") and callable(getattr(VolumeRendering, n))}
+    assert len(vr_ref) >= 12 and vr_ref <= vr_have  # the whole VolumeRendering binding (the shim adds the fused composite entry points)
 
 
 def test_no_cpu_fallback_without_cuda():

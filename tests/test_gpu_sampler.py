@@ -425,31 +425,42 @@ def test_first_sample_start_matches_reference_kernel(ref):
 
 
 def test_advance_to_next_occupied_voxel_matches_reference_kernel(ref):
-    """OccupancyGrid.advance_ray_sample_to_next_occupied_voxel (src/OccupancyGrid.cu:575-607): bit-exact against the reference's kernel;
-    the input positions are updated in place, as the reference does"""
+    """OccupancyGrid.advance_ray_sample_to_next_occupied_voxel (src/OccupancyGrid.cu:575-607): bit-exact against the reference's kernel
+    for points that leave the grid through an upper face (the reference's kernel does not return for the others: its index clamps
+    coordinates below the grid to voxel 0); the input positions are updated in place, as the reference does"""
     from volsurfs_b200.volsurfs import OccupancyGrid
 
-    sc = make_scene(20000, 64, seed=43)
+    sc = make_scene(64, 64, seed=43)
     t = _cuda_scene(sc)
     n = 20000
     og = OccupancyGrid(sc["n"], sc["extent"])
     og.set_grid_occupancy(t["occ"])
     og.set_grid_roi(t["roi"])
-    start = (t["o"] + t["d"] * (t["t_entry"] + 1e-3)).contiguous()  # just inside the grid
+    g = torch.Generator(device="cuda").manual_seed(11)
+    extent = torch.tensor([float(v) for v in sc["extent"]], device="cuda")
+    start = ((torch.rand(n, 3, device="cuda", generator=g) - 0.5) * 0.9 * extent).contiguous()  # inside the grid
+    dirs = torch.nn.functional.normalize(torch.rand(n, 3, device="cuda", generator=g) + 0.05, dim=1).contiguous()  # all components > 0
     start[::50] = 5.0  # some points outside the grid: returned unchanged, not within bounds
     ext = (ctypes.c_float * 3)(*[float(v) for v in sc["extent"]])
     r3, rw = torch.full_like(start, -7.0), torch.ones(n, 1, dtype=torch.bool, device="cuda")
-    assert ref.ref_advance_to_next_occupied(P(t["d"]), P(start), sc["n"], ext, P(t["occ"]), P(t["roi"]), P(r3), P(rw), n) == 0
+    assert ref.ref_advance_to_next_occupied(P(dirs), P(start), sc["n"], ext, P(t["occ"]), P(t["roi"]), P(r3), P(rw), n) == 0
     src = start.clone()
-    got, within = og.advance_ray_sample_to_next_occupied_voxel(t["d"], src)
+    got, within = og.advance_ray_sample_to_next_occupied_voxel(dirs, src)
     assert got.data_ptr() == src.data_ptr() and within.dtype == torch.bool and within.shape == (n, 1)
     assert torch.equal(got, r3) and torch.equal(within, rw)
     w = within[:, 0]
     assert 0 < int(w.sum()) < n and not bool(w[::50].any()) and torch.equal(got[::50], start[::50])
     occ, _ = og.check_occupancy(got[w])
     assert bool(occ.all())  # points that stayed inside stopped in an occupied voxel of the roi
+    # points leaving through a lower face end the march too (deviation: the reference never returns for them)
+    src = start[1:2000:2].clone()
+    got, within = og.advance_ray_sample_to_next_occupied_voxel(-dirs[1:2000:2].contiguous(), src)
+    w = within[:, 0]
+    assert 0 < int(w.sum()) < w.numel()
+    occ, _ = og.check_occupancy(got[w])
+    assert bool(occ.all()) and bool((got[~w].abs() <= 0.5 * extent + 1e-4).all())  # the others: last position probed inside the grid
     with pytest.raises(RuntimeError):
-        og.advance_ray_sample_to_next_occupied_voxel(t["d"][:5], src)
+        og.advance_ray_sample_to_next_occupied_voxel(dirs[:5], src)
 
 
 def test_sampler_feeds_packed_compositing():

@@ -526,7 +526,11 @@ __global__ void __launch_bounds__(128) occgrid_advance_kernel(const float* __res
     bool inside = true;
     while (true) {
         const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
-        if (!in_grid(p.voxel, g)) {
+        // Deviation: the reference's index clamps coordinates below the grid (and NaN) to voxel 0 of that axis, so a point leaving through
+        // a lower face is marched on for ever (its kernel does not return; the call site, utils/sphere_tracing.py:131, is commented
+        // out).  Here a position below the grid ends the march like one above it.
+        const bool below = !(__fadd_rn(p.ux, 0.5f) >= 0.f) || !(__fadd_rn(p.uy, 0.5f) >= 0.f) || !(__fadd_rn(p.uz, 0.5f) >= 0.f);
+        if (below || !in_grid(p.voxel, g)) {
             inside = false;
             out[3 * i] = __fmaf_rn(prec_t, dx, ox), out[3 * i + 1] = __fmaf_rn(prec_t, dy, oy), out[3 * i + 2] = __fmaf_rn(prec_t, dz, oz);
             break;

@@ -871,7 +871,8 @@ class OccupancyGrid:
 
     def advance_ray_sample_to_next_occupied_voxel(self, samples_dirs, samples_3d):
         """every point marched along its direction to the first occupied voxel of the roi, or to the last position inside the grid
-        (is_within_bounds False).  As in the reference (src/OccupancyGrid.cu:575-607, ``new_samples_3d = samples_3d``) a contiguous
+        (is_within_bounds False; a point leaving through a LOWER face ends the march too — the reference's kernel does not return for those).
+        As in the reference (src/OccupancyGrid.cu:575-607, ``new_samples_3d = samples_3d``) a contiguous
         float32 input is updated IN PLACE and returned -> (new_samples_3d [P,3], is_within_bounds [P,1] bool)"""
         p, d = _f32c(samples_3d, "samples_3d", 3), _f32c(samples_dirs, "samples_dirs", 3)
         if d.shape[0] != p.shape[0]:
