@@ -1,6 +1,5 @@
-"""ORACLE build recipe (test infrastructure): compiles raytrace_oracle.c with gcc into oracle/_build/.
-IEEE fp32, no FMA contraction (-ffp-contract=off), OpenMP over rays.  The reference's own tracer cannot be built here
-(needs Eigen, which raytracelib's setup.py downloads; no network) — see DESIGN.md."""
+"""ORACLE build recipe (test infrastructure): compiles raytrace_oracle.c with gcc into oracle/_build/ (IEEE fp32, -ffp-contract=off:
+every FMA in it is an explicit fmaf), and the reference's own kernels behind C harnesses into oracle/_ref/ — see DESIGN.md §4."""
 from __future__ import annotations
 
 import shutil
@@ -128,8 +127,43 @@ def build_ref_sampler(force: bool = False):
     return SAMPLER_LIB
 
 
+# ---- oracle/_ref: the reference's mesh ray tracer (raytracelib) behind a C harness ----------------------------------------------
+RAYTRACE_SRC = HERE / "ref_raytrace_harness.cu"
+RAYTRACE_LIB = REF_DIR / "libraytrace_ref.so"
+RAYTRACELIB = REFERENCE / "submodules/raytracelib"
+EIGEN_STANDIN = HERE / "eigen_standin"
+
+
+def raytrace_ref_available() -> bool:
+    return RAYTRACE_LIB.exists()
+
+
+def build_ref_raytrace(force: bool = False):
+    """nvcc-compile oracle/ref_raytrace_harness.cu, which #includes the reference's src/bvh.cu (and through it triangle.cuh,
+    bounding_box.cuh, bvh.cuh, common.h, gpu_memory.h) from where they lie under /root/reference/submodules/raytracelib (nothing is
+    copied), for sm_100a into oracle/_ref/libraytrace_ref.so.  Eigen (downloaded by raytracelib's setup.py, absent here) is replaced on
+    the include path by oracle/eigen_standin.  raytracelib's own flags: -O3, default floating-point mode (FMA contraction on in device
+    code); the host part goes through gcc without -mfma, i.e. without contraction.  No libtorch involved (seconds, not minutes).
+    Returns None when the reference tree is not mounted (GPU box): the prebuilt .so is used as is."""
+    if not (RAYTRACELIB / "src/bvh.cu").exists():
+        return RAYTRACE_LIB if RAYTRACE_LIB.exists() else None
+    deps = [RAYTRACE_SRC, EIGEN_STANDIN / "Eigen/Dense", RAYTRACELIB / "src/bvh.cu", *sorted((RAYTRACELIB / "include/raytracing").glob("*"))]
+    if RAYTRACE_LIB.exists() and not force and all(RAYTRACE_LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return RAYTRACE_LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    REF_DIR.mkdir(exist_ok=True)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-extended-lambda", "--expt-relaxed-constexpr",
+           "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-w", f"-I{EIGEN_STANDIN}", f"-I{RAYTRACELIB / 'include'}", f"-I{RAYTRACELIB / 'src'}",
+           str(RAYTRACE_SRC), "-o", str(RAYTRACE_LIB), "-lcudart", "-lgomp"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on the ray-tracer reference harness:\n{res.stdout[-4000:]}")
+    return RAYTRACE_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_ref())
     print(build_ref_permuto())
     print(build_ref_sampler())
+    print(build_ref_raytrace())

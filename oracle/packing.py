@@ -108,9 +108,9 @@ def pack_layer_hits(rays_o, rays_d, hit, depth):
     hit [N,K] bool, depth [N,K] f32, both in mesh order (0 = innermost,
     volsurfs.py:476-518).  Slot j of ray r holds that ray's j-th hit in
     outer -> inner order (descending mesh index, volsurfs.py:601-603).
-    samples_z = t, samples_3d = o + t*d (bvh.cu:445: ``ray_o + depth*ray_d``,
-    evaluated here as separate fp32 multiply and add per component — the
-    contract the CUDA kernel follows with __fmul_rn/__fadd_rn), samples_dirs = d.
+    samples_z = t, samples_3d = the reference kernel's ``positions`` (bvh.cu:445:
+    ``ray_o + depth*ray_d``, which nvcc contracts to one fp32 FMA per component —
+    see raytrace_oracle.c, contract "device"), samples_dirs = d.
 
     Returns (RaySamplesPackedNP uncompacted, layer_of_slot [N*K] i32 (-1 unused)).
     """
@@ -132,7 +132,9 @@ def pack_layer_hits(rays_o, rays_d, hit, depth):
     slot = ray * K + rank
     t = depth[ray, layer]
     rsp.samples_z[slot, 0] = t
-    rsp.samples_3d[slot] = (rays_o[ray] + (t[:, None] * rays_d[ray]).astype(np.float32)).astype(np.float32)
+    from .raytrace import fmaf
+
+    rsp.samples_3d[slot] = fmaf(rays_d[ray], t[:, None], rays_o[ray])
     rsp.samples_dirs[slot] = rays_d[ray]
     layer_of_slot[slot] = layer
     has = cnt > 0

@@ -22,17 +22,35 @@ def _load():
         lib.vso_bvh_num_nodes.argtypes = [ctypes.c_void_p]
         lib.vso_trace.restype = ctypes.c_int
         lib.vso_trace.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int64] + [ctypes.c_void_p] * 8
+        lib.vso_set_contract.argtypes = [ctypes.c_int]
         _lib = lib
     return _lib
+
+
+def fmaf(a, b, c):
+    """element-wise float32 fma(a, b, c) (one rounding) through the C oracle library; arrays are broadcast first"""
+    a, b, c = np.broadcast_arrays(np.asarray(a, np.float32), np.asarray(b, np.float32), np.asarray(c, np.float32))
+    a, b, c = (np.ascontiguousarray(x) for x in (a, b, c))
+    out = np.empty(a.shape, np.float32)
+    lib = _load()
+    lib.vso_fmaf_array.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64]
+    lib.vso_fmaf_array(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, a.size)
+    return out
 
 
 class OracleRayTracer:
     """Same call shape as raytracelib.RayTracer: one BVH per mesh, ``trace(rays_o, rays_d, mesh_id)`` returns the
     reference's result dict (numpy).  ``mode='bvh'`` follows the reference traversal, ``mode='brute'`` tests every
-    triangle in index order."""
+    triangle in index order.
 
-    def __init__(self, meshes, t_near=1e-3, t_far=100.0):
+    ``contract``: ``"device"`` (default) = the FMA contractions of the reference's CUDA kernel (what the product is held to, bit for
+    bit); ``"host"`` = no contraction = the reference's ``__host__`` code path under gcc.  Both are pinned by
+    oracle/_ref/libraytrace_ref.so (the reference's own src/bvh.cu), see raytrace_oracle.c."""
+
+    def __init__(self, meshes, t_near=1e-3, t_far=100.0, contract="device"):
         lib = _load()
+        assert contract in ("device", "host")
+        self.contract = 1 if contract == "device" else 0
         self.t_near, self.t_far = t_near, t_far
         self.handles = []
         self.nr_meshes = len(meshes)
@@ -65,6 +83,7 @@ class OracleRayTracer:
         bary = np.zeros((n, 3), np.float32)
         u = np.zeros(n, np.float32)
         v = np.zeros(n, np.float32)
+        _load().vso_set_contract(self.contract)
         ov = _load().vso_trace(self.handles[mesh_id], 1 if mode == "brute" else 0, o.ctypes.data, d.ctypes.data, md.ctypes.data, n,
                                positions.ctypes.data, normals.ctypes.data, depth.ctypes.data, tmid.ctypes.data, tid.ctypes.data,
                                bary.ctypes.data, u.ctypes.data, v.ctypes.data)

@@ -8,13 +8,23 @@
  *   per-ray outputs ....... src/bvh.cu:420-469  (depth, position, face normal, original triangle id, barycentric)
  *   hit flag .............. raytracelib/raytracer.py:100 (is_hit = depth <= t_far), min_depth = 0 (:70)
  *
- * Arithmetic contract ("parity unpinned" by the reference: it has no golden vectors, Eigen is not vendored and nvcc
- * contracts a*b+c into FMA in the shipped binary, which cannot be built here).  This oracle DEFINES the contract the
- * CUDA kernel is held to: IEEE fp32, round-to-nearest, NO contraction (compile with -ffp-contract=off; the CUDA side
- * uses __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn), Eigen 3.3.7 evaluation order:
- *   cross(a,b) = (a1*b2 - a2*b1, a2*b0 - a0*b2, a0*b1 - a1*b0)
- *   dot(a,b)   = a0*b0 + (a1*b1 + a2*b2)        (redux_novec_unroller splits a length-3 reduction as 1 + 2)
- *   normalized = v / sqrt(dot(v,v)) component-wise division, v unchanged if dot(v,v) == 0
+ * PINNED by the reference's own sources: oracle/ref_raytrace_harness.cu compiles src/bvh.cu + the raytracing/ headers where they lie
+ * (against oracle/eigen_standin: Eigen itself is downloaded by raytracelib's setup.py and absent here) into
+ * oracle/_ref/libraytrace_ref.so, which runs the reference's traversal both on the host (gcc) and as its CUDA kernel.
+ *
+ * Two arithmetic contracts, selected at run time by vso_set_contract():
+ *   0  "host": IEEE fp32, round-to-nearest, NO contraction (this file is compiled with -ffp-contract=off) in Eigen 3.3.7's
+ *      evaluation order — bit-identical to the reference's __host__ code path built by gcc for x86-64 (tests/test_oracle_raytrace.py):
+ *        cross(a,b) = (a1*b2 - a2*b1, a2*b0 - a0*b2, a0*b1 - a1*b0)
+ *        dot(a,b)   = a0*b0 + (a1*b1 + a2*b2)        (redux_novec_unroller splits a length-3 reduction as 1 + 2)
+ *        normalized = v / sqrt(dot(v,v)) component-wise division, v unchanged if dot(v,v) == 0
+ *   1  "device": the same expressions with the FMA contractions nvcc 12.9 -O3 applies to raytrace_kernel for sm_100a, read off the SASS
+ *      of libraytrace_ref.so (cuobjdump -sass) — bit-identical to the reference's CUDA kernel (tests/test_gpu_raytrace.py), and the
+ *      contract volsurfs_b200/csrc/shells.cu implements:
+ *        cross(a,b)_i = fma(a_j, b_k, -rn(a_k*b_j))
+ *        d.n, n.rov0, n.n  = fma(x0,y0, fma(x2,y2, rn(x1*y1)))
+ *        q.v2v0, q.v1v0    = fma(x0,y0, fma(x1,y1, rn(x2*y2)))
+ *        D = 1/(d.n) correctly rounded; u, v, t = rn(D * .);  position = fma(t, d, o);  sqrt and divisions correctly rounded
  * Ties (two triangles with bit-identical t) are resolved by traversal order in the reference; the brute-force tracer
  * below visits triangles in original index order, so the lowest index wins — the rule the CUDA kernel implements.
  */
@@ -59,18 +69,48 @@ static inline void cross3(const float* a, const float* b, float* r) {
 }
 static inline float dot3(const float* a, const float* b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
 
+/* ---- contract 1: the reference kernel's FMA contractions (see the header) ---------------------------------------------- */
+static int g_contract = 0;
+void vso_set_contract(int c) { g_contract = c; }
+int vso_get_contract(void) { return g_contract; }
+
+/* element-wise fmaf for the numpy side of the oracle (oracle/packing.py): out = a*b + c with one rounding */
+void vso_fmaf_array(const float* a, const float* b, const float* c, float* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = fmaf(a[i], b[i], c[i]);
+}
+
+static inline void cross3_dev(const float* a, const float* b, float* r) {
+    r[0] = fmaf(a[1], b[2], -(a[2] * b[1]));
+    r[1] = fmaf(a[2], b[0], -(a[0] * b[2]));
+    r[2] = fmaf(a[0], b[1], -(a[1] * b[0]));
+}
+/* dots that involve the face normal n: the middle product is the rounded one */
+static inline float dot3_dev_n(const float* a, const float* b) { return fmaf(a[0], b[0], fmaf(a[2], b[2], a[1] * b[1])); }
+/* dots of q with an edge: the last product is the rounded one */
+static inline float dot3_dev_q(const float* a, const float* b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
+
 /* triangle.cuh:42-70.  Returns is_hit; t,u,v as the reference leaves them (t = -1 on a miss). */
 static int tri_intersect(const Tri* tr, const float* o, const float* d, float* t_out, float* u_out, float* v_out) {
     float v1v0[3], v2v0[3], rov0[3], n[3], q[3];
     sub3(tr->b, tr->a, v1v0);
     sub3(tr->c, tr->a, v2v0);
     sub3(o, tr->a, rov0);
-    cross3(v1v0, v2v0, n);
-    cross3(rov0, d, q);
-    float D = 1.0f / dot3(d, n);
-    float u = D * -dot3(q, v2v0);
-    float v = D * dot3(q, v1v0);
-    float t = D * -dot3(n, rov0);
+    float u, v, t;
+    if (g_contract == 1) {
+        cross3_dev(v1v0, v2v0, n);
+        cross3_dev(rov0, d, q);
+        float D = 1.0f / dot3_dev_n(d, n);
+        u = D * -dot3_dev_q(q, v2v0);
+        v = D * dot3_dev_q(q, v1v0);
+        t = D * -dot3_dev_n(n, rov0);
+    } else {
+        cross3(v1v0, v2v0, n);
+        cross3(rov0, d, q);
+        float D = 1.0f / dot3(d, n);
+        u = D * -dot3(q, v2v0);
+        v = D * dot3(q, v1v0);
+        t = D * -dot3(n, rov0);
+    }
     int is_hit = 1;
     if (u < 0.0f || u > 1.0f || v < 0.0f || (u + v) > 1.0f || t < 0.0f) {
         is_hit = 0;
@@ -330,13 +370,19 @@ static void brute_intersect(const Bvh* b, const Tri* tris_in_index_order, const 
 static void write_outputs(const Tri* tr, int has, const float* o, const float* d, float t, float u, float v, int64_t r, float* positions,
                           float* normals, float* depth, int64_t* tri_mesh_id, int64_t* tri_id, float* bary) {
     depth[r] = t;
-    for (int k = 0; k < 3; ++k) positions[3 * r + k] = o[k] + t * d[k]; /* ray_o + depth*ray_d, no contraction */
+    for (int k = 0; k < 3; ++k) positions[3 * r + k] = g_contract == 1 ? fmaf(d[k], t, o[k]) : o[k] + t * d[k]; /* ray_o + depth*ray_d */
     if (has) {
         float e1[3], e2[3], n[3];
         sub3(tr->b, tr->a, e1);
         sub3(tr->c, tr->a, e2);
-        cross3(e1, e2, n);
-        float z = dot3(n, n);
+        float z;
+        if (g_contract == 1) {
+            cross3_dev(e1, e2, n);
+            z = dot3_dev_n(n, n);
+        } else {
+            cross3(e1, e2, n);
+            z = dot3(n, n);
+        }
         if (z > 0.0f) {
             float s = sqrtf(z);
             n[0] = n[0] / s;

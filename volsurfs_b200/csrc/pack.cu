@@ -214,9 +214,9 @@ __global__ void __launch_bounds__(256) pack_hits_kernel(const float* __restrict_
             const int64_t b = (int64_t)o + rank;
             idx_out[b] = (int32_t)(r * K + rank);
             z_out[b] = t;
-            p3d_out[3 * b] = __fadd_rn(ox, __fmul_rn(t, dx));
-            p3d_out[3 * b + 1] = __fadd_rn(oy, __fmul_rn(t, dy));
-            p3d_out[3 * b + 2] = __fadd_rn(oz, __fmul_rn(t, dz));
+            p3d_out[3 * b] = __fmaf_rn(dx, t, ox);  // = the reference kernel's positions (bvh.cu:445, contracted to one FMA by nvcc)
+            p3d_out[3 * b + 1] = __fmaf_rn(dy, t, oy);
+            p3d_out[3 * b + 2] = __fmaf_rn(dz, t, oz);
             dirs_out[3 * b] = dx;
             dirs_out[3 * b + 1] = dy;
             dirs_out[3 * b + 2] = dz;

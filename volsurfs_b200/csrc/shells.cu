@@ -13,10 +13,15 @@
 //     (cp.async.bulk + mbarrier) when the CTA starts, so the always-visited upper levels never leave the SM;
 //   * triangles are 3 x float4 (vertex + original face index), read with 16-byte loads.
 //
-// Parity contract (bit-exact hits): the ray/triangle arithmetic is the reference's (include/raytracing/triangle.cuh:42-70) in
-// IEEE fp32 with no contraction and Eigen's evaluation order, identical to oracle/raytrace_oracle.c:
-//   n = (b-a)x(c-a), q = (o-a)xd, D = 1/(d.n), u = D*-(q.(c-a)), v = D*(q.(b-a)), t = D*-(n.(o-a)),
-//   dot(x,y) = x0*y0 + (x1*y1 + x2*y2);  miss if u<0 || u>1 || v<0 || u+v>1 || t<0;  accept if t > 0 && t < best.
+// Parity contract (bit-exact hits, pinned by the reference's own kernel): the ray/triangle arithmetic is the reference's
+// (include/raytracing/triangle.cuh:42-70, Eigen 3.3.7 evaluation order) with exactly the FMA contractions nvcc -O3 applies to the
+// reference's raytrace_kernel for sm_100a — read off the SASS of oracle/_ref/libraytrace_ref.so (the reference's src/bvh.cu compiled where
+// it lies) and spelled out with __fmaf_rn/__fmul_rn so that no compiler decision is left:
+//   cross(a,b)_i = fma(a_j, b_k, -rn(a_k*b_j));   n = (b-a)x(c-a), q = (o-a)xd
+//   d.n, n.(o-a), n.n = fma(x0,y0, fma(x2,y2, rn(x1*y1)));   q.(c-a), q.(b-a) = fma(x0,y0, fma(x1,y1, rn(x2*y2)))
+//   D = 1/(d.n) (IEEE), u = rn(D*-(q.(c-a))), v = rn(D*(q.(b-a))), t = rn(D*-(n.(o-a)));  position = fma(t, d, o)
+//   miss if u<0 || u>1 || v<0 || u+v>1 || t<0;  accept if t > 0 && t < best.
+// tests/test_gpu_raytrace.py holds this kernel, the reference's kernel and oracle/raytrace_oracle.c (contract "device") to the same bits.
 // The nearest hit does not depend on the BVH as long as no box containing the winning triangle is culled, so child boxes are
 // padded by a relative epsilon and children are visited whenever t_near <= best (ties in t resolve to the lowest original
 // face index, which is what a brute-force pass in index order returns).
@@ -278,42 +283,53 @@ static void collapse_bfs(const Builder& B, std::vector<Node4>& out) {
 // =====================================================================================================================
 // device
 // =====================================================================================================================
-__device__ __forceinline__ float dot_rn(float x0, float x1, float x2, float y0, float y1, float y2) {
-    return __fadd_rn(__fmul_rn(x0, y0), __fadd_rn(__fmul_rn(x1, y1), __fmul_rn(x2, y2)));
+// dots that involve the face normal (d.n, n.rov0, n.n): the middle product is the separately rounded one
+__device__ __forceinline__ float dot_n(float x0, float x1, float x2, float y0, float y1, float y2) {
+    return __fmaf_rn(x0, y0, __fmaf_rn(x2, y2, __fmul_rn(x1, y1)));
+}
+// dots of q with a triangle edge: the last product is the separately rounded one
+__device__ __forceinline__ float dot_q(float x0, float x1, float x2, float y0, float y1, float y2) {
+    return __fmaf_rn(x0, y0, __fmaf_rn(x1, y1, __fmul_rn(x2, y2)));
+}
+__device__ __forceinline__ void cross_ref(float a0, float a1, float a2, float b0, float b1, float b2, float& r0, float& r1, float& r2) {
+    r0 = __fmaf_rn(a1, b2, -__fmul_rn(a2, b1));
+    r1 = __fmaf_rn(a2, b0, -__fmul_rn(a0, b2));
+    r2 = __fmaf_rn(a0, b1, -__fmul_rn(a1, b0));
+}
+// Eigen normalized() as the reference kernel evaluates it: v / sqrt(v.v) with IEEE sqrt and divisions, unchanged for the zero vector
+__device__ __forceinline__ void normalize_ref(float& nx, float& ny, float& nz) {
+    const float zz = dot_n(nx, ny, nz, nx, ny, nz);
+    if (zz > 0.0f) {
+        const float s = __fsqrt_rn(zz);
+        nx = __fdiv_rn(nx, s);
+        ny = __fdiv_rn(ny, s);
+        nz = __fdiv_rn(nz, s);
+    }
 }
 
-// triangle.cuh:42-70 in oracle arithmetic; returns is_hit, leaves t/u/v as computed.  e1 = b-a, e2 = c-a and n = e1 x e2 do not
-// depend on the ray: they are computed once per triangle by precompute_tri_kernel with the very same rounded operations.
+// triangle.cuh:42-70 in the reference kernel's arithmetic; returns is_hit, leaves t/u/v as computed.  e1 = b-a, e2 = c-a and n = e1 x e2
+// do not depend on the ray: they are computed once per triangle by precompute_tri_kernel with the very same rounded operations.
 __device__ __forceinline__ bool tri_test(const float4 A, const float4 E1, const float4 E2, const float4 Nn, float ox, float oy, float oz,
                                          float dx, float dy, float dz, float& t, float& u, float& v) {
     const float rx = __fsub_rn(ox, A.x), ry = __fsub_rn(oy, A.y), rz = __fsub_rn(oz, A.z);
-    const float qx = __fsub_rn(__fmul_rn(ry, dz), __fmul_rn(rz, dy));
-    const float qy = __fsub_rn(__fmul_rn(rz, dx), __fmul_rn(rx, dz));
-    const float qz = __fsub_rn(__fmul_rn(rx, dy), __fmul_rn(ry, dx));
-    const float D = __fdiv_rn(1.0f, dot_rn(dx, dy, dz, Nn.x, Nn.y, Nn.z));
-    u = __fmul_rn(D, -dot_rn(qx, qy, qz, E2.x, E2.y, E2.z));
-    v = __fmul_rn(D, dot_rn(qx, qy, qz, E1.x, E1.y, E1.z));
-    t = __fmul_rn(D, -dot_rn(Nn.x, Nn.y, Nn.z, rx, ry, rz));
+    float qx, qy, qz;
+    cross_ref(rx, ry, rz, dx, dy, dz, qx, qy, qz);
+    const float D = __fdiv_rn(1.0f, dot_n(dx, dy, dz, Nn.x, Nn.y, Nn.z));
+    u = __fmul_rn(D, -dot_q(qx, qy, qz, E2.x, E2.y, E2.z));
+    v = __fmul_rn(D, dot_q(qx, qy, qz, E1.x, E1.y, E1.z));
+    t = __fmul_rn(D, -dot_n(Nn.x, Nn.y, Nn.z, rx, ry, rz));
     return !(u < 0.0f || u > 1.0f || v < 0.0f || __fadd_rn(u, v) > 1.0f || t < 0.0f);
 }
 
-// triangle.cuh:42-70 in oracle arithmetic; returns is_hit, leaves t/u/v as computed (t untouched on a miss)
+// the same from raw vertices
 __device__ __forceinline__ bool tri_test_raw(const float4 A, const float4 Bv, const float4 C, float ox, float oy, float oz, float dx, float dy,
                                          float dz, float& t, float& u, float& v) {
     const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
     const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
-    const float rx = __fsub_rn(ox, A.x), ry = __fsub_rn(oy, A.y), rz = __fsub_rn(oz, A.z);
-    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
-    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
-    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
-    const float qx = __fsub_rn(__fmul_rn(ry, dz), __fmul_rn(rz, dy));
-    const float qy = __fsub_rn(__fmul_rn(rz, dx), __fmul_rn(rx, dz));
-    const float qz = __fsub_rn(__fmul_rn(rx, dy), __fmul_rn(ry, dx));
-    const float D = __fdiv_rn(1.0f, dot_rn(dx, dy, dz, nx, ny, nz));
-    u = __fmul_rn(D, -dot_rn(qx, qy, qz, e2x, e2y, e2z));
-    v = __fmul_rn(D, dot_rn(qx, qy, qz, e1x, e1y, e1z));
-    t = __fmul_rn(D, -dot_rn(nx, ny, nz, rx, ry, rz));
-    return !(u < 0.0f || u > 1.0f || v < 0.0f || __fadd_rn(u, v) > 1.0f || t < 0.0f);
+    float nx, ny, nz;
+    cross_ref(e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz);
+    return tri_test(A, make_float4(e1x, e1y, e1z, 0.f), make_float4(e2x, e2y, e2z, 0.f), make_float4(nx, ny, nz, 0.f), ox, oy, oz, dx, dy, dz,
+                    t, u, v);
 }
 
 __global__ void __launch_bounds__(256) precompute_tri_kernel(const float4* __restrict__ tris, float4* __restrict__ pre, int64_t n_tris) {
@@ -322,9 +338,8 @@ __global__ void __launch_bounds__(256) precompute_tri_kernel(const float4* __res
     const float4 A = tris[3 * p], Bv = tris[3 * p + 1], C = tris[3 * p + 2];
     const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
     const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
-    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
-    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
-    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    float nx, ny, nz;
+    cross_ref(e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz);
     pre[4 * p] = A;
     pre[4 * p + 1] = make_float4(e1x, e1y, e1z, 0.f);
     pre[4 * p + 2] = make_float4(e2x, e2y, e2z, 0.f);
@@ -572,25 +587,18 @@ __global__ void __launch_bounds__(256) shells_expand_kernel(const Layer* __restr
     if (r >= n_rays) return;
     const Layer L = layers[layer];
     const float t = depth[r];
-    positions[3 * r] = __fadd_rn(rays_o[3 * r], __fmul_rn(t, rays_d[3 * r]));
-    positions[3 * r + 1] = __fadd_rn(rays_o[3 * r + 1], __fmul_rn(t, rays_d[3 * r + 1]));
-    positions[3 * r + 2] = __fadd_rn(rays_o[3 * r + 2], __fmul_rn(t, rays_d[3 * r + 2]));
+    positions[3 * r] = __fmaf_rn(rays_d[3 * r], t, rays_o[3 * r]);  // ray_o + depth * ray_d, contracted by nvcc in the reference kernel
+    positions[3 * r + 1] = __fmaf_rn(rays_d[3 * r + 1], t, rays_o[3 * r + 1]);
+    positions[3 * r + 2] = __fmaf_rn(rays_d[3 * r + 2], t, rays_o[3 * r + 2]);
     const int ti = tri[r];
     if (ti >= 0) {
         const int64_t p = L.orig_to_bvh[ti];
         const float4 A = L.tris[3 * p], Bv = L.tris[3 * p + 1], C = L.tris[3 * p + 2];
         const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
         const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
-        float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
-        float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
-        float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
-        const float zz = dot_rn(nx, ny, nz, nx, ny, nz);
-        if (zz > 0.0f) {  // Eigen normalized(): v / sqrt(v.v), unchanged for the zero vector
-            const float s = __fsqrt_rn(zz);
-            nx = __fdiv_rn(nx, s);
-            ny = __fdiv_rn(ny, s);
-            nz = __fdiv_rn(nz, s);
-        }
+        float nx, ny, nz;
+        cross_ref(e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz);
+        normalize_ref(nx, ny, nz);
         normals[3 * r] = nx;
         normals[3 * r + 1] = ny;
         normals[3 * r + 2] = nz;
@@ -620,16 +628,9 @@ __global__ void __launch_bounds__(256) shells_normals_kernel(const Layer* __rest
     const float4 A = L.tris[3 * p], Bv = L.tris[3 * p + 1], C = L.tris[3 * p + 2];
     const float e1x = __fsub_rn(Bv.x, A.x), e1y = __fsub_rn(Bv.y, A.y), e1z = __fsub_rn(Bv.z, A.z);
     const float e2x = __fsub_rn(C.x, A.x), e2y = __fsub_rn(C.y, A.y), e2z = __fsub_rn(C.z, A.z);
-    float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
-    float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
-    float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
-    const float zz = dot_rn(nx, ny, nz, nx, ny, nz);
-    if (zz > 0.0f) {
-        const float sq = __fsqrt_rn(zz);
-        nx = __fdiv_rn(nx, sq);
-        ny = __fdiv_rn(ny, sq);
-        nz = __fdiv_rn(nz, sq);
-    }
+    float nx, ny, nz;
+    cross_ref(e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz);
+    normalize_ref(nx, ny, nz);
     normals[3 * s] = nx;
     normals[3 * s + 1] = ny;
     normals[3 * s + 2] = nz;
