@@ -97,7 +97,7 @@ def build_ref_permuto(force: bool = False):
 SAMPLER_SRC = HERE / "ref_sampler_harness.cu"
 SAMPLER_LIB = REF_DIR / "libsampler_ref.so"
 SAMPLER_HDRS = [REFERENCE / "kernels/volsurfs/RaySamplerGPU.cuh", REFERENCE / "kernels/volsurfs/OccupancyGridGPU.cuh",
-                REFERENCE / "kernels/volsurfs/occ_grid_helpers.h"]
+                REFERENCE / "kernels/volsurfs/occ_grid_helpers.h", REFERENCE / "kernels/volsurfs/RaySamplesPackedGPU.cuh"]
 
 
 def sampler_ref_available() -> bool:

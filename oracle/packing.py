@@ -93,11 +93,11 @@ class RaySamplesPackedNP:
             max_dt = self.ray_max_dt[r, 0]
             z = self.samples_z[s:e, 0]
             if n >= 2:
-                self.samples_dt[s:e - 1, 0] = np.clip(z[1:] - z[:-1], np.float32(0), max_dt)
+                self.samples_dt[s:e - 1, 0] = np.maximum(np.float32(0), np.minimum(z[1:] - z[:-1], max_dt))  # clamp = fmaxf(a, fminf(f, b))
             if is_background:
                 self.samples_dt[e - 1, 0] = np.float32(1e10)
             else:
-                self.samples_dt[e - 1, 0] = np.clip(self.ray_exit[r, 0] - z[-1], np.float32(0), max_dt)
+                self.samples_dt[e - 1, 0] = np.maximum(np.float32(0), np.minimum(self.ray_exit[r, 0] - z[-1], max_dt))
         self.has_dt = True
 
 

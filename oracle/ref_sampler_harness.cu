@@ -4,6 +4,7 @@
 //   /root/reference/kernels/volsurfs/RaySamplerGPU.cuh        (compute_samples_bg / _fg / _fg_in_grid_occupied_regions)
 //   /root/reference/kernels/volsurfs/OccupancyGridGPU.cuh     (get_rays_t_near_t_far, check_occupancy)
 //   /root/reference/kernels/volsurfs/occ_grid_helpers.h       (pos_to_lin_idx, distance_to_next_voxel; pulled in by the two above)
+//   /root/reference/kernels/volsurfs/RaySamplesPackedGPU.cuh  (update_dt_gpu, compact_to_valid_samples_gpu)
 // unmodified, where they lie, and launches them with the launch shape of src/RaySampler.cu / src/OccupancyGrid.cu
 // (blocks = div_round_up(n, 256), 256 threads, legacy stream, device synchronise).
 // Those headers use Eigen::Vector3f only as a 3-float parameter type (x(), y(), z()); Eigen is not installed in this image and cannot
@@ -28,6 +29,8 @@ struct Vector3f {
 #include "volsurfs/RaySamplerGPU.cuh"
 #undef BLOCK_SIZE
 #include "volsurfs/OccupancyGridGPU.cuh"
+#undef BLOCK_SIZE
+#include "volsurfs/RaySamplesPackedGPU.cuh"  // update_dt_gpu (:14-88), compact_to_valid_samples_gpu (:172-257)
 
 namespace {
 
@@ -69,7 +72,30 @@ inline pcg32 make_rng(uint64_t state, uint64_t inc) {
 
 extern "C" {
 
-int ref_sampler_abi_version() { return 1; }
+int ref_sampler_abi_version() { return 2; }
+
+// RaySamplesPacked.cu:188-273 (compact_to_valid_samples): the kernel launch; `out_indices_start` is the exclusive prefix sum the reference
+// forms with torch (`nr_samples_per_ray.cumsum(0).to(int32)` shifted by one, :218-221) — the caller passes it.  Outputs preset by the caller
+// as the RaySamplesPacked constructor does (-1 everywhere, RaySamplesPacked.cu:13-48): rays without samples keep (-1,-1).
+int ref_compact_to_valid_samples(int nr_rays, int max_in, int max_out, int values_dim, const int* sidx, const float* s3d, const float* sdirs,
+                                 const float* sz, const float* sdt, const float* sval, const int* se, const int* out_start, int* o_sidx,
+                                 float* o_s3d, float* o_sdirs, float* o_sz, float* o_sdt, float* o_sval, int* o_se) {
+    RaySamplesPackedGPU::compact_to_valid_samples_gpu<<<grid_for(nr_rays), 256>>>(
+        nr_rays, max_in, max_out, values_dim, acc2(sidx, max_in, 1), acc2(s3d, max_in, 3), acc2(sdirs, max_in, 3), acc2(sz, max_in, 1),
+        acc2(sdt, max_in, 1), acc2(sval, max_in, values_dim), acc2(se, nr_rays, 2), acc1(out_start, nr_rays), acc2(o_sidx, max_out, 1),
+        acc2(o_s3d, max_out, 3), acc2(o_sdirs, max_out, 3), acc2(o_sz, max_out, 1), acc2(o_sdt, max_out, 1), acc2(o_sval, max_out, values_dim),
+        acc2(o_se, nr_rays, 2));
+    return finish();
+}
+
+// RaySamplesPacked.cu:396-461 (update_dt): writes samples_dt in place
+int ref_update_dt(int nr_rays, int nr_samples, int is_background, const float* ray_max_dt, const float* ray_exit, const float* sz, const int* se,
+                  float* sdt) {
+    RaySamplesPackedGPU::update_dt_gpu<<<grid_for(nr_rays), 256>>>(nr_rays, nr_samples, is_background != 0, acc2(ray_max_dt, nr_rays, 1),
+                                                                  acc2(ray_exit, nr_rays, 1), acc2(sz, nr_samples, 1), acc2(se, nr_rays, 2),
+                                                                  acc2(sdt, nr_samples, 1));
+    return finish();
+}
 
 // RaySampler.cu:72-157
 int ref_samples_bg(const float* rays_o, const float* rays_d, const float* t_start, float t_far, int nr_samples_per_ray, uint64_t rng_state,

@@ -204,8 +204,13 @@ def test_next_ops_sdf2alpha_median_cdf():
     cdf = VR.compute_cdf(rsp, w.cuda())
     assert np.array_equal(cdf.cpu().numpy(), oc.packed_compute_cdf(sen, w.numpy()))
     for thr in (0.5, 0.9, 2.0):  # 2.0 is never reached: exercises the reference's fallback index
-        md = VR.median_depth_over_rays(rsp, w.cuda(), thr)
-        assert np.array_equal(md.cpu().numpy(), oc.packed_median_depth(sen, p["z"].numpy(), w.numpy(), thr, ref_bug=True)), thr
+        for bug in (True, False):  # reference_bugs: the fallback reads samples_z[n-1] (VolumeRenderingGPU.cuh:407) / samples_z[start+n-1]
+            VR.reference_bugs = bug
+            try:
+                md = VR.median_depth_over_rays(rsp, w.cuda(), thr)
+            finally:
+                VR.reference_bugs = False
+            assert np.array_equal(md.cpu().numpy(), oc.packed_median_depth(sen, p["z"].numpy(), w.numpy(), thr, ref_bug=bug)), (thr, bug)
     rsp.has_dt = False
     with pytest.raises(RuntimeError):
         VR.sdf2alpha(rsp, sdf.cuda(), beta.cuda())

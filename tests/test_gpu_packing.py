@@ -7,6 +7,47 @@ from oracle.packing import RaySamplesPackedNP, pack_layer_hits
 
 pytestmark = pytest.mark.gpu
 
+import ctypes
+from pathlib import Path
+
+REF_PATH = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libsampler_ref.so"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    """the reference's own RaySamplesPackedGPU.cuh kernels (compiled where they lie, oracle/ref_sampler_harness.cu)"""
+    if not REF_PATH.exists():
+        pytest.skip("oracle/_ref/libsampler_ref.so not built (python -m oracle.build where /root/reference is mounted)")
+    lib = ctypes.CDLL(str(REF_PATH))
+    assert lib.ref_sampler_abi_version() == 2
+    return lib
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ref_compact(ref, rsp):
+    """src/RaySamplesPacked.cu:188-273 around the reference's kernel: fresh packet (constructor fills of :13-48), torch prefix sum
+    (:218-221), compact_to_valid_samples_gpu"""
+    from volsurfs_b200.volsurfs import RaySamplesPacked
+
+    n = rsp.get_nr_rays()
+    cnt = (rsp.ray_start_end_idx[:, 1] - rsp.ray_start_end_idx[:, 0])
+    total = int(cnt.sum().item())
+    vd = rsp.samples_values.shape[1]
+    out = RaySamplesPacked(n, total, 0, vd)
+    if total == 0:
+        return out
+    start = cnt.cumsum(0).to(torch.int32)
+    start = torch.cat([torch.zeros(1, dtype=torch.int32, device=start.device), start[:-1]]).contiguous()
+    rc = ref.ref_compact_to_valid_samples(n, rsp.get_max_nr_samples(), total, vd, P(rsp.samples_idx), P(rsp.samples_3d), P(rsp.samples_dirs),
+                                          P(rsp.samples_z), P(rsp.samples_dt), P(rsp.samples_values), P(rsp.ray_start_end_idx), P(start),
+                                          P(out.samples_idx), P(out.samples_3d), P(out.samples_dirs), P(out.samples_z), P(out.samples_dt),
+                                          P(out.samples_values), P(out.ray_start_end_idx))
+    assert rc == 0
+    return out
+
 
 def _uncompacted(n_rays, M, seed, values_dim=2, p_empty=0.1):
     """slot layout of RaySamplerGPU.cuh:206-271: ray r owns slots [r*M, r*M+cnt_r)"""
@@ -49,6 +90,41 @@ def test_compact_to_valid_samples_bit_exact(n_rays, M):
         assert np.array_equal(getattr(got, name).cpu().numpy(), getattr(want, name)), name
     with pytest.raises(RuntimeError):
         got.compact_to_valid_samples()  # CHECK(!is_compacted), RaySamplesPacked.cu:193
+
+
+@pytest.mark.parametrize("n_rays,M", [(1, 4), (2048, 5), (5000, 9), (70001, 3), (300, 96)])
+def test_compact_equals_reference_kernel(ref, n_rays, M):
+    """product == the reference's compact_to_valid_samples_gpu (RaySamplesPackedGPU.cuh:172-257), every array bit for bit"""
+    src = _to_gpu(_uncompacted(n_rays, M, seed=n_rays + M))
+    src.samples_idx = torch.arange(n_rays * M, dtype=torch.int32, device="cuda").reshape(-1, 1)  # RaySamplesPacked.cu:20
+    want = ref_compact(ref, src)
+    got = src.compact_to_valid_samples()
+    assert got.get_max_nr_samples() == want.get_max_nr_samples()
+    for name in ("ray_start_end_idx", "samples_idx", "samples_3d", "samples_dirs", "samples_z", "samples_dt", "samples_values"):
+        assert torch.equal(getattr(got, name), getattr(want, name)), name
+    empty = (src.ray_start_end_idx[:, 1] - src.ray_start_end_idx[:, 0]) == 0
+    assert bool((got.ray_start_end_idx[empty] == -1).all())                                     # RaySamplesPackedGPU.cuh:211-212
+
+
+@pytest.mark.parametrize("n_rays,M", [(1, 4), (2048, 5), (5000, 9), (70001, 3), (300, 96)])
+@pytest.mark.parametrize("is_background", [False, True])
+def test_update_dt_equals_reference_kernel(ref, n_rays, M, is_background):
+    """product == the reference's update_dt_gpu (RaySamplesPackedGPU.cuh:14-88); a third of the rays carry the constructor's
+    ray_max_dt = -1 (importance_sample / init_with_one_sample_per_ray packets): clamp(x, 0, -1) = fmaxf(0, fminf(x, -1)) = 0"""
+    rsp = _to_gpu(_uncompacted(n_rays, M, seed=7 * n_rays + M)).compact_to_valid_samples()
+    if rsp.get_total_nr_samples() == 0:
+        pytest.skip("no samples")
+    rsp.samples_z = torch.sort(rsp.samples_z.abs(), dim=0).values.contiguous()      # increasing along every ray
+    rsp.ray_exit = rsp.ray_exit.abs() + rsp.samples_z.max() * torch.rand_like(rsp.ray_exit)
+    rsp.ray_max_dt = (rsp.ray_max_dt.abs() * 0.02).contiguous()
+    rsp.ray_max_dt[::3] = -1.0
+    want = torch.full_like(rsp.samples_dt, -1.0)
+    rc = ref.ref_update_dt(n_rays, rsp.get_total_nr_samples(), int(is_background), P(rsp.ray_max_dt), P(rsp.ray_exit), P(rsp.samples_z),
+                           P(rsp.ray_start_end_idx), P(want))
+    assert rc == 0
+    rsp.update_dt(is_background)
+    assert torch.equal(rsp.samples_dt, want)
+    assert float(want.min()) >= 0.0
 
 
 def test_compact_all_empty():

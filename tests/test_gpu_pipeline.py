@@ -121,3 +121,37 @@ def test_encoded_renderer_matches_the_autograd_path():
         e2 = grad_err(got["grad_lattice_" + name].cpu().numpy(), enc.encoder.lattice_values.grad.cpu().numpy())
         print(name, "head grad_err %.2e lattice grad_err %.2e" % (e1, e2))
         assert e1 < 1e-4 and e2 < 1e-4
+
+
+def test_full_path_outputs_and_gradients_vs_oracle_chain():
+    """the legacy-head step (trace -> pack -> 2 heads -> composite -> L1 -> composite bwd -> heads bwd) against the oracle chain of
+    tests/fullpath_oracle.py (C tracer in the reference kernel's arithmetic -> numpy packing -> fp32 torch heads -> dense compositing ->
+    autograd): packing bit-exact, image <= 1e-4 abs, per-sample colour/alpha <= 2e-4 abs (fp16 operands, fp32 accumulate: the bar of
+    tests/test_gpu_mlp.py), every gradient <= 3e-2 under grad_err (observed ~3e-3)"""
+    import numpy as np
+
+    from conftest import grad_err
+    from fullpath_oracle import oracle_step
+    from volsurfs_b200.pipeline import make_synthetic_renderer
+    from volsurfs_b200.synthetic import camera_rays
+
+    renderer, meshes = make_synthetic_renderer(K=5, n_lat=64, n_lon=64, hidden=(128, 128, 64))
+    o, d = camera_rays(80, 80)
+    g = torch.Generator().manual_seed(11)
+    feats = torch.rand(o.shape[0] * 5, 51, generator=g) * 2 - 1
+    gt = torch.rand(o.shape[0], 3, generator=g)
+    out = renderer.render_fwd_bwd(o.cuda(), d.cuda(), feats.cuda(), gt.cuda())
+    want = oracle_step(meshes, o, d, feats, renderer.rgb_head, renderer.alpha_head, gt)
+    S = want["n_samples"]
+    rsp = out["ray_samples_packed"]
+    assert int(rsp.total_dev.item()) == S and S > 3000
+    assert np.array_equal(rsp.ray_start_end_idx.cpu().numpy(), want["packet"].ray_start_end_idx)
+    assert np.array_equal(rsp.samples_3d[:S].cpu().numpy(), want["packet"].samples_3d)
+    assert float((out["samples_rgb"][:S].cpu() - want["samples_rgb"]).abs().max()) < 2e-4
+    assert float((out["samples_alpha"][:S].cpu() - want["samples_alpha"]).abs().max()) < 2e-4
+    assert float((out["rgb"].cpu() - want["rgb"]).abs().max()) < 1e-4
+    assert abs(float(out["loss"]) - float(want["loss"])) < 1e-5
+    errs = {k: grad_err(out[k][:S].cpu().numpy() if k.startswith("d_features") else out[k].cpu().numpy(), want[k].numpy())
+            for k in ("grad_rgb", "grad_alpha", "d_features_rgb", "d_features_alpha")}
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v < 3e-2 for v in errs.values()), errs

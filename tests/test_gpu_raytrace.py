@@ -193,3 +193,36 @@ def test_reference_meshes_vs_reference_kernel(name):
     # and the host-path golden differs from the device result only in the last bits (FMA contraction), same triangles
     same = torch.from_numpy(h["triangles_id"]).cuda() == want["triangles_id"]
     assert float(same.float().mean()) > 0.999
+
+
+def test_layer_bookkeeping_vs_reference_lines_golden():
+    """trace -> pack -> texture coordinates against tests/golden/layers_k3.npz, recorded by exec'ing volsurfs_py/methods/volsurfs.py:449-516
+    (the reference's dense surfs_hits / surfs_points / surfs_normals / surfs_uvs buffers): the packed samples, scattered back to
+    [N,K,.] by (ray, layer), reproduce every buffer bit for bit; misses stay zero; order inside a ray = descending mesh index"""
+    from conftest import GOLDEN
+    from volsurfs_b200.raytracer import ShellTracer
+    from volsurfs_b200.synthetic import shell_face_uvs
+
+    g = np.load(GOLDEN / "layers_k3.npz")
+    K, n_lat, n_lon, _ = (int(x) for x in g["params"])
+    meshes = shell_meshes(K=K, n_lat=n_lat, n_lon=n_lon)
+    o, d = torch.from_numpy(g["rays_o"]).cuda(), torch.from_numpy(g["rays_d"]).cuda()
+    tracer = ShellTracer(meshes)
+    tracer.set_face_uvs([shell_face_uvs(n_lat, n_lon)] * K)
+    rsp = tracer.render_samples(o, d, exact_size=True)
+    uv = tracer.sample_uvs(rsp)
+    N = o.shape[0]
+    S = rsp.get_total_nr_samples()
+    ray = (rsp.samples_idx[:S, 0] // K).long()
+    lay = rsp.samples_layer[:S].long()
+    hits = torch.zeros(N, K, dtype=torch.bool, device="cuda")
+    hits[ray, lay] = True
+    assert np.array_equal(hits.cpu().numpy(), g["surfs_hits"])
+    for name, src, width in (("surfs_points", rsp.samples_3d[:S], 3), ("surfs_normals", rsp.samples_normals[:S], 3), ("surfs_uvs", uv[:S], 2)):
+        dense = torch.zeros(N, K, width, device="cuda")
+        dense[ray, lay] = src
+        assert np.array_equal(dense.cpu().numpy(), g[name]), name
+    se = rsp.ray_start_end_idx.cpu().numpy()
+    lay_np = lay.cpu().numpy()
+    for r in np.nonzero(se[:, 1] - se[:, 0] > 1)[0][:500]:
+        assert np.all(np.diff(lay_np[se[r, 0]:se[r, 1]]) < 0)       # outer -> inner (volsurfs.py:601-603)

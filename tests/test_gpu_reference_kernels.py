@@ -212,7 +212,11 @@ def test_sdf2alpha_median_cdf_vs_reference_kernels(ref):
     for thr in (0.5, 0.9, 2.0):
         md_r = torch.zeros(N, 1, device="cuda")
         _ok(ref.ref_median_depth(P(sed), P(rsp.samples_z), P(w), ctypes.c_float(thr), P(md_r), N, S))
-        md = VR.median_depth_over_rays(rsp, w, thr)
+        VR.reference_bugs = True   # the reference's fallback reads samples_z[nr_samples - 1] without idx_start (VolumeRenderingGPU.cuh:407)
+        try:
+            md = VR.median_depth_over_rays(rsp, w, thr)
+        finally:
+            VR.reference_bugs = False
         assert np.array_equal(md.cpu().numpy(), md_r.cpu().numpy()), thr
         assert np.array_equal(oc.packed_median_depth(sen, p["z"].numpy(), w.cpu().numpy(), thr, ref_bug=True), md_r.cpu().numpy())
 

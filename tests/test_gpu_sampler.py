@@ -113,7 +113,7 @@ def ref():
     if not REF_PATH.exists():
         pytest.skip("oracle/_ref/libsampler_ref.so not built (python -m oracle.build where /root/reference is mounted)")
     lib = ctypes.CDLL(str(REF_PATH))
-    assert lib.ref_sampler_abi_version() == 1
+    assert lib.ref_sampler_abi_version() == 2
     return lib
 
 
@@ -139,7 +139,12 @@ def _ref_fg(ref, sc, t, min_dist, min_nr, max_nr, jitter, use_grid):
     else:
         code = ref.ref_samples_fg(*common, *outs)
     assert code == 0, f"reference harness returned CUDA error {code}"
-    return unc.compact_to_valid_samples()
+    from test_gpu_packing import ref_compact
+
+    out = ref_compact(ref, unc)   # the reference's own compaction kernel (RaySamplesPackedGPU.cuh:172-257), not the product's
+    out.ray_o, out.ray_d, out.ray_enter, out.ray_exit, out.ray_max_dt = unc.ray_o, unc.ray_d, unc.ray_enter, unc.ray_exit, unc.ray_max_dt
+    out.is_compacted = True
+    return out
 
 
 @pytest.mark.parametrize("jitter", [False, True])

@@ -124,3 +124,32 @@ def test_device_contract_differs_only_in_the_last_bits():
     h = same & a["is_hit"]
     assert np.max(np.abs(a["depth"][h] - b["depth"][h]) / a["depth"][h]) < 1e-5
     assert not np.array_equal(a["depth"], b["depth"])                    # the contraction is visible
+
+
+def test_packing_oracle_vs_reference_lines_golden():
+    """oracle/packing.py:pack_layer_hits (the packed form of the K-layer bookkeeping) against tests/golden/layers_k3.npz, recorded by exec'ing
+    volsurfs_py/methods/volsurfs.py:449-516: scattering the packed samples back by (ray, layer) gives the reference's dense buffers"""
+    from conftest import GOLDEN
+    from oracle.packing import pack_layer_hits
+
+    g = np.load(GOLDEN / "layers_k3.npz")
+    K, n_lat, n_lon, _ = (int(x) for x in g["params"])
+    meshes = shell_meshes(K=K, n_lat=n_lat, n_lon=n_lon)
+    tr = OracleRayTracer(meshes, contract="device").trace_layers(g["rays_o"], g["rays_d"])
+    assert np.array_equal(tr["is_hit"].T, g["surfs_hits"])
+    unc, layer_of_slot = pack_layer_hits(g["rays_o"], g["rays_d"], tr["is_hit"].T, tr["depth"].T)
+    rsp = unc.compact_to_valid_samples()
+    ray = rsp.samples_idx[:, 0] // K
+    lay = layer_of_slot[rsp.samples_idx[:, 0]]
+    N = g["rays_o"].shape[0]
+    pts = np.zeros((N, K, 3), np.float32)
+    pts[ray, lay] = rsp.samples_3d
+    assert np.array_equal(pts, g["surfs_points"])
+    nrm = np.zeros((N, K, 3), np.float32)
+    normals = np.stack([r["normals"] for r in tr["per_mesh"]])
+    nrm[ray, lay] = normals[lay, ray]
+    assert np.array_equal(nrm, g["surfs_normals"])
+    se = rsp.ray_start_end_idx
+    cnt = g["surfs_hits"].sum(1)
+    assert np.array_equal(se[:, 1] - se[:, 0], cnt)
+    assert np.all(se[cnt == 0] == -1)

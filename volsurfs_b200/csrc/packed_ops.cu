@@ -278,11 +278,11 @@ __global__ void __launch_bounds__(kThreads) update_dt_kernel(const int32_t* __re
             float cur = ld_stream(z + s);
             float out;
             if (i < n - 1) {
-                out = fminf(fmaxf(__fsub_rn(__ldg(z + s + 1), cur), 0.f), max_dt);
+                out = fmaxf(0.f, fminf(__fsub_rn(__ldg(z + s + 1), cur), max_dt));  // helper_math clamp(f, a, b) = fmaxf(a, fminf(f, b))
             } else if (is_background) {
                 out = 1e10f;
             } else {
-                out = fminf(fmaxf(__fsub_rn(t_exit, cur), 0.f), max_dt);
+                out = fmaxf(0.f, fminf(__fsub_rn(t_exit, cur), max_dt));
             }
             st_stream(dt + s, out);
         }

@@ -30,6 +30,10 @@
 
 namespace vs {
 
+// hard cap on the voxel marches below: a march through an n^3 grid takes O(n) steps (a few thousand with the +1e-6 nudges); the cap only
+// ends marches whose t no longer advances in fp32 (|origin| huge against the step, infinite t_exit) instead of hanging the stream
+constexpr int kMaxMarchSteps = 1 << 20;
+
 // ---- pcg32 (kernels/volsurfs/pcg32.h:32-34,60-70,84-95,158-180) ------------------------------------------------------------------
 struct Pcg {
     uint64_t state, inc;
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(128) occgrid_first_sample_kernel(const float* 
     const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
     const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
     float t = __ldg(t_entry + ray);
-    while (t < t_exit) {
+    for (int guard = 0; t < t_exit && guard < kMaxMarchSteps; ++guard) {
         const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
         if (!in_grid(p.voxel, g)) break;
         t = __fadd_rn(__fadd_rn(t, step_from_unit(p.ux, p.uy, p.uz, dx, dy, dz, g)), 1e-6f);
@@ -524,13 +528,13 @@ __global__ void __launch_bounds__(128) occgrid_advance_kernel(const float* __res
     const float dx = __ldg(dirs + 3 * i), dy = __ldg(dirs + 3 * i + 1), dz = __ldg(dirs + 3 * i + 2);
     float t = 0.f, prec_t = 0.f;
     bool inside = true;
-    while (true) {
+    for (int guard = 0;; ++guard) {
         const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
         // Deviation: the reference's index clamps coordinates below the grid (and NaN) to voxel 0 of that axis, so a point leaving through
         // a lower face is marched on for ever (its kernel does not return; the call site, utils/sphere_tracing.py:131, is commented
         // out).  Here a position below the grid ends the march like one above it.
         const bool below = !(__fadd_rn(p.ux, 0.5f) >= 0.f) || !(__fadd_rn(p.uy, 0.5f) >= 0.f) || !(__fadd_rn(p.uz, 0.5f) >= 0.f);
-        if (below || !in_grid(p.voxel, g)) {
+        if (below || !in_grid(p.voxel, g) || guard >= kMaxMarchSteps) {  // the cap: t stopped advancing in fp32 (huge |origin|, tiny step)
             inside = false;
             out[3 * i] = __fmaf_rn(prec_t, dx, ox), out[3 * i + 1] = __fmaf_rn(prec_t, dy, oy), out[3 * i + 2] = __fmaf_rn(prec_t, dz, oz);
             break;
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(128) occgrid_t_near_t_far_kernel(const float* 
     const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
     float near = t_start, far = t_start, t = t_start;
     bool first = true;
-    while (t < t_exit) {
+    for (int guard = 0; t < t_exit && guard < kMaxMarchSteps; ++guard) {
         const Probe p = probe(t, ox, oy, oz, dx, dy, dz, g);
         if (!in_grid(p.voxel, g)) break;
         const bool occ = occupied(p.voxel, g);

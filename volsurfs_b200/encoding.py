@@ -65,6 +65,10 @@ class _PermutoFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_oob):
         lattice_values, positions = ctx.saved_tensors
+        if grad_out is None:  # only the out-of-bounds mask was used downstream
+            return (None, torch.zeros_like(lattice_values) if ctx.needs_input_grad[1] else None,
+                    torch.zeros_like(positions) if ctx.needs_input_grad[2] else None, None, None, None, None)
+        grad_out = grad_out.contiguous()
         d_lat, d_pos = ctx.enc._launch_backward(lattice_values, positions, ctx.window, grad_out, ctx.bb_sides, ctx.n_valid_dev,
                                                 want_lattice=ctx.needs_input_grad[1], want_positions=ctx.needs_input_grad[2])
         return None, d_lat, d_pos, None, None, None, None
@@ -198,6 +202,8 @@ class PermutoHashEncoder:
         if bb_sides is not None:
             if isinstance(bb_sides, (float, int)):
                 bb_sides = [float(bb_sides)] * input_dim
+            if isinstance(bb_sides, torch.Tensor):       # the reference accepts tensors (and moves them to CUDA): permutohash.py:30-36
+                bb_sides = bb_sides.detach().cpu().tolist()
             bb_sides = [float(b) for b in np.asarray(bb_sides, dtype=np.float32).reshape(-1)]
         self.bb_sides = bb_sides                     # host floats: they parameterise the kernel, no device tensor needed
         self.c2f = Coarse2Fine(nr_levels)

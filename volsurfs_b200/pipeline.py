@@ -417,48 +417,3 @@ def make_synthetic_renderer(K=5, n_lat=224, n_lon=224, hidden=(128, 128, 64), po
     rgb_head = AppearanceHead(pos_dim, hidden, 3, 3, False, "gelu", False).cuda()
     alpha_head = AppearanceHead(pos_dim, hidden, 1, 3, False, "gelu", True).cuda()
     return ShellRenderer(tracer, rgb_head, alpha_head), meshes
-
-
-def smoke():
-    """small full-path pass on cuda:0 checked against the oracle (called by __graft_entry__.smoke)"""
-    import numpy as np
-
-    from oracle import appearance as oa
-    from oracle import compositing as oc
-    from oracle.packing import pack_layer_hits
-    from oracle.raytrace import OracleRayTracer
-
-    from . import _lib
-    from .synthetic import camera_rays
-
-    before = _lib.lib().vs_launch_count()
-    renderer, meshes = make_synthetic_renderer(K=5, n_lat=64, n_lon=64, hidden=(64, 64, 64))
-    o, d = camera_rays(96, 96)
-    N, K = o.shape[0], 5
-    g = torch.Generator().manual_seed(5)
-    feats = torch.rand(N * K, 51, generator=g) * 2 - 1
-    out = renderer.render(o.cuda(), d.cuda(), feats.cuda())
-    torch.cuda.synchronize()
-    # oracle: trace -> pack -> heads -> composite
-    lay = OracleRayTracer(meshes).trace_layers(o.numpy(), d.numpy(), mode="bvh")
-    unc, _ = pack_layer_hits(o.numpy(), d.numpy(), lay["is_hit"].T, lay["depth"].T)
-    want = unc.compact_to_valid_samples()
-    S = want.get_total_nr_samples()
-    rsp = out["ray_samples_packed"]
-    assert int(rsp.total_dev.item()) == S
-    assert np.array_equal(rsp.ray_start_end_idx.cpu().numpy(), want.ray_start_end_idx), "packing offsets differ"
-    assert np.array_equal(rsp.samples_z[:S].cpu().numpy(), want.samples_z), "hit depths differ"
-    normals = rsp.samples_normals[:S].cpu()
-    dirs = torch.from_numpy(want.samples_dirs)
-
-    def params(head):
-        return [l.weight.detach().cpu() for l in head.layers], [l.bias.detach().cpu() for l in head.layers]
-
-    rgb_o = oa.head_forward(feats[:S], dirs, normals, *params(renderer.rgb_head))
-    alpha_o = oa.alpha_decay(oa.head_forward(feats[:S], dirs, normals, *params(renderer.alpha_head)), dirs, normals)
-    comp = oc.fused_composite_forward(want.ray_start_end_idx, alpha_o.numpy(), rgb_o.numpy(), want.samples_z)
-    pred_o = comp["rgb"] + comp["bgT"] * 1.0
-    err = float(np.abs(out["rgb"].cpu().numpy() - pred_o).max())
-    launches = _lib.lib().vs_launch_count() - before
-    print(f"[smoke] full path {N} rays x {K} shells: {S} hits, image max abs err vs oracle {err:.2e}, kernels launched {launches}")
-    assert err < 1e-2, err

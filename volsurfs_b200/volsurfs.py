@@ -286,7 +286,8 @@ class RaySamplesPacked:
 class VolumeRendering:
     """Static packed-sample operators (include/volsurfs/VolumeRendering.cuh:19-97, bound at PyBridge.cxx:113-129)."""
 
-    #: reproduce the reference's integrate_with_weights_3d_backward z-channel bug (VolumeRenderingGPU.cuh:1021)
+    #: True reproduces the reference's two indexing bugs: integrate_with_weights_3d_backward reads channel [1] twice
+    #: (VolumeRenderingGPU.cuh:1021) and median_depth_over_rays' fallback reads samples_z[nr_samples-1] without idx_start (:407)
     reference_bugs = False
 
     @staticmethod
@@ -298,11 +299,21 @@ class VolumeRendering:
             raise RuntimeError("ray_start_end_idx must be an int32 CUDA tensor of shape [nr_rays, 2]")
         return se.contiguous(), int(se.shape[0])
 
+    @staticmethod
+    def _rows(rsp: RaySamplesPacked, *tensors):
+        """per-sample tensors must cover the packet's sample slots (the kernels index start+i without a bound; the reference guards
+        idx >= max_nr_samples in its loops)"""
+        need = rsp.get_max_nr_samples()
+        for t in tensors:
+            if t is not None and t.shape[0] < need:
+                raise RuntimeError(f"per-sample tensor has {t.shape[0]} rows, the packet addresses {need} samples")
+
     # ---- forward ops ---------------------------------------------------------------------------------------------
     @staticmethod
     def cumprod_one_minus_alpha_to_transmittance(ray_samples_packed, alpha_samples):
         se, n_rays = VolumeRendering._prep(ray_samples_packed, "cumprod")
         x = _f32c(alpha_samples, "alpha_samples", 1)
+        VolumeRendering._rows(ray_samples_packed, x)
         S = x.shape[0]
         T = torch.zeros((S, 1), dtype=torch.float32, device=x.device)
         bg = torch.empty((n_rays, 1), dtype=torch.float32, device=x.device)
@@ -316,6 +327,7 @@ class VolumeRendering:
         w = _f32c(weights, "weights", 1)
         if v.shape[0] != w.shape[0]:
             raise RuntimeError("values and weights must have the same number of samples")
+        VolumeRendering._rows(ray_samples_packed, v)
         out = torch.empty((n_rays, dim), dtype=torch.float32, device=v.device)
         check(_lib.lib().vs_integrate_fwd(ptr(se), ptr(v), ptr(w), ptr(out), dim, n_rays, v.shape[0], _stream()), "vs_integrate_fwd")
         return out
@@ -332,6 +344,7 @@ class VolumeRendering:
     def sum_over_rays(ray_samples_packed, samples_values):
         se, n_rays = VolumeRendering._prep(ray_samples_packed, "sum_over_rays")
         v = _f32c(samples_values, "samples_values")
+        VolumeRendering._rows(ray_samples_packed, v)
         d = v.shape[1]
         if not (d <= 3 or d == 32) or d == 0:
             raise RuntimeError(f"samples_values should have 1, 2, 3 or 32 values per sample, got {tuple(v.shape)}")
@@ -344,6 +357,7 @@ class VolumeRendering:
     def cumsum_over_rays(ray_samples_packed, samples_values, inverse):
         se, n_rays = VolumeRendering._prep(ray_samples_packed, "cumsum_over_rays")
         v = _f32c(samples_values, "samples_values", 1)
+        VolumeRendering._rows(ray_samples_packed, v)
         out = torch.zeros_like(v)
         check(_lib.lib().vs_cumsum(ptr(se), ptr(v), ptr(out), int(bool(inverse)), n_rays, v.shape[0], _stream()), "vs_cumsum")
         return out
@@ -357,6 +371,7 @@ class VolumeRendering:
         sdf = _f32c(samples_sdf, "samples_sdf", 1)
         beta = _f32c(logistic_beta, "logistic_beta", 1)
         dt = _f32c(ray_samples_packed.samples_dt, "samples_dt", 1)
+        VolumeRendering._rows(ray_samples_packed, sdf, beta, dt)
         alpha = torch.zeros_like(sdf)
         check(_lib.lib().vs_sdf2alpha(ptr(se), ptr(dt), ptr(sdf), ptr(beta), ptr(alpha), n_rays, sdf.shape[0], _stream()), "vs_sdf2alpha")
         return alpha
@@ -366,9 +381,11 @@ class VolumeRendering:
         se, n_rays = VolumeRendering._prep(ray_samples_packed, "median_depth")
         w = _f32c(samples_weights, "samples_weights", 1)
         z = _f32c(ray_samples_packed.samples_z, "samples_z", 1)
+        VolumeRendering._rows(ray_samples_packed, w, z)
         out = torch.zeros((n_rays, 1), dtype=torch.float32, device=w.device)
         check(
-            _lib.lib().vs_median_depth(ptr(se), ptr(z), ptr(w), float(threshold), ptr(out), n_rays, w.shape[0], 1, _stream()),
+            _lib.lib().vs_median_depth(ptr(se), ptr(z), ptr(w), float(threshold), ptr(out), n_rays, w.shape[0],
+                                       int(VolumeRendering.reference_bugs), _stream()),
             "vs_median_depth",
         )
         return out
@@ -377,6 +394,7 @@ class VolumeRendering:
     def compute_cdf(ray_samples_packed, samples_weights):
         se, n_rays = VolumeRendering._prep(ray_samples_packed, "compute_cdf")
         w = _f32c(samples_weights, "samples_weights", 1)
+        VolumeRendering._rows(ray_samples_packed, w)
         cdf = torch.zeros_like(w)
         check(_lib.lib().vs_compute_cdf(ptr(se), ptr(w), ptr(cdf), n_rays, w.shape[0], _stream()), "vs_compute_cdf")
         return cdf
@@ -567,6 +585,7 @@ class VolumeRendering:
         a = _f32c(alpha, "alpha", 1)
         c = _f32c(rgb, "rgb", 3)
         zz = _f32c(ray_samples_packed.samples_z if z is None else z, "z", 1)
+        VolumeRendering._rows(ray_samples_packed, a, c, zz)
         S = a.shape[0]
         if c.shape[0] != S or zz.shape[0] != S:
             raise RuntimeError("alpha, rgb and z must have the same number of samples")
@@ -594,6 +613,7 @@ class VolumeRendering:
         a = _f32c(alpha, "alpha", 1)
         c = _f32c(rgb, "rgb", 3)
         zz = _f32c(z, "z", 1)
+        VolumeRendering._rows(ray_samples_packed, a, c, zz)
         S = a.shape[0]
         gC = _f32c(g_rgb, "g_rgb", 3)
         gD = _f32c(g_depth, "g_depth", 1)

@@ -174,7 +174,18 @@ class VolumeRenderingNeRF(VolumeRendering):
 
 
 class VolumeRenderingNeuS(VolumeRendering):
-    """reference volume_rendering_modules.py:109-234 (the parts that sit on the packed operators)"""
+    """reference volume_rendering_modules.py:109-234"""
+
+    def compute_alphas_from_logistic_beta(self, ray_samples_packed, sdf, gradients, cos_anneal_ratio, logistic_beta, debug_ray_idx=None):
+        """NeuS discrete opacity (modules.py:115-216): section-point SDFs from the annealed ray/normal cosine, logistic CDF, ratio"""
+        dists = ray_samples_packed.samples_dt
+        true_cos = (ray_samples_packed.samples_dirs * gradients).sum(-1, keepdim=True)
+        relu = torch.nn.functional.relu
+        iter_cos = -(relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio) + relu(-true_cos) * cos_anneal_ratio)
+        # (iter_cos * dists) * 0.5, in that order: the rounding sequence of the reference expression
+        prev_cdf = torch.sigmoid((sdf - iter_cos * dists * 0.5) * logistic_beta)
+        next_cdf = torch.sigmoid((sdf + iter_cos * dists * 0.5) * logistic_beta)
+        return ((prev_cdf - next_cdf + 1e-6) / (prev_cdf + 1e-6)).clip(0.0, 1.0)
 
     def compute_transmittance_from_alphas(self, ray_samples_packed, alpha):
         transmittance, _ = self.cumprod_one_minus_alpha_to_transmittance_module(ray_samples_packed, (1 - alpha) + 1e-6)
