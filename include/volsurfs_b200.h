@@ -181,13 +181,13 @@ int64_t vs_mlp_blob_bytes(int n_layers, const int* dims);
  * arrays themselves are HOST arrays.  Writes the fp16 tensor-core layout + fp32 biases into `blob` (device, 16-byte aligned). */
 int vs_mlp_pack(int n_layers, const int* dims, const float* const* weights, const float* const* biases, void* blob, void* stream);
 /* out[s,:out] = sigmoid(MLP([pos[s] | SH_deg(dirs[s]) | normals[s] if normal_dep])) * (alpha_decay ? 2*sigmoid(10*clamp(-d.n,0,1))-1 : 1)
- * activation: 0 ReLU, 1 GELU(erf).  n_valid_dev: optional device int64 capping n_samples.  variant: 0 (debug knob). */
+ * activation: 0 ReLU, 1 GELU (torch.nn.GELU(): x*Phi(x), evaluated to 4e-5 absolute).  n_valid_dev: optional device int64 capping n_samples.  variant: 0 (debug knob). */
 int vs_mlp_forward(int n_layers, const int* dims, const void* blob, int pos_dim, int sh_degree, int normal_dep, int activation,
                    int alpha_decay, const float* pos, const float* dirs, const float* normals, float* out, void* stash, int64_t n_samples,
                    const int64_t* n_valid_dev, int variant, void* stream);
 /* Training mode: pass `stash` (vs_mlp_stash_bytes(n_samples) bytes, 16-byte aligned) to vs_mlp_forward and it also keeps, per
- * 128-sample tile, every layer's fp16 input operand and every hidden layer's activation derivative for vs_mlp_backward_stashed
- * (what torch autograd saves for backward in the reference).  NULL: inference. */
+ * 128-sample tile, the first layer's fp16 input operand and every hidden layer's fp16 pre-activations for vs_mlp_backward_stashed
+ * (what torch autograd saves for backward in the reference; 2 bytes per hidden unit and sample).  NULL: inference. */
 int64_t vs_mlp_stash_bytes(int n_layers, const int* dims, int64_t n_samples);
 
 /* ---- importance sampling chain ------------------------------------------------------------------------------
@@ -225,9 +225,10 @@ int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim
                     int alpha_decay, const float* pos, const float* dirs, const float* normals, const float* d_out, float* d_pos,
                     float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, int variant,
                     void* stream);
-/* Backward from the stash of a training-mode vs_mlp_forward (no recomputation; HBM-bound).  fwd_out: the output that forward wrote. */
+/* Backward from the stash of a training-mode vs_mlp_forward (no GEMM recomputation; HBM-bound).  activation: the forward's.
+ * fwd_out: the output that forward wrote. */
 int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree, int normal_dep,
-                            int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
+                            int activation, int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
                             float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream);
 
 /* ---- permutohedral-lattice hash encoding ---------------------------------------------------------------------
@@ -276,7 +277,7 @@ int vs_hashgrid_backward(int n_levels, int log2_hashmap_size, int base_resolutio
 int vs_mlp_forward_raw(int n_layers, const int* dims, const void* blob, int activation, const float* in, float* out, void* stash,
                        int64_t n_rows, const int64_t* n_valid_dev, void* stream);
 /* backward of a training-mode vs_mlp_forward_raw; workspace: vs_mlp_backward_workspace_bytes(n_layers, dims, dims[0], -1, 0, n_rows) */
-int vs_mlp_backward_stashed_raw(int n_layers, const int* dims, const void* blob, const void* stash, const float* d_out, float* d_in,
+int vs_mlp_backward_stashed_raw(int n_layers, const int* dims, const void* blob, const void* stash, int activation, const float* d_out, float* d_in,
                                 float* d_params, int accumulate, void* workspace, int64_t n_rows, const int64_t* n_valid_dev, void* stream);
 /* raw: HOST array of sh_deg+1 DEVICE pointers, raw[g] = [n_samples*corners, C*(2g+1)] f32; res_hw: HOST [sh_deg+1][2] (height, width);
  * range_lo / range_hi: HOST [sh_deg+1] val_range per degree (needed with squeeze); coeffs [n_samples,C,(sh_deg+1)^2] f32 or NULL;

@@ -59,7 +59,7 @@ SIGNATURES = {
     "vs_combine_merge": (c_int, [_I64, c_float, c_int] + [_P] * 19 + [_P]),
     "vs_mlp_num_params": (_I64, [c_int, _P]),
     "vs_mlp_backward_workspace_bytes": (_I64, [c_int, _P, c_int, c_int, c_int, _I64]),
-    "vs_mlp_backward_stashed": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, _P]),
+    "vs_mlp_backward_stashed": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, _P]),
     "vs_permuto_output_dims": (c_int, [c_int, c_int, c_int]),
     "vs_permuto_forward": (c_int, [c_int, c_int, _I64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _I64, _P, _P]),
     "vs_permuto_backward": (c_int, [c_int, c_int, _I64, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _P, _I64, _P, _P]),
@@ -67,7 +67,7 @@ SIGNATURES = {
     "vs_hashgrid_forward": (c_int, [c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, _P, _P, _P, _I64, _P, _P]),
     "vs_hashgrid_backward": (c_int, [c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, _P, _P, _P, _I64, _P, _P]),
     "vs_mlp_forward_raw": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _I64, _P, _P]),
-    "vs_mlp_backward_stashed_raw": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, _P]),
+    "vs_mlp_backward_stashed_raw": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P, _I64, _P, _P]),
     "vs_shtex_combine_forward": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "vs_shtex_combine_backward": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "vs_segment_offsets": (c_int, [_P, _I64, _P, _P, _P, _P]),

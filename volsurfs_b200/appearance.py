@@ -151,7 +151,7 @@ class AppearanceHead(torch.nn.Module):
             check(
                 L.vs_mlp_backward_stashed(
                     len(self.layers), self._dims_c(), ptr(self.packed()), ptr(stash), self.pos_dim, sh, int(self.normal_dep),
-                    int(self.alpha_decay), ptr(None if dirs is None else dirs.contiguous()),
+                    1 if self.activation == "gelu" else 0, int(self.alpha_decay), ptr(None if dirs is None else dirs.contiguous()),
                     ptr(None if normals is None else normals.contiguous()), ptr(fwd_out), ptr(d_out), ptr(d_pos), ptr(d_params),
                     int(bool(accumulate)), ptr(ws), S, ptr(n_valid_dev), _stream(),
                 ),

@@ -50,8 +50,8 @@ __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __rest
 //     `full` mbarrier (which the epilogue warps wait on) and requests the features of the slot's next tile by TMA as soon as the
 //     landing zone is free.
 // While the epilogue warps work on one slot the tensor core works on the other, so neither the MMA latency nor the hand-over is
-// exposed.  STASH: training mode — every layer's input operand and every hidden layer's activation derivative also go to global
-// memory (16-byte stores, a warp covers 512 contiguous bytes) for the backward.
+// exposed.  STASH: training mode — the first layer's input operand and every hidden layer's fp16 pre-activations also go to global
+// memory (16-byte stores, a warp covers 512 contiguous bytes) for the backward (layout: MlpStash).
 constexpr int kFwdThreads = kMlpThreads + 32;
 
 template <int ACT, bool STASH>  // ACT: 0 ReLU, 1 GELU (compile-time: the epilogue loop carries no branch)
@@ -250,39 +250,32 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
             if (l + 1 < L) {
                 uint8_t* hbuf = reinterpret_cast<uint8_t*>(slot_h(s));
                 uint8_t* st_a = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[l + 1] : nullptr;
-                uint8_t* st_g = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.g_off[l] : nullptr;
                 if (STASH && stash_cfg.fold[l + 1] && cg == 1)
                     *reinterpret_cast<uint4*>(st_a + ((size_t)(N / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
                 for (int c0 = cg * 16; c0 < N; c0 += 64) {
                     float v[16];
                     tmem_ld16(tmem_lane + (uint32_t)c0, v);
                     const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-                    __half2 h[8], gh[8];
+                    __half2 h[8], zh[8];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 bb = b4[q];
                         const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
-                        float a0, a1, a2, a3, g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+                        float a0, a1, a2, a3, g0, g1;
                         if (ACT == 1) {
-                            gelu_pair<STASH>(x0, x1, a0, a1, g0, g1);
-                            gelu_pair<STASH>(x2, x3, a2, a3, g2, g3);
+                            gelu_pair<false>(x0, x1, a0, a1, g0, g1);
+                            gelu_pair<false>(x2, x3, a2, a3, g0, g1);
                         } else {
                             a0 = fmaxf(x0, 0.f);
                             a1 = fmaxf(x1, 0.f);
                             a2 = fmaxf(x2, 0.f);
                             a3 = fmaxf(x3, 0.f);
-                            if (STASH) {
-                                g0 = x0 > 0.f ? 1.f : 0.f;
-                                g1 = x1 > 0.f ? 1.f : 0.f;
-                                g2 = x2 > 0.f ? 1.f : 0.f;
-                                g3 = x3 > 0.f ? 1.f : 0.f;
-                            }
                         }
                         h[2 * q] = __floats2half2_rn(a0, a1);
                         h[2 * q + 1] = __floats2half2_rn(a2, a3);
-                        if (STASH) {
-                            gh[2 * q] = __floats2half2_rn(g0, g1);
-                            gh[2 * q + 1] = __floats2half2_rn(g2, g3);
+                        if (STASH) {  // the backward recomputes act and act' from the fp16 pre-activation
+                            zh[2 * q] = __floats2half2_rn(x0, x1);
+                            zh[2 * q + 1] = __floats2half2_rn(x2, x3);
                         }
                     }
                     const size_t off = ((size_t)(c0 / 8) * kTileM + row) * 16;  // next 8-column chunk: +128 rows * 16 bytes
@@ -290,10 +283,8 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
                     *reinterpret_cast<uint4*>(hbuf + off) = lo;
                     *reinterpret_cast<uint4*>(hbuf + off + kTileM * 16) = hi;
                     if (STASH) {
-                        *reinterpret_cast<uint4*>(st_a + off) = lo;
-                        *reinterpret_cast<uint4*>(st_a + off + kTileM * 16) = hi;
-                        *reinterpret_cast<uint4*>(st_g + off) = *reinterpret_cast<const uint4*>(&gh[0]);
-                        *reinterpret_cast<uint4*>(st_g + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&gh[4]);
+                        *reinterpret_cast<uint4*>(st_a + off) = *reinterpret_cast<const uint4*>(&zh[0]);
+                        *reinterpret_cast<uint4*>(st_a + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&zh[4]);
                     }
                 }
                 announce(s);

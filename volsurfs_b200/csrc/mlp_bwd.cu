@@ -100,25 +100,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
 }
 constexpr uint32_t kIdescAMn = 1u << 15, kIdescBMn = 1u << 16;  // operand is MN-major (read "transposed")
 
-__device__ __forceinline__ float gelu_grad(float x) {
-    // d/dx [x Phi(x)] = Phi(x) + x phi(x); Phi from the same erf approximation as gelu_erf
-    const float z = fabsf(x) * 0.70710678118f;
-    float p = fmaf(z, 0.0000430638f, 0.0002765672f);
-    p = fmaf(p, z, 0.0001520143f);
-    p = fmaf(p, z, 0.0092705272f);
-    p = fmaf(p, z, 0.0422820123f);
-    p = fmaf(p, z, 0.0705230784f);
-    p = fmaf(p, z, 1.0f);
-    p = p * p;
-    p = p * p;
-    p = p * p;
-    p = p * p;
-    const float e = 1.f - __fdividef(1.f, p);
-    const float Phi = 0.5f * (1.f + copysignf(e, x));
-    const float phi = 0.3989422804f * __expf(-0.5f * x * x);
-    return fmaf(x, phi, Phi);
-}
-
 // power-of-two loss scale from max|dOut|: max * scale lands in [512, 1024) (fp16 keeps 24 binades below that)
 __device__ __forceinline__ int scale_exponent(float amax) {
     if (!(amax > 0.f)) return 0;
@@ -307,10 +288,10 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_kernel(const MlpConfig cf
                         const float4 bb = b4[q];
                         float a0 = v[4 * q] + bb.x, a1 = v[4 * q + 1] + bb.y, a2 = v[4 * q + 2] + bb.z, a3 = v[4 * q + 3] + bb.w;
                         if (ACT == 1) {
-                            a0 = gelu_erf(a0);
-                            a1 = gelu_erf(a1);
-                            a2 = gelu_erf(a2);
-                            a3 = gelu_erf(a3);
+                            a0 = gelu_fwd(a0);
+                            a1 = gelu_fwd(a1);
+                            a2 = gelu_fwd(a2);
+                            a3 = gelu_fwd(a3);
                         } else {
                             a0 = fmaxf(a0, 0.f);
                             a1 = fmaxf(a1, 0.f);
@@ -601,6 +582,7 @@ struct RingCursor {
     }
 };
 
+template <int ACT>  // 0 ReLU, 1 GELU: the backward recomputes act / act' from the stashed pre-activations
 __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpConfig cfg, const MlpBwdPlan plan, const MlpBwd2Plan p2,
                                                                       const MlpStash st, const uint8_t* __restrict__ blob,
                                                                       const uint8_t* __restrict__ stash, const float* __restrict__ dirs,
@@ -609,7 +591,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
                                                                       float* __restrict__ d_pos, float* __restrict__ partials,
                                                                       int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw, bar_ready, bar_x, bar_item[kItemBars];
+    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw, bar_ready, bar_x, bar_act, bar_item[kItemBars];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -638,6 +620,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
         mbar_init(&bar_dw, 1);
         mbar_init(&bar_ready, kMlpThreads / 32);
         mbar_init(&bar_x, kMlpThreads / 32);
+        mbar_init(&bar_act, kMlpThreads / 32);
         for (int i = 0; i < kItemBars; ++i) mbar_init(&bar_item[i], 1);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)plan.tmem_cols);
@@ -700,7 +683,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
             mbar_wait(&bar_w, 0);
             RingCursor cur{0};
             uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
-            uint32_t par_ready = 0, par_dw = 0, par_x = 0;
+            uint32_t par_ready = 0, par_dw = 0, par_x = 0, par_act = 0;
             const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
             const int pf_depth = p2.prefetch_tiles;
             for (int64_t j = 0; j < pf_depth && j < my_tiles; ++j)
@@ -734,7 +717,13 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
                                       (uint32_t)N * 16, 256, umma_idesc_f16(kTileM, K) | kIdescBMn, N / 16, false);
                         tc_commit(&bar_da);
                     }
-                    mbar_wait(&bar_item[seq_a & (kItemBars - 1)], (seq_a / kItemBars) & 1u);  // A_l has landed
+                    if (l >= 1) {
+                        mbar_wait(&bar_act, par_act);  // the epilogue warps have turned the landed Z_{l-1} into A_l = act(Z_{l-1}) in place
+                        par_act ^= 1;
+                        tc_fence_after();
+                    } else {
+                        mbar_wait(&bar_item[seq_a & (kItemBars - 1)], (seq_a / kItemBars) & 1u);  // A_0 has landed
+                    }
                     umma_gemm_f16(tmem_base + (uint32_t)plan.dw_col[l], a_addr, mn_lbo, mn_sbo, 256, dz_addr, mn_lbo, mn_sbo, 256,
                                   umma_idesc_f16(kTileM, N) | kIdescAMn | kIdescBMn, kTileM / 16, k > 0);
                     if (!plan.fold_bias[l])
@@ -769,6 +758,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
         RingCursor cur{0};
         uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
         uint32_t par_da = 0;
+        uint32_t n_act = 0;  // conversions this warp has announced on bar_act
         auto announce = [&](uint64_t* bar) {
             fence_proxy_async();
             tc_fence_before();
@@ -827,21 +817,47 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
 
             for (int l = L - 1; l >= 0; --l) {
                 const int K = cfg.k_pad[l];
-                cur.alloc(st.a_bytes[l], R);  // A_l: consumed by the tensor core only
-                ++seq;
+                const int off_a = cur.alloc(st.a_bytes[l], R);  // item l: A_0 (consumed by the tensor core only) or Z_{l-1}
+                const uint32_t seq_a = seq++;
                 if (l >= 1) {
-                    // this thread's elements of G_{l-1}: global -> registers, in flight while dA_l is being computed
-                    const uint8_t* gsrc = stash + tile * (int64_t)st.tile_bytes + st.g_off[l - 1];
+                    // Z_{l-1} (fp16 pre-activations, landed by TMA) -> A_l = act(Z_{l-1}) in place (the dW_l GEMM's operand) and this
+                    // thread's elements of act'(Z_{l-1}) in registers, while the tensor core computes dA_l
+                    mbar_wait(item_bar(seq_a), item_parity(seq_a));
+                    // nothing else orders this warp's NEXT arrival on bar_act after the completion of the phase it arrived on last (a fast
+                    // warp could otherwise arrive twice in one phase and release the dW GEMM before a slow warp has converted its part)
+                    if (n_act > 0) mbar_wait(&bar_act, (n_act - 1) & 1u);
+                    ++n_act;
                     uint4 gq[2][2];
 #pragma unroll
                     for (int it = 0; it < 2; ++it) {
                         const int c0 = cg * 16 + 64 * it;
                         if (c0 < K) {
-                            const uint4* src = reinterpret_cast<const uint4*>(gsrc + ((size_t)(c0 / 8) * kTileM + row) * 16);
-                            gq[it][0] = __ldcs(src);
-                            gq[it][1] = __ldcs(src + kTileM);
+                            uint4* zp = reinterpret_cast<uint4*>(s_ring + off_a + ((size_t)(c0 / 8) * kTileM + row) * 16);
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                uint4 zq = zp[half * kTileM];
+                                __half2* zh = reinterpret_cast<__half2*>(&zq);
+                                __half2* gh = reinterpret_cast<__half2*>(&gq[it][half]);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 z = __half22float2(zh[q]);
+                                    float a0, a1, g0, g1;
+                                    if (ACT == 1) {
+                                        gelu_pair<true>(z.x, z.y, a0, a1, g0, g1);
+                                    } else {
+                                        a0 = fmaxf(z.x, 0.f);
+                                        a1 = fmaxf(z.y, 0.f);
+                                        g0 = z.x > 0.f ? 1.f : 0.f;
+                                        g1 = z.y > 0.f ? 1.f : 0.f;
+                                    }
+                                    zh[q] = __floats2half2_rn(a0, a1);
+                                    gh[q] = __floats2half2_rn(g0, g1);
+                                }
+                                zp[half * kTileM] = zq;
+                            }
                         }
                     }
+                    announce(&bar_act);
                     const int off_next = cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
                     mbar_wait(item_bar(seq), item_parity(seq));
                     ++seq;
@@ -1025,10 +1041,11 @@ int vs_mlp_backward(int n_layers, const int* dims, const void* blob, int pos_dim
 
 }  // extern "C"
 
-// Backward of a training-mode vs_mlp_forward from its activation stash (no recomputation).  fwd_out: the [n_samples,out] output
+// Backward of a training-mode vs_mlp_forward from its activation stash (no GEMM is recomputed; act / act' are re-evaluated from the stashed
+// pre-activations: `activation` must be the forward's).  fwd_out: the [n_samples,out] output
 // that forward wrote; other arguments as vs_mlp_backward.  workspace: vs_mlp_backward_workspace_bytes bytes.
 static int mlp_backward_stashed_impl(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree,
-                                     int normal_dep, int alpha_decay, int out_linear, const float* dirs, const float* normals,
+                                     int normal_dep, int activation, int alpha_decay, int out_linear, const float* dirs, const float* normals,
                                      const float* fwd_out, const float* d_out, float* d_pos, float* d_params, int accumulate,
                                      void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream) {
     VS_CHECK_ARG(blob && stash && n_samples >= 0 && d_params && workspace);
@@ -1043,6 +1060,7 @@ static int mlp_backward_stashed_impl(int n_layers, const int* dims, const void* 
     VS_CHECK_ARG((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(stash) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(d_pos) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
     c.alpha_decay = alpha_decay ? 1 : 0;
+    c.activation = activation;
     MlpStash st;
     mlp_stash_layout(c, &st);
     MlpBwd2Plan p2;
@@ -1059,9 +1077,10 @@ static int mlp_backward_stashed_impl(int n_layers, const int* dims, const void* 
     int launches = 0;
     if (n_samples > 0) {
         mlp_absmax_kernel<<<296, 256, 0, s>>>(d_out, n_samples, c.out_dim, n_valid_dev, absmax);
-        ce = cudaFuncSetAttribute(mlp_bwd_stashed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2.smem_bytes);
+        auto kern = activation == 1 ? mlp_bwd_stashed_kernel<1> : mlp_bwd_stashed_kernel<0>;
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p2.smem_bytes);
         if (ce != cudaSuccess) return (int)ce;
-        mlp_bwd_stashed_kernel<<<grid, kBwdThreads, p2.smem_bytes, s>>>(c, p, p2, st, reinterpret_cast<const uint8_t*>(blob),
+        kern<<<grid, kBwdThreads, p2.smem_bytes, s>>>(c, p, p2, st, reinterpret_cast<const uint8_t*>(blob),
                                                                         reinterpret_cast<const uint8_t*>(stash), dirs, normals, fwd_out, d_out,
                                                                         absmax, d_pos, partials, n_samples, n_valid_dev);
         launches += 2;
@@ -1074,18 +1093,18 @@ static int mlp_backward_stashed_impl(int n_layers, const int* dims, const void* 
 extern "C" {
 
 int vs_mlp_backward_stashed(int n_layers, const int* dims, const void* blob, const void* stash, int pos_dim, int sh_degree, int normal_dep,
-                            int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
+                            int activation, int alpha_decay, const float* dirs, const float* normals, const float* fwd_out, const float* d_out, float* d_pos,
                             float* d_params, int accumulate, void* workspace, int64_t n_samples, const int64_t* n_valid_dev, void* stream) {
-    return mlp_backward_stashed_impl(n_layers, dims, blob, stash, pos_dim, sh_degree, normal_dep, alpha_decay, 0, dirs, normals, fwd_out, d_out,
+    return mlp_backward_stashed_impl(n_layers, dims, blob, stash, pos_dim, sh_degree, normal_dep, activation, alpha_decay, 0, dirs, normals, fwd_out, d_out,
                                      d_pos, d_params, accumulate, workspace, n_samples, n_valid_dev, stream);
 }
 
 // Backward of a training-mode vs_mlp_forward_raw (linear last layer): d_out [n_rows,out] -> d_in [n_rows,dims[0]] (or NULL) and the flat
 // parameter gradients; workspace: vs_mlp_backward_workspace_bytes(n_layers, dims, dims[0], -1, 0, n_rows) bytes.
-int vs_mlp_backward_stashed_raw(int n_layers, const int* dims, const void* blob, const void* stash, const float* d_out, float* d_in,
+int vs_mlp_backward_stashed_raw(int n_layers, const int* dims, const void* blob, const void* stash, int activation, const float* d_out, float* d_in,
                                 float* d_params, int accumulate, void* workspace, int64_t n_rows, const int64_t* n_valid_dev, void* stream) {
     VS_CHECK_ARG(dims);
-    return mlp_backward_stashed_impl(n_layers, dims, blob, stash, dims[0], -1, 0, 0, 1, nullptr, nullptr, nullptr, d_out, d_in, d_params,
+    return mlp_backward_stashed_impl(n_layers, dims, blob, stash, dims[0], -1, 0, activation, 0, 1, nullptr, nullptr, nullptr, d_out, d_in, d_params,
                                      accumulate, workspace, n_rows, n_valid_dev, stream);
 }
 

@@ -34,14 +34,15 @@ struct MlpConfig {
     int n_slots;             // tiles a CTA keeps in flight: 2 (MMA of one slot under the epilogue of the other) or 1 (large blobs)
 };
 
-// Activation stash written by the training-mode forward and read by the backward: per 128-sample tile, the fp16 input operand of
-// every layer (A_0 .. A_{L-1}) and the activation derivative of every hidden layer (G_0 .. G_{L-2}), each stored as the exact
-// shared-memory image the tensor core consumes ([width/8][128][8] halves), so the backward fetches them with one bulk copy each.
+// Activation stash written by the training-mode forward and read by the backward: per 128-sample tile, item 0 = the fp16 input operand
+// A_0 of the first layer and item l >= 1 = the fp16 PRE-activations Z_{l-1} (bias included) of hidden layer l-1, each stored as the exact
+// shared-memory image the tensor core consumes ([width/8][128][8] halves), so the backward fetches an item with one bulk copy.  The
+// backward turns Z_{l-1} into the operand A_l = act(Z_{l-1}) in place and keeps act'(Z_{l-1}) in registers: one 2-byte value per hidden
+// unit is all a layer costs (832 B per sample for [67,128,128,64,c]; the first version kept A_l and act' separately: 1472 B).
 struct MlpStash {
     int a_off[kMaxLayers];
     int a_bytes[kMaxLayers];  // 128 * (k_pad + 8 * fold) * 2
-    int fold[kMaxLayers];     // fan-in < 128: A_l is followed by a chunk whose channel 0 is 1 (bias gradient = one more dW row)
-    int g_off[kMaxLayers];
+    int fold[kMaxLayers];     // fan-in < 128: the item is followed by a chunk whose channel 0 is 1 (bias gradient = one more dW row)
     int tile_bytes;
 };
 
@@ -88,10 +89,6 @@ static inline void mlp_stash_layout(const MlpConfig& c, MlpStash* s) {
         s->fold[l] = c.k_pad[l] + 8 <= kMaxWidth ? 1 : 0;
         s->a_bytes[l] = kTileM * (c.k_pad[l] + 8 * s->fold[l]) * 2;
         off += s->a_bytes[l];
-    }
-    for (int l = 0; l + 1 < c.n_layers; ++l) {
-        s->g_off[l] = off;
-        off += kTileM * c.n_pad[l] * 2;
     }
     s->tile_bytes = off;
 }
@@ -172,23 +169,6 @@ __device__ __forceinline__ void umma_gemm_f16(uint32_t tmem_d, uint32_t a_addr, 
     }
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {
-    // 0.5 x (1 + erf(x/sqrt2)); erf by Abramowitz-Stegun 7.1.28: 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7 — far below
-    // the fp16 rounding of the result; one MUFU (reciprocal) per activation, everything else on the FMA pipe
-    const float z = fabsf(x) * 0.70710678118f;
-    float p = fmaf(z, 0.0000430638f, 0.0002765672f);
-    p = fmaf(p, z, 0.0001520143f);
-    p = fmaf(p, z, 0.0092705272f);
-    p = fmaf(p, z, 0.0422820123f);
-    p = fmaf(p, z, 0.0705230784f);
-    p = fmaf(p, z, 1.0f);
-    p = p * p;
-    p = p * p;
-    p = p * p;
-    p = p * p;
-    const float e = 1.f - __fdividef(1.f, p);
-    return 0.5f * x * (1.f + copysignf(e, x));
-}
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) -------------------------------
 __device__ __forceinline__ uint64_t f2_pack(float a, float b) {
     uint64_t r;
@@ -213,40 +193,49 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return r;
 }
 
-// GELU (exact-erf form, same Abramowitz-Stegun 7.1.28 erf as gelu_erf) of two values at once; with GRAD also d/dx = Phi + x phi.
-// Polynomial and squarings run on the packed FMA pipe: ~9.5 issue slots per activation instead of ~18.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// GELU(x) = x Phi(x) (torch.nn.GELU(), exact-erf form: models/mlp.py:36) evaluated as
+//     Phi(x) = 0.5 (1 + tanh(u(x))),   u(x) = x (c1 + c2 x^2 + c3 x^4)
+// with (c1, c2, c3) fitted to atanh(erf(x / sqrt 2)) on |x| <= 8 (scripts/fit_gelu.py): max |GELU error| 3.7e-5, max |GELU' error| 9.3e-5
+// — below the fp16 rounding of the activations — for ONE MUFU (tanh.approx, rel. error 2^-11) and ~5 packed-FMA issue slots per
+// activation; the A&S 7.1.28 erf used before took 1 MUFU + ~9.5 slots and a second MUFU (ex2) for the derivative, and the MUFU pipe
+// (16 lanes per SM and clock) was what bounded the forward kernel.  x^2 is clamped at 64: beyond |x| = 8 tanh has saturated and the fitted
+// polynomial (c3 < 0) must not be followed any further.  With GRAD also d/dx = Phi + 0.5 x (1 - t^2) u'(x), from the same tanh.
+constexpr float kGelu1 = 0.797422805f, kGelu2 = 0.0370039313f, kGelu3 = -3.47585310e-4f;
+
 template <bool GRAD>
 __device__ __forceinline__ void gelu_pair(float x0, float x1, float& a0, float& a1, float& g0, float& g1) {
     const uint64_t x = f2_pack(x0, x1);
-    const uint64_t z = f2_pack(fabsf(x0) * 0.70710678118f, fabsf(x1) * 0.70710678118f);
-    uint64_t p = f2_fma(z, f2_splat(0.0000430638f), f2_splat(0.0002765672f));
-    p = f2_fma(p, z, f2_splat(0.0001520143f));
-    p = f2_fma(p, z, f2_splat(0.0092705272f));
-    p = f2_fma(p, z, f2_splat(0.0422820123f));
-    p = f2_fma(p, z, f2_splat(0.0705230784f));
-    p = f2_fma(p, z, f2_splat(1.0f));
-    p = f2_mul(p, p);
-    p = f2_mul(p, p);
-    p = f2_mul(p, p);
-    p = f2_mul(p, p);
-    float p0, p1;
-    f2_unpack(p, p0, p1);
-    // erf(x/sqrt2) = sign(x) (1 - p^-16): 1 - r >= 0, so the sign is one bit operation
-    float r0, r1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
-    const float e0 = __uint_as_float(__float_as_uint(1.f - r0) | (__float_as_uint(x0) & 0x80000000u));
-    const float e1 = __uint_as_float(__float_as_uint(1.f - r1) | (__float_as_uint(x1) & 0x80000000u));
-    const uint64_t e = f2_pack(e0, e1);
+    const uint64_t s = f2_pack(fminf(x0 * x0, 64.f), fminf(x1 * x1, 64.f));
+    uint64_t p = f2_fma(s, f2_splat(kGelu3), f2_splat(kGelu2));
+    p = f2_fma(p, s, f2_splat(kGelu1));
+    float u0, u1;
+    f2_unpack(f2_mul(x, p), u0, u1);
+    const uint64_t t = f2_pack(tanh_approx(u0), tanh_approx(u1));
     const uint64_t h = f2_mul(x, f2_splat(0.5f));
-    f2_unpack(f2_fma(h, e, h), a0, a1);
+    f2_unpack(f2_fma(h, t, h), a0, a1);
     if (GRAD) {
-        const uint64_t Phi = f2_fma(e, f2_splat(0.5f), f2_splat(0.5f));
-        float t0, t1;
-        f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.72134752044f)), t0, t1);
-        const uint64_t ex = f2_pack(ex2_approx(t0), ex2_approx(t1));  // exp(-x^2/2)
-        f2_unpack(f2_fma(f2_mul(x, ex), f2_splat(0.3989422804f), Phi), g0, g1);
+        uint64_t up = f2_fma(s, f2_splat(5.f * kGelu3), f2_splat(3.f * kGelu2));
+        up = f2_fma(up, s, f2_splat(kGelu1));
+        const uint64_t sech2 = f2_fma(f2_mul(t, t), f2_splat(-1.f), f2_splat(1.f));
+        const uint64_t Phi = f2_fma(t, f2_splat(0.5f), f2_splat(0.5f));
+        f2_unpack(f2_fma(f2_mul(h, sech2), up, Phi), g0, g1);
     }
+}
+__device__ __forceinline__ float gelu_fwd(float x) {
+    float a0, a1, g0, g1;
+    gelu_pair<false>(x, x, a0, a1, g0, g1);
+    return a0;
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+    float a0, a1, g0, g1;
+    gelu_pair<true>(x, x, a0, a1, g0, g1);
+    return g0;
 }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -115,7 +115,7 @@ class TextureNetwork(torch.nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=uv.device)
         flat = torch.empty(n_params, dtype=torch.float32, device=uv.device)
         d_feat = torch.empty((rows, self.dims[0]), dtype=torch.float32, device=uv.device)
-        check(L.vs_mlp_backward_stashed_raw(n, self._dims_c(), ptr(self.packed()), ptr(stash), ptr(d_raw), ptr(d_feat), ptr(flat), 0, ptr(ws),
+        check(L.vs_mlp_backward_stashed_raw(n, self._dims_c(), ptr(self.packed()), ptr(stash), 0, ptr(d_raw), ptr(d_feat), ptr(flat), 0, ptr(ws),
                                             rows, None, _stream()), "vs_mlp_backward_stashed_raw")
         d_table = torch.zeros_like(self.table)
         check(L.vs_hashgrid_backward(*self.grid_cfg, mode, int(align), int(res_hw[0]), int(res_hw[1]), ptr(uv), ptr(d_feat), ptr(d_table), S,
