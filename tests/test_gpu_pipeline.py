@@ -127,7 +127,9 @@ def test_full_path_outputs_and_gradients_vs_oracle_chain():
     """the legacy-head step (trace -> pack -> 2 heads -> composite -> L1 -> composite bwd -> heads bwd) against the oracle chain of
     tests/fullpath_oracle.py (C tracer in the reference kernel's arithmetic -> numpy packing -> fp32 torch heads -> dense compositing ->
     autograd): packing bit-exact, image <= 1e-4 abs, per-sample colour/alpha <= 2e-4 abs (fp16 operands, fp32 accumulate: the bar of
-    tests/test_gpu_mlp.py), every gradient <= 3e-2 under grad_err (observed ~3e-3)"""
+    tests/test_gpu_mlp.py); parameter gradients <= 1e-2 under grad_err (observed 1.3e-3); the per-sample feature gradients have no averaging
+    over samples: worst entry <= 5e-2 (observed 3e-2 for the alpha head, whose gradients also carry the decay factor), rms error <= 5e-3 of
+    the tensor's rms — the bars of tests/test_gpu_mlp.py for the head alone, widened for the worst entry by the compositing chain"""
     import numpy as np
 
     from conftest import grad_err
@@ -153,5 +155,11 @@ def test_full_path_outputs_and_gradients_vs_oracle_chain():
     assert abs(float(out["loss"]) - float(want["loss"])) < 1e-5
     errs = {k: grad_err(out[k][:S].cpu().numpy() if k.startswith("d_features") else out[k].cpu().numpy(), want[k].numpy())
             for k in ("grad_rgb", "grad_alpha", "d_features_rgb", "d_features_alpha")}
-    print({k: f"{v:.2e}" for k, v in errs.items()})
-    assert all(v < 3e-2 for v in errs.values()), errs
+    rms = {}
+    for k in ("d_features_rgb", "d_features_alpha"):
+        a, b = out[k][:S].cpu().double().numpy(), want[k].double().numpy()
+        rms[k] = float(np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2)))
+    print({k: f"{v:.2e}" for k, v in errs.items()}, {k: f"{v:.2e}" for k, v in rms.items()})
+    assert errs["grad_rgb"] < 1e-2 and errs["grad_alpha"] < 1e-2, errs
+    assert errs["d_features_rgb"] < 5e-2 and errs["d_features_alpha"] < 5e-2, errs
+    assert all(v < 5e-3 for v in rms.values()), rms

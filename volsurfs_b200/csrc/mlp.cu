@@ -18,6 +18,8 @@
 //
 // Precision: fp16 operands, fp32 accumulation (the reference's default appearance path runs tiny-cuda-nn's fp16 FullyFusedMLP;
 // the legacy torch path is fp32) — parity tolerance for this stage is stated in tests/test_gpu_mlp.py (abs 4e-3 on sigmoid outputs).
+#include <cstdlib>
+
 #include "mlp_common.cuh"
 
 namespace vs {
@@ -55,7 +57,8 @@ __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __rest
 constexpr int kFwdThreads = kMlpThreads + 32;
 
 template <int ACT, bool STASH>  // ACT: 0 ReLU, 1 GELU (compile-time: the epilogue loop carries no branch)
-__global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cfg, const MlpStash stash_cfg, const uint8_t* __restrict__ blob,
+__global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_constant__ MlpConfig cfg_param,
+                                                                 const __grid_constant__ MlpStash stash_param, const uint8_t* __restrict__ blob,
                                                               const float* __restrict__ pos, const float* __restrict__ dirs,
                                                               const float* __restrict__ normals, float* __restrict__ out,
                                                               uint8_t* __restrict__ stash, int64_t n_samples,
@@ -63,6 +66,15 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_full[2], bar_ready[2];
     __shared__ uint32_t tmem_slot;
+    // the per-layer tables are indexed with the (run-time) layer number in the hot loops: from shared memory that is a ~30-cycle LDS; out
+    // of the kernel-parameter bank it is a dependent constant load per use (measured: 14 % of all stall samples on one such line)
+    __shared__ MlpConfig cfg;
+    __shared__ MlpStash stash_cfg;
+    for (int i = threadIdx.x; i < (int)(sizeof(MlpConfig) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(&cfg)[i] = reinterpret_cast<const int*>(&cfg_param)[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(MlpStash) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(&stash_cfg)[i] = reinterpret_cast<const int*>(&stash_param)[i];
+    __syncthreads();
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -117,6 +129,10 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
                 if (tile < n_tiles && (tile + 1) * kTileM <= n && F > 0) {
                     mbar_arrive_expect_tx(&bar_in[s], (uint32_t)(kTileM * F * 4));
                     bulk_g2s(slot_h(s), pos + tile * kTileM * F, (uint32_t)(kTileM * F * 4), &bar_in[s]);
+                    // the landing zone is the slot's hidden-activation buffer, so this copy can only be requested one output epilogue
+                    // ahead of its use: pull the slot's FOLLOWING tile into L2 now, a whole tile time ahead, and the copy above finds
+                    // its lines there instead of in DRAM
+                    if ((tile + step + 1) * kTileM <= n) bulk_prefetch_l2(pos + (tile + step) * kTileM * F, (uint32_t)(kTileM * F * 4));
                 }
             };
             int64_t t[2] = {(int64_t)blockIdx.x, two ? (int64_t)blockIdx.x + stride : n_tiles};
@@ -171,6 +187,20 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
             const bool full = rows == kTileM;
             const int64_t r = row0 + row;
             const bool live = row < rows;
+            // directions / normals of the row come straight from global memory: in flight while the feature tile lands
+            float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+            if (cg == 0 && live) {
+                if (dirs != nullptr) {
+                    dx = __ldg(dirs + 3 * r);
+                    dy = __ldg(dirs + 3 * r + 1);
+                    dz = __ldg(dirs + 3 * r + 2);
+                }
+                if (normals != nullptr) {
+                    nx = __ldg(normals + 3 * r);
+                    ny = __ldg(normals + 3 * r + 1);
+                    nz = __ldg(normals + 3 * r + 2);
+                }
+            }
             if (full && F > 0) {
                 mbar_wait(&bar_in[s], par_in[s]);
                 par_in[s] ^= 1;
@@ -182,19 +212,6 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
             const int tail0 = F / 8;  // first chunk that holds SH / normal / padding columns: those belong to the row's cg == 0 thread
             float* ex = slot_extra(s) + row * kExtraStride;
             if (cg == 0) {
-                float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-                if (live) {
-                    if (dirs != nullptr) {
-                        dx = __ldg(dirs + 3 * r);
-                        dy = __ldg(dirs + 3 * r + 1);
-                        dz = __ldg(dirs + 3 * r + 2);
-                    }
-                    if (normals != nullptr) {
-                        nx = __ldg(normals + 3 * r);
-                        ny = __ldg(normals + 3 * r + 1);
-                        nz = __ldg(normals + 3 * r + 2);
-                    }
-                }
                 decay[s] = 1.f;
                 if (cfg.alpha_decay) {
                     const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
@@ -213,25 +230,37 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
                 }
             }
             // row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes.  Pure feature chunks are
-            // split over column groups 1..3, the tail chunks go to column group 0.
-            const int kc_begin = cg == 0 ? tail0 : cg - 1, kc_end = cg == 0 ? k0 / 8 : tail0, kc_step = cg == 0 ? 1 : 3;
-            for (int kc = kc_begin; kc < kc_end; kc += kc_step) {
-                __half2 h[4];
+            // split over column groups 1..3 (no per-element decisions on a full tile), the tail chunks go to column group 0.
+            if (cg != 0 && full) {
+                for (int kc = cg - 1; kc < tail0; kc += 3) {
+                    const float* sp = srow + kc * 8;
+                    __half2 h[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float v2[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int c = kc * 8 + 2 * j + q;
-                        float v = 0.f;
-                        if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
-                        v2[q] = v;
-                    }
-                    h[j] = __floats2half2_rn(v2[0], v2[1]);
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(sp[2 * j], sp[2 * j + 1]);
+                    const uint4 pk = *reinterpret_cast<const uint4*>(h);
+                    *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
+                    if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
                 }
-                const uint4 pk = *reinterpret_cast<const uint4*>(h);
-                *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
-                if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+            } else {
+                const int kc_begin = cg == 0 ? tail0 : cg - 1, kc_end = cg == 0 ? k0 / 8 : tail0, kc_step = cg == 0 ? 1 : 3;
+                for (int kc = kc_begin; kc < kc_end; kc += kc_step) {
+                    __half2 h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v2[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int c = kc * 8 + 2 * j + q;
+                            float v = 0.f;
+                            if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
+                            v2[q] = v;
+                        }
+                        h[j] = __floats2half2_rn(v2[0], v2[1]);
+                    }
+                    const uint4 pk = *reinterpret_cast<const uint4*>(h);
+                    *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
+                    if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+                }
             }
             if (STASH && stash_cfg.fold[0] && cg == 1)  // the "ones" chunk behind A_0 (bias gradient row of the backward's dW GEMM)
                 *reinterpret_cast<uint4*>(st_a0 + ((size_t)(k0 / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
@@ -256,33 +285,23 @@ __global__ void __launch_bounds__(kFwdThreads) mlp_fwd_kernel(const MlpConfig cf
                     float v[16];
                     tmem_ld16(tmem_lane + (uint32_t)c0, v);
                     const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-                    __half2 h[8], zh[8];
+                    __half2 zh[8], h[8];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 bb = b4[q];
-                        const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
-                        float a0, a1, a2, a3, g0, g1;
-                        if (ACT == 1) {
-                            gelu_pair<false>(x0, x1, a0, a1, g0, g1);
-                            gelu_pair<false>(x2, x3, a2, a3, g0, g1);
-                        } else {
-                            a0 = fmaxf(x0, 0.f);
-                            a1 = fmaxf(x1, 0.f);
-                            a2 = fmaxf(x2, 0.f);
-                            a3 = fmaxf(x3, 0.f);
-                        }
-                        h[2 * q] = __floats2half2_rn(a0, a1);
-                        h[2 * q + 1] = __floats2half2_rn(a2, a3);
-                        if (STASH) {  // the backward recomputes act and act' from the fp16 pre-activation
-                            zh[2 * q] = __floats2half2_rn(x0, x1);
-                            zh[2 * q + 1] = __floats2half2_rn(x2, x3);
-                        }
+                        zh[2 * q] = __floats2half2_rn(v[4 * q] + bb.x, v[4 * q + 1] + bb.y);
+                        zh[2 * q + 1] = __floats2half2_rn(v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        __half2 g;
+                        if (ACT == 1) gelu_h2<false>(zh[q], h[q], g);
+                        else relu_h2<false>(zh[q], h[q], g);
                     }
                     const size_t off = ((size_t)(c0 / 8) * kTileM + row) * 16;  // next 8-column chunk: +128 rows * 16 bytes
-                    const uint4 lo = *reinterpret_cast<const uint4*>(&h[0]), hi = *reinterpret_cast<const uint4*>(&h[4]);
-                    *reinterpret_cast<uint4*>(hbuf + off) = lo;
-                    *reinterpret_cast<uint4*>(hbuf + off + kTileM * 16) = hi;
-                    if (STASH) {
+                    *reinterpret_cast<uint4*>(hbuf + off) = *reinterpret_cast<const uint4*>(&h[0]);
+                    *reinterpret_cast<uint4*>(hbuf + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&h[4]);
+                    if (STASH) {  // the backward re-evaluates act and act' from the fp16 pre-activation
                         *reinterpret_cast<uint4*>(st_a + off) = *reinterpret_cast<const uint4*>(&zh[0]);
                         *reinterpret_cast<uint4*>(st_a + off + kTileM * 16) = *reinterpret_cast<const uint4*>(&zh[4]);
                     }

@@ -583,8 +583,10 @@ struct RingCursor {
 };
 
 template <int ACT>  // 0 ReLU, 1 GELU: the backward recomputes act / act' from the stashed pre-activations
-__global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpConfig cfg, const MlpBwdPlan plan, const MlpBwd2Plan p2,
-                                                                      const MlpStash st, const uint8_t* __restrict__ blob,
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const __grid_constant__ MlpConfig cfg_param,
+                                                                         const __grid_constant__ MlpBwdPlan plan_param,
+                                                                         const __grid_constant__ MlpBwd2Plan p2_param,
+                                                                         const __grid_constant__ MlpStash st_param, const uint8_t* __restrict__ blob,
                                                                       const uint8_t* __restrict__ stash, const float* __restrict__ dirs,
                                                                       const float* __restrict__ normals, const float* __restrict__ fwd_out,
                                                                       const float* __restrict__ d_out, const float* __restrict__ absmax_dev,
@@ -593,6 +595,21 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw, bar_ready, bar_x, bar_act, bar_item[kItemBars];
     __shared__ uint32_t tmem_slot;
+    // per-layer tables indexed with the run-time layer number: shared-memory copies (see mlp_fwd_kernel)
+    __shared__ MlpConfig cfg;
+    __shared__ MlpBwdPlan plan;
+    __shared__ MlpBwd2Plan p2;
+    __shared__ MlpStash st;
+    {
+        auto copy_words = [&](void* dst, const void* src, int words) {
+            for (int i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<int*>(dst)[i] = reinterpret_cast<const int*>(src)[i];
+        };
+        copy_words(&cfg, &cfg_param, (int)(sizeof(MlpConfig) / 4));
+        copy_words(&plan, &plan_param, (int)(sizeof(MlpBwdPlan) / 4));
+        copy_words(&p2, &p2_param, (int)(sizeof(MlpBwd2Plan) / 4));
+        copy_words(&st, &st_param, (int)(sizeof(MlpStash) / 4));
+    }
+    __syncthreads();
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -840,18 +857,10 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
                                 __half2* gh = reinterpret_cast<__half2*>(&gq[it][half]);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
-                                    const float2 z = __half22float2(zh[q]);
-                                    float a0, a1, g0, g1;
-                                    if (ACT == 1) {
-                                        gelu_pair<true>(z.x, z.y, a0, a1, g0, g1);
-                                    } else {
-                                        a0 = fmaxf(z.x, 0.f);
-                                        a1 = fmaxf(z.y, 0.f);
-                                        g0 = z.x > 0.f ? 1.f : 0.f;
-                                        g1 = z.y > 0.f ? 1.f : 0.f;
-                                    }
-                                    zh[q] = __floats2half2_rn(a0, a1);
-                                    gh[q] = __floats2half2_rn(g0, g1);
+                                    __half2 a;
+                                    if (ACT == 1) gelu_h2<true>(zh[q], a, gh[q]);
+                                    else relu_h2<true>(zh[q], a, gh[q]);
+                                    zh[q] = a;
                                 }
                                 zp[half * kTileM] = zq;
                             }
@@ -874,10 +883,9 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_bwd_stashed_kernel(const MlpC
                             const __half2* gh = reinterpret_cast<const __half2*>(&gq[it][1]);
                             __half2 h[8];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 a = __half22float2(gl[q]), b = __half22float2(gh[q]);
-                                h[q] = __floats2half2_rn(v[2 * q] * a.x, v[2 * q + 1] * a.y);
-                                h[4 + q] = __floats2half2_rn(v[8 + 2 * q] * b.x, v[8 + 2 * q + 1] * b.y);
+                            for (int q = 0; q < 4; ++q) {  // dZ = fp16(dA) * act' in packed half precision (dZ is an fp16 operand anyway)
+                                h[q] = __hmul2(floats2half2_sat(v[2 * q], v[2 * q + 1]), gl[q]);
+                                h[4 + q] = __hmul2(floats2half2_sat(v[8 + 2 * q], v[8 + 2 * q + 1]), gh[q]);
                             }
                             uint4* slot = reinterpret_cast<uint4*>(s_ring + off_next + ((size_t)(c0 / 8) * kTileM + row) * 16);
                             slot[0] = *reinterpret_cast<const uint4*>(&h[0]);

@@ -127,6 +127,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same read split into issue and wait, so that several reads can be in flight
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor, K-major, no swizzle: element (row, k) of a [rows x K] fp16 operand lives at
 //   (k/8) * LBO + (row/8) * SBO + (row%8) * 16 + (k%8) * 2     with LBO = rows*16 bytes, SBO = 128 bytes
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -227,6 +238,51 @@ __device__ __forceinline__ void gelu_pair(float x0, float x1, float& a0, float& 
         f2_unpack(f2_fma(f2_mul(h, sech2), up, Phi), g0, g1);
     }
 }
+// ---- the same evaluation in packed half precision: what the head kernels' epilogues run ---------------------------------------------
+// The activations are rounded to fp16 anyway (they are the next GEMM's operand) and the backward re-evaluates act / act' from the fp16
+// pre-activation it finds in the stash, so the whole evaluation can stay in half2: ~9 issue slots and ONE packed MUFU (tanh.approx.f16x2) per
+// PAIR of activations, no fp32 <-> fp16 conversions around it.  Error against the fp32 evaluation: a few fp16 ulp of the result (measured
+// in tests/test_gpu_mlp.py against torch's exact-erf GELU through the whole head: the 2e-4 bar on the outputs holds with > 3x margin).
+__device__ __forceinline__ __half2 tanh_h2(__half2 x) {
+    uint32_t r, a = *reinterpret_cast<uint32_t*>(&x);
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a));
+    return *reinterpret_cast<__half2*>(&r);
+}
+template <bool GRAD>
+__device__ __forceinline__ void gelu_h2(__half2 z, __half2& a, __half2& g) {
+    const __half2 zc = __hmin2(__hmax2(z, __float2half2_rn(-8.f)), __float2half2_rn(8.f));
+    const __half2 s = __hmul2(zc, zc);
+    __half2 p = __hfma2(s, __float2half2_rn(kGelu3), __float2half2_rn(kGelu2));
+    p = __hfma2(p, s, __float2half2_rn(kGelu1));
+    const __half2 t = tanh_h2(__hmul2(zc, p));
+    const __half2 h = __hmul2(z, __float2half2_rn(0.5f));
+    a = __hfma2(h, t, h);
+    if (GRAD) {
+        __half2 up = __hfma2(s, __float2half2_rn(5.f * kGelu3), __float2half2_rn(3.f * kGelu2));
+        up = __hfma2(up, s, __float2half2_rn(kGelu1));
+        const __half2 sech2 = __hfma2(__hneg2(t), t, __float2half2_rn(1.f));
+        const __half2 Phi = __hfma2(t, __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+        g = __hfma2(__hmul2(__hmul2(zc, __float2half2_rn(0.5f)), sech2), up, Phi);
+    }
+}
+// ReLU twin: a = max(z, 0), g = z > 0
+template <bool GRAD>
+__device__ __forceinline__ void relu_h2(__half2 z, __half2& a, __half2& g) {
+    a = __hmax2(z, __float2half2_rn(0.f));
+    if (GRAD) g = __hgt2(z, __float2half2_rn(0.f));
+}
+// (lo, hi) -> half2 with saturation to the largest finite fp16 (a later product with an exact 0 must not meet an infinity)
+__device__ __forceinline__ __half2 floats2half2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 __device__ __forceinline__ float gelu_fwd(float x) {
     float a0, a1, g0, g1;
     gelu_pair<false>(x, x, a0, a1, g0, g1);
