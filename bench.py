@@ -5,11 +5,13 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic rays on every rank (rays are sharded, weak scaling):
-  K-layer shell intersection (one launch) -> hit packing -> face normals -> rgb head + alpha head (tcgen05 MLPs) ->
-  fused compositing forward -> L1 loss gradient -> fused compositing backward (d_alpha, d_rgb per hit) -> backward of both heads
-  (tcgen05: Linear weight/bias gradients + gradients of the positional features) -> (N > 1) NCCL all-reduce of the head gradients.
+  K-layer shell intersection (one launch) -> hit packing -> face normals -> permutohedral hash encoding of the hit points (one encoder
+  per head, as volsurfs_py/models/rgb.py:40-60) -> rgb head + alpha head (tcgen05 MLPs) -> fused compositing forward -> L1 loss gradient
+  -> fused compositing backward (d_alpha, d_rgb per hit) -> backward of both heads (tcgen05: Linear weight/bias gradients + gradients of
+  the positional features) -> backward of both encoders (lattice gradients) -> (N > 1) NCCL all-reduce (mean) of the head AND lattice
+  gradients, captured inside the step's CUDA graph: the colour branch's 50 MB reduce runs on a side stream under the alpha branch's backward.
 Workload at every N: BASELINE config[1] per GPU — 800x800 camera rays against 5 nested ~100k-triangle shells, legacy
-[128,128,64] GELU heads on 51 positional features (synthetic stand-in for the permutohedral encoder) + SH deg 3.
+[128,128,64] GELU heads on the 51 features of a 24-level x 2, 2^18-entry permutohedral encoder + SH deg 3.
 
 Prints ONE JSON line (rank 0).  `value` is the device-resident whole-job throughput, `e2e` the same step driven from pinned
 host ray buffers with the image copied back, `roofline` describes the dominant kernel of the step, `stages` every stage,
@@ -38,6 +40,9 @@ IMG = 800
 HIDDEN = (128, 128, 64)
 POS_DIM = 51
 CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of this workload at HEAD (profiles/r02_*.md)
+NCU_TRAFFIC = {"mlp_fwd_kernel": None, "mlp_bwd_stashed_kernel": None, "shells_trace_kernel": 45.03552e6 + 22.207488e6,
+               "permuto_fwd_kernel": None, "permuto_bwd_kernel": None, "composite_tile_fwd+bwd": None}
 
 
 _JSON_FD = None
@@ -152,13 +157,19 @@ class CpuReferencePath:
         self.rgb_w = oa.init_linear_stack(POS_DIM + 16, HIDDEN, 3, seed=11)
         self.alpha_w = oa.init_linear_stack(POS_DIM + 16, HIDDEN, 1, seed=12)
         g = torch.Generator().manual_seed(13)
-        self.feats = (torch.rand(n_rays, K_LAYERS, POS_DIM, generator=g) * 2 - 1).requires_grad_(True)
+        from oracle import permuto as op
+
+        self.op = op
+        # one permutohedral encoder per head (rgb.py:40-60; encodings/permutohash.py:10-41): 24 levels x 2, 2^18 entries, concat points
+        self.encs = [op.PermutoEncoding(3, 2 ** 18, 24, 2, np.geomspace(1.0, 1e-4, 24), True, True, 1.0, seed=21 + i) for i in range(2)]
+        self.lattice_grads = [np.zeros_like(e.lattice_values) for e in self.encs]
         for stack in (self.rgb_w, self.alpha_w):
             for lst in stack:
                 for t in lst:
                     t.requires_grad_(True)
         self.gt = torch.rand(n_rays, 3, generator=g)
         self.cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(self.cores))
 
     def step(self):
         torch, np, oa = self.torch, self.np, self.oa
@@ -166,8 +177,10 @@ class CpuReferencePath:
 
         N, K = self.n_rays, K_LAYERS
         o, d = self.o.numpy(), self.d.numpy()
+        op = self.op
         surfs_rgb = torch.zeros(N, K, 3)
         surfs_alpha = torch.zeros(N, K, 1)
+        leaves = []
         for i in range(K):                                        # volsurfs.py:476-485
             res = self.tracer.trace(o, d, i, mode="bvh")
             if not res["any_hit"]:
@@ -175,16 +188,29 @@ class CpuReferencePath:
             hits = torch.from_numpy(res["is_hit"])
             normals = torch.from_numpy(res["normals"])[hits]
             dirs = self.d[hits]
-            f = self.feats[hits, i]                               # leaf [N,K,F] requires grad: encoder-output gradient
-            rgb = oa.head_forward(f, dirs, normals, *self.rgb_w)
-            alpha = oa.alpha_decay(oa.head_forward(f, dirs, normals, *self.alpha_w), dirs, normals)
+            unit, _ = op.volsurfs_points_to_unit_cube(res["positions"][res["is_hit"]], 2.0)   # permutohash.py:77-86
+            feats = []
+            for e in self.encs:                                   # encoder forward (C twin of the numpy oracle, all host threads)
+                rows = op.forward_rows_c(unit, e.lattice_values, e.scale, e.random_shift_per_level, e.anneal_window, True, 1.0)
+                feats.append(torch.from_numpy(rows[:, :POS_DIM].copy()).requires_grad_(True))   # permutohash.py:91-94: last column dropped
+            leaves.append((unit, feats))
+            rgb = oa.head_forward(feats[0], dirs, normals, *self.rgb_w)
+            alpha = oa.alpha_decay(oa.head_forward(feats[1], dirs, normals, *self.alpha_w), dirs, normals)
             surfs_rgb = surfs_rgb.index_put((hits, torch.tensor(i)), rgb)
             surfs_alpha = surfs_alpha.index_put((hits, torch.tensor(i)), alpha)
         out = dense_composite_torch(surfs_alpha, surfs_rgb, rgb_bg=torch.ones(N, 3))   # volsurfs.py:601-640,708 (fp32 variant)
         loss = (out["rgb"] - self.gt).abs().mean()                                       # utils/losses.py:14-19
-        for t in [self.feats, *self.rgb_w[0], *self.rgb_w[1], *self.alpha_w[0], *self.alpha_w[1]]:
+        for t in [*self.rgb_w[0], *self.rgb_w[1], *self.alpha_w[0], *self.alpha_w[1]]:
             t.grad = None
         loss.backward()                                           # autograd: compositing + both heads (weights, biases, features)
+        for t in self.lattice_grads:
+            t.fill(0.0)
+        for unit, feats in leaves:                                # encoder backward: feature gradients -> lattice gradients
+            for k, e in enumerate(self.encs):
+                g = np.zeros((unit.shape[0], 2 * 26), np.float32)
+                g[:, :POS_DIM] = feats[k].grad.numpy()
+                op.backward_lattice_c(unit, e.lattice_values.shape, e.scale, e.random_shift_per_level, e.anneal_window, g,
+                                      out=self.lattice_grads[k])
         return float(loss.detach())
 
 
@@ -216,10 +242,13 @@ def workload_config(args, world):
     return {
         "workload": f"BASELINE config[1]: 5-mesh volsurf render of kitten-shaped synthetic shells (~100k tris/layer), {IMG}x{IMG} rays per GPU",
         "rays_per_gpu": IMG * IMG, "layers": K_LAYERS, "triangles_per_layer": 99904, "heads": f"rgb+alpha legacy MLP {list(HIDDEN)} GELU, "
-        f"{POS_DIM} positional features (synthetic encoder output) + SH deg 3",
-        "step": "trace(K layers, 1 launch) + pack + normals + 2 MLP heads fwd + composite fwd + L1 grad + composite bwd + 2 MLP heads bwd "
-                "(dW, db, d_features)" + (" + NCCL all-reduce of the head gradients" if world > 1 else ""),
-        "parallelism": f"rays sharded over {world} GPU(s); no data-path collective in rendering, one gradient all-reduce per step in training", "l2": "inputs_larger_than_l2 (653 MB features + 200 MB packed arrays per step)",
+        f"{POS_DIM} positional features of a permutohedral hash encoder per head (24 levels x 2, 2^18 entries) + SH deg 3",
+        "step": "trace(K layers, 1 launch) + pack + normals + 2 encoders fwd + 2 MLP heads fwd + composite fwd + L1 grad + composite bwd + "
+                "2 MLP heads bwd (dW, db, d_features) + 2 encoders bwd (lattice gradients)"
+                + (" + NCCL all-reduce (mean) of the head and lattice gradients inside the step's graph" if world > 1 else ""),
+        "parallelism": f"rays sharded over {world} GPU(s) (every rank renders the same 800x800 view: equal hit counts); no data-path "
+                       "collective in rendering, one gradient all-reduce per step in training (100.8 MB of fp32 lattice + head gradients)",
+        "l2": "inputs_larger_than_l2 (2 x 182 MB features, 2 x 743 MB activation stash, 200 MB packed arrays, 2 x 50 MB lattices per step)",
     }
 
 
@@ -242,73 +271,106 @@ def run_ours(args, rank, world, local_rank):
     pk = peaks()
 
     renderer, _ = make_synthetic_renderer(K=K_LAYERS, hidden=HIDDEN, pos_dim=POS_DIM)
-    o_h, d_h = camera_rays(IMG, IMG, azimuth_deg=30.0 + 40.0 * rank)   # every rank renders its own view
+    # every rank renders the same view (equal hit counts: the max-over-ranks step time then shows the exchange, not view imbalance)
+    o_h, d_h = camera_rays(IMG, IMG, azimuth_deg=30.0)
     N = o_h.shape[0]
     o_pin, d_pin = o_h.pin_memory(), d_h.pin_memory()
     rays_o, rays_d = o_h.to(dev), d_h.to(dev)
     g = torch.Generator().manual_seed(100 + rank)
-    feats = (torch.rand(N * K_LAYERS, POS_DIM, generator=g) * 2 - 1).to(dev)
     gt = torch.rand(N, 3, generator=g).to(dev)
     img_pin = torch.empty((N, 3), dtype=torch.float32).pin_memory()
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
 
-    from volsurfs_b200.dist import GradAllReducer
+    from volsurfs_b200.encoding import PermutoHashEncoder
 
-    stage_names = ["trace", "pack+normals", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad", "composite_bwd", "mlp_bwd_rgb",
-                   "mlp_bwd_alpha", "grad_allreduce"]
+    torch.manual_seed(4321)  # identical initial parameters on every rank
+    encs = {"rgb": PermutoHashEncoder(bb_sides=2.0, device=dev), "alpha": PermutoHashEncoder(bb_sides=2.0, device=dev)}
+    for e in encs.values():  # the reference starts the lattice at N(0, 1e-5) (modules.py:39-41): features ~0; give the heads a signal
+        with torch.no_grad():
+            e.encoder.lattice_values.normal_(0.0, 0.1)
+    assert encs["rgb"].output_dim == POS_DIM
+    heads = {"rgb": renderer.rgb_head, "alpha": renderer.alpha_head}
+    S_cap = N * K_LAYERS
+
+    stage_names = ["trace", "pack+normals", "encode_rgb", "encode_alpha", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad",
+                   "composite_bwd", "mlp_bwd_rgb", "lattice_bwd_rgb", "mlp_bwd_alpha", "lattice_bwd_alpha", "grad_allreduce"]
     n_marks = len(stage_names) + 1
-    grad_rgb = torch.zeros(renderer.rgb_head.num_params(), device=dev)
-    grad_alpha = torch.zeros(renderer.alpha_head.num_params(), device=dev)
-    dfeat_rgb, dfeat_alpha = torch.empty_like(feats), torch.empty_like(feats)
-    stash_rgb = renderer.rgb_head.new_stash(N * K_LAYERS, dev)        # activations kept by the training-mode forward for the backward
-    stash_alpha = renderer.alpha_head.new_stash(N * K_LAYERS, dev)
-    reducer = GradAllReducer()
-    ev = None
+    feats = {k: torch.zeros((S_cap, POS_DIM), device=dev) for k in heads}
+    dfeat = {k: torch.zeros((S_cap, POS_DIM), device=dev) for k in heads}
+    grad_head = {k: torch.zeros(h.num_params(), device=dev) for k, h in heads.items()}
+    grad_lat = {k: torch.zeros_like(e.encoder.lattice_values) for k, e in encs.items()}
+    stash = {k: h.new_stash(S_cap, dev) for k, h in heads.items()}   # activations kept by the training-mode forward for the backward
+    ar_stream = torch.cuda.Stream(device=dev)
+    allreduce_bytes = sum(t.numel() * 4 for t in list(grad_head.values()) + list(grad_lat.values()))
+
+    def all_reduce_branch(name):
+        """mean all-reduce of one branch's gradients (lattice: 50.3 MB, head: 0.14 MB) on the current stream"""
+        dist.all_reduce(grad_lat[name], op=dist.ReduceOp.AVG)
+        dist.all_reduce(grad_head[name], op=dist.ReduceOp.AVG)
 
     @torch.no_grad()  # forward and backward kernels are driven explicitly; no autograd graph in the timed region
-    def step(record=None, reduce=True):
+    def step(record=None, reduce=True, o=None, d=None):
+        from volsurfs_b200.raytracer import pack_layer_hits
+
+        o = rays_o if o is None else o
+        d = rays_d if d is None else d
+
         def mark(i):
             if record is not None:
                 record[i].record()
 
+        main = torch.cuda.current_stream()
         mark(0)
-        rec = renderer.tracer.trace_layers(rays_o, rays_d)
+        rec = renderer.tracer.trace_layers(o, d)
         mark(1)
-        from volsurfs_b200.raytracer import pack_layer_hits
-
         rsp = pack_layer_hits(rec["rays_o"], rec["rays_d"], rec["depth"], rec["tri"], rec["u"], rec["v"], t_far=renderer.tracer.t_far,
                               exact_size=False)
         S = rsp.get_max_nr_samples()
         rsp.samples_normals = torch.empty((S, 3), dtype=torch.float32, device=dev)
         _lib.check(lib.vs_shells_sample_normals(renderer.tracer._handle, rsp.samples_layer.data_ptr(), rsp.samples_triangle.data_ptr(), S,
-                                                rsp.total_dev.data_ptr(), rsp.samples_normals.data_ptr(),
-                                                torch.cuda.current_stream().cuda_stream), "normals")
+                                                rsp.total_dev.data_ptr(), rsp.samples_normals.data_ptr(), main.cuda_stream), "normals")
         mark(2)
-        rgb, _ = renderer.rgb_head.forward_train(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash_rgb)
-        mark(3)
-        alpha, _ = renderer.alpha_head.forward_train(feats, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash_alpha)
-        mark(4)
-        out = renderer.composite(rsp, alpha, rgb)
+        for i, k in enumerate(("rgb", "alpha")):   # permutohash.py:68-96: bounding-box normalisation + lattice slice, one launch
+            e = encs[k].encoder
+            e._launch_forward(e.lattice_values, rsp.samples_3d, encs[k].window(None), POS_DIM, encs[k].bb_sides, rsp.total_dev, out=feats[k])
+            mark(3 + i)
+        rgb, _ = heads["rgb"].forward_train(feats["rgb"], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash["rgb"])
         mark(5)
+        alpha, _ = heads["alpha"].forward_train(feats["alpha"], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev,
+                                                stash=stash["alpha"])
+        mark(6)
+        out = renderer.composite(rsp, alpha, rgb)
+        mark(7)
         diff = out["rgb"] - gt
         loss = diff.abs().mean()
         g_pred = torch.sign(diff) / diff.numel()
-        mark(6)
-        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
-        mark(7)
-        renderer.rgb_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_rgb, grad_rgb, dfeat_rgb, False, rsp.total_dev,
-                                        stash=stash_rgb, fwd_out=rgb)
-        if reduce:
-            reducer.launch([grad_rgb])   # overlaps the alpha head's backward
         mark(8)
-        renderer.alpha_head.backward_into(feats, rsp.samples_dirs, rsp.samples_normals, d_alpha, grad_alpha, dfeat_alpha, False, rsp.total_dev,
-                                          stash=stash_alpha, fwd_out=alpha)
-        if reduce:
-            reducer.launch([grad_alpha])
+        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
         mark(9)
-        if reduce:
-            reducer.wait()
-        mark(10)
+        fwd_out, d_out = {"rgb": rgb, "alpha": alpha}, {"rgb": d_rgb, "alpha": d_alpha}
+        for i, k in enumerate(("rgb", "alpha")):
+            heads[k].backward_into(feats[k], rsp.samples_dirs, rsp.samples_normals, d_out[k], grad_head[k], dfeat[k], False, rsp.total_dev,
+                                   stash=stash[k], fwd_out=fwd_out[k])
+            mark(10 + 2 * i)
+            if reduce and world > 1 and k == "alpha":
+                # the colour branch's exchange (50 MB) runs on the side stream under the alpha branch's LATTICE backward (a grid of many
+                # small CTAs); under the persistent one-CTA-per-SM head kernel NCCL's CTAs delayed whole tiles (measured: +0.12 ms)
+                ar_stream.wait_event(ar_ready)
+                with torch.cuda.stream(ar_stream):
+                    all_reduce_branch("rgb")
+            e = encs[k].encoder
+            grad_lat[k].zero_()
+            e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
+                               want_lattice=True, d_lattice=grad_lat[k])
+            mark(11 + 2 * i)
+            if reduce and world > 1 and k == "alpha":
+                all_reduce_branch("alpha")
+                main.wait_stream(ar_stream)
+            if reduce and world > 1 and k == "rgb":
+                ar_ready = torch.cuda.Event()
+                ar_ready.record(main)
+        mark(14)
+        out["loss"] = loss
         return out, loss, rsp
 
     def barrier():
@@ -323,41 +385,51 @@ def run_ours(args, rank, world, local_rank):
     n_hits = int(rsp.total_dev.item())
     assert not renderer.tracer.overflowed()
 
-    # ---- the step as ONE CUDA graph: ~45 launches of 3-700 us each leave the device waiting for the Python host otherwise
-    # (measured: 3.02 ms per eager step against 2.6 ms of kernel time).  Stage boundaries are external event-record nodes inside
-    # the graph.  With N > 1 the gradient all-reduce (NCCL) follows the graph on the same stream.
+    # ---- the step as ONE CUDA graph: ~60 launches of 3-700 us each leave the device waiting for the Python host otherwise.  Stage
+    # boundaries are external event-record nodes inside the graph.  With N > 1 the NCCL all-reduces are captured INSIDE the graph (the
+    # colour branch's on a forked side stream); if this NCCL / torch build refuses to capture collectives the exchange follows the graph.
     use_graph = not args.no_graph
     graph = graph_e2e = None
+    reduce_in_graph = world > 1
     ext = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(n_marks)]
     kernels_per_step = None
-    if use_graph:
-        try:
-            c0 = lib.vs_launch_count()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g_out, g_loss, g_rsp = step(ext, reduce=False)
-            kernels_per_step = lib.vs_launch_count() - c0
-            graph_e2e = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph_e2e):
-                rays_o.copy_(o_pin, non_blocking=True)
-                rays_d.copy_(d_pin, non_blocking=True)
-                e_out, e_loss, _ = step(None, reduce=False)
-                img_pin.copy_(e_out["rgb"], non_blocking=True)
-                loss_pin.copy_(e_loss, non_blocking=True)
-        except Exception as exc:  # noqa: BLE001
-            print(f"[bench] CUDA graph capture failed ({exc!r}); running eagerly", file=sys.stderr, flush=True)
-            torch.cuda.synchronize()
-            use_graph, graph, graph_e2e = False, None, None
 
-    def all_reduce_grads():
-        if world > 1:
-            reducer.launch([grad_rgb, grad_alpha])
-            reducer.wait()
+    def capture(with_reduce):
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            res = step(ext, reduce=with_reduce)
+        return gph, res
+
+    if use_graph:
+        c0 = lib.vs_launch_count()
+        try:
+            graph, (g_out, g_loss, g_rsp) = capture(reduce_in_graph)
+        except Exception as exc:  # noqa: BLE001
+            torch.cuda.synchronize()
+            if reduce_in_graph:
+                print(f"[bench] capturing the NCCL all-reduce in the graph failed ({exc!r}); exchange after the graph", file=sys.stderr, flush=True)
+                reduce_in_graph = False
+                try:
+                    c0 = lib.vs_launch_count()
+                    graph, (g_out, g_loss, g_rsp) = capture(False)
+                except Exception as exc2:  # noqa: BLE001
+                    print(f"[bench] CUDA graph capture failed ({exc2!r}); running eagerly", file=sys.stderr, flush=True)
+                    torch.cuda.synchronize()
+                    use_graph, graph = False, None
+            else:
+                print(f"[bench] CUDA graph capture failed ({exc!r}); running eagerly", file=sys.stderr, flush=True)
+                use_graph, graph = False, None
+        kernels_per_step = lib.vs_launch_count() - c0 if use_graph else None
+
+    def all_reduce_after_graph():
+        if world > 1 and not reduce_in_graph:
+            all_reduce_branch("rgb")
+            all_reduce_branch("alpha")
 
     def run_step(record=None):
         if use_graph:
             graph.replay()
-            all_reduce_grads()
+            all_reduce_after_graph()
         else:
             step(record)
 
@@ -392,10 +464,10 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             per.append([ext[i].elapsed_time(ext[i + 1]) for i in range(n_marks - 1)])
         stage_ms = [statistics.mean(p[i] for p in per) for i in range(n_marks - 1)]
-        if world > 1:
+        if world > 1 and not reduce_in_graph:
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
-            all_reduce_grads()
+            all_reduce_after_graph()
             a1.record()
             torch.cuda.synchronize()
             stage_ms[-1] = a0.elapsed_time(a1)
@@ -410,29 +482,24 @@ def run_ours(args, rank, world, local_rank):
         try:
             from volsurfs_b200.pipeline import PipelinedTrainingStep
 
-            loop = PipelinedTrainingStep(renderer, o_pin, d_pin, feats, gt, img_pin, loss_pin)
-            e2e_mode = "PipelinedTrainingStep: 2 alternating CUDA graphs, H2D of the next step's rays and D2H of the previous step's image + loss on copy streams forked inside the graph"
+            loop = PipelinedTrainingStep(renderer, o_pin, d_pin, None, gt, img_pin, loss_pin,
+                                         step_fn=lambda o, d: step(None, reduce=reduce_in_graph, o=o, d=d)[0])
+            e2e_mode = ("PipelinedTrainingStep: 2 alternating CUDA graphs, H2D of the next step's rays and D2H of the previous step's image + "
+                        "loss on copy streams forked inside the graph")
         except Exception as exc:  # noqa: BLE001
-            print(f"[bench] pipelined e2e capture failed ({exc!r}); using the single-stream graph", file=sys.stderr, flush=True)
+            print(f"[bench] pipelined e2e capture failed ({exc!r}); eager e2e", file=sys.stderr, flush=True)
             torch.cuda.synchronize()
             loop = None
-            e2e_mode = "one CUDA graph per step, copies in line with the kernels"
 
     def e2e_run(n_steps):
         if loop is not None:
             loop.prime()
             for i in range(n_steps):
-                o = loop.step(i)
-                if world > 1:
-                    reducer.launch([o["grad_rgb"], o["grad_alpha"]])
-                    reducer.wait()
+                loop.step(i)
+                all_reduce_after_graph()
             loop.drain(n_steps)
             return
         for _ in range(n_steps):
-            if use_graph:
-                graph_e2e.replay()
-                all_reduce_grads()
-                continue
             rays_o.copy_(o_pin, non_blocking=True)
             rays_d.copy_(d_pin, non_blocking=True)
             out_e, loss_e, _ = step()
@@ -468,18 +535,20 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_rays * args.steps / (ms_e2e * 1e-3) / 1e6
 
     # ---- per-stage rooflines (rank 0's numbers)
-    S_cap = N * K_LAYERS
     flops_head = lambda out_dim: 2.0 * n_hits * (67 * 128 + 128 * 128 + 128 * 64 + 64 * out_dim)  # noqa: E731
+    enc_bytes = n_hits * (12 + POS_DIM * 4)                 # compulsory: point in, feature row out (the 24 x 4 lattice gathers hit L2)
     stage_alg = {
         "trace": ("hbm", N * K_LAYERS * (24 + 16)),                                   # rays in, (t, face, u, v) out per (ray, layer)
         "pack+normals": ("hbm", N * (16 * K_LAYERS + 8 + 24) + n_hits * (4 + 4 + 12 + 12 + 4 + 4 + 8 + 12)),
+        "encode_rgb": ("hbm", enc_bytes), "encode_alpha": ("hbm", enc_bytes),
         "mlp_rgb": ("tensor", flops_head(3)),
         "mlp_alpha": ("tensor", flops_head(1)),
         "composite_fwd": ("hbm", 32 * N + 20 * n_hits),
         "loss_grad": ("hbm", N * 12 * 6),
         "composite_bwd": ("hbm", 32 * N + 36 * n_hits),
-        "mlp_bwd_rgb": ("tensor", 2.0 * flops_head(3)),                               # dA + dW GEMMs (the recomputation is not counted)
+        "mlp_bwd_rgb": ("tensor", 2.0 * flops_head(3)),                               # dA + dW GEMMs
         "mlp_bwd_alpha": ("tensor", 2.0 * flops_head(1)),
+        "lattice_bwd_rgb": ("hbm", enc_bytes + 2 ** 18 * 24 * 8), "lattice_bwd_alpha": ("hbm", enc_bytes + 2 ** 18 * 24 * 8),
         "grad_allreduce": ("hbm", 0.0),
     }
     stages = {}
@@ -491,9 +560,15 @@ def run_ours(args, rank, world, local_rank):
             ach, peak, unit = alg / (ms * 1e-3) / 1e12, pk["tflops_sustained"], "TFLOP/s"
         stages[name] = {"ms": round(ms, 4), "share": round(ms / sum(stage_ms), 3), "bound": bound, "achieved": round(ach, 2), "peak": peak,
                         "unit": unit, "frac": round(ach / peak, 4)}
+    if world > 1:
+        stages["grad_allreduce"]["note"] = (
+            f"exposed tail only: {allreduce_bytes / 1e6:.1f} MB of fp32 gradients per step, the colour branch's half overlapped with the alpha "
+            "branch's backward on a side stream" + ("" if reduce_in_graph else " (NOT captured: exchange after the graph)"))
     # the dominant KERNEL of the step: stages that launch the same kernel are summed (both heads run mlp_fwd_kernel / mlp_bwd_stashed_kernel)
     kernel_of = {"trace": "shells_trace_kernel", "mlp_rgb": "mlp_fwd_kernel", "mlp_alpha": "mlp_fwd_kernel",
-                 "mlp_bwd_rgb": "mlp_bwd_stashed_kernel", "mlp_bwd_alpha": "mlp_bwd_stashed_kernel"}
+                 "mlp_bwd_rgb": "mlp_bwd_stashed_kernel", "mlp_bwd_alpha": "mlp_bwd_stashed_kernel",
+                 "encode_rgb": "permuto_fwd_kernel", "encode_alpha": "permuto_fwd_kernel",
+                 "lattice_bwd_rgb": "permuto_bwd_kernel", "lattice_bwd_alpha": "permuto_bwd_kernel"}
     per_kernel = {}
     for name, kern in kernel_of.items():
         per_kernel.setdefault(kern, []).append(name)
@@ -511,9 +586,8 @@ def run_ours(args, rank, world, local_rank):
                 "launches_per_step": len(dom_stages), "ms_per_launch": round(dom_ms, 4),
                 "share_of_step": round(sum(stages[n]["ms"] for n in dom_stages) / sum(stage_ms), 3)}
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the stage's kernel from the ncu --set full captures of
-    # this same workload (profiles/r01_mlp_fwd_v4.md, r01_mlp_bwd_v3.md, r01_shells_trace_v2.md); None where no capture exists
-    ncu_traffic = {"mlp_rgb": 212.285952e6 + 1.274396e9, "mlp_alpha": 212.285952e6 + 1.274396e9, "mlp_bwd_rgb": 1.335758e9 + 188.86016e6,
-                   "mlp_bwd_alpha": 1.335758e9 + 188.86016e6, "trace": 45.03552e6 + 22.207488e6}
+    # this same workload at HEAD (profiles/r02_*.md); None where no capture exists
+    ncu_traffic = NCU_TRAFFIC
     if dom_kernel in ("mlp_fwd_kernel", "mlp_bwd_stashed_kernel"):
         # the training-mode head kernels also stream the activation stash (what autograd keeps for the backward): their HBM view.
         # forward: features in + stash out + outputs; backward: stash in + upstream gradient + forward output in, feature gradient out
@@ -522,16 +596,16 @@ def run_ours(args, rank, world, local_rank):
         hb = (stash_b + io) / (dom_ms * 1e-3) / 1e9
         roofline["hbm_view"] = {"bound": "hbm", "achieved": round(hb, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(hb / pk["hbm_gbs"], 4),
                                 "bytes_per_launch": int(stash_b + io),
-                                "note": "same launch against the HBM roofline: activation stash + features + outputs (algorithmic bytes of a "
-                                        "training-mode launch); the kernel sits between its two rooflines (epilogue ALU bound)"}
-    roofline.update(kernel=dom_kernel, traffic=ncu_traffic.get(dominant), peak_source=pk["source"],
+                                "note": "same launch against the HBM roofline: activation stash (832 B per hit) + features + outputs"}
+    roofline.update(kernel=dom_kernel, traffic=ncu_traffic.get(dom_kernel), peak_source=pk["source"],
                     note="algorithmic flops (or bytes) of one launch over the stage's mean CUDA-event duration inside the timed region "
                          "(event-record nodes of the replayed graph); traffic = DRAM bytes of one launch from the ncu capture in profiles/")
 
     # ---- the headline compositing kernels at the size SURVEY 8d prescribes (2^24 rays x 5, traffic >> L2)
     comp = None
     if not args.skip_composite_roofline:
-        del feats, dfeat_rgb, dfeat_alpha, stash_rgb, stash_alpha
+        feats.clear(), dfeat.clear(), stash.clear()
+        del loop, graph
         torch.cuda.empty_cache()
         n_big = 1 << 24
         d = all_hit_packed(n_big, K_LAYERS)
@@ -600,22 +674,29 @@ def run_ours(args, rank, world, local_rank):
         dt = time.perf_counter() - t0
         cpu = {"value": round(path.n_rays * reps / dt / 1e6, 4), "unit": UNIT, "cores": path.cores, "kind": "port",
                "sample": f"{reps} steps x {path.n_rays} rays (rows through the image centre) of the same workload; oracle port of the "
-                         "reference algorithm (C BVH tracer with OpenMP, torch CPU heads, dense torch compositing, autograd through compositing and heads)"}
+                         "reference algorithm (C BVH tracer with OpenMP, C permutohedral encoders with OpenMP, torch CPU heads, dense torch compositing, autograd "
+                         "through compositing and heads, encoder backward)"}
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (ray/triangle, packing, compositing); f16 operands x f32 accumulate (MLP heads)", "data": "synthetic",
-        "config": workload_config(args, world) | {"hits_per_step_all_ranks": n_hits_all},
+        "config": workload_config(args, world) | {"hits_per_step_all_ranks": n_hits_all, "allreduce_bytes_per_step": allreduce_bytes if world > 1 else 0,
+                                                  "allreduce_in_graph": bool(reduce_in_graph) if world > 1 else None},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(N * 24), "d2h_bytes_per_step": int(N * 12 + 4),
                 "ms_per_step": round(ms_e2e / args.steps, 4), "mode": e2e_mode,
-                "note": "pinned host rays -> device every step, composited image + loss -> pinned host every step; the positional "
-                        "features are produced on the device by the encoder stage and stay device-resident"},
+                "note": "pinned host rays -> device every step, composited image + loss -> pinned host every step; everything between "
+                        "(hits, encoder features, head outputs, gradients) is produced and consumed on the device"},
         "gpu_launches": int(launches),
         "launch_mode": ("one CUDA graph per step (%d kernels of this library per step + torch elementwise ops)" % kernels_per_step) if use_graph
                        else "eager (one Python call per kernel)",
         "roofline": roofline,
+        "roofline_hbm": None if comp is None else {
+            "kernel": "composite_fwd_tile_kernel<TMA> + composite_bwd_tile_kernel<TMA>", "bound": "hbm", "achieved": comp["achieved"],
+            "peak": comp["peak"], "unit": "GB/s", "frac": comp["frac"], "traffic": NCU_TRAFFIC.get("composite_tile_fwd+bwd"),
+            "note": "BASELINE's '% of HBM roofline': fused compositing fwd+bwd at 2^24 rays x 5 samples, algorithmic bytes 64 + 56 s per ray "
+                    "(SURVEY 8d) over CUDA-event time; traffic = DRAM bytes of the pair of launches from the ncu capture"},
         "stages": stages,
         "compositing_roofline": comp,
         "cpu_baseline": cpu,

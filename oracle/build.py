@@ -26,6 +26,26 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+PERMUTO_C_SRC = HERE / "permuto_oracle.c"
+PERMUTO_C_LIB = OUT_DIR / "libpermuto_oracle.so"
+
+
+def build_permuto_c(force: bool = False) -> Path:
+    """gcc-compile oracle/permuto_oracle.c (the C twin of oracle/permuto.py used by bench.py's CPU baseline)"""
+    if PERMUTO_C_LIB.exists() and not force and PERMUTO_C_LIB.stat().st_mtime >= PERMUTO_C_SRC.stat().st_mtime:
+        return PERMUTO_C_LIB
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        raise RuntimeError("gcc not found")
+    OUT_DIR.mkdir(exist_ok=True)
+    cmd = [gcc, "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC", str(PERMUTO_C_SRC), "-o",
+           str(PERMUTO_C_LIB), "-lm"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"gcc failed:\n{res.stdout}")
+    return PERMUTO_C_LIB
+
+
 # ---- oracle/_ref: the reference's own packed volume-rendering kernels behind a C harness -------------------------------------
 REFERENCE = Path("/root/reference")
 REF_SRC = HERE / "ref_harness.cu"
@@ -163,6 +183,7 @@ def build_ref_raytrace(force: bool = False):
 
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_permuto_c(force=True))
     print(build_ref())
     print(build_ref_permuto())
     print(build_ref_sampler())

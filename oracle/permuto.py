@@ -239,3 +239,48 @@ def volsurfs_points_to_unit_cube(points, bb_sides=2.0):
     oob = np.logical_or((p <= -half).any(axis=1), (p >= half).any(axis=1))
     scaled = (p * (F(1) / half)).astype(F)
     return ((scaled + F(1)) / F(2)).astype(F), oob
+
+
+# ---- the C twin (oracle/permuto_oracle.c): same arithmetic with fma=False, all host threads; used by bench.py's CPU baseline --------------
+_clib = None
+
+
+def _c():
+    global _clib
+    if _clib is None:
+        import ctypes
+
+        from . import build as _build
+
+        lib = ctypes.CDLL(str(_build.build_permuto_c()))
+        P, I64, I, Fl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+        lib.vpo_forward.argtypes = [P, I64, I, P, I, I64, P, P, P, I, Fl, P]
+        lib.vpo_backward_lattice.argtypes = [P, I64, I, I, I64, P, P, P, P, I, P]
+        _clib = lib
+    return _clib
+
+
+def forward_rows_c(positions, lattice_values, scale, shift, window, concat_points=True, points_scaling=1.0):
+    """``to_rows(forward(...))`` computed by the C twin: [N, 2*(L+extra)]"""
+    pos = np.ascontiguousarray(positions, F)
+    lat = np.ascontiguousarray(lattice_values, F)
+    sc, sh, w = (np.ascontiguousarray(x, F) for x in (scale, shift, window))
+    n, d = pos.shape
+    L, cap, _ = lat.shape
+    out = np.empty((n, 2 * (L + n_extra_levels(d, 2, concat_points))), F)
+    _c().vpo_forward(pos.ctypes.data, n, d, lat.ctypes.data, L, cap, sc.ctypes.data, sh.ctypes.data, w.ctypes.data, int(concat_points),
+                     float(points_scaling), out.ctypes.data)
+    return out
+
+
+def backward_lattice_c(positions, lattice_shape, scale, shift, window, grad_rows, out=None):
+    """lattice gradient [L,capacity,2] from the gradient of the rows ([N, 2*(L+extra)]), C twin; ``out``: accumulate into this table"""
+    pos = np.ascontiguousarray(positions, F)
+    g = np.ascontiguousarray(grad_rows, F)
+    sc, sh, w = (np.ascontiguousarray(x, F) for x in (scale, shift, window))
+    n, d = pos.shape
+    L, cap, _ = lattice_shape
+    g_lat = np.zeros((L, cap, 2), F) if out is None else out
+    _c().vpo_backward_lattice(pos.ctypes.data, n, d, L, cap, sc.ctypes.data, sh.ctypes.data, w.ctypes.data, g.ctypes.data, g.shape[1],
+                              g_lat.ctypes.data)
+    return g_lat

@@ -12,7 +12,10 @@ from volsurfs_b200.volsurfs import RaySamplesPacked, VolumeRendering as VR  # no
 
 modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1]
 which = sys.argv[2] if len(sys.argv) > 2 else "shells"
-d = all_hit_packed(1 << 22, 5) if which == "shells" else nerf_packets(200000, seed_offset=3)
+# shells: 2^22 rays x 5; shells24: the roofline size of SURVEY 8d (2^24 rays x 5, 5.8 GB of traffic per fwd+bwd pair); nerf: 200 k rays of
+# config[2]-shaped packets; nerf640k: BASELINE config[2] itself (640 k rays, ~59 M samples)
+d = {"shells": lambda: all_hit_packed(1 << 22, 5), "shells24": lambda: all_hit_packed(1 << 24, 5),
+     "nerf": lambda: nerf_packets(200000, seed_offset=3), "nerf640k": lambda: nerf_packets(640000, seed_offset=3)}[which]()
 rsp = RaySamplesPacked(0, 0, 0, 1)
 rsp.ray_start_end_idx = d["se"].cuda()
 a, c, z = d["alpha"].cuda(), d["rgb"].cuda(), d["z"].cuda()

@@ -147,3 +147,23 @@ def test_host_mirror_shapes_without_gpu():
         enc(torch.rand(8, 3))
     with pytest.raises(RuntimeError):
         ve.PermutoEncoding(3, 1024, 2, 4, [1.0, 0.5])
+
+
+def test_c_twin_equals_the_numpy_oracle():
+    """oracle/permuto_oracle.c (bench.py's multi-threaded CPU baseline of the encoder) against oracle/permuto.py with fma=False: forward
+    rows bit for bit, lattice gradient bit for bit (same position-ordered accumulation)"""
+    from oracle import permuto as op
+
+    rng = np.random.default_rng(3)
+    n, L, cap = 3000, 24, 2 ** 12
+    enc = op.PermutoEncoding(3, cap, L, 2, np.geomspace(1.0, 1e-4, L), True, True, 1.0, seed=5)
+    enc.lattice_values = rng.standard_normal(enc.lattice_values.shape).astype(np.float32)
+    pos = rng.random((n, 3)).astype(np.float32)
+    want = enc.forward(pos, fma=False)
+    got = op.forward_rows_c(pos, enc.lattice_values, enc.scale, enc.random_shift_per_level, enc.anneal_window, True, 1.0)
+    assert np.array_equal(got, want)
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    want_lat, _ = op.backward(pos, enc.lattice_values, enc.scale, enc.random_shift_per_level, enc.anneal_window, op.from_rows(g), True, False,
+                              fma=False)
+    got_lat = op.backward_lattice_c(pos, enc.lattice_values.shape, enc.scale, enc.random_shift_per_level, enc.anneal_window, g)
+    assert np.array_equal(got_lat, want_lat)

@@ -232,8 +232,12 @@ class PipelinedTrainingStep:
         loop.drain(steps)                 # results of the last step
     """
 
-    def __init__(self, renderer: "ShellRenderer", o_pin, d_pin, pos_features, gt_rgb, img_pin, loss_pin, warmup: int = 2):
-        dev = pos_features.device
+    def __init__(self, renderer: "ShellRenderer", o_pin, d_pin, pos_features, gt_rgb, img_pin, loss_pin, warmup: int = 2, step_fn=None):
+        """``step_fn(rays_o, rays_d) -> dict`` (with "rgb" and "loss") replaces ``renderer.render_fwd_bwd(rays_o, rays_d, pos_features,
+        gt_rgb)`` when given: any capturable step (e.g. one with real encoders and an in-graph gradient exchange) can be pipelined"""
+        dev = gt_rgb.device
+        if step_fn is None:
+            step_fn = lambda o, d: renderer.render_fwd_bwd(o, d, pos_features, gt_rgb)  # noqa: E731
         self.renderer = renderer
         self.o_pin, self.d_pin, self.img_pin, self.loss_pin = o_pin, d_pin, img_pin, loss_pin
         self.rays_o = [torch.empty(o_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
@@ -248,7 +252,7 @@ class PipelinedTrainingStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
-                renderer.render_fwd_bwd(self.rays_o[0], self.rays_d[0], pos_features, gt_rgb)
+                step_fn(self.rays_o[0], self.rays_d[0])
         torch.cuda.current_stream().wait_stream(side)
         self.graphs, self.outs = [], []
         for b in range(2):
@@ -263,7 +267,7 @@ class PipelinedTrainingStep:
                 with torch.cuda.stream(self.copy_out):
                     img_pin.copy_(self.img[1 - b], non_blocking=True)
                     loss_pin.copy_(self.loss[1 - b], non_blocking=True)
-                out = renderer.render_fwd_bwd(self.rays_o[b], self.rays_d[b], pos_features, gt_rgb)
+                out = step_fn(self.rays_o[b], self.rays_d[b])
                 self.img[b].copy_(out["rgb"])
                 self.loss[b].copy_(out["loss"])
                 main.wait_stream(self.copy_in)
