@@ -41,8 +41,13 @@ HIDDEN = (128, 128, 64)
 POS_DIM = 51
 CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of this workload at HEAD (profiles/r02_*.md)
-NCU_TRAFFIC = {"mlp_fwd_kernel": None, "mlp_bwd_stashed_kernel": None, "shells_trace_kernel": 45.03552e6 + 22.207488e6,
-               "permuto_fwd_kernel": None, "permuto_bwd_kernel": None, "composite_tile_fwd+bwd": None}
+NCU_TRAFFIC = {"mlp_fwd_kernel": 204.150272e6 + 696.295936e6,            # profiles/r02_mlp_fwd.md
+               "mlp_bwd_stashed_kernel": 764.377344e6 + 169.448704e6,    # profiles/r02_mlp_bwd.md
+               "shells_trace_kernel": 43.836416e6 + 20.213248e6,         # profiles/r02_shells_trace.md
+               "permuto_fwd_kernel": 33.416960e6 + 131.241472e6,         # profiles/r02_permuto_fwd.md
+               "permuto_bwd_kernel": 238.130432e6 + 14.766592e6,         # profiles/r02_permuto_bwd.md
+               # composite_fwd_tile_kernel<1> + composite_bwd_tile_kernel<1> at 2^24 rays x 5 (algorithmic: 5.77 GB)
+               "composite_tile_fwd+bwd": 1.811964e9 + 389.046272e6 + 2.214682e9 + 1.307265e9}   # profiles/r02_composite_{fwd,bwd}_tile.md
 
 
 _JSON_FD = None
@@ -212,6 +217,53 @@ class CpuReferencePath:
                 op.backward_lattice_c(unit, e.lattice_values.shape, e.scale, e.random_shift_per_level, e.anneal_window, g,
                                       out=self.lattice_grads[k])
         return float(loss.detach())
+
+
+def cpu_compositing_c1(warmup: int = 20, iters: int = 200):
+    """SURVEY 8(d)'s CPU baseline protocol: the reference's torch compositing path (volsurfs_py/methods/volsurfs.py:601-640,708, restated
+    by oracle/compositing.py:dense_composite_torch and pinned bit-exact to those very lines by tests/golden/dense_composite_*.npz) on CPU
+    tensors for BASELINE config[0] (4096 rays x 5 layers), forward + autograd backward, fp32 and the reference-faithful fp16 variant,
+    all physical cores, 20 warm-ups + 200 timed iterations, median."""
+    import torch
+
+    from oracle.compositing import dense_composite_torch
+    from volsurfs_b200.synthetic import dense_layers
+
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    n_log = os.cpu_count() or 1
+    try:
+        import psutil
+
+        n_phys = psutil.cpu_count(logical=False) or n_log
+    except Exception:  # noqa: BLE001
+        n_phys = n_log
+    torch.set_num_threads(n_phys)
+    dl = dense_layers(4096, 5, seed_offset=1)
+    out = {"workload": "BASELINE config[0]: dense K-layer compositing fwd+bwd, 4096 rays x 5 layers, CPU tensors", "cpu_model": model,
+           "physical_cores": n_phys, "logical_cpus": n_log, "torch_threads": torch.get_num_threads(), "warmup": warmup, "iters": iters}
+    for half in (False, True):
+        a = dl["alpha"].clone().requires_grad_(True)
+        c = dl["rgb"].clone().requires_grad_(True)
+        bg = torch.ones(4096, 3)
+        ts = []
+        for it in range(warmup + iters):
+            a.grad = c.grad = None
+            t0 = time.perf_counter()
+            o = dense_composite_torch(a, c, rgb_bg=bg, half=half)
+            ((o["rgb"] * dl["g_rgb"]).sum() + (o["bg_transmittance"] * dl["g_bgT"]).sum()).backward()
+            if it >= warmup:
+                ts.append(time.perf_counter() - t0)
+        ms = statistics.median(ts) * 1e3
+        key = "fp16_reference_faithful" if half else "fp32"
+        out[key] = {"ms_median": round(ms, 4), "mrays_s": round(4096 / ms / 1e3, 3)}
+    return out
 
 
 def run_reference_arm(args, rank, world):
@@ -676,6 +728,7 @@ def run_ours(args, rank, world, local_rank):
                "sample": f"{reps} steps x {path.n_rays} rays (rows through the image centre) of the same workload; oracle port of the "
                          "reference algorithm (C BVH tracer with OpenMP, C permutohedral encoders with OpenMP, torch CPU heads, dense torch compositing, autograd "
                          "through compositing and heads, encoder backward)"}
+        cpu["compositing_c1"] = cpu_compositing_c1()
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -6,11 +6,26 @@ No host synchronisation happens between the stages: packing keeps capacity-sized
 count on the device (the reference syncs after every mesh trace and reads ``any_hit`` on the host, volsurfs.py:481)."""
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from .appearance import AppearanceHead
 from .raytracer import ShellTracer
 from .volsurfs import VolumeRendering as VR
+
+
+@contextlib.contextmanager
+def span(name: str):
+    """NVTX range with the reference's profiler span names (mvdatasets/utils/profiler.py:4-103; spans ``meshes_raytracing``,
+    ``ray_color_inference``, ``render_fg`` at volsurfs_py/methods/volsurfs.py:473-488,520-599,627-643 and ``forward_pass`` /
+    ``backward_pass`` at callbacks/callback.py:79-107), so that nsys / ncu timelines of this path read like the reference's profile.
+    Host-side markers only: nothing is synchronised (the reference's profiler relies on CUDA_LAUNCH_BLOCKING=1)."""
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 class ShellRenderer:
@@ -24,34 +39,37 @@ class ShellRenderer:
     # ---- stages ------------------------------------------------------------------------------------------------------
     def intersect_and_pack(self, rays_o, rays_d):
         """stage 1+2: all K layers in one launch, hits packed outer -> inner, face normals gathered"""
-        return self.tracer.render_samples(rays_o, rays_d, exact_size=False, with_normals=True)
+        with span("meshes_raytracing"):
+            return self.tracer.render_samples(rays_o, rays_d, exact_size=False, with_normals=True)
 
     def shade_train(self, rsp, pos_features):
         """stage 3 in training mode: like ``shade`` but both heads keep their activations (per-head stash buffers owned by the
         renderer, re-used across steps) for ``heads_backward``"""
         S = int(pos_features.shape[0])
         outs = []
-        for name, head in (("rgb", self.rgb_head), ("alpha", self.alpha_head)):
-            stash = getattr(self, "_stash_" + name, None)
-            if stash is None or stash.numel() < head.stash_bytes(S) or stash.device != pos_features.device:
-                stash = head.new_stash(S, pos_features.device)
-                setattr(self, "_stash_" + name, stash)
-            out, _ = head.forward_train(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash)
-            outs.append(out)
+        with span("ray_color_inference"):
+            for name, head in (("rgb", self.rgb_head), ("alpha", self.alpha_head)):
+                stash = getattr(self, "_stash_" + name, None)
+                if stash is None or stash.numel() < head.stash_bytes(S) or stash.device != pos_features.device:
+                    stash = head.new_stash(S, pos_features.device)
+                    setattr(self, "_stash_" + name, stash)
+                out, _ = head.forward_train(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash)
+                outs.append(out)
         return outs[0], outs[1]
 
     def shade(self, rsp, pos_features):
         """stage 3: per-hit colour and alpha (volsurfs.py:544-599).  ``pos_features`` [N*K, F]: output of the positional
         encoder for ``rsp.samples_3d`` (the permutohedral encoding is the stage before this path; synthetic in benchmarks)."""
-        with torch.no_grad():  # this class drives forward and backward explicitly (render_fwd_bwd); no autograd graph
+        with torch.no_grad(), span("ray_color_inference"):  # forward and backward are driven explicitly (render_fwd_bwd); no autograd graph
             rgb = self.rgb_head(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
             alpha = self.alpha_head(pos_features, rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev)
         return rgb, alpha
 
     def composite(self, rsp, alpha, rgb):
         """stage 4 forward: (rgb_fg, depth, acc, bgT) and the composited prediction rgb_fg + bgT * bg (volsurfs.py:708)"""
-        rgb_fg, depth, acc, bgT = VR.composite(rsp, alpha, rgb, rsp.samples_z)
-        pred = torch.addcmul(rgb_fg, bgT, self.bg_color.view(1, 3))
+        with span("render_fg"):
+            rgb_fg, depth, acc, bgT = VR.composite(rsp, alpha, rgb, rsp.samples_z)
+            pred = torch.addcmul(rgb_fg, bgT, self.bg_color.view(1, 3))
         return {"rgb": pred, "rgb_fg": rgb_fg, "depth": depth, "acc": acc, "bg_transmittance": bgT}
 
     def composite_backward(self, rsp, alpha, rgb, g_pred):
@@ -96,22 +114,25 @@ class ShellRenderer:
         """one pass of the hot path with the L1 photometric loss of the reference (utils/losses.py:14-19):
         forward, d loss / d pred, compositing backward down to per-sample colour and alpha gradients, then the backward of both
         appearance heads (parameter gradients + gradients of their positional features)"""
-        if heads_backward:
-            rsp = self.intersect_and_pack(rays_o, rays_d)
-            rgb, alpha = self.shade_train(rsp, pos_features)
-            out = self.composite(rsp, alpha, rgb)
-            out.update(ray_samples_packed=rsp, samples_rgb=rgb, samples_alpha=alpha)
-        else:
-            out = self.render(rays_o, rays_d, pos_features)
-        diff = out["rgb"] - gt_rgb
-        loss = diff.abs().mean()
-        g_pred = torch.sign(diff) / diff.numel()
-        rsp = out["ray_samples_packed"]
-        d_alpha, d_rgb = self.composite_backward(rsp, out["samples_alpha"], out["samples_rgb"], g_pred)
-        out.update(loss=loss, d_alpha=d_alpha, d_rgb=d_rgb)
-        if heads_backward:
-            out.update(self.heads_backward(rsp, pos_features, d_rgb, d_alpha,
-                                           fwd_outs={"rgb": out["samples_rgb"], "alpha": out["samples_alpha"]}))
+        with span("forward_pass"):
+            if heads_backward:
+                rsp = self.intersect_and_pack(rays_o, rays_d)
+                rgb, alpha = self.shade_train(rsp, pos_features)
+                out = self.composite(rsp, alpha, rgb)
+                out.update(ray_samples_packed=rsp, samples_rgb=rgb, samples_alpha=alpha)
+            else:
+                out = self.render(rays_o, rays_d, pos_features)
+            with span("losses"):
+                diff = out["rgb"] - gt_rgb
+                loss = diff.abs().mean()
+                g_pred = torch.sign(diff) / diff.numel()
+        with span("backward_pass"):
+            rsp = out["ray_samples_packed"]
+            d_alpha, d_rgb = self.composite_backward(rsp, out["samples_alpha"], out["samples_rgb"], g_pred)
+            out.update(loss=loss, d_alpha=d_alpha, d_rgb=d_rgb)
+            if heads_backward:
+                out.update(self.heads_backward(rsp, pos_features, d_rgb, d_alpha,
+                                               fwd_outs={"rgb": out["samples_rgb"], "alpha": out["samples_alpha"]}))
         return out
 
 
