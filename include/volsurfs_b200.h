@@ -353,6 +353,18 @@ int vs_occgrid_rays_t_near_t_far(const float* rays_o, const float* rays_d, const
 int vs_occgrid_check_occupancy(const float* points, int nr_voxels_per_dim, const float* extent, const float* values, const uint8_t* occupancy,
                                const uint8_t* roi, uint8_t* out_occupancy, float* out_values, int64_t n_points, void* stream);
 
+/* ---- baked-texture mesh renderer ------------------------------------------------------------------------------
+ * Replaces everything MeshRenderer.render_rays + shade (volsurfs_py/renderers/mesh_renderer.py:62-201) run after the mesh trace: texture
+ * coordinates from the barycentrics, TensorTexture(lerp=True) bilinear lookup of the baked SH-coefficient texture
+ * (mvdatasets/utils/tensor_texture.py:66-96), fp16 coefficients, SHEncoder.eval (encodings/sphericalharmonics.py:156-229), sigmoid and
+ * the shaded output buffers, in one launch.  Inputs as RayTracer.trace returns them (is_hit as u8, triangles_id i64); tex is the
+ * ZERO-PADDED texture [(res_h+2), (res_w+2), 4*nr_coeffs] f32 that TensorTexture keeps; nr_coeffs in {1,4,9,16}; bg_rgb: HOST float[3].
+ * Outputs ("ray_traced" dict): is_hit [N,1], normals [N,3], uvs [N,3], rgb [N,3], alpha [N,1], view_dirs [N,3] f32. */
+int vs_baked_texture_shade(const uint8_t* is_hit, const int64_t* tri_id, const float* bary, const float* dirs, const float* normals,
+                           const float* face_uvs, const float* tex, int res_h, int res_w, int nr_coeffs, const float* bg_rgb,
+                           float* o_hit, float* o_normals, float* o_uvs, float* o_rgb, float* o_alpha, float* o_dirs, int64_t n_rays,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

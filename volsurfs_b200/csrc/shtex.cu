@@ -753,3 +753,117 @@ int vs_shtex_combine_backward(int sh_deg, int nr_channels, int mode, int align, 
 }
 
 }  // extern "C"
+
+// =====================================================================================================================================
+// Baked-texture mesh renderer (second half): volsurfs_py/renderers/mesh_renderer.py:112-201 (render_rays) + :62-110 (shade)
+// after the mesh trace — texture coordinates from the barycentrics, bilinear lookup of the baked SH-coefficient texture
+// (mvdatasets/utils/tensor_texture.py:66-96 with lerp=True: zero-padded image, corners / weights of images.py:30-43,70-81,97-118), fp16
+// coefficients, mixed-precision SH evaluation (encodings/sphericalharmonics.py:156-229), sigmoid, and the shaded output buffers — in ONE
+// launch, thread per ray (the reference: ~40 torch kernels and boolean-mask gathers).  Same evaluation order as torch, operation by
+// operation; the bilinear sum runs k = 0..3 in sequence.
+// =====================================================================================================================================
+namespace vs {
+
+__global__ void __launch_bounds__(256) baked_shade_kernel(const uint8_t* __restrict__ is_hit, const int64_t* __restrict__ tri_id,
+                                                          const float* __restrict__ bary, const float* __restrict__ dirs,
+                                                          const float* __restrict__ normals, const float* __restrict__ face_uvs,
+                                                          const float* __restrict__ tex, int res_h, int res_w, int nr_coeffs, float bg_r,
+                                                          float bg_g, float bg_b, float* __restrict__ o_hit, float* __restrict__ o_normals,
+                                                          float* __restrict__ o_uvs, float* __restrict__ o_rgb, float* __restrict__ o_alpha,
+                                                          float* __restrict__ o_dirs, int64_t n_rays) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float bg[3] = {bg_r, bg_g, bg_b};
+    if (!is_hit[r]) {
+        o_hit[r] = 0.f;
+        o_alpha[r] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o_normals[3 * r + k] = o_uvs[3 * r + k] = o_rgb[3 * r + k] = o_dirs[3 * r + k] = bg[k];
+        return;
+    }
+    const float dx = __ldg(dirs + 3 * r), dy = __ldg(dirs + 3 * r + 1), dz = __ldg(dirs + 3 * r + 2);
+    o_hit[r] = 1.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // (x + 1) * 0.5 (mesh_renderer.py:76,103)
+        o_normals[3 * r + k] = __fmul_rn(__fadd_rn(__ldg(normals + 3 * r + k), 1.f), 0.5f);
+        o_dirs[3 * r + k] = __fmul_rn(__fadd_rn(__ldg(dirs + 3 * r + k), 1.f), 0.5f);
+    }
+    // uv = sum_j barycentric_j * face_uv_j (mesh_renderer.py:147-150), torch's order ((b0 uv0) + (b1 uv1)) + (b2 uv2)
+    const float b0 = __ldg(bary + 3 * r), b1 = __ldg(bary + 3 * r + 1), b2 = __ldg(bary + 3 * r + 2);
+    const float2* f = reinterpret_cast<const float2*>(face_uvs) + 3 * __ldg(tri_id + r);
+    const float2 u0 = __ldg(f), u1 = __ldg(f + 1), u2 = __ldg(f + 2);
+    const float u = __fadd_rn(__fadd_rn(__fmul_rn(b0, u0.x), __fmul_rn(b1, u1.x)), __fmul_rn(b2, u2.x));
+    const float v = __fadd_rn(__fadd_rn(__fmul_rn(b0, u0.y), __fmul_rn(b1, u1.y)), __fmul_rn(b2, u2.y));
+    o_uvs[3 * r] = u;
+    o_uvs[3 * r + 1] = v;
+    o_uvs[3 * r + 2] = 0.f;
+    // bilinear corners and weights in the texture's non-normalised space (tensor_texture.py:70-86)
+    const float a = __fmul_rn(u, (float)res_w), b = __fmul_rn(v, (float)res_h);
+    const float fx = floorf(__fsub_rn(a, 0.5f)), fy = floorf(__fsub_rn(b, 0.5f));
+    const float ddx = __fsub_rn(a, __fadd_rn(fx, 0.5f)), ddy = __fsub_rn(b, __fadd_rn(fy, 0.5f));
+    const float w[4] = {__fmul_rn(__fsub_rn(1.f, ddx), __fsub_rn(1.f, ddy)), __fmul_rn(ddx, __fsub_rn(1.f, ddy)),
+                        __fmul_rn(__fsub_rn(1.f, ddx), ddy), __fmul_rn(ddx, ddy)};
+    const int C4 = 4 * nr_coeffs, pw = res_w + 2;
+    const float* texel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // floor(corner) + 1 in the zero-padded image (tensor_texture.py:88-92)
+        long long px = (long long)floorf(__fadd_rn(__fadd_rn(fx, (float)(k & 1)), 0.5f)) + 1;
+        long long py = (long long)floorf(__fadd_rn(__fadd_rn(fy, (float)(k >> 1)), 0.5f)) + 1;
+        px = min(max(px, 0LL), (long long)res_w + 1);
+        py = min(max(py, 0LL), (long long)res_h + 1);
+        texel[k] = tex + ((size_t)py * pw + (size_t)px) * C4;
+    }
+    const int deg = nr_coeffs == 1 ? 0 : (nr_coeffs == 4 ? 1 : (nr_coeffs == 9 ? 2 : 3));
+    float P[16];
+    sh_factors(dx, dy, dz, deg, P);
+    float rgba[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        float co[16];
+        for (int k = 0; k < nr_coeffs; ++k) {
+            const int c = ch * nr_coeffs + k;  // sh_coeffs.view(-1, 4, nr_coeffs)
+            float acc = __fmul_rn(__ldg(texel[0] + c), w[0]);
+            acc = __fadd_rn(acc, __fmul_rn(__ldg(texel[1] + c), w[1]));
+            acc = __fadd_rn(acc, __fmul_rn(__ldg(texel[2] + c), w[2]));
+            acc = __fadd_rn(acc, __fmul_rn(__ldg(texel[3] + c), w[3]));
+            co[k] = round_half(acc);  // .half()
+        }
+        float res = round_half(__fmul_rn(co[0], P[0]));  // degree 0: an fp16 product; every later term promotes to fp32
+        if (deg > 0) {
+            res = __fsub_rn(res, __fmul_rn(P[1], co[1]));
+            res = __fadd_rn(res, __fmul_rn(P[2], co[2]));
+            res = __fsub_rn(res, __fmul_rn(P[3], co[3]));
+        }
+        for (int k = 4; k < nr_coeffs; ++k) res = __fadd_rn(res, __fmul_rn(P[k], co[k]));
+        const float o = sigmoid_precise(res);
+        rgba[ch] = deg == 0 ? round_half(o) : o;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o_rgb[3 * r + k] = fminf(fmaxf(rgba[k], 0.f), 1.f);
+    o_alpha[r] = fminf(fmaxf(rgba[3], 0.f), 1.f);
+}
+
+}  // namespace vs
+
+extern "C" {
+
+// Shaded buffers of MeshRenderer.render_rays (volsurfs_py/renderers/mesh_renderer.py:112-201) from one mesh trace: is_hit [N] u8,
+// triangles_id [N] i64, barycentric / view dirs / unit normals [N,3] f32 as RayTracer.trace returns them; face_uvs [F,3,2];
+// tex: the baked SH-coefficient texture ZERO-PADDED by one texel on every side, [(res_h+2), (res_w+2), 4*nr_coeffs] f32 (what
+// TensorTexture(lerp=True) keeps, tensor_texture.py:55-64); nr_coeffs in {1, 4, 9, 16}.  Outputs: is_hit [N,1], normals [N,3],
+// uvs [N,3], rgb [N,3], alpha [N,1], view_dirs [N,3] f32 (the "ray_traced" dict of the reference).  All pointers DEVICE.
+int vs_baked_texture_shade(const uint8_t* is_hit, const int64_t* tri_id, const float* bary, const float* dirs, const float* normals,
+                           const float* face_uvs, const float* tex, int res_h, int res_w, int nr_coeffs, const float* bg_rgb_host,
+                           float* o_hit, float* o_normals, float* o_uvs, float* o_rgb, float* o_alpha, float* o_dirs, int64_t n_rays,
+                           void* stream) {
+    VS_CHECK_ARG(n_rays >= 0 && res_h > 0 && res_w > 0 && bg_rgb_host);
+    VS_CHECK_ARG(nr_coeffs == 1 || nr_coeffs == 4 || nr_coeffs == 9 || nr_coeffs == 16);
+    if (n_rays == 0) return VS_OK;
+    VS_CHECK_ARG(is_hit && tri_id && bary && dirs && normals && face_uvs && tex && o_hit && o_normals && o_uvs && o_rgb && o_alpha && o_dirs);
+    vs::baked_shade_kernel<<<(unsigned)vs::div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        is_hit, tri_id, bary, dirs, normals, face_uvs, tex, res_h, res_w, nr_coeffs, bg_rgb_host[0], bg_rgb_host[1], bg_rgb_host[2], o_hit,
+        o_normals, o_uvs, o_rgb, o_alpha, o_dirs, n_rays);
+    return vs::launched(1);
+}
+
+}  // extern "C"
