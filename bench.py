@@ -39,6 +39,7 @@ K_LAYERS = 5
 IMG = 800
 HIDDEN = (128, 128, 64)
 POS_DIM = 51
+AR_BLOCKS = 4            # level blocks of the last lattice gradient (each reduced while the next is computed)
 CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of this workload at HEAD (profiles/r02_*.md)
 NCU_TRAFFIC = {"mlp_fwd_kernel": 204.150272e6 + 696.295936e6,            # profiles/r02_mlp_fwd.md
@@ -407,20 +408,30 @@ def run_ours(args, rank, world, local_rank):
             if reduce and world > 1 and k == "alpha":
                 # the colour branch's exchange (50 MB) runs on the side stream under the alpha branch's LATTICE backward (a grid of many
                 # small CTAs); under the persistent one-CTA-per-SM head kernel NCCL's CTAs delayed whole tiles (measured: +0.12 ms)
-                ar_stream.wait_event(ar_ready)
+                ar_stream.wait_stream(main)   # after the alpha head's backward (in the captured graph the dependency IS the schedule)
                 with torch.cuda.stream(ar_stream):
                     all_reduce_branch("rgb")
             e = encs[k].encoder
             grad_lat[k].zero_()
-            e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
-                               want_lattice=True, d_lattice=grad_lat[k])
-            mark(11 + 2 * i)
             if reduce and world > 1 and k == "alpha":
-                all_reduce_branch("alpha")
+                # the last gradient of the step: produced in level blocks, every finished block goes to the exchange (side stream) while
+                # the next one is computed, so that only the last block's all-reduce is exposed
+                L = e.nr_levels
+                for b in range(AR_BLOCKS):
+                    l0, l1 = L * b // AR_BLOCKS, L * (b + 1) // AR_BLOCKS
+                    e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
+                                       want_lattice=True, d_lattice=grad_lat[k], levels=(l0, l1))
+                    ar_stream.wait_stream(main)
+                    with torch.cuda.stream(ar_stream):
+                        dist.all_reduce(grad_lat[k][l0:l1], op=dist.ReduceOp.AVG)
+                        if b == AR_BLOCKS - 1:
+                            dist.all_reduce(grad_head[k], op=dist.ReduceOp.AVG)
+                mark(13)
                 main.wait_stream(ar_stream)
-            if reduce and world > 1 and k == "rgb":
-                ar_ready = torch.cuda.Event()
-                ar_ready.record(main)
+            else:
+                e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
+                                   want_lattice=True, d_lattice=grad_lat[k])
+                mark(11 + 2 * i)
         mark(14)
         out["loss"] = loss
         return out, loss, rsp

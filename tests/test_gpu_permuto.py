@@ -232,3 +232,25 @@ def test_full_size_adjoint_property():
     lhs = float((out.double() * grad.double()).sum())
     rhs = float((d_lat.double() * enc.lattice_values.detach().double()).sum())
     assert abs(lhs - rhs) <= 1e-5 * abs(lhs) + 1.0, (lhs, rhs)
+
+
+def test_lattice_backward_in_level_blocks_equals_the_full_backward():
+    """``_launch_backward(levels=(l0, l1))`` (used to pipeline the gradient exchange with the backward, bench.py): four level blocks fill the
+    same table as one full launch — equal up to the order of the fp32 atomics"""
+    from volsurfs_b200.encoding import PermutoHashEncoder
+
+    torch.manual_seed(3)
+    enc = PermutoHashEncoder(log2_hashmap_size=16, bb_sides=2.0, device=torch.device("cuda", 0))
+    e = enc.encoder
+    with torch.no_grad():
+        e.lattice_values.normal_(0.0, 0.1)
+    n = 50000
+    pos = (torch.rand(n, 3, device="cuda") - 0.5) * 1.2
+    g = torch.randn(n, enc.output_dim, device="cuda")
+    full, _ = e._launch_backward(e.lattice_values, pos, enc.window(None), g, enc.bb_sides, None, want_lattice=True)
+    parts = torch.zeros_like(e.lattice_values)
+    for b in range(4):
+        e._launch_backward(e.lattice_values, pos, enc.window(None), g, enc.bb_sides, None, want_lattice=True, d_lattice=parts,
+                           levels=(6 * b, 6 * b + 6))
+    scale = float(full.abs().max())
+    assert scale > 0 and float((parts - full).abs().max()) <= 1e-5 * scale

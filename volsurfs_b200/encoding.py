@@ -135,7 +135,10 @@ class PermutoEncoding(torch.nn.Module):
         return out, oob
 
     def _launch_backward(self, lattice_values, positions, window, grad_out, bb_sides, n_valid_dev, want_lattice=True, want_positions=False,
-                         d_lattice=None, d_positions=None):
+                         d_lattice=None, d_positions=None, levels=None):
+        """``levels=(l0, l1)``: lattice gradient of that level range only (the levels are independent: every argument of the C entry
+        point is simply offset to the range), so that a caller can hand finished level blocks to the gradient exchange while the next block
+        is still being computed"""
         positions = positions.contiguous()
         grad_out = grad_out.contiguous()
         n = int(positions.shape[0])
@@ -143,6 +146,19 @@ class PermutoEncoding(torch.nn.Module):
             d_lattice = torch.zeros_like(lattice_values)
         if want_positions and d_positions is None:
             d_positions = torch.zeros_like(positions)
+        if levels is not None:
+            l0, l1 = int(levels[0]), int(levels[1])
+            assert want_lattice and not want_positions and 0 <= l0 < l1 <= self.nr_levels
+            cols = min(2 * (l1 - l0), int(grad_out.shape[1]) - 2 * l0)
+            assert cols >= 1
+            fs = 4  # bytes per float
+            check(_lib.lib().vs_permuto_backward(
+                self.pos_dim, l1 - l0, self.capacity, 0, self._bb_c(bb_sides, self.pos_dim), ptr(positions),
+                lattice_values.data_ptr() + l0 * self.capacity * 2 * fs, self.scale_factor.data_ptr() + l0 * self.pos_dim * fs,
+                self.random_shift_per_level.data_ptr() + l0 * self.pos_dim * fs, window.data_ptr() + l0 * fs,
+                grad_out.data_ptr() + 2 * l0 * fs, cols, int(grad_out.stride(0)), d_lattice.data_ptr() + l0 * self.capacity * 2 * fs,
+                None, n, ptr(n_valid_dev), _stream()), "vs_permuto_backward")
+            return d_lattice, None
         check(_lib.lib().vs_permuto_backward(
             self.pos_dim, self.nr_levels, self.capacity, int(self.concat_points), self._bb_c(bb_sides, self.pos_dim), ptr(positions),
             ptr(lattice_values.detach()), ptr(self.scale_factor), ptr(self.random_shift_per_level.detach()), ptr(window), ptr(grad_out),
