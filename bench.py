@@ -8,8 +8,8 @@ One "step" = one pass of the hot path over one batch of synthetic rays on every 
   K-layer shell intersection (one launch) -> hit packing -> face normals -> permutohedral hash encoding of the hit points (one encoder
   per head, as volsurfs_py/models/rgb.py:40-60) -> rgb head + alpha head (tcgen05 MLPs) -> fused compositing forward -> L1 loss gradient
   -> fused compositing backward (d_alpha, d_rgb per hit) -> backward of both heads (tcgen05: Linear weight/bias gradients + gradients of
-  the positional features) -> backward of both encoders (lattice gradients) -> (N > 1) NCCL all-reduce (mean) of the head AND lattice
-  gradients, captured inside the step's CUDA graph: the colour branch's 50 MB reduce runs on a side stream under the alpha branch's backward.
+  the positional features) -> backward of both encoders (lattice gradients) -> (N > 1) ONE NCCL all-reduce (mean) of the head AND lattice
+  gradients (100.8 MB, one flat buffer), captured inside the step's CUDA graph.
 Workload at every N: BASELINE config[1] per GPU — 800x800 camera rays against 5 nested ~100k-triangle shells, legacy
 [128,128,64] GELU heads on the 51 features of a 24-level x 2, 2^18-entry permutohedral encoder + SH deg 3.
 
@@ -39,7 +39,6 @@ K_LAYERS = 5
 IMG = 800
 HIDDEN = (128, 128, 64)
 POS_DIM = 51
-AR_BLOCKS = 4            # level blocks of the last lattice gradient (each reduced while the next is computed)
 CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of this workload at HEAD (profiles/r02_*.md)
 NCU_TRAFFIC = {"mlp_fwd_kernel": 204.150272e6 + 696.295936e6,            # profiles/r02_mlp_fwd.md
@@ -350,16 +349,26 @@ def run_ours(args, rank, world, local_rank):
     n_marks = len(stage_names) + 1
     feats = {k: torch.zeros((S_cap, POS_DIM), device=dev) for k in heads}
     dfeat = {k: torch.zeros((S_cap, POS_DIM), device=dev) for k in heads}
-    grad_head = {k: torch.zeros(h.num_params(), device=dev) for k, h in heads.items()}
-    grad_lat = {k: torch.zeros_like(e.encoder.lattice_values) for k, e in encs.items()}
+    # every gradient of the step lives in ONE flat fp32 buffer (lattices first, then the heads), so that the exchange is a single NCCL call
+    n_lat = {k: e.encoder.lattice_values.numel() for k, e in encs.items()}
+    n_head = {k: h.num_params() for k, h in heads.items()}
+    grad_flat = torch.zeros(sum(n_lat.values()) + sum(n_head.values()), device=dev)
+    grad_lat, grad_head, off = {}, {}, 0
+    for k, e in encs.items():
+        grad_lat[k] = grad_flat[off:off + n_lat[k]].view_as(e.encoder.lattice_values)
+        off += n_lat[k]
+    for k in heads:
+        grad_head[k] = grad_flat[off:off + n_head[k]]
+        off += n_head[k]
     stash = {k: h.new_stash(S_cap, dev) for k, h in heads.items()}   # activations kept by the training-mode forward for the backward
-    ar_stream = torch.cuda.Stream(device=dev)
-    allreduce_bytes = sum(t.numel() * 4 for t in list(grad_head.values()) + list(grad_lat.values()))
+    allreduce_bytes = grad_flat.numel() * 4
 
-    def all_reduce_branch(name):
-        """mean all-reduce of one branch's gradients (lattice: 50.3 MB, head: 0.14 MB) on the current stream"""
-        dist.all_reduce(grad_lat[name], op=dist.ReduceOp.AVG)
-        dist.all_reduce(grad_head[name], op=dist.ReduceOp.AVG)
+    def all_reduce_grads():
+        """ONE mean all-reduce of every gradient of the step (2 x 50.3 MB lattice + 2 x 0.14 MB head), on the current stream, after the last
+        backward kernel.  Overlapping it with the backward was measured and lost on this step (profiles/r02_scaling_notes.md): NCCL's
+        CTAs under the persistent one-CTA-per-SM head kernel delay whole tile columns (+0.24 ms for 0.20 ms hidden), under the atomics-bound
+        lattice backward both slow down (+0.22 ms), and two 50 MB calls cost 0.40 ms where one 100.7 MB call costs 0.32 ms."""
+        dist.all_reduce(grad_flat, op=dist.ReduceOp.AVG)
 
     @torch.no_grad()  # forward and backward kernels are driven explicitly; no autograd graph in the timed region
     def step(record=None, reduce=True, o=None, d=None):
@@ -405,33 +414,13 @@ def run_ours(args, rank, world, local_rank):
             heads[k].backward_into(feats[k], rsp.samples_dirs, rsp.samples_normals, d_out[k], grad_head[k], dfeat[k], False, rsp.total_dev,
                                    stash=stash[k], fwd_out=fwd_out[k])
             mark(10 + 2 * i)
-            if reduce and world > 1 and k == "alpha":
-                # the colour branch's exchange (50 MB) runs on the side stream under the alpha branch's LATTICE backward (a grid of many
-                # small CTAs); under the persistent one-CTA-per-SM head kernel NCCL's CTAs delayed whole tiles (measured: +0.12 ms)
-                ar_stream.wait_stream(main)   # after the alpha head's backward (in the captured graph the dependency IS the schedule)
-                with torch.cuda.stream(ar_stream):
-                    all_reduce_branch("rgb")
             e = encs[k].encoder
             grad_lat[k].zero_()
-            if reduce and world > 1 and k == "alpha":
-                # the last gradient of the step: produced in level blocks, every finished block goes to the exchange (side stream) while
-                # the next one is computed, so that only the last block's all-reduce is exposed
-                L = e.nr_levels
-                for b in range(AR_BLOCKS):
-                    l0, l1 = L * b // AR_BLOCKS, L * (b + 1) // AR_BLOCKS
-                    e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
-                                       want_lattice=True, d_lattice=grad_lat[k], levels=(l0, l1))
-                    ar_stream.wait_stream(main)
-                    with torch.cuda.stream(ar_stream):
-                        dist.all_reduce(grad_lat[k][l0:l1], op=dist.ReduceOp.AVG)
-                        if b == AR_BLOCKS - 1:
-                            dist.all_reduce(grad_head[k], op=dist.ReduceOp.AVG)
-                mark(13)
-                main.wait_stream(ar_stream)
-            else:
-                e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
-                                   want_lattice=True, d_lattice=grad_lat[k])
-                mark(11 + 2 * i)
+            e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
+                               want_lattice=True, d_lattice=grad_lat[k])
+            mark(11 + 2 * i)
+        if reduce and world > 1:
+            all_reduce_grads()
         mark(14)
         out["loss"] = loss
         return out, loss, rsp
@@ -486,8 +475,7 @@ def run_ours(args, rank, world, local_rank):
 
     def all_reduce_after_graph():
         if world > 1 and not reduce_in_graph:
-            all_reduce_branch("rgb")
-            all_reduce_branch("alpha")
+            all_reduce_grads()
 
     def run_step(record=None):
         if use_graph:
@@ -625,8 +613,10 @@ def run_ours(args, rank, world, local_rank):
                         "unit": unit, "frac": round(ach / peak, 4)}
     if world > 1:
         stages["grad_allreduce"]["note"] = (
-            f"exposed tail only: {allreduce_bytes / 1e6:.1f} MB of fp32 gradients per step, the colour branch's half overlapped with the alpha "
-            "branch's backward on a side stream" + ("" if reduce_in_graph else " (NOT captured: exchange after the graph)"))
+            f"one NCCL all-reduce (mean) of {allreduce_bytes / 1e6:.1f} MB of fp32 gradients (2 lattices + 2 heads, one flat buffer) per step, "
+            f"algorithm bandwidth {allreduce_bytes / 1e9 / (stages['grad_allreduce']['ms'] * 1e-3):.0f} GB/s, bus bandwidth "
+            f"{allreduce_bytes / 1e9 / (stages['grad_allreduce']['ms'] * 1e-3) * 2 * (world - 1) / world:.0f} GB/s"
+            + (", captured inside the step's CUDA graph" if reduce_in_graph else " (NOT captured: exchange after the graph)"))
     # the dominant KERNEL of the step: stages that launch the same kernel are summed (both heads run mlp_fwd_kernel / mlp_bwd_stashed_kernel)
     kernel_of = {"trace": "shells_trace_kernel", "mlp_rgb": "mlp_fwd_kernel", "mlp_alpha": "mlp_fwd_kernel",
                  "mlp_bwd_rgb": "mlp_bwd_stashed_kernel", "mlp_bwd_alpha": "mlp_bwd_stashed_kernel",
