@@ -8,8 +8,9 @@ One "step" = one pass of the hot path over one batch of synthetic rays on every 
   K-layer shell intersection (one launch) -> hit packing -> face normals -> permutohedral hash encoding of the hit points (one encoder
   per head, as volsurfs_py/models/rgb.py:40-60) -> rgb head + alpha head (tcgen05 MLPs) -> fused compositing forward -> L1 loss gradient
   -> fused compositing backward (d_alpha, d_rgb per hit) -> backward of both heads (tcgen05: Linear weight/bias gradients + gradients of
-  the positional features) -> backward of both encoders (lattice gradients) -> (N > 1) ONE NCCL all-reduce (mean) of the head AND lattice
-  gradients (100.8 MB, one flat buffer), captured inside the step's CUDA graph.
+  the positional features) -> backward of both encoders (lattice gradients); (N > 1) ONE NCCL all-reduce (mean) of the head AND lattice
+  gradients (100.8 MB, one flat buffer), captured inside the step's CUDA graph on a side stream under the NEXT step's trace + pack
+  (software pipelining by one step: every replay performs one whole step and one whole exchange).
 Workload at every N: BASELINE config[1] per GPU — 800x800 camera rays against 5 nested ~100k-triangle shells, legacy
 [128,128,64] GELU heads on the 51 features of a 24-level x 2, 2^18-entry permutohedral encoder + SH deg 3.
 
@@ -344,8 +345,8 @@ def run_ours(args, rank, world, local_rank):
     heads = {"rgb": renderer.rgb_head, "alpha": renderer.alpha_head}
     S_cap = N * K_LAYERS
 
-    stage_names = ["trace", "pack+normals", "encode_rgb", "encode_alpha", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad",
-                   "composite_bwd", "mlp_bwd_rgb", "lattice_bwd_rgb", "mlp_bwd_alpha", "lattice_bwd_alpha", "grad_allreduce"]
+    stage_names = ["trace", "pack+normals", "grad_allreduce", "encode_rgb", "encode_alpha", "mlp_rgb", "mlp_alpha", "composite_fwd", "loss_grad",
+                   "composite_bwd", "mlp_bwd_rgb", "lattice_bwd_rgb", "mlp_bwd_alpha", "lattice_bwd_alpha"]
     n_marks = len(stage_names) + 1
     feats = {k: torch.zeros((S_cap, POS_DIM), device=dev) for k in heads}
     dfeat = {k: torch.zeros((S_cap, POS_DIM), device=dev) for k in heads}
@@ -362,12 +363,17 @@ def run_ours(args, rank, world, local_rank):
         off += n_head[k]
     stash = {k: h.new_stash(S_cap, dev) for k, h in heads.items()}   # activations kept by the training-mode forward for the backward
     allreduce_bytes = grad_flat.numel() * 4
+    ar_stream = torch.cuda.Stream(device=dev)
 
     def all_reduce_grads():
-        """ONE mean all-reduce of every gradient of the step (2 x 50.3 MB lattice + 2 x 0.14 MB head), on the current stream, after the last
-        backward kernel.  Overlapping it with the backward was measured and lost on this step (profiles/r02_scaling_notes.md): NCCL's
-        CTAs under the persistent one-CTA-per-SM head kernel delay whole tile columns (+0.24 ms for 0.20 ms hidden), under the atomics-bound
-        lattice backward both slow down (+0.22 ms), and two 50 MB calls cost 0.40 ms where one 100.7 MB call costs 0.32 ms."""
+        """ONE mean all-reduce of every gradient of a step (2 x 50.3 MB lattice + 2 x 0.14 MB head) on the current stream.
+
+        Where it runs: software-pipelined by one step.  Intersection and packing do not depend on the parameters, so the exchange of step
+        i's gradients runs on a side stream under the trace + pack of step i+1 and is joined before the encoders (where an optimizer step
+        would sit) — every replay of the step's graph performs one whole step and one whole exchange.  Overlapping the exchange with the
+        BACKWARD of its own step was measured and lost (profiles/r02_scaling_notes.md): NCCL's CTAs under the persistent one-CTA-per-SM head
+        kernel delay whole tile columns, under the atomics-bound lattice backward both slow down, and two 50 MB calls cost 0.40 ms where one
+        100.7 MB call costs 0.32 ms."""
         dist.all_reduce(grad_flat, op=dist.ReduceOp.AVG)
 
     @torch.no_grad()  # forward and backward kernels are driven explicitly; no autograd graph in the timed region
@@ -383,6 +389,10 @@ def run_ours(args, rank, world, local_rank):
 
         main = torch.cuda.current_stream()
         mark(0)
+        if reduce and world > 1:   # exchange of the PREVIOUS step's gradients, under this step's trace + pack
+            ar_stream.wait_stream(main)
+            with torch.cuda.stream(ar_stream):
+                all_reduce_grads()
         rec = renderer.tracer.trace_layers(o, d)
         mark(1)
         rsp = pack_layer_hits(rec["rays_o"], rec["rays_d"], rec["depth"], rec["tri"], rec["u"], rec["v"], t_far=renderer.tracer.t_far,
@@ -392,36 +402,36 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(lib.vs_shells_sample_normals(renderer.tracer._handle, rsp.samples_layer.data_ptr(), rsp.samples_triangle.data_ptr(), S,
                                                 rsp.total_dev.data_ptr(), rsp.samples_normals.data_ptr(), main.cuda_stream), "normals")
         mark(2)
+        if reduce and world > 1:
+            main.wait_stream(ar_stream)   # the reduced gradients are complete here: this is where the optimizer step belongs
+        mark(3)
         for i, k in enumerate(("rgb", "alpha")):   # permutohash.py:68-96: bounding-box normalisation + lattice slice, one launch
             e = encs[k].encoder
             e._launch_forward(e.lattice_values, rsp.samples_3d, encs[k].window(None), POS_DIM, encs[k].bb_sides, rsp.total_dev, out=feats[k])
-            mark(3 + i)
+            mark(4 + i)
         rgb, _ = heads["rgb"].forward_train(feats["rgb"], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash["rgb"])
-        mark(5)
+        mark(6)
         alpha, _ = heads["alpha"].forward_train(feats["alpha"], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev,
                                                 stash=stash["alpha"])
-        mark(6)
-        out = renderer.composite(rsp, alpha, rgb)
         mark(7)
+        out = renderer.composite(rsp, alpha, rgb)
+        mark(8)
         diff = out["rgb"] - gt
         loss = diff.abs().mean()
         g_pred = torch.sign(diff) / diff.numel()
-        mark(8)
-        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
         mark(9)
+        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
+        mark(10)
         fwd_out, d_out = {"rgb": rgb, "alpha": alpha}, {"rgb": d_rgb, "alpha": d_alpha}
         for i, k in enumerate(("rgb", "alpha")):
             heads[k].backward_into(feats[k], rsp.samples_dirs, rsp.samples_normals, d_out[k], grad_head[k], dfeat[k], False, rsp.total_dev,
                                    stash=stash[k], fwd_out=fwd_out[k])
-            mark(10 + 2 * i)
+            mark(11 + 2 * i)
             e = encs[k].encoder
             grad_lat[k].zero_()
             e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
                                want_lattice=True, d_lattice=grad_lat[k])
-            mark(11 + 2 * i)
-        if reduce and world > 1:
-            all_reduce_grads()
-        mark(14)
+            mark(12 + 2 * i)
         out["loss"] = loss
         return out, loss, rsp
 
@@ -521,9 +531,22 @@ def run_ours(args, rank, world, local_rank):
             all_reduce_after_graph()
             a1.record()
             torch.cuda.synchronize()
-            stage_ms[-1] = a0.elapsed_time(a1)
+            stage_ms[stage_names.index("grad_allreduce")] = a0.elapsed_time(a1)
     else:
         stage_ms = [statistics.mean(records[s][i].elapsed_time(records[s][i + 1]) for s in range(args.steps)) for i in range(n_marks - 1)]
+
+    ar_alone_ms = 0.0
+    if world > 1:
+        for _ in range(3):
+            all_reduce_grads()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            all_reduce_grads()
+        a1.record()
+        torch.cuda.synchronize()
+        ar_alone_ms = a0.elapsed_time(a1) / 10
 
     # ---- e2e: pinned host rays in, image + loss out, every step — through the public API (pipeline.PipelinedTrainingStep): two
     # alternating graphs; the copy engines move step i+1's rays in and step i-1's image + loss out while step i computes
@@ -613,10 +636,12 @@ def run_ours(args, rank, world, local_rank):
                         "unit": unit, "frac": round(ach / peak, 4)}
     if world > 1:
         stages["grad_allreduce"]["note"] = (
-            f"one NCCL all-reduce (mean) of {allreduce_bytes / 1e6:.1f} MB of fp32 gradients (2 lattices + 2 heads, one flat buffer) per step, "
-            f"algorithm bandwidth {allreduce_bytes / 1e9 / (stages['grad_allreduce']['ms'] * 1e-3):.0f} GB/s, bus bandwidth "
-            f"{allreduce_bytes / 1e9 / (stages['grad_allreduce']['ms'] * 1e-3) * 2 * (world - 1) / world:.0f} GB/s"
-            + (", captured inside the step's CUDA graph" if reduce_in_graph else " (NOT captured: exchange after the graph)"))
+            f"one NCCL all-reduce (mean) of {allreduce_bytes / 1e6:.1f} MB of fp32 gradients (2 lattices + 2 heads, one flat buffer) per step"
+            + (", captured inside the step's CUDA graph on a side stream under trace + pack (the previous step's gradients: software "
+               "pipelining by one step); this stage is the time the main stream waits at the join before the encoders; the exchange alone: "
+               f"{ar_alone_ms:.3f} ms = {allreduce_bytes / 1e9 / (ar_alone_ms * 1e-3):.0f} GB/s algorithm, "
+               f"{allreduce_bytes / 1e9 / (ar_alone_ms * 1e-3) * 2 * (world - 1) / world:.0f} GB/s bus bandwidth"
+               if reduce_in_graph else " (NOT captured: exchange after the graph)"))
     # the dominant KERNEL of the step: stages that launch the same kernel are summed (both heads run mlp_fwd_kernel / mlp_bwd_stashed_kernel)
     kernel_of = {"trace": "shells_trace_kernel", "mlp_rgb": "mlp_fwd_kernel", "mlp_alpha": "mlp_fwd_kernel",
                  "mlp_bwd_rgb": "mlp_bwd_stashed_kernel", "mlp_bwd_alpha": "mlp_bwd_stashed_kernel",
