@@ -93,15 +93,17 @@ __device__ __forceinline__ void locate(const float (&pos)[D], const float* __res
     }
     // barycentric weights.  The reference scatters +delta_i into slot D-rank_i and -delta_i into slot D+1-rank_i of a zeroed array;
     // rank is a permutation, so slot t holds delta[rank == D-t] - delta[rank == D+1-t], one rounding whichever term came first.
-    float by_rank[D + 1];
+    // (gathered per slot — "the delta whose rank is k" — not scattered per vertex: the scatter form is compiled into a dynamically indexed
+    // local-memory array, 16 STL + 1 LDL per level in the SASS of round 1)
+    float delta[D + 1], by_rank[D + 1];
 #pragma unroll
-    for (int k = 0; k <= D; k++) by_rank[k] = 0.f;
+    for (int i = 0; i <= D; i++) delta[i] = (elevated[i] - s.rem0[i]) * (1.0f / (D + 1));
 #pragma unroll
-    for (int i = 0; i <= D; i++) {
-        float delta = (elevated[i] - s.rem0[i]) * (1.0f / (D + 1));
+    for (int k = 0; k <= D; k++) {
+        float v = 0.f;
 #pragma unroll
-        for (int k = 0; k <= D; k++)
-            if (s.rank[i] == k) by_rank[k] = delta;
+        for (int i = 0; i <= D; i++) v = (s.rank[i] == k) ? delta[i] : v;
+        by_rank[k] = v;
     }
 #pragma unroll
     for (int t = 1; t <= D; t++) s.bary[t] = by_rank[D - t] - by_rank[D + 1 - t];
