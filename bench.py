@@ -610,7 +610,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- per-stage rooflines (rank 0's numbers)
     flops_head = lambda out_dim: 2.0 * n_hits * (67 * 128 + 128 * 128 + 128 * 64 + 64 * out_dim)  # noqa: E731
-    enc_bytes = n_hits * (12 + POS_DIM * 4)                 # compulsory: point in, feature row out (the 24 x 4 lattice gathers hit L2)
+    # 24 levels x 4 vertices x 8 B gathered (scattered as atomics in the backward) = 768 B per sample, + point in, feature
+    # row (or its gradient) out / in.  The lattice traffic is L2-resident (ncu: ~0.25 GB of DRAM per launch), so this is an upper view
+    enc_bytes = n_hits * (768 + 12 + POS_DIM * 4)
     stage_alg = {
         "trace": ("hbm", N * K_LAYERS * (24 + 16)),                                   # rays in, (t, face, u, v) out per (ray, layer)
         "pack+normals": ("hbm", N * (16 * K_LAYERS + 8 + 24) + n_hits * (4 + 4 + 12 + 12 + 4 + 4 + 8 + 12)),
@@ -622,7 +624,7 @@ def run_ours(args, rank, world, local_rank):
         "composite_bwd": ("hbm", 32 * N + 36 * n_hits),
         "mlp_bwd_rgb": ("tensor", 2.0 * flops_head(3)),                               # dA + dW GEMMs
         "mlp_bwd_alpha": ("tensor", 2.0 * flops_head(1)),
-        "lattice_bwd_rgb": ("hbm", enc_bytes + 2 ** 18 * 24 * 8), "lattice_bwd_alpha": ("hbm", enc_bytes + 2 ** 18 * 24 * 8),
+        "lattice_bwd_rgb": ("hbm", enc_bytes), "lattice_bwd_alpha": ("hbm", enc_bytes),
         "grad_allreduce": ("hbm", 0.0),
     }
     stages = {}

@@ -18,6 +18,8 @@
 // forward output agrees bit for bit with the reference kernels wherever the discrete simplex choice agrees.  The lattice
 // gradient is accumulated with fp32 atomics (as in the reference: order, hence last-ulp rounding, is unspecified).
 #include "volsurfs_b200.h"
+#include <cstdlib>
+
 #include "vs_common.cuh"
 
 namespace vs {
@@ -29,6 +31,7 @@ constexpr int PM_MAX_COLS = 72;    // 2 * (levels + extra) <= 72  (levels <= 32)
 
 struct PermutoArgs {
     int n_levels, n_extra, concat_points, pow2;
+    int agg_max_heads;   // red_add_runs aggregates runs of equal slots when a warp has at most this many runs
     uint32_t capacity;
     float points_scaling;
     int has_bb;
@@ -110,17 +113,41 @@ __device__ __forceinline__ void locate(const float (&pos)[D], const float* __res
     s.bary[0] = by_rank[D] + (1.0f + (0.0f - by_rank[0]));
 }
 
-// EncodingGPU.cuh:22-45,216-227: hash slot of the simplex vertex with this remainder
+// EncodingGPU.cuh:22-45,216-227: hash slot of the simplex vertex with this remainder.  The reference folds the D keys
+// key_i = rem0_i + remainder - (rank_i > D - remainder ? D + 1 : 0) as k = (k + key_i) * M, i = 0..D-1: in uint32 ring arithmetic that is
+// the LINEAR form  sum_i key_i M^(D-i)  =  [sum_i rem0_i M^(D-i)]  +  remainder [sum_i M^(D-i)]  -  (D+1) sum_i [rank_i + remainder > D] M^(D-i),
+// bit-identical (wrap-around arithmetic is exact), with the first bracket computed once per simplex (HashBase) instead of once per vertex.
 template <int D>
-__device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, int remainder, uint32_t capacity, int pow2) {
+struct HashBase {
+    uint32_t base;
+};
+template <int D>
+__device__ __forceinline__ constexpr uint32_t hash_pow(int e) {   // M^e mod 2^32
+    uint32_t p = 1u;
+    for (int i = 0; i < e; i++) p *= 2531011u;
+    return p;
+}
+template <int D>
+__device__ __forceinline__ HashBase<D> hash_base(const Simplex<D>& s) {
+    HashBase<D> h;
     uint32_t k = 0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        int key = s.rem0[i] + remainder;
-        if (s.rank[i] > D - remainder) key -= (D + 1);
-        k += (uint32_t)key;
+        k += (uint32_t)s.rem0[i];
         k *= 2531011u;
     }
+    h.base = k;
+    return h;
+}
+template <int D>
+__device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, const HashBase<D>& h, int remainder, uint32_t capacity, int pow2) {
+    uint32_t sum_pow = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) sum_pow += hash_pow<D>(D - i);
+    uint32_t k = h.base + (uint32_t)remainder * sum_pow;
+#pragma unroll
+    for (int i = 0; i < D; i++)
+        if (s.rank[i] + remainder > D) k -= (uint32_t)(D + 1) * hash_pow<D>(D - i);
     return pow2 ? (k & (capacity - 1u)) : (k % capacity);
 }
 
@@ -146,11 +173,11 @@ __device__ __forceinline__ void red_add_f32x2(float2* addr, float x, float y) {
 // One (x, y) contribution per lane into table[slot].  Lanes of a warp are consecutive positions: on the coarse levels long runs of
 // lanes hit the same vertex, and 32 same-address atomics serialise in L2 — so runs of equal slots are summed with shuffles first and
 // the run's first lane issues one vector reduction.  When most lanes differ (fine levels) the atomics go out directly.
-__device__ __forceinline__ void red_add_runs(float2* table, uint32_t slot, float x, float y, bool valid, int lane) {
+__device__ __forceinline__ void red_add_runs(float2* table, uint32_t slot, float x, float y, bool valid, int lane, int agg_max_heads) {
     uint32_t prev = __shfl_up_sync(VS_FULL_MASK, slot, 1);
     bool head = (lane == 0) || (prev != slot);
     uint32_t heads = __ballot_sync(VS_FULL_MASK, head);
-    if (__popc(heads) > 20) {
+    if (__popc(heads) > agg_max_heads) {
         if (valid) red_add_f32x2(table + slot, x, y);
         return;
     }
@@ -191,9 +218,10 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
         locate<D>(pos, shift + lvl * D, scale + lvl * D, s);
         const float w_lvl = __ldg(window + lvl);
         const float2* table = lattice + (size_t)lvl * a.capacity;
+        const HashBase<D> hb = hash_base<D>(s);
         float2 v[D + 1];
 #pragma unroll
-        for (int r = 0; r <= D; r++) v[r] = __ldg(table + vertex_slot<D>(s, r, a.capacity, a.pow2));
+        for (int r = 0; r <= D; r++) v[r] = __ldg(table + vertex_slot<D>(s, hb, r, a.capacity, a.pow2));
         float ax = 0.f, ay = 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
@@ -218,10 +246,18 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
     }
     __syncthreads();
     const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
+    // flat walk over the tile's [rows, out_cols] block: (r, c) advance incrementally (one division per thread, not one per element)
     const int total = rows * out_cols;
+    const int step_r = PM_THREADS / out_cols, step_c = PM_THREADS - step_r * out_cols;
+    int r = threadIdx.x / out_cols, c = threadIdx.x - r * out_cols;
     for (int i = threadIdx.x; i < total; i += PM_THREADS) {
-        int r = i / out_cols, c = i - r * out_cols;
         out[(base + r) * out_stride + c] = tile[c * PM_PAD + r];
+        r += step_r;
+        c += step_c;
+        if (c >= out_cols) {
+            c -= out_cols;
+            ++r;
+        }
     }
 }
 
@@ -242,9 +278,18 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
     const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
     const int n_cols = 2 * a.n_levels;   // the concat-points columns pass no gradient (Encoding.cu:135-139,163)
 
-    for (int i = threadIdx.x; i < PM_TILE * in_cols; i += PM_THREADS) {
-        int r = i / in_cols, c = i - r * in_cols;
-        if (c < n_cols) tile[c * PM_PAD + r] = (r < rows) ? __ldg(d_out + (base + r) * in_stride + c) : 0.f;
+    {   // flat walk, (r, c) advanced incrementally (see permuto_fwd_kernel)
+        const int step_r = PM_THREADS / in_cols, step_c = PM_THREADS - step_r * in_cols;
+        int r = threadIdx.x / in_cols, c = threadIdx.x - r * in_cols;
+        for (int i = threadIdx.x; i < PM_TILE * in_cols; i += PM_THREADS) {
+            if (c < n_cols) tile[c * PM_PAD + r] = (r < rows) ? __ldg(d_out + (base + r) * in_stride + c) : 0.f;
+            r += step_r;
+            c += step_c;
+            if (c >= in_cols) {
+                c -= in_cols;
+                ++r;
+            }
+        }
     }
     float pos[D];
     load_position<D>(a, positions, idx, valid, pos);
@@ -261,15 +306,16 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
         Simplex<D> s;
         locate<D>(pos, shift + lvl * D, scale + lvl * D, s);
         const float w_lvl = __ldg(window + lvl);
+        const HashBase<D> hb = hash_base<D>(s);
         uint32_t slot[D + 1];
 #pragma unroll
-        for (int r = 0; r <= D; r++) slot[r] = vertex_slot<D>(s, r, a.capacity, a.pow2);
+        for (int r = 0; r <= D; r++) slot[r] = vertex_slot<D>(s, hb, r, a.capacity, a.pow2);
         if (d_lattice) {
             float2* table = d_lattice + (size_t)lvl * a.capacity;
 #pragma unroll
             for (int r = 0; r <= D; r++) {
                 float w = s.bary[r] * w_lvl;
-                red_add_runs(table, slot[r], gx * w, gy * w, valid, lane);
+                red_add_runs(table, slot[r], gx * w, gy * w, valid, lane, a.agg_max_heads);
             }
         }
         if (d_positions) {   // EncodingGPU.cuh:630-690
@@ -337,6 +383,8 @@ static int fill_args(PermutoArgs& a, int pos_dim, int n_levels, int64_t capacity
     a.pow2 = (capacity & (capacity - 1)) == 0;
     a.points_scaling = points_scaling;
     a.has_bb = bb_sides != nullptr;
+    static const int agg_env = getenv("VS_PERMUTO_AGG") ? atoi(getenv("VS_PERMUTO_AGG")) : 4;   // measured on B200: 0 -> 2.35 ms, 4 -> 0.494, 20 -> 0.512, 32 -> 0.524
+    a.agg_max_heads = agg_env;
     for (int i = 0; i < 8; i++) {
         a.bb_half[i] = 1.f;
         a.bb_inv_half[i] = 1.f;
