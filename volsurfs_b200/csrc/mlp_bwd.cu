@@ -531,7 +531,7 @@ struct MlpBwd2Plan {
 };
 
 constexpr int kItemBars = 16;
-constexpr int kBwdThreads = kMlpThreads + 32;
+constexpr int kBwdThreads = kMlpThreads + 64;  // 16 epilogue warps + the MMA issuer warp + the ring warp
 
 static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_dim, int want_dx, MlpBwd2Plan* p) {
     std::memset(p, 0, sizeof(*p));
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                                                                       float* __restrict__ d_pos, float* __restrict__ partials,
                                                                       int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw, bar_ready, bar_x, bar_act, bar_item[kItemBars];
+    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw[4], bar_ready, bar_x, bar_act, bar_item[kItemBars];
     __shared__ uint32_t tmem_slot;
     // per-layer tables indexed with the run-time layer number: shared-memory copies (see mlp_fwd_kernel)
     __shared__ MlpConfig cfg;
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
     if (tid == 0) {
         mbar_init(&bar_w, 1);
         mbar_init(&bar_da, 1);
-        mbar_init(&bar_dw, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_dw[i], 1);
         mbar_init(&bar_ready, kMlpThreads / 32);
         mbar_init(&bar_x, kMlpThreads / 32);
         mbar_init(&bar_act, kMlpThreads / 32);
@@ -651,8 +651,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
     auto item_bar = [&](uint32_t seq) { return &bar_item[seq & (kItemBars - 1)]; };
     auto item_parity = [&](uint32_t seq) { return (seq / kItemBars) & 1u; };
 
-    if (warp == kMlpThreads / 32) {
-        // ================= control warp: ring producer + MMA issuer =================
+    if (warp == kMlpThreads / 32 + 1) {
+        // ================= ring warp: TMA producer, ring-space accounting, input-gradient store =================
+        // Kept off the MMA issuer's lane: a release + produce round is several hundred cycles of dependent scalar work, which sat
+        // between every layer's dW commit and the next layer's dA issue while one lane did both jobs (clock64 trace, round 2).
         if (lane == 0 && my_tiles > 0) {
             mbar_arrive_expect_tx(&bar_w, (uint32_t)cfg.blob_bytes);
             bulk_g2s(s_blob, blob, (uint32_t)cfg.blob_bytes, &bar_w);
@@ -697,22 +699,52 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                 }
             };
             produce();
-            mbar_wait(&bar_w, 0);
-            RingCursor cur{0};
-            uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
-            uint32_t par_ready = 0, par_dw = 0, par_x = 0, par_act = 0;
-            const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
             const int pf_depth = p2.prefetch_tiles;
             for (int64_t j = 0; j < pf_depth && j < my_tiles; ++j)
                 bulk_prefetch_l2(stash + (blockIdx.x + j * gridDim.x) * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
+            RingCursor cur{0};  // only the input-gradient item's offset is needed here
+            uint32_t n_dw = 0, par_x = 0;
             for (int64_t k = 0; k < my_tiles; ++k) {
                 const int64_t tile = blockIdx.x + k * gridDim.x;
                 const bool full = (tile + 1) * kTileM <= n;
-                // the ring holds less than one tile: the DRAM latency of the saved operands (TMA items) and of the activation
-                // derivatives (read by the epilogue warps) is taken off the critical path by pulling whole tile images into L2
-                // `pf_depth` tiles ahead
+                // the ring holds less than one tile: the DRAM latency of the saved operands (TMA items) is taken off the critical
+                // path by pulling whole tile images into L2 `pf_depth` tiles ahead
                 if (pf_depth > 0 && k + pf_depth < my_tiles)
                     bulk_prefetch_l2(stash + (tile + pf_depth * gridDim.x) * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
+                cur.alloc(p2.item_bytes[0], R);
+                for (int l = L - 1; l >= 0; --l) {
+                    cur.alloc(st.a_bytes[l], R);
+                    if (l >= 1) cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
+                    // once the dW / db GEMMs of layer l are done, dZ_l and A_l leave the ring.  Four barriers in turn: this lane would
+                    // have to fall four commits (a whole tile of operands, more than the ring holds) behind to miss a phase.
+                    mbar_wait(&bar_dw[n_dw & 3u], (n_dw >> 2) & 1u);
+                    ++n_dw;
+                    release(2);
+                    produce();
+                    if (l == 0 && p2.want_dx) {
+                        const int off_x = cur.alloc(p2.item_bytes[n_items - 1], R);
+                        mbar_wait(&bar_x, par_x);  // every epilogue warp has staged its part of the input gradient
+                        par_x ^= 1;
+                        if (full) {
+                            bulk_s2g(d_pos + tile * kTileM * F, s_ring + off_x, (uint32_t)(kTileM * F * 4));
+                            bulk_commit();
+                            bulk_wait_read_all();
+                        }
+                        release(1);
+                        produce();
+                    }
+                }
+            }
+        }
+    } else if (warp == kMlpThreads / 32) {
+        // ================= MMA issuer warp =================
+        if (lane == 0 && my_tiles > 0) {
+            mbar_wait(&bar_w, 0);
+            RingCursor cur{0};
+            uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
+            uint32_t par_ready = 0, par_act = 0, n_dw = 0;
+            const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
+            for (int64_t k = 0; k < my_tiles; ++k) {
                 int off_dz = cur.alloc(p2.item_bytes[0], R);
                 ++seq;
                 for (int l = L - 1; l >= 0; --l) {
@@ -746,24 +778,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     if (!plan.fold_bias[l])
                         umma_gemm_f16(tmem_base + (uint32_t)plan.db_col[l], dz_addr, mn_lbo, mn_sbo, 256, ones_addr, mn_lbo, mn_sbo, 256,
                                       umma_idesc_f16(kTileM, 16) | kIdescAMn | kIdescBMn, kTileM / 16, k > 0);
-                    tc_commit(&bar_dw);
-                    // the dW / db GEMMs run under the epilogue; once they are done dZ_l and A_l leave the ring
-                    mbar_wait(&bar_dw, par_dw);
-                    par_dw ^= 1;
-                    release(2);
-                    produce();
+                    tc_commit(&bar_dw[n_dw & 3u]);  // the ring warp frees dZ_l and A_l when these GEMMs have read them
+                    ++n_dw;
                     if (want_dx) {
-                        const int off_x = cur.alloc(p2.item_bytes[n_items - 1], R);
+                        cur.alloc(p2.item_bytes[p2.n_items - 1], R);
                         ++seq;
-                        mbar_wait(&bar_x, par_x);  // every epilogue warp has staged its part of the input gradient
-                        par_x ^= 1;
-                        if (full) {
-                            bulk_s2g(d_pos + tile * kTileM * F, s_ring + off_x, (uint32_t)(kTileM * F * 4));
-                            bulk_commit();
-                            bulk_wait_read_all();
-                        }
-                        release(1);
-                        produce();
                     }
                     off_dz = off_next;
                 }
