@@ -582,6 +582,36 @@ struct RingCursor {
     }
 };
 
+// Opt-in clock64 event trace of CTA 0 (scripts/trace_mlp_bwd.py builds a private library with -DVS_KERNEL_TRACE; the product
+// build compiles the macros to nothing).  who: 0 MMA issuer, 1 epilogue thread 0, 2 ring lane.  An event is one clock read and one
+// fire-and-forget store (the event counter lives in a register), a few tens of cycles.
+#ifdef VS_KERNEL_TRACE
+constexpr int kTraceCap = 256;
+__device__ long long g_trace[3][2 * kTraceCap];
+__device__ int g_trace_n[3];
+#define VS_TR_DECL int tr_n_ = 0
+#define VS_TR(who, id)                                                             \
+    do {                                                                           \
+        if (blockIdx.x == 0 && k >= 2 && k < 4 && tr_n_ < kTraceCap) {             \
+            g_trace[who][2 * tr_n_] = (id);                                        \
+            g_trace[who][2 * tr_n_ + 1] = clock64();                               \
+            ++tr_n_;                                                               \
+        }                                                                          \
+    } while (0)
+#define VS_TR_END(who)                             \
+    do {                                           \
+        if (blockIdx.x == 0) g_trace_n[who] = tr_n_; \
+    } while (0)
+#else
+#define VS_TR_DECL ((void)0)
+#define VS_TR(who, id) ((void)0)
+#define VS_TR_END(who) ((void)0)
+#endif
+#define VS_TR_E(id)               \
+    do {                          \
+        if (tid == 0) VS_TR(1, id); \
+    } while (0)
+
 template <int ACT>  // 0 ReLU, 1 GELU: the backward recomputes act / act' from the stashed pre-activations
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const __grid_constant__ MlpConfig cfg_param,
                                                                          const __grid_constant__ MlpBwdPlan plan_param,
@@ -700,27 +730,48 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             };
             produce();
             const int pf_depth = p2.prefetch_tiles;
-            for (int64_t j = 0; j < pf_depth && j < my_tiles; ++j)
-                bulk_prefetch_l2(stash + (blockIdx.x + j * gridDim.x) * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
+            // a future tile's image, and the rows of the output-layer gradient the epilogue warps read with plain loads at the top of
+            // that tile (a DRAM miss there stalls the whole CTA for 2.5 - 3.8k cycles under this kernel's traffic: clock64 trace)
+            auto prefetch_rows = [&](const float* rows, int width, int64_t tile) {  // bulk prefetches want 16-byte aligned addresses
+                const float* p = rows + tile * kTileM * width;
+                if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) bulk_prefetch_l2(p, (uint32_t)(kTileM * width * 4));
+            };
+            auto prefetch_tile = [&](int64_t tile) {
+                bulk_prefetch_l2(stash + tile * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
+                if ((tile + 1) * kTileM <= n) {
+                    prefetch_rows(d_out, cfg.out_dim, tile);
+                    if (!cfg.out_linear) {
+                        prefetch_rows(fwd_out, cfg.out_dim, tile);
+                        if (cfg.alpha_decay) {
+                            prefetch_rows(dirs, 3, tile);
+                            prefetch_rows(normals, 3, tile);
+                        }
+                    }
+                }
+            };
+            for (int64_t j = 0; j < pf_depth && j < my_tiles; ++j) prefetch_tile(blockIdx.x + j * gridDim.x);
             RingCursor cur{0};  // only the input-gradient item's offset is needed here
+            VS_TR_DECL;
             uint32_t n_dw = 0, par_x = 0;
             for (int64_t k = 0; k < my_tiles; ++k) {
                 const int64_t tile = blockIdx.x + k * gridDim.x;
                 const bool full = (tile + 1) * kTileM <= n;
                 // the ring holds less than one tile: the DRAM latency of the saved operands (TMA items) is taken off the critical
                 // path by pulling whole tile images into L2 `pf_depth` tiles ahead
-                if (pf_depth > 0 && k + pf_depth < my_tiles)
-                    bulk_prefetch_l2(stash + (tile + pf_depth * gridDim.x) * (int64_t)st.tile_bytes, (uint32_t)st.tile_bytes);
+                if (pf_depth > 0 && k + pf_depth < my_tiles) prefetch_tile(tile + pf_depth * gridDim.x);
                 cur.alloc(p2.item_bytes[0], R);
                 for (int l = L - 1; l >= 0; --l) {
                     cur.alloc(st.a_bytes[l], R);
                     if (l >= 1) cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
                     // once the dW / db GEMMs of layer l are done, dZ_l and A_l leave the ring.  Four barriers in turn: this lane would
                     // have to fall four commits (a whole tile of operands, more than the ring holds) behind to miss a phase.
+                    VS_TR(2, 10 + l);
                     mbar_wait(&bar_dw[n_dw & 3u], (n_dw >> 2) & 1u);
+                    VS_TR(2, 20 + l);
                     ++n_dw;
                     release(2);
                     produce();
+                    VS_TR(2, 30 + l);
                     if (l == 0 && p2.want_dx) {
                         const int off_x = cur.alloc(p2.item_bytes[n_items - 1], R);
                         mbar_wait(&bar_x, par_x);  // every epilogue warp has staged its part of the input gradient
@@ -732,9 +783,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                         }
                         release(1);
                         produce();
+                        VS_TR(2, 40);
                     }
                 }
             }
+            VS_TR_END(2);
         }
     } else if (warp == kMlpThreads / 32) {
         // ================= MMA issuer warp =================
@@ -743,6 +796,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             RingCursor cur{0};
             uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
             uint32_t par_ready = 0, par_act = 0, n_dw = 0;
+            VS_TR_DECL;
             const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
             for (int64_t k = 0; k < my_tiles; ++k) {
                 int off_dz = cur.alloc(p2.item_bytes[0], R);
@@ -758,7 +812,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     }
                     const bool want_dx = (l == 0) && p2.want_dx;
                     const uint32_t a_addr = ring_addr + (uint32_t)off_a, dz_addr = ring_addr + (uint32_t)off_dz;
+                    VS_TR(0, 10 + l);
                     mbar_wait(&bar_ready, par_ready);  // dZ_l is complete (and the work columns have been read)
+                    VS_TR(0, 20 + l);
                     par_ready ^= 1;
                     tc_fence_after();
                     if (l >= 1 || want_dx) {  // dA_l = dZ_l W_l: A = dZ_l K-major (K = fan-out), B = W_l read MN-major from the blob
@@ -766,6 +822,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                                       (uint32_t)N * 16, 256, umma_idesc_f16(kTileM, K) | kIdescBMn, N / 16, false);
                         tc_commit(&bar_da);
                     }
+                    VS_TR(0, 30 + l);
                     if (l >= 1) {
                         mbar_wait(&bar_act, par_act);  // the epilogue warps have turned the landed Z_{l-1} into A_l = act(Z_{l-1}) in place
                         par_act ^= 1;
@@ -773,6 +830,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     } else {
                         mbar_wait(&bar_item[seq_a & (kItemBars - 1)], (seq_a / kItemBars) & 1u);  // A_0 has landed
                     }
+                    VS_TR(0, 40 + l);
                     umma_gemm_f16(tmem_base + (uint32_t)plan.dw_col[l], a_addr, mn_lbo, mn_sbo, 256, dz_addr, mn_lbo, mn_sbo, 256,
                                   umma_idesc_f16(kTileM, N) | kIdescAMn | kIdescBMn, kTileM / 16, k > 0);
                     if (!plan.fold_bias[l])
@@ -780,6 +838,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                                       umma_idesc_f16(kTileM, 16) | kIdescAMn | kIdescBMn, kTileM / 16, k > 0);
                     tc_commit(&bar_dw[n_dw & 3u]);  // the ring warp frees dZ_l and A_l when these GEMMs have read them
                     ++n_dw;
+                    VS_TR(0, 50 + l);
                     if (want_dx) {
                         cur.alloc(p2.item_bytes[p2.n_items - 1], R);
                         ++seq;
@@ -787,6 +846,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     off_dz = off_next;
                 }
             }
+            VS_TR_END(0);
         }
     } else {
         // ================= epilogue warps =================
@@ -795,6 +855,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
         uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
         uint32_t par_da = 0;
         uint32_t n_act = 0;  // conversions this warp has announced on bar_act
+        VS_TR_DECL;
         auto announce = [&](uint64_t* bar) {
             fence_proxy_async();
             tc_fence_before();
@@ -809,6 +870,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             const int64_t r = row0 + row;
             const bool live = row < rows;
 
+            VS_TR_E(1);
             // item 0: dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z))
             const int off_last = cur.alloc(p2.item_bytes[0], R);
             // each 8-column chunk of dZ_last belongs to one column group (the output layer is 16 or 32 columns wide)
@@ -840,7 +902,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                         g[j] = __ldg(d_out + r * cfg.out_dim + j) * ds * scale;
                     }
             }
+            VS_TR_E(2);
             mbar_wait(item_bar(seq), item_parity(seq));  // the ring space is reserved (its previous tenants have been released)
+            VS_TR_E(3);
+            VS_TR_E(4);  // calibration: the cost of an event itself
+            VS_TR_E(5);
             ++seq;
             if (cg < n_chunks_last) {
                 __half2 h[4];
@@ -858,11 +924,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                 if (l >= 1) {
                     // Z_{l-1} (fp16 pre-activations, landed by TMA) -> A_l = act(Z_{l-1}) in place (the dW_l GEMM's operand) and this
                     // thread's elements of act'(Z_{l-1}) in registers, while the tensor core computes dA_l
+                    VS_TR_E(10 + l);
                     mbar_wait(item_bar(seq_a), item_parity(seq_a));
+                    VS_TR_E(20 + l);
                     // nothing else orders this warp's NEXT arrival on bar_act after the completion of the phase it arrived on last (a fast
                     // warp could otherwise arrive twice in one phase and release the dW GEMM before a slow warp has converted its part)
                     if (n_act > 0) mbar_wait(&bar_act, (n_act - 1) & 1u);
                     ++n_act;
+                    VS_TR_E(30 + l);
                     uint4 gq[2][2];
 #pragma unroll
                     for (int it = 0; it < 2; ++it) {
@@ -886,10 +955,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                         }
                     }
                     announce(&bar_act);
+                    VS_TR_E(40 + l);
                     const int off_next = cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
                     mbar_wait(item_bar(seq), item_parity(seq));
+                    VS_TR_E(50 + l);
                     ++seq;
                     mbar_wait(&bar_da, par_da);
+                    VS_TR_E(60 + l);
                     par_da ^= 1;
                     tc_fence_after();
 #pragma unroll
@@ -912,12 +984,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                         }
                     }
                     announce(&bar_ready);
+                    VS_TR_E(70 + l);
                 } else if (p2.want_dx) {
                     const int off_x = cur.alloc(p2.item_bytes[p2.n_items - 1], R);
+                    VS_TR_E(80);
                     mbar_wait(item_bar(seq), item_parity(seq));
+                    VS_TR_E(81);
                     ++seq;
                     float* xs = reinterpret_cast<float*>(s_ring + off_x);
                     mbar_wait(&bar_da, par_da);
+                    VS_TR_E(82);
                     par_da ^= 1;
                     tc_fence_after();
 #pragma unroll
@@ -938,9 +1014,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                         }
                     }
                     announce(&bar_x);
+                    VS_TR_E(83);
                 }
             }
         }
+        if (tid == 0) VS_TR_END(1);
     }
 
     // ---- this CTA's parameter-gradient accumulators -> its slice of the workspace ---------------------------------------
@@ -982,6 +1060,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
 using namespace vs;
 
 extern "C" {
+
+#ifdef VS_KERNEL_TRACE
+// copies the trace out (out_host: 3 * 2 * 256 int64, n_host: 3 counters)
+int vs_debug_trace(long long* out_host, int* n_host) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out_host, g_trace, sizeof(g_trace));
+    cudaMemcpyFromSymbol(n_host, g_trace_n, sizeof(g_trace_n));
+    return 0;
+}
+#endif
 
 static int bwd_setup(int n_layers, const int* dims, int pos_dim, int sh_degree, int normal_dep, MlpConfig* c, MlpBwdPlan* p,
                      bool check_recompute_smem = true) {
