@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                                                                       float* __restrict__ d_pos, float* __restrict__ partials,
                                                                       int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw[4], bar_ready, bar_x, bar_act, bar_item[kItemBars];
+    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw[4], bar_ready, bar_x, bar_act[2], bar_item[kItemBars];
     __shared__ uint32_t tmem_slot;
     // per-layer tables indexed with the run-time layer number: shared-memory copies (see mlp_fwd_kernel)
     __shared__ MlpConfig cfg;
@@ -667,7 +667,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
         for (int i = 0; i < 4; ++i) mbar_init(&bar_dw[i], 1);
         mbar_init(&bar_ready, kMlpThreads / 32);
         mbar_init(&bar_x, kMlpThreads / 32);
-        mbar_init(&bar_act, kMlpThreads / 32);
+        mbar_init(&bar_act[0], kMlpThreads / 32);
+        mbar_init(&bar_act[1], kMlpThreads / 32);
         for (int i = 0; i < kItemBars; ++i) mbar_init(&bar_item[i], 1);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)plan.tmem_cols);
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             mbar_wait(&bar_w, 0);
             RingCursor cur{0};
             uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
-            uint32_t par_ready = 0, par_act = 0, n_dw = 0;
+            uint32_t par_ready = 0, n_act = 0, n_dw = 0;
             VS_TR_DECL;
             const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
             for (int64_t k = 0; k < my_tiles; ++k) {
@@ -824,8 +825,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     }
                     VS_TR(0, 30 + l);
                     if (l >= 1) {
-                        mbar_wait(&bar_act, par_act);  // the epilogue warps have turned the landed Z_{l-1} into A_l = act(Z_{l-1}) in place
-                        par_act ^= 1;
+                        // the epilogue warps have turned the landed Z_{l-1} into A_l = act(Z_{l-1}) in place
+                        mbar_wait(&bar_act[n_act & 1u], (n_act >> 1) & 1u);
+                        ++n_act;
                         tc_fence_after();
                     } else {
                         mbar_wait(&bar_item[seq_a & (kItemBars - 1)], (seq_a / kItemBars) & 1u);  // A_0 has landed
@@ -862,6 +864,66 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
+        // dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z)); each 8-column
+        // chunk of it belongs to one column group (the output layer is 16 or 32 columns wide).  Its global loads are issued a tile
+        // ahead (fetch_last) from clamped, always-valid addresses -- unconditional volatile asm, so that nothing (no select against
+        // a default, no sinking to the use) waits for them before finish_last turns them into g[] at the top of their tile.
+        const int n_chunks_last = cfg.n_pad[L - 1] / 8;
+        float g[8], raw_d[8], raw_o[8], raw_n[6];
+        int64_t raw_r = 0;
+        auto ld_early = [](const float* p) {
+            float v;
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+            return v;
+        };
+        const bool loads_rows = cfg.out_linear ? cg < n_chunks_last : cg == 0;
+        auto fetch_last = [&](int64_t k) {
+            raw_r = k < my_tiles ? (blockIdx.x + k * gridDim.x) * kTileM + row : n;
+            if (!loads_rows) return;
+            const int64_t r = min(raw_r, n - 1);
+            const int od = cfg.out_dim;
+            if (cfg.out_linear) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) raw_d[j] = ld_early(d_out + r * od + min(cg * 8 + j, od - 1));
+            } else {
+                if (cfg.alpha_decay) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        raw_n[j] = ld_early(dirs + 3 * r + j);
+                        raw_n[3 + j] = ld_early(normals + 3 * r + j);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    raw_o[j] = ld_early(fwd_out + r * od + min(j, od - 1));
+                    raw_d[j] = ld_early(d_out + r * od + min(j, od - 1));
+                }
+            }
+        };
+        auto finish_last = [&]() {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = 0.f;
+            if (!loads_rows || raw_r >= n) return;
+            if (cfg.out_linear) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (cg * 8 + j < cfg.out_dim) g[j] = raw_d[j] * scale;
+            } else {
+                float decay = 1.f;
+                if (cfg.alpha_decay) {
+                    const float dot = fminf(fmaxf(-(raw_n[0] * raw_n[3] + raw_n[1] * raw_n[4] + raw_n[2] * raw_n[5]), 0.f), 1.f);
+                    decay = 2.f * sigmoid_f(10.f * dot) - 1.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < cfg.out_dim) {
+                        const float o = raw_o[j];
+                        const float ds = decay != 0.f ? o * (1.f - __fdividef(o, decay)) : 0.f;
+                        g[j] = raw_d[j] * ds * scale;
+                    }
+            }
+        };
+        if (n > 0) fetch_last(0);
         for (int64_t k = 0; k < my_tiles; ++k) {
             const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t row0 = tile * kTileM;
@@ -871,37 +933,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             const bool live = row < rows;
 
             VS_TR_E(1);
-            // item 0: dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z))
+            // item 0: dZ of the output layer (g[], loaded one tile ahead: see fetch_last / finish_last)
             const int off_last = cur.alloc(p2.item_bytes[0], R);
-            // each 8-column chunk of dZ_last belongs to one column group (the output layer is 16 or 32 columns wide)
-            const int n_chunks_last = cfg.n_pad[L - 1] / 8;
-            float g[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = 0.f;
-            if (cfg.out_linear) {
-                if (cg < n_chunks_last && live) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = cg * 8 + j;
-                        if (col < cfg.out_dim) g[j] = __ldg(d_out + r * cfg.out_dim + col) * scale;
-                    }
-                }
-            } else if (cg == 0 && live) {
-                float decay = 1.f;
-                if (cfg.alpha_decay) {
-                    const float dx = __ldg(dirs + 3 * r), dy = __ldg(dirs + 3 * r + 1), dz = __ldg(dirs + 3 * r + 2);
-                    const float nx = __ldg(normals + 3 * r), ny = __ldg(normals + 3 * r + 1), nz = __ldg(normals + 3 * r + 2);
-                    const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
-                    decay = 2.f * sigmoid_f(10.f * dot) - 1.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < cfg.out_dim) {
-                        const float o = __ldg(fwd_out + r * cfg.out_dim + j);
-                        const float ds = decay != 0.f ? o * (1.f - __fdividef(o, decay)) : 0.f;
-                        g[j] = __ldg(d_out + r * cfg.out_dim + j) * ds * scale;
-                    }
-            }
+            VS_TR_E(6);
+            finish_last();
+            VS_TR_E(7);
+            fetch_last(k + 1);
             VS_TR_E(2);
             mbar_wait(item_bar(seq), item_parity(seq));  // the ring space is reserved (its previous tenants have been released)
             VS_TR_E(3);
@@ -927,10 +964,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     VS_TR_E(10 + l);
                     mbar_wait(item_bar(seq_a), item_parity(seq_a));
                     VS_TR_E(20 + l);
-                    // nothing else orders this warp's NEXT arrival on bar_act after the completion of the phase it arrived on last (a fast
-                    // warp could otherwise arrive twice in one phase and release the dW GEMM before a slow warp has converted its part)
-                    if (n_act > 0) mbar_wait(&bar_act, (n_act - 1) & 1u);
-                    ++n_act;
+                    // conversions are announced on two barriers in turn: nothing orders a warp's next conversion after the completion of
+                    // the phase it arrived on last (a fast warp would arrive twice in one phase of a single barrier and release the dW GEMM
+                    // before a slow warp has converted its part), but its conversion after that lies behind a dA GEMM that every warp's
+                    // previous announcement precedes
                     VS_TR_E(30 + l);
                     uint4 gq[2][2];
 #pragma unroll
@@ -954,7 +991,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                             }
                         }
                     }
-                    announce(&bar_act);
+                    announce(&bar_act[n_act & 1u]);
+                    ++n_act;
                     VS_TR_E(40 + l);
                     const int off_next = cur.alloc(kTileM * cfg.n_pad[l - 1] * 2, R);
                     mbar_wait(item_bar(seq), item_parity(seq));
