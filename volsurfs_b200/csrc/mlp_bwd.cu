@@ -20,6 +20,7 @@
 //   4. the input gradient (first pos_dim columns of dA_0, un-scaled) leaves through shared memory as one TMA bulk store per tile.
 // After its last tile a CTA writes its dW/db accumulators to a per-CTA slice of the workspace; mlp_bwd_reduce_kernel sums the slices
 // in a fixed order (deterministic), removes the loss scale and writes / accumulates the fp32 parameter gradients.
+#include <type_traits>
 #include <cstdlib>
 
 #include "mlp_common.cuh"
@@ -531,7 +532,7 @@ struct MlpBwd2Plan {
 };
 
 constexpr int kItemBars = 16;
-constexpr int kBwdThreads = kMlpThreads + 64;  // 16 epilogue warps + the MMA issuer warp + the ring warp
+constexpr int kBwdThreads = kMlpThreads + 96;  // 16 epilogue warps + the MMA issuer warp + the ring warp + the output-gradient warp
 
 static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_dim, int want_dx, MlpBwd2Plan* p) {
     std::memset(p, 0, sizeof(*p));
@@ -556,7 +557,7 @@ static inline int mlp_bwd2_plan(const MlpConfig& c, const MlpStash& st, int pos_
     // ring | ones (bias side-GEMM operand) | blob.  MN-major operands read a fixed 16-chunk (32 KB) window from their base: what
     // lies behind the ring must cover it.
     const int tail = kOnesBytes + std::max(c.blob_bytes, 16 * kChunkBytes);
-    int ring = (227 * 1024 - 512 - tail) / 2048 * 2048;
+    int ring = (227 * 1024 - 2048 - tail) / 2048 * 2048;  // 2 KB: the kernel's static shared memory (barriers, table copies) + alignment
     int top3[3] = {0, 0, 0};
     for (int k = 0; k < p->n_items; ++k) {
         int b = p->item_bytes[k];
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                                                                       float* __restrict__ d_pos, float* __restrict__ partials,
                                                                       int64_t n_samples, const int64_t* __restrict__ n_valid_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw[4], bar_ready, bar_x, bar_act[2], bar_item[kItemBars];
+    __shared__ __align__(8) uint64_t bar_w, bar_da, bar_dw[4], bar_ready, bar_x, bar_act[2], bar_item[kItemBars], bar_fill[kItemBars];
     __shared__ uint32_t tmem_slot;
     // per-layer tables indexed with the run-time layer number: shared-memory copies (see mlp_fwd_kernel)
     __shared__ MlpConfig cfg;
@@ -670,6 +671,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
         mbar_init(&bar_act[0], kMlpThreads / 32);
         mbar_init(&bar_act[1], kMlpThreads / 32);
         for (int i = 0; i < kItemBars; ++i) mbar_init(&bar_item[i], 1);
+        for (int i = 0; i < kItemBars; ++i) mbar_init(&bar_fill[i], 1);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)plan.tmem_cols);
     if (tid < kTileM) *reinterpret_cast<uint4*>(s_ones + tid * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
@@ -682,7 +684,117 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
     auto item_bar = [&](uint32_t seq) { return &bar_item[seq & (kItemBars - 1)]; };
     auto item_parity = [&](uint32_t seq) { return (seq / kItemBars) & 1u; };
 
-    if (warp == kMlpThreads / 32 + 1) {
+    if (warp == kMlpThreads / 32 + 2) {
+        // ================= output-gradient warp: fills item 0 (dZ of the output layer) of every tile =================
+        // dZ_last = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z)); linear heads: dOut * scale.
+        // A lane owns four rows.  This used to be the first thing the epilogue warps did in a tile: ~1.7k cycles of dependent loads
+        // and scalar code with the tensor core and every other warp waiting (clock64 trace).  Here it runs as far ahead of them as
+        // the ring reserves the item (most of a tile).  bar_fill uses the item barriers' slot scheme, so a slot's next phase cannot
+        // start before the issuer has consumed this one (the item is released after the GEMMs that read it).
+        if (my_tiles > 0) {
+            RingCursor cur{0};
+            uint32_t seq = 0;
+            const int n_items = p2.n_items;
+            const int n_chunks_last = cfg.n_pad[L - 1] / 8;
+            const int od = cfg.out_dim;
+            const bool linear = cfg.out_linear != 0, use_decay = cfg.alpha_decay != 0;
+            for (int64_t k = 0; k < my_tiles; ++k) {
+                const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTileM;
+                const int off_last = cur.alloc(p2.item_bytes[0], R);
+                for (int i = 1; i < n_items; ++i) cur.alloc(p2.item_bytes[i], R);
+                const uint32_t seq0 = seq;
+                seq += (uint32_t)n_items;
+                // the values are computed into registers BEFORE the wait for the item's ring space (that reservation comes late: the
+                // item sits behind the previous tile's input-gradient item), all loads of a batch issued together
+                if (!linear) {  // sigmoid heads: at most 8 outputs, chunk 0 carries them, the other chunks are zero
+                    // W outputs wide, ROWS rows of the lane in flight at a time (the first batch before the wait for the ring space)
+                    auto fill = [&](auto w_tag, auto rows_tag) {
+                        constexpr int W = decltype(w_tag)::value, ROWS = decltype(rows_tag)::value;
+#pragma unroll 1
+                        for (int q0 = 0; q0 < kTileM / 32; q0 += ROWS) {
+                            uint4 hv[ROWS];
+#pragma unroll
+                            for (int q = 0; q < ROWS; ++q) {
+                                const int64_t r_raw = row0 + lane + 32 * (q0 + q);
+                                const int64_t r = min(r_raw, n - 1);  // clamped: the loads carry no branch; dead rows are zeroed below
+                                float d[W], o[W], dn[6];
+#pragma unroll
+                                for (int j = 0; j < W; ++j) {
+                                    const int col = min(j, od - 1);
+                                    d[j] = __ldg(d_out + r * od + col);
+                                    o[j] = __ldg(fwd_out + r * od + col);
+                                }
+                                float decay = 1.f;
+                                if (use_decay) {
+#pragma unroll
+                                    for (int j = 0; j < 3; ++j) {
+                                        dn[j] = __ldg(dirs + 3 * r + j);
+                                        dn[3 + j] = __ldg(normals + 3 * r + j);
+                                    }
+                                    const float dot = fminf(fmaxf(-(dn[0] * dn[3] + dn[1] * dn[4] + dn[2] * dn[5]), 0.f), 1.f);
+                                    decay = 2.f * sigmoid_f(10.f * dot) - 1.f;
+                                }
+                                float g[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+                                for (int j = 0; j < W; ++j) {
+                                    const float ds = decay != 0.f ? o[j] * (1.f - __fdividef(o[j], decay)) : 0.f;
+                                    if (r_raw < n && j < od) g[j] = d[j] * ds * scale;
+                                }
+                                __half2 h[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(g[2 * j], g[2 * j + 1]);
+                                hv[q] = *reinterpret_cast<const uint4*>(h);
+                            }
+                            if (q0 == 0) mbar_wait(item_bar(seq0), item_parity(seq0));  // the ring space is reserved
+#pragma unroll
+                            for (int q = 0; q < ROWS; ++q) {
+                                uint4* dst = reinterpret_cast<uint4*>(s_ring + off_last + (size_t)(lane + 32 * (q0 + q)) * 16);
+                                dst[0] = hv[q];
+                                for (int c = 1; c < n_chunks_last; ++c) dst[c * kTileM] = make_uint4(0u, 0u, 0u, 0u);
+                            }
+                        }
+                    };
+                    if (od <= 4) fill(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
+                    else fill(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+                } else {  // linear heads (texture nets, up to 32 outputs): two rows per lane in registers at a time
+                    constexpr int kMaxChunks = 4;  // the output layer is at most 32 columns wide (mlp_layout)
+#pragma unroll 1
+                    for (int q0 = 0; q0 < kTileM / 32; q0 += 2) {
+                        uint4 hv[2][kMaxChunks];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int64_t r = min(row0 + lane + 32 * (q0 + q), n - 1);
+                            const bool live = row0 + lane + 32 * (q0 + q) < n;
+#pragma unroll
+                            for (int c = 0; c < kMaxChunks; ++c) {
+                                float d[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) d[j] = __ldg(d_out + r * od + min(c * 8 + j, od - 1));
+                                __half2 h[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    h[j] = __floats2half2_rn((live && c * 8 + 2 * j < od) ? d[2 * j] * scale : 0.f,
+                                                             (live && c * 8 + 2 * j + 1 < od) ? d[2 * j + 1] * scale : 0.f);
+                                hv[q][c] = *reinterpret_cast<const uint4*>(h);
+                            }
+                        }
+                        if (q0 == 0) mbar_wait(item_bar(seq0), item_parity(seq0));
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int c = 0; c < kMaxChunks; ++c)
+                                if (c < n_chunks_last)
+                                    *reinterpret_cast<uint4*>(s_ring + off_last + ((size_t)c * kTileM + lane + 32 * (q0 + q)) * 16) = hv[q][c];
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_fill[seq0 & (kItemBars - 1)]);
+            }
+        }
+    } else if (warp == kMlpThreads / 32 + 1) {
         // ================= ring warp: TMA producer, ring-space accounting, input-gradient store =================
         // Kept off the MMA issuer's lane: a release + produce round is several hundred cycles of dependent scalar work, which sat
         // between every layer's dW commit and the next layer's dA issue while one lane did both jobs (clock64 trace, round 2).
@@ -796,12 +908,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             mbar_wait(&bar_w, 0);
             RingCursor cur{0};
             uint32_t seq = 0;  // only its low bits matter (barrier slot and phase parity)
-            uint32_t par_ready = 0, n_act = 0, n_dw = 0;
+            uint32_t par_ready = 0, n_act = 0, n_dw = 0, fill_parity = 0;
             VS_TR_DECL;
             const uint32_t blob_addr = smem_u32(s_blob), ring_addr = smem_u32(s_ring), ones_addr = smem_u32(s_ones);
             for (int64_t k = 0; k < my_tiles; ++k) {
                 int off_dz = cur.alloc(p2.item_bytes[0], R);
-                ++seq;
+                const uint32_t seq0 = seq++;
                 for (int l = L - 1; l >= 0; --l) {
                     const int K = cfg.k_pad[l], N = cfg.n_pad[l];
                     const int off_a = cur.alloc(st.a_bytes[l], R);
@@ -817,6 +929,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
                     mbar_wait(&bar_ready, par_ready);  // dZ_l is complete (and the work columns have been read)
                     VS_TR(0, 20 + l);
                     par_ready ^= 1;
+                    if (l == L - 1) {  // dZ of the output layer is there (a fill slot only sees the item-0 arrivals: its parity is kept here)
+                        const uint32_t s0 = seq0 & (kItemBars - 1);
+                        mbar_wait(&bar_fill[s0], (fill_parity >> s0) & 1u);
+                        fill_parity ^= 1u << s0;
+                    }
                     tc_fence_after();
                     if (l >= 1 || want_dx) {  // dA_l = dZ_l W_l: A = dZ_l K-major (K = fan-out), B = W_l read MN-major from the blob
                         umma_gemm_f16(tmem_base, dz_addr, kChunkBytes, 128, 2 * kChunkBytes, blob_addr + (uint32_t)cfg.w_off[l], 128u,
@@ -864,66 +981,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
-        // dZ of the output layer = dOut * d(out)/dz * scale, d(out)/dz = out (1 - out/decay)  (out = decay * sigmoid(z)); each 8-column
-        // chunk of it belongs to one column group (the output layer is 16 or 32 columns wide).  Its global loads are issued a tile
-        // ahead (fetch_last) from clamped, always-valid addresses -- unconditional volatile asm, so that nothing (no select against
-        // a default, no sinking to the use) waits for them before finish_last turns them into g[] at the top of their tile.
-        const int n_chunks_last = cfg.n_pad[L - 1] / 8;
-        float g[8], raw_d[8], raw_o[8], raw_n[6];
-        int64_t raw_r = 0;
-        auto ld_early = [](const float* p) {
-            float v;
-            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-            return v;
-        };
-        const bool loads_rows = cfg.out_linear ? cg < n_chunks_last : cg == 0;
-        auto fetch_last = [&](int64_t k) {
-            raw_r = k < my_tiles ? (blockIdx.x + k * gridDim.x) * kTileM + row : n;
-            if (!loads_rows) return;
-            const int64_t r = min(raw_r, n - 1);
-            const int od = cfg.out_dim;
-            if (cfg.out_linear) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) raw_d[j] = ld_early(d_out + r * od + min(cg * 8 + j, od - 1));
-            } else {
-                if (cfg.alpha_decay) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        raw_n[j] = ld_early(dirs + 3 * r + j);
-                        raw_n[3 + j] = ld_early(normals + 3 * r + j);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    raw_o[j] = ld_early(fwd_out + r * od + min(j, od - 1));
-                    raw_d[j] = ld_early(d_out + r * od + min(j, od - 1));
-                }
-            }
-        };
-        auto finish_last = [&]() {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = 0.f;
-            if (!loads_rows || raw_r >= n) return;
-            if (cfg.out_linear) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (cg * 8 + j < cfg.out_dim) g[j] = raw_d[j] * scale;
-            } else {
-                float decay = 1.f;
-                if (cfg.alpha_decay) {
-                    const float dot = fminf(fmaxf(-(raw_n[0] * raw_n[3] + raw_n[1] * raw_n[4] + raw_n[2] * raw_n[5]), 0.f), 1.f);
-                    decay = 2.f * sigmoid_f(10.f * dot) - 1.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < cfg.out_dim) {
-                        const float o = raw_o[j];
-                        const float ds = decay != 0.f ? o * (1.f - __fdividef(o, decay)) : 0.f;
-                        g[j] = raw_d[j] * ds * scale;
-                    }
-            }
-        };
-        if (n > 0) fetch_last(0);
         for (int64_t k = 0; k < my_tiles; ++k) {
             const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t row0 = tile * kTileM;
@@ -933,25 +990,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_stashed_kernel(const _
             const bool live = row < rows;
 
             VS_TR_E(1);
-            // item 0: dZ of the output layer (g[], loaded one tile ahead: see fetch_last / finish_last)
-            const int off_last = cur.alloc(p2.item_bytes[0], R);
-            VS_TR_E(6);
-            finish_last();
-            VS_TR_E(7);
-            fetch_last(k + 1);
-            VS_TR_E(2);
-            mbar_wait(item_bar(seq), item_parity(seq));  // the ring space is reserved (its previous tenants have been released)
-            VS_TR_E(3);
-            VS_TR_E(4);  // calibration: the cost of an event itself
-            VS_TR_E(5);
+            // item 0 (dZ of the output layer) is filled by the output-gradient warp; this announcement only says that the warp has read
+            // the previous tile's last accumulator out of the work columns
+            cur.alloc(p2.item_bytes[0], R);
             ++seq;
-            if (cg < n_chunks_last) {
-                __half2 h[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
-                uint4* dst = reinterpret_cast<uint4*>(s_ring + off_last + (size_t)row * 16);
-                dst[cg * kTileM] = *reinterpret_cast<const uint4*>(h);
-            }
             announce(&bar_ready);
 
             for (int l = L - 1; l >= 0; --l) {
