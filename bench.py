@@ -430,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
             e = encs[k].encoder
             grad_lat[k].zero_()
             e._launch_backward(e.lattice_values, rsp.samples_3d, encs[k].window(None), dfeat[k], encs[k].bb_sides, rsp.total_dev,
-                               want_lattice=True, d_lattice=grad_lat[k])
+                               want_lattice=True, d_lattice=grad_lat[k], order_key=rsp.samples_layer)
             mark(12 + 2 * i)
         out["loss"] = loss
         return out, loss, rsp

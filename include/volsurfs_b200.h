@@ -252,6 +252,15 @@ int vs_permuto_forward(int pos_dim, int n_levels, int64_t capacity, int concat_p
 int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
                         const float* lattice, const float* scale, const float* shift, const float* window, const float* d_out, int in_cols,
                         int64_t in_stride, float* d_lattice, float* d_positions, int64_t n, const int64_t* n_valid_dev, void* stream);
+/* Same, with a per-position ordering hint order_key [n] (int32, low 5 bits used) or NULL: every block of 128 positions is walked in key
+ * order, which makes positions with equal keys neighbours in a warp.  For a packed K-layer ray packet key = samples_layer turns the
+ * same-layer hits of neighbouring rays (which share lattice vertices) into adjacent lanes, whose reductions are merged before they leave
+ * the SM.  A pure performance hint: the sums are the same contributions in another order (the reference's atomics are unordered too,
+ * EncodingGPU.cuh:560-612). */
+int vs_permuto_backward_keyed(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
+                              const int32_t* order_key, const float* lattice, const float* scale, const float* shift, const float* window,
+                              const float* d_out, int in_cols, int64_t in_stride, float* d_lattice, float* d_positions, int64_t n,
+                              const int64_t* n_valid_dev, void* stream);
 
 /* ---- SH neural textures: the default appearance (SURVEY 8a row a6' / 8f row 4) ------------------------------------------------------
  * Replaces SHNeuralTextures.forward (volsurfs_py/models/sh_neural_textures.py:64-97), NeuralTexture.forward

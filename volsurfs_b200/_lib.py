@@ -63,6 +63,7 @@ SIGNATURES = {
     "vs_permuto_output_dims": (c_int, [c_int, c_int, c_int]),
     "vs_permuto_forward": (c_int, [c_int, c_int, _I64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _I64, _P, _P]),
     "vs_permuto_backward": (c_int, [c_int, c_int, _I64, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _P, _I64, _P, _P]),
+    "vs_permuto_backward_keyed": (c_int, [c_int, c_int, _I64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _P, _P, _I64, _P, _P]),
     "vs_hashgrid_levels": (_I64, [c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     "vs_hashgrid_forward": (c_int, [c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, _P, _P, _P, _I64, _P, _P]),
     "vs_hashgrid_backward": (c_int, [c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, _P, _P, _P, _I64, _P, _P]),

@@ -117,6 +117,13 @@ __device__ __forceinline__ void locate(const float (&pos)[D], const float* __res
 // key_i = rem0_i + remainder - (rank_i > D - remainder ? D + 1 : 0) as k = (k + key_i) * M, i = 0..D-1: in uint32 ring arithmetic that is
 // the LINEAR form  sum_i key_i M^(D-i)  =  [sum_i rem0_i M^(D-i)]  +  remainder [sum_i M^(D-i)]  -  (D+1) sum_i [rank_i + remainder > D] M^(D-i),
 // bit-identical (wrap-around arithmetic is exact), with the first bracket computed once per simplex (HashBase) instead of once per vertex.
+// a == k ? x : y as one setp + selp the compiler cannot re-interpret as an indexed array read
+__device__ __forceinline__ float select_eq(int a, int k, float x, float y) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tselp.f32 %0, %3, %4, p;\n\t}" : "=f"(r) : "r"(a), "r"(k), "f"(x), "f"(y));
+    return r;
+}
+
 template <int D>
 struct HashBase {
     uint32_t base;
@@ -261,8 +268,15 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
     }
 }
 
-template <int D>
+// DPOS: also the position gradient (the lattice-only instantiation, the training step's, carries none of that code or its registers).
+// KEYED: the block walks its 128 positions in the order of a small per-position key (a stable counting sort inside the tile).  The
+// lattice gradient is bound by the number of reduction lanes that leave the SM, and red_add_runs only merges ADJACENT lanes that hit
+// one vertex: in a packed K-layer ray packet adjacent samples are the K hits of one ray, while the samples that share vertices on the
+// mid and fine levels are the same layer's hits of the neighbouring rays, K lanes apart.  With key = layer they become neighbours
+// (B200, 893 k hits of the 5-shell benchmark scene: 0.604 ms in packed order, 0.416 ms layer-major, 1.33 ms shuffled).
+template <int D, bool DPOS, bool KEYED>
 __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, const float* __restrict__ positions,
+                                                                 const int* __restrict__ order_key,
                                                                  const float2* __restrict__ lattice, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, const float* __restrict__ window,
                                                                  const float* __restrict__ d_out, int in_cols, int64_t in_stride,
@@ -272,11 +286,50 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
     const int64_t n_eff = n_valid_dev ? min(n, *n_valid_dev) : n;
     const int64_t base = (int64_t)blockIdx.x * PM_TILE;
     if (base >= n_eff) return;
-    const int p = threadIdx.x & (PM_TILE - 1), half = threadIdx.x >> 7, lane = threadIdx.x & 31;
-    const int64_t idx = base + p;
-    const bool valid = idx < n_eff;
+    const int half = threadIdx.x >> 7, lane = threadIdx.x & 31;
+    int p = threadIdx.x & (PM_TILE - 1);   // row of the tile this thread works on
     const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
     const int n_cols = 2 * a.n_levels;   // the concat-points columns pass no gradient (Encoding.cu:135-139,163)
+    if (KEYED) {   // stable counting sort of the tile's rows by key (32 bins; rows beyond the end sort last)
+        __shared__ int s_count[PM_TILE / 32][32];
+        __shared__ unsigned char s_perm[PM_TILE];
+        const int w = p >> 5;
+        const int key = (p < rows) ? (__ldg(order_key + base + p) & 31) : 31;
+        const uint32_t peers = __match_any_sync(VS_FULL_MASK, key);
+        const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (half == 0) {
+            s_count[w][lane] = 0;
+            __syncwarp();
+            if (rank_in_warp == 0) s_count[w][key] = __popc(peers);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {   // lane k: rows with key k per warp -> start of (warp, key) in the sorted order
+            int c[PM_TILE / 32], tot = 0;
+#pragma unroll
+            for (int i = 0; i < PM_TILE / 32; i++) {
+                c[i] = s_count[i][lane];
+                tot += c[i];
+            }
+            int incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int o = __shfl_up_sync(VS_FULL_MASK, incl, d);
+                if (lane >= d) incl += o;
+            }
+            int start = incl - tot;
+#pragma unroll
+            for (int i = 0; i < PM_TILE / 32; i++) {
+                s_count[i][lane] = start;
+                start += c[i];
+            }
+        }
+        __syncthreads();
+        if (half == 0) s_perm[s_count[w][key] + rank_in_warp] = (unsigned char)p;
+        __syncthreads();
+        p = s_perm[p];
+    }
+    const int64_t idx = base + p;
+    const bool valid = idx < n_eff;
 
     {   // flat walk, (r, c) advanced incrementally (see permuto_fwd_kernel)
         const int step_r = PM_THREADS / in_cols, step_c = PM_THREADS - step_r * in_cols;
@@ -318,7 +371,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
                 red_add_runs(table, slot[r], gx * w, gy * w, valid, lane, a.agg_max_heads);
             }
         }
-        if (d_positions) {   // EncodingGPU.cuh:630-690
+        if (DPOS) {   // EncodingGPU.cuh:630-690
             const float2* table = lattice + (size_t)lvl * a.capacity;
             float dl_db[D + 2];
 #pragma unroll
@@ -330,18 +383,23 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
                 dl_db[r] = t;
             }
             dl_db[D + 1] = 0.f + dl_db[0];
+            // dl_de_i = dl_db[D - rank_i] / (D+1) - dl_db[D + 1 - rank_i] / (D+1): evaluated once per RANK (static indices), then each
+            // vertex picks the value of its rank with a chain of selects spelled in PTX (any C++ form of `x = table[rank_i]`, select chains
+            // included, is compiled into a dynamically indexed local-memory array: 5 STL + 40 LDL per level in the SASS of round 2)
+            float e_by_rank[D + 1];
+#pragma unroll
+            for (int k = 0; k <= D; k++) {
+                float e = 0.f;
+                e += dl_db[D - k] * (1.0f / (D + 1));
+                e -= dl_db[D + 1 - k] * (1.0f / (D + 1));
+                e_by_rank[k] = e;
+            }
             float dl_de[D + 1];
 #pragma unroll
             for (int i = 0; i <= D; i++) {
-                float plus = 0.f, minus = 0.f;   // dl_db[D - rank_i], dl_db[D + 1 - rank_i]
-#pragma unroll
-                for (int t = 0; t <= D + 1; t++) {
-                    if (D - s.rank[i] == t) plus = dl_db[t];
-                    if (D + 1 - s.rank[i] == t) minus = dl_db[t];
-                }
                 float e = 0.f;
-                e += plus * (1.0f / (D + 1));
-                e -= minus * (1.0f / (D + 1));
+#pragma unroll
+                for (int k = 0; k <= D; k++) e = select_eq(s.rank[i], k, e_by_rank[k], e);
                 dl_de[i] = e;
             }
 #pragma unroll
@@ -355,7 +413,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
             }
         }
     }
-    if (d_positions) {
+    if (DPOS) {
         __syncthreads();   // every thread is done reading the gradient tile
         if (half == 1) {
 #pragma unroll
@@ -434,9 +492,10 @@ int vs_permuto_forward(int pos_dim, int n_levels, int64_t capacity, int concat_p
     return launched(1);
 }
 
-int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
-                        const float* lattice, const float* scale, const float* shift, const float* window, const float* d_out, int in_cols,
-                        int64_t in_stride, float* d_lattice, float* d_positions, int64_t n, const int64_t* n_valid_dev, void* stream) {
+int vs_permuto_backward_keyed(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
+                              const int32_t* order_key, const float* lattice, const float* scale, const float* shift, const float* window,
+                              const float* d_out, int in_cols, int64_t in_stride, float* d_lattice, float* d_positions, int64_t n,
+                              const int64_t* n_valid_dev, void* stream) {
     PermutoArgs a;
     int rc = fill_args(a, pos_dim, n_levels, capacity, concat_points, 1.0f, bb_sides);
     if (rc != VS_OK) return rc;
@@ -448,17 +507,36 @@ int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_
     const dim3 grid((unsigned)div_up(n, PM_TILE));
     const size_t smem = (size_t)cols * PM_PAD * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-#define VS_PM_BWD(D)                                                                                                                       \
-    permuto_bwd_kernel<D><<<grid, PM_THREADS, smem, st>>>(a, positions, (const float2*)lattice, scale, shift, window, d_out, in_cols,      \
-                                                           in_stride, (float2*)d_lattice, d_positions, n, n_valid_dev)
-    if (pos_dim == 2)
+#define VS_PM_BWD_(D, DPOS, KEYED)                                                                                                         \
+    permuto_bwd_kernel<D, DPOS, KEYED><<<grid, PM_THREADS, smem, st>>>(a, positions, order_key, (const float2*)lattice, scale, shift,      \
+                                                                        window, d_out, in_cols, in_stride, (float2*)d_lattice,             \
+                                                                        d_positions, n, n_valid_dev)
+#define VS_PM_BWD(D)                      \
+    if (d_positions && order_key)         \
+        VS_PM_BWD_(D, true, true);        \
+    else if (d_positions)                 \
+        VS_PM_BWD_(D, true, false);       \
+    else if (order_key)                   \
+        VS_PM_BWD_(D, false, true);       \
+    else                                  \
+        VS_PM_BWD_(D, false, false)
+    if (pos_dim == 2) {
         VS_PM_BWD(2);
-    else if (pos_dim == 3)
+    } else if (pos_dim == 3) {
         VS_PM_BWD(3);
-    else
+    } else {
         VS_PM_BWD(4);
+    }
 #undef VS_PM_BWD
+#undef VS_PM_BWD_
     return launched(1);
+}
+
+int vs_permuto_backward(int pos_dim, int n_levels, int64_t capacity, int concat_points, const float* bb_sides, const float* positions,
+                        const float* lattice, const float* scale, const float* shift, const float* window, const float* d_out, int in_cols,
+                        int64_t in_stride, float* d_lattice, float* d_positions, int64_t n, const int64_t* n_valid_dev, void* stream) {
+    return vs_permuto_backward_keyed(pos_dim, n_levels, capacity, concat_points, bb_sides, positions, nullptr, lattice, scale, shift, window,
+                                     d_out, in_cols, in_stride, d_lattice, d_positions, n, n_valid_dev, stream);
 }
 
 }  // extern "C"

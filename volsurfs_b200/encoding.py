@@ -135,13 +135,17 @@ class PermutoEncoding(torch.nn.Module):
         return out, oob
 
     def _launch_backward(self, lattice_values, positions, window, grad_out, bb_sides, n_valid_dev, want_lattice=True, want_positions=False,
-                         d_lattice=None, d_positions=None, levels=None):
+                         d_lattice=None, d_positions=None, levels=None, order_key=None):
         """``levels=(l0, l1)``: lattice gradient of that level range only (the levels are independent: every argument of the C entry
         point is simply offset to the range), so that a caller can hand finished level blocks to the gradient exchange while the next block
-        is still being computed"""
+        is still being computed.  ``order_key`` [N] int32 (e.g. ``RaySamplesPacked.samples_layer``): ordering hint, see
+        ``vs_permuto_backward_keyed`` in include/volsurfs_b200.h"""
         positions = positions.contiguous()
         grad_out = grad_out.contiguous()
         n = int(positions.shape[0])
+        if order_key is not None:
+            order_key = order_key.view(-1)
+            assert order_key.dtype == torch.int32 and order_key.is_contiguous() and order_key.shape[0] >= n
         if want_lattice and d_lattice is None:
             d_lattice = torch.zeros_like(lattice_values)
         if want_positions and d_positions is None:
@@ -152,18 +156,18 @@ class PermutoEncoding(torch.nn.Module):
             cols = min(2 * (l1 - l0), int(grad_out.shape[1]) - 2 * l0)
             assert cols >= 1
             fs = 4  # bytes per float
-            check(_lib.lib().vs_permuto_backward(
-                self.pos_dim, l1 - l0, self.capacity, 0, self._bb_c(bb_sides, self.pos_dim), ptr(positions),
+            check(_lib.lib().vs_permuto_backward_keyed(
+                self.pos_dim, l1 - l0, self.capacity, 0, self._bb_c(bb_sides, self.pos_dim), ptr(positions), ptr(order_key),
                 lattice_values.data_ptr() + l0 * self.capacity * 2 * fs, self.scale_factor.data_ptr() + l0 * self.pos_dim * fs,
                 self.random_shift_per_level.data_ptr() + l0 * self.pos_dim * fs, window.data_ptr() + l0 * fs,
                 grad_out.data_ptr() + 2 * l0 * fs, cols, int(grad_out.stride(0)), d_lattice.data_ptr() + l0 * self.capacity * 2 * fs,
-                None, n, ptr(n_valid_dev), _stream()), "vs_permuto_backward")
+                None, n, ptr(n_valid_dev), _stream()), "vs_permuto_backward_keyed")
             return d_lattice, None
-        check(_lib.lib().vs_permuto_backward(
+        check(_lib.lib().vs_permuto_backward_keyed(
             self.pos_dim, self.nr_levels, self.capacity, int(self.concat_points), self._bb_c(bb_sides, self.pos_dim), ptr(positions),
-            ptr(lattice_values.detach()), ptr(self.scale_factor), ptr(self.random_shift_per_level.detach()), ptr(window), ptr(grad_out),
+            ptr(order_key), ptr(lattice_values.detach()), ptr(self.scale_factor), ptr(self.random_shift_per_level.detach()), ptr(window), ptr(grad_out),
             int(grad_out.shape[1]), int(grad_out.stride(0)), ptr(d_lattice) if want_lattice else None,
-            ptr(d_positions) if want_positions else None, n, ptr(n_valid_dev), _stream()), "vs_permuto_backward")
+            ptr(d_positions) if want_positions else None, n, ptr(n_valid_dev), _stream()), "vs_permuto_backward_keyed")
         return (d_lattice if want_lattice else None), (d_positions if want_positions else None)
 
     # ---- reference interface -----------------------------------------------------------------------------------------------------

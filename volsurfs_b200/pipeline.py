@@ -204,7 +204,7 @@ class EncodedShellRenderer(ShellRenderer):
         d_lat = self._buf("dlat_" + name, tuple(e.lattice_values.shape), zero=True)
         d_lat.zero_()
         e._launch_backward(e.lattice_values, rsp.samples_3d, enc.window(None), d_feat, enc.bb_sides, rsp.total_dev, want_lattice=True,
-                           d_lattice=d_lat)
+                           d_lattice=d_lat, order_key=rsp.samples_layer)   # same-layer hits of neighbouring rays share lattice vertices
         return {"grad_" + name: flat, "grad_lattice_" + name: d_lat}
 
 
