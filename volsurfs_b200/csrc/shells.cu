@@ -8,9 +8,12 @@
 // Here:
 //   * the BVH of each layer is built on the host with a binned surface-area heuristic, collapsed to 4-wide nodes whose four
 //     child boxes sit in one 128-byte line (SoA: 6 x float4 + 4 child refs), emitted in breadth-first order;
-//   * one launch covers all (layer, ray) pairs: blockIdx.y is the layer, a CTA walks `kRaysPerBlock` consecutive rays;
+//   * one launch covers all (layer, ray) pairs with persistent CTAs (kTraceCtasPerSm per SM, split over the layers): every WARP draws
+//     its next 32 consecutive rays from the layer's work counter, so a warp whose rays miss everything is not parked until the slowest
+//     warp of its CTA is done (B200, C2 scene: 0.695 ms with a static 512-rays-per-CTA mapping, achieved occupancy 33 % of a 50 %
+//     limit -> 0.616 ms); a CTA whose layer has run dry moves on to the next layer that still has work;
 //   * the top of the layer's tree (first kTopNodes nodes = 4 levels) is staged into shared memory by one TMA bulk copy
-//     (cp.async.bulk + mbarrier) when the CTA starts, so the always-visited upper levels never leave the SM;
+//     (cp.async.bulk + mbarrier) when a CTA takes up a layer, so the always-visited upper levels never leave the SM;
 //   * triangles are 3 x float4 (vertex + original face index), read with 16-byte loads.
 //
 // Parity contract (bit-exact hits, pinned by the reference's own kernel): the ray/triangle arithmetic is the reference's
@@ -38,8 +41,9 @@ namespace vs {
 
 constexpr float kMaxDist = 1e6f;  // include/raytracing/common.h:21
 constexpr int kTraceThreads = 128;
-constexpr int kRaysPerThread = 4;
-constexpr int kRaysPerBlock = kTraceThreads * kRaysPerThread;
+constexpr int kTraceCtasPerSm = 8;   // 63 registers x 128 threads: 8 CTAs fit (measured: 4 -> 0.74 ms, 8 -> 0.616, 12 -> 0.646)
+constexpr int kTraceMaxLayers = 64;
+constexpr int kCounterSets = 8;      // work-counter sets handed out in turn, so that launches in flight on different streams do not share one
 constexpr int kTopNodes = 85;  // 1 + 4 + 16 + 64 nodes = first four levels of a full 4-ary tree (10.6 KB)
 constexpr int kStack = 48;
 constexpr int kLeafMax = 4;
@@ -64,7 +68,8 @@ struct Shells {
     int K = 0;
     std::vector<Layer> layers;
     Layer* layers_dev = nullptr;  // device copy of the table
-    int* overflow_dev = nullptr;  // set to 1 if a traversal stack ever overflowed
+    int* overflow_dev = nullptr;  // [0] set to 1 if a traversal stack ever overflowed; then kCounterSets x kTraceMaxLayers work counters
+    unsigned launches = 0;        // picks the counter set
 };
 
 // =====================================================================================================================
@@ -362,28 +367,41 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                                                                      const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                      int64_t n_rays, float* __restrict__ depth_out,
                                                                      int32_t* __restrict__ tri_out, float* __restrict__ u_out,
-                                                                     float* __restrict__ v_out, int* __restrict__ overflow) {
+                                                                     float* __restrict__ v_out, int* __restrict__ overflow, int layer_count,
+                                                                     int* __restrict__ work_counter) {
     __shared__ __align__(128) Node4 s_top[kTopNodes];
     __shared__ __align__(8) uint64_t bar;
-    const int layer = layer_first + blockIdx.y;
-    const Layer L = layers[layer];
+    __shared__ int s_dry;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    uint32_t n_staged = 0;
+    // the CTA's own layer first, then (once that one has run dry) the others in turn
+    for (int a = 0; a < layer_count; ++a) {
+    const int li = (int)((blockIdx.y + a) % layer_count);
+    __syncthreads();   // every warp is done with the previous layer's s_top (and the barrier is initialised)
+    if (threadIdx.x == 0) s_dry = (int64_t)(*reinterpret_cast<volatile int*>(work_counter + li)) * 32 >= n_rays;
+    __syncthreads();
+    if (s_dry) continue;
+    const Layer L = layers[layer_first + li];
     const int n_top = min(L.n_nodes, kTopNodes);
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
         mbar_arrive_expect_tx(&bar, (uint32_t)(n_top * sizeof(Node4)));
         bulk_g2s(s_top, L.nodes, (uint32_t)(n_top * sizeof(Node4)), &bar);
     }
-    __syncthreads();
-    mbar_wait(&bar, 0);
+    mbar_wait(&bar, n_staged & 1u);
+    ++n_staged;
 
     const Node4* __restrict__ gnodes = L.nodes;
     const float4* __restrict__ pre = L.pre;
     const float4* __restrict__ tris = L.tris;
-    const int64_t out_base = (int64_t)blockIdx.y * n_rays;  // outputs are [n_layers_traced, n_rays]
+    const int64_t out_base = (int64_t)li * n_rays;  // outputs are [n_layers_traced, n_rays]
 
-    for (int it = 0; it < kRaysPerThread; ++it) {
-        const int64_t r = (int64_t)blockIdx.x * kRaysPerBlock + it * kTraceThreads + threadIdx.x;
-        if (r >= n_rays) break;
+    for (;;) {
+        int c = 0;
+        if ((threadIdx.x & 31) == 0) c = atomicAdd(work_counter + li, 1);
+        c = __shfl_sync(VS_FULL_MASK, c, 0);
+        if ((int64_t)c * 32 >= n_rays) break;
+        const int64_t r = (int64_t)c * 32 + (threadIdx.x & 31);
+        if (r >= n_rays) continue;
         const float ox = __ldg(rays_o + 3 * r), oy = __ldg(rays_o + 3 * r + 1), oz = __ldg(rays_o + 3 * r + 2);
         const float dx = __ldg(rays_d + 3 * r), dy = __ldg(rays_d + 3 * r + 1), dz = __ldg(rays_d + 3 * r + 2);
         const float idx_ = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
@@ -574,6 +592,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
         u_out[out_base + r] = best_u;
         v_out[out_base + r] = best_v;
     }
+    }
 }
 
 // reference-format outputs of RayTracer.trace(mesh_id) (bvh.cu:440-468, raytracer.py:103-113) from the compact hit record
@@ -723,8 +742,8 @@ int vs_shells_build(int K, const float* const* verts, const int64_t* n_verts, co
         if ((err = cudaDeviceSynchronize()) != cudaSuccess) break;
         if ((err = cudaMemcpy(L.orig_to_bvh, o2b.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice)) != cudaSuccess) break;
     }
-    if (err == cudaSuccess) err = cudaMalloc(&S->overflow_dev, sizeof(int));
-    if (err == cudaSuccess) err = cudaMemset(S->overflow_dev, 0, sizeof(int));
+    if (err == cudaSuccess) err = cudaMalloc(&S->overflow_dev, (1 + kCounterSets * kTraceMaxLayers) * sizeof(int));
+    if (err == cudaSuccess) err = cudaMemset(S->overflow_dev, 0, (1 + kCounterSets * kTraceMaxLayers) * sizeof(int));
     if (err == cudaSuccess) err = cudaMalloc(&S->layers_dev, sizeof(Layer) * K);
     if (err == cudaSuccess) err = cudaMemcpy(S->layers_dev, S->layers.data(), sizeof(Layer) * K, cudaMemcpyHostToDevice);
     if (err != cudaSuccess) {
@@ -772,17 +791,30 @@ int vs_shells_num_layers(const void* handle) { return handle ? reinterpret_cast<
 int vs_shells_trace(const void* handle, const float* rays_o, const float* rays_d, int64_t n_rays, int layer_first, int layer_count,
                     float* depth_out, int32_t* tri_out, float* u_out, float* v_out, void* stream) {
     VS_CHECK_ARG(handle && n_rays >= 0);
-    const Shells* S = reinterpret_cast<const Shells*>(handle);
-    VS_CHECK_ARG(layer_first >= 0 && layer_count > 0 && layer_first + layer_count <= S->K);
+    Shells* S = const_cast<Shells*>(reinterpret_cast<const Shells*>(handle));
+    VS_CHECK_ARG(layer_first >= 0 && layer_count > 0 && layer_first + layer_count <= S->K && layer_count <= kTraceMaxLayers);
     if (n_rays == 0) return VS_OK;
     VS_CHECK_ARG(rays_o && rays_d && depth_out && tri_out && u_out && v_out);
-    dim3 grid((unsigned)div_up(n_rays, kRaysPerBlock), (unsigned)layer_count);
+    VS_CHECK_ARG(div_up(n_rays, 32) < 0x7fffff00);   // chunk numbers are ints (the counter runs a little past the last chunk)
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int64_t chunks = div_up(n_rays, 32);
+    const int ctas_per_layer = (int)std::max<int64_t>(1, std::min<int64_t>((sms * kTraceCtasPerSm + layer_count - 1) / layer_count,
+                                                                             div_up(chunks, kTraceThreads / 32)));
+    dim3 grid((unsigned)ctas_per_layer, (unsigned)layer_count);
+    int* work_counter = S->overflow_dev + 1 + (S->launches++ % kCounterSets) * kTraceMaxLayers;
+    if (cudaMemsetAsync(work_counter, 0, layer_count * sizeof(int), (cudaStream_t)stream) != cudaSuccess) return (int)cudaGetLastError();
     // traversal variants kept for A/B measurements (profiles/): 1 = default (per-entry pop, precomputed triangle edges/normal);
     // 0 = raw vertices; 2/3 = "while-while" traversal (measured slower on B200: 0.86 vs 0.72 ms on the C2 scene)
     static const int variant = getenv("VS_TRACE_VARIANT") ? atoi(getenv("VS_TRACE_VARIANT")) : 1;
 #define VS_TRACE(WW, PRE)                                                                                                               \
     shells_trace_kernel<WW, PRE><<<grid, kTraceThreads, 0, (cudaStream_t)stream>>>(S->layers_dev, layer_first, rays_o, rays_d, n_rays, \
-                                                                                    depth_out, tri_out, u_out, v_out, S->overflow_dev)
+                                                                                    depth_out, tri_out, u_out, v_out, S->overflow_dev,    \
+                                                                                    layer_count, work_counter)
     switch (variant) {
         case 0: VS_TRACE(false, false); break;
         case 2: VS_TRACE(true, false); break;
