@@ -208,13 +208,17 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
                                                                  const float* __restrict__ shift, const float* __restrict__ window,
                                                                  float* __restrict__ out, int out_cols, int64_t out_stride,
                                                                  uint8_t* __restrict__ oob_out, int64_t n, const int64_t* __restrict__ n_valid_dev) {
-    extern __shared__ float tile[];   // [cols][PM_PAD]
+    extern __shared__ __align__(128) float tile[];   // [cols][PM_PAD], or the tile's output rows as they lie in memory (bulk path)
     const int64_t n_eff = n_valid_dev ? min(n, *n_valid_dev) : n;
     const int64_t base = (int64_t)blockIdx.x * PM_TILE;
     if (base >= n_eff) return;
     const int p = threadIdx.x & (PM_TILE - 1), half = threadIdx.x >> 7;
     const int64_t idx = base + p;
     const bool valid = idx < n_eff;
+    // A full tile of densely packed rows leaves as ONE bulk copy: the threads write their columns where the row-major image wants them
+    // (row stride out_cols: odd strides are bank-conflict free) instead of a transposed tile that a second loop walks out to memory.
+    const bool bulk = out_stride == out_cols && base + PM_TILE <= n_eff && (reinterpret_cast<uintptr_t>(out + base * out_stride) & 15) == 0;
+    const int t_row = bulk ? out_cols : 1, t_col = bulk ? 1 : PM_PAD;   // tile[row * t_row + col * t_col]
 
     float pos[D];
     const bool oob = load_position<D>(a, positions, idx, valid, pos);
@@ -236,8 +240,8 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
             ax = ax + v[r].x * w;
             ay = ay + v[r].y * w;
         }
-        tile[(2 * lvl) * PM_PAD + p] = ax;
-        tile[(2 * lvl + 1) * PM_PAD + p] = ay;
+        if (2 * lvl < out_cols) tile[p * t_row + (2 * lvl) * t_col] = ax;
+        if (2 * lvl + 1 < out_cols) tile[p * t_row + (2 * lvl + 1) * t_col] = ay;
     }
     // concat-points levels (EncodingGPU.cuh:104-124): raw (normalised) coordinates, zero padded
     for (int e = half; e < a.n_extra; e += 2) {
@@ -248,8 +252,19 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
 #pragma unroll
             for (int k = 0; k < D; k++)
                 if (k == src) val = pos[k] * a.points_scaling;
-            tile[(2 * (a.n_levels + e) + i) * PM_PAD + p] = val;
+            const int c = 2 * (a.n_levels + e) + i;
+            if (c < out_cols) tile[p * t_row + c * t_col] = val;
         }
+    }
+    if (bulk) {
+        fence_proxy_async();   // the tile was written through the generic proxy, the bulk copy reads it through the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(out + base * out_stride, tile, (uint32_t)(PM_TILE * out_cols * sizeof(float)));
+            bulk_commit();
+            bulk_wait_read_all();   // shared memory must outlive the read
+        }
+        return;
     }
     __syncthreads();
     const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
@@ -282,7 +297,8 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
                                                                  const float* __restrict__ d_out, int in_cols, int64_t in_stride,
                                                                  float2* __restrict__ d_lattice, float* __restrict__ d_positions, int64_t n,
                                                                  const int64_t* __restrict__ n_valid_dev) {
-    extern __shared__ float tile[];   // [cols][PM_PAD] upstream gradient, then [D][PM_PAD] position gradient of the upper half
+    extern __shared__ __align__(128) float tile[];   // upstream gradient [cols][PM_PAD] (or row-major as in memory: bulk path), then [D][PM_PAD]
+    __shared__ __align__(8) uint64_t bar;
     const int64_t n_eff = n_valid_dev ? min(n, *n_valid_dev) : n;
     const int64_t base = (int64_t)blockIdx.x * PM_TILE;
     if (base >= n_eff) return;
@@ -290,6 +306,16 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
     int p = threadIdx.x & (PM_TILE - 1);   // row of the tile this thread works on
     const int rows = (int)min((int64_t)PM_TILE, n_eff - base);
     const int n_cols = 2 * a.n_levels;   // the concat-points columns pass no gradient (Encoding.cu:135-139,163)
+    // a full tile of densely packed gradient rows arrives as ONE bulk copy (row-major, read with the odd row stride in_cols) while the
+    // threads sort the tile / load their positions, instead of a transposing loop whose loads every thread waits for (16 % of all stall
+    // samples of the round-2 capture sat on that loop's stores)
+    const bool bulk = in_stride == in_cols && rows == PM_TILE && (reinterpret_cast<uintptr_t>(d_out + base * in_stride) & 15) == 0;
+    if (bulk && threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bar, (uint32_t)(PM_TILE * in_cols * sizeof(float)));
+        bulk_g2s(tile, d_out + base * in_stride, (uint32_t)(PM_TILE * in_cols * sizeof(float)), &bar);
+    }
     if (KEYED) {   // stable counting sort of the tile's rows by key (32 bins; rows beyond the end sort last)
         __shared__ int s_count[PM_TILE / 32][32];
         __shared__ unsigned char s_perm[PM_TILE];
@@ -331,7 +357,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
     const int64_t idx = base + p;
     const bool valid = idx < n_eff;
 
-    {   // flat walk, (r, c) advanced incrementally (see permuto_fwd_kernel)
+    if (!bulk) {   // flat walk, (r, c) advanced incrementally (see permuto_fwd_kernel)
         const int step_r = PM_THREADS / in_cols, step_c = PM_THREADS - step_r * in_cols;
         int r = threadIdx.x / in_cols, c = threadIdx.x - r * in_cols;
         for (int i = threadIdx.x; i < PM_TILE * in_cols; i += PM_THREADS) {
@@ -347,6 +373,8 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
     float pos[D];
     load_position<D>(a, positions, idx, valid, pos);
     __syncthreads();
+    if (bulk) mbar_wait(&bar, 0);
+    const int t_row = bulk ? in_cols : 1, t_col = bulk ? 1 : PM_PAD;   // tile[row * t_row + col * t_col]
 
     float d_pos[D];
 #pragma unroll
@@ -354,8 +382,8 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
 
     for (int lvl = half; lvl < a.n_levels; lvl += 2) {
         // columns beyond in_cols (a caller that dropped trailing columns, e.g. remove_last_element) carry zero gradient
-        const float gx = (2 * lvl < in_cols) ? tile[(2 * lvl) * PM_PAD + p] : 0.f;
-        const float gy = (2 * lvl + 1 < in_cols) ? tile[(2 * lvl + 1) * PM_PAD + p] : 0.f;
+        const float gx = (2 * lvl < in_cols) ? tile[p * t_row + (2 * lvl) * t_col] : 0.f;
+        const float gy = (2 * lvl + 1 < in_cols) ? tile[p * t_row + (2 * lvl + 1) * t_col] : 0.f;
         Simplex<D> s;
         locate<D>(pos, shift + lvl * D, scale + lvl * D, s);
         const float w_lvl = __ldg(window + lvl);
