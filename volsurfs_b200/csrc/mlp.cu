@@ -56,6 +56,36 @@ __global__ void mlp_pack_kernel(const float* __restrict__ W, const float* __rest
 // memory (16-byte stores, a warp covers 512 contiguous bytes) for the backward (layout: MlpStash).
 constexpr int kFwdThreads = kMlpThreads + 32;
 
+// Opt-in clock64 event trace of CTA 0's third and fourth tile pairs (scripts/trace_mlp_fwd.py, -DVS_KERNEL_TRACE; see mlp_bwd.cu)
+#ifdef VS_KERNEL_TRACE
+constexpr int kFwdTraceCap = 256;
+__device__ long long g_trace_fwd[2][2 * kFwdTraceCap];
+__device__ int g_trace_fwd_n[2];
+#define VS_TRF_DECL int tr_n_ = 0, tr_k_ = 0
+#define VS_TRF_NEXT ++tr_k_
+#define VS_TRF(who, id)                                                                  \
+    do {                                                                                 \
+        if (blockIdx.x == 0 && tr_k_ >= 2 && tr_k_ < 4 && tr_n_ < kFwdTraceCap) {        \
+            g_trace_fwd[who][2 * tr_n_] = (id);                                          \
+            g_trace_fwd[who][2 * tr_n_ + 1] = clock64();                                 \
+            ++tr_n_;                                                                     \
+        }                                                                                \
+    } while (0)
+#define VS_TRF_END(who)                                  \
+    do {                                                 \
+        if (blockIdx.x == 0) g_trace_fwd_n[who] = tr_n_; \
+    } while (0)
+#else
+#define VS_TRF_DECL ((void)0)
+#define VS_TRF_NEXT ((void)0)
+#define VS_TRF(who, id) ((void)0)
+#define VS_TRF_END(who) ((void)0)
+#endif
+#define VS_TRF_E(id)                  \
+    do {                              \
+        if (tid == 0) VS_TRF(1, id);  \
+    } while (0)
+
 template <int ACT, bool STASH>  // ACT: 0 ReLU, 1 GELU (compile-time: the epilogue loop carries no branch)
 __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_constant__ MlpConfig cfg_param,
                                                                  const __grid_constant__ MlpStash stash_param, const uint8_t* __restrict__ blob,
@@ -134,18 +164,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                     // its lines there instead of in DRAM
                     if ((tile + step + 1) * kTileM <= n) bulk_prefetch_l2(pos + (tile + step) * kTileM * F, (uint32_t)(kTileM * F * 4));
                 }
+                // the rows' directions / normals are read with plain loads at the top of build_a0: a DRAM miss there (queued behind this
+                // kernel's stash writes) is 2 - 3 k cycles on the tile's critical path; from L2 it is a few hundred
+                if (tile < n_tiles && (tile + 1) * kTileM <= n) {
+                    const float* dp = dirs + tile * kTileM * 3;
+                    const float* np = normals + tile * kTileM * 3;
+                    if (dirs != nullptr && (reinterpret_cast<uintptr_t>(dp) & 15) == 0) bulk_prefetch_l2(dp, (uint32_t)(kTileM * 12));
+                    if (normals != nullptr && (reinterpret_cast<uintptr_t>(np) & 15) == 0) bulk_prefetch_l2(np, (uint32_t)(kTileM * 12));
+                }
             };
             int64_t t[2] = {(int64_t)blockIdx.x, two ? (int64_t)blockIdx.x + stride : n_tiles};
             request_features(0, t[0]);
             request_features(1, t[1]);
             mbar_wait(&bar_w, 0);
             uint32_t par_ready[2] = {0, 0}, par_full[2] = {0, 0};
+            VS_TRF_DECL;
             while (t[0] < n_tiles) {
                 for (int l = 0; l < L; ++l) {
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
                         if (t[s] >= n_tiles) continue;
+                        VS_TRF(0, 100 + 10 * l + s);
                         mbar_wait(&bar_ready[s], par_ready[s]);  // every epilogue warp has written its part of the operand
+                        VS_TRF(0, 200 + 10 * l + s);
                         par_ready[s] ^= 1;
                         tc_fence_after();
                         const int K = cfg.k_pad[l], N = cfg.n_pad[l];
@@ -155,24 +196,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                         umma_gemm_f16(tmem_base + (uint32_t)(s * cfg.tmem_cols), a_base, a_lbo, 128, 2 * a_lbo, b_base, b_lbo, 128, 2 * b_lbo,
                                       umma_idesc_f16(kTileM, N), K / 16, false);
                         tc_commit(&bar_full[s]);  // arrives when the MMAs above have completed
+                        VS_TRF(0, 300 + 10 * l + s);
                         if (l == L - 1) {
                             // the (short) output-layer GEMM was the last reader of H: fetch the slot's next features under the
                             // other slot's epilogue
                             mbar_wait(&bar_full[s], par_full[s]);
                             request_features(s, t[s] + step);
+                            VS_TRF(0, 400 + s);
                         }
                         par_full[s] ^= 1;
                     }
                 }
                 t[0] += step;
                 if (two) t[1] += step;
+                VS_TRF_NEXT;
             }
+            VS_TRF_END(0);
         }
     } else {
         // ================= epilogue warps =================
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
         uint32_t par_in[2] = {0, 0}, par_full[2] = {0, 0};
         float decay[2] = {1.f, 1.f};  // alpha decay of this thread's row (used by the row's cg == 0 thread in the output epilogue)
+        VS_TRF_DECL;
 
         auto announce = [&](int s) {  // this warp's writes to the slot's next operand are done
             fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -201,10 +247,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                     nz = __ldg(normals + 3 * r + 2);
                 }
             }
+            VS_TRF_E(10 + s);
             if (full && F > 0) {
                 mbar_wait(&bar_in[s], par_in[s]);
                 par_in[s] ^= 1;
             }
+            VS_TRF_E(20 + s);
             const float* srow = full ? reinterpret_cast<const float*>(slot_h(s)) + row * F : pos + r * F;
             __half* a0 = slot_a0(s);
             uint8_t* st_a0 = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[0] : nullptr;
@@ -230,46 +278,57 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                 }
             }
             // row -> fp16 A operand (K-major core matrices): chunk kc of row r at (kc*128 + r) * 16 bytes.  Pure feature chunks are
-            // split over column groups 1..3 (no per-element decisions on a full tile), the tail chunks go to column group 0.
-            if (cg != 0 && full) {
-                for (int kc = cg - 1; kc < tail0; kc += 3) {
-                    const float* sp = srow + kc * 8;
-                    __half2 h[4];
+            // split over column groups 1..3 (no per-element decisions on a full tile) while column group 0 evaluates the row's SH /
+            // normal columns into its scratch row; then the four warps that share these 32 rows meet on a named barrier and the tail
+            // chunks (features' last columns, SH, normal, padding: a per-element select each) are split over all four column groups.
+            // (One column group doing the whole tail was 3 - 4 k cycles per tile with the other twelve warps and the tensor core
+            // waiting: clock64 trace, round 2.)
+            auto tail_chunk = [&](int kc) {
+                __half2 h[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(sp[2 * j], sp[2 * j + 1]);
-                    const uint4 pk = *reinterpret_cast<const uint4*>(h);
-                    *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
-                    if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
-                }
-            } else {
-                const int kc_begin = cg == 0 ? tail0 : cg - 1, kc_end = cg == 0 ? k0 / 8 : tail0, kc_step = cg == 0 ? 1 : 3;
-                for (int kc = kc_begin; kc < kc_end; kc += kc_step) {
-                    __half2 h[4];
+                for (int j = 0; j < 4; ++j) {
+                    float v2[2];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v2[2];
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int c = kc * 8 + 2 * j + q;
-                            float v = 0.f;
-                            if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
-                            v2[q] = v;
-                        }
-                        h[j] = __floats2half2_rn(v2[0], v2[1]);
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = kc * 8 + 2 * j + q;
+                        float v = 0.f;
+                        if (live && c < in_dim) v = c < F ? srow[c] : ex[c - F];
+                        v2[q] = v;
                     }
-                    const uint4 pk = *reinterpret_cast<const uint4*>(h);
-                    *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
-                    if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+                    h[j] = __floats2half2_rn(v2[0], v2[1]);
+                }
+                const uint4 pk = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
+                if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+            };
+            if (cg != 0) {
+                if (full) {
+                    for (int kc = cg - 1; kc < tail0; kc += 3) {
+                        const float* sp = srow + kc * 8;
+                        __half2 h[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(sp[2 * j], sp[2 * j + 1]);
+                        const uint4 pk = *reinterpret_cast<const uint4*>(h);
+                        *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
+                        if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
+                    }
+                } else {
+                    for (int kc = cg - 1; kc < tail0; kc += 3) tail_chunk(kc);
                 }
             }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(4 * 32) : "memory");  // the row group's scratch rows are written
+            for (int kc = tail0 + ((cg + 3) & 3); kc < k0 / 8; kc += 4) tail_chunk(kc);
             if (STASH && stash_cfg.fold[0] && cg == 1)  // the "ones" chunk behind A_0 (bias gradient row of the backward's dW GEMM)
                 *reinterpret_cast<uint4*>(st_a0 + ((size_t)(k0 / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
             announce(s);
+            VS_TRF_E(30 + s);
         };
 
         // layer l of slot s has landed in TMEM: bias + activation -> next operand (hidden) or sigmoid -> out (last layer)
         auto epilogue = [&](int s, int l, int64_t tile) {
+            VS_TRF_E(100 + 10 * l + s);
             mbar_wait(&bar_full[s], par_full[s]);
+            VS_TRF_E(200 + 10 * l + s);
             par_full[s] ^= 1;
             tc_fence_after();
             const int N = cfg.n_pad[l];
@@ -307,6 +366,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                     }
                 }
                 announce(s);
+                VS_TRF_E(300 + 10 * l + s);
             } else if (cg * 16 < N) {  // output layer: N is 16 (sigmoid heads, <= 8 outputs) or up to 32 (linear texture nets)
                 const int c0 = cg * 16;
                 float v[16];
@@ -337,7 +397,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
             }
             tA += step;
             if (two) tB += step;
+            VS_TRF_E(900);
+            VS_TRF_NEXT;
         }
+        if (tid == 0) VS_TRF_END(1);
     }
 
     tc_fence_before();
@@ -355,6 +418,15 @@ static size_t mlp_smem_bytes(const MlpConfig& c) {
 using namespace vs;
 
 extern "C" {
+
+#ifdef VS_KERNEL_TRACE
+int vs_debug_trace_fwd(long long* out_host, int* n_host) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out_host, g_trace_fwd, sizeof(g_trace_fwd));
+    cudaMemcpyFromSymbol(n_host, g_trace_fwd_n, sizeof(g_trace_fwd_n));
+    return 0;
+}
+#endif
 
 // bytes of the packed weight blob for an MLP with dims = [in, h1, ..., out] (n_layers + 1 entries); < 0 on error
 int64_t vs_mlp_blob_bytes(int n_layers, const int* dims) {
