@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
         // ================= epilogue warps =================
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
         uint32_t par_in[2] = {0, 0}, par_full[2] = {0, 0};
-        float decay[2] = {1.f, 1.f};  // alpha decay of this thread's row (used by the row's cg == 0 thread in the output epilogue)
+        // Slot s's row specials (SH / normal columns and alpha decay in build_a0, the sigmoid outputs in the last epilogue) belong to
+        // column group s: the two slots' serial single-column-group stretches run side by side instead of queueing on column group 0.
+        float decay[2] = {1.f, 1.f};  // alpha decay of this thread's row (held by the row's owner thread of the slot)
         VS_TRF_DECL;
 
         auto announce = [&](int s) {  // this warp's writes to the slot's next operand are done
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
             const bool live = row < rows;
             // directions / normals of the row come straight from global memory: in flight while the feature tile lands
             float dx = 0.f, dy = 0.f, dz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-            if (cg == 0 && live) {
+            const int q = (cg - s + 3) & 3;  // 3: the slot's owner column group; 0..2: the others in turn
+            if (q == 3 && live) {
                 if (dirs != nullptr) {
                     dx = __ldg(dirs + 3 * r);
                     dy = __ldg(dirs + 3 * r + 1);
@@ -257,9 +260,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
             __half* a0 = slot_a0(s);
             uint8_t* st_a0 = STASH ? stash + tile * (int64_t)stash_cfg.tile_bytes + stash_cfg.a_off[0] : nullptr;
             const int in_dim = cfg.in_dim;
-            const int tail0 = F / 8;  // first chunk that holds SH / normal / padding columns: those belong to the row's cg == 0 thread
+            const int tail0 = F / 8;  // first chunk that holds SH / normal / padding columns
             float* ex = slot_extra(s) + row * kExtraStride;
-            if (cg == 0) {
+            if (q == 3) {
                 decay[s] = 1.f;
                 if (cfg.alpha_decay) {
                     const float dot = fminf(fmaxf(-(dx * nx + dy * ny + dz * nz), 0.f), 1.f);
@@ -301,9 +304,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                 *reinterpret_cast<uint4*>(a0 + ((size_t)kc * kTileM + row) * 8) = pk;
                 if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
             };
-            if (cg != 0) {
+            if (q != 3) {
                 if (full) {
-                    for (int kc = cg - 1; kc < tail0; kc += 3) {
+                    for (int kc = q; kc < tail0; kc += 3) {
                         const float* sp = srow + kc * 8;
                         __half2 h[4];
 #pragma unroll
@@ -313,11 +316,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                         if (STASH) *reinterpret_cast<uint4*>(st_a0 + ((size_t)kc * kTileM + row) * 16) = pk;
                     }
                 } else {
-                    for (int kc = cg - 1; kc < tail0; kc += 3) tail_chunk(kc);
+                    for (int kc = q; kc < tail0; kc += 3) tail_chunk(kc);
                 }
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(4 * 32) : "memory");  // the row group's scratch rows are written
-            for (int kc = tail0 + ((cg + 3) & 3); kc < k0 / 8; kc += 4) tail_chunk(kc);
+            for (int kc = tail0 + q; kc < k0 / 8; kc += 4) tail_chunk(kc);
             if (STASH && stash_cfg.fold[0] && cg == 1)  // the "ones" chunk behind A_0 (bias gradient row of the backward's dW GEMM)
                 *reinterpret_cast<uint4*>(st_a0 + ((size_t)(k0 / 8) * kTileM + row) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
             announce(s);
@@ -367,8 +370,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
                 }
                 announce(s);
                 VS_TRF_E(300 + 10 * l + s);
-            } else if (cg * 16 < N) {  // output layer: N is 16 (sigmoid heads, <= 8 outputs) or up to 32 (linear texture nets)
-                const int c0 = cg * 16;
+            } else if (cfg.out_linear ? cg * 16 < N : cg == s) {  // output layer: N is 16 (sigmoid heads, <= 8 outputs: the slot's owner
+                                                                    // column group) or up to 32 (linear texture nets: 16 columns per group)
+                const int c0 = cfg.out_linear ? cg * 16 : 0;
                 float v[16];
                 tmem_ld16(tmem_lane + (uint32_t)c0, v);
                 if (r < n) {
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c0 + j < cfg.out_dim) out[r * cfg.out_dim + c0 + j] = v[j] + bias[c0 + j];
-                    } else if (cg == 0) {
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (j < cfg.out_dim) out[r * cfg.out_dim + j] = sigmoid_f(v[j] + bias[j]) * decay[s];
