@@ -146,8 +146,10 @@ __device__ __forceinline__ HashBase<D> hash_base(const Simplex<D>& s) {
     h.base = k;
     return h;
 }
-template <int D>
-__device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, const HashBase<D>& h, int remainder, uint32_t capacity, int pow2) {
+// POW2 is a template parameter: as a run-time flag both reductions were compiled in, and the general 32-bit modulo was a quarter of the
+// forward kernel's instructions (23 per vertex, ncu source page, round 2) although every table of the benchmark is 2^18 entries
+template <int D, bool POW2>
+__device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, const HashBase<D>& h, int remainder, uint32_t capacity) {
     uint32_t sum_pow = 0;
 #pragma unroll
     for (int i = 0; i < D; i++) sum_pow += hash_pow<D>(D - i);
@@ -155,7 +157,7 @@ __device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, const HashB
 #pragma unroll
     for (int i = 0; i < D; i++)
         if (s.rank[i] + remainder > D) k -= (uint32_t)(D + 1) * hash_pow<D>(D - i);
-    return pow2 ? (k & (capacity - 1u)) : (k % capacity);
+    return POW2 ? (k & (capacity - 1u)) : (k % capacity);
 }
 
 template <int D>
@@ -202,7 +204,7 @@ __device__ __forceinline__ void red_add_runs(float2* table, uint32_t slot, float
     if (head && valid) red_add_f32x2(table + slot, x, y);
 }
 
-template <int D>
+template <int D, bool POW2>
 __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, const float* __restrict__ positions,
                                                                  const float2* __restrict__ lattice, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, const float* __restrict__ window,
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
         const HashBase<D> hb = hash_base<D>(s);
         float2 v[D + 1];
 #pragma unroll
-        for (int r = 0; r <= D; r++) v[r] = __ldg(table + vertex_slot<D>(s, hb, r, a.capacity, a.pow2));
+        for (int r = 0; r <= D; r++) v[r] = __ldg(table + vertex_slot<D, POW2>(s, hb, r, a.capacity));
         float ax = 0.f, ay = 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
 // one vertex: in a packed K-layer ray packet adjacent samples are the K hits of one ray, while the samples that share vertices on the
 // mid and fine levels are the same layer's hits of the neighbouring rays, K lanes apart.  With key = layer they become neighbours
 // (B200, 893 k hits of the 5-shell benchmark scene: 0.604 ms in packed order, 0.416 ms layer-major, 1.33 ms shuffled).
-template <int D, bool DPOS, bool KEYED>
+template <int D, bool DPOS, bool KEYED, bool POW2>
 __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, const float* __restrict__ positions,
                                                                  const int* __restrict__ order_key,
                                                                  const float2* __restrict__ lattice, const float* __restrict__ scale,
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
         const HashBase<D> hb = hash_base<D>(s);
         uint32_t slot[D + 1];
 #pragma unroll
-        for (int r = 0; r <= D; r++) slot[r] = vertex_slot<D>(s, hb, r, a.capacity, a.pow2);
+        for (int r = 0; r <= D; r++) slot[r] = vertex_slot<D, POW2>(s, hb, r, a.capacity);
         if (d_lattice) {
             float2* table = d_lattice + (size_t)lvl * a.capacity;
 #pragma unroll
@@ -507,16 +509,23 @@ int vs_permuto_forward(int pos_dim, int n_levels, int64_t capacity, int concat_p
     const dim3 grid((unsigned)div_up(n, PM_TILE));
     const size_t smem = (size_t)cols * PM_PAD * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-#define VS_PM_FWD(D)                                                                                                                       \
-    permuto_fwd_kernel<D><<<grid, PM_THREADS, smem, st>>>(a, positions, (const float2*)lattice, scale, shift, window, out, out_cols,       \
-                                                           out_stride, out_of_bounds, n, n_valid_dev)
-    if (pos_dim == 2)
+#define VS_PM_FWD_(D, POW2)                                                                                                                \
+    permuto_fwd_kernel<D, POW2><<<grid, PM_THREADS, smem, st>>>(a, positions, (const float2*)lattice, scale, shift, window, out, out_cols, \
+                                                                 out_stride, out_of_bounds, n, n_valid_dev)
+#define VS_PM_FWD(D)           \
+    if (a.pow2)                \
+        VS_PM_FWD_(D, true);   \
+    else                       \
+        VS_PM_FWD_(D, false)
+    if (pos_dim == 2) {
         VS_PM_FWD(2);
-    else if (pos_dim == 3)
+    } else if (pos_dim == 3) {
         VS_PM_FWD(3);
-    else
+    } else {
         VS_PM_FWD(4);
+    }
 #undef VS_PM_FWD
+#undef VS_PM_FWD_
     return launched(1);
 }
 
@@ -535,19 +544,25 @@ int vs_permuto_backward_keyed(int pos_dim, int n_levels, int64_t capacity, int c
     const dim3 grid((unsigned)div_up(n, PM_TILE));
     const size_t smem = (size_t)cols * PM_PAD * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-#define VS_PM_BWD_(D, DPOS, KEYED)                                                                                                         \
-    permuto_bwd_kernel<D, DPOS, KEYED><<<grid, PM_THREADS, smem, st>>>(a, positions, order_key, (const float2*)lattice, scale, shift,      \
-                                                                        window, d_out, in_cols, in_stride, (float2*)d_lattice,             \
-                                                                        d_positions, n, n_valid_dev)
+#define VS_PM_BWD__(D, DPOS, KEYED, POW2)                                                                                                  \
+    permuto_bwd_kernel<D, DPOS, KEYED, POW2><<<grid, PM_THREADS, smem, st>>>(a, positions, order_key, (const float2*)lattice, scale,       \
+                                                                              shift, window, d_out, in_cols, in_stride,                    \
+                                                                              (float2*)d_lattice, d_positions, n, n_valid_dev)
+#define VS_PM_BWD_(D, DPOS, KEYED)           \
+    if (a.pow2)                              \
+        VS_PM_BWD__(D, DPOS, KEYED, true);   \
+    else                                     \
+        VS_PM_BWD__(D, DPOS, KEYED, false)
 #define VS_PM_BWD(D)                      \
-    if (d_positions && order_key)         \
+    if (d_positions && order_key) {       \
         VS_PM_BWD_(D, true, true);        \
-    else if (d_positions)                 \
+    } else if (d_positions) {             \
         VS_PM_BWD_(D, true, false);       \
-    else if (order_key)                   \
+    } else if (order_key) {               \
         VS_PM_BWD_(D, false, true);       \
-    else                                  \
-        VS_PM_BWD_(D, false, false)
+    } else {                              \
+        VS_PM_BWD_(D, false, false);      \
+    }
     if (pos_dim == 2) {
         VS_PM_BWD(2);
     } else if (pos_dim == 3) {
@@ -557,6 +572,7 @@ int vs_permuto_backward_keyed(int pos_dim, int n_levels, int64_t capacity, int c
     }
 #undef VS_PM_BWD
 #undef VS_PM_BWD_
+#undef VS_PM_BWD__
     return launched(1);
 }
 
