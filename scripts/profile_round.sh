@@ -17,6 +17,7 @@ $NCU -k regex:composite_bwd_ring -s 1 -c 1 -o $OUT/prof_r02_composite_bwd_ring p
 $NCU -k regex:mlp_fwd -s 2 -c 1 -o $OUT/prof_r02_mlp_fwd python scripts/profile_heads.py > /dev/null 2>&1
 $NCU -k regex:mlp_bwd_stashed -s 1 -c 1 -o $OUT/prof_r02_mlp_bwd python scripts/profile_heads.py > /dev/null 2>&1
 $NCU -k regex:shells_trace -s 3 -c 1 -o $OUT/prof_r02_shells_trace python scripts/bench_trace.py > /dev/null 2>&1
-$NCU -k regex:permuto_fwd -s 3 -c 1 -o $OUT/prof_r02_permuto_fwd python scripts/bench_permuto.py 892741 3 rays > /dev/null 2>&1
-$NCU -k regex:permuto_bwd -s 3 -c 1 -o $OUT/prof_r02_permuto_bwd python scripts/bench_permuto.py 892741 3 rays > /dev/null 2>&1
+# encoder kernels on the benchmark's real hit points (packed order; the backward with key = samples_layer as the step calls it)
+$NCU -k regex:permuto_fwd -s 3 -c 1 -o $OUT/prof_r02_permuto_fwd python scripts/bench_permuto_hits.py > /dev/null 2>&1
+$NCU -k regex:permuto_bwd -s 45 -c 1 -o $OUT/prof_r02_permuto_bwd python scripts/bench_permuto_hits.py > /dev/null 2>&1
 ls -la $OUT/*.ncu-rep $OUT/r02_launches_step.csv

@@ -146,18 +146,30 @@ __device__ __forceinline__ HashBase<D> hash_base(const Simplex<D>& s) {
     h.base = k;
     return h;
 }
+// All D+1 slots of a simplex.  From remainder r-1 to r the sum gains sum_i M^(D-i) and loses (D+1) M^(D-i) for the ONE coordinate whose
+// rank is D+1-r (rank is a permutation; nothing if that coordinate is the last one, which the hash does not read): two adds per vertex
+// after a select chain over the ranks, instead of D compare-and-subtract steps per vertex.  Same uint32 ring arithmetic, same bits.
 // POW2 is a template parameter: as a run-time flag both reductions were compiled in, and the general 32-bit modulo was a quarter of the
-// forward kernel's instructions (23 per vertex, ncu source page, round 2) although every table of the benchmark is 2^18 entries
+// forward kernel's instructions (23 per vertex, ncu source page, round 2) although every table of the benchmark is 2^18 entries.
 template <int D, bool POW2>
-__device__ __forceinline__ uint32_t vertex_slot(const Simplex<D>& s, const HashBase<D>& h, int remainder, uint32_t capacity) {
+__device__ __forceinline__ void vertex_slots(const Simplex<D>& s, const HashBase<D>& h, uint32_t capacity, uint32_t (&slot)[D + 1]) {
     uint32_t sum_pow = 0;
 #pragma unroll
     for (int i = 0; i < D; i++) sum_pow += hash_pow<D>(D - i);
-    uint32_t k = h.base + (uint32_t)remainder * sum_pow;
+    uint32_t lose[D + 1];   // by rank
 #pragma unroll
-    for (int i = 0; i < D; i++)
-        if (s.rank[i] + remainder > D) k -= (uint32_t)(D + 1) * hash_pow<D>(D - i);
-    return POW2 ? (k & (capacity - 1u)) : (k % capacity);
+    for (int k = 0; k <= D; k++) {
+        uint32_t c = 0u;
+#pragma unroll
+        for (int i = 0; i < D; i++) c = (s.rank[i] == k) ? (uint32_t)(D + 1) * hash_pow<D>(D - i) : c;
+        lose[k] = c;
+    }
+    uint32_t k = h.base;
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        if (r > 0) k += sum_pow - lose[D + 1 - r];
+        slot[r] = POW2 ? (k & (capacity - 1u)) : (k % capacity);
+    }
 }
 
 template <int D>
@@ -232,9 +244,11 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_fwd_kernel(PermutoArgs a, 
         const float w_lvl = __ldg(window + lvl);
         const float2* table = lattice + (size_t)lvl * a.capacity;
         const HashBase<D> hb = hash_base<D>(s);
+        uint32_t slot[D + 1];
+        vertex_slots<D, POW2>(s, hb, a.capacity, slot);
         float2 v[D + 1];
 #pragma unroll
-        for (int r = 0; r <= D; r++) v[r] = __ldg(table + vertex_slot<D, POW2>(s, hb, r, a.capacity));
+        for (int r = 0; r <= D; r++) v[r] = __ldg(table + slot[r]);
         float ax = 0.f, ay = 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
@@ -391,8 +405,7 @@ __global__ void __launch_bounds__(PM_THREADS) permuto_bwd_kernel(PermutoArgs a, 
         const float w_lvl = __ldg(window + lvl);
         const HashBase<D> hb = hash_base<D>(s);
         uint32_t slot[D + 1];
-#pragma unroll
-        for (int r = 0; r <= D; r++) slot[r] = vertex_slot<D, POW2>(s, hb, r, a.capacity);
+        vertex_slots<D, POW2>(s, hb, a.capacity, slot);
         if (d_lattice) {
             float2* table = d_lattice + (size_t)lvl * a.capacity;
 #pragma unroll
