@@ -90,6 +90,17 @@ for name, nbytes, prod, refk in OPS:
         if ref is not None:
             ms_r = timed(refk)
             row["reference_kernel_ms"], row["speedup"] = round(ms_r, 4), round(ms_r / ms, 2)
+        if name == "median_depth_over_rays":
+            # like for like with the reference arm (its kernel alone): the product's entry point on a preallocated, pre-zeroed output --
+            # on a 40 us operator the public call's allocation + zero fill is a quarter of the time
+            from volsurfs_b200 import _lib
+            o_k = torch.zeros(n, 1, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            ms_k = timed(lambda: _lib.check(_lib.lib().vs_median_depth(se.data_ptr(), rsp.samples_z.data_ptr(), w.data_ptr(), 0.5,
+                                                                         o_k.data_ptr(), n, S, 0, st), "vs_median_depth"))
+            row["product_kernel_ms"] = round(ms_k, 4)
+            if ref is not None:
+                row["speedup_kernel_only"] = round(ms_r / ms_k, 2)
     except Exception as e:  # one op failing must not hide the others
         row["error"] = repr(e)[:200]
     print(json.dumps(row), flush=True)

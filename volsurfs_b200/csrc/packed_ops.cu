@@ -353,9 +353,26 @@ __global__ void __launch_bounds__(kThreads) median_depth_kernel(const int32_t* _
     int start;
     const int n = load_segment(se, ray, start);
     if (n == 0) return;  // output keeps its zero initialisation
+    // the running sum is the reference's (one fp32 add per sample, in order); the loads of the next eight weights do not depend on it and
+    // are issued together, so the thread pays one memory latency per eight samples instead of one per sample
+    const float* __restrict__ wr = w + start;
     float run = 0.f;
-    for (int i = 0; i < n; ++i) {
-        run = __fadd_rn(run, w[(int64_t)start + i]);
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = __ldg(wr + i + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            run = __fadd_rn(run, wv[j]);
+            if (run >= threshold) {
+                out[ray] = z[(int64_t)start + i + j];
+                return;
+            }
+        }
+    }
+    for (; i < n; ++i) {
+        run = __fadd_rn(run, __ldg(wr + i));
         if (run >= threshold) {
             out[ray] = z[(int64_t)start + i];
             return;
@@ -373,11 +390,26 @@ __global__ void __launch_bounds__(kThreads) compute_cdf_kernel(const int32_t* __
     int start;
     const int n = load_segment(se, ray, start);
     if (n < 2) return;
+    // the reference's running sum (one fp32 add per sample, in order); eight weights are loaded together ahead of the adds
+    const float* __restrict__ wr = w + start;
+    float* __restrict__ cr = cdf + start;
     float run = 0.f, last = 0.f;
-    for (int i = 0; i < n; ++i) {
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = __ldg(wr + i + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            last = run;
+            cr[i + j] = run;
+            run = __fadd_rn(run, wv[j]);
+        }
+    }
+    for (; i < n; ++i) {
         last = run;
-        cdf[(int64_t)start + i] = run;
-        run = __fadd_rn(run, w[(int64_t)start + i]);
+        cr[i] = run;
+        run = __fadd_rn(run, __ldg(wr + i));
     }
     if (fabs((double)run - 1.0) < 1e-3 && fabs((double)last - 1.0) > 1e-3) cdf[(int64_t)start + n - 1] = 1.0f;
 }
