@@ -42,13 +42,13 @@ HIDDEN = (128, 128, 64)
 POS_DIM = 51
 CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/base_5.cfg:8)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of this workload at HEAD (profiles/r02_*.md)
-NCU_TRAFFIC = {"mlp_fwd_kernel": 204.150272e6 + 696.295936e6,            # profiles/r02_mlp_fwd.md
-               "mlp_bwd_stashed_kernel": 764.377344e6 + 169.448704e6,    # profiles/r02_mlp_bwd.md
-               "shells_trace_kernel": 43.836416e6 + 20.213248e6,         # profiles/r02_shells_trace.md
-               "permuto_fwd_kernel": 33.416960e6 + 131.241472e6,         # profiles/r02_permuto_fwd.md
-               "permuto_bwd_kernel": 238.130432e6 + 14.766592e6,         # profiles/r02_permuto_bwd.md
+NCU_TRAFFIC = {"mlp_fwd_kernel": 204.320000e6 + 693.690368e6,            # profiles/r02_mlp_fwd.md
+               "mlp_bwd_stashed_kernel": 764.562432e6 + 169.221120e6,    # profiles/r02_mlp_bwd.md
+               "shells_trace_kernel": 46.952192e6 + 20.749056e6,         # profiles/r02_shells_trace.md
+               "permuto_fwd_kernel": 31.724800e6 + 133.739264e6,         # profiles/r02_permuto_fwd.md
+               "permuto_bwd_kernel": 214.678784e6 + 8.321536e6,          # profiles/r02_permuto_bwd.md
                # composite_fwd_tile_kernel<1> + composite_bwd_tile_kernel<1> at 2^24 rays x 5 (algorithmic: 5.77 GB)
-               "composite_tile_fwd+bwd": 1.811964e9 + 389.046272e6 + 2.214682e9 + 1.307265e9}   # profiles/r02_composite_{fwd,bwd}_tile.md
+               "composite_tile_fwd+bwd": 1.812154e9 + 389.939712e6 + 2.214624e9 + 1.307345e9}   # profiles/r02_composite_{fwd,bwd}_tile.md
 
 
 _JSON_FD = None

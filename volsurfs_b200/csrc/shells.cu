@@ -11,9 +11,9 @@
 //   * one launch covers all (layer, ray) pairs with persistent CTAs (kTraceCtasPerSm per SM, split over the layers): every WARP draws
 //     its next 32 consecutive rays from the layer's work counter, so a warp whose rays miss everything is not parked until the slowest
 //     warp of its CTA is done (B200, C2 scene: 0.695 ms with a static 512-rays-per-CTA mapping, achieved occupancy 33 % of a 50 %
-//     limit -> 0.616 ms); a CTA whose layer has run dry moves on to the next layer that still has work;
+//     limit -> 0.616 ms); a warp whose layer has run dry moves on to the layers that still have work;
 //   * the top of the layer's tree (first kTopNodes nodes = 4 levels) is staged into shared memory by one TMA bulk copy
-//     (cp.async.bulk + mbarrier) when a CTA takes up a layer, so the always-visited upper levels never leave the SM;
+//     (cp.async.bulk + mbarrier) when the CTA starts, so the always-visited upper levels never leave the SM;
 //   * triangles are 3 x float4 (vertex + original face index), read with 16-byte loads.
 //
 // Parity contract (bit-exact hits, pinned by the reference's own kernel): the ray/triangle arithmetic is the reference's
@@ -371,24 +371,23 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                                                                      int* __restrict__ work_counter) {
     __shared__ __align__(128) Node4 s_top[kTopNodes];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_dry;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    uint32_t n_staged = 0;
-    // the CTA's own layer first, then (once that one has run dry) the others in turn
+    const Layer L0 = layers[layer_first + blockIdx.y];
+    const int n_top0 = min(L0.n_nodes, kTopNodes);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bar, (uint32_t)(n_top0 * sizeof(Node4)));
+        bulk_g2s(s_top, L0.nodes, (uint32_t)(n_top0 * sizeof(Node4)), &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // the CTA's own layer first, its top levels in shared memory; a WARP whose layer has run dry moves on to the others by itself (their
+    // top levels then come through L1 like the rest of the tree): no block-wide hand-over, nobody waits for a neighbour's last chunk
     for (int a = 0; a < layer_count; ++a) {
     const int li = (int)((blockIdx.y + a) % layer_count);
-    __syncthreads();   // every warp is done with the previous layer's s_top (and the barrier is initialised)
-    if (threadIdx.x == 0) s_dry = (int64_t)(*reinterpret_cast<volatile int*>(work_counter + li)) * 32 >= n_rays;
-    __syncthreads();
-    if (s_dry) continue;
+    if (a > 0 && (int64_t)(*reinterpret_cast<volatile int*>(work_counter + li)) * 32 >= n_rays) continue;
     const Layer L = layers[layer_first + li];
-    const int n_top = min(L.n_nodes, kTopNodes);
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bar, (uint32_t)(n_top * sizeof(Node4)));
-        bulk_g2s(s_top, L.nodes, (uint32_t)(n_top * sizeof(Node4)), &bar);
-    }
-    mbar_wait(&bar, n_staged & 1u);
-    ++n_staged;
+    const int n_top = a == 0 ? n_top0 : 0;
 
     const Node4* __restrict__ gnodes = L.nodes;
     const float4* __restrict__ pre = L.pre;
