@@ -150,7 +150,10 @@ int vs_shells_overflowed(const void* handle);
 
 /* Nearest hit (t > 0, first along the ray) with layers [layer_first, layer_first+layer_count) in one launch.
  * Outputs layer-major [layer_count, n_rays]: depth (1e6 on a miss, include/raytracing/common.h:21), original face index
- * (-1 on a miss), barycentric u and v of triangle.cuh:53-55 (0 on a miss). */
+ * (-1 on a miss), barycentric u and v of triangle.cuh:53-55 (0 on a miss).
+ * layer_count <= 64.  The launch uses a small set of per-layer work counters owned by the handle (eight sets, handed out in turn and
+ * cleared by a memset node on `stream` in front of the kernel): launches on different streams may overlap, and the call can be captured
+ * into a CUDA graph (a graph keeps the set it was captured with). */
 int vs_shells_trace(const void* handle, const float* rays_o, const float* rays_d, int64_t n_rays, int layer_first, int layer_count,
                     float* depth_out, int32_t* tri_out, float* u_out, float* v_out, void* stream);
 

@@ -157,7 +157,8 @@ def test_container_accessors_match_reference_semantics():
         rsp.set_samples_values(torch.zeros(rsp.get_max_nr_samples(), 3).cuda())
 
 
-@pytest.mark.parametrize("n_rays,K", [(4096, 5), (1000, 9), (33, 1), (100000, 5)])
+# K <= 16: the shared-memory staged scatter; K = 20: the thread-per-ray scatter it falls back to
+@pytest.mark.parametrize("n_rays,K", [(4096, 5), (1000, 9), (33, 1), (100000, 5), (777, 16), (500, 20)])
 def test_pack_layer_hits_bit_exact(n_rays, K):
     from volsurfs_b200.raytracer import pack_layer_hits as pack_gpu
 
