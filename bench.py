@@ -414,13 +414,12 @@ def run_ours(args, rank, world, local_rank):
         alpha, _ = heads["alpha"].forward_train(feats["alpha"], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev,
                                                 stash=stash["alpha"])
         mark(7)
-        out = renderer.composite(rsp, alpha, rgb)
+        rgb_fg, depth, acc, bgT = VR.composite(rsp, alpha, rgb, rsp.samples_z)
         mark(8)
-        diff = out["rgb"] - gt
-        loss = diff.abs().mean()
-        g_pred = torch.sign(diff) / diff.numel()
+        pred, loss, g_pred, g_bgT = renderer.blend_l1(rgb_fg, bgT, gt)   # background blend + L1 loss + its gradient: one launch
+        out = {"rgb": pred, "rgb_fg": rgb_fg, "depth": depth, "acc": acc, "bg_transmittance": bgT}
         mark(9)
-        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred)
+        d_alpha, d_rgb = renderer.composite_backward(rsp, alpha, rgb, g_pred, g_bgT)
         mark(10)
         fwd_out, d_out = {"rgb": rgb, "alpha": alpha}, {"rgb": d_rgb, "alpha": d_alpha}
         for i, k in enumerate(("rgb", "alpha")):

@@ -377,6 +377,16 @@ int vs_baked_texture_shade(const uint8_t* is_hit, const int64_t* tri_id, const f
                            float* o_hit, float* o_normals, float* o_uvs, float* o_rgb, float* o_alpha, float* o_dirs, int64_t n_rays,
                            void* stream);
 
+/* ---- training tail of the per-ray path: background blend + L1 loss + its gradient in one launch ------------------------------------
+ * Replaces the torch glue between the compositing forward and backward of a training step: pred = rgb_fg + bgT * bg
+ * (volsurfs_py/methods/volsurfs.py:708), loss = (gt - pred).abs().mean() (volsurfs_py/utils/losses.py:14-19 as called at
+ * volsurfs.py:804-806 without a mask) and what autograd returns for them: g_pred = sign(pred - gt) / numel, g_bgT = sum_c g_pred_c bg_c.
+ * rgb_fg, gt, pred, g_pred [n,3]; bgT, g_bgT [n,1]; bg_rgb: HOST float[3]; loss: one device float; scratch: 16 bytes of device memory,
+ * zero before the first call (the kernel leaves it zero), not shared between calls that may run concurrently.  The mean is accumulated in
+ * fixed point with integer atomics: its value does not depend on the order the blocks finish in (a replayed CUDA graph returns the same bits). */
+int vs_blend_l1_loss(const float* rgb_fg, const float* bgT, const float* gt, const float* bg_rgb, float* pred, float* g_pred, float* g_bgT,
+                     float* loss, void* scratch, int64_t n_rays, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

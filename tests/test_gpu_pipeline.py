@@ -163,3 +163,37 @@ def test_full_path_outputs_and_gradients_vs_oracle_chain():
     assert errs["grad_rgb"] < 1e-2 and errs["grad_alpha"] < 1e-2, errs
     assert errs["d_features_rgb"] < 5e-2 and errs["d_features_alpha"] < 5e-2, errs
     assert all(v < 5e-3 for v in rms.values()), rms
+
+
+@pytest.mark.parametrize("n", [1, 1000, 70001])
+def test_blend_l1_loss_matches_the_torch_lines_it_replaces(n):
+    """vs_blend_l1_loss against volsurfs.py:708 + utils/losses.py:14-19 + autograd, written out in torch: the blend and the gradient sign
+    are the same roundings (bit-exact), the loss is an fp32 mean accumulated in another order (1e-6 relative)"""
+    from volsurfs_b200 import _lib
+    from volsurfs_b200.pipeline import ctypes_float3
+
+    g = torch.Generator().manual_seed(n)
+    rgb_fg = torch.rand(n, 3, generator=g).cuda()
+    bgT = torch.rand(n, 1, generator=g).cuda()
+    gt = torch.rand(n, 3, generator=g).cuda()
+    gt[0] = rgb_fg[0] + bgT[0] * torch.tensor([1.0, 0.5, 0.25]).cuda()   # exact zeros of the difference: sign(0) = 0
+    bg = torch.tensor([1.0, 0.5, 0.25])
+    pred_ref = (rgb_fg + bgT * bg.cuda().view(1, 3)).detach().requires_grad_(True)
+    loss_ref = (gt - pred_ref).abs().mean()
+    loss_ref.backward()
+    g_bgT_ref = (pred_ref.grad * bg.cuda().view(1, 3)).sum(dim=1, keepdim=True)
+    pred, g_pred = torch.empty_like(rgb_fg), torch.empty_like(rgb_fg)
+    g_bgT, loss = torch.empty_like(bgT), torch.full((), 7.0, device="cuda")
+    scratch = torch.zeros(2, dtype=torch.int64, device="cuda")
+    losses = []
+    for _ in range(3):   # the scratch cleans itself; the fixed-point mean is the same bits every time
+        _lib.check(_lib.lib().vs_blend_l1_loss(rgb_fg.data_ptr(), bgT.data_ptr(), gt.data_ptr(), ctypes_float3(bg), pred.data_ptr(),
+                                               g_pred.data_ptr(), g_bgT.data_ptr(), loss.data_ptr(), scratch.data_ptr(), n,
+                                               torch.cuda.current_stream().cuda_stream), "vs_blend_l1_loss")
+        torch.cuda.synchronize()
+        losses.append(float(loss))
+    assert losses[0] == losses[1] == losses[2] and int(scratch.abs().sum()) == 0
+    assert torch.equal(pred, pred_ref.detach())
+    assert torch.equal(g_pred, pred_ref.grad)
+    assert torch.allclose(g_bgT, g_bgT_ref, rtol=1e-6, atol=1e-12)
+    assert abs(float(loss) - float(loss_ref)) <= 2e-6 * abs(float(loss_ref)) + 1e-12

@@ -86,6 +86,7 @@ SIGNATURES = {
     "vs_occgrid_check_occupancy": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "vs_mlp_backward": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _I64, _P, c_int, _P]),
     "vs_baked_texture_shade": (c_int, [_P] * 7 + [c_int, c_int, c_int, _P] + [_P] * 6 + [_I64, _P]),
+    "vs_blend_l1_loss": (c_int, [_P] * 9 + [_I64, _P]),
 }
 
 _lib = None

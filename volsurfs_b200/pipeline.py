@@ -15,6 +15,13 @@ from .raytracer import ShellTracer
 from .volsurfs import VolumeRendering as VR
 
 
+def ctypes_float3(t):
+    """HOST float[3] for the entry points that take a background colour by value (built once: reading a device tensor synchronises)"""
+    import ctypes
+
+    return (ctypes.c_float * 3)(*[float(x) for x in t.detach().cpu().view(-1)[:3]])
+
+
 @contextlib.contextmanager
 def span(name: str):
     """NVTX range with the reference's profiler span names (mvdatasets/utils/profiler.py:4-103; spans ``meshes_raytracing``,
@@ -35,6 +42,9 @@ class ShellRenderer:
         self.alpha_head = alpha_head
         self.K = tracer.nr_meshes
         self.bg_color = torch.tensor(bg_color, dtype=torch.float32, device=tracer.device)  # white (config/data_config.cfg:22-26)
+        self._bg_host = ctypes_float3(torch.tensor(bg_color, dtype=torch.float32))
+        self._loss_scratch = None  # 16 bytes the fused loss kernel accumulates in (self-clearing)
+        self._zero_rows = None  # [N,1] zeros: the depth / accumulation outputs carry no gradient in a photometric loss
 
     # ---- stages ------------------------------------------------------------------------------------------------------
     def intersect_and_pack(self, rays_o, rays_d):
@@ -72,10 +82,39 @@ class ShellRenderer:
             pred = torch.addcmul(rgb_fg, bgT, self.bg_color.view(1, 3))
         return {"rgb": pred, "rgb_fg": rgb_fg, "depth": depth, "acc": acc, "bg_transmittance": bgT}
 
-    def composite_backward(self, rsp, alpha, rgb, g_pred):
+    def blend_l1(self, rgb_fg, bgT, gt_rgb):
+        """background blend + L1 loss + the loss gradient in one launch (``vs_blend_l1_loss``: volsurfs.py:708, utils/losses.py:14-19
+        and their autograd) -> (pred [N,3], loss 0-d, g_pred [N,3], g_bgT [N,1])"""
+        from . import _lib
+
+        with span("losses"):
+            n = int(rgb_fg.shape[0])
+            pred, g_pred = torch.empty_like(rgb_fg), torch.empty_like(rgb_fg)
+            g_bgT, loss = torch.empty_like(bgT), torch.empty((), dtype=torch.float32, device=rgb_fg.device)
+            if self._loss_scratch is None or self._loss_scratch.device != rgb_fg.device:
+                self._loss_scratch = torch.zeros(2, dtype=torch.int64, device=rgb_fg.device)
+            _lib.check(_lib.lib().vs_blend_l1_loss(rgb_fg.data_ptr(), bgT.data_ptr(), gt_rgb.contiguous().data_ptr(), self._bg_host,
+                                                   pred.data_ptr(), g_pred.data_ptr(), g_bgT.data_ptr(), loss.data_ptr(),
+                                                   self._loss_scratch.data_ptr(), n, torch.cuda.current_stream().cuda_stream),
+                       "vs_blend_l1_loss")
+        return pred, loss, g_pred, g_bgT
+
+    def composite_l1(self, rsp, alpha, rgb, gt_rgb):
+        """stage 4 forward of a TRAINING step: compositing, then ``blend_l1``.  Returns the dict of ``composite`` plus ``loss``,
+        ``g_pred`` and ``g_bgT`` for ``composite_backward(..., g_bgT=...)``."""
+        with span("render_fg"):
+            rgb_fg, depth, acc, bgT = VR.composite(rsp, alpha, rgb, rsp.samples_z)
+        pred, loss, g_pred, g_bgT = self.blend_l1(rgb_fg, bgT, gt_rgb)
+        return {"rgb": pred, "rgb_fg": rgb_fg, "depth": depth, "acc": acc, "bg_transmittance": bgT, "loss": loss, "g_pred": g_pred,
+                "g_bgT": g_bgT}
+
+    def composite_backward(self, rsp, alpha, rgb, g_pred, g_bgT=None):
         """stage 4 backward for a loss on the composited prediction: g_rgb_fg = g_pred, g_bgT = g_pred . bg"""
-        g_bgT = (g_pred * self.bg_color.view(1, 3)).sum(dim=1, keepdim=True)
-        zeros = torch.zeros_like(g_bgT)
+        if g_bgT is None:
+            g_bgT = (g_pred * self.bg_color.view(1, 3)).sum(dim=1, keepdim=True)
+        if self._zero_rows is None or self._zero_rows.shape != g_bgT.shape or self._zero_rows.device != g_bgT.device:
+            self._zero_rows = torch.zeros_like(g_bgT)
+        zeros = self._zero_rows
         d_alpha, d_rgb, _ = VR.composite_backward(rsp, alpha, rgb, rsp.samples_z, g_pred.contiguous(), zeros, zeros, g_bgT)
         return d_alpha, d_rgb
 
@@ -118,17 +157,15 @@ class ShellRenderer:
             if heads_backward:
                 rsp = self.intersect_and_pack(rays_o, rays_d)
                 rgb, alpha = self.shade_train(rsp, pos_features)
-                out = self.composite(rsp, alpha, rgb)
+                out = self.composite_l1(rsp, alpha, rgb, gt_rgb)
                 out.update(ray_samples_packed=rsp, samples_rgb=rgb, samples_alpha=alpha)
             else:
                 out = self.render(rays_o, rays_d, pos_features)
-            with span("losses"):
-                diff = out["rgb"] - gt_rgb
-                loss = diff.abs().mean()
-                g_pred = torch.sign(diff) / diff.numel()
+                out["rgb"], out["loss"], out["g_pred"], out["g_bgT"] = self.blend_l1(out["rgb_fg"], out["bg_transmittance"], gt_rgb)
+            loss, g_pred = out["loss"], out["g_pred"]
         with span("backward_pass"):
             rsp = out["ray_samples_packed"]
-            d_alpha, d_rgb = self.composite_backward(rsp, out["samples_alpha"], out["samples_rgb"], g_pred)
+            d_alpha, d_rgb = self.composite_backward(rsp, out["samples_alpha"], out["samples_rgb"], g_pred, out["g_bgT"])
             out.update(loss=loss, d_alpha=d_alpha, d_rgb=d_rgb)
             if heads_backward:
                 out.update(self.heads_backward(rsp, pos_features, d_rgb, d_alpha,
@@ -177,12 +214,9 @@ class EncodedShellRenderer(ShellRenderer):
             stashes[name] = stash
             outs[name], _ = head.forward_train(feats[name], rsp.samples_dirs, rsp.samples_normals, n_valid_dev=rsp.total_dev, stash=stash,
                                                out=self._buf("out_" + name, (cap, head.out_dim)))
-        comp = self.composite(rsp, outs["alpha"], outs["rgb"])
-        diff = comp["rgb"] - gt_rgb
-        loss = diff.abs().mean()
-        g_pred = torch.sign(diff) / diff.numel()
-        d_alpha, d_rgb = self.composite_backward(rsp, outs["alpha"], outs["rgb"], g_pred)
-        result = {"loss": loss, "rgb": comp["rgb"], "ray_samples_packed": rsp}
+        comp = self.composite_l1(rsp, outs["alpha"], outs["rgb"], gt_rgb)
+        d_alpha, d_rgb = self.composite_backward(rsp, outs["alpha"], outs["rgb"], comp["g_pred"], comp["g_bgT"])
+        result = {"loss": comp["loss"], "rgb": comp["rgb"], "ray_samples_packed": rsp}
         self._state = (rsp, feats, outs, stashes, {"rgb": d_rgb, "alpha": d_alpha})
         for name in (("rgb",) if rgb_branch_only else ("rgb", "alpha")):
             result.update(self.branch_backward(name))
