@@ -289,7 +289,8 @@ class PipelinedTrainingStep:
 
     def __init__(self, renderer: "ShellRenderer", o_pin, d_pin, pos_features, gt_rgb, img_pin, loss_pin, warmup: int = 2, step_fn=None):
         """``step_fn(rays_o, rays_d) -> dict`` (with "rgb" and "loss") replaces ``renderer.render_fwd_bwd(rays_o, rays_d, pos_features,
-        gt_rgb)`` when given: any capturable step (e.g. one with real encoders and an in-graph gradient exchange) can be pipelined"""
+        gt_rgb)`` when given: any capturable step (e.g. one with real encoders and an in-graph gradient exchange) can be pipelined.
+        ``img_pin = None``: only the loss comes back to the host every step (a training loop that does not look at the image)"""
         dev = gt_rgb.device
         if step_fn is None:
             step_fn = lambda o, d: renderer.render_fwd_bwd(o, d, pos_features, gt_rgb)  # noqa: E731
@@ -297,7 +298,7 @@ class PipelinedTrainingStep:
         self.o_pin, self.d_pin, self.img_pin, self.loss_pin = o_pin, d_pin, img_pin, loss_pin
         self.rays_o = [torch.empty(o_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
         self.rays_d = [torch.empty(d_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
-        self.img = [torch.empty(img_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.img = [torch.empty(img_pin.shape, dtype=torch.float32, device=dev) for _ in range(2)] if img_pin is not None else None
         self.loss = [torch.empty((), dtype=torch.float32, device=dev) for _ in range(2)]
         self.copy_in, self.copy_out = torch.cuda.Stream(), torch.cuda.Stream()
         for b in range(2):
@@ -320,10 +321,12 @@ class PipelinedTrainingStep:
                     self.rays_o[1 - b].copy_(o_pin, non_blocking=True)
                     self.rays_d[1 - b].copy_(d_pin, non_blocking=True)
                 with torch.cuda.stream(self.copy_out):
-                    img_pin.copy_(self.img[1 - b], non_blocking=True)
+                    if img_pin is not None:
+                        img_pin.copy_(self.img[1 - b], non_blocking=True)
                     loss_pin.copy_(self.loss[1 - b], non_blocking=True)
                 out = step_fn(self.rays_o[b], self.rays_d[b])
-                self.img[b].copy_(out["rgb"])
+                if img_pin is not None:
+                    self.img[b].copy_(out["rgb"])
                 self.loss[b].copy_(out["loss"])
                 main.wait_stream(self.copy_in)
                 main.wait_stream(self.copy_out)
@@ -340,7 +343,8 @@ class PipelinedTrainingStep:
 
     def drain(self, n_steps: int):
         b = (n_steps - 1) & 1
-        self.img_pin.copy_(self.img[b], non_blocking=True)
+        if self.img_pin is not None:
+            self.img_pin.copy_(self.img[b], non_blocking=True)
         self.loss_pin.copy_(self.loss[b], non_blocking=True)
 
 
