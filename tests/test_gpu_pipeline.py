@@ -196,4 +196,5 @@ def test_blend_l1_loss_matches_the_torch_lines_it_replaces(n):
     assert torch.equal(pred, pred_ref.detach())
     assert torch.equal(g_pred, pred_ref.grad)
     assert torch.allclose(g_bgT, g_bgT_ref, rtol=1e-6, atol=1e-12)
-    assert abs(float(loss) - float(loss_ref)) <= 2e-6 * abs(float(loss_ref)) + 1e-12
+    want = float(loss_ref.detach())
+    assert abs(float(loss) - want) <= 2e-6 * abs(want) + 1e-12
