@@ -507,16 +507,16 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
             }
     
         } else {
-        int stack_ref[kStack];
-            float stack_t[kStack];
+            // one 8-byte entry (node reference, entry distance): a push or a pop is ONE 64-bit local-memory access, not two 32-bit ones
+            int2 stack[kStack];
             int sp = 0;
-            stack_ref[sp] = 0;  // the root is wide node 0
-            stack_t[sp] = -FLT_MAX;
+            stack[sp] = make_int2(0, __float_as_int(-FLT_MAX));  // the root is wide node 0
             ++sp;
             while (sp > 0) {
                 --sp;
-                const int ref = stack_ref[sp];
-                if (stack_t[sp] > best_t) continue;
+                const int2 top = stack[sp];
+                const int ref = top.x;
+                if (__int_as_float(top.y) > best_t) continue;
                 if (ref < 0) {
                     const int enc = ~ref;
                     const int first = enc >> 3, cnt = (enc & 7) + 1;
@@ -575,8 +575,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                 for (int i = 0; i < 4; ++i) {
                     if (tn[i] != FLT_MAX) {
                         if (sp < kStack) {
-                            stack_ref[sp] = cr[i];
-                            stack_t[sp] = tn[i];
+                            stack[sp] = make_int2(cr[i], __float_as_int(tn[i]));
                             ++sp;
                         } else {
                             atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
