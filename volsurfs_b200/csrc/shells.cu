@@ -510,13 +510,21 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
             // one 8-byte entry (node reference, entry distance): a push or a pop is ONE 64-bit local-memory access, not two 32-bit ones
             int2 stack[kStack];
             int sp = 0;
-            stack[sp] = make_int2(0, __float_as_int(-FLT_MAX));  // the root is wide node 0
-            ++sp;
-            while (sp > 0) {
-                --sp;
-                const int2 top = stack[sp];
-                const int ref = top.x;
-                if (__int_as_float(top.y) > best_t) continue;
+            // the entry to work on lives in registers: the nearest child of a node is taken up directly, only its siblings go through
+            // the stack
+            int ref = 0;  // the root is wide node 0
+            float ref_t = -FLT_MAX;
+            bool have = true;
+            for (;;) {
+                if (!have) {
+                    if (sp == 0) break;
+                    --sp;
+                    const int2 top = stack[sp];
+                    ref = top.x;
+                    ref_t = __int_as_float(top.y);
+                }
+                have = false;
+                if (ref_t > best_t) continue;
                 if (ref < 0) {
                     const int enc = ~ref;
                     const int first = enc >> 3, cnt = (enc & 7) + 1;
@@ -572,7 +580,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                 cswap_desc(tn[2], cr[2], tn[3], cr[3]);
                 cswap_desc(tn[1], cr[1], tn[2], cr[2]);
     #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 3; ++i) {
                     if (tn[i] != FLT_MAX) {
                         if (sp < kStack) {
                             stack[sp] = make_int2(cr[i], __float_as_int(tn[i]));
@@ -581,6 +589,11 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                             atomicOr(overflow, 1);  // never expected (depth*3 << kStack); reported by vs_shells_overflowed
                         }
                     }
+                }
+                if (tn[3] != FLT_MAX) {  // (sorted far -> near: a node with any hit child has its nearest in slot 3)
+                    ref = cr[3];
+                    ref_t = tn[3];
+                    have = true;
                 }
             }
     
