@@ -12,8 +12,9 @@
 //     its next 32 consecutive rays from the layer's work counter, so a warp whose rays miss everything is not parked until the slowest
 //     warp of its CTA is done (B200, C2 scene: 0.695 ms with a static 512-rays-per-CTA mapping, achieved occupancy 33 % of a 50 %
 //     limit -> 0.616 ms); a warp whose layer has run dry moves on to the layers that still have work;
-//   * the top of the layer's tree (first kTopNodes nodes = 4 levels) is staged into shared memory by one TMA bulk copy
-//     (cp.async.bulk + mbarrier) when the CTA starts, so the always-visited upper levels never leave the SM;
+//   * nodes and triangles are read through L1 / L2.  (Rounds 1-2 staged the top four levels of the CTA's layer in shared memory by a TMA
+//     bulk copy: with persistent CTAs that copy is a one-off and the 87 KB of shared memory per SM it took are worth more as L1 —
+//     0.546 ms staged, 0.535 ms without, B200, C2 scene);
 //   * triangles are 3 x float4 (vertex + original face index), read with 16-byte loads.
 //
 // Parity contract (bit-exact hits, pinned by the reference's own kernel): the ray/triangle arithmetic is the reference's
@@ -44,7 +45,6 @@ constexpr int kTraceThreads = 128;
 constexpr int kTraceCtasPerSm = 8;   // 63 registers x 128 threads: 8 CTAs fit (measured: 4 -> 0.74 ms, 8 -> 0.616, 12 -> 0.646)
 constexpr int kTraceMaxLayers = 64;
 constexpr int kCounterSets = 8;      // work-counter sets handed out in turn, so that launches in flight on different streams do not share one
-constexpr int kTopNodes = 85;  // 1 + 4 + 16 + 64 nodes = first four levels of a full 4-ary tree (10.6 KB)
 constexpr int kStack = 48;
 constexpr int kLeafMax = 2;  // measured on the C2 scene (B200, persistent kernel): 1 -> 0.580 ms, 2 -> 0.569, 4 -> 0.593, 6 -> 0.607, 8 -> 0.640
 
@@ -369,25 +369,12 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                                                                      int32_t* __restrict__ tri_out, float* __restrict__ u_out,
                                                                      float* __restrict__ v_out, int* __restrict__ overflow, int layer_count,
                                                                      int* __restrict__ work_counter) {
-    __shared__ __align__(128) Node4 s_top[kTopNodes];
-    __shared__ __align__(8) uint64_t bar;
-    const Layer L0 = layers[layer_first + blockIdx.y];
-    const int n_top0 = min(L0.n_nodes, kTopNodes);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&bar, (uint32_t)(n_top0 * sizeof(Node4)));
-        bulk_g2s(s_top, L0.nodes, (uint32_t)(n_top0 * sizeof(Node4)), &bar);
-    }
-    __syncthreads();
-    mbar_wait(&bar, 0);
-    // the CTA's own layer first, its top levels in shared memory; a WARP whose layer has run dry moves on to the others by itself (their
-    // top levels then come through L1 like the rest of the tree): no block-wide hand-over, nobody waits for a neighbour's last chunk
+    // the CTA's own layer first; a WARP whose layer has run dry moves on to the others by itself: no block-wide hand-over, nobody waits
+    // for a neighbour's last chunk.  No shared memory: the whole tree comes through L1 (see the header comment)
     for (int a = 0; a < layer_count; ++a) {
     const int li = (int)((blockIdx.y + a) % layer_count);
     if (a > 0 && (int64_t)(*reinterpret_cast<volatile int*>(work_counter + li)) * 32 >= n_rays) continue;
     const Layer L = layers[layer_first + li];
-    const int n_top = a == 0 ? n_top0 : 0;
 
     const Node4* __restrict__ gnodes = L.nodes;
     const float4* __restrict__ pre = L.pre;
@@ -430,7 +417,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
             };
             while (alive) {
                 while (alive && ref >= 0) {
-                    const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
+                    const Node4* nd = &gnodes[ref];
                     const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
                     const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
                     const float4 hiy = *reinterpret_cast<const float4*>(nd->hiy), hiz = *reinterpret_cast<const float4*>(nd->hiz);
@@ -553,7 +540,7 @@ __global__ void __launch_bounds__(kTraceThreads) shells_trace_kernel(const Layer
                     }
                     continue;
                 }
-                const Node4* nd = ref < n_top ? &s_top[ref] : &gnodes[ref];
+                const Node4* nd = &gnodes[ref];
                 const float4 lox = *reinterpret_cast<const float4*>(nd->lox), loy = *reinterpret_cast<const float4*>(nd->loy);
                 const float4 loz = *reinterpret_cast<const float4*>(nd->loz), hix = *reinterpret_cast<const float4*>(nd->hix);
                 const float4 hiy = *reinterpret_cast<const float4*>(nd->hiy), hiz = *reinterpret_cast<const float4*>(nd->hiz);
@@ -743,7 +730,7 @@ int vs_shells_build(int K, const float* const* verts, const int64_t* n_verts, co
         Layer& L = S->layers[k];
         L.n_nodes = (int32_t)wide.size();
         L.n_tris = T;
-        if ((err = cudaMalloc(&L.nodes, sizeof(Node4) * std::max<size_t>(wide.size(), kTopNodes))) != cudaSuccess) break;
+        if ((err = cudaMalloc(&L.nodes, sizeof(Node4) * std::max<size_t>(wide.size(), 1))) != cudaSuccess) break;
         if ((err = cudaMalloc(&L.tris, sizeof(float4) * 3 * T)) != cudaSuccess) break;
         if ((err = cudaMalloc(&L.orig_to_bvh, sizeof(int32_t) * T)) != cudaSuccess) break;
         if ((err = cudaMemcpy(L.nodes, wide.data(), sizeof(Node4) * wide.size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
