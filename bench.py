@@ -44,7 +44,7 @@ CPU_SAMPLE_RAYS = 16384  # the reference's own render chunk (config/volsurfs/bas
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of this workload at HEAD (profiles/r02_*.md)
 NCU_TRAFFIC = {"mlp_fwd_kernel": 204.320000e6 + 693.690368e6,            # profiles/r02_mlp_fwd.md
                "mlp_bwd_stashed_kernel": 764.562432e6 + 169.221120e6,    # profiles/r02_mlp_bwd.md
-               "shells_trace_kernel": 47.417088e6 + 19.896832e6,         # profiles/r02_shells_trace.md
+               "shells_trace_kernel": 44.94848e6 + 19.424512e6,         # profiles/r02_shells_trace.md
                "permuto_fwd_kernel": 31.724800e6 + 133.739264e6,         # profiles/r02_permuto_fwd.md
                "permuto_bwd_kernel": 214.678784e6 + 8.321536e6,          # profiles/r02_permuto_bwd.md
                # composite_fwd_tile_kernel<1> + composite_bwd_tile_kernel<1> at 2^24 rays x 5 (algorithmic: 5.77 GB)
